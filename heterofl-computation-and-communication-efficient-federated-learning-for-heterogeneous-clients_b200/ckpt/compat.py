@@ -1,0 +1,70 @@
+"""Reference-compatible (de)serialisation.
+
+Checkpoints are ``torch.save(obj, path, pickle_protocol=2)`` dicts (reference ``src/utils.py:27-46``) that pickle a
+``logger.Logger`` instance and -- for language models -- a ``datasets.lm.Vocab`` inside ``cfg``.  Those module paths
+only exist when the reference's ``src/`` is the working directory, so :func:`compat_modules` installs tiny alias
+modules under those names *for the duration of a save/load* (and removes them again): files written here unpickle in
+the reference, and files written by the reference unpickle here.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+
+@contextlib.contextmanager
+def compat_modules():
+    from ..data.datasets import Vocab
+    from ..utils.logger import Logger
+    Vocab.__module__ = "datasets.lm"
+    installed = []
+
+    def _install(name, **attrs):
+        if name in sys.modules:
+            mod = sys.modules[name]
+            for k, v in attrs.items():
+                if not hasattr(mod, k):
+                    setattr(mod, k, v)
+            return
+        mod = types.ModuleType(name)
+        mod.__dict__.update(attrs)
+        sys.modules[name] = mod
+        installed.append(name)
+
+    _install("logger", Logger=Logger)
+    _install("datasets")
+    _install("datasets.lm", Vocab=Vocab)
+    if "datasets" in installed:
+        sys.modules["datasets"].lm = sys.modules["datasets.lm"]
+    try:
+        yield
+    finally:
+        for name in installed:
+            sys.modules.pop(name, None)
+
+
+def save(obj, path, protocol: int = 2, mode: str = "torch") -> None:
+    d = os.path.dirname(path)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    if mode == "torch":
+        with compat_modules():
+            torch.save(obj, path, pickle_protocol=protocol)
+    elif mode == "numpy":
+        np.save(path, obj, allow_pickle=True)
+    else:
+        raise ValueError("Not valid save mode")
+
+
+def load(path, mode: str = "torch"):
+    if mode == "torch":
+        with compat_modules():
+            return torch.load(path, map_location="cpu", weights_only=False)
+    if mode == "numpy":
+        return np.load(path, allow_pickle=True)
+    raise ValueError("Not valid save mode")

@@ -33,13 +33,13 @@ def label_mask_tensor(label_split_u: Sequence[int], n_rows: int) -> torch.Tensor
 
 class Federation:
     def __init__(self, cfg: Dict, spec: ModelSpec, global_arena: torch.Tensor, label_split,
-                 backend: str = "auto"):
+                 backend: str = "auto", channels_last: bool = False):
         self.cfg, self.spec = cfg, spec
         self.global_arena = global_arena
         self.label_split = label_split
         self.global_rate = float(cfg["global_model_rate"])
         levels = sorted(set(float(r) for r in cfg["model_rate"]) | {self.global_rate}, reverse=True)
-        self.tables: FedTables = build_tables(spec, self.global_rate, levels)
+        self.tables: FedTables = build_tables(spec, self.global_rate, levels, channels_last)
         assert self.tables.global_layout.size == global_arena.numel(), "global arena does not match layout"
         self.backend = backend
         self.label_rows = max([int(p.out.local(self.global_rate)) for p in spec.params if p.label_rows] + [1])
@@ -143,8 +143,7 @@ def combine_torch(tables: FedTables, global_arena: torch.Tensor, client_arenas: 
         cnt = torch.zeros(g.shape, dtype=torch.float32, device=dev)
         for arena, rate, lm in zip(client_arenas, rates, label_masks):
             lay = tables.level_layouts[tables.level_id(rate)]
-            e = lay.entries[p.name]
-            loc = arena[e.offset:e.offset + e.numel].view(e.shape).to(device=dev, dtype=torch.float32)
+            loc = lay.view(arena, p.name).to(device=dev, dtype=torch.float32)
             idx = _maps(tables, rate)[p.name]
             if p.inp is None:
                 oi = idx.to(dev)

@@ -33,8 +33,8 @@ class Entry:
 class Layout:
     """Offsets of every parameter of a model built at absolute width ``rate``."""
 
-    def __init__(self, spec: ModelSpec, rate: float):
-        self.spec, self.rate = spec, float(rate)
+    def __init__(self, spec: ModelSpec, rate: float, channels_last: bool = False):
+        self.spec, self.rate, self.channels_last = spec, float(rate), bool(channels_last)
         self.entries: "OrderedDict[str, Entry]" = OrderedDict()
         off = 0
         for p in spec.params:
@@ -45,15 +45,26 @@ class Layout:
         self.size = off                      # arena length in elements (padded)
         self.num_params = sum(e.numel for e in self.entries.values())
 
+    def view(self, arena: torch.Tensor, name: str) -> torch.Tensor:
+        """Zero-copy view of one parameter.  With ``channels_last`` (device arenas) 4-D conv filters are *stored*
+        K,R,S,C -- the GEMM-K axis (r,s,c) is contiguous, which is what NHWC implicit-GEMM kernels and cuDNN's NHWC
+        path consume without a per-step re-layout -- and returned as a logical ``[K, C, R, S]`` tensor with
+        channels-last strides.  Host arenas keep the plain K,C,R,S order."""
+        e = self.entries[name]
+        flat = arena[e.offset:e.offset + e.numel]
+        if len(e.shape) == 4 and self.channels_last:
+            K, C, R, S = e.shape
+            return flat.view(K, R, S, C).permute(0, 3, 1, 2)
+        return flat.view(e.shape)
+
     def views(self, arena: torch.Tensor) -> "OrderedDict[str, torch.Tensor]":
         """Zero-copy per-parameter views into a flat arena tensor."""
-        out = OrderedDict()
-        for e in self.entries.values():
-            out[e.name] = arena[e.offset:e.offset + e.numel].view(e.shape)
-        return out
+        return OrderedDict((name, self.view(arena, name)) for name in self.entries)
 
     def state_dict(self, arena: torch.Tensor) -> "OrderedDict[str, torch.Tensor]":
-        return OrderedDict((k, v.clone()) for k, v in self.views(arena).items())
+        """Reference-format state dict (contiguous ``[K, C, R, S]`` filters)."""
+        return OrderedDict((k, v.detach().clone(memory_format=torch.contiguous_format))
+                           for k, v in self.views(arena).items())
 
     def load_state_dict(self, arena: torch.Tensor, sd: Dict[str, torch.Tensor], strict: bool = True) -> None:
         v = self.views(arena)
@@ -93,7 +104,8 @@ def index_maps(spec: ModelSpec, rate: float, global_rate: float) -> "OrderedDict
 # ----------------------------------------------------------------------------------------------------------
 # kernel descriptor tables
 # ----------------------------------------------------------------------------------------------------------
-# One row per (tensor):   [g_off, R, C, inner, rH, cH, label_rows, _pad]
+# One row per (tensor):   [g_off, R, C, inner, rH, cH, label_rows, col_innermost]
+#   physical order of a tensor is [R, C, inner] (col_innermost=0) or [R, inner, C] (col_innermost=1, conv filters)
 # One row per (tensor, level): [l_off, r_loc, c_loc, r_dl, r_dg, c_dl, c_dg, _pad]
 #   local row i = h*r_dl + t  <->  global row h*r_dg + t   (rH heads; plain prefix: rH=1, r_dl=r_loc, r_dg=R)
 TENSOR_COLS = 8
@@ -128,17 +140,19 @@ class FedTables:
         raise KeyError(rate)
 
 
-def build_tables(spec: ModelSpec, global_rate: float, rates: Sequence[float]) -> FedTables:
+def build_tables(spec: ModelSpec, global_rate: float, rates: Sequence[float],
+                 channels_last: bool = False) -> FedTables:
     rates = sorted({float(r) for r in rates}, reverse=True)
-    gl = Layout(spec, global_rate)
-    lls = [Layout(spec, r) for r in rates]
+    gl = Layout(spec, global_rate, channels_last)
+    lls = [Layout(spec, r, channels_last) for r in rates]
     T = len(spec.params)
     tt = np.zeros((T, TENSOR_COLS), dtype=np.int64)
     lt = np.zeros((len(rates), T, LEVEL_COLS), dtype=np.int64)
     for t, p in enumerate(spec.params):
         R, _, rH, _, _ = _axis_desc(p.out, global_rate, global_rate)
         C, _, cH, _, _ = _axis_desc(p.inp, global_rate, global_rate)
-        tt[t] = [gl.entries[p.name].offset, R, C, p.inner, rH, cH, int(p.label_rows), 0]
+        tt[t] = [gl.entries[p.name].offset, R, C, p.inner, rH, cH, int(p.label_rows),
+                 int(len(p.tail) == 2 and channels_last)]
         for li, r in enumerate(rates):
             _, rl, _, rdl, rdg = _axis_desc(p.out, r, global_rate)
             _, cl, _, cdl, cdg = _axis_desc(p.inp, r, global_rate)
