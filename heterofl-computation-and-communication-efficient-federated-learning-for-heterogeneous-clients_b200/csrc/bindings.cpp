@@ -1,0 +1,206 @@
+// Python bindings (pybind11 / ATen) for the hfl_b200 sm_100a kernels and the peer-memory runtime.
+#include <torch/extension.h>
+#include <c10/cuda/CUDAStream.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+extern "C" {
+void hfl_aggregate(const void*, const void*, int, const void*, int, int, const void*, const void*, const void*, int,
+                   int, const void*, int, cudaStream_t);
+void hfl_distribute(const void*, const void*, int, const void*, const void*, int, const float*, const void*,
+                    const void*, const void*, const void*, int, cudaStream_t);
+void hfl_peer_sum(const void*, int, float*, int, cudaStream_t);
+int hfl_fed_chunk();
+int hfl_fed_max_clients();
+void hfl_sgd_clip_step(float*, void*, void*, int, float*, long, const float*, float, float, float, float*,
+                       cudaStream_t);
+void hfl_masked_ce(const void*, int, const long long*, const unsigned char*, int, int, void*, float*, float*, float,
+                   float*, double*, cudaStream_t);
+void hfl_augment(const unsigned char*, const long long*, const int*, const float*, const float*, int, int, int, int,
+                 int, void*, int, cudaStream_t);
+long hfl_launch_count();
+void hfl_launch_count_add(long);
+void hfl_peer_barrier(const void*, int, int, unsigned, int*, cudaStream_t);
+}
+
+#define CHECK_CUDA_T(x) TORCH_CHECK((x).is_cuda(), #x " must be a CUDA tensor")
+#define CHECK_CONTIG(x) TORCH_CHECK((x).is_contiguous(), #x " must be contiguous")
+#define CUDA_OK(e)                                                                        \
+  do {                                                                                    \
+    cudaError_t _e = (e);                                                                 \
+    TORCH_CHECK(_e == cudaSuccess, "CUDA error: ", cudaGetErrorString(_e), " at ", #e);   \
+  } while (0)
+
+static cudaStream_t cur_stream() { return c10::cuda::getCurrentCUDAStream().stream(); }
+static void check_launch() { CUDA_OK(cudaGetLastError()); }
+
+// ---- federation ------------------------------------------------------------------------------------------
+void aggregate(torch::Tensor tensor_tab, torch::Tensor level_tab, torch::Tensor block_tab, int64_t block_lo,
+               int64_t n_blocks, torch::Tensor client_ptr, torch::Tensor client_level, torch::Tensor client_mask,
+               torch::Tensor out_ptr) {
+  CHECK_CUDA_T(tensor_tab); CHECK_CUDA_T(level_tab); CHECK_CUDA_T(block_tab); CHECK_CUDA_T(client_ptr);
+  CHECK_CUDA_T(client_level); CHECK_CUDA_T(client_mask); CHECK_CUDA_T(out_ptr);
+  const int T = tensor_tab.size(0), M = client_ptr.size(0);
+  TORCH_CHECK(M <= hfl_fed_max_clients(), "too many clients for one aggregate launch");
+  TORCH_CHECK(client_mask.dim() == 2 && client_mask.size(0) == M && client_mask.is_contiguous());
+  c10::cuda::CUDAGuard guard(tensor_tab.device());
+  hfl_aggregate(tensor_tab.data_ptr(), level_tab.data_ptr(), T, block_tab.data_ptr(), (int)block_lo, (int)n_blocks,
+                client_ptr.data_ptr(), client_level.data_ptr(), client_mask.data_ptr(), (int)client_mask.size(1), M,
+                out_ptr.data_ptr(), (int)out_ptr.size(0), cur_stream());
+  check_launch();
+}
+
+void distribute(torch::Tensor tensor_tab, torch::Tensor level_tab, torch::Tensor lvl_block_tab,
+                torch::Tensor lvl_block_start, int64_t max_blocks, torch::Tensor global_w, torch::Tensor w_ptr,
+                c10::optional<torch::Tensor> wc_ptr, c10::optional<torch::Tensor> mom_ptr,
+                torch::Tensor client_level) {
+  CHECK_CUDA_T(global_w); CHECK_CONTIG(global_w);
+  TORCH_CHECK(global_w.scalar_type() == torch::kFloat32);
+  const int T = tensor_tab.size(0), M = w_ptr.size(0);
+  c10::cuda::CUDAGuard guard(global_w.device());
+  hfl_distribute(tensor_tab.data_ptr(), level_tab.data_ptr(), T, lvl_block_tab.data_ptr(),
+                 lvl_block_start.data_ptr(), (int)max_blocks, global_w.data_ptr<float>(), w_ptr.data_ptr(),
+                 wc_ptr.has_value() ? wc_ptr->data_ptr() : nullptr,
+                 mom_ptr.has_value() ? mom_ptr->data_ptr() : nullptr, client_level.data_ptr(), M, cur_stream());
+  check_launch();
+}
+
+void peer_sum(torch::Tensor src_ptr, torch::Tensor dst) {
+  CHECK_CUDA_T(dst); CHECK_CONTIG(dst);
+  TORCH_CHECK(dst.scalar_type() == torch::kFloat32);
+  c10::cuda::CUDAGuard guard(dst.device());
+  hfl_peer_sum(src_ptr.data_ptr(), (int)src_ptr.size(0), dst.data_ptr<float>(), (int)dst.numel(), cur_stream());
+  check_launch();
+}
+
+// ---- optimiser -------------------------------------------------------------------------------------------
+void sgd_clip_step(torch::Tensor w, c10::optional<torch::Tensor> wc, torch::Tensor g, torch::Tensor mom,
+                   torch::Tensor lr, double mu, double wd, double max_norm, torch::Tensor scratch) {
+  CHECK_CUDA_T(w); CHECK_CONTIG(w); CHECK_CONTIG(g); CHECK_CONTIG(mom);
+  TORCH_CHECK(w.scalar_type() == torch::kFloat32 && mom.scalar_type() == torch::kFloat32);
+  TORCH_CHECK(w.numel() % 8 == 0 && g.numel() == w.numel() && mom.numel() == w.numel());
+  TORCH_CHECK(lr.is_cuda() && lr.scalar_type() == torch::kFloat32 && scratch.numel() >= 4);
+  const bool gb = g.scalar_type() == torch::kBFloat16;
+  TORCH_CHECK(gb || g.scalar_type() == torch::kFloat32);
+  void* wcp = nullptr;
+  if (wc.has_value()) { TORCH_CHECK(wc->scalar_type() == torch::kBFloat16 && wc->numel() == w.numel()); wcp = wc->data_ptr(); }
+  c10::cuda::CUDAGuard guard(w.device());
+  hfl_sgd_clip_step(w.data_ptr<float>(), wcp, g.data_ptr(), gb ? 1 : 0, mom.data_ptr<float>(), (long)w.numel(),
+                    lr.data_ptr<float>(), (float)mu, (float)wd, (float)max_norm, scratch.data_ptr<float>(),
+                    cur_stream());
+  check_launch();
+}
+
+// ---- loss ------------------------------------------------------------------------------------------------
+// returns (loss[1] fp32, dlogits like logits)
+std::vector<torch::Tensor> masked_ce(torch::Tensor logits, torch::Tensor target, c10::optional<torch::Tensor> mask,
+                                     double n_weight, c10::optional<torch::Tensor> meter, bool need_grad) {
+  CHECK_CUDA_T(logits); CHECK_CONTIG(logits); CHECK_CONTIG(target);
+  TORCH_CHECK(logits.dim() == 2 && target.scalar_type() == torch::kInt64 && target.numel() == logits.size(0));
+  const bool bf = logits.scalar_type() == torch::kBFloat16;
+  TORCH_CHECK(bf || logits.scalar_type() == torch::kFloat32);
+  const int rows = logits.size(0), V = logits.size(1);
+  const unsigned char* mp = nullptr;
+  if (mask.has_value()) {
+    TORCH_CHECK(mask->is_cuda() && mask->scalar_type() == torch::kUInt8 && mask->numel() >= V);
+    mp = mask->data_ptr<unsigned char>();
+  }
+  double* mt = nullptr;
+  if (meter.has_value()) { TORCH_CHECK(meter->scalar_type() == torch::kFloat64 && meter->numel() >= 4); mt = meter->data_ptr<double>(); }
+  c10::cuda::CUDAGuard guard(logits.device());
+  auto fopt = torch::TensorOptions().dtype(torch::kFloat32).device(logits.device());
+  auto loss = torch::empty({1}, fopt);
+  auto rows_buf = torch::empty({2, rows}, fopt);
+  torch::Tensor dl = need_grad ? torch::empty_like(logits) : torch::Tensor();
+  hfl_masked_ce(logits.data_ptr(), bf ? 1 : 0, (const long long*)target.data_ptr<int64_t>(), mp, rows, V,
+                need_grad ? dl.data_ptr() : nullptr, rows_buf.data_ptr<float>(), rows_buf.data_ptr<float>() + rows,
+                (float)n_weight, loss.data_ptr<float>(), mt, cur_stream());
+  check_launch();
+  return {loss, dl};
+}
+
+// ---- data ------------------------------------------------------------------------------------------------
+torch::Tensor augment(torch::Tensor src, c10::optional<torch::Tensor> idx, c10::optional<torch::Tensor> params,
+                      torch::Tensor mean, torch::Tensor inv_std, int64_t pad, bool out_bf16) {
+  CHECK_CUDA_T(src); CHECK_CONTIG(src);
+  TORCH_CHECK(src.scalar_type() == torch::kUInt8 && src.dim() == 4);
+  const int H = src.size(1), W = src.size(2), C = src.size(3);
+  const int B = idx.has_value() ? idx->numel() : src.size(0);
+  if (idx.has_value()) TORCH_CHECK(idx->is_cuda() && idx->scalar_type() == torch::kInt64 && idx->is_contiguous());
+  if (params.has_value()) TORCH_CHECK(params->is_cuda() && params->scalar_type() == torch::kInt32 && params->is_contiguous() && params->numel() >= 3 * B);
+  TORCH_CHECK(mean.numel() == C && inv_std.numel() == C && mean.scalar_type() == torch::kFloat32);
+  c10::cuda::CUDAGuard guard(src.device());
+  auto out = torch::empty({B, C, H, W}, torch::TensorOptions().dtype(out_bf16 ? torch::kBFloat16 : torch::kFloat32)
+                                           .device(src.device()).memory_format(torch::MemoryFormat::ChannelsLast));
+  hfl_augment(src.data_ptr<unsigned char>(), idx.has_value() ? (const long long*)idx->data_ptr<int64_t>() : nullptr,
+              params.has_value() ? params->data_ptr<int>() : nullptr, mean.data_ptr<float>(),
+              inv_std.data_ptr<float>(), B, H, W, C, (int)pad, out.data_ptr(), out_bf16 ? 1 : 0, cur_stream());
+  check_launch();
+  return out;
+}
+
+// ---- peer memory runtime (cudaMalloc + CUDA IPC) ---------------------------------------------------------
+int64_t peer_alloc(int64_t bytes) {
+  void* p = nullptr;
+  CUDA_OK(cudaMalloc(&p, (size_t)bytes));
+  CUDA_OK(cudaMemset(p, 0, (size_t)bytes));
+  return (int64_t)p;
+}
+void peer_free(int64_t ptr) { CUDA_OK(cudaFree((void*)ptr)); }
+py::bytes ipc_get_handle(int64_t ptr) {
+  cudaIpcMemHandle_t h;
+  CUDA_OK(cudaIpcGetMemHandle(&h, (void*)ptr));
+  return py::bytes(reinterpret_cast<const char*>(&h), sizeof(h));
+}
+int64_t ipc_open_handle(const std::string& handle) {
+  TORCH_CHECK(handle.size() == sizeof(cudaIpcMemHandle_t), "bad IPC handle size");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle.data(), sizeof(h));
+  void* p = nullptr;
+  CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  return (int64_t)p;
+}
+void ipc_close_handle(int64_t ptr) { CUDA_OK(cudaIpcCloseMemHandle((void*)ptr)); }
+
+torch::Tensor tensor_from_ptr(int64_t ptr, int64_t numel, const std::string& dtype, int64_t device) {
+  torch::ScalarType st = torch::kFloat32;
+  if (dtype == "float32") st = torch::kFloat32;
+  else if (dtype == "bfloat16") st = torch::kBFloat16;
+  else if (dtype == "uint8") st = torch::kUInt8;
+  else if (dtype == "int32") st = torch::kInt32;
+  else if (dtype == "int64") st = torch::kInt64;
+  else if (dtype == "float64") st = torch::kFloat64;
+  else TORCH_CHECK(false, "unsupported dtype ", dtype);
+  return torch::from_blob((void*)ptr, {numel}, torch::TensorOptions().dtype(st).device(torch::kCUDA, (int)device));
+}
+
+void peer_barrier(torch::Tensor flag_ptrs, int64_t rank, int64_t world, int64_t epoch, torch::Tensor err) {
+  CHECK_CUDA_T(flag_ptrs);
+  c10::cuda::CUDAGuard guard(flag_ptrs.device());
+  hfl_peer_barrier(flag_ptrs.data_ptr(), (int)rank, (int)world, (unsigned)epoch, err.data_ptr<int>(), cur_stream());
+  check_launch();
+}
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("aggregate", &aggregate);
+  m.def("distribute", &distribute);
+  m.def("peer_sum", &peer_sum);
+  m.def("fed_chunk", &hfl_fed_chunk);
+  m.def("fed_max_clients", &hfl_fed_max_clients);
+  m.def("sgd_clip_step", &sgd_clip_step);
+  m.def("masked_ce", &masked_ce);
+  m.def("augment", &augment);
+  m.def("launch_count", &hfl_launch_count);
+  m.def("launch_count_add", &hfl_launch_count_add);
+  m.def("peer_alloc", &peer_alloc);
+  m.def("peer_free", &peer_free);
+  m.def("ipc_get_handle", &ipc_get_handle);
+  m.def("ipc_open_handle", &ipc_open_handle);
+  m.def("ipc_close_handle", &ipc_close_handle);
+  m.def("tensor_from_ptr", &tensor_from_ptr);
+  m.def("peer_barrier", &peer_barrier);
+}

@@ -1,0 +1,116 @@
+// Fused clip_grad_norm_(.,max_norm) + SGD(momentum, weight_decay) over a client's FLAT parameter arena.
+//
+// Reference per step (src/train_classifier_fed.py:202-206): zero_grad, backward, clip_grad_norm_ (one norm kernel per
+// tensor + stack + norm + per-tensor scale), SGD.step (foreach over 56-74 tensors).  Here: 2 launches total.
+//   pass 1: ||g||^2 (block partials -> one atomicAdd each)
+//   pass 2: coef = min(1, max_norm/(||g||+1e-6));  g' = coef*g + wd*w;  m = mu*m + g';  w -= lr*m;
+//           also refreshes the bf16 compute copy of w and zeroes g for the next backward.
+#include "common.cuh"
+
+namespace hfl {
+
+template <typename G> struct GradVec;
+template <> struct GradVec<float> {
+  static __device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void zero4(float* p) { *reinterpret_cast<float4*>(p) = make_float4(0, 0, 0, 0); }
+};
+template <> struct GradVec<__nv_bfloat16> {
+  static __device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ void zero4(__nv_bfloat16* p) { *reinterpret_cast<uint2*>(p) = make_uint2(0, 0); }
+};
+
+template <typename G>
+__global__ void __launch_bounds__(256) grad_norm_sq_kernel(const G* __restrict__ g, int n4, float* __restrict__ scratch) {
+  __shared__ float sm[33];
+  float acc = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    float v[4];
+    GradVec<G>::load4(g + 4 * (size_t)i, v);
+    acc += v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+  }
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) atomicAdd(scratch, acc);
+}
+
+template <typename G>
+__global__ void __launch_bounds__(256)
+sgd_update_kernel(float* __restrict__ w, __nv_bfloat16* __restrict__ wc, G* __restrict__ g, float* __restrict__ mom,
+                  int n4, const float* __restrict__ lr_p, float mu, float wd, float max_norm,
+                  float* __restrict__ scratch /* [0]=norm^2, [1]=done-block counter (as uint) */) {
+  const float total = sqrtf(*reinterpret_cast<volatile float*>(scratch));
+  const float coef = fminf(1.f, max_norm / (total + 1e-6f));
+  const float lr = *lr_p;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const size_t o = 4 * (size_t)i;
+    float gv[4];
+    GradVec<G>::load4(g + o, gv);
+    float4 wv = *reinterpret_cast<const float4*>(w + o);
+    float4 mv = *reinterpret_cast<const float4*>(mom + o);
+    float* wp = reinterpret_cast<float*>(&wv);
+    float* mp = reinterpret_cast<float*>(&mv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gg = gv[k] * coef + wd * wp[k];
+      mp[k] = mu * mp[k] + gg;
+      wp[k] -= lr * mp[k];
+    }
+    *reinterpret_cast<float4*>(w + o) = wv;
+    *reinterpret_cast<float4*>(mom + o) = mv;
+    if (wc) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(wp[0], wp[1]);
+      __nv_bfloat162 b = __floats2bfloat162_rn(wp[2], wp[3]);
+      uint2 t;
+      t.x = *reinterpret_cast<unsigned*>(&a);
+      t.y = *reinterpret_cast<unsigned*>(&b);
+      *reinterpret_cast<uint2*>(wc + o) = t;
+    }
+    GradVec<G>::zero4(g + o);
+  }
+  // the last block to finish re-arms the scratch for the next step (every block has read scratch[0] by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned* cnt = reinterpret_cast<unsigned*>(scratch + 1);
+    const unsigned done = atomicAdd(cnt, 1u);
+    if (done == gridDim.x - 1) {
+      scratch[0] = 0.f;
+      *cnt = 0u;
+      scratch[2] = total;  // last observed grad norm (diagnostics)
+    }
+  }
+}
+
+}  // namespace hfl
+
+using namespace hfl;
+
+static int grid_for(int n4) {
+  int b = (n4 + 255) / 256;
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  return b;
+}
+
+extern "C" void hfl_sgd_clip_step(float* w, void* wc, void* g, int g_is_bf16, float* mom, long n,
+                                  const float* lr, float mu, float wd, float max_norm, float* scratch,
+                                  cudaStream_t stream) {
+  const int n4 = (int)(n / 4);
+  const int grid = grid_for(n4);
+  if (g_is_bf16) {
+    grad_norm_sq_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)g, n4, scratch);
+    sgd_update_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w, (__nv_bfloat16*)wc, (__nv_bfloat16*)g, mom, n4, lr,
+                                                              mu, wd, max_norm, scratch);
+  } else {
+    grad_norm_sq_kernel<float><<<grid, 256, 0, stream>>>((const float*)g, n4, scratch);
+    sgd_update_kernel<float><<<grid, 256, 0, stream>>>(w, (__nv_bfloat16*)wc, (float*)g, mom, n4, lr, mu, wd,
+                                                      max_norm, scratch);
+  }
+  count_launch(2);
+}

@@ -35,13 +35,16 @@ class VisionAugment:
         r[:, 2] = torch.randint(0, 2, (n,), generator=generator)
         return r.to(self.device)
 
-    def __call__(self, img_u8: torch.Tensor, params: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """``img_u8 [B, H, W, C]`` uint8 -> ``[B, C, H, W]`` (channels-last strides on GPU) normalised."""
-        if img_u8.is_cuda:
+    def __call__(self, src_u8: torch.Tensor, idx: Optional[torch.Tensor] = None,
+                 params: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Gather ``src_u8[idx]`` (``[n, H, W, C]`` uint8; all of it when ``idx`` is None), augment with
+        ``params [B, 3]`` and return ``[B, C, H, W]`` (channels-last strides on GPU) normalised."""
+        if src_u8.is_cuda:
             from ..ops import cuda as cu
             if cu.available():
-                return cu.augment_batch(img_u8, params if self.augment else None, self.mean, self.inv_std,
+                return cu.augment_batch(src_u8, idx, params if self.augment else None, self.mean, self.inv_std,
                                         self.pad, self.dtype)
+        img_u8 = src_u8 if idx is None else src_u8[idx]
         B, H, W, C = img_u8.shape
         x = img_u8
         if self.augment and params is not None:

@@ -1,0 +1,499 @@
+"""The federated training engine: one process per GPU, a round's active clients sharded over ranks.
+
+Round = (reference ``src/train_classifier_fed.py:74-94`` / ``train`` :99-124 / ``stats`` :127-138 / ``test`` :141-169)
+
+1. sample active users (``randperm``) and -- in ``dynamic`` mode -- re-draw every user's rate (``multinomial``);
+   same RNG calls in the same order as the reference, executed identically on every rank (nothing is broadcast);
+2. deal the active clients to ranks (LPT on a per-level cost model) and, per rank, to resident :class:`TrainSlot`
+   contexts; ONE distribute launch slices ``W_g`` into all of the rank's starting slots;
+3. local training: each slot replays its captured train-step graph on its own stream, slots interleaved;
+4. heterogeneous FedAvg: one fused launch; with several ranks the kernel pulls the client arenas of every peer over
+   NVLink and publishes the new ``W_g`` shard into every replica (``parallel/peer.py``); the NCCL/gloo path
+   (all-reduce of padded sum/count buffers) is kept as the A/B baseline and CPU plumbing;
+5. sBN statistics pass + Local/Global test, sharded over ranks;
+6. logger / LR schedule / checkpoint in the reference's formats (rank 0).
+"""
+from __future__ import annotations
+
+import copy
+import os
+import shutil
+import time
+from collections import deque
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from ..ckpt import compat as ckpt
+from ..config.control import make_cfg, model_tag
+from ..data.datasets import LMData, VisionData, fetch_dataset, process_dataset
+from ..data.pipeline import VisionAugment
+from ..data.split import split_dataset
+from ..models import Model
+from ..ops import cuda as cu
+from ..parallel.dist import DistInfo, all_reduce_sum, barrier
+from ..parallel.schedule import assign_clients, client_cost
+from ..plan.spec import build_spec
+from ..utils.logger import Logger
+from ..utils.optim import make_scheduler_state
+from .evaluator import Evaluator
+from .federation import Federation, combine_torch, label_mask_tensor
+from .trainer import TrainSlot
+
+
+@dataclass
+class EngineOptions:
+    compute_dtype: str = "auto"          # auto: bf16 on CUDA, fp32 on CPU
+    use_graph: Optional[bool] = None     # auto: CUDA graphs on GPU
+    max_concurrent: int = 16             # resident client slots training concurrently per GPU
+    data_on_device: bool = True          # False: dataset stays in pinned host memory, shards are copied every round
+    agg_backend: str = "auto"            # auto | p2p | allreduce
+    eval_every: int = 1
+    out_dir: str = "./output"
+    tensorboard: bool = False
+    quiet: bool = False
+    save: bool = True
+    stats_chunk_groups: int = 256
+    test_chunk: int = 2500
+
+
+class PhaseTimer:
+    """CUDA-event (or wall-clock on CPU) phase timing; ``result()`` synchronises once."""
+
+    def __init__(self, device):
+        self.cuda = torch.device(device).type == "cuda"
+        self.device = device
+        self.marks: List = []
+
+    def mark(self, name: str) -> None:
+        if self.cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(self.device))
+            self.marks.append((name, ev))
+        else:
+            self.marks.append((name, time.perf_counter()))
+
+    def result(self) -> Dict[str, float]:
+        out = {}
+        if self.cuda and self.marks:
+            self.marks[-1][1].synchronize()
+        for (n0, e0), (n1, e1) in zip(self.marks[:-1], self.marks[1:]):
+            ms = e0.elapsed_time(e1) if self.cuda else (e1 - e0) * 1e3
+            out[n1] = out.get(n1, 0.0) + ms
+        return out
+
+
+class Engine:
+    def __init__(self, cfg: Dict, info: Optional[DistInfo] = None, dataset: Optional[Dict] = None,
+                 options: Optional[EngineOptions] = None, seed: Optional[int] = None):
+        self.cfg = cfg
+        self.info = info if info is not None else DistInfo()
+        self.opt = options if options is not None else EngineOptions()
+        self.device = self.info.device
+        self.is_cuda = self.device.type == "cuda"
+        self.seed = int(cfg.get("init_seed", 0) if seed is None else seed)
+        cfg["model_tag"] = model_tag(cfg, self.seed)
+        torch.manual_seed(self.seed)
+        if self.is_cuda:
+            torch.cuda.manual_seed(self.seed)
+        self.dtype = {"auto": torch.bfloat16 if self.is_cuda else torch.float32, "bf16": torch.bfloat16,
+                      "fp32": torch.float32}[self.opt.compute_dtype]
+        self.use_graph = self.is_cuda if self.opt.use_graph is None else bool(self.opt.use_graph and self.is_cuda)
+        # ---- data ----
+        self.dataset = dataset if dataset is not None else fetch_dataset(cfg)
+        process_dataset(cfg, self.dataset)
+        self.is_lm = isinstance(self.dataset["train"], LMData)
+        # ---- model ----
+        self.spec = build_spec(cfg)
+        if not self.spec.federable:
+            raise ValueError("Not valid k")  # Bottleneck ResNets cannot be sliced (reference src/fed.py:89)
+        self.channels_last = self.is_cuda
+        self.host_model = Model(self.spec, cfg, cfg["global_model_rate"], False)
+        self.global_model = Model(self.spec, cfg, cfg["global_model_rate"], self.channels_last)
+        host_arena = self.host_model.new_arena()                       # consumes the global RNG like a model init
+        self.global_arena = self.host_model.convert_arena(host_arena, self.global_model).to(self.device)
+        # ---- bookkeeping ----
+        self.epoch = 1
+        self.logger = Logger(os.path.join(self.opt.out_dir, "runs", "train_%s" % cfg["model_tag"]),
+                             tensorboard=self.opt.tensorboard)
+        self.sched = make_scheduler_state(cfg, len(self.spec.params))
+        self.data_split = None
+        self.label_split = None
+        self.running: Dict = {}
+        self.timings: Dict[str, float] = {}
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self._slots: Dict[int, List[TrainSlot]] = {}
+        self._models: Dict[float, Model] = {}
+        self._peer = None
+        self._setup_done = False
+
+    # ------------------------------------------------------------------------------------------------------
+    def setup(self, resume_mode: Optional[int] = None) -> None:
+        cfg = self.cfg
+        mode = cfg.get("resume_mode", 0) if resume_mode is None else resume_mode
+        if mode in (1, 2):
+            self._resume(mode)
+        if self.data_split is None:
+            self.data_split, self.label_split = split_dataset(self.dataset, cfg["num_users"], cfg["data_split_mode"],
+                                                              cfg.get("classes_size", 0))
+        self.federation = Federation(cfg, self.spec, self.global_arena, self.label_split,
+                                     channels_last=self.channels_last)
+        self.tables = self.federation.tables
+        self.evaluator = Evaluator(self.global_model, cfg, self.info, self.dtype, self.opt.stats_chunk_groups,
+                                   self.opt.test_chunk)
+        self._stage_data()
+        self._agg_backend = self._pick_agg_backend()
+        self._setup_done = True
+
+    def _pick_agg_backend(self) -> str:
+        b = self.opt.agg_backend
+        if self.info.world == 1:
+            return "local"
+        if b == "auto":
+            b = "p2p" if self.is_cuda else "allreduce"
+        if b == "p2p":
+            from ..parallel.peer import PeerPool
+            need = self._round_arena_bytes()
+            self._peer = PeerPool(self.info, need)
+            # the global arena moves into the peer pool so that peers can publish W_g shards into it
+            ga = self._peer.alloc_persistent(self.global_arena.numel(), torch.float32)
+            ga.copy_(self.global_arena)
+            self.global_arena = ga
+            self.federation.global_arena = ga
+            self._peer.exchange()
+        return b
+
+    def _round_arena_bytes(self) -> int:
+        n_act = int(np.ceil(self.cfg["frac"] * self.cfg["num_users"]))
+        biggest = self.tables.level_layouts[0].size
+        return (n_act * biggest + self.global_arena.numel()) * 4 + (1 << 20)
+
+    # -- data staging --------------------------------------------------------------------------------------
+    def _stage_data(self) -> None:
+        tr, te = self.dataset["train"], self.dataset["test"]
+        dev = self.device
+        on_dev = self.opt.data_on_device or not self.is_cuda
+        if self.is_lm:
+            self.train_rows = tr.token.to(dev) if on_dev else tr.token.pin_memory()
+            self.test_rows = te.token.to(dev) if on_dev else te.token.pin_memory()
+            return
+        pin = (lambda t: t.pin_memory()) if self.is_cuda else (lambda t: t)
+        self.train_img = tr.img.to(dev) if on_dev else pin(tr.img)
+        self.train_lab = tr.target.to(dev) if on_dev else pin(tr.target)
+        self.test_img = te.img.to(dev) if on_dev else pin(te.img)
+        self.test_lab = te.target.to(dev) if on_dev else pin(te.target)
+        self.aug_train = VisionAugment(tr, True, dev, self.dtype)
+        U, C = self.cfg["num_users"], self.cfg["classes_size"]
+        owner = torch.full((len(te),), -1, dtype=torch.int64)
+        for u in range(U):
+            owner[torch.as_tensor(self.data_split["test"][u], dtype=torch.long)] = u
+        masks = torch.zeros(U, C, dtype=torch.uint8)
+        for u in range(U):
+            masks[u, torch.as_tensor(list(self.label_split[u]), dtype=torch.long)] = 1
+        self.test_owner = owner.to(dev)
+        self.user_masks = masks.to(dev)
+
+    def _h2d(self, t: torch.Tensor) -> torch.Tensor:
+        if t.device == self.device:
+            return t
+        self.h2d_bytes += t.numel() * t.element_size()
+        return t.to(self.device, non_blocking=True)
+
+    # -- slots ---------------------------------------------------------------------------------------------
+    def _model_for(self, rate: float) -> Model:
+        if rate not in self._models:
+            self._models[rate] = Model(self.spec, self.cfg, rate, self.channels_last)
+        return self._models[rate]
+
+    def _acquire_slot(self, level: int, busy: set) -> TrainSlot:
+        pool = self._slots.setdefault(level, [])
+        for s in pool:
+            if id(s) not in busy:
+                return s
+        rate = self.tables.rates[level]
+        s = TrainSlot(self._model_for(rate), self.cfg, self.device, self.dtype, self.use_graph)
+        pool.append(s)
+        return s
+
+    # ------------------------------------------------------------------------------------------------------
+    def current_lr(self) -> float:
+        return float(self.sched.lr)
+
+    def run_round(self, epoch: Optional[int] = None, evaluate: Optional[bool] = None) -> Dict:
+        """One communication round; returns metrics + phase timings (ms)."""
+        if not self._setup_done:
+            self.setup()
+        cfg, fed, info = self.cfg, self.federation, self.info
+        epoch = self.epoch if epoch is None else epoch
+        evaluate = (epoch % max(self.opt.eval_every, 1) == 0) if evaluate is None else evaluate
+        timer = PhaseTimer(self.device)
+        timer.mark("start")
+        lr = self.current_lr()
+        # 1. sampling (same RNG order as the reference: randperm, then multinomial inside distribute)
+        user_idx = fed.sample_users()
+        fed.make_model_rate()
+        rates = [float(fed.model_rate[u]) for u in user_idx]
+        levels = [self.tables.level_id(r) for r in rates]
+        M = len(user_idx)
+        # 2. schedule
+        steps = [self._client_steps(u) for u in user_idx]
+        costs = [client_cost(r, s) for r, s in zip(rates, steps)]
+        self._assignment = assign_clients(costs, info.world)
+        mine = self._assignment[info.rank]
+        # 3. local training (per-client RNG streams keyed by (seed, round, user): results do not depend on the
+        #    number of ranks or on which rank trains a client)
+        results = self._train_clients(user_idx, rates, levels, mine, lr, epoch)
+        timer.mark("train")
+        # 4. aggregation
+        self._aggregate(user_idx, levels, mine, results)
+        timer.mark("aggregate")
+        # train metrics (sums over my clients -> all ranks)
+        tm = torch.zeros(4, dtype=torch.float64, device=self.device)
+        for r in results.values():
+            tm += r["meter"]
+        all_reduce_sum(info, tm)
+        out: Dict = {"epoch": epoch, "lr": lr, "num_active": M, "user_idx": user_idx, "rates": rates}
+        # 5. evaluation
+        if evaluate:
+            shared = torch.Generator().manual_seed(self.seed * 1000003 + epoch * 7919 + 104729)
+            if self.is_lm:
+                test = self.evaluator.test_lm(self.global_arena, self._h2d(self.test_rows))
+                timer.mark("test")
+            else:
+                tr_img = self._h2d(self.train_img)
+                self.running = self.evaluator.sbn_stats(self.global_arena, self.dataset["train"], tr_img, shared)
+                timer.mark("sbn")
+                test = self.evaluator.test_vision(self.global_arena, self.running, self.dataset["test"],
+                                                  self._h2d(self.test_img), self._h2d(self.test_lab),
+                                                  self.test_owner, self.user_masks)
+                timer.mark("test")
+            out["test"] = {k: v for k, v in test.items() if not k.startswith("_")}
+            out["_test_n"] = {k: v for k, v in test.items() if k.startswith("_")}
+        t = tm.tolist()                                       # device -> host read of the round's result
+        self.d2h_bytes += 32
+        n = max(t[2], 1.0)
+        train = {"Local-Loss": t[0] / n}
+        if self.is_lm:
+            train["Local-Perplexity"] = t[3] / n
+        else:
+            train["Local-Accuracy"] = 100.0 * t[1] / n
+        out["train"], out["train_n"] = train, t[2]
+        out["timings_ms"] = timer.result()
+        return out
+
+    def _client_steps(self, u: int) -> int:
+        cfg = self.cfg
+        if self.is_lm:
+            T = self.dataset["train"].token.shape[1]
+            return cfg["num_epochs"]["local"] * int(np.ceil(T / cfg["bptt"]))
+        n = len(self.data_split["train"][u])
+        return cfg["num_epochs"]["local"] * int(np.ceil(n / cfg["batch_size"]["train"]))
+
+    # -- local training ------------------------------------------------------------------------------------
+    def _train_clients(self, user_idx, rates, levels, mine, lr, epoch) -> Dict[int, Dict]:
+        cfg, fed = self.cfg, self.federation
+        main = torch.cuda.current_stream(self.device) if self.is_cuda else None
+        order = sorted(mine, key=lambda i: -client_cost(rates[i], self._client_steps(user_idx[i])))
+        pending = deque(order)
+        active: List = []
+        busy: set = set()
+        results: Dict[int, Dict] = {}
+        result_arenas = self._result_arenas([levels[i] for i in mine], mine)
+        epochs = cfg["num_epochs"]["local"]
+
+        def start_batch(batch_pos: List[int]) -> None:
+            slots = []
+            for i in batch_pos:
+                s = self._acquire_slot(levels[i], busy)
+                busy.add(id(s))
+                slots.append(s)
+            # ONE distribute launch for the whole batch of starting clients
+            if self.is_cuda and cu.available():
+                from ..ops import fed_ops
+                fed_ops.distribute(self.tables, self.global_arena, [s.w for s in slots], [levels[i] for i in batch_pos],
+                                   [s.wc for s in slots] if slots[0].mixed else None, [s.mom for s in slots])
+                for s in slots:
+                    s.g.zero_()
+            else:
+                arenas = fed.distribute([user_idx[i] for i in batch_pos], redraw=False)
+                for s, a in zip(slots, arenas):
+                    s.load_params(a)
+            for i, s in zip(batch_pos, slots):
+                u = user_idx[i]
+                s.begin_client(lr, fed.user_label_mask(u))
+                if self.is_lm:
+                    rows = self._h2d(self.train_rows[torch.as_tensor(self.data_split["train"][u])])
+                    g = s.train_lm(rows, epochs, int(cfg["bptt"]))
+                else:
+                    idx = torch.as_tensor(self.data_split["train"][u], dtype=torch.long)
+                    if self.train_img.device == self.device:
+                        di = idx.to(self.device)
+                        imgs, labs = self.train_img[di], self.train_lab[di]
+                    else:
+                        imgs = self._h2d(self.train_img[idx].pin_memory() if self.is_cuda else self.train_img[idx])
+                        labs = self._h2d(self.train_lab[idx])
+                    gen = torch.Generator().manual_seed((self.seed * 1000003 + epoch * 7919) * 4099 + int(u))
+                    g = s.train_vision(imgs, labs, self.aug_train, epochs, int(cfg["batch_size"]["train"]), gen)
+                if self.is_cuda:
+                    s.stream.wait_stream(main)
+                active.append([g, s, i])
+
+        while pending or active:
+            room = self.opt.max_concurrent - len(active)
+            if pending and room > 0:
+                start_batch([pending.popleft() for _ in range(min(room, len(pending)))])
+            for item in list(active):
+                g, s, i = item
+                try:
+                    if self.is_cuda:
+                        with torch.cuda.stream(s.stream):
+                            next(g)
+                    else:
+                        next(g)
+                except StopIteration:
+                    if self.is_cuda:
+                        with torch.cuda.stream(s.stream):
+                            result_arenas[i].copy_(s.w, non_blocking=True)
+                            meter = s.meter.buf.clone()
+                        main.wait_stream(s.stream)
+                    else:
+                        result_arenas[i].copy_(s.w)
+                        meter = s.meter.buf.clone()
+                    results[i] = {"arena": result_arenas[i], "meter": meter, "level": levels[i]}
+                    busy.discard(id(s))
+                    active.remove(item)
+        return results
+
+    def _result_arenas(self, my_levels: List[int], mine: List[int]) -> Dict[int, torch.Tensor]:
+        out = {}
+        if self._peer is not None:
+            self._peer.reset_round()
+        for i, lv in zip(mine, my_levels):
+            n = self.tables.level_layouts[lv].size
+            if self._peer is not None:
+                out[i] = self._peer.alloc_round(n, torch.float32)
+            else:
+                out[i] = torch.empty(n, dtype=torch.float32, device=self.device)
+        return out
+
+    # -- aggregation ---------------------------------------------------------------------------------------
+    def _aggregate(self, user_idx, levels, mine, results) -> None:
+        fed, info = self.federation, self.info
+        masks_all = [fed.user_label_mask(u) for u in user_idx]
+        if self._agg_backend == "local":
+            order = sorted(results.keys())
+            arenas = [results[i]["arena"] for i in order]
+            if self.is_cuda and cu.available():
+                from ..ops import fed_ops
+                fed_ops.aggregate(self.tables, self.global_arena, arenas, [levels[i] for i in order],
+                                  [masks_all[i] for i in order])
+            else:
+                combine_torch(self.tables, self.global_arena, arenas, [self.tables.rates[levels[i]] for i in order],
+                              [masks_all[i] for i in order])
+        elif self._agg_backend == "p2p":
+            from ..parallel.peer import p2p_aggregate
+            p2p_aggregate(self._peer, self.tables, self.global_arena, levels, self._assignment, masks_all, info)
+        else:
+            from ..parallel.baseline import allreduce_aggregate
+            allreduce_aggregate(self.tables, self.global_arena, levels, results, masks_all, info)
+
+    # -- full training loop --------------------------------------------------------------------------------
+    def fit(self, num_rounds: Optional[int] = None) -> None:
+        if not self._setup_done:
+            self.setup()
+        cfg = self.cfg
+        last = cfg["num_epochs"]["global"] if num_rounds is None else min(cfg["num_epochs"]["global"],
+                                                                          self.epoch + num_rounds - 1)
+        while self.epoch <= last:
+            ep = self.epoch
+            self.logger.safe(True)
+            t0 = time.time()
+            res = self.run_round(ep)
+            dt = time.time() - t0
+            self._log_round(res, dt)
+            self.sched.step()
+            self.logger.safe(False)
+            if self.opt.save and self.info.is_main:
+                self.save_checkpoint(ep + 1, res)
+            self.logger.reset()
+            self.epoch = ep + 1
+            barrier(self.info)
+        self.logger.safe(False)
+
+    def _log_round(self, res: Dict, dt: float) -> None:
+        cfg, lg = self.cfg, self.logger
+        names = cfg["metric_name"]
+        lg.append(res["train"], "train", n=max(res["train_n"], 1.0))
+        left = (cfg["num_epochs"]["global"] - res["epoch"]) * dt
+        info = {"info": ["Model: {}".format(cfg["model_tag"]),
+                         "Train Epoch: {}(100%)".format(res["epoch"]),
+                         "Clients: {}".format(res["num_active"]),
+                         "Learning rate: {}".format(res["lr"]),
+                         "Round time: {:.3f}s".format(dt),
+                         "Experiment Finished Time: {:.0f}s".format(left)]}
+        lg.append(info, "train", mean=False)
+        quiet = self.opt.quiet or not self.info.is_main
+        lg.write("train", names["train"]["Local"], quiet=quiet)
+        if "test" in res:
+            tn = res.get("_test_n", {})
+            loc = {k: v for k, v in res["test"].items() if k.startswith("Local-")}
+            glo = {k: v for k, v in res["test"].items() if k.startswith("Global-")}
+            if loc:
+                lg.append(loc, "test", n=max(tn.get("_n_local", 1.0), 1.0))
+            lg.append(glo, "test", n=max(tn.get("_n_global", 1.0), 1.0))
+            lg.append({"info": ["Model: {}".format(cfg["model_tag"]),
+                                "Test Epoch: {}(100%)".format(res["epoch"])]}, "test", mean=False)
+            tnames = names["test"].get("Local", []) + names["test"]["Global"]
+            lg.write("test", tnames, quiet=quiet)
+
+    # -- checkpointing (reference format) ------------------------------------------------------
+    def state_dict(self) -> "OrderedDict[str, torch.Tensor]":
+        return self.global_model.layout.state_dict(self.global_arena.detach().float().cpu())
+
+    def load_state_dict(self, sd, strict: bool = True) -> None:
+        host = torch.zeros(self.global_model.layout.size)
+        cur = self.global_arena.detach().float().cpu()
+        host.copy_(cur)
+        self.global_model.layout.load_state_dict(host, sd, strict=strict)
+        self.global_arena.copy_(host.to(self.device))
+
+    def save_checkpoint(self, next_epoch: int, res: Optional[Dict] = None) -> str:
+        cfg = self.cfg
+        path = os.path.join(self.opt.out_dir, "model", "%s_checkpoint.pt" % cfg["model_tag"])
+        save_cfg = {k: v for k, v in cfg.items()}
+        obj = {"cfg": save_cfg, "epoch": next_epoch, "data_split": self.data_split, "label_split": self.label_split,
+               "model_dict": self.state_dict(), "optimizer_dict": self.sched.optimizer.state_dict(),
+               "scheduler_dict": self.sched.scheduler.state_dict(), "logger": self.logger}
+        ckpt.save(obj, path)
+        pm = "test/%s" % cfg["pivot_metric"]
+        if pm in self.logger.mean:
+            cur = self.logger.mean[pm]
+            better = cur > cfg["pivot"] if cfg["pivot_metric"].endswith("Accuracy") else cur < cfg["pivot"]
+            if better:
+                cfg["pivot"] = cur
+                shutil.copy(path, os.path.join(self.opt.out_dir, "model", "%s_best.pt" % cfg["model_tag"]))
+        return path
+
+    def _resume(self, mode: int, load_tag: str = "checkpoint") -> None:
+        cfg = self.cfg
+        path = os.path.join(self.opt.out_dir, "model", "%s_%s.pt" % (cfg["model_tag"], load_tag))
+        if not os.path.exists(path):
+            if self.info.is_main and not self.opt.quiet:
+                print("Not exists model tag: {}, start from scratch".format(cfg["model_tag"]))
+            return
+        ck = ckpt.load(path)
+        self.data_split, self.label_split = ck["data_split"], ck["label_split"]
+        self.load_state_dict(ck["model_dict"])
+        if mode == 1:
+            self.epoch = ck["epoch"]
+            self.sched.optimizer.load_state_dict(ck["optimizer_dict"])
+            self.sched.scheduler.load_state_dict(ck["scheduler_dict"])
+            self.logger = ck["logger"]
+            if self.info.is_main and not self.opt.quiet:
+                print("Resume from {}".format(self.epoch))
+        else:
+            self.logger = Logger(os.path.join(self.opt.out_dir, "runs", "%s" % cfg["model_tag"]),
+                                 tensorboard=self.opt.tensorboard)

@@ -1,0 +1,158 @@
+"""Server-side evaluation: static-BatchNorm statistics pass + Local/Global test.
+
+Reference ``stats()`` (``src/train_classifier_fed.py:127-138``) pushes the whole train set through a
+``track_running_stats=True`` copy of the global model in train-mode batches of 10 (5 000 forwards per round on
+CIFAR-10) and ``test()`` (``:141-169``) runs 100 per-user loaders plus one global loader.  Here
+
+* the sBN pass evaluates G ghost batches per launch (:class:`NormCtx` ``stats`` mode), is sharded over ranks and
+  merged with one tiny all-reduce of ``[sum mean, sum var]`` vectors;
+* the test pass computes the logits of every test image ONCE: *Global* metrics use them as is, *Local* metrics apply
+  each sample's owner's label mask (zero-fill) to the same logits -- identical numbers, half the forwards.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from ..data.datasets import LMData, VisionData
+from ..data.pipeline import VisionAugment, lm_windows
+from ..models import Model
+from ..ops.nn import NormCtx
+from ..parallel.dist import DistInfo, all_reduce_sum
+
+
+class Evaluator:
+    def __init__(self, model: Model, cfg: Dict, info: DistInfo, compute_dtype=torch.float32,
+                 stats_chunk_groups: int = 256, test_chunk: int = 2500):
+        self.model, self.cfg, self.info = model, cfg, info
+        self.device, self.dtype = info.device, compute_dtype
+        self.stats_chunk_groups, self.test_chunk = stats_chunk_groups, test_chunk
+        self._aug = {}
+
+    def _params(self, global_arena: torch.Tensor) -> Dict[str, torch.Tensor]:
+        wc = global_arena if self.dtype == torch.float32 else global_arena.to(self.dtype)
+        return self.model.layout.views(wc)
+
+    def _augment(self, ds: VisionData, train: bool) -> VisionAugment:
+        key = (ds.split, train)
+        if key not in self._aug:
+            self._aug[key] = VisionAugment(ds, train, self.device, self.dtype)
+        return self._aug[key]
+
+    # -- sBN ---------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def sbn_stats(self, global_arena: torch.Tensor, ds: VisionData, imgs_dev: torch.Tensor,
+                  generator: Optional[torch.Generator] = None) -> Dict:
+        """Running statistics of every BN layer = average over train-mode batches of ``batch_size['train']``."""
+        bn = self.model.bn_layers()
+        if not bn:
+            return {}
+        P = self._params(global_arena)
+        B = int(self.cfg["batch_size"]["train"])
+        N = imgs_dev.shape[0]
+        perm = torch.randperm(N, generator=generator)
+        n_full = N // B
+        aug = self._augment(ds, True)
+        params = aug.draw(N, generator)
+        perm_d = perm.to(self.device)
+        ctx = NormCtx("stats", group=B)
+        G = self.stats_chunk_groups
+        chunks = [(g0, min(g0 + G, n_full)) for g0 in range(0, n_full, G)]
+        labels_dummy = None
+        for ci, (g0, g1) in enumerate(chunks):
+            if ci % self.info.world != self.info.rank:
+                continue
+            idx = perm_d[g0 * B:g1 * B]
+            x = aug(imgs_dev, idx, params[g0 * B:g1 * B].contiguous())
+            self.model.forward(P, {"img": x}, ctx, None, want_score="raw")
+            ctx.n_groups += g1 - g0
+        if N % B and self.info.rank == 0:
+            idx = perm_d[n_full * B:]
+            x = aug(imgs_dev, idx, params[n_full * B:].contiguous())
+            ctx.group = int(idx.numel())
+            self.model.forward(P, {"img": x}, ctx, None, want_score="raw")
+            ctx.n_groups += 1
+        # merge across ranks: one flat vector [sum_mean..., sum_var..., n_groups]
+        widths = [w for _, w in bn]
+        flat = torch.zeros(2 * sum(widths) + 1, dtype=torch.float32, device=self.device)
+        off = 0
+        for name, w in bn:
+            if name in ctx.acc:
+                flat[off:off + w] = ctx.acc[name][0]
+                flat[off + w:off + 2 * w] = ctx.acc[name][1]
+            off += 2 * w
+        flat[-1] = ctx.n_groups
+        all_reduce_sum(self.info, flat)
+        n = flat[-1].clamp(min=1.0)
+        running, off = {}, 0
+        for name, w in bn:
+            running[name] = (flat[off:off + w] / n, flat[off + w:off + 2 * w] / n)
+            off += 2 * w
+        self.last_num_batches = int(flat[-1].item()) if False else None
+        return running
+
+    # -- test --------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def test_vision(self, global_arena: torch.Tensor, running: Dict, ds: VisionData, imgs_dev: torch.Tensor,
+                    labels_dev: torch.Tensor, owner_dev: Optional[torch.Tensor],
+                    user_masks_dev: Optional[torch.Tensor]) -> Dict[str, float]:
+        """``owner_dev[i]`` = user whose test split holds sample i (-1: none); ``user_masks_dev [U, classes]``."""
+        P = self._params(global_arena)
+        ctx = NormCtx("eval", running=running)
+        aug = self._augment(ds, False)
+        N = imgs_dev.shape[0]
+        acc = torch.zeros(6, dtype=torch.float64, device=self.device)
+        chunks = [(s, min(s + self.test_chunk, N)) for s in range(0, N, self.test_chunk)]
+        for ci, (s, e) in enumerate(chunks):
+            if ci % self.info.world != self.info.rank:
+                continue
+            idx = torch.arange(s, e, device=self.device)
+            x = aug(imgs_dev, idx, None)
+            y = labels_dev[s:e]
+            z = self.model.forward(P, {"img": x}, ctx, None, want_score="raw")["logits"]
+            acc[3] += F.cross_entropy(z, y, reduction="sum").double()
+            acc[4] += (z.argmax(1) == y).sum()
+            acc[5] += e - s
+            if owner_dev is not None:
+                own = owner_dev[s:e]
+                sel = own >= 0
+                if bool(self.cfg["mask"]) and user_masks_dev is not None:
+                    m = user_masks_dev[own.clamp(min=0)].bool()
+                    zl = z.masked_fill(~m, 0.0)
+                else:
+                    zl = z
+                ce = F.cross_entropy(zl, y, reduction="none")
+                acc[0] += (ce * sel).sum().double()
+                acc[1] += ((zl.argmax(1) == y) & sel).sum()
+                acc[2] += sel.sum()
+        all_reduce_sum(self.info, acc)
+        a = acc.tolist()
+        out = {"Global-Loss": a[3] / max(a[5], 1), "Global-Accuracy": 100.0 * a[4] / max(a[5], 1)}
+        if owner_dev is not None:
+            out["Local-Loss"] = a[0] / max(a[2], 1)
+            out["Local-Accuracy"] = 100.0 * a[1] / max(a[2], 1)
+        out["_n_local"], out["_n_global"] = a[2], a[5]
+        return out
+
+    @torch.no_grad()
+    def test_lm(self, global_arena: torch.Tensor, rows_dev: torch.Tensor) -> Dict[str, float]:
+        """Global masked-LM loss / perplexity over bptt windows of the batchified test stream; every window weighs
+        ``rows`` (reference ``src/train_transformer_fed.py:127-143``)."""
+        P = self._params(global_arena)
+        ctx = NormCtx("eval")
+        r, T = rows_dev.shape
+        acc = torch.zeros(3, dtype=torch.float64, device=self.device)
+        for wi, (s, l) in enumerate(lm_windows(T, int(self.cfg["bptt"]))):
+            if wi % self.info.world != self.info.rank:
+                continue
+            out = self.model.forward(P, {"label": rows_dev[:, s:s + l].contiguous()}, ctx, None, want_score=False)
+            lf = out["loss"].double()
+            acc[0] += lf * r
+            acc[1] += torch.exp(lf) * r
+            acc[2] += r
+        all_reduce_sum(self.info, acc)
+        a = acc.tolist()
+        return {"Global-Loss": a[0] / max(a[2], 1), "Global-Perplexity": a[1] / max(a[2], 1), "_n_global": a[2]}

@@ -1,0 +1,248 @@
+"""Client-side local training.
+
+Reference ``Local.train`` (``src/train_classifier_fed.py:185-210``, ``src/train_transformer_fed.py:152-183``) builds a
+fresh ``nn.Module`` + fresh SGD per client and loops ``zero_grad -> forward -> backward -> clip_grad_norm_(1) ->
+step -> .item() metrics`` with ~300 kernel launches and 2 host syncs per step.
+
+Here a :class:`TrainSlot` is a *resident* execution context for one complexity level:
+
+* parameters in a flat fp32 master arena ``w`` (filled directly by the distribute kernel, read directly by the
+  aggregate kernel -- possibly by a peer GPU), a bf16 compute copy ``wc`` and a bf16 gradient arena ``g`` whose
+  per-tensor views are the autograd leaves, fp32 momentum ``mom``;
+* the client's data shard resident on the device; batches are gathered/augmented by one kernel from a device-side
+  step counter, so a whole train step (batch assembly, forward, loss+metrics, backward, clip+SGD) is ONE captured
+  CUDA graph that is replayed ``epochs * steps`` times without touching the host;
+* metrics accumulate on the device and are read back once per client.
+
+Several slots run concurrently on their own streams, which is how a 148-SM B200 is kept busy by clients whose layers
+are as narrow as 4 channels.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from ..data.datasets import LMData, VisionData
+from ..data.pipeline import VisionAugment, lm_windows
+from ..models import Model
+from ..ops import cuda as cu
+from ..ops.nn import NormCtx
+from ..utils.metrics import DeviceMeter
+
+
+def sgd_clip_step_torch(w, wc, g, mom, lr: float, momentum: float, wd: float, max_norm: float) -> None:
+    """Flat-arena reference implementation of clip_grad_norm_ + SGD (used on CPU and as the kernel oracle)."""
+    gf = g.float()
+    total = gf.norm()
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    gg = gf * coef + wd * w
+    mom.mul_(momentum).add_(gg)
+    w.add_(mom, alpha=-lr)
+    if wc is not None and wc.data_ptr() != w.data_ptr():
+        wc.copy_(w)
+    g.zero_()
+
+
+class TrainSlot:
+    def __init__(self, model: Model, cfg: Dict, device, compute_dtype=torch.float32, use_graph: bool = False,
+                 w: Optional[torch.Tensor] = None):
+        self.model, self.cfg, self.device = model, cfg, torch.device(device)
+        self.dtype = compute_dtype
+        n = model.layout.size
+        self.w = w if w is not None else torch.zeros(n, dtype=torch.float32, device=device)
+        self.mixed = compute_dtype != torch.float32
+        self.wc = torch.zeros(n, dtype=compute_dtype, device=device) if self.mixed else self.w
+        self.g = torch.zeros(n, dtype=compute_dtype, device=device)
+        self.mom = torch.zeros(n, dtype=torch.float32, device=device)
+        self.P = {}
+        gviews = model.layout.views(self.g)
+        for k, v in model.layout.views(self.wc).items():
+            leaf = v.detach().requires_grad_(True)
+            leaf.grad = gviews[k]
+            self.P[k] = leaf
+        self.meter = DeviceMeter(device)
+        self.is_cuda = self.device.type == "cuda"
+        self.use_kernels = self.is_cuda and cu.available()
+        self.use_graph = bool(use_graph and self.is_cuda)
+        self.stream = torch.cuda.Stream(device=device) if self.is_cuda else None
+        self.lr_t = torch.zeros(1, dtype=torch.float32, device=device)
+        self.scratch = torch.zeros(4, dtype=torch.float32, device=device)
+        self.momentum, self.wd = float(cfg["momentum"]), float(cfg["weight_decay"])
+        self.max_norm = 1.0
+        self.label_rows = max([model.layout.entries[p.name].shape[0] for p in model.spec.params if p.label_rows] + [1])
+        self.mask_t = torch.ones(self.label_rows, dtype=torch.uint8, device=device)
+        self.use_mask = bool(cfg["mask"])
+        self.graphs: Dict = {}
+        self.graph_kernels: Dict = {}
+        self.step_ctr = torch.zeros(1, dtype=torch.int64, device=device)
+        self._static: Dict = {}
+        self.lr = 0.0
+
+    # -- per-client setup ----------------------------------------------------------------------------------
+    def begin_client(self, lr: float, label_mask: torch.Tensor) -> None:
+        """Parameters are expected in ``w`` (+``wc``) already (distribute kernel); reset optimiser state + meter."""
+        self.lr = float(lr)
+        self.lr_t.fill_(float(lr))
+        self.mask_t.copy_(label_mask.to(self.mask_t.device), non_blocking=True)
+        self.meter.zero_()
+        self.step_ctr.zero_()
+
+    def load_params(self, arena: torch.Tensor) -> None:
+        """Host/fallback path: copy a distributed arena in and reset momentum."""
+        self.w.copy_(arena)
+        if self.mixed:
+            self.wc.copy_(self.w)
+        self.mom.zero_()
+        self.g.zero_()
+
+    # -- one optimisation step -----------------------------------------------------------------------------
+    def _opt_step(self) -> None:
+        if self.use_kernels:
+            cu.sgd_clip_step(self.w, self.wc if self.mixed else None, self.g, self.mom, self.lr_t, self.momentum,
+                             self.wd, self.max_norm, self.scratch)
+        else:
+            sgd_clip_step_torch(self.w, self.wc, self.g, self.mom, self.lr, self.momentum, self.wd, self.max_norm)
+
+    def _fwd_bwd(self, inp: Dict, n_weight: float) -> None:
+        mask = self.mask_t if self.use_mask else None
+        if self.use_kernels:
+            inp = dict(inp)
+            inp["_meter"] = (self.meter.buf, n_weight)
+        out = self.model.forward(self.P, inp, NormCtx("train"), mask, want_score=not self.use_kernels
+                                 and not self.model.is_lm)
+        out["loss"].backward()
+        if not self.use_kernels:
+            self.meter.add(out["loss"], n_weight, out.get("score"), inp["label"] if "score" in out else None)
+
+    # -- vision --------------------------------------------------------------------------------------------
+    def train_vision(self, imgs_u8: torch.Tensor, labels: torch.Tensor, aug: VisionAugment, epochs: int, batch: int,
+                     generator: Optional[torch.Generator] = None):
+        """Generator yielding after every optimisation step (lets the engine interleave slots across streams)."""
+        n = imgs_u8.shape[0]
+        full, rem = n // batch, n % batch
+        steps_per_epoch = full + (1 if rem else 0)
+        perms = torch.stack([torch.randperm(n, generator=generator) for _ in range(epochs)])
+        params = aug.draw(epochs * n, generator).view(epochs, n, 3)
+        perms_d = perms.to(self.device, non_blocking=True)
+        if self.use_graph and full > 0:
+            self._vision_static(imgs_u8, labels, aug, batch, perms_d, params, epochs, full)
+        for ep in range(epochs):
+            for s in range(steps_per_epoch):
+                lo = s * batch
+                bs = min(batch, n - lo)
+                if self.use_graph and bs == batch:
+                    self._replay(("v", batch, tuple(imgs_u8.shape[1:])))
+                else:
+                    idx = perms_d[ep, lo:lo + bs]
+                    x = aug(imgs_u8, idx, params[ep, lo:lo + bs].contiguous())
+                    y = labels[idx]
+                    self._fwd_bwd({"img": x, "label": y}, float(bs))
+                    self._opt_step()
+                yield
+
+    def _vision_static(self, imgs_u8, labels, aug, batch, perms_d, params, epochs, full):
+        """(Re)bind the static buffers the captured step reads from, capturing the graph on first use."""
+        key = ("v", batch, tuple(imgs_u8.shape[1:]))
+        n = imgs_u8.shape[0]
+        cap = self._static.get(key)
+        max_n = max(n, cap["imgs"].shape[0]) if cap else n
+        max_rows = epochs * full
+        if cap is None or cap["imgs"].shape[0] < n or cap["idx"].shape[0] < max_rows:
+            cap = {"imgs": torch.zeros((max_n,) + tuple(imgs_u8.shape[1:]), dtype=torch.uint8, device=self.device),
+                   "labels": torch.zeros(max_n, dtype=torch.int64, device=self.device),
+                   "idx": torch.zeros(max_rows, batch, dtype=torch.int64, device=self.device),
+                   "par": torch.zeros(max_rows, batch, 3, dtype=torch.int32, device=self.device),
+                   "row": self.step_ctr}
+            self._static[key] = cap
+            self.graphs.pop(key, None)
+        cap["imgs"][:n].copy_(imgs_u8, non_blocking=True)
+        cap["labels"][:n].copy_(labels, non_blocking=True)
+        # only full batches go through the graph: rows = (epoch, step) pairs in execution order
+        for ep in range(epochs):
+            cap["idx"][ep * full:(ep + 1) * full].copy_(perms_d[ep, :full * batch].view(full, batch), non_blocking=True)
+            cap["par"][ep * full:(ep + 1) * full].copy_(params[ep, :full * batch].view(full, batch, 3),
+                                                        non_blocking=True)
+        if key not in self.graphs:
+            def step():
+                row = cap["row"]
+                idx = cap["idx"].index_select(0, row).view(-1)
+                par = cap["par"].index_select(0, row).view(-1, 3)
+                x = aug(cap["imgs"], idx, par)
+                y = cap["labels"].index_select(0, idx)
+                self._fwd_bwd({"img": x, "label": y}, float(batch))
+                self._opt_step()
+                row.add_(1)
+            self._capture(key, step)
+        return cap
+
+    # -- language model ------------------------------------------------------------------------------------
+    def train_lm(self, rows: torch.Tensor, epochs: int, bptt: int):
+        """``rows [r, T]`` token matrix of this client; one step per bptt window (reference BatchDataset order)."""
+        r, T = rows.shape
+        wins = lm_windows(T, bptt)
+        n_full = sum(1 for _, l in wins if l == bptt)
+        if self.use_graph and n_full > 0:
+            key = ("lm", r, bptt)
+            cap = self._static.get(key)
+            if cap is None or cap["win"].shape[0] < n_full:
+                cap = {"win": torch.zeros(n_full, r, bptt, dtype=torch.int64, device=self.device),
+                       "row": self.step_ctr}
+                self._static[key] = cap
+                self.graphs.pop(key, None)
+            cap["win"][:n_full].copy_(rows[:, :n_full * bptt].view(r, n_full, bptt).transpose(0, 1),
+                                      non_blocking=True)
+            if key not in self.graphs:
+                def step():
+                    tok = cap["win"].index_select(0, cap["row"]).view(r, bptt)
+                    self._fwd_bwd({"label": tok}, float(r))
+                    self._opt_step()
+                    cap["row"].add_(1)
+                self._capture(key, step)
+        for ep in range(epochs):
+            if self.use_graph:
+                self.step_ctr.zero_()
+            for (s, l) in wins:
+                if self.use_graph and l == bptt:
+                    self._replay(("lm", r, bptt))
+                else:
+                    self._fwd_bwd({"label": rows[:, s:s + l].contiguous()}, float(r))
+                    self._opt_step()
+                yield
+
+    # -- CUDA graph plumbing -------------------------------------------------------------------------------
+    def _capture(self, key, step_fn) -> None:
+        """Warm up on a side stream, then capture one full train step.  The warm-up steps really train, so state is
+        snapshotted and restored around them."""
+        snap = (self.w.clone(), self.wc.clone(), self.mom.clone(), self.meter.buf.clone(), self.step_ctr.clone())
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                step_fn()
+                self.step_ctr.zero_()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        k0 = cu.launch_count()
+        with torch.cuda.graph(graph, stream=s):
+            step_fn()
+        self.graph_kernels[key] = cu.launch_count() - k0
+        self.graphs[key] = graph
+        torch.cuda.synchronize(self.device)
+        self.w.copy_(snap[0])
+        self.wc.copy_(snap[1])
+        self.mom.copy_(snap[2])
+        self.meter.buf.copy_(snap[3])
+        self.step_ctr.copy_(snap[4])
+        self.g.zero_()
+        self.scratch.zero_()
+
+    def _replay(self, key) -> None:
+        self.graphs[key].replay()
+        cu.launch_count_add(self.graph_kernels.get(key, 0))
+
+    # -- results -------------------------------------------------------------------------------------------
+    def metrics(self) -> Dict[str, float]:
+        return self.meter.result("Local-", lm=self.model.is_lm)

@@ -17,7 +17,9 @@ from ..plan.spec import ModelSpec
 
 
 def _out(score: torch.Tensor, inp: Dict, label_mask: Optional[torch.Tensor], want_score: bool) -> Dict:
-    out = {"loss": masked_cross_entropy(score, inp["label"], label_mask)}
+    if want_score == "raw":          # evaluation: unmasked logits only (masks / metrics applied by the caller)
+        return {"logits": score.float()}
+    out = {"loss": masked_cross_entropy(score, inp["label"], label_mask, inp.get("_meter"))}
     if want_score:
         out["score"] = masked_logits(score.float(), label_mask)
     return out

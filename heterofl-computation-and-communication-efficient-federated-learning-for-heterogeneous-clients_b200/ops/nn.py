@@ -105,15 +105,19 @@ def layer_norm_scaled(x: torch.Tensor, weight, bias, scale_rate: float, training
     return F.layer_norm(x, (x.shape[-1],), weight, bias, 1e-5 * s * s)
 
 
-def masked_cross_entropy(logits: torch.Tensor, target: torch.Tensor,
-                         label_mask: Optional[torch.Tensor]) -> torch.Tensor:
+def masked_cross_entropy(logits: torch.Tensor, target: torch.Tensor, label_mask: Optional[torch.Tensor],
+                         meter=None) -> torch.Tensor:
     """Mean CE over rows of ``logits [M, V]`` after zero-filling masked-out classes.
 
     ``label_mask``: uint8/bool ``[V]`` (1 = class present on this client) or None.
+    ``meter``: optional ``(float64[4] device tensor, n_weight)`` bumped inside the fused kernel with
+    ``[loss*n, #correct, n, exp(loss)*n]`` (GPU path only).
     """
     if logits.is_cuda:
         from . import cuda as cu
         if cu.available():
+            if meter is not None:
+                return cu.masked_ce(logits, target, label_mask, meter[1], meter[0])
             return cu.masked_ce(logits, target, label_mask)
     z = logits.float()
     if label_mask is not None:
