@@ -186,6 +186,7 @@ class Engine:
         self.test_img = te.img.to(dev) if on_dev else pin(te.img)
         self.test_lab = te.target.to(dev) if on_dev else pin(te.target)
         self.aug_train = VisionAugment(tr, True, dev, self.dtype)
+        self._max_shard = max(len(v) for v in self.data_split["train"].values())
         U, C = self.cfg["num_users"], self.cfg["classes_size"]
         owner = torch.full((len(te),), -1, dtype=torch.int64)
         for u in range(U):
@@ -217,6 +218,39 @@ class Engine:
         s = TrainSlot(self._model_for(rate), self.cfg, self.device, self.dtype, self.use_graph)
         pool.append(s)
         return s
+
+    def prewarm(self, slots_per_level: Optional[int] = None) -> int:
+        """Create the resident slots and capture their train-step graphs up front (one dummy step each), so no
+        capture happens inside a measured round.  Returns the number of slots warmed."""
+        if not self._setup_done:
+            self.setup()
+        if not self.use_graph:
+            return 0
+        cfg = self.cfg
+        n_act = int(np.ceil(cfg["frac"] * cfg["num_users"]))
+        per_rank = int(np.ceil(n_act / self.info.world))
+        S = min(self.opt.max_concurrent, per_rank) if slots_per_level is None else slots_per_level
+        client_levels = sorted({self.tables.level_id(float(r)) for r in cfg["model_rate"]})
+        u = 0
+        warmed = 0
+        for lv in client_levels:
+            busy: set = set()
+            for _ in range(S):
+                s = self._acquire_slot(lv, busy)
+                busy.add(id(s))
+                s.load_params(torch.zeros_like(s.w).normal_(0, 0.02))
+                s.begin_client(0.0, self.federation.user_label_mask(u))
+                with torch.cuda.stream(s.stream):
+                    g = self._client_generator(s, u, 1, 0)
+                    next(g)
+                warmed += 1
+        torch.cuda.synchronize(self.device)
+        return warmed
+
+    def set_data_residency(self, on_device: bool) -> None:
+        """Switch between a device-resident dataset and a pinned-host dataset streamed H2D every round."""
+        self.opt.data_on_device = bool(on_device)
+        self._stage_data()
 
     # ------------------------------------------------------------------------------------------------------
     def current_lr(self) -> float:
@@ -324,19 +358,7 @@ class Engine:
             for i, s in zip(batch_pos, slots):
                 u = user_idx[i]
                 s.begin_client(lr, fed.user_label_mask(u))
-                if self.is_lm:
-                    rows = self._h2d(self.train_rows[torch.as_tensor(self.data_split["train"][u])])
-                    g = s.train_lm(rows, epochs, int(cfg["bptt"]))
-                else:
-                    idx = torch.as_tensor(self.data_split["train"][u], dtype=torch.long)
-                    if self.train_img.device == self.device:
-                        di = idx.to(self.device)
-                        imgs, labs = self.train_img[di], self.train_lab[di]
-                    else:
-                        imgs = self._h2d(self.train_img[idx].pin_memory() if self.is_cuda else self.train_img[idx])
-                        labs = self._h2d(self.train_lab[idx])
-                    gen = torch.Generator().manual_seed((self.seed * 1000003 + epoch * 7919) * 4099 + int(u))
-                    g = s.train_vision(imgs, labs, self.aug_train, epochs, int(cfg["batch_size"]["train"]), gen)
+                g = self._client_generator(s, u, epochs, epoch)
                 if self.is_cuda:
                     s.stream.wait_stream(main)
                 active.append([g, s, i])
@@ -366,6 +388,26 @@ class Engine:
                     busy.discard(id(s))
                     active.remove(item)
         return results
+
+    def _client_generator(self, s: TrainSlot, u: int, epochs: int, epoch: int):
+        cfg = self.cfg
+        if self.is_lm:
+            ridx = torch.as_tensor(self.data_split["train"][u])
+            if self.train_rows.device == self.device:
+                rows = self.train_rows[ridx.to(self.device)]
+            else:
+                rows = self._h2d(self.train_rows[ridx].pin_memory() if self.is_cuda else self.train_rows[ridx])
+            return s.train_lm(rows, epochs, int(cfg["bptt"]))
+        idx = torch.as_tensor(self.data_split["train"][u], dtype=torch.long)
+        if self.train_img.device == self.device:
+            di = idx.to(self.device)
+            imgs, labs = self.train_img[di], self.train_lab[di]
+        else:
+            imgs = self._h2d(self.train_img[idx].pin_memory() if self.is_cuda else self.train_img[idx])
+            labs = self._h2d(self.train_lab[idx].pin_memory() if self.is_cuda else self.train_lab[idx])
+        gen = torch.Generator().manual_seed((self.seed * 1000003 + epoch * 7919) * 4099 + int(u))
+        return s.train_vision(imgs, labs, self.aug_train, epochs, int(cfg["batch_size"]["train"]), gen,
+                              max_n=self._max_shard, max_epochs=int(cfg["num_epochs"]["local"]))
 
     def _result_arenas(self, my_levels: List[int], mine: List[int]) -> Dict[int, torch.Tensor]:
         out = {}

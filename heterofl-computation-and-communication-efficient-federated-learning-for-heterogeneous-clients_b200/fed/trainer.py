@@ -118,7 +118,7 @@ class TrainSlot:
 
     # -- vision --------------------------------------------------------------------------------------------
     def train_vision(self, imgs_u8: torch.Tensor, labels: torch.Tensor, aug: VisionAugment, epochs: int, batch: int,
-                     generator: Optional[torch.Generator] = None):
+                     generator: Optional[torch.Generator] = None, max_n: int = 0, max_epochs: int = 0):
         """Generator yielding after every optimisation step (lets the engine interleave slots across streams)."""
         n = imgs_u8.shape[0]
         full, rem = n // batch, n % batch
@@ -127,7 +127,7 @@ class TrainSlot:
         params = aug.draw(epochs * n, generator).view(epochs, n, 3)
         perms_d = perms.to(self.device, non_blocking=True)
         if self.use_graph and full > 0:
-            self._vision_static(imgs_u8, labels, aug, batch, perms_d, params, epochs, full)
+            self._vision_static(imgs_u8, labels, aug, batch, perms_d, params, epochs, full, max_n, max_epochs)
         for ep in range(epochs):
             for s in range(steps_per_epoch):
                 lo = s * batch
@@ -142,13 +142,14 @@ class TrainSlot:
                     self._opt_step()
                 yield
 
-    def _vision_static(self, imgs_u8, labels, aug, batch, perms_d, params, epochs, full):
-        """(Re)bind the static buffers the captured step reads from, capturing the graph on first use."""
+    def _vision_static(self, imgs_u8, labels, aug, batch, perms_d, params, epochs, full, max_n=0, max_epochs=0):
+        """(Re)bind the static buffers the captured step reads from, capturing the graph on first use.  ``max_n`` /
+        ``max_epochs`` (largest shard / local epochs of the run) size the buffers so they never have to grow."""
         key = ("v", batch, tuple(imgs_u8.shape[1:]))
         n = imgs_u8.shape[0]
         cap = self._static.get(key)
-        max_n = max(n, cap["imgs"].shape[0]) if cap else n
-        max_rows = epochs * full
+        max_n = max(n, max_n, cap["imgs"].shape[0] if cap else 0)
+        max_rows = max(epochs, max_epochs) * (max_n // batch)
         if cap is None or cap["imgs"].shape[0] < n or cap["idx"].shape[0] < max_rows:
             cap = {"imgs": torch.zeros((max_n,) + tuple(imgs_u8.shape[1:]), dtype=torch.uint8, device=self.device),
                    "labels": torch.zeros(max_n, dtype=torch.int64, device=self.device),

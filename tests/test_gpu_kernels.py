@@ -1,0 +1,206 @@
+"""sm_100a kernels vs plain PyTorch fp32 references (run on the B200 box: ``pytest -m gpu``)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from hfl_b200.config.control import make_cfg
+from hfl_b200.plan.layout import build_tables
+from hfl_b200.plan.spec import build_spec
+
+
+def _cu():
+    from hfl_b200.ops import cuda as cu
+    assert cu.available(), "extension must be loaded on a GPU box"
+    return cu
+
+
+def test_extension_loaded():
+    cu = _cu()
+    assert cu.launch_count() >= 0
+
+
+@pytest.mark.parametrize("data,model,control,extra,cl", [
+    ("CIFAR10", "resnet18", "1_10_0.5_non-iid-2_fix_a1-b1-c1-d1-e1_bn_1_1", dict(classes_size=10), True),
+    ("MNIST", "conv", "1_10_0.5_iid_fix_b1-e1_gn_1_1", dict(classes_size=10), True),
+    ("WikiText2", "transformer", "1_10_0.5_iid_fix_a1-b1-c1-d1-e1_none_1_0", dict(num_tokens=331), False),
+])
+def test_distribute_aggregate_match_torch(data, model, control, extra, cl):
+    _cu()
+    from hfl_b200.fed.federation import combine_torch, distribute_torch
+    from hfl_b200.ops import fed_ops
+    cfg = make_cfg(data, model, control, **extra)
+    spec = build_spec(cfg)
+    rates = sorted(set(cfg["model_rate"]), reverse=True)
+    tables = build_tables(spec, cfg["global_model_rate"], rates, channels_last=cl)
+    dev = torch.device("cuda")
+    g = torch.randn(tables.global_layout.size, device=dev)
+    client_rates = [rates[i % len(rates)] for i in range(7)]
+    levels = [tables.level_id(r) for r in client_rates]
+    # distribute
+    ref = [torch.zeros(tables.level_layouts[l].size, device=dev) for l in levels]
+    distribute_torch(tables, g, ref, client_rates)
+    w = [torch.full((tables.level_layouts[l].size,), 7.0, device=dev) for l in levels]
+    wc = [torch.zeros(tables.level_layouts[l].size, device=dev, dtype=torch.bfloat16) for l in levels]
+    mom = [torch.ones(tables.level_layouts[l].size, device=dev) for l in levels]
+    fed_ops.distribute(tables, g, w, levels, wc, mom)
+    for a, b, c, m, l in zip(ref, w, wc, mom, levels):
+        lay = tables.level_layouts[l]
+        for name in lay.entries:
+            assert torch.equal(lay.view(a, name), lay.view(b, name)), name
+            assert torch.equal(lay.view(a, name).bfloat16(), lay.view(c, name)), name
+            assert float(lay.view(m, name).abs().max()) == 0.0
+    # aggregate
+    rows = max(int(p.out.local(cfg["global_model_rate"])) for p in spec.params if p.label_rows)
+    rng = np.random.RandomState(0)
+    masks = []
+    for _ in levels:
+        m = torch.zeros(rows, dtype=torch.uint8)
+        m[torch.as_tensor(rng.choice(rows, size=max(2, rows // 3), replace=False))] = 1
+        masks.append(m)
+    local = [torch.randn_like(a) for a in w]
+    g_ref, g_k = g.clone(), g.clone()
+    combine_torch(tables, g_ref, local, client_rates, masks)
+    fed_ops.aggregate(tables, g_k, local, levels, masks)
+    torch.cuda.synchronize()
+    assert torch.allclose(g_ref, g_k, atol=1e-5, rtol=1e-5)
+    assert not torch.equal(g_k, g)
+
+
+@pytest.mark.parametrize("gdtype", [torch.float32, torch.bfloat16])
+def test_sgd_clip_step(gdtype):
+    cu = _cu()
+    from hfl_b200.fed.trainer import sgd_clip_step_torch
+    dev = torch.device("cuda")
+    n = 8 * 12345
+    w = torch.randn(n, device=dev)
+    mom = torch.randn(n, device=dev) * 0.1
+    lr_t = torch.tensor([0.1], device=dev)
+    scratch = torch.zeros(4, device=dev)
+    for scale in (0.001, 3.0):                # below and above the clipping threshold
+        g = (torch.randn(n, device=dev) * scale / n ** 0.5 * 3).to(gdtype)
+        w_ref, m_ref, g_ref = w.clone(), mom.clone(), g.clone()
+        wc_ref = torch.zeros(n, device=dev, dtype=torch.bfloat16)
+        sgd_clip_step_torch(w_ref, wc_ref, g_ref, m_ref, 0.1, 0.9, 5e-4, 1.0)
+        wc = torch.zeros(n, device=dev, dtype=torch.bfloat16)
+        cu.sgd_clip_step(w, wc, g, mom, lr_t, 0.9, 5e-4, 1.0, scratch)
+        torch.cuda.synchronize()
+        assert torch.allclose(w, w_ref, atol=1e-6, rtol=1e-5)
+        assert torch.allclose(mom, m_ref, atol=1e-6, rtol=1e-5)
+        assert torch.equal(wc, w.bfloat16())
+        assert float(g.float().abs().max()) == 0.0
+        assert float(scratch[0]) == 0.0 and float(scratch[1]) == 0.0
+
+
+@pytest.mark.parametrize("rows,V,dtype,masked", [(10, 10, torch.float32, True), (10, 10, torch.bfloat16, False),
+                                                  (64, 33278, torch.bfloat16, True), (37, 1000, torch.float32, True)])
+def test_masked_ce(rows, V, dtype, masked):
+    cu = _cu()
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    z = (torch.randn(rows, V, device=dev) * 2).to(dtype).requires_grad_(True)
+    y = torch.randint(0, V, (rows,), device=dev)
+    mask = None
+    if masked:
+        mask = (torch.rand(V, device=dev) < 0.5).to(torch.uint8)
+        mask[y] = 1
+    meter = torch.zeros(4, dtype=torch.float64, device=dev)
+    loss = cu.masked_ce(z, y, mask, 7.0, meter)
+    (loss * 2.0).backward()
+    zr = z.detach().float().requires_grad_(True)
+    zm = zr if mask is None else zr.masked_fill(mask.bool().logical_not().view(1, -1), 0.0)
+    lr = F.cross_entropy(zm, y)
+    (lr * 2.0).backward()
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert torch.allclose(loss, lr, atol=1e-4, rtol=1e-4)
+    assert torch.allclose(z.grad.float(), zr.grad, atol=tol * (1.0 / rows + 1e-3), rtol=tol * 10)
+    m = meter.tolist()
+    assert m[0] == pytest.approx(float(lr) * 7.0, rel=1e-4) and m[2] == 7.0
+    assert m[1] == float((zm.argmax(1) == y).sum()) and m[3] == pytest.approx(float(torch.exp(lr)) * 7.0, rel=1e-4)
+
+
+def test_augment_matches_torch():
+    cu = _cu()
+    from hfl_b200.data.datasets import synth_vision
+    from hfl_b200.data.pipeline import VisionAugment
+    dev = torch.device("cuda")
+    ds = synth_vision("CIFAR10", "train", 64)
+    img = ds.img.to(dev)
+    idx = torch.randperm(64, device=dev)[:10]
+    for dtype in (torch.float32, torch.bfloat16):
+        aug = VisionAugment(ds, True, dev, dtype)
+        par = aug.draw(10)
+        got = aug(img, idx, par)
+        cpu_aug = VisionAugment(ds, True, "cpu", torch.float32)
+        want = cpu_aug(ds.img, idx.cpu(), par.cpu())
+        assert got.shape == (10, 3, 32, 32) and got.is_contiguous(memory_format=torch.channels_last)
+        assert torch.allclose(got.float().cpu(), want, atol=2e-2 if dtype == torch.bfloat16 else 1e-5)
+
+
+def test_train_slot_graph_matches_eager():
+    """A captured train-step graph replays exactly what the eager step computes (fp32 compute)."""
+    _cu()
+    from hfl_b200.data.datasets import synth_vision
+    from hfl_b200.data.pipeline import VisionAugment
+    from hfl_b200.fed.trainer import TrainSlot
+    from hfl_b200.models import Model
+    dev = torch.device("cuda")
+    cfg = make_cfg("CIFAR10", "resnet18", "1_10_0.5_iid_fix_a1-d1_bn_1_1", classes_size=10)
+    spec = build_spec(cfg)
+    ds = synth_vision("CIFAR10", "train", 40)
+    img, lab = ds.img.to(dev), ds.target.to(dev)
+    aug = VisionAugment(ds, True, dev, torch.float32)
+    init = None
+    outs = []
+    for use_graph in (False, True):
+        model = Model(spec, cfg, 0.125, True)
+        slot = TrainSlot(model, cfg, dev, torch.float32, use_graph)
+        if init is None:
+            init = model.new_arena(dev)
+        slot.load_params(init)
+        slot.begin_client(0.05, torch.ones(10, dtype=torch.uint8))
+        g = torch.Generator().manual_seed(5)
+        with torch.cuda.stream(slot.stream):
+            for _ in slot.train_vision(img, lab, aug, 2, 10, g):
+                pass
+        torch.cuda.synchronize()
+        outs.append((slot.w.clone(), slot.metrics()))
+    assert torch.allclose(outs[0][0], outs[1][0], atol=2e-4, rtol=1e-3)
+    assert outs[0][1]["Local-Loss"] == pytest.approx(outs[1][1]["Local-Loss"], rel=1e-3)
+
+
+@pytest.mark.parametrize("data,model,control,sizes", [
+    ("CIFAR10", "resnet18", "1_10_0.5_non-iid-2_dynamic_a1-b1-c1-d1-e1_bn_1_1", {"train": 1000, "test": 200}),
+    ("MNIST", "conv", "1_10_0.5_iid_fix_a1-e1_bn_1_1", {"train": 1000, "test": 200}),
+])
+def test_engine_round_gpu(tmp_path, data, model, control, sizes):
+    """Convergence smoke on the GPU path (bf16 compute, CUDA graphs, fused kernels): loss falls, metrics finite."""
+    _cu()
+    from hfl_b200.fed.engine import Engine, EngineOptions
+    from hfl_b200.parallel.dist import DistInfo
+    dev = torch.device("cuda", 0)
+    cfg = make_cfg(data, model, control, synthetic=True, synthetic_size=sizes)
+    cfg["num_epochs"] = {"global": 3, "local": 2}
+    eng = Engine(cfg, DistInfo(0, 1, 0, dev, None), options=EngineOptions(out_dir=str(tmp_path), quiet=True))
+    eng.fit()
+    h = eng.logger.history
+    assert all(np.isfinite(v) for v in h["train/Local-Loss"] + h["test/Global-Loss"] + h["test/Local-Loss"])
+    assert h["train/Local-Loss"][-1] < h["train/Local-Loss"][0]
+    assert h["test/Local-Accuracy"][-1] > 100.0 / 10 * 1.5
+
+
+def test_engine_lm_round_gpu(tmp_path):
+    _cu()
+    from hfl_b200.fed.engine import Engine, EngineOptions
+    from hfl_b200.parallel.dist import DistInfo
+    dev = torch.device("cuda", 0)
+    cfg = make_cfg("WikiText2", "transformer", "1_10_0.5_iid_fix_a5-b5_none_1_1", synthetic=True,
+                   synthetic_size={"train": 100 * 64 * 6, "test": 10 * 64 * 4}, synthetic_vocab=500)
+    cfg["num_epochs"] = {"global": 2, "local": 1}
+    eng = Engine(cfg, DistInfo(0, 1, 0, dev, None), options=EngineOptions(out_dir=str(tmp_path), quiet=True))
+    eng.fit()
+    h = eng.logger.history
+    assert all(np.isfinite(v) for v in h["train/Local-Loss"] + h["test/Global-Perplexity"])
+    assert h["train/Local-Loss"][-1] < h["train/Local-Loss"][0]
