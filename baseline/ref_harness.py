@@ -60,12 +60,16 @@ def _fabricate_data(data_name: str, seed: int = 0) -> None:
 
 
 def run(args, data_name: str, model_name: str, control: str, ClockSampler) -> None:
+    # the reference calls torch.load() on numpy/object pickles without weights_only=False (torch < 2.6 semantics)
+    os.environ["TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD"] = "1"
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
+    use_cuda = torch.cuda.is_available()
+    if use_cuda:
+        torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -78,7 +82,8 @@ def run(args, data_name: str, model_name: str, control: str, ClockSampler) -> No
     sys.path.insert(0, REF_SRC)
     is_lm = model_name == "transformer"
     entry = "train_transformer_fed" if is_lm else "train_classifier_fed"
-    sys.argv = [entry + ".py", "--data_name", data_name, "--model_name", model_name, "--control_name", control]
+    sys.argv = [entry + ".py", "--data_name", data_name, "--model_name", model_name, "--control_name", control,
+                "--device", "cuda" if use_cuda else "cpu"]
     if rank == 0:
         _fabricate_data(data_name)
     if world > 1:
@@ -101,7 +106,8 @@ def run(args, data_name: str, model_name: str, control: str, ClockSampler) -> No
             return out
         nn.TransformerEncoder.forward = _enc_forward
     torch.manual_seed(0)
-    torch.cuda.manual_seed(0)
+    if use_cuda:
+        torch.cuda.manual_seed(0)
     dataset = T.fetch_dataset(cfg["data_name"], cfg["subset"])
     T.process_dataset(dataset)
     model = eval('T.models.{}(model_rate=cfg["global_model_rate"]).to(cfg["device"])'.format(cfg["model_name"]))
@@ -140,22 +146,29 @@ def run(args, data_name: str, model_name: str, control: str, ClockSampler) -> No
             ep += 1
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        if use_cuda:
+            torch.cuda.synchronize()
         samples_box[0] = 0.0
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if use_cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local_rank) as cs:
-            e0.record()
+            t0 = time.perf_counter()
+            if use_cuda:
+                e0.record()
             for _ in range(args.steps):
                 one_round(ep)
                 ep += 1
-            e1.record()
-            torch.cuda.synchronize()
+            if use_cuda:
+                e1.record()
+                torch.cuda.synchronize()
+            wall_ms = (time.perf_counter() - t0) * 1e3
         if world > 1:
             dist.barrier()
     finally:
         sys.stdout = stdout
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    smp = torch.tensor([samples_box[0]], device="cuda", dtype=torch.float64)
+    dev = "cuda" if use_cuda else "cpu"
+    ms = torch.tensor([e0.elapsed_time(e1) if use_cuda else wall_ms], device=dev, dtype=torch.float64)
+    smp = torch.tensor([samples_box[0]], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(smp, op=dist.ReduceOp.SUM)

@@ -16,7 +16,7 @@ from hfl_b200.parallel.dist import DistInfo
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 cfg = make_cfg("CIFAR10", "resnet18", "1_100_0.1_non-iid-2_dynamic_a1-b1-c1-d1-e1_bn_1_1", synthetic=True,
-               synthetic_size={"train": 5000, "test": 1000})
+               synthetic_size={"train": 50000, "test": 1000})
 eng = Engine(cfg, DistInfo(0, 1, 0, dev, None), options=EngineOptions(out_dir="/tmp/p", quiet=True, save=False))
 eng.setup()
 eng.prewarm(4)
