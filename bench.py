@@ -95,6 +95,8 @@ def run_ours(args):
     cfg = make_cfg(data, model, control, synthetic=True, **({"synthetic_size": sizes} if sizes else {}))
     if args.local_epochs:
         cfg["num_epochs"]["local"] = args.local_epochs
+    if args.no_fused:
+        cfg["fused"] = False
     eng = Engine(cfg, info, options=EngineOptions(out_dir="/tmp/hfl_bench", quiet=True, save=False,
                                                   max_concurrent=args.max_concurrent,
                                                   agg_backend=args.agg_backend))
@@ -189,6 +191,7 @@ def main():
     ap.add_argument("--local-epochs", type=int, default=0)
     ap.add_argument("--max-concurrent", type=int, default=16)
     ap.add_argument("--agg-backend", default="auto")
+    ap.add_argument("--no-fused", action="store_true", help="A/B: autograd + library-BN path instead of the fused path")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus != world:

@@ -22,6 +22,14 @@ void hfl_masked_ce(const void*, int, const long long*, const unsigned char*, int
                    float*, double*, cudaStream_t);
 void hfl_augment(const unsigned char*, const long long*, const int*, const float*, const float*, int, int, int, int,
                  int, void*, int, cudaStream_t);
+int hfl_bn_act_fwd(const void*, const void*, void*, void*, const void*, const void*, int, float, int, int, int, int,
+                   float*, float*, float*, cudaStream_t);
+void hfl_affine_act(const void*, const void*, void*, void*, const float*, const float*, long, int, int, cudaStream_t);
+int hfl_bn_act_bwd(const void*, const void*, const void*, const void*, const float*, const float*, const void*,
+                   const void*, int, int, int, int, float, int, void*, void*, void*, cudaStream_t);
+int hfl_ms_chunk();
+void hfl_multi_sgd_clip_step(const void*, const void*, int, float*, void*, float*, const float*, float, float, float,
+                             float*, cudaStream_t);
 long hfl_launch_count();
 void hfl_launch_count_add(long);
 void hfl_peer_barrier(const void*, int, int, unsigned, int*, cudaStream_t);
@@ -143,6 +151,94 @@ torch::Tensor augment(torch::Tensor src, c10::optional<torch::Tensor> idx, c10::
   return out;
 }
 
+// ---- fused norm ------------------------------------------------------------------------------------------
+static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+static const void* optp(const c10::optional<torch::Tensor>& t) { return t.has_value() ? t->data_ptr() : nullptr; }
+
+// x, res: NHWC-dense bf16 activations (any logical shape with C the fastest physical dim); returns
+// [s (or undefined), y, mean[G,C], invstd[G,C], var_unbiased[G,C]]
+std::vector<torch::Tensor> bn_act_fwd(torch::Tensor x, c10::optional<torch::Tensor> res, torch::Tensor gamma,
+                                      torch::Tensor beta, double eps, int64_t groups, int64_t C, bool relu) {
+  CHECK_CUDA_T(x);
+  TORCH_CHECK(x.scalar_type() == torch::kBFloat16, "bn_act_fwd: bf16 activations only");
+  TORCH_CHECK(is_pow2(C) && C >= 4 && C <= 2048, "bn_act_fwd: C must be a power of two in [4, 2048]");
+  const int64_t M = x.numel() / C;
+  TORCH_CHECK(M % groups == 0 && ((M / groups) * C) % 8 == 0);
+  const bool pb = gamma.scalar_type() == torch::kBFloat16;
+  TORCH_CHECK(pb || gamma.scalar_type() == torch::kFloat32);
+  TORCH_CHECK(gamma.is_contiguous() && beta.is_contiguous() && beta.scalar_type() == gamma.scalar_type());
+  c10::cuda::CUDAGuard guard(x.device());
+  auto y = torch::empty_like(x);
+  torch::Tensor s;
+  if (res.has_value()) { TORCH_CHECK(res->numel() == x.numel() && res->scalar_type() == torch::kBFloat16); s = torch::empty_like(x); }
+  auto fopt = torch::TensorOptions().dtype(torch::kFloat32).device(x.device());
+  auto stats = torch::empty({3, groups, C}, fopt);
+  float* sp = stats.data_ptr<float>();
+  int e = hfl_bn_act_fwd(x.data_ptr(), optp(res), res.has_value() ? s.data_ptr() : nullptr, y.data_ptr(),
+                         gamma.data_ptr(), beta.data_ptr(), pb ? 1 : 0, (float)eps, (int)groups, (int)(M / groups),
+                         (int)C, relu ? 1 : 0, sp, sp + groups * C, sp + 2 * groups * C, cur_stream());
+  TORCH_CHECK(e == 0, "bn_act_fwd launch failed: ", cudaGetErrorString((cudaError_t)e));
+  check_launch();
+  return {s, y, stats[0], stats[1], stats[2]};
+}
+
+std::vector<torch::Tensor> affine_act(torch::Tensor x, c10::optional<torch::Tensor> res, torch::Tensor a,
+                                      torch::Tensor b, int64_t C, bool relu) {
+  CHECK_CUDA_T(x);
+  TORCH_CHECK(x.scalar_type() == torch::kBFloat16 && x.numel() % 8 == 0 && is_pow2(C));
+  TORCH_CHECK(a.scalar_type() == torch::kFloat32 && b.scalar_type() == torch::kFloat32 && a.numel() == C);
+  c10::cuda::CUDAGuard guard(x.device());
+  auto y = torch::empty_like(x);
+  torch::Tensor s;
+  if (res.has_value()) s = torch::empty_like(x);
+  hfl_affine_act(x.data_ptr(), optp(res), res.has_value() ? s.data_ptr() : nullptr, y.data_ptr(),
+                 a.data_ptr<float>(), b.data_ptr<float>(), (long)x.numel(), (int)C, relu ? 1 : 0, cur_stream());
+  check_launch();
+  return {s, y};
+}
+
+// returns ds; writes dgamma / dbeta in place (views into the gradient arena)
+torch::Tensor bn_act_bwd(torch::Tensor dy, c10::optional<torch::Tensor> dy2, c10::optional<torch::Tensor> dres,
+                         torch::Tensor s, torch::Tensor mean, torch::Tensor invstd, torch::Tensor gamma,
+                         torch::Tensor beta, torch::Tensor dgamma, torch::Tensor dbeta, int64_t C, int64_t hw,
+                         double dy_scale, bool relu) {
+  CHECK_CUDA_T(dy); CHECK_CUDA_T(s);
+  TORCH_CHECK(s.scalar_type() == torch::kBFloat16 && dy.scalar_type() == torch::kBFloat16);
+  TORCH_CHECK(is_pow2(C) && C >= 4 && C <= 2048);
+  const int64_t M = s.numel() / C;
+  TORCH_CHECK((M * C) % 8 == 0);
+  if (hw > 0) {
+    TORCH_CHECK(dy.numel() * hw == s.numel() && (hw * C) % 8 == 0);
+  } else {
+    TORCH_CHECK(dy.numel() == s.numel());
+  }
+  const bool pb = gamma.scalar_type() == torch::kBFloat16;
+  TORCH_CHECK(dgamma.scalar_type() == gamma.scalar_type() && dbeta.scalar_type() == gamma.scalar_type());
+  TORCH_CHECK(dgamma.is_contiguous() && dbeta.is_contiguous() && mean.scalar_type() == torch::kFloat32);
+  c10::cuda::CUDAGuard guard(s.device());
+  auto ds = torch::empty_like(s);
+  int e = hfl_bn_act_bwd(dy.data_ptr(), optp(dy2), optp(dres), s.data_ptr(), mean.data_ptr<float>(),
+                         invstd.data_ptr<float>(), gamma.data_ptr(), beta.data_ptr(), pb ? 1 : 0, (int)M, (int)C,
+                         (int)hw, (float)dy_scale, relu ? 1 : 0, ds.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                         cur_stream());
+  TORCH_CHECK(e == 0, "bn_act_bwd launch failed: ", cudaGetErrorString((cudaError_t)e));
+  check_launch();
+  return ds;
+}
+
+void multi_sgd_clip_step(torch::Tensor segs, torch::Tensor blocks, torch::Tensor w, c10::optional<torch::Tensor> wc,
+                         torch::Tensor mom, torch::Tensor lr, double mu, double wd, double max_norm,
+                         torch::Tensor scratch) {
+  CHECK_CUDA_T(segs); CHECK_CUDA_T(blocks); CHECK_CUDA_T(w);
+  TORCH_CHECK(segs.scalar_type() == torch::kInt64 && segs.dim() == 2 && segs.size(1) == 4 && segs.is_contiguous());
+  TORCH_CHECK(blocks.scalar_type() == torch::kInt32 && blocks.dim() == 2 && blocks.size(1) == 2);
+  c10::cuda::CUDAGuard guard(w.device());
+  hfl_multi_sgd_clip_step(segs.data_ptr(), blocks.data_ptr(), (int)blocks.size(0), w.data_ptr<float>(),
+                          wc.has_value() ? wc->data_ptr() : nullptr, mom.data_ptr<float>(), lr.data_ptr<float>(),
+                          (float)mu, (float)wd, (float)max_norm, scratch.data_ptr<float>(), cur_stream());
+  check_launch();
+}
+
 // ---- peer memory runtime (cudaMalloc + CUDA IPC) ---------------------------------------------------------
 int64_t peer_alloc(int64_t bytes) {
   void* p = nullptr;
@@ -194,6 +290,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("sgd_clip_step", &sgd_clip_step);
   m.def("masked_ce", &masked_ce);
   m.def("augment", &augment);
+  m.def("bn_act_fwd", &bn_act_fwd);
+  m.def("affine_act", &affine_act);
+  m.def("bn_act_bwd", &bn_act_bwd);
+  m.def("multi_sgd_clip_step", &multi_sgd_clip_step);
+  m.def("ms_chunk", &hfl_ms_chunk);
   m.def("launch_count", &hfl_launch_count);
   m.def("launch_count_add", &hfl_launch_count_add);
   m.def("peer_alloc", &peer_alloc);

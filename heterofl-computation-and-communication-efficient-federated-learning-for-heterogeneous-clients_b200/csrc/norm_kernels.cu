@@ -1,0 +1,391 @@
+// Fused (residual-add +) BatchNorm(batch statistics) + ReLU, forward and backward, one launch each (sm_100a).
+//
+// Reference per norm layer (src/models/resnet.py:44-50): Scaler div, batch_norm (stats + apply), relu, and the
+// residual `out += shortcut` of the previous block are separate kernels in forward, and relu_backward,
+// batch_norm_backward (2 reductions + apply), add (gradient join) again in backward.  Here:
+//
+//   bn_act_fwd : s = x (+ res);  mean/var over the batch;  y = relu((s-mean)*invstd*gamma + beta)
+//   bn_act_bwd : g = (dy (+dy2)) * [y>0];  dbeta = sum g; dgamma = sum g*xhat;
+//                ds = gamma*invstd*(g - dbeta/n - xhat*dgamma/n) (+ dres)
+//
+// One thread-block CLUSTER (<= 8 CTAs, DSMEM all-reduce of the per-channel partials, cluster.sync between the
+// reduction pass and the apply pass) handles one statistics group, so statistics + apply is a single launch
+// instead of 2-4; the second pass re-reads the tile from L2.  `groups` > 1 evaluates ghost batches (the sBN
+// statistics pass: G train-mode batches per launch).  The Scaler is folded into `eps` by the caller.
+// Activations are NHWC bf16, viewed as [rows, C]; C is a power of two (4..4096).
+#include <cooperative_groups.h>
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace hfl {
+
+constexpr int NT = 512;  // threads per CTA
+
+struct Vec8 { uint4 u; };
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __low2float(h[i]); f[2 * i + 1] = __high2float(h[i]); }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+__device__ __forceinline__ float ldp(const __nv_bfloat16* p, int i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ float ldp(const float* p, int i) { return p[i]; }
+__device__ __forceinline__ void stp(__nv_bfloat16* p, int i, float v) { p[i] = __float2bfloat16(v); }
+__device__ __forceinline__ void stp(float* p, int i, float v) { p[i] = v; }
+
+// Reduce per-thread channel partials a[8], b[8] into smem sa[C], sb[C].  Thread t owns channels (8*t+e) % C.
+__device__ __forceinline__ void cta_channel_reduce(float (&a)[8], float (&b)[8], int C, float* sa, float* sb) {
+  const int lane = threadIdx.x & 31;
+  if (C < 8) {  // C == 4: slots e and e+4 are the same channel
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { a[e] += a[e + 4]; b[e] += b[e + 4]; }
+  }
+  const int cols = C >= 8 ? C / 8 : 1;  // lanes l, l+cols, ... own the same channels
+  if (cols < 32) {
+    for (int o = 16; o >= cols; o >>= 1) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        a[e] += __shfl_xor_sync(0xffffffffu, a[e], o);
+        b[e] += __shfl_xor_sync(0xffffffffu, b[e], o);
+      }
+    }
+  }
+  if (cols >= 32 || lane < cols) {
+    const int ne = C < 8 ? C : 8;
+    const int base = (8 * threadIdx.x) % C;
+    for (int e = 0; e < ne; ++e) {
+      atomicAdd(&sa[(base + e) % C], a[e]);
+      atomicAdd(&sb[(base + e) % C], b[e]);
+    }
+  }
+}
+
+// Sum the CTA partials of every CTA in the cluster (DSMEM) into local totals ta[C], tb[C].
+__device__ __forceinline__ void cluster_channel_reduce(cg::cluster_group& cluster, int C, float* sa, float* sb,
+                                                       float* ta, float* tb) {
+  const unsigned K = cluster.num_blocks();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float x = 0.f, y = 0.f;
+    for (unsigned r = 0; r < K; ++r) {
+      x += cluster.map_shared_rank(sa, r)[c];
+      y += cluster.map_shared_rank(sb, r)[c];
+    }
+    ta[c] = x;
+    tb[c] = y;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward
+// grid = (K, G), cluster (K,1,1).  Group g covers rows [g*Mg, (g+1)*Mg); CTA k of the cluster covers a slice.
+// smem: 6*C floats
+// ---------------------------------------------------------------------------------------------------------
+template <typename PT>
+__global__ void __launch_bounds__(NT)
+bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                  __nv_bfloat16* __restrict__ s_out, __nv_bfloat16* __restrict__ y, const PT* __restrict__ gamma,
+                  const PT* __restrict__ beta, float eps, int Mg, int C, int relu, float* __restrict__ mean_out,
+                  float* __restrict__ invstd_out, float* __restrict__ varu_out) {
+  extern __shared__ float smem[];
+  float *sa = smem, *sb = smem + C, *ta = smem + 2 * C, *tb = smem + 3 * C, *sc_a = smem + 4 * C, *sc_b = smem + 5 * C;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int K = cluster.num_blocks(), k = cluster.block_rank(), g = blockIdx.y;
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) smem[c] = 0.f;
+  __syncthreads();
+  // slice of this CTA, in 8-element vectors
+  const long gvec0 = (long)g * Mg * C / 8;
+  const int nvec = Mg * C / 8;
+  const int per = ((nvec + K - 1) / K + NT - 1) / NT * NT;   // multiple of NT => channel ownership is slice-invariant
+  const int v0 = min(k * per, nvec), v1 = min(v0 + per, nvec);
+  const uint4* xv = reinterpret_cast<const uint4*>(x) + gvec0;
+  const uint4* rv = res ? reinterpret_cast<const uint4*>(res) + gvec0 : nullptr;
+  uint4* sv = s_out ? reinterpret_cast<uint4*>(s_out) + gvec0 : nullptr;
+  float a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
+  for (int v = v0 + threadIdx.x; v < v1; v += NT) {
+    float f[8];
+    unpack8(xv[v], f);
+    if (rv) {
+      float r[8];
+      unpack8(rv[v], r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += r[e];
+      const uint4 packed = pack8(f);
+      sv[v] = packed;
+      unpack8(packed, f);   // statistics of the bf16-rounded sum (what a separate add kernel would have produced)
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { a[e] += f[e]; b[e] += f[e] * f[e]; }
+  }
+  cta_channel_reduce(a, b, C, sa, sb);
+  __syncthreads();
+  cluster.sync();
+  cluster_channel_reduce(cluster, C, sa, sb, ta, tb);
+  __syncthreads();
+  const float inv_n = 1.f / (float)Mg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mean = ta[c] * inv_n;
+    const float var = fmaxf(tb[c] * inv_n - mean * mean, 0.f);
+    const float invstd = rsqrtf(var + eps);
+    const float ga = ldp(gamma, c), be = ldp(beta, c);
+    sc_a[c] = invstd * ga;
+    sc_b[c] = be - mean * invstd * ga;
+    if (k == 0) {
+      mean_out[(long)g * C + c] = mean;
+      invstd_out[(long)g * C + c] = invstd;
+      if (varu_out) varu_out[(long)g * C + c] = var * ((float)Mg / fmaxf((float)Mg - 1.f, 1.f));
+    }
+  }
+  __syncthreads();
+  // pass 2: normalise + affine + relu
+  float pa[8], pb[8];
+  {
+    const int base = (8 * threadIdx.x) % C;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { pa[e] = sc_a[(base + e) % C]; pb[e] = sc_b[(base + e) % C]; }
+  }
+  const uint4* in2 = rv ? reinterpret_cast<const uint4*>(sv) : xv;
+  uint4* yv = reinterpret_cast<uint4*>(y) + gvec0;
+  for (int v = v0 + threadIdx.x; v < v1; v += NT) {
+    float f[8];
+    unpack8(in2[v], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      f[e] = f[e] * pa[e] + pb[e];
+      if (relu) f[e] = fmaxf(f[e], 0.f);
+    }
+    yv[v] = pack8(f);
+  }
+  cluster.sync();   // keep this CTA's smem alive until every peer has read it
+}
+
+// eval / generic: y = relu((x + res) * a[c] + b[c]) with precomputed per-channel a, b
+__global__ void affine_act_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                                  __nv_bfloat16* __restrict__ s_out, __nv_bfloat16* __restrict__ y,
+                                  const float* __restrict__ a, const float* __restrict__ b, long nvec, int C, int relu) {
+  const uint4* xv = reinterpret_cast<const uint4*>(x);
+  const uint4* rv = reinterpret_cast<const uint4*>(res);
+  for (long v = blockIdx.x * (long)blockDim.x + threadIdx.x; v < nvec; v += (long)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8(xv[v], f);
+    if (res) {
+      float r[8];
+      unpack8(rv[v], r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += r[e];
+      const uint4 p = pack8(f);
+      reinterpret_cast<uint4*>(s_out)[v] = p;
+      unpack8(p, f);
+    }
+    const int base = (int)((8 * v) % C);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = (base + e) % C;
+      f[e] = f[e] * a[c] + b[c];
+      if (relu) f[e] = fmaxf(f[e], 0.f);
+    }
+    reinterpret_cast<uint4*>(y)[v] = pack8(f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward (one statistics group: the training batch).  grid = (K), cluster (K,1,1).  smem: 6*C floats
+// dy may be a [N, C] tensor broadcast over the HW positions of each sample (hw > 0: global-average-pool grad).
+// ---------------------------------------------------------------------------------------------------------
+template <typename PT>
+__global__ void __launch_bounds__(NT)
+bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
+                  const __nv_bfloat16* __restrict__ dres, const __nv_bfloat16* __restrict__ s,
+                  const float* __restrict__ mean, const float* __restrict__ invstd, const PT* __restrict__ gamma,
+                  const PT* __restrict__ beta, int M, int C, int hw, float dy_scale, int relu,
+                  __nv_bfloat16* __restrict__ ds, PT* __restrict__ dgamma, PT* __restrict__ dbeta) {
+  extern __shared__ float smem[];
+  float *sa = smem, *sb = smem + C, *ta = smem + 2 * C, *tb = smem + 3 * C, *c_m = smem + 4 * C, *c_i = smem + 5 * C;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int K = cluster.num_blocks(), k = cluster.block_rank();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) smem[c] = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { c_m[c] = mean[c]; c_i[c] = invstd[c]; }
+  __syncthreads();
+  const int nvec = M * C / 8;
+  const int per = ((nvec + K - 1) / K + NT - 1) / NT * NT;
+  const int v0 = min(k * per, nvec), v1 = min(v0 + per, nvec);
+  const uint4* sv = reinterpret_cast<const uint4*>(s);
+  const uint4* gv = reinterpret_cast<const uint4*>(dy);
+  const uint4* g2v = reinterpret_cast<const uint4*>(dy2);
+  // per-thread channel constants
+  float pm[8], pi[8], pg[8], pb[8];
+  {
+    const int base = (8 * threadIdx.x) % C;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = (base + e) % C;
+      pm[e] = c_m[c]; pi[e] = c_i[c]; pg[e] = ldp(gamma, c); pb[e] = ldp(beta, c);
+    }
+  }
+  const int vec_per_sample = hw > 0 ? hw * C / 8 : 1;   // vectors per sample when dy is broadcast over HW
+  auto load_g = [&](int v, float (&g)[8]) {
+    if (hw > 0) {
+      // element i of vector v belongs to sample n = v / vec_per_sample, channel (8v+e) % C
+      const int n = v / vec_per_sample;
+      const int base = (int)((8L * v) % C);
+      if (C >= 8) {
+        unpack8(reinterpret_cast<const uint4*>(dy + (long)n * C + base)[0], g);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = __bfloat162float(dy[(long)n * C + (base + e) % C]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] *= dy_scale;
+    } else {
+      unpack8(gv[v], g);
+      if (dy2) {
+        float t[8];
+        unpack8(g2v[v], t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] += t[e];
+      }
+    }
+  };
+  float a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
+  for (int v = v0 + threadIdx.x; v < v1; v += NT) {
+    float x[8], g[8];
+    unpack8(sv[v], x);
+    load_g(v, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xh = (x[e] - pm[e]) * pi[e];
+      const float pre = x[e] * (pi[e] * pg[e]) + (pb[e] - pm[e] * pi[e] * pg[e]);   // same expression as forward
+      const float ge = (!relu || pre > 0.f) ? g[e] : 0.f;
+      a[e] += ge;
+      b[e] += ge * xh;
+    }
+  }
+  cta_channel_reduce(a, b, C, sa, sb);
+  __syncthreads();
+  cluster.sync();
+  cluster_channel_reduce(cluster, C, sa, sb, ta, tb);
+  __syncthreads();
+  if (k == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { stp(dbeta, c, ta[c]); stp(dgamma, c, tb[c]); }
+  }
+  const float inv_n = 1.f / (float)M;
+  float qa[8], qb[8];
+  {
+    const int base = (8 * threadIdx.x) % C;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { qa[e] = ta[(base + e) % C] * inv_n; qb[e] = tb[(base + e) % C] * inv_n; }
+  }
+  const uint4* rv = reinterpret_cast<const uint4*>(dres);
+  uint4* dv = reinterpret_cast<uint4*>(ds);
+  for (int v = v0 + threadIdx.x; v < v1; v += NT) {
+    float x[8], g[8], o[8];
+    unpack8(sv[v], x);
+    load_g(v, g);
+    float r[8];
+    if (dres) unpack8(rv[v], r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xh = (x[e] - pm[e]) * pi[e];
+      const float pre = x[e] * (pi[e] * pg[e]) + (pb[e] - pm[e] * pi[e] * pg[e]);
+      const float ge = (!relu || pre > 0.f) ? g[e] : 0.f;
+      o[e] = pg[e] * pi[e] * (ge - qa[e] - xh * qb[e]);
+      if (dres) o[e] += r[e];
+    }
+    dv[v] = pack8(o);
+  }
+  cluster.sync();
+}
+
+}  // namespace hfl
+
+using namespace hfl;
+
+static int pick_cluster(long elems) {
+  long k = (elems + 65535) / 65536;
+  if (k < 1) k = 1;
+  if (k > 8) k = 8;
+  // power of two cluster sizes only (1,2,4,8)
+  int p = 1;
+  while (p * 2 <= k) p *= 2;
+  return p;
+}
+
+template <typename Kern, typename... Args>
+static cudaError_t launch_cluster(Kern kern, dim3 grid, int cluster_x, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+extern "C" int hfl_bn_act_fwd(const void* x, const void* res, void* s_out, void* y, const void* gamma,
+                              const void* beta, int param_bf16, float eps, int groups, int Mg, int C, int relu,
+                              float* mean_out, float* invstd_out, float* varu_out, cudaStream_t stream) {
+  const int K = pick_cluster((long)Mg * C);
+  const size_t smem = 6 * (size_t)C * sizeof(float);
+  dim3 grid(K, groups);
+  cudaError_t e;
+  if (param_bf16)
+    e = launch_cluster(bn_act_fwd_kernel<__nv_bfloat16>, grid, K, smem, stream, (const __nv_bfloat16*)x,
+                       (const __nv_bfloat16*)res, (__nv_bfloat16*)s_out, (__nv_bfloat16*)y,
+                       (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, eps, Mg, C, relu, mean_out, invstd_out,
+                       varu_out);
+  else
+    e = launch_cluster(bn_act_fwd_kernel<float>, grid, K, smem, stream, (const __nv_bfloat16*)x,
+                       (const __nv_bfloat16*)res, (__nv_bfloat16*)s_out, (__nv_bfloat16*)y, (const float*)gamma,
+                       (const float*)beta, eps, Mg, C, relu, mean_out, invstd_out, varu_out);
+  count_launch();
+  return (int)e;
+}
+
+extern "C" void hfl_affine_act(const void* x, const void* res, void* s_out, void* y, const float* a, const float* b,
+                               long n, int C, int relu, cudaStream_t stream) {
+  const long nvec = n / 8;
+  long blocks = (nvec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  affine_act_kernel<<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res,
+                                                     (__nv_bfloat16*)s_out, (__nv_bfloat16*)y, a, b, nvec, C, relu);
+  count_launch();
+}
+
+extern "C" int hfl_bn_act_bwd(const void* dy, const void* dy2, const void* dres, const void* s, const float* mean,
+                              const float* invstd, const void* gamma, const void* beta, int param_bf16, int M, int C,
+                              int hw, float dy_scale, int relu, void* ds, void* dgamma, void* dbeta,
+                              cudaStream_t stream) {
+  const int K = pick_cluster((long)M * C);
+  const size_t smem = 6 * (size_t)C * sizeof(float);
+  dim3 grid(K);
+  cudaError_t e;
+  if (param_bf16)
+    e = launch_cluster(bn_act_bwd_kernel<__nv_bfloat16>, grid, K, smem, stream, (const __nv_bfloat16*)dy,
+                       (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean, invstd,
+                       (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, M, C, hw, dy_scale, relu,
+                       (__nv_bfloat16*)ds, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta);
+  else
+    e = launch_cluster(bn_act_bwd_kernel<float>, grid, K, smem, stream, (const __nv_bfloat16*)dy,
+                       (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean, invstd,
+                       (const float*)gamma, (const float*)beta, M, C, hw, dy_scale, relu, (__nv_bfloat16*)ds,
+                       (float*)dgamma, (float*)dbeta);
+  count_launch();
+  return (int)e;
+}

@@ -114,3 +114,81 @@ extern "C" void hfl_sgd_clip_step(float* w, void* wc, void* g, int g_is_bf16, fl
   }
   count_launch(2);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Multi-tensor variant: gradients live wherever their producer left them (cuDNN wgrad outputs inside the CUDA-graph
+// pool, fused-norm kernels' dgamma/dbeta, ...) and are described by a segment table
+//     seg[i] = { grad pointer, arena offset, numel, grad-is-bf16 }
+// while w / wc / mom stay flat arenas.  No gradient copy, no accumulate, no zeroing pass.
+// ---------------------------------------------------------------------------------------------------------
+namespace hfl {
+
+struct Seg { const void* g; long off; long n; long bf16; };
+constexpr int MS_CHUNK = 4096;
+
+__device__ __forceinline__ float seg_grad(const Seg& s, long i) {
+  return s.bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(s.g)[i])
+                : reinterpret_cast<const float*>(s.g)[i];
+}
+
+__global__ void __launch_bounds__(256) multi_norm_sq_kernel(const Seg* __restrict__ segs, const int2* __restrict__ blocks,
+                                                            float* __restrict__ scratch) {
+  __shared__ float sm[33];
+  const int2 b = blocks[blockIdx.x];
+  const Seg s = segs[b.x];
+  const long end = min((long)b.y + MS_CHUNK, s.n);
+  float acc = 0.f;
+  for (long i = b.y + threadIdx.x; i < end; i += 256) {
+    const float v = seg_grad(s, i);
+    acc += v * v;
+  }
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) atomicAdd(scratch, acc);
+}
+
+__global__ void __launch_bounds__(256)
+multi_sgd_update_kernel(const Seg* __restrict__ segs, const int2* __restrict__ blocks, float* __restrict__ w,
+                        __nv_bfloat16* __restrict__ wc, float* __restrict__ mom, const float* __restrict__ lr_p,
+                        float mu, float wd, float max_norm, float* __restrict__ scratch) {
+  const float total = sqrtf(*reinterpret_cast<volatile float*>(scratch));
+  const float coef = fminf(1.f, max_norm / (total + 1e-6f));
+  const float lr = *lr_p;
+  const int2 b = blocks[blockIdx.x];
+  const Seg s = segs[b.x];
+  const long end = min((long)b.y + MS_CHUNK, s.n);
+  for (long i = b.y + threadIdx.x; i < end; i += 256) {
+    const long o = s.off + i;
+    const float wv = w[o];
+    const float gg = seg_grad(s, i) * coef + wd * wv;
+    const float mv = mu * mom[o] + gg;
+    const float nw = wv - lr * mv;
+    mom[o] = mv;
+    w[o] = nw;
+    if (wc) wc[o] = __float2bfloat16(nw);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned* cnt = reinterpret_cast<unsigned*>(scratch + 1);
+    const unsigned done = atomicAdd(cnt, 1u);
+    if (done == gridDim.x - 1) {
+      scratch[0] = 0.f;
+      *cnt = 0u;
+      scratch[2] = total;
+    }
+  }
+}
+
+}  // namespace hfl
+
+extern "C" int hfl_ms_chunk() { return hfl::MS_CHUNK; }
+
+extern "C" void hfl_multi_sgd_clip_step(const void* segs, const void* blocks, int n_blocks, float* w, void* wc,
+                                        float* mom, const float* lr, float mu, float wd, float max_norm,
+                                        float* scratch, cudaStream_t stream) {
+  if (n_blocks <= 0) return;
+  hfl::multi_norm_sq_kernel<<<n_blocks, 256, 0, stream>>>((const hfl::Seg*)segs, (const int2*)blocks, scratch);
+  hfl::multi_sgd_update_kernel<<<n_blocks, 256, 0, stream>>>((const hfl::Seg*)segs, (const int2*)blocks, w,
+                                                            (__nv_bfloat16*)wc, mom, lr, mu, wd, max_norm, scratch);
+  hfl::count_launch(2);
+}

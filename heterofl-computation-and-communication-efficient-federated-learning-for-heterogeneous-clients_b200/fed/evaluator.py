@@ -20,6 +20,8 @@ import torch.nn.functional as F
 from ..data.datasets import LMData, VisionData
 from ..data.pipeline import VisionAugment, lm_windows
 from ..models import Model
+from ..models.fused_resnet import FusedResNet
+from ..ops import cuda as cu
 from ..ops.nn import NormCtx
 from ..parallel.dist import DistInfo, all_reduce_sum
 
@@ -31,6 +33,10 @@ class Evaluator:
         self.device, self.dtype = info.device, compute_dtype
         self.stats_chunk_groups, self.test_chunk = stats_chunk_groups, test_chunk
         self._aug = {}
+        self.fused = None
+        if self.device.type == "cuda" and compute_dtype == torch.bfloat16 and cu.available() \
+                and cfg.get("fused", True) and FusedResNet.eligible(model.spec):
+            self.fused = FusedResNet(model.spec, model.scale_rate)
 
     def _params(self, global_arena: torch.Tensor) -> Dict[str, torch.Tensor]:
         wc = global_arena if self.dtype == torch.float32 else global_arena.to(self.dtype)
@@ -67,13 +73,16 @@ class Evaluator:
                 continue
             idx = perm_d[g0 * B:g1 * B]
             x = aug(imgs_dev, idx, params[g0 * B:g1 * B].contiguous())
-            self.model.forward(P, {"img": x}, ctx, None, want_score="raw")
+            if self.fused is not None:
+                self.fused.forward_stats(P, x, ctx)
+            else:
+                self.model.forward(P, {"img": x}, ctx, None, want_score="raw")
             ctx.n_groups += g1 - g0
         if N % B and self.info.rank == 0:
             idx = perm_d[n_full * B:]
             x = aug(imgs_dev, idx, params[n_full * B:].contiguous())
             ctx.group = int(idx.numel())
-            self.model.forward(P, {"img": x}, ctx, None, want_score="raw")
+            self.model.forward(P, {"img": x}, ctx, None, want_score="raw")   # odd-sized tail: generic path
             ctx.n_groups += 1
         # merge across ranks: one flat vector [sum_mean..., sum_var..., n_groups]
         widths = [w for _, w in bn]
@@ -91,7 +100,6 @@ class Evaluator:
         for name, w in bn:
             running[name] = (flat[off:off + w] / n, flat[off + w:off + 2 * w] / n)
             off += 2 * w
-        self.last_num_batches = int(flat[-1].item()) if False else None
         return running
 
     # -- test --------------------------------------------------------------------------------------------
@@ -102,6 +110,7 @@ class Evaluator:
         """``owner_dev[i]`` = user whose test split holds sample i (-1: none); ``user_masks_dev [U, classes]``."""
         P = self._params(global_arena)
         ctx = NormCtx("eval", running=running)
+        ab = self.fused.eval_affine(P, running) if self.fused is not None else None
         aug = self._augment(ds, False)
         N = imgs_dev.shape[0]
         acc = torch.zeros(6, dtype=torch.float64, device=self.device)
@@ -112,7 +121,10 @@ class Evaluator:
             idx = torch.arange(s, e, device=self.device)
             x = aug(imgs_dev, idx, None)
             y = labels_dev[s:e]
-            z = self.model.forward(P, {"img": x}, ctx, None, want_score="raw")["logits"]
+            if ab is not None:
+                z = self.fused.forward_eval(P, x, ab)
+            else:
+                z = self.model.forward(P, {"img": x}, ctx, None, want_score="raw")["logits"]
             acc[3] += F.cross_entropy(z, y, reduction="sum").double()
             acc[4] += (z.argmax(1) == y).sum()
             acc[5] += e - s

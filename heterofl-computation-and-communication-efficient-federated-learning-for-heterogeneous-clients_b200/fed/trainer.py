@@ -27,6 +27,7 @@ import torch
 from ..data.datasets import LMData, VisionData
 from ..data.pipeline import VisionAugment, lm_windows
 from ..models import Model
+from ..models.fused_resnet import FusedResNet
 from ..ops import cuda as cu
 from ..ops.nn import NormCtx
 from ..utils.metrics import DeviceMeter
@@ -74,6 +75,22 @@ class TrainSlot:
         self.label_rows = max([model.layout.entries[p.name].shape[0] for p in model.spec.params if p.label_rows] + [1])
         self.mask_t = torch.ones(self.label_rows, dtype=torch.uint8, device=device)
         self.use_mask = bool(cfg["mask"])
+        # manual-backward fused path (bf16 + kernels): no autograd graph, no gradient arena traffic
+        self.fused = None
+        if self.use_kernels and self.mixed and compute_dtype == torch.bfloat16 and cfg.get("fused", True) \
+                and FusedResNet.eligible(model.spec):
+            self.fused = FusedResNet(model.spec, model.scale_rate)
+            self.Pv = model.layout.views(self.wc)
+            self._names = list(model.layout.entries.keys())
+            chunk = cu.C().ms_chunk()
+            blk = []
+            for ti, name in enumerate(self._names):
+                blk += [(ti, s0) for s0 in range(0, model.layout.entries[name].numel, chunk)]
+            self.blk_tab = torch.tensor(blk, dtype=torch.int32, device=device).reshape(-1, 2)
+            self.seg_tab = torch.zeros(len(self._names), 4, dtype=torch.int64, device=device)
+            self._grads = None
+            self._capturing = False
+            self._captured_segs = None
         self.graphs: Dict = {}
         self.graph_kernels: Dict = {}
         self.step_ctr = torch.zeros(1, dtype=torch.int64, device=device)
@@ -98,7 +115,37 @@ class TrainSlot:
         self.g.zero_()
 
     # -- one optimisation step -----------------------------------------------------------------------------
+    def _seg_rows(self):
+        rows = []
+        lay = self.model.layout
+        for name in self._names:
+            g = self._grads[name]
+            e = lay.entries[name]
+            if g.dim() == 4:
+                dense = g.permute(0, 2, 3, 1).is_contiguous() if lay.channels_last else g.is_contiguous()
+            else:
+                dense = g.is_contiguous()
+            if not dense:   # re-lay into the arena's physical order (not expected on the cuDNN NHWC path)
+                g = g.contiguous(memory_format=torch.channels_last if (g.dim() == 4 and lay.channels_last)
+                                 else torch.contiguous_format)
+                self._grads[name] = g
+            assert g.numel() == e.numel, name
+            rows.append((g.data_ptr(), e.offset, e.numel, 1 if g.dtype == torch.bfloat16 else 0))
+        return rows
+
     def _opt_step(self) -> None:
+        if self.fused is not None:
+            rows = self._seg_rows()
+            if self._capturing:
+                self._captured_segs = rows          # pointers are fixed inside the graph pool: table filled after capture
+            else:
+                self.seg_tab.copy_(torch.tensor(rows, dtype=torch.int64), non_blocking=False)
+                self._seg_active = None
+            cu.C().multi_sgd_clip_step(self.seg_tab, self.blk_tab, self.w, self.wc, self.mom, self.lr_t,
+                                       self.momentum, self.wd, self.max_norm, self.scratch)
+            if not self._capturing:
+                self._grads = None
+            return
         if self.use_kernels:
             cu.sgd_clip_step(self.w, self.wc if self.mixed else None, self.g, self.mom, self.lr_t, self.momentum,
                              self.wd, self.max_norm, self.scratch)
@@ -107,6 +154,9 @@ class TrainSlot:
 
     def _fwd_bwd(self, inp: Dict, n_weight: float) -> None:
         mask = self.mask_t if self.use_mask else None
+        if self.fused is not None:
+            _, self._grads = self.fused.train_step(self.Pv, inp["img"], inp["label"], mask, (self.meter.buf, n_weight))
+            return
         if self.use_kernels:
             inp = dict(inp)
             inp["_meter"] = (self.meter.buf, n_weight)
@@ -227,8 +277,18 @@ class TrainSlot:
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         k0 = cu.launch_count()
+        if self.fused is not None:
+            self._capturing = True
         with torch.cuda.graph(graph, stream=s):
             step_fn()
+        if self.fused is not None:
+            self._capturing = False
+            # keep the captured gradient tensors alive (their addresses are baked into the segment table)
+            self._graph_keepalive = getattr(self, "_graph_keepalive", {})
+            self._graph_keepalive[key] = self._grads
+            self._grads = None
+            self._seg_for = getattr(self, "_seg_for", {})
+            self._seg_for[key] = torch.tensor(self._captured_segs, dtype=torch.int64)
         self.graph_kernels[key] = cu.launch_count() - k0
         self.graphs[key] = graph
         torch.cuda.synchronize(self.device)
@@ -241,6 +301,10 @@ class TrainSlot:
         self.scratch.zero_()
 
     def _replay(self, key) -> None:
+        if self.fused is not None and getattr(self, "_seg_active", None) != key:
+            # (re)bind the optimiser's segment table to this graph's gradient addresses
+            self.seg_tab.copy_(self._seg_for[key])
+            self._seg_active = key
         self.graphs[key].replay()
         cu.launch_count_add(self.graph_kernels.get(key, 0))
 

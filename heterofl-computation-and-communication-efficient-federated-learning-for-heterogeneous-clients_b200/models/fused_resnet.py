@@ -1,0 +1,167 @@
+"""Pre-activation ResNet train / statistics / eval passes with a hand-scheduled backward.
+
+Same network as :func:`hfl_b200.models.vision.resnet_forward` (reference ``src/models/resnet.py:140-158``) but the
+step is written as an explicit sequence of fused ops instead of an autograd graph:
+
+* ``bn_act_fwd`` = previous block's residual add + BatchNorm statistics + apply + ReLU in ONE launch
+  (``csrc/norm_kernels.cu``); ``bn_act_bwd`` = gradient join + ReLU mask + BN backward reductions + apply in ONE;
+* convolutions go through the library (cuDNN) for now -- ``ops.fused.conv_fwd / conv_bwd`` are the seams where the
+  tcgen05 implicit-GEMM kernels plug in;
+* weight gradients are consumed where their producer leaves them (segment table of the multi-tensor optimiser), so
+  there is no AccumulateGrad add, no gradient copy and no zero-fill pass.
+
+Kernel launches per train step drop from ~300 (autograd path) to ~130.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from ..ops import cuda as cu
+from ..ops import fused as fo
+from ..ops.nn import BN_EPS, NormCtx
+from ..plan.spec import ModelSpec
+
+
+class FusedResNet:
+    def __init__(self, spec: ModelSpec, scale_rate: float):
+        assert spec.family == "resnet" and spec.meta["norm"] == "bn" and spec.meta["kind"] == "block"
+        self.spec, self.blocks = spec, spec.meta["blocks"]
+        self.scale_rate = float(scale_rate)
+
+    @staticmethod
+    def eligible(spec: ModelSpec) -> bool:
+        return spec.family == "resnet" and spec.meta.get("norm") == "bn" and spec.meta.get("kind") == "block"
+
+    # ---------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def train_step(self, P: Dict[str, torch.Tensor], x: torch.Tensor, y: torch.Tensor,
+                   label_mask: Optional[torch.Tensor], meter=None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+        """One forward+backward.  Returns ``(loss, grads)`` with a gradient tensor for every parameter."""
+        s_rate = self.scale_rate
+        eps = BN_EPS * s_rate * s_rate          # Scaler folded into epsilon
+        G: Dict[str, torch.Tensor] = {}
+        saved = []
+        c0 = fo.conv_fwd(x, P["conv1.weight"], 1, 1)
+        cur, res = c0, None                     # block input is s = cur (+ res)
+        for blk in self.blocks:
+            pre, stride = blk["prefix"], blk["stride"]
+            s_in, o1, m1, i1, _ = fo.bn_act_fwd(cur, res, P[pre + ".n1.weight"], P[pre + ".n1.bias"], eps)
+            sc = fo.conv_fwd(o1, P[pre + ".shortcut.weight"], stride, 0) if blk["shortcut"] else s_in
+            c1 = fo.conv_fwd(o1, P[pre + ".conv1.weight"], stride, 1)
+            _, o2, m2, i2, _ = fo.bn_act_fwd(c1, None, P[pre + ".n2.weight"], P[pre + ".n2.bias"], eps)
+            c2 = fo.conv_fwd(o2, P[pre + ".conv2.weight"], 1, 1)
+            saved.append((blk, s_in, o1, m1, i1, c1, o2, m2, i2))
+            cur, res = c2, sc
+        s4, y4, m4, i4, _ = fo.bn_act_fwd(cur, res, P["n4.weight"], P["n4.bias"], eps)
+        # ---- head: global average pool -> linear -> masked CE (forward + backward) ----
+        N, C, H, W = y4.shape
+        pooled = y4.mean(dim=(2, 3))
+        Wl, bl = P["linear.weight"], P["linear.bias"]
+        logits = F.linear(pooled, Wl, bl)
+        loss, dlogits = self._ce(logits, y, label_mask, meter)
+        G["linear.weight"] = dlogits.t().mm(pooled)
+        G["linear.bias"] = dlogits.sum(0)
+        dpooled = dlogits.mm(Wl)                                  # [N, C]
+        # ---- backward ----
+        G["n4.weight"], G["n4.bias"] = torch.empty_like(P["n4.weight"]), torch.empty_like(P["n4.bias"])
+        ds = fo.bn_act_bwd(dpooled, None, None, s4, m4, i4, P["n4.weight"], P["n4.bias"], G["n4.weight"], G["n4.bias"],
+                           hw=H * W, dy_scale=1.0 / (H * W))
+        for (blk, s_in, o1, m1, i1, c1, o2, m2, i2) in reversed(saved):
+            pre, stride = blk["prefix"], blk["stride"]
+            # ds = grad wrt block output (= c2 + sc)
+            do2, G[pre + ".conv2.weight"] = fo.conv_bwd(ds, o2, P[pre + ".conv2.weight"], 1, 1)
+            G[pre + ".n2.weight"] = torch.empty_like(P[pre + ".n2.weight"])
+            G[pre + ".n2.bias"] = torch.empty_like(P[pre + ".n2.bias"])
+            dc1 = fo.bn_act_bwd(do2, None, None, c1, m2, i2, P[pre + ".n2.weight"], P[pre + ".n2.bias"],
+                                G[pre + ".n2.weight"], G[pre + ".n2.bias"])
+            do1, G[pre + ".conv1.weight"] = fo.conv_bwd(dc1, o1, P[pre + ".conv1.weight"], stride, 1)
+            G[pre + ".n1.weight"] = torch.empty_like(P[pre + ".n1.weight"])
+            G[pre + ".n1.bias"] = torch.empty_like(P[pre + ".n1.bias"])
+            if blk["shortcut"]:
+                do1b, G[pre + ".shortcut.weight"] = fo.conv_bwd(ds, o1, P[pre + ".shortcut.weight"], stride, 0)
+                ds = fo.bn_act_bwd(do1, do1b, None, s_in, m1, i1, P[pre + ".n1.weight"], P[pre + ".n1.bias"],
+                                   G[pre + ".n1.weight"], G[pre + ".n1.bias"])
+            else:
+                ds = fo.bn_act_bwd(do1, None, ds, s_in, m1, i1, P[pre + ".n1.weight"], P[pre + ".n1.bias"],
+                                   G[pre + ".n1.weight"], G[pre + ".n1.bias"])
+        _, G["conv1.weight"] = fo.conv_bwd(ds, x, P["conv1.weight"], 1, 1, need_dx=False)
+        return loss, G
+
+    @staticmethod
+    def _ce(logits, y, label_mask, meter):
+        if logits.is_cuda and cu.available():
+            mt, nw = (meter if meter is not None else (None, float(logits.shape[0])))
+            mask = label_mask
+            if mask is not None and mask.dtype != torch.uint8:
+                mask = mask.to(torch.uint8)
+            loss, dl = cu.C().masked_ce(logits.contiguous(), y.contiguous(), mask, float(nw), mt, True)
+            return loss.view(()), dl
+        z = logits if logits.dtype == torch.float64 else logits.float()
+        if label_mask is not None:
+            keep = label_mask.to(z.device).bool().view(1, -1)
+            z = z.masked_fill(~keep, 0.0)
+        lse = torch.logsumexp(z, dim=1)
+        loss = (lse - z.gather(1, y.view(-1, 1)).squeeze(1)).mean()
+        dl = torch.softmax(z, dim=1)
+        dl[torch.arange(z.shape[0]), y] -= 1.0
+        dl = dl / z.shape[0]
+        if label_mask is not None:
+            dl = dl * keep
+        return loss, dl.to(logits.dtype)
+
+    # ---------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_stats(self, P: Dict[str, torch.Tensor], x: torch.Tensor, ctx: NormCtx) -> None:
+        """sBN statistics pass over ``groups = N // ctx.group`` ghost batches; accumulates into ``ctx.acc``."""
+        s_rate = self.scale_rate
+        eps = BN_EPS * s_rate * s_rate
+        Gn = max(x.shape[0] // ctx.group, 1)
+
+        def acc(name, mean, varu):
+            m, v = mean.sum(0), varu.sum(0)
+            if s_rate != 1.0:
+                m, v = m / s_rate, v / (s_rate * s_rate)
+            if name in ctx.acc:
+                ctx.acc[name][0].add_(m)
+                ctx.acc[name][1].add_(v)
+            else:
+                ctx.acc[name] = (m.clone(), v.clone())
+
+        cur, res = fo.conv_fwd(x, P["conv1.weight"], 1, 1), None
+        for blk in self.blocks:
+            pre, stride = blk["prefix"], blk["stride"]
+            s_in, o1, m1, _, v1 = fo.bn_act_fwd(cur, res, P[pre + ".n1.weight"], P[pre + ".n1.bias"], eps, Gn)
+            acc(pre + ".n1", m1, v1)
+            sc = fo.conv_fwd(o1, P[pre + ".shortcut.weight"], stride, 0) if blk["shortcut"] else s_in
+            c1 = fo.conv_fwd(o1, P[pre + ".conv1.weight"], stride, 1)
+            _, o2, m2, _, v2 = fo.bn_act_fwd(c1, None, P[pre + ".n2.weight"], P[pre + ".n2.bias"], eps, Gn)
+            acc(pre + ".n2", m2, v2)
+            cur, res = fo.conv_fwd(o2, P[pre + ".conv2.weight"], 1, 1), sc
+        _, _, m4, _, v4 = fo.bn_act_fwd(cur, res, P["n4.weight"], P["n4.bias"], eps, Gn)
+        acc("n4", m4, v4)
+
+    @staticmethod
+    def eval_affine(P: Dict[str, torch.Tensor], running: Dict) -> Dict[str, Tuple[torch.Tensor, torch.Tensor]]:
+        """Per-BN ``(a, b)`` with ``y = x*a + b`` from running statistics (computed once per round)."""
+        out = {}
+        for name, (rm, rv) in running.items():
+            a = P[name + ".weight"].float() * torch.rsqrt(rv.float() + BN_EPS)
+            out[name] = (a.contiguous(), (P[name + ".bias"].float() - rm.float() * a).contiguous())
+        return out
+
+    @torch.no_grad()
+    def forward_eval(self, P: Dict[str, torch.Tensor], x: torch.Tensor, ab: Dict) -> torch.Tensor:
+        """Eval-mode logits (running statistics, Scaler = identity)."""
+        cur, res = fo.conv_fwd(x, P["conv1.weight"], 1, 1), None
+        for blk in self.blocks:
+            pre, stride = blk["prefix"], blk["stride"]
+            s_in, o1 = fo.affine_act(cur, res, *ab[pre + ".n1"])
+            sc = fo.conv_fwd(o1, P[pre + ".shortcut.weight"], stride, 0) if blk["shortcut"] else s_in
+            c1 = fo.conv_fwd(o1, P[pre + ".conv1.weight"], stride, 1)
+            _, o2 = fo.affine_act(c1, None, *ab[pre + ".n2"])
+            cur, res = fo.conv_fwd(o2, P[pre + ".conv2.weight"], 1, 1), sc
+        _, y4 = fo.affine_act(cur, res, *ab["n4"])
+        return F.linear(y4.mean(dim=(2, 3)), P["linear.weight"], P["linear.bias"]).float()

@@ -1,0 +1,115 @@
+"""Fused building blocks of the manual-backward training path (GPU: ``csrc/norm_kernels.cu``; CPU: torch oracle).
+
+Activations are logical ``[N, C, H, W]`` tensors with channels-last strides (physically ``[N*H*W, C]``).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import cuda as cu
+
+
+def _use_kernels(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dtype == torch.bfloat16 and cu.available()
+
+
+def _f(t: torch.Tensor) -> torch.Tensor:
+    """working precision of the torch oracle paths: fp32 for 16-bit inputs, unchanged otherwise (fp64 stays fp64)."""
+    return t.float() if t.dtype in (torch.bfloat16, torch.float16) else t
+
+
+def _rows(x: torch.Tensor) -> torch.Tensor:
+    """physical [M, C] view of a channels-last activation (or of a plain [N, C] matrix)."""
+    if x.dim() == 4:
+        return x.permute(0, 2, 3, 1).reshape(-1, x.shape[1])
+    return x.reshape(-1, x.shape[-1])
+
+
+def bn_act_fwd(x: torch.Tensor, res: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+               groups: int = 1, relu: bool = True):
+    """``s = x (+ res)``; per-group batch statistics; ``y = relu(bn(s))``.
+
+    Returns ``(s, y, mean[G,C], invstd[G,C], var_unbiased[G,C])`` (``s is x`` when ``res`` is None).
+    """
+    C = x.shape[1]
+    if _use_kernels(x):
+        s, y, mean, invstd, varu = cu.C().bn_act_fwd(x, res, gamma, beta, float(eps), int(groups), int(C), bool(relu))
+        return (s if res is not None else x), y, mean, invstd, varu
+    s = x if res is None else (x + res)
+    N = s.shape[0]
+    sf = _f(s).reshape(groups, N // groups, C, -1)
+    var, mean = torch.var_mean(sf, dim=(1, 3), unbiased=False, keepdim=True)
+    invstd = torch.rsqrt(var + eps)
+    y = (sf - mean) * invstd * _f(gamma).view(1, 1, C, 1) + _f(beta).view(1, 1, C, 1)
+    if relu:
+        y = F.relu(y)
+    y = y.reshape(s.shape).to(s.dtype)
+    if s.dim() == 4 and s.is_cuda:
+        y = y.contiguous(memory_format=torch.channels_last)
+    n = sf.shape[1] * sf.shape[3]
+    return s, y, mean.reshape(groups, C), invstd.reshape(groups, C), (var * (n / max(n - 1, 1))).reshape(groups, C)
+
+
+def affine_act(x: torch.Tensor, res: Optional[torch.Tensor], a: torch.Tensor, b: torch.Tensor, relu: bool = True):
+    """Eval-mode norm: ``s = x (+ res)``, ``y = relu(s * a[c] + b[c])``."""
+    C = x.shape[1]
+    if _use_kernels(x):
+        s, y = cu.C().affine_act(x, res, a, b, int(C), bool(relu))
+        return (s if res is not None else x), y
+    s = x if res is None else (x + res)
+    shape = (1, C) + (1,) * (s.dim() - 2)
+    y = _f(s) * a.view(shape) + b.view(shape)
+    if relu:
+        y = F.relu(y)
+    return s, y.to(s.dtype)
+
+
+def bn_act_bwd(dy: torch.Tensor, dy2: Optional[torch.Tensor], dres: Optional[torch.Tensor], s: torch.Tensor,
+               mean: torch.Tensor, invstd: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+               dgamma: torch.Tensor, dbeta: torch.Tensor, hw: int = 0, dy_scale: float = 1.0,
+               relu: bool = True) -> torch.Tensor:
+    """Backward of ``y = relu(bn(s))`` for one statistics group.  ``dy`` is the gradient w.r.t. ``y`` (``hw > 0``:
+    ``dy`` is ``[N, C]`` and is broadcast over the ``hw`` positions of every sample, scaled by ``dy_scale``);
+    ``dy2`` is an optional second gradient w.r.t. ``y``; ``dres`` an optional gradient w.r.t. ``s`` arriving through
+    the identity path.  Writes ``dgamma``/``dbeta`` in place, returns ``ds``."""
+    C = s.shape[1]
+    if _use_kernels(s):
+        return cu.C().bn_act_bwd(dy, dy2, dres, s, mean.reshape(-1), invstd.reshape(-1), gamma, beta, dgamma, dbeta,
+                                 int(C), int(hw), float(dy_scale), bool(relu))
+    shape = (1, C) + (1,) * (s.dim() - 2)
+    sf = _f(s)
+    m, iv = mean.reshape(shape).float(), invstd.reshape(shape).float()
+    ga, be = _f(gamma).view(shape), _f(beta).view(shape)
+    xh = (sf - m) * iv
+    if hw > 0:
+        g = (_f(dy) * dy_scale).view(dy.shape[0], C, *([1] * (s.dim() - 2))).expand_as(sf)
+    else:
+        g = _f(dy) if dy2 is None else _f(dy) + _f(dy2)
+    if relu:
+        g = g * ((xh * ga + be) > 0)
+    red = [d for d in range(s.dim()) if d != 1]
+    sb, sg = g.sum(red), (g * xh).sum(red)
+    n = sf.numel() // C
+    ds = ga * iv * (g - sb.view(shape) / n - xh * sg.view(shape) / n)
+    if dres is not None:
+        ds = ds + _f(dres)
+    dgamma.copy_(sg.to(dgamma.dtype))
+    dbeta.copy_(sb.to(dbeta.dtype))
+    ds = ds.to(s.dtype)
+    if ds.dim() == 4 and ds.is_cuda:
+        ds = ds.contiguous(memory_format=torch.channels_last)
+    return ds
+
+
+def conv_fwd(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> torch.Tensor:
+    return F.conv2d(x, w, None, stride, pad)
+
+
+def conv_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int, pad: int, need_dx: bool = True):
+    """(dx | None, dw) through the library convolution backward (cuDNN dgrad + wgrad)."""
+    dx, dw, _ = torch.ops.aten.convolution_backward(dy, x, w, None, (stride, stride), (pad, pad), (1, 1), False,
+                                                    (0, 0), 1, (need_dx, True, False))
+    return dx, dw

@@ -119,7 +119,7 @@ def masked_cross_entropy(logits: torch.Tensor, target: torch.Tensor, label_mask:
             if meter is not None:
                 return cu.masked_ce(logits, target, label_mask, meter[1], meter[0])
             return cu.masked_ce(logits, target, label_mask)
-    z = logits.float()
+    z = logits if logits.dtype == torch.float64 else logits.float()
     if label_mask is not None:
         z = z.masked_fill(label_mask.to(z.device).bool().logical_not().view(1, -1), 0.0)
     return F.cross_entropy(z, target)

@@ -94,6 +94,36 @@ def test_sgd_clip_step(gdtype):
         assert float(scratch[0]) == 0.0 and float(scratch[1]) == 0.0
 
 
+def test_multi_tensor_sgd_matches_flat():
+    cu = _cu()
+    from hfl_b200.fed.trainer import sgd_clip_step_torch
+    dev = torch.device("cuda")
+    sizes = [8 * 37, 4096 * 3 + 8, 16, 8 * 1001]
+    offs, n = [], 0
+    for sz in sizes:
+        offs.append(n)
+        n += sz
+    w = torch.randn(n, device=dev)
+    mom = torch.randn(n, device=dev) * 0.1
+    grads = [(torch.randn(sz, device=dev) * 0.05).to(torch.bfloat16 if i % 2 == 0 else torch.float32)
+             for i, sz in enumerate(sizes)]
+    gflat = torch.cat([g.float() for g in grads])
+    w_ref, m_ref = w.clone(), mom.clone()
+    wc_ref = torch.zeros(n, device=dev, dtype=torch.bfloat16)
+    sgd_clip_step_torch(w_ref, wc_ref, gflat.clone(), m_ref, 0.1, 0.9, 5e-4, 1.0)
+    chunk = cu.C().ms_chunk()
+    blk = [(i, s0) for i, sz in enumerate(sizes) for s0 in range(0, sz, chunk)]
+    seg = torch.tensor([(g.data_ptr(), o, g.numel(), 1 if g.dtype == torch.bfloat16 else 0)
+                        for g, o in zip(grads, offs)], dtype=torch.int64, device=dev)
+    wc = torch.zeros(n, device=dev, dtype=torch.bfloat16)
+    scratch = torch.zeros(4, device=dev)
+    cu.C().multi_sgd_clip_step(seg, torch.tensor(blk, dtype=torch.int32, device=dev).reshape(-1, 2), w, wc, mom,
+                               torch.tensor([0.1], device=dev), 0.9, 5e-4, 1.0, scratch)
+    torch.cuda.synchronize()
+    assert torch.allclose(w, w_ref, atol=1e-6, rtol=1e-5) and torch.allclose(mom, m_ref, atol=1e-6, rtol=1e-5)
+    assert torch.equal(wc, w.bfloat16()) and float(scratch[0]) == 0.0
+
+
 @pytest.mark.parametrize("rows,V,dtype,masked", [(10, 10, torch.float32, True), (10, 10, torch.bfloat16, False),
                                                   (64, 33278, torch.bfloat16, True), (37, 1000, torch.float32, True)])
 def test_masked_ce(rows, V, dtype, masked):
