@@ -29,6 +29,7 @@ for rate in (1.0, 0.0625):
     g = slot.train_vision(img, lab, aug, 1, 10)
     for _ in range(5):
         next(g)
+    print("fused" if slot.fused is not None else "autograd", file=sys.stderr)
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         next(g)

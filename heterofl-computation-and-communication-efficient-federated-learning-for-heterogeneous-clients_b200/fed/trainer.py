@@ -67,7 +67,10 @@ class TrainSlot:
         self.is_cuda = self.device.type == "cuda"
         self.use_kernels = self.is_cuda and cu.available()
         self.use_graph = bool(use_graph and self.is_cuda)
-        self.stream = torch.cuda.Stream(device=device) if self.is_cuda else None
+        # wider sub-networks sit on the round's critical path (their steps are the longest): give their streams
+        # scheduling priority so the narrow clients fill the gaps instead of delaying them
+        prio = -1 if model.rate >= 0.5 else 0
+        self.stream = torch.cuda.Stream(device=device, priority=prio) if self.is_cuda else None
         self.lr_t = torch.zeros(1, dtype=torch.float32, device=device)
         self.scratch = torch.zeros(4, dtype=torch.float32, device=device)
         self.momentum, self.wd = float(cfg["momentum"]), float(cfg["weight_decay"])
