@@ -30,6 +30,8 @@ int hfl_bn_act_bwd(const void*, const void*, const void*, const void*, const flo
 int hfl_ms_chunk();
 void hfl_multi_sgd_clip_step(const void*, const void*, int, float*, void*, float*, const float*, float, float, float,
                              float*, cudaStream_t);
+int hfl_gemm_bf16_tn(const void*, int, const void*, int, void*, int, int, const float*, float, int, int, int, int,
+                     cudaStream_t);
 long hfl_launch_count();
 void hfl_launch_count_add(long);
 void hfl_peer_barrier(const void*, int, int, unsigned, int*, cudaStream_t);
@@ -239,6 +241,32 @@ void multi_sgd_clip_step(torch::Tensor segs, torch::Tensor blocks, torch::Tensor
   check_launch();
 }
 
+// ---- tcgen05 GEMM ----------------------------------------------------------------------------------------
+// y[M,N] = act(alpha * x[M,K] @ w[N,K]^T + bias)   (x, w bf16 with K contiguous; bias fp32; y bf16 or fp32)
+torch::Tensor gemm_bf16_tn(torch::Tensor x, torch::Tensor w, c10::optional<torch::Tensor> bias, double alpha,
+                           bool gelu, bool out_fp32) {
+  CHECK_CUDA_T(x); CHECK_CUDA_T(w);
+  TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1), "gemm_bf16_tn: shape mismatch");
+  TORCH_CHECK(x.scalar_type() == torch::kBFloat16 && w.scalar_type() == torch::kBFloat16);
+  TORCH_CHECK(x.stride(1) == 1 && w.stride(1) == 1, "gemm_bf16_tn: K must be contiguous");
+  const int64_t M = x.size(0), K = x.size(1), N = w.size(0);
+  TORCH_CHECK(K % 8 == 0 && x.stride(0) % 8 == 0 && w.stride(0) % 8 == 0, "gemm_bf16_tn: 16-byte row alignment");
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(x.data_ptr()) & 15) == 0 && (reinterpret_cast<uintptr_t>(w.data_ptr()) & 15) == 0);
+  const float* bp = nullptr;
+  torch::Tensor bf;
+  if (bias.has_value()) {
+    bf = bias->scalar_type() == torch::kFloat32 ? bias->contiguous() : bias->to(torch::kFloat32).contiguous();
+    TORCH_CHECK(bf.numel() == N);
+    bp = bf.data_ptr<float>();
+  }
+  c10::cuda::CUDAGuard guard(x.device());
+  auto y = torch::empty({M, N}, torch::TensorOptions().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16).device(x.device()));
+  int e = hfl_gemm_bf16_tn(x.data_ptr(), (int)x.stride(0), w.data_ptr(), (int)w.stride(0), y.data_ptr(), (int)N,
+                           out_fp32 ? 0 : 1, bp, (float)alpha, gelu ? 1 : 0, (int)M, (int)N, (int)K, cur_stream());
+  TORCH_CHECK(e == 0, "gemm_bf16_tn failed with code ", e);
+  return y;
+}
+
 // ---- peer memory runtime (cudaMalloc + CUDA IPC) ---------------------------------------------------------
 int64_t peer_alloc(int64_t bytes) {
   void* p = nullptr;
@@ -295,6 +323,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_act_bwd", &bn_act_bwd);
   m.def("multi_sgd_clip_step", &multi_sgd_clip_step);
   m.def("ms_chunk", &hfl_ms_chunk);
+  m.def("gemm_bf16_tn", &gemm_bf16_tn);
   m.def("launch_count", &hfl_launch_count);
   m.def("launch_count_add", &hfl_launch_count_add);
   m.def("peer_alloc", &peer_alloc);

@@ -87,43 +87,75 @@ __device__ __forceinline__ void cluster_channel_reduce(cg::cluster_group& cluste
 // grid = (K, G), cluster (K,1,1).  Group g covers rows [g*Mg, (g+1)*Mg); CTA k of the cluster covers a slice.
 // smem: 6*C floats
 // ---------------------------------------------------------------------------------------------------------
-template <typename PT>
+template <typename PT, int NV>
 __global__ void __launch_bounds__(NT)
 bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                   __nv_bfloat16* __restrict__ s_out, __nv_bfloat16* __restrict__ y, const PT* __restrict__ gamma,
                   const PT* __restrict__ beta, float eps, int Mg, int C, int relu, float* __restrict__ mean_out,
                   float* __restrict__ invstd_out, float* __restrict__ varu_out) {
+  // NV > 0: the CTA's slice (NV vectors per thread) stays in registers between the statistics pass and the apply
+  //         pass -- one global read, one write, all loads in flight at once.
+  // NV == 0: looping fallback for tensors larger than 16 CTAs x 512 threads x 10 vectors (second pass re-reads L2).
   extern __shared__ float smem[];
   float *sa = smem, *sb = smem + C, *ta = smem + 2 * C, *tb = smem + 3 * C, *sc_a = smem + 4 * C, *sc_b = smem + 5 * C;
   cg::cluster_group cluster = cg::this_cluster();
   const int K = cluster.num_blocks(), k = cluster.block_rank(), g = blockIdx.y;
   for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) smem[c] = 0.f;
   __syncthreads();
-  // slice of this CTA, in 8-element vectors
   const long gvec0 = (long)g * Mg * C / 8;
   const int nvec = Mg * C / 8;
-  const int per = ((nvec + K - 1) / K + NT - 1) / NT * NT;   // multiple of NT => channel ownership is slice-invariant
+  const int per = NV > 0 ? NV * NT : ((nvec + K - 1) / K + NT - 1) / NT * NT;   // multiple of NT
   const int v0 = min(k * per, nvec), v1 = min(v0 + per, nvec);
   const uint4* xv = reinterpret_cast<const uint4*>(x) + gvec0;
   const uint4* rv = res ? reinterpret_cast<const uint4*>(res) + gvec0 : nullptr;
   uint4* sv = s_out ? reinterpret_cast<uint4*>(s_out) + gvec0 : nullptr;
+  uint4* yv = reinterpret_cast<uint4*>(y) + gvec0;
+  constexpr int NR = NV > 0 ? NV : 1;
+  uint4 keep[NR];
   float a[8], b[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
-  for (int v = v0 + threadIdx.x; v < v1; v += NT) {
-    float f[8];
-    unpack8(xv[v], f);
-    if (rv) {
-      float r[8];
-      unpack8(rv[v], r);
+  if (NV > 0) {
+    uint4 rr[NR];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] += r[e];
-      const uint4 packed = pack8(f);
-      sv[v] = packed;
-      unpack8(packed, f);   // statistics of the bf16-rounded sum (what a separate add kernel would have produced)
+    for (int j = 0; j < NR; ++j) {
+      const int v = v0 + j * NT + threadIdx.x;
+      keep[j] = v < v1 ? xv[v] : make_uint4(0, 0, 0, 0);
+      if (rv) rr[j] = v < v1 ? rv[v] : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { a[e] += f[e]; b[e] += f[e] * f[e]; }
+    for (int j = 0; j < NR; ++j) {
+      const int v = v0 + j * NT + threadIdx.x;
+      float f[8];
+      unpack8(keep[j], f);
+      if (rv) {
+        float r[8];
+        unpack8(rr[j], r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] += r[e];
+        keep[j] = pack8(f);
+        if (v < v1) sv[v] = keep[j];
+        unpack8(keep[j], f);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { a[e] += f[e]; b[e] += f[e] * f[e]; }
+    }
+  } else {
+    for (int v = v0 + threadIdx.x; v < v1; v += NT) {
+      float f[8];
+      unpack8(xv[v], f);
+      if (rv) {
+        float r[8];
+        unpack8(rv[v], r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] += r[e];
+        const uint4 packed = pack8(f);
+        sv[v] = packed;
+        unpack8(packed, f);   // statistics of the bf16-rounded sum (what a separate add kernel would have produced)
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { a[e] += f[e]; b[e] += f[e] * f[e]; }
+    }
   }
   cta_channel_reduce(a, b, C, sa, sb);
   __syncthreads();
@@ -145,24 +177,37 @@ bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
     }
   }
   __syncthreads();
-  // pass 2: normalise + affine + relu
   float pa[8], pb[8];
   {
     const int base = (8 * threadIdx.x) % C;
 #pragma unroll
     for (int e = 0; e < 8; ++e) { pa[e] = sc_a[(base + e) % C]; pb[e] = sc_b[(base + e) % C]; }
   }
-  const uint4* in2 = rv ? reinterpret_cast<const uint4*>(sv) : xv;
-  uint4* yv = reinterpret_cast<uint4*>(y) + gvec0;
-  for (int v = v0 + threadIdx.x; v < v1; v += NT) {
-    float f[8];
-    unpack8(in2[v], f);
+  if (NV > 0) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      f[e] = f[e] * pa[e] + pb[e];
-      if (relu) f[e] = fmaxf(f[e], 0.f);
+    for (int j = 0; j < NR; ++j) {
+      const int v = v0 + j * NT + threadIdx.x;
+      float f[8];
+      unpack8(keep[j], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        f[e] = f[e] * pa[e] + pb[e];
+        if (relu) f[e] = fmaxf(f[e], 0.f);
+      }
+      if (v < v1) yv[v] = pack8(f);
     }
-    yv[v] = pack8(f);
+  } else {
+    const uint4* in2 = rv ? reinterpret_cast<const uint4*>(sv) : xv;
+    for (int v = v0 + threadIdx.x; v < v1; v += NT) {
+      float f[8];
+      unpack8(in2[v], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        f[e] = f[e] * pa[e] + pb[e];
+        if (relu) f[e] = fmaxf(f[e], 0.f);
+      }
+      yv[v] = pack8(f);
+    }
   }
   cluster.sync();   // keep this CTA's smem alive until every peer has read it
 }
@@ -200,7 +245,7 @@ __global__ void affine_act_kernel(const __nv_bfloat16* __restrict__ x, const __n
 // backward (one statistics group: the training batch).  grid = (K), cluster (K,1,1).  smem: 6*C floats
 // dy may be a [N, C] tensor broadcast over the HW positions of each sample (hw > 0: global-average-pool grad).
 // ---------------------------------------------------------------------------------------------------------
-template <typename PT>
+template <typename PT, int NV>
 __global__ void __launch_bounds__(NT)
 bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
                   const __nv_bfloat16* __restrict__ dres, const __nv_bfloat16* __restrict__ s,
@@ -215,12 +260,13 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
   for (int c = threadIdx.x; c < C; c += blockDim.x) { c_m[c] = mean[c]; c_i[c] = invstd[c]; }
   __syncthreads();
   const int nvec = M * C / 8;
-  const int per = ((nvec + K - 1) / K + NT - 1) / NT * NT;
+  const int per = NV > 0 ? NV * NT : ((nvec + K - 1) / K + NT - 1) / NT * NT;
   const int v0 = min(k * per, nvec), v1 = min(v0 + per, nvec);
   const uint4* sv = reinterpret_cast<const uint4*>(s);
   const uint4* gv = reinterpret_cast<const uint4*>(dy);
   const uint4* g2v = reinterpret_cast<const uint4*>(dy2);
-  // per-thread channel constants
+  const uint4* rv = reinterpret_cast<const uint4*>(dres);
+  uint4* dv = reinterpret_cast<uint4*>(ds);
   float pm[8], pi[8], pg[8], pb[8];
   {
     const int base = (8 * threadIdx.x) % C;
@@ -230,12 +276,12 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
       pm[e] = c_m[c]; pi[e] = c_i[c]; pg[e] = ldp(gamma, c); pb[e] = ldp(beta, c);
     }
   }
-  const int vec_per_sample = hw > 0 ? hw * C / 8 : 1;   // vectors per sample when dy is broadcast over HW
-  auto load_g = [&](int v, float (&g)[8]) {
+  const int vec_per_sample = hw > 0 ? hw * C / 8 : 1;
+  auto load_g_raw = [&](int v) -> uint4 {   // packed bf16 gradient w.r.t. y for vector v (before the ReLU mask)
     if (hw > 0) {
-      // element i of vector v belongs to sample n = v / vec_per_sample, channel (8v+e) % C
       const int n = v / vec_per_sample;
       const int base = (int)((8L * v) % C);
+      float g[8];
       if (C >= 8) {
         unpack8(reinterpret_cast<const uint4*>(dy + (long)n * C + base)[0], g);
       } else {
@@ -244,30 +290,66 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) g[e] *= dy_scale;
-    } else {
-      unpack8(gv[v], g);
-      if (dy2) {
-        float t[8];
-        unpack8(g2v[v], t);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) g[e] += t[e];
-      }
+      return pack8(g);
     }
+    uint4 u = gv[v];
+    if (dy2) {
+      float g[8], t[8];
+      unpack8(u, g);
+      unpack8(g2v[v], t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] += t[e];
+      u = pack8(g);
+    }
+    return u;
   };
+  constexpr int NR = NV > 0 ? NV : 1;
+  constexpr bool KEEP_G = NV > 0 && NV <= 4;   // wide slices keep only s in registers and re-read the gradient
+  constexpr int NG = KEEP_G ? NR : 1;
+  uint4 ks[NR], kg[NG];
   float a[8], b[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
-  for (int v = v0 + threadIdx.x; v < v1; v += NT) {
+  auto accumulate = [&](const uint4& xs, uint4& gs) {
     float x[8], g[8];
-    unpack8(sv[v], x);
-    load_g(v, g);
+    unpack8(xs, x);
+    unpack8(gs, g);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float xh = (x[e] - pm[e]) * pi[e];
       const float pre = x[e] * (pi[e] * pg[e]) + (pb[e] - pm[e] * pi[e] * pg[e]);   // same expression as forward
-      const float ge = (!relu || pre > 0.f) ? g[e] : 0.f;
-      a[e] += ge;
-      b[e] += ge * xh;
+      if (relu && !(pre > 0.f)) g[e] = 0.f;
+      a[e] += g[e];
+      b[e] += g[e] * xh;
+    }
+    gs = pack8(g);   // masked gradient (exact: zeroing does not change the bf16 values)
+  };
+  if (NV > 0) {
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      const int v = v0 + j * NT + threadIdx.x;
+      ks[j] = v < v1 ? sv[v] : make_uint4(0, 0, 0, 0);
+    }
+    if (KEEP_G) {
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        const int v = v0 + j * NT + threadIdx.x;
+        kg[j % NG] = v < v1 ? load_g_raw(v) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int j = 0; j < NR; ++j) accumulate(ks[j], kg[j % NG]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        const int v = v0 + j * NT + threadIdx.x;
+        uint4 gs = v < v1 ? load_g_raw(v) : make_uint4(0, 0, 0, 0);
+        accumulate(ks[j], gs);
+      }
+    }
+  } else {
+    for (int v = v0 + threadIdx.x; v < v1; v += NT) {
+      uint4 gs = load_g_raw(v);
+      accumulate(sv[v], gs);
     }
   }
   cta_channel_reduce(a, b, C, sa, sb);
@@ -285,23 +367,44 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
 #pragma unroll
     for (int e = 0; e < 8; ++e) { qa[e] = ta[(base + e) % C] * inv_n; qb[e] = tb[(base + e) % C] * inv_n; }
   }
-  const uint4* rv = reinterpret_cast<const uint4*>(dres);
-  uint4* dv = reinterpret_cast<uint4*>(ds);
-  for (int v = v0 + threadIdx.x; v < v1; v += NT) {
-    float x[8], g[8], o[8];
-    unpack8(sv[v], x);
-    load_g(v, g);
-    float r[8];
+  auto apply = [&](int v, const uint4& xs, const uint4& gs) {
+    float x[8], g[8], o[8], r[8];
+    unpack8(xs, x);
+    unpack8(gs, g);
     if (dres) unpack8(rv[v], r);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float xh = (x[e] - pm[e]) * pi[e];
-      const float pre = x[e] * (pi[e] * pg[e]) + (pb[e] - pm[e] * pi[e] * pg[e]);
-      const float ge = (!relu || pre > 0.f) ? g[e] : 0.f;
-      o[e] = pg[e] * pi[e] * (ge - qa[e] - xh * qb[e]);
+      o[e] = pg[e] * pi[e] * (g[e] - qa[e] - xh * qb[e]);
       if (dres) o[e] += r[e];
     }
     dv[v] = pack8(o);
+  };
+  auto masked_g = [&](int v, const uint4& xs) -> uint4 {
+    float x[8], g[8];
+    unpack8(xs, x);
+    unpack8(load_g_raw(v), g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float pre = x[e] * (pi[e] * pg[e]) + (pb[e] - pm[e] * pi[e] * pg[e]);
+      if (relu && !(pre > 0.f)) g[e] = 0.f;
+    }
+    return pack8(g);
+  };
+  if (NV > 0) {
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      const int v = v0 + j * NT + threadIdx.x;
+      if (v < v1) {
+        if (KEEP_G) apply(v, ks[j], kg[j % NG]);
+        else apply(v, ks[j], masked_g(v, ks[j]));
+      }
+    }
+  } else {
+    for (int v = v0 + threadIdx.x; v < v1; v += NT) {
+      const uint4 xs = sv[v];
+      apply(v, xs, masked_g(v, xs));
+    }
   }
   cluster.sync();
 }
@@ -310,18 +413,29 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
 
 using namespace hfl;
 
-static int pick_cluster(long elems) {
-  long k = (elems + 65535) / 65536;
-  if (k < 1) k = 1;
-  if (k > 8) k = 8;
-  // power of two cluster sizes only (1,2,4,8)
-  int p = 1;
-  while (p * 2 <= k) p *= 2;
-  return p;
+// Choose (cluster size K, vectors per thread NV) so that K * NT * NV vectors cover one statistics group.
+// NV == 0 selects the looping kernel (very large groups only).
+static void pick_shape(long elems, int& K, int& NV) {
+  const long nvec = elems / 8;
+  const int nvs[4] = {1, 2, 4, 10};
+  for (int ki = 0; ki < 5; ++ki) {
+    const int kk = 1 << ki;                       // 1, 2, 4, 8, 16
+    for (int ni = 0; ni < 4; ++ni) {
+      // prefer spreading over more CTAs before holding more vectors per thread
+      if (nvs[ni] > 2 && kk < 16) continue;
+      if ((long)kk * NT * nvs[ni] >= nvec) { K = kk; NV = nvs[ni]; return; }
+    }
+  }
+  K = 8;
+  NV = 0;
 }
 
 template <typename Kern, typename... Args>
 static cudaError_t launch_cluster(Kern kern, dim3 grid, int cluster_x, size_t smem, cudaStream_t stream, Args... args) {
+  if (cluster_x > 8) {
+    cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e0 != cudaSuccess) return e0;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(NT);
@@ -337,22 +451,34 @@ static cudaError_t launch_cluster(Kern kern, dim3 grid, int cluster_x, size_t sm
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
+#define HFL_NV_DISPATCH(NVVAL, CALL) \
+  switch (NVVAL) {                   \
+    case 1: { constexpr int NVC = 1; CALL; break; }   \
+    case 2: { constexpr int NVC = 2; CALL; break; }   \
+    case 4: { constexpr int NVC = 4; CALL; break; }   \
+    case 10: { constexpr int NVC = 10; CALL; break; } \
+    default: { constexpr int NVC = 0; CALL; break; }  \
+  }
+
 extern "C" int hfl_bn_act_fwd(const void* x, const void* res, void* s_out, void* y, const void* gamma,
                               const void* beta, int param_bf16, float eps, int groups, int Mg, int C, int relu,
                               float* mean_out, float* invstd_out, float* varu_out, cudaStream_t stream) {
-  const int K = pick_cluster((long)Mg * C);
+  int K, NV;
+  pick_shape((long)Mg * C, K, NV);
   const size_t smem = 6 * (size_t)C * sizeof(float);
   dim3 grid(K, groups);
-  cudaError_t e;
-  if (param_bf16)
-    e = launch_cluster(bn_act_fwd_kernel<__nv_bfloat16>, grid, K, smem, stream, (const __nv_bfloat16*)x,
-                       (const __nv_bfloat16*)res, (__nv_bfloat16*)s_out, (__nv_bfloat16*)y,
-                       (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, eps, Mg, C, relu, mean_out, invstd_out,
-                       varu_out);
-  else
-    e = launch_cluster(bn_act_fwd_kernel<float>, grid, K, smem, stream, (const __nv_bfloat16*)x,
-                       (const __nv_bfloat16*)res, (__nv_bfloat16*)s_out, (__nv_bfloat16*)y, (const float*)gamma,
-                       (const float*)beta, eps, Mg, C, relu, mean_out, invstd_out, varu_out);
+  cudaError_t e = cudaSuccess;
+  if (param_bf16) {
+    HFL_NV_DISPATCH(NV, (e = launch_cluster(bn_act_fwd_kernel<__nv_bfloat16, NVC>, grid, K, smem, stream,
+                                            (const __nv_bfloat16*)x, (const __nv_bfloat16*)res, (__nv_bfloat16*)s_out,
+                                            (__nv_bfloat16*)y, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
+                                            eps, Mg, C, relu, mean_out, invstd_out, varu_out)))
+  } else {
+    HFL_NV_DISPATCH(NV, (e = launch_cluster(bn_act_fwd_kernel<float, NVC>, grid, K, smem, stream,
+                                            (const __nv_bfloat16*)x, (const __nv_bfloat16*)res, (__nv_bfloat16*)s_out,
+                                            (__nv_bfloat16*)y, (const float*)gamma, (const float*)beta, eps, Mg, C, relu,
+                                            mean_out, invstd_out, varu_out)))
+  }
   count_launch();
   return (int)e;
 }
@@ -372,20 +498,24 @@ extern "C" int hfl_bn_act_bwd(const void* dy, const void* dy2, const void* dres,
                               const float* invstd, const void* gamma, const void* beta, int param_bf16, int M, int C,
                               int hw, float dy_scale, int relu, void* ds, void* dgamma, void* dbeta,
                               cudaStream_t stream) {
-  const int K = pick_cluster((long)M * C);
+  int K, NV;
+  pick_shape((long)M * C, K, NV);
   const size_t smem = 6 * (size_t)C * sizeof(float);
   dim3 grid(K);
-  cudaError_t e;
-  if (param_bf16)
-    e = launch_cluster(bn_act_bwd_kernel<__nv_bfloat16>, grid, K, smem, stream, (const __nv_bfloat16*)dy,
-                       (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean, invstd,
-                       (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, M, C, hw, dy_scale, relu,
-                       (__nv_bfloat16*)ds, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta);
-  else
-    e = launch_cluster(bn_act_bwd_kernel<float>, grid, K, smem, stream, (const __nv_bfloat16*)dy,
-                       (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean, invstd,
-                       (const float*)gamma, (const float*)beta, M, C, hw, dy_scale, relu, (__nv_bfloat16*)ds,
-                       (float*)dgamma, (float*)dbeta);
+  cudaError_t e = cudaSuccess;
+  if (param_bf16) {
+    HFL_NV_DISPATCH(NV, (e = launch_cluster(bn_act_bwd_kernel<__nv_bfloat16, NVC>, grid, K, smem, stream,
+                                            (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2,
+                                            (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean, invstd,
+                                            (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, M, C, hw, dy_scale,
+                                            relu, (__nv_bfloat16*)ds, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta)))
+  } else {
+    HFL_NV_DISPATCH(NV, (e = launch_cluster(bn_act_bwd_kernel<float, NVC>, grid, K, smem, stream,
+                                            (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2,
+                                            (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean, invstd,
+                                            (const float*)gamma, (const float*)beta, M, C, hw, dy_scale, relu,
+                                            (__nv_bfloat16*)ds, (float*)dgamma, (float*)dbeta)))
+  }
   count_launch();
   return (int)e;
 }

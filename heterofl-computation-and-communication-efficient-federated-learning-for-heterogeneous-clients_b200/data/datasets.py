@@ -235,6 +235,9 @@ def fetch_dataset(cfg: Dict, root: str = "./data") -> Dict[str, object]:
     out = {}
     synth = cfg.get("synthetic", "auto")
     sizes = cfg.get("synthetic_size") or {}
+    if not sizes and os.environ.get("HFL_SYNTH_SIZES"):          # "train,test" override for smoke tests
+        a, b = os.environ["HFL_SYNTH_SIZES"].split(",")
+        sizes = {"train": int(a), "test": int(b)}
     for split in ("train", "test"):
         if name in DATA_SIZES:
             got = None

@@ -136,7 +136,11 @@ class TrainSlot:
             rows.append((g.data_ptr(), e.offset, e.numel, 1 if g.dtype == torch.bfloat16 else 0))
         return rows
 
+    grad_sync = None   # optional callable run between backward and the optimiser (data-parallel all-reduce)
+
     def _opt_step(self) -> None:
+        if self.grad_sync is not None:
+            self.grad_sync()
         if self.fused is not None:
             rows = self._seg_rows()
             if self._capturing:

@@ -239,3 +239,27 @@ def test_engine_lm_round_gpu(tmp_path):
     h = eng.logger.history
     assert all(np.isfinite(v) for v in h["train/Local-Loss"] + h["test/Global-Perplexity"])
     assert h["train/Local-Loss"][-1] < h["train/Local-Loss"][0]
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (64, 256, 256), (640, 64, 576), (10240, 64, 27 * 8), (200, 1000, 128),
+                                   (64, 33278, 256), (1, 16, 8), (129, 40, 72)])
+def test_tcgen05_gemm_matches_torch(M, N, K):
+    cu = _cu()
+    dev = torch.device("cuda")
+    torch.manual_seed(M + N + K)
+    x = (torch.randn(M, K, device=dev)).bfloat16()
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device=dev)
+    ref = x.float() @ w.float().t()
+    y = cu.C().gemm_bf16_tn(x, w, None, 1.0, False, True)
+    torch.cuda.synchronize()
+    assert torch.allclose(y, ref, atol=2e-3, rtol=2e-3), float((y - ref).abs().max())
+    y2 = cu.C().gemm_bf16_tn(x, w, b, 0.5, True, False)
+    ref2 = torch.nn.functional.gelu(ref * 0.5 + b)
+    assert torch.allclose(y2.float(), ref2, atol=3e-2, rtol=3e-2)
+    # strided (sliced) operands: K-contiguous views into wider buffers
+    if K >= 16:
+        xb = torch.randn(M, K + 8, device=dev).bfloat16()
+        wb = torch.randn(N, K + 16, device=dev).bfloat16()
+        y3 = cu.C().gemm_bf16_tn(xb[:, :K], wb[:, 8:8 + K], None, 1.0, False, True)
+        assert torch.allclose(y3, xb[:, :K].float() @ wb[:, 8:8 + K].float().t(), atol=1e-2, rtol=1e-2)
