@@ -32,6 +32,9 @@ void hfl_multi_sgd_clip_step(const void*, const void*, int, float*, void*, float
                              float*, cudaStream_t);
 int hfl_gemm_bf16_tn(const void*, int, const void*, int, void*, int, int, const float*, float, int, int, int, int,
                      cudaStream_t);
+int hfl_head_smem_bytes(int, int, int);
+int hfl_head_fwd_bwd(const void*, int, int, int, const void*, const void*, int, int, const long long*,
+                     const unsigned char*, float, float*, double*, void*, void*, void*, cudaStream_t);
 long hfl_launch_count();
 void hfl_launch_count_add(long);
 void hfl_peer_barrier(const void*, int, int, unsigned, int*, cudaStream_t);
@@ -241,6 +244,34 @@ void multi_sgd_clip_step(torch::Tensor segs, torch::Tensor blocks, torch::Tensor
   check_launch();
 }
 
+// ---- classifier head (pool + linear + masked CE, forward and backward) ----------------------------------
+// y4: [N, C, H, W] channels-last bf16.  Returns [loss, dW, db, dpooled[N, C] (bf16)]
+std::vector<torch::Tensor> head_fwd_bwd(torch::Tensor y4, torch::Tensor W, torch::Tensor bias, torch::Tensor target,
+                                        c10::optional<torch::Tensor> mask, double n_weight,
+                                        c10::optional<torch::Tensor> meter) {
+  CHECK_CUDA_T(y4);
+  TORCH_CHECK(y4.dim() == 4 && y4.scalar_type() == torch::kBFloat16 && y4.is_contiguous(torch::MemoryFormat::ChannelsLast));
+  const int N = y4.size(0), C = y4.size(1), HW = y4.size(2) * y4.size(3), Kc = W.size(0);
+  TORCH_CHECK(W.is_contiguous() && W.size(1) == C && bias.numel() == Kc && target.numel() == N);
+  const bool pb = W.scalar_type() == torch::kBFloat16;
+  TORCH_CHECK((pb || W.scalar_type() == torch::kFloat32) && bias.scalar_type() == W.scalar_type());
+  TORCH_CHECK(hfl_head_smem_bytes(N, C, Kc) <= 200 * 1024, "head_fwd_bwd: problem too large for one CTA");
+  const unsigned char* mp = nullptr;
+  if (mask.has_value()) { TORCH_CHECK(mask->scalar_type() == torch::kUInt8 && mask->numel() >= Kc); mp = mask->data_ptr<unsigned char>(); }
+  double* mt = nullptr;
+  if (meter.has_value()) { TORCH_CHECK(meter->scalar_type() == torch::kFloat64 && meter->numel() >= 4); mt = meter->data_ptr<double>(); }
+  c10::cuda::CUDAGuard guard(y4.device());
+  auto loss = torch::empty({1}, torch::TensorOptions().dtype(torch::kFloat32).device(y4.device()));
+  auto dW = torch::empty_like(W);
+  auto db = torch::empty_like(bias);
+  auto dp = torch::empty({N, C}, torch::TensorOptions().dtype(torch::kBFloat16).device(y4.device()));
+  int e = hfl_head_fwd_bwd(y4.data_ptr(), N, HW, C, W.data_ptr(), bias.data_ptr(), pb ? 1 : 0, Kc,
+                           (const long long*)target.data_ptr<int64_t>(), mp, (float)n_weight, loss.data_ptr<float>(), mt,
+                           dW.data_ptr(), db.data_ptr(), dp.data_ptr(), cur_stream());
+  TORCH_CHECK(e == 0, "head_fwd_bwd failed: ", e);
+  return {loss, dW, db, dp};
+}
+
 // ---- tcgen05 GEMM ----------------------------------------------------------------------------------------
 // y[M,N] = act(alpha * x[M,K] @ w[N,K]^T + bias)   (x, w bf16 with K contiguous; bias fp32; y bf16 or fp32)
 torch::Tensor gemm_bf16_tn(torch::Tensor x, torch::Tensor w, c10::optional<torch::Tensor> bias, double alpha,
@@ -323,6 +354,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_act_bwd", &bn_act_bwd);
   m.def("multi_sgd_clip_step", &multi_sgd_clip_step);
   m.def("ms_chunk", &hfl_ms_chunk);
+  m.def("head_fwd_bwd", &head_fwd_bwd);
+  m.def("head_smem_bytes", &hfl_head_smem_bytes);
   m.def("gemm_bf16_tn", &gemm_bf16_tn);
   m.def("launch_count", &hfl_launch_count);
   m.def("launch_count_add", &hfl_launch_count_add);

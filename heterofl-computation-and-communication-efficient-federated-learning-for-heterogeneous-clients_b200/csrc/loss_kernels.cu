@@ -98,3 +98,130 @@ extern "C" void hfl_masked_ce(const void* logits, int is_bf16, const long long* 
   ce_finalize_kernel<<<1, 256, 0, stream>>>(row_loss, row_correct, rows, n_weight, loss_out, meter);
   count_launch(2);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Classifier head, forward + backward in ONE single-CTA launch:
+//   pooled = mean_hw(y)  ->  logits = pooled W^T + b  ->  masked CE (loss, metrics)  ->  dW, db, dpooled
+// (reference: adaptive_avg_pool2d, view, linear, masked_fill, cross_entropy + their 5 backward kernels,
+//  src/models/resnet.py:149-157).  Sizes are tiny (N=10, C<=512, 10 classes): everything lives in shared memory.
+// ---------------------------------------------------------------------------------------------------------
+namespace hfl {
+
+template <typename PT>
+__global__ void __launch_bounds__(512)
+head_fwd_bwd_kernel(const __nv_bfloat16* __restrict__ y, int N, int HW, int C, const PT* __restrict__ W,
+                    const PT* __restrict__ bias, int Kc, const long long* __restrict__ target,
+                    const unsigned char* __restrict__ mask, float n_weight, float* __restrict__ loss_out,
+                    double* __restrict__ meter, PT* __restrict__ dW, PT* __restrict__ db,
+                    __nv_bfloat16* __restrict__ dpooled) {
+  extern __shared__ float sm[];
+  float* pooled = sm;                 // [N, C]
+  float* logit = pooled + N * C;      // [N, Kc]  (becomes dlogits)
+  float* red = logit + N * Kc;        // [N] row losses, [N] correct
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const float inv_hw = 1.f / (float)HW;
+  for (int i = tid; i < N * C; i += nt) {
+    const int n = i / C, c = i - n * C;
+    const __nv_bfloat16* p = y + ((size_t)n * HW) * C + c;
+    float s = 0.f;
+    for (int h = 0; h < HW; ++h) s += __bfloat162float(p[(size_t)h * C]);
+    pooled[i] = __bfloat162float(__float2bfloat16(s * inv_hw));   // bf16-rounded like the unfused mean()
+  }
+  __syncthreads();
+  // logits: one warp per (n, k)
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  for (int o = warp; o < N * Kc; o += nw) {
+    const int n = o / Kc, k = o - n * Kc;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += pooled[n * C + c] * (float)W[(size_t)k * C + c];
+    s = warp_sum(s);
+    if (lane == 0) {
+      float z = __bfloat162float(__float2bfloat16(s + (float)bias[k]));
+      if (mask != nullptr && !mask[k]) z = 0.f;
+      logit[o] = z;
+    }
+  }
+  __syncthreads();
+  // softmax-CE per row (one warp per row), gradient of the mean loss
+  for (int n = warp; n < N; n += nw) {
+    float mx = -INFINITY;
+    int arg = 0x7fffffff;
+    for (int k = lane; k < Kc; k += 32) { const float z = logit[n * Kc + k]; if (z > mx) { mx = z; arg = k; } }
+    const float bmx = warp_max(mx);
+    int cand = (mx == bmx) ? arg : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+    float se = 0.f;
+    for (int k = lane; k < Kc; k += 32) se += __expf(logit[n * Kc + k] - bmx);
+    se = warp_sum(se);
+    const float lse = __logf(se) + bmx;
+    const int t = (int)target[n];
+    if (lane == 0) { red[n] = lse - logit[n * Kc + t]; red[N + n] = (cand == t) ? 1.f : 0.f; }
+    __syncwarp();
+    for (int k = lane; k < Kc; k += 32) {
+      const bool on = (mask == nullptr || mask[k]);
+      const float g = on ? (__expf(logit[n * Kc + k] - lse) - (k == t ? 1.f : 0.f)) / (float)N : 0.f;
+      logit[n * Kc + k] = __bfloat162float(__float2bfloat16(g));
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float a = 0.f, c = 0.f;
+    for (int n = 0; n < N; ++n) { a += red[n]; c += red[N + n]; }
+    const float loss = a / (float)N;
+    *loss_out = loss;
+    if (meter != nullptr) {
+      meter[0] += (double)loss * n_weight;
+      meter[1] += (double)c;
+      meter[2] += (double)n_weight;
+      meter[3] += (double)__expf(loss) * n_weight;
+    }
+  }
+  // dW[k][c] = sum_n dl[n][k] pooled[n][c];  db[k] = sum_n dl[n][k];  dpooled[n][c] = sum_k dl[n][k] W[k][c]
+  for (int i = tid; i < Kc * C; i += nt) {
+    const int k = i / C, c = i - k * C;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += logit[n * Kc + k] * pooled[n * C + c];
+    dW[i] = (PT)s;
+  }
+  for (int k = tid; k < Kc; k += nt) {
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += logit[n * Kc + k];
+    db[k] = (PT)s;
+  }
+  for (int i = tid; i < N * C; i += nt) {
+    const int n = i / C, c = i - n * C;
+    float s = 0.f;
+    for (int k = 0; k < Kc; ++k) s += logit[n * Kc + k] * (float)W[(size_t)k * C + c];
+    dpooled[i] = __float2bfloat16(s);
+  }
+}
+
+}  // namespace hfl
+
+extern "C" int hfl_head_smem_bytes(int N, int C, int Kc) { return (N * C + N * Kc + 2 * N) * (int)sizeof(float); }
+
+extern "C" int hfl_head_fwd_bwd(const void* y, int N, int HW, int C, const void* W, const void* bias, int param_bf16,
+                                int Kc, const long long* target, const unsigned char* mask, float n_weight,
+                                float* loss_out, double* meter, void* dW, void* db, void* dpooled,
+                                cudaStream_t stream) {
+  const int smem = hfl_head_smem_bytes(N, C, Kc);
+  if (smem > 200 * 1024) return -1;
+  cudaError_t e = cudaSuccess;
+  if (param_bf16) {
+    auto kern = hfl::head_fwd_bwd_kernel<__nv_bfloat16>;
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<1, 512, smem, stream>>>((const __nv_bfloat16*)y, N, HW, C, (const __nv_bfloat16*)W,
+                                  (const __nv_bfloat16*)bias, Kc, target, mask, n_weight, loss_out, meter,
+                                  (__nv_bfloat16*)dW, (__nv_bfloat16*)db, (__nv_bfloat16*)dpooled);
+  } else {
+    auto kern = hfl::head_fwd_bwd_kernel<float>;
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<1, 512, smem, stream>>>((const __nv_bfloat16*)y, N, HW, C, (const float*)W, (const float*)bias, Kc, target,
+                                  mask, n_weight, loss_out, meter, (float*)dW, (float*)db, (__nv_bfloat16*)dpooled);
+  }
+  hfl::count_launch();
+  return (int)cudaGetLastError();
+}

@@ -40,9 +40,12 @@ __device__ __forceinline__ float ldp(const float* p, int i) { return p[i]; }
 __device__ __forceinline__ void stp(__nv_bfloat16* p, int i, float v) { p[i] = __float2bfloat16(v); }
 __device__ __forceinline__ void stp(float* p, int i, float v) { p[i] = v; }
 
-// Reduce per-thread channel partials a[8], b[8] into smem sa[C], sb[C].  Thread t owns channels (8*t+e) % C.
-__device__ __forceinline__ void cta_channel_reduce(float (&a)[8], float (&b)[8], int C, float* sa, float* sb) {
-  const int lane = threadIdx.x & 31;
+// Reduce per-thread channel partials a[8], b[8] into smem sa[C], sb[C] (no atomics: warp shuffles, then one smem
+// slab per warp, then a 16-way column sum).  Thread t owns channels (8*t+e) % C.  `part` holds 2 * NW * min(C,256) floats.
+constexpr int NW = NT / 32;
+__device__ __forceinline__ void cta_channel_reduce(float (&a)[8], float (&b)[8], int C, float* sa, float* sb,
+                                                   float* part) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (C < 8) {  // C == 4: slots e and e+4 are the same channel
 #pragma unroll
     for (int e = 0; e < 4; ++e) { a[e] += a[e + 4]; b[e] += b[e + 4]; }
@@ -57,13 +60,25 @@ __device__ __forceinline__ void cta_channel_reduce(float (&a)[8], float (&b)[8],
       }
     }
   }
+  const int CW = C < 256 ? C : 256;          // channels covered by one warp
+  float* pa = part;
+  float* pb = part + NW * CW;
   if (cols >= 32 || lane < cols) {
     const int ne = C < 8 ? C : 8;
-    const int base = (8 * threadIdx.x) % C;
+    const int base = (8 * lane) % CW;
     for (int e = 0; e < ne; ++e) {
-      atomicAdd(&sa[(base + e) % C], a[e]);
-      atomicAdd(&sb[(base + e) % C], b[e]);
+      pa[w * CW + base + e] = a[e];
+      pb[w * CW + base + e] = b[e];
     }
+  }
+  __syncthreads();
+  const int nrep = C > 256 ? C / 256 : 1;    // warps w, w+nrep, ... cover the same 256-channel window
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int win = c / CW, cl = c - win * CW;
+    float x = 0.f, y = 0.f;
+    for (int ww = win % nrep; ww < NW; ww += nrep) { x += pa[ww * CW + cl]; y += pb[ww * CW + cl]; }
+    sa[c] = x;
+    sb[c] = y;
   }
 }
 
@@ -157,7 +172,7 @@ bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
       for (int e = 0; e < 8; ++e) { a[e] += f[e]; b[e] += f[e] * f[e]; }
     }
   }
-  cta_channel_reduce(a, b, C, sa, sb);
+  cta_channel_reduce(a, b, C, sa, sb, smem + 6 * C);
   __syncthreads();
   cluster.sync();
   cluster_channel_reduce(cluster, C, sa, sb, ta, tb);
@@ -352,7 +367,7 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
       accumulate(sv[v], gs);
     }
   }
-  cta_channel_reduce(a, b, C, sa, sb);
+  cta_channel_reduce(a, b, C, sa, sb, smem + 6 * C);
   __syncthreads();
   cluster.sync();
   cluster_channel_reduce(cluster, C, sa, sb, ta, tb);
@@ -465,7 +480,7 @@ extern "C" int hfl_bn_act_fwd(const void* x, const void* res, void* s_out, void*
                               float* mean_out, float* invstd_out, float* varu_out, cudaStream_t stream) {
   int K, NV;
   pick_shape((long)Mg * C, K, NV);
-  const size_t smem = 6 * (size_t)C * sizeof(float);
+  const size_t smem = (6 * (size_t)C + 2 * 16 * (size_t)(C < 256 ? C : 256)) * sizeof(float);
   dim3 grid(K, groups);
   cudaError_t e = cudaSuccess;
   if (param_bf16) {
@@ -500,7 +515,7 @@ extern "C" int hfl_bn_act_bwd(const void* dy, const void* dy2, const void* dres,
                               cudaStream_t stream) {
   int K, NV;
   pick_shape((long)M * C, K, NV);
-  const size_t smem = 6 * (size_t)C * sizeof(float);
+  const size_t smem = (6 * (size_t)C + 2 * 16 * (size_t)(C < 256 ? C : 256)) * sizeof(float);
   dim3 grid(K);
   cudaError_t e = cudaSuccess;
   if (param_bf16) {

@@ -58,13 +58,21 @@ class FusedResNet:
         s4, y4, m4, i4, _ = fo.bn_act_fwd(cur, res, P["n4.weight"], P["n4.bias"], eps)
         # ---- head: global average pool -> linear -> masked CE (forward + backward) ----
         N, C, H, W = y4.shape
-        pooled = y4.mean(dim=(2, 3))
         Wl, bl = P["linear.weight"], P["linear.bias"]
-        logits = F.linear(pooled, Wl, bl)
-        loss, dlogits = self._ce(logits, y, label_mask, meter)
-        G["linear.weight"] = dlogits.t().mm(pooled)
-        G["linear.bias"] = dlogits.sum(0)
-        dpooled = dlogits.mm(Wl)                                  # [N, C]
+        if y4.is_cuda and y4.dtype == torch.bfloat16 and cu.available() \
+                and cu.C().head_smem_bytes(N, C, Wl.shape[0]) <= 200 * 1024:
+            mt, nw = (meter if meter is not None else (None, float(N)))
+            mask = label_mask if (label_mask is None or label_mask.dtype == torch.uint8) else label_mask.to(torch.uint8)
+            loss, G["linear.weight"], G["linear.bias"], dpooled = cu.C().head_fwd_bwd(
+                y4, Wl, bl, y.contiguous(), mask, float(nw), mt)
+            loss = loss.view(())
+        else:
+            pooled = y4.mean(dim=(2, 3))
+            logits = F.linear(pooled, Wl, bl)
+            loss, dlogits = self._ce(logits, y, label_mask, meter)
+            G["linear.weight"] = dlogits.t().mm(pooled)
+            G["linear.bias"] = dlogits.sum(0)
+            dpooled = dlogits.mm(Wl)                                  # [N, C]
         # ---- backward ----
         G["n4.weight"], G["n4.bias"] = torch.empty_like(P["n4.weight"]), torch.empty_like(P["n4.bias"])
         ds = fo.bn_act_bwd(dpooled, None, None, s4, m4, i4, P["n4.weight"], P["n4.bias"], G["n4.weight"], G["n4.bias"],
