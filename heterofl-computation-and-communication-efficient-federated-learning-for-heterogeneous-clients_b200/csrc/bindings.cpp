@@ -23,10 +23,10 @@ void hfl_masked_ce(const void*, int, const long long*, const unsigned char*, int
 void hfl_augment(const unsigned char*, const long long*, const int*, const float*, const float*, int, int, int, int,
                  int, void*, int, cudaStream_t);
 int hfl_bn_act_fwd(const void*, const void*, void*, void*, const void*, const void*, int, float, int, int, int, int,
-                   float*, float*, float*, cudaStream_t);
+                   float*, float*, float*, float*, cudaStream_t);
 void hfl_affine_act(const void*, const void*, void*, void*, const float*, const float*, long, int, int, cudaStream_t);
 int hfl_bn_act_bwd(const void*, const void*, const void*, const void*, const float*, const float*, const void*,
-                   const void*, int, int, int, int, float, int, void*, void*, void*, cudaStream_t);
+                   const void*, int, int, int, int, float, int, void*, void*, void*, float*, cudaStream_t);
 int hfl_ms_chunk();
 void hfl_multi_sgd_clip_step(const void*, const void*, int, float*, void*, float*, const float*, float, float, float,
                              float*, cudaStream_t);
@@ -34,7 +34,10 @@ int hfl_gemm_bf16_tn(const void*, int, const void*, int, void*, int, int, const 
                      cudaStream_t);
 int hfl_head_smem_bytes(int, int, int);
 int hfl_head_fwd_bwd(const void*, int, int, int, const void*, const void*, int, int, const long long*,
-                     const unsigned char*, float, float*, double*, void*, void*, void*, cudaStream_t);
+                     const unsigned char*, float, float*, double*, void*, void*, void*, float*, cudaStream_t);
+int hfl_conv_tc_supported(int, int, int, int, int, int, int, int);
+int hfl_conv_fprop_tc(const void*, const void*, void*, const void*, float*, int, int, int, int, int, int, int, int,
+                      cudaStream_t);
 long hfl_launch_count();
 void hfl_launch_count_add(long);
 void hfl_peer_barrier(const void*, int, int, unsigned, int*, cudaStream_t);
@@ -179,9 +182,11 @@ std::vector<torch::Tensor> bn_act_fwd(torch::Tensor x, c10::optional<torch::Tens
   auto fopt = torch::TensorOptions().dtype(torch::kFloat32).device(x.device());
   auto stats = torch::empty({3, groups, C}, fopt);
   float* sp = stats.data_ptr<float>();
+  auto ws = torch::empty({2, C}, fopt);           // scratch of the split (wide) path
   int e = hfl_bn_act_fwd(x.data_ptr(), optp(res), res.has_value() ? s.data_ptr() : nullptr, y.data_ptr(),
                          gamma.data_ptr(), beta.data_ptr(), pb ? 1 : 0, (float)eps, (int)groups, (int)(M / groups),
-                         (int)C, relu ? 1 : 0, sp, sp + groups * C, sp + 2 * groups * C, cur_stream());
+                         (int)C, relu ? 1 : 0, sp, sp + groups * C, sp + 2 * groups * C, ws.data_ptr<float>(),
+                         cur_stream());
   TORCH_CHECK(e == 0, "bn_act_fwd launch failed: ", cudaGetErrorString((cudaError_t)e));
   check_launch();
   return {s, y, stats[0], stats[1], stats[2]};
@@ -222,10 +227,11 @@ torch::Tensor bn_act_bwd(torch::Tensor dy, c10::optional<torch::Tensor> dy2, c10
   TORCH_CHECK(dgamma.is_contiguous() && dbeta.is_contiguous() && mean.scalar_type() == torch::kFloat32);
   c10::cuda::CUDAGuard guard(s.device());
   auto ds = torch::empty_like(s);
+  auto ws = torch::empty({2, C}, torch::TensorOptions().dtype(torch::kFloat32).device(s.device()));
   int e = hfl_bn_act_bwd(dy.data_ptr(), optp(dy2), optp(dres), s.data_ptr(), mean.data_ptr<float>(),
                          invstd.data_ptr<float>(), gamma.data_ptr(), beta.data_ptr(), pb ? 1 : 0, (int)M, (int)C,
                          (int)hw, (float)dy_scale, relu ? 1 : 0, ds.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                         cur_stream());
+                         ws.data_ptr<float>(), cur_stream());
   TORCH_CHECK(e == 0, "bn_act_bwd launch failed: ", cudaGetErrorString((cudaError_t)e));
   check_launch();
   return ds;
@@ -265,9 +271,10 @@ std::vector<torch::Tensor> head_fwd_bwd(torch::Tensor y4, torch::Tensor W, torch
   auto dW = torch::empty_like(W);
   auto db = torch::empty_like(bias);
   auto dp = torch::empty({N, C}, torch::TensorOptions().dtype(torch::kBFloat16).device(y4.device()));
+  auto pooled = torch::empty({N, C}, torch::TensorOptions().dtype(torch::kFloat32).device(y4.device()));
   int e = hfl_head_fwd_bwd(y4.data_ptr(), N, HW, C, W.data_ptr(), bias.data_ptr(), pb ? 1 : 0, Kc,
                            (const long long*)target.data_ptr<int64_t>(), mp, (float)n_weight, loss.data_ptr<float>(), mt,
-                           dW.data_ptr(), db.data_ptr(), dp.data_ptr(), cur_stream());
+                           dW.data_ptr(), db.data_ptr(), dp.data_ptr(), pooled.data_ptr<float>(), cur_stream());
   TORCH_CHECK(e == 0, "head_fwd_bwd failed: ", e);
   return {loss, dW, db, dp};
 }
@@ -295,6 +302,40 @@ torch::Tensor gemm_bf16_tn(torch::Tensor x, torch::Tensor w, c10::optional<torch
   int e = hfl_gemm_bf16_tn(x.data_ptr(), (int)x.stride(0), w.data_ptr(), (int)w.stride(0), y.data_ptr(), (int)N,
                            out_fp32 ? 0 : 1, bp, (float)alpha, gelu ? 1 : 0, (int)M, (int)N, (int)K, cur_stream());
   TORCH_CHECK(e == 0, "gemm_bf16_tn failed with code ", e);
+  return y;
+}
+
+// ---- tcgen05 implicit-GEMM convolution (forward) ---------------------------------------------------------
+bool conv_tc_supported(int64_t N, int64_t H, int64_t W, int64_t C, int64_t Kout, int64_t R, int64_t S, int64_t stride) {
+  return hfl_conv_tc_supported((int)N, (int)H, (int)W, (int)C, (int)Kout, (int)R, (int)S, (int)stride) == 0;
+}
+
+// x: [N, C, H, W] channels-last bf16; w: [K, C, R, S] with channels-last strides (physically K,R,S,C);
+// residual: like the output (optional); stats: fp32 [2, K] accumulated in place (optional).  padding = R/2.
+torch::Tensor conv_fprop_tc(torch::Tensor x, torch::Tensor w, c10::optional<torch::Tensor> residual,
+                            c10::optional<torch::Tensor> stats, int64_t stride) {
+  CHECK_CUDA_T(x); CHECK_CUDA_T(w);
+  TORCH_CHECK(x.dim() == 4 && w.dim() == 4 && x.scalar_type() == torch::kBFloat16 && w.scalar_type() == torch::kBFloat16);
+  TORCH_CHECK(x.is_contiguous(torch::MemoryFormat::ChannelsLast), "conv_fprop_tc: x must be channels-last");
+  TORCH_CHECK(w.permute({0, 2, 3, 1}).is_contiguous(), "conv_fprop_tc: w must be stored K,R,S,C");
+  const int N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3);
+  const int K = w.size(0), R = w.size(2), S = w.size(3);
+  TORCH_CHECK(w.size(1) == C);
+  TORCH_CHECK(hfl_conv_tc_supported(N, H, W, C, K, R, S, (int)stride) == 0, "conv_fprop_tc: unsupported problem");
+  const int pad = R / 2;
+  const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - S) / stride + 1;
+  c10::cuda::CUDAGuard guard(x.device());
+  auto y = torch::empty({N, K, OH, OW}, x.options().memory_format(torch::MemoryFormat::ChannelsLast));
+  const void* rp = nullptr;
+  if (residual.has_value()) {
+    TORCH_CHECK(residual->sizes() == y.sizes() && residual->is_contiguous(torch::MemoryFormat::ChannelsLast) &&
+                residual->scalar_type() == torch::kBFloat16);
+    rp = residual->data_ptr();
+  }
+  float* sp = nullptr;
+  if (stats.has_value()) { TORCH_CHECK(stats->scalar_type() == torch::kFloat32 && stats->numel() == 2 * K && stats->is_contiguous()); sp = stats->data_ptr<float>(); }
+  int e = hfl_conv_fprop_tc(x.data_ptr(), w.data_ptr(), y.data_ptr(), rp, sp, N, H, W, C, K, R, S, (int)stride, cur_stream());
+  TORCH_CHECK(e == 0, "conv_fprop_tc failed with code ", e);
   return y;
 }
 
@@ -357,6 +398,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("head_fwd_bwd", &head_fwd_bwd);
   m.def("head_smem_bytes", &hfl_head_smem_bytes);
   m.def("gemm_bf16_tn", &gemm_bf16_tn);
+  m.def("conv_tc_supported", &conv_tc_supported);
+  m.def("conv_fprop_tc", &conv_fprop_tc);
   m.def("launch_count", &hfl_launch_count);
   m.def("launch_count_add", &hfl_launch_count_add);
   m.def("peer_alloc", &peer_alloc);

@@ -1,0 +1,250 @@
+// Implicit-GEMM convolution forward on tcgen05 / TMEM, operands fed by TMA (sm_100a).
+//
+//   Y[n, oh, ow, k] = sum_{r,s,c} X[n, oh*stride + r - pad, ow*stride + s - pad, c] * Wt[k, r, s, c]   (+ residual)
+//
+// X, Y are NHWC bf16, Wt is K,R,S,C bf16 (the layout the parameter arenas store, plan/layout.py), fp32 accumulation.
+// GEMM view: M = N*OH*OW output pixels, N = K_out, K = R*S*C.  One CTA computes a 128-pixel x BLOCK_N tile:
+//
+//   * the 128 pixels are a (bn images) x (bh rows) x (OW columns) brick, so the A-operand slice for filter tap (r,s)
+//     and channel block cb is ONE 4-D TMA box {64 ch, OW, bh, bn} of X starting at the tap's halo offset -- padding is
+//     the TMA unit's out-of-bounds zero fill, stride-2 is the tensor map's traversal stride.  No im2col buffer, no
+//     index arithmetic in the kernel: the producer warp only changes box coordinates.
+//   * B-operand slices are 2-D boxes of the [K_out, R*S*C] filter matrix; both land in 128B-swizzled smem and are
+//     consumed by tcgen05.mma (M128 x BLOCK_N x K16, cta_group::1) issued by one elected thread; a 4-stage mbarrier
+//     ring overlaps TMA with MMA; the accumulator lives in TMEM and is drained by 4 epilogue warps with tcgen05.ld.
+//   * epilogue: optional residual add, bf16 store, and (optional) per-channel sum / sum-of-squares of the tile
+//     (BatchNorm batch statistics of the conv output) reduced in-warp and atomically added to a [2, K_out] buffer.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace hfl {
+
+constexpr int CV_BLOCK_M = 128;
+constexpr int CV_BLOCK_K = 64;
+constexpr int CV_STAGES = 4;
+constexpr int CV_THREADS = 256;
+
+struct ConvGeom {
+  int N, H, W, C, Kout, OH, OW, R, S, stride, pad;
+  int bn, bh, bw;          // pixel brick of one tile (bn*bh*bw == 128, bw == OW)
+  int tiles_h;             // ceil(OH / bh)
+};
+
+template <int BLOCK_N>
+struct ConvSmem {
+  static constexpr int A_BYTES = CV_BLOCK_M * CV_BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * CV_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = CV_STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                          __nv_bfloat16* __restrict__ Y, const __nv_bfloat16* __restrict__ residual,
+                          float* __restrict__ stats /* [2, Kout] or null */, const ConvGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  using S = ConvSmem<BLOCK_N>;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + CV_STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + CV_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + CV_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.x / g.tiles_h;           // image-group index
+  const int tile_h = blockIdx.x - tile_n * g.tiles_h;  // row-group index
+  const int n0 = tile_n * g.bn, oh0 = tile_h * g.bh;
+  const int n_blk = blockIdx.y;
+  const int cblocks = g.C / CV_BLOCK_K;
+  const int num_k = g.R * g.S * cblocks;
+  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < CV_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int st = kb % CV_STAGES;
+        const uint32_t ph = (kb / CV_STAGES) & 1;
+        const int tap = kb / cblocks, cb = kb - tap * cblocks;
+        const int r = tap / g.S, s = tap - r * g.S;
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        uint8_t* sa = smem + st * S::STAGE_BYTES;
+        uint8_t* sb = sa + S::A_BYTES;
+        mbar_expect_tx(&full_bar[st], S::STAGE_BYTES);
+        // A: box {64ch, bw, bh, bn} at (c, w, h, n) = (cb*64, s - pad, oh0*stride + r - pad, n0); halo -> zero fill
+        tma_load_4d(sa, &tmap_x, &full_bar[st], cb * CV_BLOCK_K, s - g.pad, oh0 * g.stride + r - g.pad, n0);
+        // B: rows = output channels, cols = (tap, c)
+        tma_load_2d(sb, &tmap_w, &full_bar[st], tap * g.C + cb * CV_BLOCK_K, n_blk * BLOCK_N);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16(CV_BLOCK_M, BLOCK_N);
+    for (int kb = 0; kb < num_k; ++kb) {
+      const int st = kb % CV_STAGES;
+      const uint32_t ph = (kb / CV_STAGES) & 1;
+      mbar_wait(&full_bar[st], ph);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(smem + st * S::STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc_sw128(a_addr);
+        const uint64_t bdesc = make_smem_desc_sw128(a_addr + S::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < CV_BLOCK_K / 16; ++k) umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        umma_commit(&empty_bar[st]);
+        if (kb == num_k - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int m = q * 32 + lane;                          // pixel within the brick: ((n_l*bh + h_l)*bw + w_l)
+    const int w_l = m % g.bw;
+    const int t = m / g.bw;
+    const int h_l = t % g.bh, n_l = t / g.bh;
+    const int n = n0 + n_l, oh = oh0 + h_l;
+    const bool ok = (n < g.N) && (oh < g.OH);
+    const size_t pix = ((size_t)n * g.OH + oh) * g.OW + w_l;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      const int col0 = n_blk * BLOCK_N + c0;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = ok ? __uint_as_float(v[j]) : 0.f;
+      if (ok) {
+        __nv_bfloat16* dst = Y + pix * g.Kout + col0;
+        if (residual != nullptr) {
+          const uint4* rp = reinterpret_cast<const uint4*>(residual + pix * g.Kout + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 u = rp[j];
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { f[8 * j + 2 * e] += __low2float(h[e]); f[8 * j + 2 * e + 1] += __high2float(h[e]); }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 u;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+          h[0] = __floats2bfloat162_rn(f[j], f[j + 1]);
+          h[1] = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+          h[2] = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+          h[3] = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+          *reinterpret_cast<uint4*>(dst + j) = u;
+          if (stats != nullptr) {   // statistics of the bf16-rounded outputs (what a separate BN kernel would read)
+            f[j] = __low2float(h[0]); f[j + 1] = __high2float(h[0]); f[j + 2] = __low2float(h[1]); f[j + 3] = __high2float(h[1]);
+            f[j + 4] = __low2float(h[2]); f[j + 5] = __high2float(h[2]); f[j + 6] = __low2float(h[3]); f[j + 7] = __high2float(h[3]);
+          }
+        }
+      }
+      if (stats != nullptr) {
+        // column sums over the warp's 32 rows: butterfly where lane j ends up owning column j
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float sx = f[j], sq = f[j] * f[j];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, o);
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+          }
+          if (lane == j) {
+            atomicAdd(&stats[col0 + j], sx);
+            atomicAdd(&stats[g.Kout + col0 + j], sq);
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace hfl
+
+using namespace hfl;
+
+template <int BLOCK_N>
+static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, const void* residual, float* stats,
+                       const ConvGeom& g, int tiles_m, cudaStream_t stream) {
+  auto kern = conv_fprop_tcgen05_kernel<BLOCK_N>;
+  constexpr int smem = ConvSmem<BLOCK_N>::TOTAL;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  dim3 grid(tiles_m, g.Kout / BLOCK_N);
+  kern<<<grid, CV_THREADS, smem, stream>>>(tx, tw, (__nv_bfloat16*)Y, (const __nv_bfloat16*)residual, stats, g);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// 0 if this problem can run on the tcgen05 path
+extern "C" int hfl_conv_tc_supported(int N, int H, int W, int C, int Kout, int R, int S, int stride) {
+  if (C % 64 != 0 || Kout % 64 != 0) return 1;
+  if (!((R == 3 && S == 3) || (R == 1 && S == 1))) return 2;
+  if (stride != 1 && stride != 2) return 3;
+  const int pad = R / 2;
+  const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - S) / stride + 1;
+  if (OW > 128 || (128 % OW) != 0) return 4;
+  const int rows = 128 / OW;                   // bh * bn
+  if (rows > OH && (rows % OH) != 0) return 5;
+  if (rows < OH && (OH % rows) != 0) return 6;
+  if (OW * stride > 256 || (rows < OH ? rows : OH) * stride > 256) return 7;
+  return 0;
+}
+
+extern "C" int hfl_conv_fprop_tc(const void* X, const void* Wt, void* Y, const void* residual, float* stats, int N,
+                                 int H, int W, int C, int Kout, int R, int S, int stride, cudaStream_t stream) {
+  if (hfl_conv_tc_supported(N, H, W, C, Kout, R, S, stride) != 0) return -2;
+  ConvGeom g;
+  g.N = N; g.H = H; g.W = W; g.C = C; g.Kout = Kout; g.R = R; g.S = S; g.stride = stride; g.pad = R / 2;
+  g.OH = (H + 2 * g.pad - R) / stride + 1;
+  g.OW = (W + 2 * g.pad - S) / stride + 1;
+  g.bw = g.OW;
+  const int rows = 128 / g.OW;
+  g.bh = rows < g.OH ? rows : g.OH;
+  g.bn = rows / g.bh;
+  g.tiles_h = (g.OH + g.bh - 1) / g.bh;
+  const int tiles_m = ((N + g.bn - 1) / g.bn) * g.tiles_h;
+  const int block_n = (Kout % 128 == 0) ? 128 : 64;
+  CUtensorMap tx, tw;
+  // traversal strides: box extents are given in traversed elements (ceil(box/stride) elements are loaded)
+  int r = make_tmap_nhwc_bf16(&tx, X, (uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N, CV_BLOCK_K,
+                              (uint32_t)(g.bw * stride), (uint32_t)(g.bh * stride), (uint32_t)g.bn, (uint32_t)stride,
+                              (uint32_t)stride, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (r) return 1000 + r;
+  r = make_tmap_2d_bf16(&tw, Wt, (uint64_t)R * S * C, (uint64_t)Kout, (uint64_t)R * S * C * 2, CV_BLOCK_K, block_n);
+  if (r) return 2000 + r;
+  if (block_n == 128) return launch_conv<128>(tx, tw, Y, residual, stats, g, tiles_m, stream);
+  return launch_conv<64>(tx, tw, Y, residual, stats, g, tiles_m, stream);
+}

@@ -107,9 +107,21 @@ extern "C" void hfl_masked_ce(const void* logits, int is_bf16, const long long* 
 // ---------------------------------------------------------------------------------------------------------
 namespace hfl {
 
+// pass 1: global average pool, one thread per (n, c); 20 small CTAs instead of one long loop
+__global__ void head_pool_kernel(const __nv_bfloat16* __restrict__ y, int N, int HW, int C, float* __restrict__ pooled) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i - n * C;
+  const __nv_bfloat16* p = y + ((size_t)n * HW) * C + c;
+  float s = 0.f;
+  for (int h = 0; h < HW; ++h) s += __bfloat162float(p[(size_t)h * C]);
+  pooled[i] = __bfloat162float(__float2bfloat16(s / (float)HW));   // bf16-rounded like the unfused mean()
+}
+
+// pass 2: every CTA recomputes the (tiny) logits + CE, then produces its channel slice of dW / dpooled
 template <typename PT>
 __global__ void __launch_bounds__(512)
-head_fwd_bwd_kernel(const __nv_bfloat16* __restrict__ y, int N, int HW, int C, const PT* __restrict__ W,
+head_fwd_bwd_kernel(const float* __restrict__ pooled_g, int N, int C, const PT* __restrict__ W,
                     const PT* __restrict__ bias, int Kc, const long long* __restrict__ target,
                     const unsigned char* __restrict__ mask, float n_weight, float* __restrict__ loss_out,
                     double* __restrict__ meter, PT* __restrict__ dW, PT* __restrict__ db,
@@ -119,16 +131,8 @@ head_fwd_bwd_kernel(const __nv_bfloat16* __restrict__ y, int N, int HW, int C, c
   float* logit = pooled + N * C;      // [N, Kc]  (becomes dlogits)
   float* red = logit + N * Kc;        // [N] row losses, [N] correct
   const int tid = threadIdx.x, nt = blockDim.x;
-  const float inv_hw = 1.f / (float)HW;
-  for (int i = tid; i < N * C; i += nt) {
-    const int n = i / C, c = i - n * C;
-    const __nv_bfloat16* p = y + ((size_t)n * HW) * C + c;
-    float s = 0.f;
-    for (int h = 0; h < HW; ++h) s += __bfloat162float(p[(size_t)h * C]);
-    pooled[i] = __bfloat162float(__float2bfloat16(s * inv_hw));   // bf16-rounded like the unfused mean()
-  }
+  for (int i = tid; i < N * C; i += nt) pooled[i] = pooled_g[i];
   __syncthreads();
-  // logits: one warp per (n, k)
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   for (int o = warp; o < N * Kc; o += nw) {
     const int n = o / Kc, k = o - n * Kc;
@@ -142,7 +146,6 @@ head_fwd_bwd_kernel(const __nv_bfloat16* __restrict__ y, int N, int HW, int C, c
     }
   }
   __syncthreads();
-  // softmax-CE per row (one warp per row), gradient of the mean loss
   for (int n = warp; n < N; n += nw) {
     float mx = -INFINITY;
     int arg = 0x7fffffff;
@@ -165,35 +168,41 @@ head_fwd_bwd_kernel(const __nv_bfloat16* __restrict__ y, int N, int HW, int C, c
     }
   }
   __syncthreads();
-  if (tid == 0) {
-    float a = 0.f, c = 0.f;
-    for (int n = 0; n < N; ++n) { a += red[n]; c += red[N + n]; }
-    const float loss = a / (float)N;
-    *loss_out = loss;
-    if (meter != nullptr) {
-      meter[0] += (double)loss * n_weight;
-      meter[1] += (double)c;
-      meter[2] += (double)n_weight;
-      meter[3] += (double)__expf(loss) * n_weight;
+  if (blockIdx.x == 0) {
+    if (tid == 0) {
+      float a = 0.f, c = 0.f;
+      for (int n = 0; n < N; ++n) { a += red[n]; c += red[N + n]; }
+      const float loss = a / (float)N;
+      *loss_out = loss;
+      if (meter != nullptr) {
+        meter[0] += (double)loss * n_weight;
+        meter[1] += (double)c;
+        meter[2] += (double)n_weight;
+        meter[3] += (double)__expf(loss) * n_weight;
+      }
+    }
+    for (int k = tid; k < Kc; k += nt) {
+      float s = 0.f;
+      for (int n = 0; n < N; ++n) s += logit[n * Kc + k];
+      db[k] = (PT)s;
     }
   }
-  // dW[k][c] = sum_n dl[n][k] pooled[n][c];  db[k] = sum_n dl[n][k];  dpooled[n][c] = sum_k dl[n][k] W[k][c]
-  for (int i = tid; i < Kc * C; i += nt) {
-    const int k = i / C, c = i - k * C;
+  // channel slice of this CTA
+  const int cs = (C + gridDim.x - 1) / gridDim.x;
+  const int c0 = blockIdx.x * cs, c1 = min(c0 + cs, C);
+  const int wsl = c1 - c0;
+  if (wsl <= 0) return;
+  for (int i = tid; i < Kc * wsl; i += nt) {
+    const int k = i / wsl, c = c0 + (i - k * wsl);
     float s = 0.f;
     for (int n = 0; n < N; ++n) s += logit[n * Kc + k] * pooled[n * C + c];
-    dW[i] = (PT)s;
+    dW[(size_t)k * C + c] = (PT)s;
   }
-  for (int k = tid; k < Kc; k += nt) {
-    float s = 0.f;
-    for (int n = 0; n < N; ++n) s += logit[n * Kc + k];
-    db[k] = (PT)s;
-  }
-  for (int i = tid; i < N * C; i += nt) {
-    const int n = i / C, c = i - n * C;
+  for (int i = tid; i < N * wsl; i += nt) {
+    const int n = i / wsl, c = c0 + (i - n * wsl);
     float s = 0.f;
     for (int k = 0; k < Kc; ++k) s += logit[n * Kc + k] * (float)W[(size_t)k * C + c];
-    dpooled[i] = __float2bfloat16(s);
+    dpooled[(size_t)n * C + c] = __float2bfloat16(s);
   }
 }
 
@@ -203,25 +212,27 @@ extern "C" int hfl_head_smem_bytes(int N, int C, int Kc) { return (N * C + N * K
 
 extern "C" int hfl_head_fwd_bwd(const void* y, int N, int HW, int C, const void* W, const void* bias, int param_bf16,
                                 int Kc, const long long* target, const unsigned char* mask, float n_weight,
-                                float* loss_out, double* meter, void* dW, void* db, void* dpooled,
+                                float* loss_out, double* meter, void* dW, void* db, void* dpooled, float* pooled_ws,
                                 cudaStream_t stream) {
   const int smem = hfl_head_smem_bytes(N, C, Kc);
   if (smem > 200 * 1024) return -1;
+  hfl::head_pool_kernel<<<(N * C + 255) / 256, 256, 0, stream>>>((const __nv_bfloat16*)y, N, HW, C, pooled_ws);
+  const int grid = C >= 128 ? C / 64 : 1;
   cudaError_t e = cudaSuccess;
   if (param_bf16) {
     auto kern = hfl::head_fwd_bwd_kernel<__nv_bfloat16>;
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<1, 512, smem, stream>>>((const __nv_bfloat16*)y, N, HW, C, (const __nv_bfloat16*)W,
-                                  (const __nv_bfloat16*)bias, Kc, target, mask, n_weight, loss_out, meter,
-                                  (__nv_bfloat16*)dW, (__nv_bfloat16*)db, (__nv_bfloat16*)dpooled);
+    kern<<<grid, 512, smem, stream>>>(pooled_ws, N, C, (const __nv_bfloat16*)W, (const __nv_bfloat16*)bias, Kc, target,
+                                     mask, n_weight, loss_out, meter, (__nv_bfloat16*)dW, (__nv_bfloat16*)db,
+                                     (__nv_bfloat16*)dpooled);
   } else {
     auto kern = hfl::head_fwd_bwd_kernel<float>;
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<1, 512, smem, stream>>>((const __nv_bfloat16*)y, N, HW, C, (const float*)W, (const float*)bias, Kc, target,
-                                  mask, n_weight, loss_out, meter, (float*)dW, (float*)db, (__nv_bfloat16*)dpooled);
+    kern<<<grid, 512, smem, stream>>>(pooled_ws, N, C, (const float*)W, (const float*)bias, Kc, target, mask, n_weight,
+                                     loss_out, meter, (float*)dW, (float*)db, (__nv_bfloat16*)dpooled);
   }
-  hfl::count_launch();
+  hfl::count_launch(2);
   return (int)cudaGetLastError();
 }

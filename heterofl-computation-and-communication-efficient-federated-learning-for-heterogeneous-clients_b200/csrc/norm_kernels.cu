@@ -82,16 +82,21 @@ __device__ __forceinline__ void cta_channel_reduce(float (&a)[8], float (&b)[8],
   }
 }
 
-// Sum the CTA partials of every CTA in the cluster (DSMEM) into local totals ta[C], tb[C].
+// Sum the CTA partials of every CTA in the cluster (DSMEM) into local totals ta[C], tb[C].  All remote loads of a
+// thread are issued before the first add (one DSMEM latency instead of 2K of them).
 __device__ __forceinline__ void cluster_channel_reduce(cg::cluster_group& cluster, int C, float* sa, float* sb,
                                                        float* ta, float* tb) {
   const unsigned K = cluster.num_blocks();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float x = 0.f, y = 0.f;
-    for (unsigned r = 0; r < K; ++r) {
-      x += cluster.map_shared_rank(sa, r)[c];
-      y += cluster.map_shared_rank(sb, r)[c];
+    float vx[16], vy[16];
+#pragma unroll
+    for (unsigned r = 0; r < 16; ++r) {
+      vx[r] = r < K ? cluster.map_shared_rank(sa, r)[c] : 0.f;
+      vy[r] = r < K ? cluster.map_shared_rank(sb, r)[c] : 0.f;
     }
+    float x = 0.f, y = 0.f;
+#pragma unroll
+    for (unsigned r = 0; r < 16; ++r) { x += vx[r]; y += vy[r]; }
     ta[c] = x;
     tb[c] = y;
   }
@@ -424,6 +429,184 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
   cluster.sync();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Split path for LARGE single-group tensors (> 16 CTAs x 512 thr x 4 vectors): a wide statistics kernel (global
+// atomics into ws[2][C]) followed by a wide apply kernel.  Two fully parallel launches beat one 16-CTA cluster here.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+bn_stats_wide_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                     __nv_bfloat16* __restrict__ s_out, int nvec, int C, float* __restrict__ ws) {
+  extern __shared__ float smem[];
+  float *sa = smem, *sb = smem + C;
+  const uint4* xv = reinterpret_cast<const uint4*>(x);
+  const uint4* rv = reinterpret_cast<const uint4*>(res);
+  uint4* sv = reinterpret_cast<uint4*>(s_out);
+  float a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
+  for (int v = blockIdx.x * NT + threadIdx.x; v < nvec; v += gridDim.x * NT) {
+    float f[8];
+    unpack8(xv[v], f);
+    if (res) {
+      float r[8];
+      unpack8(rv[v], r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += r[e];
+      const uint4 p = pack8(f);
+      sv[v] = p;
+      unpack8(p, f);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { a[e] += f[e]; b[e] += f[e] * f[e]; }
+  }
+  cta_channel_reduce(a, b, C, sa, sb, smem + 2 * C);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { atomicAdd(&ws[c], sa[c]); atomicAdd(&ws[C + c], sb[c]); }
+}
+
+template <typename PT>
+__global__ void __launch_bounds__(NT)
+bn_apply_wide_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restrict__ y, const PT* __restrict__ gamma,
+                     const PT* __restrict__ beta, float eps, int M, int C, int relu, const float* __restrict__ ws,
+                     float* __restrict__ mean_out, float* __restrict__ invstd_out, float* __restrict__ varu_out) {
+  extern __shared__ float smem[];
+  float *sc_a = smem, *sc_b = smem + C;
+  const float inv_n = 1.f / (float)M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mean = ws[c] * inv_n;
+    const float var = fmaxf(ws[C + c] * inv_n - mean * mean, 0.f);
+    const float invstd = rsqrtf(var + eps);
+    const float ga = ldp(gamma, c), be = ldp(beta, c);
+    sc_a[c] = invstd * ga;
+    sc_b[c] = be - mean * invstd * ga;
+    if (blockIdx.x == 0) {
+      mean_out[c] = mean;
+      invstd_out[c] = invstd;
+      if (varu_out) varu_out[c] = var * ((float)M / fmaxf((float)M - 1.f, 1.f));
+    }
+  }
+  __syncthreads();
+  float pa[8], pb[8];
+  {
+    const int base = (8 * threadIdx.x) % C;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { pa[e] = sc_a[(base + e) % C]; pb[e] = sc_b[(base + e) % C]; }
+  }
+  const int nvec = M * C / 8;
+  const uint4* sv = reinterpret_cast<const uint4*>(s);
+  uint4* yv = reinterpret_cast<uint4*>(y);
+  for (int v = blockIdx.x * NT + threadIdx.x; v < nvec; v += gridDim.x * NT) {
+    float f[8];
+    unpack8(sv[v], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      f[e] = f[e] * pa[e] + pb[e];
+      if (relu) f[e] = fmaxf(f[e], 0.f);
+    }
+    yv[v] = pack8(f);
+  }
+}
+
+template <typename PT>
+__global__ void __launch_bounds__(NT)
+bn_bwd_reduce_wide_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
+                          const __nv_bfloat16* __restrict__ s, const float* __restrict__ mean,
+                          const float* __restrict__ invstd, const PT* __restrict__ gamma, const PT* __restrict__ beta,
+                          int nvec, int C, int relu, float* __restrict__ ws) {
+  extern __shared__ float smem[];
+  float *sa = smem, *sb = smem + C;
+  float pm[8], pi[8], pg[8], pb[8];
+  {
+    const int base = (8 * threadIdx.x) % C;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = (base + e) % C;
+      pm[e] = mean[c]; pi[e] = invstd[c]; pg[e] = ldp(gamma, c); pb[e] = ldp(beta, c);
+    }
+  }
+  const uint4* sv = reinterpret_cast<const uint4*>(s);
+  const uint4* gv = reinterpret_cast<const uint4*>(dy);
+  const uint4* g2v = reinterpret_cast<const uint4*>(dy2);
+  float a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
+  for (int v = blockIdx.x * NT + threadIdx.x; v < nvec; v += gridDim.x * NT) {
+    float x[8], g[8];
+    unpack8(sv[v], x);
+    unpack8(gv[v], g);
+    if (dy2) {
+      float t[8];
+      unpack8(g2v[v], t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] += t[e];
+      unpack8(pack8(g), g);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xh = (x[e] - pm[e]) * pi[e];
+      const float pre = x[e] * (pi[e] * pg[e]) + (pb[e] - pm[e] * pi[e] * pg[e]);
+      const float ge = (!relu || pre > 0.f) ? g[e] : 0.f;
+      a[e] += ge;
+      b[e] += ge * xh;
+    }
+  }
+  cta_channel_reduce(a, b, C, sa, sb, smem + 2 * C);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { atomicAdd(&ws[c], sa[c]); atomicAdd(&ws[C + c], sb[c]); }
+}
+
+template <typename PT>
+__global__ void __launch_bounds__(NT)
+bn_bwd_apply_wide_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
+                         const __nv_bfloat16* __restrict__ dres, const __nv_bfloat16* __restrict__ s,
+                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                         const PT* __restrict__ gamma, const PT* __restrict__ beta, int M, int C, int relu,
+                         const float* __restrict__ ws, __nv_bfloat16* __restrict__ ds, PT* __restrict__ dgamma,
+                         PT* __restrict__ dbeta) {
+  float pm[8], pi[8], pg[8], pb[8], qa[8], qb[8];
+  const float inv_n = 1.f / (float)M;
+  {
+    const int base = (8 * threadIdx.x) % C;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = (base + e) % C;
+      pm[e] = mean[c]; pi[e] = invstd[c]; pg[e] = ldp(gamma, c); pb[e] = ldp(beta, c);
+      qa[e] = ws[c] * inv_n; qb[e] = ws[C + c] * inv_n;
+    }
+  }
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { stp(dbeta, c, ws[c]); stp(dgamma, c, ws[C + c]); }
+  const int nvec = M * C / 8;
+  const uint4* sv = reinterpret_cast<const uint4*>(s);
+  const uint4* gv = reinterpret_cast<const uint4*>(dy);
+  const uint4* g2v = reinterpret_cast<const uint4*>(dy2);
+  const uint4* rv = reinterpret_cast<const uint4*>(dres);
+  uint4* dv = reinterpret_cast<uint4*>(ds);
+  for (int v = blockIdx.x * NT + threadIdx.x; v < nvec; v += gridDim.x * NT) {
+    float x[8], g[8], o[8], r[8];
+    unpack8(sv[v], x);
+    unpack8(gv[v], g);
+    if (dy2) {
+      float t[8];
+      unpack8(g2v[v], t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] += t[e];
+      unpack8(pack8(g), g);
+    }
+    if (dres) unpack8(rv[v], r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xh = (x[e] - pm[e]) * pi[e];
+      const float pre = x[e] * (pi[e] * pg[e]) + (pb[e] - pm[e] * pi[e] * pg[e]);
+      const float ge = (!relu || pre > 0.f) ? g[e] : 0.f;
+      o[e] = pg[e] * pi[e] * (ge - qa[e] - xh * qb[e]);
+      if (dres) o[e] += r[e];
+    }
+    dv[v] = pack8(o);
+  }
+}
+
 }  // namespace hfl
 
 using namespace hfl;
@@ -432,7 +615,7 @@ using namespace hfl;
 // NV == 0 selects the looping kernel (very large groups only).
 static void pick_shape(long elems, int& K, int& NV) {
   const long nvec = elems / 8;
-  const int nvs[4] = {1, 2, 4, 10};
+  const int nvs[4] = {1, 2, 4, 10};   // NV=10 only reachable for multi-group (ghost batch) launches
   for (int ki = 0; ki < 5; ++ki) {
     const int kk = 1 << ki;                       // 1, 2, 4, 8, 16
     for (int ni = 0; ni < 4; ++ni) {
@@ -475,9 +658,36 @@ static cudaError_t launch_cluster(Kern kern, dim3 grid, int cluster_x, size_t sm
     default: { constexpr int NVC = 0; CALL; break; }  \
   }
 
+static const long WIDE_ELEMS = 16L * NT * 4 * 8;     // above this a single group uses the split (2-launch) path
+static size_t wide_smem(int C) { return (2 * (size_t)C + 2 * 16 * (size_t)(C < 256 ? C : 256)) * sizeof(float); }
+static int wide_grid(long nvec) {
+  long b = (nvec + NT * 2 - 1) / (NT * 2);
+  if (b > 148 * 2) b = 148 * 2;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
 extern "C" int hfl_bn_act_fwd(const void* x, const void* res, void* s_out, void* y, const void* gamma,
                               const void* beta, int param_bf16, float eps, int groups, int Mg, int C, int relu,
-                              float* mean_out, float* invstd_out, float* varu_out, cudaStream_t stream) {
+                              float* mean_out, float* invstd_out, float* varu_out, float* ws, cudaStream_t stream) {
+  if (groups == 1 && (long)Mg * C > WIDE_ELEMS && ws != nullptr) {
+    const int nvec = Mg * C / 8;
+    const int grid = wide_grid(nvec);
+    cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(float), stream);
+    bn_stats_wide_kernel<<<grid, NT, wide_smem(C), stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res,
+                                                             (__nv_bfloat16*)s_out, nvec, C, ws);
+    const void* sin = res ? s_out : x;
+    if (param_bf16)
+      bn_apply_wide_kernel<__nv_bfloat16><<<grid, NT, 2 * C * sizeof(float), stream>>>(
+          (const __nv_bfloat16*)sin, (__nv_bfloat16*)y, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, eps, Mg, C,
+          relu, ws, mean_out, invstd_out, varu_out);
+    else
+      bn_apply_wide_kernel<float><<<grid, NT, 2 * C * sizeof(float), stream>>>(
+          (const __nv_bfloat16*)sin, (__nv_bfloat16*)y, (const float*)gamma, (const float*)beta, eps, Mg, C, relu, ws,
+          mean_out, invstd_out, varu_out);
+    count_launch(2);
+    return (int)cudaGetLastError();
+  }
   int K, NV;
   pick_shape((long)Mg * C, K, NV);
   const size_t smem = (6 * (size_t)C + 2 * 16 * (size_t)(C < 256 ? C : 256)) * sizeof(float);
@@ -511,8 +721,32 @@ extern "C" void hfl_affine_act(const void* x, const void* res, void* s_out, void
 
 extern "C" int hfl_bn_act_bwd(const void* dy, const void* dy2, const void* dres, const void* s, const float* mean,
                               const float* invstd, const void* gamma, const void* beta, int param_bf16, int M, int C,
-                              int hw, float dy_scale, int relu, void* ds, void* dgamma, void* dbeta,
+                              int hw, float dy_scale, int relu, void* ds, void* dgamma, void* dbeta, float* ws,
                               cudaStream_t stream) {
+  if (hw == 0 && (long)M * C > WIDE_ELEMS && ws != nullptr) {
+    const int nvec = M * C / 8;
+    const int grid = wide_grid(nvec);
+    cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(float), stream);
+    if (param_bf16) {
+      bn_bwd_reduce_wide_kernel<__nv_bfloat16><<<grid, NT, wide_smem(C), stream>>>(
+          (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)s, mean, invstd,
+          (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, nvec, C, relu, ws);
+      bn_bwd_apply_wide_kernel<__nv_bfloat16><<<grid, NT, 0, stream>>>(
+          (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean,
+          invstd, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, M, C, relu, ws, (__nv_bfloat16*)ds,
+          (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta);
+    } else {
+      bn_bwd_reduce_wide_kernel<float><<<grid, NT, wide_smem(C), stream>>>(
+          (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)s, mean, invstd, (const float*)gamma,
+          (const float*)beta, nvec, C, relu, ws);
+      bn_bwd_apply_wide_kernel<float><<<grid, NT, 0, stream>>>(
+          (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean,
+          invstd, (const float*)gamma, (const float*)beta, M, C, relu, ws, (__nv_bfloat16*)ds, (float*)dgamma,
+          (float*)dbeta);
+    }
+    count_launch(2);
+    return (int)cudaGetLastError();
+  }
   int K, NV;
   pick_shape((long)M * C, K, NV);
   const size_t smem = (6 * (size_t)C + 2 * 16 * (size_t)(C < 256 ? C : 256)) * sizeof(float);

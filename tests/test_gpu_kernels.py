@@ -263,3 +263,32 @@ def test_tcgen05_gemm_matches_torch(M, N, K):
         wb = torch.randn(N, K + 16, device=dev).bfloat16()
         y3 = cu.C().gemm_bf16_tn(xb[:, :K], wb[:, 8:8 + K], None, 1.0, False, True)
         assert torch.allclose(y3, xb[:, :K].float() @ wb[:, 8:8 + K].float().t(), atol=1e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("N,C,H,K,R,stride", [(10, 64, 32, 64, 3, 1), (10, 64, 32, 128, 3, 2), (10, 128, 16, 128, 3, 1),
+                                               (10, 64, 32, 128, 1, 2), (10, 256, 8, 256, 3, 1), (10, 256, 8, 512, 3, 2),
+                                               (10, 512, 4, 512, 3, 1), (3, 128, 16, 256, 1, 2), (64, 64, 32, 64, 3, 1)])
+def test_tcgen05_conv_fprop_matches_torch(N, C, H, K, R, stride):
+    cu = _cu()
+    dev = torch.device("cuda")
+    torch.manual_seed(N + C + K + R)
+    x = torch.randn(N, C, H, H, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(K, C, R, R, device=dev) / (C * R * R) ** 0.5).bfloat16().contiguous(memory_format=torch.channels_last)
+    if R == 1:
+        w = w.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    assert cu.C().conv_tc_supported(N, H, H, C, K, R, R, stride)
+    ref = torch.nn.functional.conv2d(x.float(), w.float(), None, stride, R // 2)
+    y = cu.C().conv_fprop_tc(x, w, None, None, stride)
+    torch.cuda.synchronize()
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    err = float((y.float() - ref).abs().max())
+    assert err < 3e-2 * max(1.0, float(ref.abs().max())), err
+    # fused epilogue: residual add + BatchNorm batch statistics of the output
+    res = torch.randn_like(ref).bfloat16().contiguous(memory_format=torch.channels_last)
+    stats = torch.zeros(2, K, device=dev)
+    y2 = cu.C().conv_fprop_tc(x, w, res, stats, stride)
+    ref2 = (ref + res.float())
+    assert float((y2.float() - ref2).abs().max()) < 4e-2 * max(1.0, float(ref2.abs().max()))
+    yf = y2.float()
+    assert torch.allclose(stats[0], yf.sum(dim=(0, 2, 3)), rtol=2e-3, atol=0.5)
+    assert torch.allclose(stats[1], (yf * yf).sum(dim=(0, 2, 3)), rtol=2e-3, atol=0.5)
