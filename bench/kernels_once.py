@@ -1,0 +1,59 @@
+"""Run each hand-written kernel a few times on representative shapes (target for `ncu -k regex:...`)."""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from hfl_b200.config.control import make_cfg
+from hfl_b200.ops import cuda as cu
+from hfl_b200.ops import fed_ops
+from hfl_b200.ops import fused as fo
+from hfl_b200.plan.layout import build_tables
+from hfl_b200.plan.spec import build_spec
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+dev = torch.device("cuda")
+C = cu.C()
+reps = 5
+
+if which in ("all", "conv"):
+    x = torch.randn(2560, 64, 32, 32, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(64, 64, 3, 3, device=dev) * 0.05).bfloat16().contiguous(memory_format=torch.channels_last)
+    for _ in range(reps):
+        C.conv_fprop_tc(x, w, None, None, 1)
+    x2 = torch.randn(2560, 256, 8, 8, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    w2 = (torch.randn(256, 256, 3, 3, device=dev) * 0.02).bfloat16().contiguous(memory_format=torch.channels_last)
+    for _ in range(reps):
+        C.conv_fprop_tc(x2, w2, None, None, 1)
+if which in ("all", "gemm"):
+    a = torch.randn(8192, 4096, device=dev).bfloat16()
+    b = torch.randn(4096, 4096, device=dev).bfloat16()
+    for _ in range(reps):
+        C.gemm_bf16_tn(a, b, None, 1.0, False, False)
+    a2 = torch.randn(64, 256, device=dev).bfloat16()
+    b2 = torch.randn(33278, 256, device=dev).bfloat16()
+    for _ in range(reps):
+        C.gemm_bf16_tn(a2, b2, None, 1.0, False, False)
+if which in ("all", "fed"):
+    cfg = make_cfg("CIFAR10", "resnet18", "1_800_0.1_non-iid-2_fix_a2-b8_bn_1_1", classes_size=10)
+    spec = build_spec(cfg)
+    tables = build_tables(spec, 1.0, [1.0, 0.5], channels_last=True)
+    g = torch.randn(tables.global_layout.size, device=dev)
+    levels = [0] * 16 + [1] * 64
+    arenas = [torch.randn(tables.level_layouts[l].size, device=dev) for l in levels]
+    masks = [torch.ones(10, dtype=torch.uint8) for _ in levels]
+    wc = [torch.zeros(a.numel(), device=dev, dtype=torch.bfloat16) for a in arenas]
+    mom = [torch.zeros_like(a) for a in arenas]
+    for _ in range(reps):
+        fed_ops.distribute(tables, g, arenas, levels, wc, mom)
+        fed_ops.aggregate(tables, g, arenas, levels, masks)
+if which in ("all", "norm"):
+    for (Cc, H) in ((64, 32), (256, 8)):
+        x = torch.randn(10, Cc, H, H, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+        ga = torch.ones(Cc, device=dev).bfloat16()
+        be = torch.zeros(Cc, device=dev).bfloat16()
+        for _ in range(reps):
+            s, y, m, iv, _ = fo.bn_act_fwd(x, None, ga, be, 1e-5)
+            fo.bn_act_bwd(y, None, None, x, m, iv, ga, be, torch.empty_like(ga), torch.empty_like(be))
+torch.cuda.synchronize()
+print("done", which)

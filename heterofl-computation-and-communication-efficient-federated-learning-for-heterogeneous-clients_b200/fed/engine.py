@@ -163,13 +163,16 @@ class Engine:
             ga.copy_(self.global_arena)
             self.global_arena = ga
             self.federation.global_arena = ga
+            self._peer.enable_all_reduce()
             self._peer.exchange()
+            from ..parallel.dist import set_peer_pool
+            set_peer_pool(self._peer)       # sBN statistic merge goes over peer memory too (fp32 vectors)
         return b
 
     def _round_arena_bytes(self) -> int:
         n_act = int(np.ceil(self.cfg["frac"] * self.cfg["num_users"]))
         biggest = self.tables.level_layouts[0].size
-        return (n_act * biggest + self.global_arena.numel()) * 4 + (1 << 20)
+        return (n_act * biggest + self.global_arena.numel()) * 4 + (2 << 20)
 
     # -- data staging --------------------------------------------------------------------------------------
     def _stage_data(self) -> None:

@@ -16,13 +16,14 @@ from typing import Dict, Optional
 import torch
 import torch.nn.functional as F
 
+from ..ops.linear import tc_linear
 from ..ops.nn import NormCtx, layer_norm_scaled, masked_cross_entropy, masked_logits
 from ..plan.spec import ModelSpec
 
 
 def _linear(x, w, b, alpha: float = 1.0):
-    y = F.linear(x, w, b)
-    return y if alpha == 1.0 else y * alpha
+    """``alpha * (x W^T + b)`` -- tcgen05 GEMM with the Scaler as its alpha on the GPU, F.linear elsewhere."""
+    return tc_linear(x, w, b, alpha)
 
 
 def transformer_forward(spec: ModelSpec, P: Dict[str, torch.Tensor], inp: Dict, ctx: NormCtx, scale_rate: float,
@@ -51,16 +52,16 @@ def transformer_forward(spec: ModelSpec, P: Dict[str, torch.Tensor], inp: Dict, 
     temp = math.sqrt(dh)
     for l in range(L):
         pre = "transformer_encoder.layers.%d" % l
-        q = F.linear(x, P[pre + ".mha.linear_q.weight"], P[pre + ".mha.linear_q.bias"])
-        k = F.linear(x, P[pre + ".mha.linear_k.weight"], P[pre + ".mha.linear_k.bias"])
-        v = F.linear(x, P[pre + ".mha.linear_v.weight"], P[pre + ".mha.linear_v.bias"])
+        q = _linear(x, P[pre + ".mha.linear_q.weight"], P[pre + ".mha.linear_q.bias"])
+        k = _linear(x, P[pre + ".mha.linear_k.weight"], P[pre + ".mha.linear_k.bias"])
+        v = _linear(x, P[pre + ".mha.linear_v.weight"], P[pre + ".mha.linear_v.bias"], inv)
         q = q.view(N, S, H, dh).transpose(1, 2)
         k = k.view(N, S, H, dh).transpose(1, 2)
         v = v.view(N, S, H, dh).transpose(1, 2)
         # (q/s)(k/s)^T / temp: the q/k scalers fold into the softmax scale; v/s and the post-projection
         # scaler are plain alpha factors
         att = torch.softmax((q @ k.transpose(-2, -1)) * (inv * inv / temp), dim=-1)
-        o = (att @ (v if s == 1.0 else v * inv)).transpose(1, 2).reshape(N, S, E)
+        o = (att @ v).transpose(1, 2).reshape(N, S, E)      # v already carries its 1/s (GEMM alpha)
         o = _linear(o, P[pre + ".mha.linear_o.weight"], P[pre + ".mha.linear_o.bias"], inv)
         x = F.layer_norm(x + F.dropout(o, p_drop, train), (E,), P[pre + ".norm1.weight"], P[pre + ".norm1.bias"])
         h = F.gelu(_linear(x, P[pre + ".linear1.weight"], P[pre + ".linear1.bias"], inv))
@@ -68,7 +69,7 @@ def transformer_forward(spec: ModelSpec, P: Dict[str, torch.Tensor], inp: Dict, 
         x = F.layer_norm(x + F.dropout(h, p_drop, train), (E,), P[pre + ".norm2.weight"], P[pre + ".norm2.bias"])
     d = F.gelu(_linear(x, P["decoder.linear1.weight"], P["decoder.linear1.bias"], inv))
     d = F.layer_norm(d, (E,), P["decoder.norm1.weight"], P["decoder.norm1.bias"])
-    logits = F.linear(d, P["decoder.linear2.weight"], P["decoder.linear2.bias"]).reshape(N * S, V)
+    logits = _linear(d, P["decoder.linear2.weight"], P["decoder.linear2.bias"]).reshape(N * S, V)
     out = {"loss": masked_cross_entropy(logits, tokens.reshape(-1), label_mask, inp.get("_meter"))}
     if want_score:
         out["score"] = masked_logits(logits.float(), label_mask).view(N, S, V).permute(0, 2, 1)

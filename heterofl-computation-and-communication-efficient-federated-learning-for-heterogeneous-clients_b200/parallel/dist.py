@@ -53,9 +53,22 @@ def barrier(info: DistInfo) -> None:
         dist.barrier()
 
 
+_PEER_POOL = None
+
+
+def set_peer_pool(pool) -> None:
+    """Route small all-reduces through the peer-memory kernel path (``parallel/peer.py``) instead of NCCL."""
+    global _PEER_POOL
+    _PEER_POOL = pool
+
+
 def all_reduce_sum(info: DistInfo, t: torch.Tensor) -> torch.Tensor:
     if info.world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if _PEER_POOL is not None and t.is_cuda and t.numel() <= _PEER_POOL.SCRATCH_FLOATS \
+                and t.dtype in (torch.float32,):
+            _PEER_POOL.all_reduce_sum_(t)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
 
 

@@ -100,6 +100,32 @@ class PeerPool:
         self.epoch += 1
         self.C.peer_barrier(self._flag_ptrs, self.info.rank, self.info.world, self.epoch, self.err)
 
+    # -- small one-shot all-reduce over peer memory (sBN statistic merge, metric merge) ----------------------------
+    SCRATCH_FLOATS = 1 << 16
+
+    def enable_all_reduce(self) -> None:
+        """Reserve the persistent scratch slab (must be called on every rank BEFORE ``exchange``)."""
+        self._scratch = self.alloc_persistent(self.SCRATCH_FLOATS, torch.float32)
+        self._scratch_ptrs = None
+
+    def all_reduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place sum of a small fp32/fp64 tensor over all ranks: every rank publishes its values in its pool slab,
+        a flag barrier orders the stores, ``peer_sum_kernel`` reads all slabs over NVLink, a second barrier frees the
+        slab for the next call.  No NCCL, no host synchronisation."""
+        n = t.numel()
+        assert n <= self.SCRATCH_FLOATS, "all_reduce_sum_ is meant for small vectors"
+        if self._scratch_ptrs is None:
+            off = self._scratch._hfl_pool_offset
+            self._scratch_ptrs = torch.tensor([b + off for b in self.peer_base], dtype=torch.int64).to(self.info.device)
+        src = t.reshape(-1)
+        self._scratch[:n].copy_(src.to(torch.float32))
+        self.barrier()
+        out = torch.empty(n, dtype=torch.float32, device=self.info.device)
+        self.C.peer_sum(self._scratch_ptrs, out)
+        self.barrier()
+        src.copy_(out.to(t.dtype))
+        return t
+
     def check(self) -> None:
         if int(self.err.item()) != 0:
             raise RuntimeError("peer barrier timed out (a rank did not arrive)")

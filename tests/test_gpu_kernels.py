@@ -292,3 +292,21 @@ def test_tcgen05_conv_fprop_matches_torch(N, C, H, K, R, stride):
     yf = y2.float()
     assert torch.allclose(stats[0], yf.sum(dim=(0, 2, 3)), rtol=2e-3, atol=0.5)
     assert torch.allclose(stats[1], (yf * yf).sum(dim=(0, 2, 3)), rtol=2e-3, atol=0.5)
+
+
+def test_tc_linear_forward_backward():
+    _cu()
+    from hfl_b200.ops.linear import tc_linear
+    dev = torch.device("cuda")
+    torch.manual_seed(3)
+    x = torch.randn(2, 64, 256, device=dev).bfloat16().requires_grad_(True)
+    w = (torch.randn(512, 256, device=dev) * 0.05).bfloat16().requires_grad_(True)
+    b = (torch.randn(512, device=dev) * 0.1).bfloat16().requires_grad_(True)
+    y = tc_linear(x, w, b, 0.5)
+    (y.float() ** 2).sum().backward()
+    xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, b))
+    yr = torch.nn.functional.linear(xr, wr, br) * 0.5
+    (yr ** 2).sum().backward()
+    assert torch.allclose(y.float(), yr, atol=3e-2, rtol=3e-2)
+    for a, r in ((x, xr), (w, wr), (b, br)):
+        assert torch.allclose(a.grad.float(), r.grad, atol=0.05 * float(r.grad.abs().max()), rtol=5e-2)
