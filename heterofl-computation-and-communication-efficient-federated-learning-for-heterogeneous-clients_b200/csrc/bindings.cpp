@@ -38,6 +38,8 @@ int hfl_head_fwd_bwd(const void*, int, int, int, const void*, const void*, int, 
 int hfl_conv_tc_supported(int, int, int, int, int, int, int, int);
 int hfl_conv_fprop_tc(const void*, const void*, void*, const void*, float*, int, int, int, int, int, int, int, int,
                       cudaStream_t);
+int hfl_gemm_bf16_general(const void*, int, int, const void*, int, int, void*, int, int, float, int, int, int,
+                          cudaStream_t);
 long hfl_launch_count();
 void hfl_launch_count_add(long);
 void hfl_peer_barrier(const void*, int, int, unsigned, int*, cudaStream_t);
@@ -305,6 +307,25 @@ torch::Tensor gemm_bf16_tn(torch::Tensor x, torch::Tensor w, c10::optional<torch
   return y;
 }
 
+// C[M,N] = alpha * op(A) . op(B)^T with explicit layouts: a is [M,K] (a_mn=false) or [K,M] (a_mn=true); b is [N,K]
+// (b_mn=false) or [K,N] (b_mn=true); all row-major with the last dim contiguous.
+torch::Tensor gemm_bf16_general(torch::Tensor a, bool a_mn, torch::Tensor b, bool b_mn, double alpha, bool out_fp32) {
+  CHECK_CUDA_T(a); CHECK_CUDA_T(b);
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.scalar_type() == torch::kBFloat16 && b.scalar_type() == torch::kBFloat16);
+  TORCH_CHECK(a.stride(1) == 1 && b.stride(1) == 1);
+  const int64_t M = a_mn ? a.size(1) : a.size(0), K = a_mn ? a.size(0) : a.size(1);
+  const int64_t N = b_mn ? b.size(1) : b.size(0), Kb = b_mn ? b.size(0) : b.size(1);
+  TORCH_CHECK(K == Kb, "gemm_bf16_general: reduction dims differ");
+  TORCH_CHECK(a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0 && a.size(1) % 8 == 0 && b.size(1) % 8 == 0);
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(a.data_ptr()) & 15) == 0 && (reinterpret_cast<uintptr_t>(b.data_ptr()) & 15) == 0);
+  c10::cuda::CUDAGuard guard(a.device());
+  auto y = torch::empty({M, N}, torch::TensorOptions().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16).device(a.device()));
+  int e = hfl_gemm_bf16_general(a.data_ptr(), (int)a.stride(0), a_mn ? 1 : 0, b.data_ptr(), (int)b.stride(0), b_mn ? 1 : 0,
+                                y.data_ptr(), (int)N, out_fp32 ? 0 : 1, (float)alpha, (int)M, (int)N, (int)K, cur_stream());
+  TORCH_CHECK(e == 0, "gemm_bf16_general failed with code ", e);
+  return y;
+}
+
 // ---- tcgen05 implicit-GEMM convolution (forward) ---------------------------------------------------------
 bool conv_tc_supported(int64_t N, int64_t H, int64_t W, int64_t C, int64_t Kout, int64_t R, int64_t S, int64_t stride) {
   return hfl_conv_tc_supported((int)N, (int)H, (int)W, (int)C, (int)Kout, (int)R, (int)S, (int)stride) == 0;
@@ -398,6 +419,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("head_fwd_bwd", &head_fwd_bwd);
   m.def("head_smem_bytes", &hfl_head_smem_bytes);
   m.def("gemm_bf16_tn", &gemm_bf16_tn);
+  m.def("gemm_bf16_general", &gemm_bf16_general);
   m.def("conv_tc_supported", &conv_tc_supported);
   m.def("conv_fprop_tc", &conv_fprop_tc);
   m.def("launch_count", &hfl_launch_count);

@@ -114,11 +114,26 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                                // layout type SWIZZLE_128B,  bits [61,64)
   return d;
 }
-// kind::f16 instruction descriptor: bf16 A/B (K-major), fp32 accumulate   (cute::UMMA::InstrDescriptor bit layout)
-__device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
+// MN-major operand tile (the M/N index is the contiguous one): built from 64(mn) x 64(k) TMA boxes with
+// CU_TENSOR_MAP_SWIZZLE_128B; canonical layout ((8,8,m),(8,k)):((1,8,LBO),(64,SBO)) in elements:
+//   64 contiguous mn-elements (128 B) per k-row, 8 k-rows per 1024-byte swizzle atom (SBO = 1024 B),
+//   the next 64 mn-elements one whole box further (LBO = 64 rows x 128 B = 8192 B).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;                      // leading byte offset: next 64-element mn block
+  d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset: next group of 8 k-rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: bf16 A/B, fp32 accumulate   (cute::UMMA::InstrDescriptor bit layout)
+__device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, bool a_mn = false, bool b_mn = false) {
   return (1u << 4)                   // c_format = F32
          | (1u << 7)                 // a_format = BF16
          | (1u << 10)                // b_format = BF16
+         | ((a_mn ? 1u : 0u) << 15)  // a_major: 0 = K-major, 1 = MN-major
+         | ((b_mn ? 1u : 0u) << 16)  // b_major
          | ((uint32_t)(N >> 3) << 17)  // n_dim
          | ((uint32_t)(M >> 4) << 24); // m_dim
 }

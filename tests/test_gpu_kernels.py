@@ -310,3 +310,20 @@ def test_tc_linear_forward_backward():
     assert torch.allclose(y.float(), yr, atol=3e-2, rtol=3e-2)
     for a, r in ((x, xr), (w, wr), (b, br)):
         assert torch.allclose(a.grad.float(), r.grad, atol=0.05 * float(r.grad.abs().max()), rtol=5e-2)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 192), (64, 512, 640), (200, 136, 72)])
+def test_tcgen05_gemm_general_layouts(a_mn, b_mn, M, N, K):
+    """MN-major (transposed-in-memory) operands through UMMA descriptors: what dgrad / wgrad GEMMs need."""
+    cu = _cu()
+    dev = torch.device("cuda")
+    torch.manual_seed(M * 3 + N * 5 + K)
+    A = torch.randn(M, K, device=dev).bfloat16()
+    B = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    ref = A.float() @ B.float().t()
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    y = cu.C().gemm_bf16_general(a, a_mn, b, b_mn, 1.0, True)
+    torch.cuda.synchronize()
+    assert torch.allclose(y, ref, atol=3e-3, rtol=3e-3), float((y - ref).abs().max())
