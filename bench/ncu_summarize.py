@@ -1,0 +1,68 @@
+"""Turn gpurun_out/*.ncu-rep into committed summaries under profiles/ (run on the CPU box: `ncu -i` needs no GPU)."""
+import csv
+import io
+import json
+import os
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__cluster_size",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+        "smsp__cycles_active.avg", "sm__cycles_elapsed.avg.per_second"]
+
+
+def raw_rows(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    if len(rows) < 3:
+        return []
+    header, units = rows[0], rows[1]
+    recs = []
+    for r in rows[2:]:
+        recs.append({h: (v, u) for h, v, u in zip(header, r, units)})
+    return recs
+
+
+def main():
+    src = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out"
+    dst = sys.argv[2] if len(sys.argv) > 2 else "profiles"
+    os.makedirs(dst, exist_ok=True)
+    peaks = json.load(open("MEASURED_PEAKS.json")) if os.path.exists("MEASURED_PEAKS.json") else {}
+    for fn in sorted(os.listdir(src)):
+        if not fn.endswith(".ncu-rep"):
+            continue
+        recs = raw_rows(os.path.join(src, fn))
+        lines = ["# %s" % fn, "", "`ncu --set full --clock-control none --import-source on` on one B200 (see bench/ncu_capture.sh).",
+                 "Roofline denominators (MEASURED_PEAKS.json): HBM %s GB/s, bf16 %s TFLOP/s (burst)." % (
+                     peaks.get("hbm_gbs"), peaks.get("bf16_tflops")), ""]
+        for rec in recs:
+            name = rec.get("Kernel Name", ("?", ""))[0]
+            lines.append("## `%s`" % name[:140])
+            lines.append("")
+            lines.append("| metric | value | unit |")
+            lines.append("|---|---|---|")
+            for k in KEYS:
+                if k in rec:
+                    lines.append("| %s | %s | %s |" % (k, rec[k][0], rec[k][1]))
+            try:
+                t_ns = float(rec["gpu__time_duration.sum"][0].replace(",", ""))
+                rd = float(rec["dram__bytes_read.sum"][0].replace(",", ""))
+                wr = float(rec["dram__bytes_write.sum"][0].replace(",", ""))
+                unit = rec["dram__bytes_read.sum"][1]
+                scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+                tunit = {"ns": 1e-9, "us": 1e-6, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9}.get(rec["gpu__time_duration.sum"][1], 1e-9)
+                gbs = (rd + wr) * scale / (t_ns * tunit) / 1e9
+                lines.append("| derived DRAM GB/s | %.1f (%.2f of measured copy peak) | |" % (gbs, gbs / peaks.get("hbm_gbs", 6478.3)))
+            except Exception:
+                pass
+            lines.append("")
+        with open(os.path.join(dst, fn.replace(".ncu-rep", ".md")), "w") as f:
+            f.write("\n".join(lines) + "\n")
+        print("wrote", fn, len(recs), "kernels")
+
+
+if __name__ == "__main__":
+    main()

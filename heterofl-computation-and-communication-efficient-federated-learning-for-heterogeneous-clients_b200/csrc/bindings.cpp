@@ -184,7 +184,7 @@ std::vector<torch::Tensor> bn_act_fwd(torch::Tensor x, c10::optional<torch::Tens
   auto fopt = torch::TensorOptions().dtype(torch::kFloat32).device(x.device());
   auto stats = torch::empty({3, groups, C}, fopt);
   float* sp = stats.data_ptr<float>();
-  auto ws = torch::empty({2, C}, fopt);           // scratch of the split (wide) path
+  auto ws = torch::empty({groups, 2, C}, fopt);   // scratch of the split (wide) path
   int e = hfl_bn_act_fwd(x.data_ptr(), optp(res), res.has_value() ? s.data_ptr() : nullptr, y.data_ptr(),
                          gamma.data_ptr(), beta.data_ptr(), pb ? 1 : 0, (float)eps, (int)groups, (int)(M / groups),
                          (int)C, relu ? 1 : 0, sp, sp + groups * C, sp + 2 * groups * C, ws.data_ptr<float>(),

@@ -437,18 +437,21 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
 __global__ void __launch_bounds__(NT)
 bn_stats_wide_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                      __nv_bfloat16* __restrict__ s_out, int nvec, int C, float* __restrict__ ws) {
+  // blockIdx.y = statistics group (ghost batch); nvec = vectors per group; ws = [G][2][C]
   extern __shared__ float smem[];
   float *sa = smem, *sb = smem + C;
-  const uint4* xv = reinterpret_cast<const uint4*>(x);
-  const uint4* rv = reinterpret_cast<const uint4*>(res);
-  uint4* sv = reinterpret_cast<uint4*>(s_out);
+  const long goff = (long)blockIdx.y * nvec;
+  ws += (long)blockIdx.y * 2 * C;
+  const uint4* xv = reinterpret_cast<const uint4*>(x) + goff;
+  const uint4* rv = res ? reinterpret_cast<const uint4*>(res) + goff : nullptr;
+  uint4* sv = s_out ? reinterpret_cast<uint4*>(s_out) + goff : nullptr;
   float a[8], b[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
   for (int v = blockIdx.x * NT + threadIdx.x; v < nvec; v += gridDim.x * NT) {
     float f[8];
     unpack8(xv[v], f);
-    if (res) {
+    if (rv) {
       float r[8];
       unpack8(rv[v], r);
 #pragma unroll
@@ -473,6 +476,15 @@ bn_apply_wide_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restr
   extern __shared__ float smem[];
   float *sc_a = smem, *sc_b = smem + C;
   const float inv_n = 1.f / (float)M;
+  {   // blockIdx.y = statistics group
+    const long g = blockIdx.y;
+    ws += g * 2 * C;
+    mean_out += g * C;
+    invstd_out += g * C;
+    if (varu_out) varu_out += g * C;
+    s += g * (long)M * C;
+    y += g * (long)M * C;
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float mean = ws[c] * inv_n;
     const float var = fmaxf(ws[C + c] * inv_n - mean * mean, 0.f);
@@ -658,7 +670,7 @@ static cudaError_t launch_cluster(Kern kern, dim3 grid, int cluster_x, size_t sm
     default: { constexpr int NVC = 0; CALL; break; }  \
   }
 
-static const long WIDE_ELEMS = 16L * NT * 4 * 8;     // above this a single group uses the split (2-launch) path
+static const long WIDE_ELEMS = 128L * 1024;          // per-group elements above which the split (2-launch) path wins
 static size_t wide_smem(int C) { return (2 * (size_t)C + 2 * 16 * (size_t)(C < 256 ? C : 256)) * sizeof(float); }
 static int wide_grid(long nvec) {
   long b = (nvec + NT * 2 - 1) / (NT * 2);
@@ -670,10 +682,12 @@ static int wide_grid(long nvec) {
 extern "C" int hfl_bn_act_fwd(const void* x, const void* res, void* s_out, void* y, const void* gamma,
                               const void* beta, int param_bf16, float eps, int groups, int Mg, int C, int relu,
                               float* mean_out, float* invstd_out, float* varu_out, float* ws, cudaStream_t stream) {
-  if (groups == 1 && (long)Mg * C > WIDE_ELEMS && ws != nullptr) {
+  if ((long)Mg * C > WIDE_ELEMS && ws != nullptr) {
     const int nvec = Mg * C / 8;
-    const int grid = wide_grid(nvec);
-    cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(float), stream);
+    int gx = wide_grid(nvec);
+    if (groups > 1 && gx > 16) gx = 16;           // many groups already fill the machine
+    dim3 grid(gx, groups);
+    cudaMemsetAsync(ws, 0, 2 * (size_t)C * groups * sizeof(float), stream);
     bn_stats_wide_kernel<<<grid, NT, wide_smem(C), stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res,
                                                              (__nv_bfloat16*)s_out, nvec, C, ws);
     const void* sin = res ? s_out : x;

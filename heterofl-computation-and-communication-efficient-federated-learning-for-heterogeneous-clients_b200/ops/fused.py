@@ -4,6 +4,7 @@ Activations are logical ``[N, C, H, W]`` tensors with channels-last strides (phy
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -104,7 +105,31 @@ def bn_act_bwd(dy: torch.Tensor, dy2: Optional[torch.Tensor], dres: Optional[tor
     return ds
 
 
+# tcgen05 implicit-GEMM forward convolution: "off" | "on" (whenever the shape qualifies) | "auto" (qualifying shapes
+# with at least CONV_TC_MIN_PIXELS output pixels -- the regime where it beats the library, see profiles/conv_bench.md)
+CONV_TC_MODE = os.environ.get("HFL_CONV_TC", "auto")
+CONV_TC_MIN_PIXELS = int(os.environ.get("HFL_CONV_TC_MIN_PIXELS", "100000"))
+
+
+def _tc_conv_ok(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> bool:
+    if CONV_TC_MODE == "off" or not _use_kernels(x) or w.dtype != torch.bfloat16:
+        return False
+    N, C, H, W = x.shape
+    K, _, R, S = w.shape
+    if pad != R // 2 or not x.is_contiguous(memory_format=torch.channels_last):
+        return False
+    if not w.permute(0, 2, 3, 1).is_contiguous():
+        return False
+    if not cu.C().conv_tc_supported(N, H, W, C, K, R, S, stride):
+        return False
+    if CONV_TC_MODE == "auto":
+        return N * (H // stride) * (W // stride) >= CONV_TC_MIN_PIXELS
+    return True
+
+
 def conv_fwd(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> torch.Tensor:
+    if _tc_conv_ok(x, w, stride, pad):
+        return cu.C().conv_fprop_tc(x, w, None, None, stride)
     return F.conv2d(x, w, None, stride, pad)
 
 
