@@ -99,7 +99,7 @@ def run_ours(args):
         cfg["fused"] = False
     eng = Engine(cfg, info, options=EngineOptions(out_dir="/tmp/hfl_bench", quiet=True, save=False,
                                                   max_concurrent=args.max_concurrent,
-                                                  agg_backend=args.agg_backend))
+                                                  agg_backend=args.agg_backend, async_eval=not args.sync_eval))
     eng.setup()
     t0 = time.time()
     eng.prewarm()
@@ -116,6 +116,9 @@ def run_ours(args):
         for k in range(n_rounds):
             last = eng.run_round(first_epoch + k, evaluate=not args.no_eval)
             samples += last["train_n"]
+        ev = eng.collect_eval()            # the last round's evaluation finishes INSIDE the timed region
+        if ev is not None:
+            last["test"] = ev["test"]
         e1.record()
         torch.cuda.synchronize()
         barrier(info)
@@ -127,6 +130,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         eng.run_round(ep, evaluate=not args.no_eval)
         ep += 1
+    eng.collect_eval()
     with ClockSampler(info.local_rank) as cs:
         ms, samples, launches, last = timed(args.steps, ep)
     ep += args.steps
@@ -135,6 +139,7 @@ def run_ours(args):
     # the round's metrics are read back D2H (run_round already does that)
     eng.set_data_residency(False)
     eng.run_round(ep, evaluate=not args.no_eval)
+    eng.collect_eval()
     ep += 1
     eng.h2d_bytes = eng.d2h_bytes = 0
     ms_e, samples_e, _, _ = timed(args.steps, ep)
@@ -153,6 +158,9 @@ def run_ours(args):
             "config": {"model": "%s %s %s" % (data, model, control), "global_batch": cfg["batch_size"]["train"],
                        "seq_len": None, "parallelism": "client-parallel x%d (P2P aggregate)" % info.world,
                        "round": "distribute+local-train+aggregate" + ("" if args.no_eval else "+sBN-stats+test"),
+                       "eval_overlap": "sBN+test of round r overlap local training of round r+1 (side stream); the "
+                                       "last round's evaluation completes inside the timed region"
+                       if not args.sync_eval else "none",
                        "train_samples_per_round": samples / args.steps, "l2": "inputs_exceed_L2 (150 MB train set "
                        "+ per-client arenas streamed every round; no cross-round reuse fits the 126 MB L2)",
                        "local_epochs": cfg["num_epochs"]["local"], "prewarm_s": round(prewarm_s, 1)},
@@ -191,6 +199,8 @@ def main():
     ap.add_argument("--local-epochs", type=int, default=0)
     ap.add_argument("--max-concurrent", type=int, default=16)
     ap.add_argument("--agg-backend", default="auto")
+    ap.add_argument("--sync-eval", action="store_true",
+                    help="run sBN+test of round r before round r+1 starts (default: overlapped on a side stream)")
     ap.add_argument("--no-fused", action="store_true", help="A/B: autograd + library-BN path instead of the fused path")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -682,7 +682,7 @@ static int wide_grid(long nvec) {
 extern "C" int hfl_bn_act_fwd(const void* x, const void* res, void* s_out, void* y, const void* gamma,
                               const void* beta, int param_bf16, float eps, int groups, int Mg, int C, int relu,
                               float* mean_out, float* invstd_out, float* varu_out, float* ws, cudaStream_t stream) {
-  if ((long)Mg * C > WIDE_ELEMS && ws != nullptr) {
+  if (((long)Mg * C > WIDE_ELEMS || groups > 1) && ws != nullptr) {   // ghost batches: always the wide path
     const int nvec = Mg * C / 8;
     int gx = wide_grid(nvec);
     if (groups > 1 && gx > 16) gx = 16;           // many groups already fill the machine

@@ -57,6 +57,7 @@ class EngineOptions:
     save: bool = True
     stats_chunk_groups: int = 256
     test_chunk: int = 2500
+    async_eval: bool = False             # overlap round r's sBN+test with round r+1's training (run_round/collect_eval)
 
 
 class PhaseTimer:
@@ -294,7 +295,11 @@ class Engine:
         all_reduce_sum(info, tm)
         out: Dict = {"epoch": epoch, "lr": lr, "num_active": M, "user_idx": user_idx, "rates": rates}
         # 5. evaluation
-        if evaluate:
+        if evaluate and self._async_eval_ok():
+            self._launch_eval(epoch)
+            out["eval_pending"] = True
+            timer.mark("eval_launch")
+        elif evaluate:
             shared = torch.Generator().manual_seed(self.seed * 1000003 + epoch * 7919 + 104729)
             if self.is_lm:
                 test = self.evaluator.test_lm(self.global_arena, self._h2d(self.test_rows))
@@ -320,6 +325,52 @@ class Engine:
         out["train"], out["train_n"] = train, t[2]
         out["timings_ms"] = timer.result()
         return out
+
+    # -- asynchronous evaluation ----------------------------------------------------------------------------
+    def _async_eval_ok(self) -> bool:
+        return bool(self.opt.async_eval and self.is_cuda and self._agg_backend in ("local", "p2p"))
+
+    def _launch_eval(self, epoch: int) -> None:
+        """Snapshot ``W_g`` and enqueue the sBN + test passes on a low-priority side stream; the next round's
+        training proceeds on the main / slot streams meanwhile.  Results are fetched by :meth:`collect_eval`."""
+        from ..parallel.dist import peer_channel
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_eval_stream", None) is None:
+            self._eval_stream = torch.cuda.Stream(device=self.device, priority=0)
+            self._eval_arena = torch.empty_like(self.global_arena)
+            self._eval_done = None
+            self._eval_result = None
+        if self._eval_done is not None:
+            main.wait_event(self._eval_done)           # previous evaluation must have consumed the snapshot
+        self._eval_arena.copy_(self.global_arena, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        shared = torch.Generator().manual_seed(self.seed * 1000003 + epoch * 7919 + 104729)
+        with torch.cuda.stream(self._eval_stream), peer_channel(1):
+            self._eval_stream.wait_event(ready)
+            if self.is_lm:
+                test = self.evaluator.test_lm(self._eval_arena, self._h2d(self.test_rows), sync=False)
+            else:
+                self.running = self.evaluator.sbn_stats(self._eval_arena, self.dataset["train"],
+                                                        self._h2d(self.train_img), shared)
+                test = self.evaluator.test_vision(self._eval_arena, self.running, self.dataset["test"],
+                                                  self._h2d(self.test_img), self._h2d(self.test_lab), self.test_owner,
+                                                  self.user_masks, sync=False)
+            self._eval_done = torch.cuda.Event()
+            self._eval_done.record(self._eval_stream)
+        self._eval_result = (epoch, test)
+
+    def collect_eval(self) -> Optional[Dict]:
+        """Wait for the most recently launched evaluation and return ``{'epoch', 'test': {...}}`` (None if none)."""
+        if getattr(self, "_eval_result", None) is None:
+            return None
+        self._eval_done.synchronize()
+        epoch, pending = self._eval_result
+        self._eval_result = None
+        test = self.evaluator.finish(pending)
+        self.d2h_bytes += 48
+        return {"epoch": epoch, "test": {k: v for k, v in test.items() if not k.startswith("_")},
+                "_test_n": {k: v for k, v in test.items() if k.startswith("_")}}
 
     def _client_steps(self, u: int) -> int:
         cfg = self.cfg

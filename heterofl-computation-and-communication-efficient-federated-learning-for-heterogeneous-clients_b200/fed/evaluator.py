@@ -106,7 +106,7 @@ class Evaluator:
     @torch.no_grad()
     def test_vision(self, global_arena: torch.Tensor, running: Dict, ds: VisionData, imgs_dev: torch.Tensor,
                     labels_dev: torch.Tensor, owner_dev: Optional[torch.Tensor],
-                    user_masks_dev: Optional[torch.Tensor]) -> Dict[str, float]:
+                    user_masks_dev: Optional[torch.Tensor], sync: bool = True):
         """``owner_dev[i]`` = user whose test split holds sample i (-1: none); ``user_masks_dev [U, classes]``."""
         P = self._params(global_arena)
         ctx = NormCtx("eval", running=running)
@@ -141,16 +141,25 @@ class Evaluator:
                 acc[1] += ((zl.argmax(1) == y) & sel).sum()
                 acc[2] += sel.sum()
         all_reduce_sum(self.info, acc)
+        pending = ("vision", acc, owner_dev is not None)
+        return self.finish(pending) if sync else pending
+
+    @staticmethod
+    def finish(pending) -> Dict[str, float]:
+        """Host read of an evaluation's device accumulator (the only synchronising step)."""
+        kind, acc, flag = pending
         a = acc.tolist()
+        if kind == "lm":
+            return {"Global-Loss": a[0] / max(a[2], 1), "Global-Perplexity": a[1] / max(a[2], 1), "_n_global": a[2]}
         out = {"Global-Loss": a[3] / max(a[5], 1), "Global-Accuracy": 100.0 * a[4] / max(a[5], 1)}
-        if owner_dev is not None:
+        if flag:
             out["Local-Loss"] = a[0] / max(a[2], 1)
             out["Local-Accuracy"] = 100.0 * a[1] / max(a[2], 1)
         out["_n_local"], out["_n_global"] = a[2], a[5]
         return out
 
     @torch.no_grad()
-    def test_lm(self, global_arena: torch.Tensor, rows_dev: torch.Tensor) -> Dict[str, float]:
+    def test_lm(self, global_arena: torch.Tensor, rows_dev: torch.Tensor, sync: bool = True):
         """Global masked-LM loss / perplexity over bptt windows of the batchified test stream; every window weighs
         ``rows`` (reference ``src/train_transformer_fed.py:127-143``)."""
         P = self._params(global_arena)
@@ -166,5 +175,5 @@ class Evaluator:
             acc[1] += torch.exp(lf) * r
             acc[2] += r
         all_reduce_sum(self.info, acc)
-        a = acc.tolist()
-        return {"Global-Loss": a[0] / max(a[2], 1), "Global-Perplexity": a[1] / max(a[2], 1), "_n_global": a[2]}
+        pending = ("lm", acc, False)
+        return self.finish(pending) if sync else pending

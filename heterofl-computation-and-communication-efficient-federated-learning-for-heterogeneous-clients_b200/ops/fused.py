@@ -105,10 +105,11 @@ def bn_act_bwd(dy: torch.Tensor, dy2: Optional[torch.Tensor], dres: Optional[tor
     return ds
 
 
-# tcgen05 implicit-GEMM forward convolution: "off" | "on" (whenever the shape qualifies) | "auto" (qualifying shapes
-# with at least CONV_TC_MIN_PIXELS output pixels -- the regime where it beats the library, see profiles/conv_bench.md)
+# tcgen05 implicit-GEMM forward convolution: "off" | "on" (whenever the shape qualifies) | "auto" = only where it
+# measurably beats the library (profiles/conv_bench.md): the latency-bound training shapes with <= 9 K-blocks
+# (C_in = 64, batch-10 tiles); large-batch and deep-K shapes stay on cuDNN until the kernel is persistent / 2-CTA.
 CONV_TC_MODE = os.environ.get("HFL_CONV_TC", "auto")
-CONV_TC_MIN_PIXELS = int(os.environ.get("HFL_CONV_TC_MIN_PIXELS", "100000"))
+CONV_TC_MAX_PIXELS = int(os.environ.get("HFL_CONV_TC_MAX_PIXELS", "20480"))
 
 
 def _tc_conv_ok(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> bool:
@@ -123,7 +124,7 @@ def _tc_conv_ok(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> bool
     if not cu.C().conv_tc_supported(N, H, W, C, K, R, S, stride):
         return False
     if CONV_TC_MODE == "auto":
-        return N * (H // stride) * (W // stride) >= CONV_TC_MIN_PIXELS
+        return N * (H // stride) * (W // stride) <= CONV_TC_MAX_PIXELS and C <= 64
     return True
 
 

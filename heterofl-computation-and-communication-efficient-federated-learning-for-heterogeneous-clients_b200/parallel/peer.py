@@ -27,7 +27,9 @@ from ..ops import cuda as cu
 from ..plan.layout import FedTables
 
 _ALIGN = 256
-_FLAG_BYTES = 1024
+_CHANNELS = 4                      # independent barrier / all-reduce channels (one per concurrently used stream)
+_FLAG_STRIDE = 256                 # bytes per channel flag row (>= 4 * world)
+_FLAG_BYTES = _CHANNELS * _FLAG_STRIDE
 
 
 def _align(n: int) -> int:
@@ -45,9 +47,9 @@ class PeerPool:
         self.round_base = self.off
         self.peer_base: List[int] = [0] * info.world
         self.peer_base[info.rank] = self.base
-        self.epoch = 0
+        self.epoch = [0] * _CHANNELS
         self.err = torch.zeros(1, dtype=torch.int32, device=info.device)
-        self._flag_ptrs: Optional[torch.Tensor] = None
+        self._flag_ptrs: List[Optional[torch.Tensor]] = [None] * _CHANNELS
         self._opened: List[int] = []
 
     # -- allocation (deterministic bump allocator) -----------------------------------------------------------
@@ -92,37 +94,41 @@ class PeerPool:
             p = int(self.C.ipc_open_handle(h))
             self.peer_base[r] = p
             self._opened.append(p)
-        self._flag_ptrs = torch.tensor(self.peer_base, dtype=torch.int64).to(self.info.device)
+        for ch in range(_CHANNELS):
+            self._flag_ptrs[ch] = torch.tensor([b + ch * _FLAG_STRIDE for b in self.peer_base],
+                                               dtype=torch.int64).to(self.info.device)
         dist.barrier()
 
-    def barrier(self) -> None:
-        """Stream-ordered cross-GPU barrier (device-side flags, no host sync)."""
-        self.epoch += 1
-        self.C.peer_barrier(self._flag_ptrs, self.info.rank, self.info.world, self.epoch, self.err)
+    def barrier(self, channel: int = 0) -> None:
+        """Stream-ordered cross-GPU barrier (device-side flags, no host sync).  Streams that run concurrently must use
+        different channels (every rank has to issue the barriers of one channel in the same order)."""
+        self.epoch[channel] += 1
+        self.C.peer_barrier(self._flag_ptrs[channel], self.info.rank, self.info.world, self.epoch[channel], self.err)
 
     # -- small one-shot all-reduce over peer memory (sBN statistic merge, metric merge) ----------------------------
     SCRATCH_FLOATS = 1 << 16
 
     def enable_all_reduce(self) -> None:
-        """Reserve the persistent scratch slab (must be called on every rank BEFORE ``exchange``)."""
-        self._scratch = self.alloc_persistent(self.SCRATCH_FLOATS, torch.float32)
-        self._scratch_ptrs = None
+        """Reserve the persistent scratch slabs (must be called on every rank BEFORE ``exchange``)."""
+        self._scratch = [self.alloc_persistent(self.SCRATCH_FLOATS, torch.float32) for _ in range(_CHANNELS)]
+        self._scratch_ptrs = [None] * _CHANNELS
 
-    def all_reduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+    def all_reduce_sum_(self, t: torch.Tensor, channel: int = 0) -> torch.Tensor:
         """In-place sum of a small fp32/fp64 tensor over all ranks: every rank publishes its values in its pool slab,
         a flag barrier orders the stores, ``peer_sum_kernel`` reads all slabs over NVLink, a second barrier frees the
         slab for the next call.  No NCCL, no host synchronisation."""
         n = t.numel()
         assert n <= self.SCRATCH_FLOATS, "all_reduce_sum_ is meant for small vectors"
-        if self._scratch_ptrs is None:
-            off = self._scratch._hfl_pool_offset
-            self._scratch_ptrs = torch.tensor([b + off for b in self.peer_base], dtype=torch.int64).to(self.info.device)
+        if self._scratch_ptrs[channel] is None:
+            off = self._scratch[channel]._hfl_pool_offset
+            self._scratch_ptrs[channel] = torch.tensor([b + off for b in self.peer_base],
+                                                       dtype=torch.int64).to(self.info.device)
         src = t.reshape(-1)
-        self._scratch[:n].copy_(src.to(torch.float32))
-        self.barrier()
+        self._scratch[channel][:n].copy_(src.to(torch.float32))
+        self.barrier(channel)
         out = torch.empty(n, dtype=torch.float32, device=self.info.device)
-        self.C.peer_sum(self._scratch_ptrs, out)
-        self.barrier()
+        self.C.peer_sum(self._scratch_ptrs[channel], out)
+        self.barrier(channel)
         src.copy_(out.to(t.dtype))
         return t
 
