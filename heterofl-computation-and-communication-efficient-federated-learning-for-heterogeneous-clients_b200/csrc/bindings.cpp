@@ -40,6 +40,7 @@ int hfl_conv_fprop_tc(const void*, const void*, void*, const void*, float*, int,
                       cudaStream_t);
 int hfl_gemm_bf16_general(const void*, int, int, const void*, int, int, void*, int, int, float, int, int, int,
                           cudaStream_t);
+int hfl_conv_dgrad_tc(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, cudaStream_t);
 long hfl_launch_count();
 void hfl_launch_count_add(long);
 void hfl_peer_barrier(const void*, int, int, unsigned, int*, cudaStream_t);
@@ -360,6 +361,27 @@ torch::Tensor conv_fprop_tc(torch::Tensor x, torch::Tensor w, c10::optional<torc
   return y;
 }
 
+// dy: [N, K, H, W] channels-last bf16 (stride-1 conv output grad); w: [K, C, R, S] stored K,R,S,C; returns dx [N, C, H, W]
+torch::Tensor conv_dgrad_tc(torch::Tensor dy, torch::Tensor w, c10::optional<torch::Tensor> residual) {
+  CHECK_CUDA_T(dy); CHECK_CUDA_T(w);
+  TORCH_CHECK(dy.dim() == 4 && w.dim() == 4 && dy.scalar_type() == torch::kBFloat16 && w.scalar_type() == torch::kBFloat16);
+  TORCH_CHECK(dy.is_contiguous(torch::MemoryFormat::ChannelsLast) && w.permute({0, 2, 3, 1}).is_contiguous());
+  const int N = dy.size(0), K = dy.size(1), H = dy.size(2), W = dy.size(3);
+  const int C = w.size(1), R = w.size(2), S = w.size(3);
+  TORCH_CHECK(w.size(0) == K);
+  TORCH_CHECK(hfl_conv_tc_supported(N, H, W, K, C, R, S, 1) == 0, "conv_dgrad_tc: unsupported problem");
+  c10::cuda::CUDAGuard guard(dy.device());
+  auto dx = torch::empty({N, C, H, W}, dy.options().memory_format(torch::MemoryFormat::ChannelsLast));
+  const void* rp = nullptr;
+  if (residual.has_value()) {
+    TORCH_CHECK(residual->sizes() == dx.sizes() && residual->is_contiguous(torch::MemoryFormat::ChannelsLast));
+    rp = residual->data_ptr();
+  }
+  int e = hfl_conv_dgrad_tc(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), rp, N, H, W, C, K, R, S, cur_stream());
+  TORCH_CHECK(e == 0, "conv_dgrad_tc failed with code ", e);
+  return dx;
+}
+
 // ---- peer memory runtime (cudaMalloc + CUDA IPC) ---------------------------------------------------------
 int64_t peer_alloc(int64_t bytes) {
   void* p = nullptr;
@@ -422,6 +444,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_bf16_general", &gemm_bf16_general);
   m.def("conv_tc_supported", &conv_tc_supported);
   m.def("conv_fprop_tc", &conv_fprop_tc);
+  m.def("conv_dgrad_tc", &conv_dgrad_tc);
   m.def("launch_count", &hfl_launch_count);
   m.def("launch_count_add", &hfl_launch_count_add);
   m.def("peer_alloc", &peer_alloc);

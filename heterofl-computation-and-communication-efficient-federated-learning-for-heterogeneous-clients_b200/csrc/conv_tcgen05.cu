@@ -42,7 +42,12 @@ struct ConvSmem {
   static constexpr int TOTAL = CV_STAGES * STAGE_BYTES + 1024 + 256;
 };
 
-template <int BLOCK_N>
+// DGRAD = true turns the same kernel into the stride-1 data-gradient:
+//   dX[n,h,w,c] = sum_{r,s,k} dY[n, h+pad-r, w+pad-s, k] * Wt[k,r,s,c]
+// "x" is then dY (reduction over its K_out channels, geometry fields C/Kout are swapped by the host), the filter taps
+// are visited with mirrored halo offsets, and the B operand -- Wt[k, tap, c-range] with c contiguous -- is consumed
+// MN-major straight from the K,R,S,C filter matrix (no transposed / flipped weight copy).
+template <int BLOCK_N, bool DGRAD>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                           __nv_bfloat16* __restrict__ Y, const __nv_bfloat16* __restrict__ residual,
@@ -90,14 +95,24 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         uint8_t* sa = smem + st * S::STAGE_BYTES;
         uint8_t* sb = sa + S::A_BYTES;
         mbar_expect_tx(&full_bar[st], S::STAGE_BYTES);
-        // A: box {64ch, bw, bh, bn} at (c, w, h, n) = (cb*64, s - pad, oh0*stride + r - pad, n0); halo -> zero fill
-        tma_load_4d(sa, &tmap_x, &full_bar[st], cb * CV_BLOCK_K, s - g.pad, oh0 * g.stride + r - g.pad, n0);
-        // B: rows = output channels, cols = (tap, c)
-        tma_load_2d(sb, &tmap_w, &full_bar[st], tap * g.C + cb * CV_BLOCK_K, n_blk * BLOCK_N);
+        if (!DGRAD) {
+          // A: box {64ch, bw, bh, bn} at (c, w, h, n) = (cb*64, s - pad, oh0*stride + r - pad, n0); halo -> zero fill
+          tma_load_4d(sa, &tmap_x, &full_bar[st], cb * CV_BLOCK_K, s - g.pad, oh0 * g.stride + r - g.pad, n0);
+          // B: rows = output channels, cols = (tap, c)
+          tma_load_2d(sb, &tmap_w, &full_bar[st], tap * g.C + cb * CV_BLOCK_K, n_blk * BLOCK_N);
+        } else {
+          // A: dY box at the mirrored tap offset
+          tma_load_4d(sa, &tmap_x, &full_bar[st], cb * CV_BLOCK_K, g.pad - s, oh0 + g.pad - r, n0);
+          // B (MN-major): 64(c) x 64(k_out) boxes of the [K_out_total, R*S*C_total] filter matrix; here g.Kout is the
+          // number of dX channels (= filter C) and g.C the reduction length (= filter K_out)
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_2d(sb + j * 8192, &tmap_w, &full_bar[st], tap * g.Kout + n_blk * BLOCK_N + j * 64, cb * CV_BLOCK_K);
+        }
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(CV_BLOCK_M, BLOCK_N);
+    const uint32_t idesc = make_idesc_bf16(CV_BLOCK_M, BLOCK_N, false, DGRAD);
     for (int kb = 0; kb < num_k; ++kb) {
       const int st = kb % CV_STAGES;
       const uint32_t ph = (kb / CV_STAGES) & 1;
@@ -106,9 +121,11 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(smem + st * S::STAGE_BYTES);
         const uint64_t adesc = make_smem_desc_sw128(a_addr);
-        const uint64_t bdesc = make_smem_desc_sw128(a_addr + S::A_BYTES);
+        const uint64_t bdesc = DGRAD ? make_smem_desc_sw128_mn(a_addr + S::A_BYTES) : make_smem_desc_sw128(a_addr + S::A_BYTES);
+        constexpr uint64_t b_step = DGRAD ? (2048 >> 4) : (32 >> 4);
 #pragma unroll
-        for (int k = 0; k < CV_BLOCK_K / 16; ++k) umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        for (int k = 0; k < CV_BLOCK_K / 16; ++k)
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + b_step * k, idesc, (kb | k) != 0);
         umma_commit(&empty_bar[st]);
         if (kb == num_k - 1) umma_commit(tmem_full_bar);
       }
@@ -191,10 +208,10 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
 
 using namespace hfl;
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool DGRAD = false>
 static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, const void* residual, float* stats,
                        const ConvGeom& g, int tiles_m, cudaStream_t stream) {
-  auto kern = conv_fprop_tcgen05_kernel<BLOCK_N>;
+  auto kern = conv_fprop_tcgen05_kernel<BLOCK_N, DGRAD>;
   constexpr int smem = ConvSmem<BLOCK_N>::TOTAL;
   static bool configured = false;
   if (!configured) {
@@ -247,4 +264,32 @@ extern "C" int hfl_conv_fprop_tc(const void* X, const void* Wt, void* Y, const v
   if (r) return 2000 + r;
   if (block_n == 128) return launch_conv<128>(tx, tw, Y, residual, stats, g, tiles_m, stream);
   return launch_conv<64>(tx, tw, Y, residual, stats, g, tiles_m, stream);
+}
+
+// Stride-1 data gradient: dX[N,H,W,C] from dY[N,H,W,Kout] and the K,R,S,C filter.  `residual` is an optional tensor
+// added to dX (gradient arriving through a skip connection).
+extern "C" int hfl_conv_dgrad_tc(const void* dY, const void* Wt, void* dX, const void* residual, int N, int H, int W,
+                                 int C, int Kout, int R, int S, cudaStream_t stream) {
+  // the forward-shape predicate with the channel roles swapped
+  if (hfl_conv_tc_supported(N, H, W, Kout, C, R, S, 1) != 0) return -2;
+  ConvGeom g;
+  g.N = N; g.H = H; g.W = W; g.R = R; g.S = S; g.stride = 1; g.pad = R / 2;
+  g.C = Kout;            // reduction channels (dY)
+  g.Kout = C;            // produced channels (dX)
+  g.OH = H; g.OW = W;
+  g.bw = W;
+  const int rows = 128 / W;
+  g.bh = rows < H ? rows : H;
+  g.bn = rows / g.bh;
+  g.tiles_h = (H + g.bh - 1) / g.bh;
+  const int tiles_m = ((N + g.bn - 1) / g.bn) * g.tiles_h;
+  const int block_n = (C % 128 == 0) ? 128 : 64;
+  CUtensorMap tx, tw;
+  int r = make_tmap_nhwc_bf16(&tx, dY, (uint64_t)Kout, (uint64_t)W, (uint64_t)H, (uint64_t)N, CV_BLOCK_K, (uint32_t)g.bw,
+                              (uint32_t)g.bh, (uint32_t)g.bn, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (r) return 1000 + r;
+  r = make_tmap_2d_bf16(&tw, Wt, (uint64_t)R * S * C, (uint64_t)Kout, (uint64_t)R * S * C * 2, 64, CV_BLOCK_K);
+  if (r) return 2000 + r;
+  if (block_n == 128) return launch_conv<128, true>(tx, tw, dX, residual, nullptr, g, tiles_m, stream);
+  return launch_conv<64, true>(tx, tw, dX, residual, nullptr, g, tiles_m, stream);
 }

@@ -207,6 +207,13 @@ class Engine:
         self.h2d_bytes += t.numel() * t.element_size()
         return t.to(self.device, non_blocking=True)
 
+    def _src(self, t: torch.Tensor) -> torch.Tensor:
+        """Hand a (possibly pinned-host) tensor to the evaluator, which copies it into its static device buffer;
+        the H2D bytes are accounted here."""
+        if t.device != self.device:
+            self.h2d_bytes += t.numel() * t.element_size()
+        return t
+
     # -- slots ---------------------------------------------------------------------------------------------
     def _model_for(self, rate: float) -> Model:
         if rate not in self._models:
@@ -305,11 +312,11 @@ class Engine:
                 test = self.evaluator.test_lm(self.global_arena, self._h2d(self.test_rows))
                 timer.mark("test")
             else:
-                tr_img = self._h2d(self.train_img)
-                self.running = self.evaluator.sbn_stats(self.global_arena, self.dataset["train"], tr_img, shared)
+                self.running = self.evaluator.sbn_stats(self.global_arena, self.dataset["train"],
+                                                        self._src(self.train_img), shared)
                 timer.mark("sbn")
                 test = self.evaluator.test_vision(self.global_arena, self.running, self.dataset["test"],
-                                                  self._h2d(self.test_img), self._h2d(self.test_lab),
+                                                  self._src(self.test_img), self._src(self.test_lab),
                                                   self.test_owner, self.user_masks)
                 timer.mark("test")
             out["test"] = {k: v for k, v in test.items() if not k.startswith("_")}
@@ -352,9 +359,9 @@ class Engine:
                 test = self.evaluator.test_lm(self._eval_arena, self._h2d(self.test_rows), sync=False)
             else:
                 self.running = self.evaluator.sbn_stats(self._eval_arena, self.dataset["train"],
-                                                        self._h2d(self.train_img), shared)
+                                                        self._src(self.train_img), shared)
                 test = self.evaluator.test_vision(self._eval_arena, self.running, self.dataset["test"],
-                                                  self._h2d(self.test_img), self._h2d(self.test_lab), self.test_owner,
+                                                  self._src(self.test_img), self._src(self.test_lab), self.test_owner,
                                                   self.user_masks, sync=False)
             self._eval_done = torch.cuda.Event()
             self._eval_done.record(self._eval_stream)

@@ -33,6 +33,9 @@ class Evaluator:
         self.device, self.dtype = info.device, compute_dtype
         self.stats_chunk_groups, self.test_chunk = stats_chunk_groups, test_chunk
         self._aug = {}
+        self.use_graph = bool(cfg.get("eval_graph", True))
+        self._sbn_g = None
+        self._test_g = None
         self.fused = None
         if self.device.type == "cuda" and compute_dtype == torch.bfloat16 and cu.available() \
                 and cfg.get("fused", True) and FusedResNet.eligible(model.spec):
@@ -56,9 +59,15 @@ class Evaluator:
         bn = self.model.bn_layers()
         if not bn:
             return {}
-        P = self._params(global_arena)
         B = int(self.cfg["batch_size"]["train"])
         N = imgs_dev.shape[0]
+        if self.fused is not None and self.use_graph and N % B == 0:
+            plan = self._chunk_plan(N // B, self.stats_chunk_groups)
+            if plan is not None:
+                return self._sbn_graphed(global_arena, ds, imgs_dev, generator, B, plan)
+        if not imgs_dev.is_cuda and self.device.type == "cuda":
+            imgs_dev = imgs_dev.to(self.device, non_blocking=True)
+        P = self._params(global_arena)
         perm = torch.randperm(N, generator=generator)
         n_full = N // B
         aug = self._augment(ds, True)
@@ -102,12 +111,114 @@ class Evaluator:
             off += 2 * w
         return running
 
+    # -- graph-captured evaluation (fused path) ----------------------------------------------------------
+    def _chunk_plan(self, n_units: int, max_per_chunk: int):
+        """(units per chunk, chunks per rank) with every rank getting the same number of equal chunks, or None."""
+        w = self.info.world
+        for per_rank in range(1, 4096):
+            nch = per_rank * w
+            if n_units % nch == 0 and n_units // nch <= max_per_chunk:
+                return n_units // nch, per_rank
+            if nch > n_units:
+                break
+        return None
+
+    def _merge_stats(self, bn, acc, n_groups: int) -> Dict:
+        widths = [w for _, w in bn]
+        flat = torch.zeros(2 * sum(widths) + 1, dtype=torch.float32, device=self.device)
+        off = 0
+        for name, w in bn:
+            if name in acc:
+                flat[off:off + w] = acc[name][0]
+                flat[off + w:off + 2 * w] = acc[name][1]
+            off += 2 * w
+        flat[-1] = n_groups
+        all_reduce_sum(self.info, flat)
+        n = flat[-1].clamp(min=1.0)
+        running, off = {}, 0
+        for name, w in bn:
+            running[name] = (flat[off:off + w] / n, flat[off + w:off + 2 * w] / n)
+            off += 2 * w
+        return running
+
+    def _capture(self, fn):
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            fn()                                   # warm-up (allocations, cuDNN plans)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        k0 = cu.launch_count()
+        with torch.cuda.graph(g, stream=s):
+            fn()
+        return g, cu.launch_count() - k0
+
+    def _sbn_graphed(self, global_arena, ds, imgs_src, generator, B, plan) -> Dict:
+        """sBN pass as ``chunks_per_rank`` replays of ONE captured chunk graph (no per-kernel host work, so the pass can
+        overlap the next round's training when launched on a side stream)."""
+        Gc, per_rank = plan
+        bn = self.model.bn_layers()
+        N = imgs_src.shape[0]
+        st = self._sbn_g
+        if st is None or st["key"] != (N, B, Gc, per_rank):
+            wc = torch.empty(self.model.layout.size, dtype=self.dtype, device=self.device)
+            st = {"key": (N, B, Gc, per_rank), "wc": wc, "P": self.model.layout.views(wc),
+                  "imgs": torch.empty(imgs_src.shape, dtype=torch.uint8, device=self.device),
+                  "perm": torch.zeros(per_rank, Gc * B, dtype=torch.int64, device=self.device),
+                  "par": torch.zeros(per_rank, Gc * B, 3, dtype=torch.int32, device=self.device),
+                  "row": torch.zeros(1, dtype=torch.int64, device=self.device),
+                  "ctx": NormCtx("stats", group=B), "graph": None}
+            for name, w in bn:
+                st["ctx"].acc[name] = (torch.zeros(w, dtype=torch.float32, device=self.device),
+                                       torch.zeros(w, dtype=torch.float32, device=self.device))
+            self._sbn_g = st
+        aug = self._augment(ds, True)
+        perm = torch.randperm(N, generator=generator)
+        params = aug.draw(N, generator)
+        w_, r_ = self.info.world, self.info.rank
+        rows = [ci for ci in range(per_rank * w_) if ci % w_ == r_]
+        pv = perm.view(per_rank * w_, Gc * B)[rows].contiguous()
+        st["perm"].copy_(pv.to(self.device, non_blocking=True))
+        st["par"].copy_(params.view(per_rank * w_, Gc * B, 3)[torch.as_tensor(rows, device=params.device)])
+        st["imgs"].copy_(imgs_src, non_blocking=True)
+        st["wc"].copy_(global_arena)
+        st["row"].zero_()
+        for a, b in st["ctx"].acc.values():
+            a.zero_()
+            b.zero_()
+        if st["graph"] is None:
+            def chunk():
+                idx = st["perm"].index_select(0, st["row"]).view(-1)
+                par = st["par"].index_select(0, st["row"]).view(-1, 3)
+                x = aug(st["imgs"], idx, par)
+                self.fused.forward_stats(st["P"], x, st["ctx"])
+                st["row"].add_(1)
+            snap = {k: (a.clone(), b.clone()) for k, (a, b) in st["ctx"].acc.items()}
+            st["graph"], st["kernels"] = self._capture(chunk)
+            st["row"].zero_()
+            for k, (a, b) in snap.items():
+                st["ctx"].acc[k][0].copy_(a)
+                st["ctx"].acc[k][1].copy_(b)
+        for _ in range(per_rank):
+            st["graph"].replay()
+            cu.launch_count_add(st["kernels"])
+        return self._merge_stats(bn, st["ctx"].acc, per_rank * Gc)
+
     # -- test --------------------------------------------------------------------------------------------
     @torch.no_grad()
     def test_vision(self, global_arena: torch.Tensor, running: Dict, ds: VisionData, imgs_dev: torch.Tensor,
                     labels_dev: torch.Tensor, owner_dev: Optional[torch.Tensor],
                     user_masks_dev: Optional[torch.Tensor], sync: bool = True):
         """``owner_dev[i]`` = user whose test split holds sample i (-1: none); ``user_masks_dev [U, classes]``."""
+        if self.fused is not None and self.use_graph and owner_dev is not None:
+            plan = self._chunk_plan(imgs_dev.shape[0], self.test_chunk)
+            if plan is not None:
+                pending = self._test_graphed(global_arena, running, ds, imgs_dev, labels_dev, owner_dev,
+                                             user_masks_dev, plan)
+                return self.finish(pending) if sync else pending
+        if not imgs_dev.is_cuda and self.device.type == "cuda":
+            imgs_dev, labels_dev = imgs_dev.to(self.device, non_blocking=True), labels_dev.to(self.device, non_blocking=True)
         P = self._params(global_arena)
         ctx = NormCtx("eval", running=running)
         ab = self.fused.eval_affine(P, running) if self.fused is not None else None
@@ -143,6 +254,64 @@ class Evaluator:
         all_reduce_sum(self.info, acc)
         pending = ("vision", acc, owner_dev is not None)
         return self.finish(pending) if sync else pending
+
+    def _test_graphed(self, global_arena, running, ds, imgs_src, labels_src, owner_dev, user_masks_dev, plan):
+        Nc, per_rank = plan
+        N = imgs_src.shape[0]
+        st = self._test_g
+        bn = self.model.bn_layers()
+        if st is None or st["key"] != (N, Nc, per_rank):
+            wc = torch.empty(self.model.layout.size, dtype=self.dtype, device=self.device)
+            st = {"key": (N, Nc, per_rank), "wc": wc, "P": self.model.layout.views(wc),
+                  "imgs": torch.empty(imgs_src.shape, dtype=torch.uint8, device=self.device),
+                  "labels": torch.empty(N, dtype=torch.int64, device=self.device),
+                  "idx": torch.zeros(per_rank, Nc, dtype=torch.int64, device=self.device),
+                  "row": torch.zeros(1, dtype=torch.int64, device=self.device),
+                  "acc": torch.zeros(6, dtype=torch.float64, device=self.device),
+                  "ab": {name: (torch.zeros(w, dtype=torch.float32, device=self.device),
+                                torch.zeros(w, dtype=torch.float32, device=self.device)) for name, w in bn},
+                  "graph": None}
+            w_, r_ = self.info.world, self.info.rank
+            rows = [ci for ci in range(per_rank * w_) if ci % w_ == r_]
+            st["idx"].copy_(torch.arange(N).view(per_rank * w_, Nc)[rows].to(self.device))
+            self._test_g = st
+        aug = self._augment(ds, False)
+        st["imgs"].copy_(imgs_src, non_blocking=True)
+        st["labels"].copy_(labels_src, non_blocking=True)
+        st["wc"].copy_(global_arena)
+        for name, (a, b) in self.fused.eval_affine(st["P"], running).items():
+            st["ab"][name][0].copy_(a)
+            st["ab"][name][1].copy_(b)
+        st["row"].zero_()
+        st["acc"].zero_()
+        use_mask = bool(self.cfg["mask"]) and user_masks_dev is not None
+        if st["graph"] is None:
+            def chunk():
+                idx = st["idx"].index_select(0, st["row"]).view(-1)
+                x = aug(st["imgs"], idx, None)
+                y = st["labels"].index_select(0, idx)
+                z = self.fused.forward_eval(st["P"], x, st["ab"])
+                acc = st["acc"]
+                acc[3] += F.cross_entropy(z, y, reduction="sum").double()
+                acc[4] += (z.argmax(1) == y).sum()
+                acc[5] += Nc
+                own = owner_dev.index_select(0, idx)
+                sel = own >= 0
+                zl = z.masked_fill(~user_masks_dev[own.clamp(min=0)].bool(), 0.0) if use_mask else z
+                ce = F.cross_entropy(zl, y, reduction="none")
+                acc[0] += (ce * sel).sum().double()
+                acc[1] += ((zl.argmax(1) == y) & sel).sum()
+                acc[2] += sel.sum()
+                st["row"].add_(1)
+            st["graph"], st["kernels"] = self._capture(chunk)
+            st["row"].zero_()
+            st["acc"].zero_()
+        for _ in range(per_rank):
+            st["graph"].replay()
+            cu.launch_count_add(st["kernels"])
+        acc = st["acc"].clone()
+        all_reduce_sum(self.info, acc)
+        return ("vision", acc, True)
 
     @staticmethod
     def finish(pending) -> Dict[str, float]:

@@ -3,8 +3,9 @@
 ``tc_linear(x, w, b, alpha)`` = ``alpha * (x @ w^T + b)`` -- the Scaler of the reference's Transformer
 (``src/models/transformer.py:80-84,116,132``: ``scaler(linear(x))``) rides along as the GEMM's ``alpha`` instead of a
 separate elementwise kernel.  Forward runs on the hand-written TMA/TMEM kernel whenever the operands qualify (CUDA,
-bf16, K multiple of 8, 16-byte aligned rows); the backward GEMMs (which need transposed operands) currently go through
-the library.  Falls back to ``F.linear`` everywhere else (CPU, fp32, odd shapes).
+bf16, K multiple of 8, 16-byte aligned rows); the backward GEMMs read their transposed operands in place through
+MN-major UMMA descriptors (``gemm_tcgen05_general_kernel``).  Falls back to ``F.linear`` everywhere else (CPU, fp32,
+odd shapes).
 """
 from __future__ import annotations
 
@@ -39,11 +40,22 @@ class _TCLinear(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        # backward GEMMs on the same tcgen05 kernel family; the transposed operands are consumed in place through
+        # MN-major UMMA descriptors (no transpose kernels):
+        #   dX[M,K] = alpha * dY[M,N] . W[N,K]      (B = W read as [red=N, out=K]: MN-major)
+        #   dW[N,K] = alpha * dY[M,N]^T . X[M,K]    (A = dY as [red=M, out=N], B = X as [red=M, out=K]: both MN-major)
         x2, w = ctx.saved_tensors
-        g = dy if ctx.alpha == 1.0 else dy * ctx.alpha
-        dx = g.mm(w) if ctx.needs_input_grad[0] else None
-        dw = g.t().mm(x2) if ctx.needs_input_grad[1] else None
-        db = g.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        a = float(ctx.alpha)
+        dy = dy.contiguous()
+        M, N = dy.shape
+        ok = (M % 8 == 0 and N % 8 == 0 and dy.data_ptr() % 16 == 0 and w.stride(0) % 8 == 0 and x2.stride(0) % 8 == 0)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = cu.C().gemm_bf16_general(dy, False, w, True, a, False) if ok else (dy.mm(w) * a)
+        if ctx.needs_input_grad[1]:
+            dw = cu.C().gemm_bf16_general(dy, True, x2, True, a, False) if ok else (dy.t().mm(x2) * a)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(0) if a == 1.0 else dy.sum(0) * a
         return dx, dw, db, None
 
 

@@ -327,3 +327,25 @@ def test_tcgen05_gemm_general_layouts(a_mn, b_mn, M, N, K):
     y = cu.C().gemm_bf16_general(a, a_mn, b, b_mn, 1.0, True)
     torch.cuda.synchronize()
     assert torch.allclose(y, ref, atol=3e-3, rtol=3e-3), float((y - ref).abs().max())
+
+
+@pytest.mark.parametrize("N,C,H,K,R", [(10, 64, 32, 64, 3), (10, 128, 16, 128, 3), (10, 64, 16, 128, 3), (10, 256, 8, 256, 3),
+                                        (10, 512, 4, 512, 3), (4, 128, 16, 64, 1)])
+def test_tcgen05_conv_dgrad_matches_autograd(N, C, H, K, R):
+    """Stride-1 data gradient on the implicit-GEMM kernel (mirrored taps, MN-major filter operand)."""
+    cu = _cu()
+    dev = torch.device("cuda")
+    torch.manual_seed(N + C + K)
+    x = torch.randn(N, C, H, H, device=dev, requires_grad=True)
+    w = (torch.randn(K, C, R, R, device=dev) / (C * R * R) ** 0.5).bfloat16()
+    dy = torch.randn(N, K, H, H, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    y = torch.nn.functional.conv2d(x, w.float(), None, 1, R // 2)
+    y.backward(dy.float())
+    wk = w.contiguous(memory_format=torch.channels_last) if R > 1 else w.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    dx = cu.C().conv_dgrad_tc(dy, wk, None)
+    torch.cuda.synchronize()
+    ref = x.grad
+    assert float((dx.float() - ref).abs().max()) < 3e-2 * max(1.0, float(ref.abs().max()))
+    res = torch.randn_like(ref).bfloat16().contiguous(memory_format=torch.channels_last)
+    dx2 = cu.C().conv_dgrad_tc(dy, wk, res)
+    assert float((dx2.float() - ref - res.float()).abs().max()) < 4e-2 * max(1.0, float(ref.abs().max()))
