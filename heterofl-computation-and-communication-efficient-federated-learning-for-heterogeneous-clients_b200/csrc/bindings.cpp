@@ -41,6 +41,8 @@ int hfl_conv_fprop_tc(const void*, const void*, void*, const void*, float*, int,
 int hfl_gemm_bf16_general(const void*, int, int, const void*, int, int, void*, int, int, float, int, int, int,
                           cudaStream_t);
 int hfl_conv_dgrad_tc(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, cudaStream_t);
+int hfl_conv_wgrad_tc_supported(int, int, int, int, int, int, int, int);
+int hfl_conv_wgrad_tc(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 long hfl_launch_count();
 void hfl_launch_count_add(long);
 void hfl_peer_barrier(const void*, int, int, unsigned, int*, cudaStream_t);
@@ -382,6 +384,26 @@ torch::Tensor conv_dgrad_tc(torch::Tensor dy, torch::Tensor w, c10::optional<tor
   return dx;
 }
 
+bool conv_wgrad_tc_supported(int64_t N, int64_t H, int64_t W, int64_t C, int64_t Kout, int64_t R, int64_t S,
+                             int64_t stride) {
+  return hfl_conv_wgrad_tc_supported((int)N, (int)H, (int)W, (int)C, (int)Kout, (int)R, (int)S, (int)stride) == 0;
+}
+
+// dy: [N, K, OH, OW], x: [N, C, H, W] (channels-last bf16) -> dw fp32, logical [K, C, R, S] stored K,R,S,C
+torch::Tensor conv_wgrad_tc(torch::Tensor dy, torch::Tensor x, int64_t R, int64_t stride) {
+  CHECK_CUDA_T(dy); CHECK_CUDA_T(x);
+  TORCH_CHECK(dy.scalar_type() == torch::kBFloat16 && x.scalar_type() == torch::kBFloat16);
+  TORCH_CHECK(dy.is_contiguous(torch::MemoryFormat::ChannelsLast) && x.is_contiguous(torch::MemoryFormat::ChannelsLast));
+  const int N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3), K = dy.size(1);
+  TORCH_CHECK(hfl_conv_wgrad_tc_supported(N, H, W, C, K, (int)R, (int)R, (int)stride) == 0, "conv_wgrad_tc: unsupported");
+  c10::cuda::CUDAGuard guard(x.device());
+  auto dw = torch::empty({K, R, R, C}, torch::TensorOptions().dtype(torch::kFloat32).device(x.device()));
+  int e = hfl_conv_wgrad_tc(dy.data_ptr(), x.data_ptr(), dw.data_ptr<float>(), N, H, W, C, K, (int)R, (int)R, (int)stride, 1,
+                            cur_stream());
+  TORCH_CHECK(e >= 1, "conv_wgrad_tc failed with code ", e);
+  return dw.permute({0, 3, 1, 2});
+}
+
 // ---- peer memory runtime (cudaMalloc + CUDA IPC) ---------------------------------------------------------
 int64_t peer_alloc(int64_t bytes) {
   void* p = nullptr;
@@ -445,6 +467,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv_tc_supported", &conv_tc_supported);
   m.def("conv_fprop_tc", &conv_fprop_tc);
   m.def("conv_dgrad_tc", &conv_dgrad_tc);
+  m.def("conv_wgrad_tc", &conv_wgrad_tc);
+  m.def("conv_wgrad_tc_supported", &conv_wgrad_tc_supported);
   m.def("launch_count", &hfl_launch_count);
   m.def("launch_count_add", &hfl_launch_count_add);
   m.def("peer_alloc", &peer_alloc);

@@ -293,3 +293,183 @@ extern "C" int hfl_conv_dgrad_tc(const void* dY, const void* Wt, void* dX, const
   if (block_n == 128) return launch_conv<128, true>(tx, tw, dX, residual, nullptr, g, tiles_m, stream);
   return launch_conv<64, true>(tx, tw, dX, residual, nullptr, g, tiles_m, stream);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Weight gradient on tcgen05:   dW[k, r, s, c] = sum_{n,oh,ow} dY[n,oh,ow,k] * X[n, oh*st + r - pad, ow*st + s - pad, c]
+//
+// GEMM view per filter tap: M = K_out, N = C, reduction = output pixels.  BOTH operands are MN-major (the reduction
+// index -- the pixel -- is the strided one in NHWC), which UMMA reads directly: per K-block one 64-pixel brick
+// {bn x bh x OW} of dY (two 64-channel boxes -> M = 128) and the tap-shifted brick of X (one 64-channel box), both
+// fetched by 4-D TMA.  grid = (K_out/128 tiles, C/64 tiles, taps * splits); split-K partial sums are reduced with fp32
+// atomics into a zero-initialised [K,R,S,C] fp32 buffer (which the multi-tensor optimiser consumes as is).
+// ---------------------------------------------------------------------------------------------------------
+namespace hfl {
+
+struct WgradGeom {
+  int N, H, W, C, Kout, OH, OW, R, S, stride, pad;
+  int bn, bh, bw;          // 64-pixel brick (bn*bh*bw == 64, bw == OW)
+  int bricks_h, bricks;    // bricks per image-group along H, total bricks
+  int splits;
+};
+
+constexpr int WG_STAGES = 4;
+constexpr int WG_A_BYTES = 128 * 64 * 2;    // two 64(k_out) x 64(pixel) boxes
+constexpr int WG_B_BYTES = 64 * 64 * 2;     // one 64(c) x 64(pixel) box
+constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                          float* __restrict__ dW, const WgradGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + WG_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + WG_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k_blk = blockIdx.x, c_blk = blockIdx.y;
+  const int tap = blockIdx.z / g.splits, split = blockIdx.z - tap * g.splits;
+  const int r = tap / g.S, s = tap - r * g.S;
+  const int per = (g.bricks + g.splits - 1) / g.splits;
+  const int b0 = split * per, b1 = min(b0 + per, g.bricks);
+  const int num_k = b1 - b0;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_dy); tma_prefetch_desc(&tmap_x); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_smem, 64);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  if (num_k > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int kb = 0; kb < num_k; ++kb) {
+          const int st = kb % WG_STAGES;
+          const uint32_t ph = (kb / WG_STAGES) & 1;
+          const int brick = b0 + kb;
+          const int tn = brick / g.bricks_h, th = brick - tn * g.bricks_h;
+          const int n0 = tn * g.bn, oh0 = th * g.bh;
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          uint8_t* sa = smem + st * WG_STAGE_BYTES;
+          uint8_t* sb = sa + WG_A_BYTES;
+          mbar_expect_tx(&full_bar[st], WG_STAGE_BYTES);
+          tma_load_4d(sa, &tmap_dy, &full_bar[st], k_blk * 128, 0, oh0, n0);
+          tma_load_4d(sa + 8192, &tmap_dy, &full_bar[st], k_blk * 128 + 64, 0, oh0, n0);
+          tma_load_4d(sb, &tmap_x, &full_bar[st], c_blk * 64, s - g.pad, oh0 * g.stride + r - g.pad, n0);
+        }
+      }
+    } else if (warp == 1) {
+      const uint32_t idesc = make_idesc_bf16(128, 64, true, true);
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int st = kb % WG_STAGES;
+        const uint32_t ph = (kb / WG_STAGES) & 1;
+        mbar_wait(&full_bar[st], ph);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + st * WG_STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc_sw128_mn(a_addr);
+          const uint64_t bdesc = make_smem_desc_sw128_mn(a_addr + WG_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)      // 64 pixels = 4 x UMMA_K(16); +16 k-rows = +2048 B
+            umma_bf16(tmem_base, adesc + (2048 >> 4) * k, bdesc + (2048 >> 4) * k, idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[st]);
+          if (kb == num_k - 1) umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+      }
+    } else if (warp >= 4) {
+      const int q = warp - 4;
+      mbar_wait(tmem_full_bar, 0);
+      tcgen05_fence_after();
+      const int k = k_blk * 128 + q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        if (k < g.Kout) {
+          float* dst = dW + ((size_t)k * g.R * g.S + tap) * g.C + c_blk * 64 + c0;
+          if (g.splits == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+          }
+        }
+      }
+      tcgen05_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+}  // namespace hfl
+
+extern "C" int hfl_conv_wgrad_tc_supported(int N, int H, int W, int C, int Kout, int R, int S, int stride) {
+  if (C % 64 != 0 || Kout % 64 != 0) return 1;
+  if (!((R == 3 && S == 3) || (R == 1 && S == 1))) return 2;
+  if (stride != 1 && stride != 2) return 3;
+  const int pad = R / 2;
+  const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - S) / stride + 1;
+  if (OW > 64 || (64 % OW) != 0) return 4;
+  const int rows = 64 / OW;
+  if (rows > OH && (rows % OH) != 0) return 5;
+  if (rows < OH && (OH % rows) != 0) return 6;
+  const int bh = rows < OH ? rows : OH, bn = rows / bh;
+  if (N % bn != 0) return 7;        // partial image groups would need masking of dY rows (TMA OOB handles X only)
+  return 0;
+}
+
+// dW (fp32, [K,R,S,C]) must be zero-initialised by the caller when the returned split count is > 1; returns < 0 on
+// error, otherwise the number of K-splits used.
+extern "C" int hfl_conv_wgrad_tc(const void* dY, const void* X, float* dW, int N, int H, int W, int C, int Kout, int R,
+                                 int S, int stride, int zero_first, cudaStream_t stream) {
+  if (hfl_conv_wgrad_tc_supported(N, H, W, C, Kout, R, S, stride) != 0) return -2;
+  hfl::WgradGeom g;
+  g.N = N; g.H = H; g.W = W; g.C = C; g.Kout = Kout; g.R = R; g.S = S; g.stride = stride; g.pad = R / 2;
+  g.OH = (H + 2 * g.pad - R) / stride + 1;
+  g.OW = (W + 2 * g.pad - S) / stride + 1;
+  g.bw = g.OW;
+  const int rows = 64 / g.OW;
+  g.bh = rows < g.OH ? rows : g.OH;
+  g.bn = rows / g.bh;
+  g.bricks_h = g.OH / g.bh;
+  g.bricks = (N / g.bn) * g.bricks_h;
+  const int base_ctas = ((Kout + 127) / 128) * (C / 64) * R * S;
+  int splits = 1;
+  while (base_ctas * splits < 96 && splits * 8 <= g.bricks) splits *= 2;   // fill the machine, keep >= 8 bricks per CTA
+  g.splits = splits;
+  CUtensorMap tdy, tx;
+  int r = hfl::make_tmap_nhwc_bf16(&tdy, dY, (uint64_t)Kout, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)N, 64, (uint32_t)g.bw,
+                                   (uint32_t)g.bh, (uint32_t)g.bn, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (r) return -(1000 + r);
+  r = hfl::make_tmap_nhwc_bf16(&tx, X, (uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N, 64, (uint32_t)(g.bw * stride),
+                               (uint32_t)(g.bh * stride), (uint32_t)g.bn, (uint32_t)stride, (uint32_t)stride,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+  if (r) return -(2000 + r);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(hfl::conv_wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         hfl::WG_SMEM);
+    if (e != cudaSuccess) return -(int)e;
+    configured = true;
+  }
+  if (splits > 1 && zero_first) cudaMemsetAsync(dW, 0, (size_t)Kout * R * S * C * sizeof(float), stream);
+  dim3 grid((Kout + 127) / 128, C / 64, R * S * splits);
+  hfl::conv_wgrad_tcgen05_kernel<<<grid, hfl::CV_THREADS, hfl::WG_SMEM, stream>>>(tdy, tx, dW, g);
+  hfl::count_launch();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? splits : -(int)e;
+}

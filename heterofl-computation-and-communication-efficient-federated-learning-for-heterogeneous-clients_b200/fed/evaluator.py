@@ -268,6 +268,8 @@ class Evaluator:
                   "idx": torch.zeros(per_rank, Nc, dtype=torch.int64, device=self.device),
                   "row": torch.zeros(1, dtype=torch.int64, device=self.device),
                   "acc": torch.zeros(6, dtype=torch.float64, device=self.device),
+                  "owner": torch.empty_like(owner_dev),
+                  "masks": torch.empty_like(user_masks_dev) if user_masks_dev is not None else None,
                   "ab": {name: (torch.zeros(w, dtype=torch.float32, device=self.device),
                                 torch.zeros(w, dtype=torch.float32, device=self.device)) for name, w in bn},
                   "graph": None}
@@ -278,13 +280,16 @@ class Evaluator:
         aug = self._augment(ds, False)
         st["imgs"].copy_(imgs_src, non_blocking=True)
         st["labels"].copy_(labels_src, non_blocking=True)
+        st["owner"].copy_(owner_dev, non_blocking=True)      # the graph only ever reads evaluator-owned buffers
+        if st["masks"] is not None:
+            st["masks"].copy_(user_masks_dev, non_blocking=True)
         st["wc"].copy_(global_arena)
         for name, (a, b) in self.fused.eval_affine(st["P"], running).items():
             st["ab"][name][0].copy_(a)
             st["ab"][name][1].copy_(b)
         st["row"].zero_()
         st["acc"].zero_()
-        use_mask = bool(self.cfg["mask"]) and user_masks_dev is not None
+        use_mask = bool(self.cfg["mask"]) and st["masks"] is not None
         if st["graph"] is None:
             def chunk():
                 idx = st["idx"].index_select(0, st["row"]).view(-1)
@@ -295,9 +300,9 @@ class Evaluator:
                 acc[3] += F.cross_entropy(z, y, reduction="sum").double()
                 acc[4] += (z.argmax(1) == y).sum()
                 acc[5] += Nc
-                own = owner_dev.index_select(0, idx)
+                own = st["owner"].index_select(0, idx)
                 sel = own >= 0
-                zl = z.masked_fill(~user_masks_dev[own.clamp(min=0)].bool(), 0.0) if use_mask else z
+                zl = z.masked_fill(~st["masks"][own.clamp(min=0)].bool(), 0.0) if use_mask else z
                 ce = F.cross_entropy(zl, y, reduction="none")
                 acc[0] += (ce * sel).sum().double()
                 acc[1] += ((zl.argmax(1) == y) & sel).sum()

@@ -349,3 +349,25 @@ def test_tcgen05_conv_dgrad_matches_autograd(N, C, H, K, R):
     res = torch.randn_like(ref).bfloat16().contiguous(memory_format=torch.channels_last)
     dx2 = cu.C().conv_dgrad_tc(dy, wk, res)
     assert float((dx2.float() - ref - res.float()).abs().max()) < 4e-2 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("N,C,H,K,R,stride", [(10, 64, 32, 64, 3, 1), (10, 64, 32, 128, 3, 2), (10, 128, 16, 128, 3, 1),
+                                               (10, 64, 32, 128, 1, 2), (10, 256, 8, 256, 3, 1), (12, 512, 4, 512, 3, 1),
+                                               (8, 256, 8, 512, 3, 2)])
+def test_tcgen05_conv_wgrad_matches_autograd(N, C, H, K, R, stride):
+    """Weight gradient with both operands MN-major (pixels = reduction), split-K with fp32 atomics."""
+    cu = _cu()
+    dev = torch.device("cuda")
+    torch.manual_seed(N + C + K + R)
+    x = torch.randn(N, C, H, H, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(K, C, R, R, device=dev) * 0.05).requires_grad_(True)
+    y = torch.nn.functional.conv2d(x.float(), w, None, stride, R // 2)
+    dy = torch.randn_like(y).bfloat16().contiguous(memory_format=torch.channels_last)
+    y.backward(dy.float())
+    if not cu.C().conv_wgrad_tc_supported(N, H, H, C, K, R, R, stride):
+        pytest.skip("shape not supported by the wgrad kernel")
+    dw = cu.C().conv_wgrad_tc(dy, x, R, stride)
+    torch.cuda.synchronize()
+    ref = w.grad
+    assert dw.shape == ref.shape
+    assert float((dw - ref).abs().max()) < 2e-2 * max(1.0, float(ref.abs().max()))
