@@ -16,6 +16,8 @@ from __future__ import annotations
 import argparse
 import os
 import sys
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # many concurrent client streams (set before CUDA init)
 from typing import Dict, List, Optional
 
 import torch

@@ -338,37 +338,60 @@ class Engine:
         return bool(self.opt.async_eval and self.is_cuda and self._agg_backend in ("local", "p2p"))
 
     def _launch_eval(self, epoch: int) -> None:
-        """Snapshot ``W_g`` and enqueue the sBN + test passes on a low-priority side stream; the next round's
-        training proceeds on the main / slot streams meanwhile.  Results are fetched by :meth:`collect_eval`."""
-        from ..parallel.dist import peer_channel
+        """Snapshot ``W_g`` and run the sBN + test passes on a low-priority side stream, enqueued from a helper host
+        thread (graph launches block the issuing thread once the stream's queue is full); the next round's training
+        proceeds on the main thread / slot streams meanwhile.  Results are fetched by :meth:`collect_eval`."""
+        import threading
         main = torch.cuda.current_stream(self.device)
         if getattr(self, "_eval_stream", None) is None:
             self._eval_stream = torch.cuda.Stream(device=self.device, priority=0)
             self._eval_arena = torch.empty_like(self.global_arena)
             self._eval_done = None
             self._eval_result = None
+            self._eval_thread = None
+        self._join_eval_thread()
         if self._eval_done is not None:
             main.wait_event(self._eval_done)           # previous evaluation must have consumed the snapshot
         self._eval_arena.copy_(self.global_arena, non_blocking=True)
         ready = torch.cuda.Event()
         ready.record(main)
-        shared = torch.Generator().manual_seed(self.seed * 1000003 + epoch * 7919 + 104729)
-        with torch.cuda.stream(self._eval_stream), peer_channel(1):
-            self._eval_stream.wait_event(ready)
-            if self.is_lm:
-                test = self.evaluator.test_lm(self._eval_arena, self._h2d(self.test_rows), sync=False)
-            else:
-                self.running = self.evaluator.sbn_stats(self._eval_arena, self.dataset["train"],
-                                                        self._src(self.train_img), shared)
-                test = self.evaluator.test_vision(self._eval_arena, self.running, self.dataset["test"],
-                                                  self._src(self.test_img), self._src(self.test_lab), self.test_owner,
-                                                  self.user_masks, sync=False)
-            self._eval_done = torch.cuda.Event()
-            self._eval_done.record(self._eval_stream)
-        self._eval_result = (epoch, test)
+        self._eval_error = None
+        self._eval_thread = threading.Thread(target=self._eval_worker, args=(epoch, ready), daemon=True)
+        self._eval_thread.start()
+
+    def _eval_worker(self, epoch: int, ready) -> None:
+        from ..parallel.dist import peer_channel
+        try:
+            torch.cuda.set_device(self.device)
+            shared = torch.Generator().manual_seed(self.seed * 1000003 + epoch * 7919 + 104729)
+            with torch.cuda.stream(self._eval_stream), peer_channel(1), torch.no_grad():
+                self._eval_stream.wait_event(ready)
+                if self.is_lm:
+                    test = self.evaluator.test_lm(self._eval_arena, self._h2d(self.test_rows), sync=False)
+                else:
+                    self.running = self.evaluator.sbn_stats(self._eval_arena, self.dataset["train"],
+                                                            self._src(self.train_img), shared)
+                    test = self.evaluator.test_vision(self._eval_arena, self.running, self.dataset["test"],
+                                                      self._src(self.test_img), self._src(self.test_lab),
+                                                      self.test_owner, self.user_masks, sync=False)
+                done = torch.cuda.Event()
+                done.record(self._eval_stream)
+            self._eval_done = done
+            self._eval_result = (epoch, test)
+        except BaseException as e:      # surfaced by collect_eval on the main thread
+            self._eval_error = e
+
+    def _join_eval_thread(self) -> None:
+        t = getattr(self, "_eval_thread", None)
+        if t is not None:
+            t.join()
+            self._eval_thread = None
+            if self._eval_error is not None:
+                raise self._eval_error
 
     def collect_eval(self) -> Optional[Dict]:
         """Wait for the most recently launched evaluation and return ``{'epoch', 'test': {...}}`` (None if none)."""
+        self._join_eval_thread()
         if getattr(self, "_eval_result", None) is None:
             return None
         self._eval_done.synchronize()

@@ -134,8 +134,35 @@ def conv_fwd(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> torch.T
     return F.conv2d(x, w, None, stride, pad)
 
 
+# backward convolutions on the tcgen05 kernels: "off" | "on" | "auto" (table from profiles/conv_bwd_bench.md)
+CONV_BWD_TC_MODE = os.environ.get("HFL_CONV_BWD_TC", "off")
+
+
+def _tc_bwd_ok(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> bool:
+    if CONV_BWD_TC_MODE == "off" or not _use_kernels(x) or w.dtype != torch.bfloat16 or pad != w.shape[2] // 2:
+        return False
+    return (x.is_contiguous(memory_format=torch.channels_last) and dy.is_contiguous(memory_format=torch.channels_last)
+            and w.permute(0, 2, 3, 1).is_contiguous())
+
+
 def conv_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int, pad: int, need_dx: bool = True):
-    """(dx | None, dw) through the library convolution backward (cuDNN dgrad + wgrad)."""
+    """``(dx | None, dw)``.  Library path: cuDNN dgrad + wgrad.  tcgen05 path (``HFL_CONV_BWD_TC``): stride-1 dgrad as
+    an implicit GEMM with mirrored taps + MN-major filter operand, wgrad with both operands MN-major and split-K;
+    ``dw`` then comes back as fp32 (the multi-tensor optimiser reads either precision)."""
+    if _tc_bwd_ok(dy, x, w, stride, pad):
+        N, C, H, W = x.shape
+        K, _, R, S = w.shape
+        C_ = cu.C()
+        dx = dw = None
+        if need_dx and stride == 1 and C_.conv_tc_supported(N, H, W, K, C, R, S, 1):
+            dx = C_.conv_dgrad_tc(dy, w, None)
+        if C_.conv_wgrad_tc_supported(N, H, W, C, K, R, S, stride):
+            dw = C_.conv_wgrad_tc(dy, x, R, stride)
+        if (dx is not None or not need_dx) and dw is not None:
+            return dx, dw
+        rest = torch.ops.aten.convolution_backward(dy, x, w, None, (stride, stride), (pad, pad), (1, 1), False, (0, 0), 1,
+                                                   (need_dx and dx is None, dw is None, False))
+        return (dx if dx is not None else rest[0]), (dw if dw is not None else rest[1])
     dx, dw, _ = torch.ops.aten.convolution_backward(dy, x, w, None, (stride, stride), (pad, pad), (1, 1), False,
                                                     (0, 0), 1, (need_dx, True, False))
     return dx, dw

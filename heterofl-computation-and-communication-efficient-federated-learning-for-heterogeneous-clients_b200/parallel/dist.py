@@ -62,30 +62,36 @@ def set_peer_pool(pool) -> None:
     _PEER_POOL = pool
 
 
-_CHANNEL = 0
+import threading
+
+_TLS = threading.local()
+
+
+def _channel() -> int:
+    return getattr(_TLS, "channel", 0)
 
 
 class peer_channel:
-    """Context manager: small all-reduces issued inside use barrier channel ``ch`` (one channel per CUDA stream)."""
+    """Context manager (thread-local): small all-reduces issued inside use barrier channel ``ch`` -- one channel per
+    concurrently used CUDA stream / host thread."""
 
     def __init__(self, ch: int):
         self.ch, self.prev = ch, 0
 
     def __enter__(self):
-        global _CHANNEL
-        self.prev, _CHANNEL = _CHANNEL, self.ch
+        self.prev = _channel()
+        _TLS.channel = self.ch
         return self
 
     def __exit__(self, *a):
-        global _CHANNEL
-        _CHANNEL = self.prev
+        _TLS.channel = self.prev
 
 
 def all_reduce_sum(info: DistInfo, t: torch.Tensor) -> torch.Tensor:
     if info.world > 1:
         if _PEER_POOL is not None and t.is_cuda and t.numel() <= _PEER_POOL.SCRATCH_FLOATS \
                 and t.dtype in (torch.float32, torch.float64):
-            _PEER_POOL.all_reduce_sum_(t, _CHANNEL)       # fp64 meters travel as fp32 (sums < 1e6, counts exact)
+            _PEER_POOL.all_reduce_sum_(t, _channel())       # fp64 meters travel as fp32 (sums < 1e6, counts exact)
         else:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
