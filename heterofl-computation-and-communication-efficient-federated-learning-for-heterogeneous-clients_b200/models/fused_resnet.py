@@ -26,10 +26,27 @@ from ..plan.spec import ModelSpec
 
 
 class FusedResNet:
-    def __init__(self, spec: ModelSpec, scale_rate: float):
+    def __init__(self, spec: ModelSpec, scale_rate: float, overlap_wgrad: bool = True):
         assert spec.family == "resnet" and spec.meta["norm"] == "bn" and spec.meta["kind"] == "block"
         self.spec, self.blocks = spec, spec.meta["blocks"]
         self.scale_rate = float(scale_rate)
+        self.overlap_wgrad = overlap_wgrad
+        self._side = None
+
+    def _conv_bwd(self, dy, x, w, stride, pad, keep, need_dx=True):
+        """dgrad on the current stream (it feeds the next layer's backward: the critical path), wgrad on a side stream
+        (only the optimiser needs it).  ``keep`` holds every tensor the side stream reads until the step's join."""
+        if not (self.overlap_wgrad and dy.is_cuda):
+            return fo.conv_bwd(dy, x, w, stride, pad, need_dx=need_dx)
+        main = torch.cuda.current_stream(dy.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dy.device)
+        keep.extend((dy, x))
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            _, dw = fo.conv_bwd(dy, x, w, stride, pad, need_dx=False)
+        dx = fo.conv_bwd(dy, x, w, stride, pad, need_dx=True, need_dw=False)[0] if need_dx else None
+        return dx, dw
 
     @staticmethod
     def eligible(spec: ModelSpec) -> bool:
@@ -44,6 +61,7 @@ class FusedResNet:
         eps = BN_EPS * s_rate * s_rate          # Scaler folded into epsilon
         G: Dict[str, torch.Tensor] = {}
         saved = []
+        keep: List[torch.Tensor] = []
         c0 = fo.conv_fwd(x, P["conv1.weight"], 1, 1)
         cur, res = c0, None                     # block input is s = cur (+ res)
         for blk in self.blocks:
@@ -80,22 +98,24 @@ class FusedResNet:
         for (blk, s_in, o1, m1, i1, c1, o2, m2, i2) in reversed(saved):
             pre, stride = blk["prefix"], blk["stride"]
             # ds = grad wrt block output (= c2 + sc)
-            do2, G[pre + ".conv2.weight"] = fo.conv_bwd(ds, o2, P[pre + ".conv2.weight"], 1, 1)
+            do2, G[pre + ".conv2.weight"] = self._conv_bwd(ds, o2, P[pre + ".conv2.weight"], 1, 1, keep)
             G[pre + ".n2.weight"] = torch.empty_like(P[pre + ".n2.weight"])
             G[pre + ".n2.bias"] = torch.empty_like(P[pre + ".n2.bias"])
             dc1 = fo.bn_act_bwd(do2, None, None, c1, m2, i2, P[pre + ".n2.weight"], P[pre + ".n2.bias"],
                                 G[pre + ".n2.weight"], G[pre + ".n2.bias"])
-            do1, G[pre + ".conv1.weight"] = fo.conv_bwd(dc1, o1, P[pre + ".conv1.weight"], stride, 1)
+            do1, G[pre + ".conv1.weight"] = self._conv_bwd(dc1, o1, P[pre + ".conv1.weight"], stride, 1, keep)
             G[pre + ".n1.weight"] = torch.empty_like(P[pre + ".n1.weight"])
             G[pre + ".n1.bias"] = torch.empty_like(P[pre + ".n1.bias"])
             if blk["shortcut"]:
-                do1b, G[pre + ".shortcut.weight"] = fo.conv_bwd(ds, o1, P[pre + ".shortcut.weight"], stride, 0)
+                do1b, G[pre + ".shortcut.weight"] = self._conv_bwd(ds, o1, P[pre + ".shortcut.weight"], stride, 0, keep)
                 ds = fo.bn_act_bwd(do1, do1b, None, s_in, m1, i1, P[pre + ".n1.weight"], P[pre + ".n1.bias"],
                                    G[pre + ".n1.weight"], G[pre + ".n1.bias"])
             else:
                 ds = fo.bn_act_bwd(do1, None, ds, s_in, m1, i1, P[pre + ".n1.weight"], P[pre + ".n1.bias"],
                                    G[pre + ".n1.weight"], G[pre + ".n1.bias"])
-        _, G["conv1.weight"] = fo.conv_bwd(ds, x, P["conv1.weight"], 1, 1, need_dx=False)
+        _, G["conv1.weight"] = self._conv_bwd(ds, x, P["conv1.weight"], 1, 1, keep, need_dx=False)
+        if self._side is not None and x.is_cuda:
+            torch.cuda.current_stream(x.device).wait_stream(self._side)    # join: all weight gradients are complete
         return loss, G
 
     @staticmethod

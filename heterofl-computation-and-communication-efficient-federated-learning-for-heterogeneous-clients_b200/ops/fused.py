@@ -145,10 +145,18 @@ def _tc_bwd_ok(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int, 
             and w.permute(0, 2, 3, 1).is_contiguous())
 
 
-def conv_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int, pad: int, need_dx: bool = True):
+def conv_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int, pad: int, need_dx: bool = True,
+             need_dw: bool = True):
     """``(dx | None, dw)``.  Library path: cuDNN dgrad + wgrad.  tcgen05 path (``HFL_CONV_BWD_TC``): stride-1 dgrad as
     an implicit GEMM with mirrored taps + MN-major filter operand, wgrad with both operands MN-major and split-K;
     ``dw`` then comes back as fp32 (the multi-tensor optimiser reads either precision)."""
+    if not need_dw:
+        if _tc_bwd_ok(dy, x, w, stride, pad) and stride == 1 and cu.C().conv_tc_supported(
+                x.shape[0], x.shape[2], x.shape[3], w.shape[0], x.shape[1], w.shape[2], w.shape[3], 1):
+            return cu.C().conv_dgrad_tc(dy, w, None), None
+        dx, _, _ = torch.ops.aten.convolution_backward(dy, x, w, None, (stride, stride), (pad, pad), (1, 1), False,
+                                                       (0, 0), 1, (True, False, False))
+        return dx, None
     if _tc_bwd_ok(dy, x, w, stride, pad):
         N, C, H, W = x.shape
         K, _, R, S = w.shape
