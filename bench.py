@@ -101,7 +101,8 @@ def run_ours(args):
         cfg["fused"] = False
     eng = Engine(cfg, info, options=EngineOptions(out_dir="/tmp/hfl_bench", quiet=True, save=False,
                                                   max_concurrent=args.max_concurrent,
-                                                  agg_backend=args.agg_backend, async_eval=args.async_eval))
+                                                  agg_backend=args.agg_backend, async_eval=args.async_eval,
+                                                  threaded_issue=not args.single_thread_issue))
     eng.setup()
     t0 = time.time()
     eng.prewarm()
@@ -201,6 +202,7 @@ def main():
     ap.add_argument("--local-epochs", type=int, default=0)
     ap.add_argument("--max-concurrent", type=int, default=16)
     ap.add_argument("--agg-backend", default="auto")
+    ap.add_argument("--single-thread-issue", action="store_true", help="A/B: issue all graph replays from one host thread")
     ap.add_argument("--async-eval", action="store_true",
                     help="overlap sBN+test of round r with the training of round r+1 on a side stream (measured: no "
                          "gain on one GPU -- the big eval kernels delay the latency-bound training kernels)")

@@ -58,6 +58,7 @@ class EngineOptions:
     stats_chunk_groups: int = 256
     test_chunk: int = 2500
     async_eval: bool = False             # overlap round r's sBN+test with round r+1's training (run_round/collect_eval)
+    threaded_issue: bool = True          # one host thread per active client slot issues its graph replays
 
 
 class PhaseTimer:
@@ -447,6 +448,44 @@ class Engine:
                     s.stream.wait_stream(main)
                 active.append([g, s, i])
 
+        if self.is_cuda and self.opt.threaded_issue:
+            # One host thread per active slot drives that slot's graph replays.  cudaGraphLaunch of graphs whose
+            # kernel nodes carry TMA descriptors (cuDNN's sm_100 kernels, our tcgen05 kernels) blocks its caller for
+            # hundreds of microseconds; issued round-robin from ONE thread those stalls serialise all slots.
+            import threading
+            errors: List[BaseException] = []
+
+            def worker(g, s, i):
+                try:
+                    torch.cuda.set_device(self.device)
+                    with torch.cuda.stream(s.stream):
+                        for _ in g:
+                            pass
+                        result_arenas[i].copy_(s.w, non_blocking=True)
+                        meter = s.meter.buf.clone()
+                    results[i] = {"arena": result_arenas[i], "meter": meter, "level": levels[i]}
+                except BaseException as e:       # re-raised on the main thread
+                    errors.append(e)
+
+            while pending:
+                wave = [pending.popleft() for _ in range(min(self.opt.max_concurrent, len(pending)))]
+                start_batch(wave)
+                threads = []
+                for g, s, i in active:
+                    with torch.cuda.stream(s.stream):
+                        next(g, None)            # first step on the main thread: static-buffer setup / graph capture
+                    t = threading.Thread(target=worker, args=(g, s, i), daemon=True)
+                    t.start()
+                    threads.append(t)
+                for t in threads:
+                    t.join()
+                for g, s, i in active:
+                    main.wait_stream(s.stream)
+                    busy.discard(id(s))
+                active.clear()
+                if errors:
+                    raise errors[0]
+            return results
         while pending or active:
             room = self.opt.max_concurrent - len(active)
             if pending and room > 0:

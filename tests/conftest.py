@@ -57,6 +57,18 @@ class _RefOracle:
         self.mods = dict(config=rconfig, fed=rfed, models=rmodels, utils=rutils, data=rdata)
         return self.mods
 
+    def reset_cfg(self):
+        """Restore the reference's global cfg to the pristine config.yml contents (its entry-point modules build an
+        argparse flag per cfg key at import time and choke on keys derived by earlier process_control() calls)."""
+        import yaml
+        m = self.load()
+        with open(os.path.join(REFERENCE_SRC, "config.yml"), "r") as f:
+            fresh = yaml.load(f, Loader=yaml.FullLoader)
+        cfg = m["config"].cfg
+        cfg.clear()
+        cfg.update(fresh)
+        return cfg
+
     def set_cfg(self, data_name, model_name, control_name, **extra):
         m = self.load()
         cfg = m["config"].cfg

@@ -43,7 +43,7 @@ def test_local_global_metrics_match_reference(ref, tmp_path, mask):
     argv = sys.argv
     sys.argv = ["train_classifier_fed.py", "--data_name", "MNIST", "--model_name", "conv", "--control_name", control,
                 "--device", "cpu"]
-    saved = {k: m["config"].cfg.pop(k) for k in list(m["config"].cfg) if k in ("control_name",)}
+    ref.reset_cfg()
     try:
         sys.modules.pop("train_classifier_fed", None)
         T = importlib.import_module("train_classifier_fed")

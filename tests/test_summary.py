@@ -23,7 +23,7 @@ def test_summary_matches_reference_hooks(ref, data, model, control, extra, shape
     sys.path.insert(0, "/root/reference/src")
     argv = sys.argv
     sys.argv = ["summary.py", "--data_name", data, "--model_name", model, "--control_name", control, "--device", "cpu"]
-    saved = {k: m["config"].cfg.pop(k) for k in ("control_name",) if k in m["config"].cfg}
+    ref.reset_cfg()
     try:
         import tabulate  # noqa: F401
         sys.modules.pop("summary", None)
