@@ -7,11 +7,11 @@ gathers a batch, applies crop/flip/normalise and emits channels-last activations
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 
-from .datasets import LMData, VisionData
+from .datasets import VisionData
 
 
 class VisionAugment:

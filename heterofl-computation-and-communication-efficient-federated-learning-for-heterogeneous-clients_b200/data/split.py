@@ -13,7 +13,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 import torch
 
-from .datasets import LMData, VisionData
+from .datasets import VisionData
 
 
 def _labels_of(ds) -> torch.Tensor:

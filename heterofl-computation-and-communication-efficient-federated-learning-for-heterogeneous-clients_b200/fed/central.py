@@ -14,7 +14,6 @@ import shutil
 import time
 from typing import Dict, Optional
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

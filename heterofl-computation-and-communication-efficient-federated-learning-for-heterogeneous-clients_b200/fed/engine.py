@@ -15,20 +15,19 @@ Round = (reference ``src/train_classifier_fed.py:74-94`` / ``train`` :99-124 / `
 """
 from __future__ import annotations
 
-import copy
 import os
 import shutil
 import time
 from collections import deque
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional
 
 import numpy as np
 import torch
 
 from ..ckpt import compat as ckpt
-from ..config.control import make_cfg, model_tag
-from ..data.datasets import LMData, VisionData, fetch_dataset, process_dataset
+from ..config.control import model_tag
+from ..data.datasets import LMData, fetch_dataset, process_dataset
 from ..data.pipeline import VisionAugment
 from ..data.split import split_dataset
 from ..models import Model
@@ -39,7 +38,7 @@ from ..plan.spec import build_spec
 from ..utils.logger import Logger
 from ..utils.optim import make_scheduler_state
 from .evaluator import Evaluator
-from .federation import Federation, combine_torch, label_mask_tensor
+from .federation import Federation, combine_torch
 from .trainer import TrainSlot
 
 

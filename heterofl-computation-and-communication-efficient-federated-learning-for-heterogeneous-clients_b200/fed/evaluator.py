@@ -11,13 +11,12 @@ CIFAR-10) and ``test()`` (``:141-169``) runs 100 per-user loaders plus one globa
 """
 from __future__ import annotations
 
-import math
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
 import torch.nn.functional as F
 
-from ..data.datasets import LMData, VisionData
+from ..data.datasets import VisionData
 from ..data.pipeline import VisionAugment, lm_windows
 from ..models import Model
 from ..models.fused_resnet import FusedResNet
@@ -76,7 +75,6 @@ class Evaluator:
         ctx = NormCtx("stats", group=B)
         G = self.stats_chunk_groups
         chunks = [(g0, min(g0 + G, n_full)) for g0 in range(0, n_full, G)]
-        labels_dummy = None
         for ci, (g0, g1) in enumerate(chunks):
             if ci % self.info.world != self.info.rank:
                 continue

@@ -19,12 +19,10 @@ are as narrow as 4 channels.
 """
 from __future__ import annotations
 
-import math
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, Optional
 
 import torch
 
-from ..data.datasets import LMData, VisionData
 from ..data.pipeline import VisionAugment, lm_windows
 from ..models import Model
 from ..models.fused_resnet import FusedResNet

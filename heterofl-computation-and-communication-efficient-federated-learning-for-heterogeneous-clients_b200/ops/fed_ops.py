@@ -1,7 +1,7 @@
 """Device-side distribute / aggregate: descriptor tables + launch wrappers for ``csrc/fed_kernels.cu``."""
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch

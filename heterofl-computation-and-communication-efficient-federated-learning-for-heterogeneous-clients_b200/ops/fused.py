@@ -5,7 +5,7 @@ Activations are logical ``[N, C, H, W]`` tensors with channels-last strides (phy
 from __future__ import annotations
 
 import os
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 import torch.nn.functional as F

@@ -18,7 +18,7 @@ the padded sum/count all-reduce baseline (``parallel/baseline.py``).
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import List, Optional
 
 import torch
 import torch.distributed as dist

@@ -17,7 +17,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from .spec import FIXED, HEADS, PREFIX, Axis, ModelSpec, ParamSpec
+from .spec import FIXED, HEADS, PREFIX, Axis, ModelSpec
 
 ALIGN = 8  # elements; keeps every tensor 32 B (fp32) / 16 B (bf16) aligned inside the arena
 

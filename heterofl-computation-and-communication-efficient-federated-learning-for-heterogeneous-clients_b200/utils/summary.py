@@ -10,7 +10,7 @@ twice.  Here the same table is derived analytically from the :class:`ModelSpec` 
 from __future__ import annotations
 
 import os
-from typing import Dict, List, Tuple
+from typing import Dict, List
 
 import numpy as np
 
