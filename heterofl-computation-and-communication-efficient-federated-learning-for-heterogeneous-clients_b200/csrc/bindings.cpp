@@ -23,10 +23,10 @@ void hfl_masked_ce(const void*, int, const long long*, const unsigned char*, int
 void hfl_augment(const unsigned char*, const long long*, const int*, const float*, const float*, int, int, int, int,
                  int, void*, int, cudaStream_t);
 int hfl_bn_act_fwd(const void*, const void*, void*, void*, const void*, const void*, int, float, int, int, int, int,
-                   float*, float*, float*, float*, cudaStream_t);
+                   float*, float*, float*, float*, int, cudaStream_t);
 void hfl_affine_act(const void*, const void*, void*, void*, const float*, const float*, long, int, int, cudaStream_t);
 int hfl_bn_act_bwd(const void*, const void*, const void*, const void*, const float*, const float*, const void*,
-                   const void*, int, int, int, int, float, int, void*, void*, void*, float*, cudaStream_t);
+                   const void*, int, int, int, int, float, int, void*, void*, void*, float*, int, cudaStream_t);
 int hfl_ms_chunk();
 void hfl_multi_sgd_clip_step(const void*, const void*, int, float*, void*, float*, const float*, float, float, float,
                              float*, cudaStream_t);
@@ -171,7 +171,8 @@ static const void* optp(const c10::optional<torch::Tensor>& t) { return t.has_va
 // x, res: NHWC-dense bf16 activations (any logical shape with C the fastest physical dim); returns
 // [s (or undefined), y, mean[G,C], invstd[G,C], var_unbiased[G,C]]
 std::vector<torch::Tensor> bn_act_fwd(torch::Tensor x, c10::optional<torch::Tensor> res, torch::Tensor gamma,
-                                      torch::Tensor beta, double eps, int64_t groups, int64_t C, bool relu) {
+                                      torch::Tensor beta, double eps, int64_t groups, int64_t C, bool relu,
+                                      c10::optional<torch::Tensor> ws_persistent) {
   CHECK_CUDA_T(x);
   TORCH_CHECK(x.scalar_type() == torch::kBFloat16, "bn_act_fwd: bf16 activations only");
   TORCH_CHECK(is_pow2(C) && C >= 4 && C <= 2048, "bn_act_fwd: C must be a power of two in [4, 2048]");
@@ -187,10 +188,14 @@ std::vector<torch::Tensor> bn_act_fwd(torch::Tensor x, c10::optional<torch::Tens
   auto fopt = torch::TensorOptions().dtype(torch::kFloat32).device(x.device());
   auto stats = torch::empty({3, groups, C}, fopt);
   float* sp = stats.data_ptr<float>();
-  auto ws = torch::empty({groups, 2, C}, fopt);   // scratch of the split (wide) path
+  // scratch of the split (wide) path: per call, or a caller-owned zero-initialised fp32 [2C+1] slab that the apply
+  // kernel re-zeroes itself (no memset node in captured graphs)
+  const bool wp = ws_persistent.has_value() && groups == 1;
+  if (wp) TORCH_CHECK(ws_persistent->scalar_type() == torch::kFloat32 && ws_persistent->numel() >= 2 * C + 1);
+  auto ws = wp ? *ws_persistent : torch::empty({groups, 2, C}, fopt);
   int e = hfl_bn_act_fwd(x.data_ptr(), optp(res), res.has_value() ? s.data_ptr() : nullptr, y.data_ptr(),
                          gamma.data_ptr(), beta.data_ptr(), pb ? 1 : 0, (float)eps, (int)groups, (int)(M / groups),
-                         (int)C, relu ? 1 : 0, sp, sp + groups * C, sp + 2 * groups * C, ws.data_ptr<float>(),
+                         (int)C, relu ? 1 : 0, sp, sp + groups * C, sp + 2 * groups * C, ws.data_ptr<float>(), wp ? 1 : 0,
                          cur_stream());
   TORCH_CHECK(e == 0, "bn_act_fwd launch failed: ", cudaGetErrorString((cudaError_t)e));
   check_launch();
@@ -216,7 +221,7 @@ std::vector<torch::Tensor> affine_act(torch::Tensor x, c10::optional<torch::Tens
 torch::Tensor bn_act_bwd(torch::Tensor dy, c10::optional<torch::Tensor> dy2, c10::optional<torch::Tensor> dres,
                          torch::Tensor s, torch::Tensor mean, torch::Tensor invstd, torch::Tensor gamma,
                          torch::Tensor beta, torch::Tensor dgamma, torch::Tensor dbeta, int64_t C, int64_t hw,
-                         double dy_scale, bool relu) {
+                         double dy_scale, bool relu, c10::optional<torch::Tensor> ws_persistent) {
   CHECK_CUDA_T(dy); CHECK_CUDA_T(s);
   TORCH_CHECK(s.scalar_type() == torch::kBFloat16 && dy.scalar_type() == torch::kBFloat16);
   TORCH_CHECK(is_pow2(C) && C >= 4 && C <= 2048);
@@ -232,11 +237,13 @@ torch::Tensor bn_act_bwd(torch::Tensor dy, c10::optional<torch::Tensor> dy2, c10
   TORCH_CHECK(dgamma.is_contiguous() && dbeta.is_contiguous() && mean.scalar_type() == torch::kFloat32);
   c10::cuda::CUDAGuard guard(s.device());
   auto ds = torch::empty_like(s);
-  auto ws = torch::empty({2, C}, torch::TensorOptions().dtype(torch::kFloat32).device(s.device()));
+  const bool wp = ws_persistent.has_value();
+  if (wp) TORCH_CHECK(ws_persistent->scalar_type() == torch::kFloat32 && ws_persistent->numel() >= 2 * C + 1);
+  auto ws = wp ? *ws_persistent : torch::empty({2, C}, torch::TensorOptions().dtype(torch::kFloat32).device(s.device()));
   int e = hfl_bn_act_bwd(dy.data_ptr(), optp(dy2), optp(dres), s.data_ptr(), mean.data_ptr<float>(),
                          invstd.data_ptr<float>(), gamma.data_ptr(), beta.data_ptr(), pb ? 1 : 0, (int)M, (int)C,
                          (int)hw, (float)dy_scale, relu ? 1 : 0, ds.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                         ws.data_ptr<float>(), cur_stream());
+                         ws.data_ptr<float>(), wp ? 1 : 0, cur_stream());
   TORCH_CHECK(e == 0, "bn_act_bwd launch failed: ", cudaGetErrorString((cudaError_t)e));
   check_launch();
   return ds;

@@ -468,11 +468,28 @@ bn_stats_wide_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
   for (int c = threadIdx.x; c < C; c += blockDim.x) { atomicAdd(&ws[c], sa[c]); atomicAdd(&ws[C + c], sb[c]); }
 }
 
+// Persistent scratch protocol: ws = [2C sums][1 ticket]; every CTA of the consumer kernel takes a ticket after it has
+// copied the sums it needs; the last one zeroes sums + ticket, so the next producer launch starts from zero without a
+// memset node in the captured graph.
+__device__ __forceinline__ void ws_release(float* ws, int C, unsigned nblocks) {
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned* ticket = reinterpret_cast<unsigned*>(ws + 2 * C);
+    const unsigned t = atomicAdd(ticket, 1u);
+    if (t == nblocks - 1) {
+      for (int c = 0; c < 2 * C; ++c) ws[c] = 0.f;
+      *ticket = 0u;
+      __threadfence();
+    }
+  }
+}
+
 template <typename PT>
 __global__ void __launch_bounds__(NT)
 bn_apply_wide_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restrict__ y, const PT* __restrict__ gamma,
-                     const PT* __restrict__ beta, float eps, int M, int C, int relu, const float* __restrict__ ws,
-                     float* __restrict__ mean_out, float* __restrict__ invstd_out, float* __restrict__ varu_out) {
+                     const PT* __restrict__ beta, float eps, int M, int C, int relu, float* __restrict__ ws,
+                     float* __restrict__ mean_out, float* __restrict__ invstd_out, float* __restrict__ varu_out,
+                     int self_clean) {
   extern __shared__ float smem[];
   float *sc_a = smem, *sc_b = smem + C;
   const float inv_n = 1.f / (float)M;
@@ -499,6 +516,7 @@ bn_apply_wide_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restr
     }
   }
   __syncthreads();
+  if (self_clean) ws_release(ws, C, gridDim.x);   // last CTA to have read the sums re-zeroes them for the next launch
   float pa[8], pb[8];
   {
     const int base = (8 * threadIdx.x) % C;
@@ -574,8 +592,8 @@ bn_bwd_apply_wide_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat
                          const __nv_bfloat16* __restrict__ dres, const __nv_bfloat16* __restrict__ s,
                          const float* __restrict__ mean, const float* __restrict__ invstd,
                          const PT* __restrict__ gamma, const PT* __restrict__ beta, int M, int C, int relu,
-                         const float* __restrict__ ws, __nv_bfloat16* __restrict__ ds, PT* __restrict__ dgamma,
-                         PT* __restrict__ dbeta) {
+                         float* __restrict__ ws, __nv_bfloat16* __restrict__ ds, PT* __restrict__ dgamma,
+                         PT* __restrict__ dbeta, int self_clean) {
   float pm[8], pi[8], pg[8], pb[8], qa[8], qb[8];
   const float inv_n = 1.f / (float)M;
   {
@@ -589,6 +607,8 @@ bn_bwd_apply_wide_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat
   }
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < C; c += blockDim.x) { stp(dbeta, c, ws[c]); stp(dgamma, c, ws[C + c]); }
+  __syncthreads();
+  if (self_clean) ws_release(ws, C, gridDim.x);
   const int nvec = M * C / 8;
   const uint4* sv = reinterpret_cast<const uint4*>(s);
   const uint4* gv = reinterpret_cast<const uint4*>(dy);
@@ -670,7 +690,7 @@ static cudaError_t launch_cluster(Kern kern, dim3 grid, int cluster_x, size_t sm
     default: { constexpr int NVC = 0; CALL; break; }  \
   }
 
-static const long WIDE_ELEMS = 128L * 1024;          // per-group elements above which the split (2-launch) path wins
+static const long WIDE_ELEMS = 48L * 1024;          // per-group elements above which the split (2-launch) path wins
 static size_t wide_smem(int C) { return (2 * (size_t)C + 2 * 16 * (size_t)(C < 256 ? C : 256)) * sizeof(float); }
 static int wide_grid(long nvec) {
   long b = (nvec + NT * 2 - 1) / (NT * 2);
@@ -681,24 +701,26 @@ static int wide_grid(long nvec) {
 
 extern "C" int hfl_bn_act_fwd(const void* x, const void* res, void* s_out, void* y, const void* gamma,
                               const void* beta, int param_bf16, float eps, int groups, int Mg, int C, int relu,
-                              float* mean_out, float* invstd_out, float* varu_out, float* ws, cudaStream_t stream) {
+                              float* mean_out, float* invstd_out, float* varu_out, float* ws, int ws_persistent,
+                              cudaStream_t stream) {
   if (((long)Mg * C > WIDE_ELEMS || groups > 1) && ws != nullptr) {   // ghost batches: always the wide path
     const int nvec = Mg * C / 8;
     int gx = wide_grid(nvec);
     if (groups > 1 && gx > 16) gx = 16;           // many groups already fill the machine
     dim3 grid(gx, groups);
-    cudaMemsetAsync(ws, 0, 2 * (size_t)C * groups * sizeof(float), stream);
+    const int self_clean = (ws_persistent && groups == 1) ? 1 : 0;
+    if (!self_clean) cudaMemsetAsync(ws, 0, 2 * (size_t)C * groups * sizeof(float), stream);
     bn_stats_wide_kernel<<<grid, NT, wide_smem(C), stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res,
                                                              (__nv_bfloat16*)s_out, nvec, C, ws);
     const void* sin = res ? s_out : x;
     if (param_bf16)
       bn_apply_wide_kernel<__nv_bfloat16><<<grid, NT, 2 * C * sizeof(float), stream>>>(
           (const __nv_bfloat16*)sin, (__nv_bfloat16*)y, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, eps, Mg, C,
-          relu, ws, mean_out, invstd_out, varu_out);
+          relu, ws, mean_out, invstd_out, varu_out, self_clean);
     else
       bn_apply_wide_kernel<float><<<grid, NT, 2 * C * sizeof(float), stream>>>(
           (const __nv_bfloat16*)sin, (__nv_bfloat16*)y, (const float*)gamma, (const float*)beta, eps, Mg, C, relu, ws,
-          mean_out, invstd_out, varu_out);
+          mean_out, invstd_out, varu_out, self_clean);
     count_launch(2);
     return (int)cudaGetLastError();
   }
@@ -736,11 +758,12 @@ extern "C" void hfl_affine_act(const void* x, const void* res, void* s_out, void
 extern "C" int hfl_bn_act_bwd(const void* dy, const void* dy2, const void* dres, const void* s, const float* mean,
                               const float* invstd, const void* gamma, const void* beta, int param_bf16, int M, int C,
                               int hw, float dy_scale, int relu, void* ds, void* dgamma, void* dbeta, float* ws,
-                              cudaStream_t stream) {
+                              int ws_persistent, cudaStream_t stream) {
   if (hw == 0 && (long)M * C > WIDE_ELEMS && ws != nullptr) {
     const int nvec = M * C / 8;
     const int grid = wide_grid(nvec);
-    cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(float), stream);
+    const int self_clean = ws_persistent ? 1 : 0;
+    if (!self_clean) cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(float), stream);
     if (param_bf16) {
       bn_bwd_reduce_wide_kernel<__nv_bfloat16><<<grid, NT, wide_smem(C), stream>>>(
           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)s, mean, invstd,
@@ -748,7 +771,7 @@ extern "C" int hfl_bn_act_bwd(const void* dy, const void* dy2, const void* dres,
       bn_bwd_apply_wide_kernel<__nv_bfloat16><<<grid, NT, 0, stream>>>(
           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean,
           invstd, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, M, C, relu, ws, (__nv_bfloat16*)ds,
-          (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta);
+          (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, self_clean);
     } else {
       bn_bwd_reduce_wide_kernel<float><<<grid, NT, wide_smem(C), stream>>>(
           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)s, mean, invstd, (const float*)gamma,
@@ -756,7 +779,7 @@ extern "C" int hfl_bn_act_bwd(const void* dy, const void* dy2, const void* dres,
       bn_bwd_apply_wide_kernel<float><<<grid, NT, 0, stream>>>(
           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean,
           invstd, (const float*)gamma, (const float*)beta, M, C, relu, ws, (__nv_bfloat16*)ds, (float*)dgamma,
-          (float*)dbeta);
+          (float*)dbeta, self_clean);
     }
     count_launch(2);
     return (int)cudaGetLastError();

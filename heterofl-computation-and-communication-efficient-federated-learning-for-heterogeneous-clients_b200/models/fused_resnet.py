@@ -32,6 +32,18 @@ class FusedResNet:
         self.scale_rate = float(scale_rate)
         self.overlap_wgrad = overlap_wgrad
         self._side = None
+        self._ws: Dict[str, torch.Tensor] = {}
+
+    def _scratch(self, name: str, like: torch.Tensor) -> Optional[torch.Tensor]:
+        """Persistent, self-cleaning fp32 [2C+1] scratch of one BN call site (forward and backward use separate
+        slabs); lets the wide statistics kernels run without a memset node per launch."""
+        if not like.is_cuda:
+            return None
+        t = self._ws.get(name)
+        if t is None:
+            t = torch.zeros(2 * like.shape[1] + 1, dtype=torch.float32, device=like.device)
+            self._ws[name] = t
+        return t
 
     def _conv_bwd(self, dy, x, w, stride, pad, keep, need_dx=True):
         """dgrad on the current stream (it feeds the next layer's backward: the critical path), wgrad on a side stream
@@ -66,14 +78,16 @@ class FusedResNet:
         cur, res = c0, None                     # block input is s = cur (+ res)
         for blk in self.blocks:
             pre, stride = blk["prefix"], blk["stride"]
-            s_in, o1, m1, i1, _ = fo.bn_act_fwd(cur, res, P[pre + ".n1.weight"], P[pre + ".n1.bias"], eps)
+            s_in, o1, m1, i1, _ = fo.bn_act_fwd(cur, res, P[pre + ".n1.weight"], P[pre + ".n1.bias"], eps,
+                                                ws=self._scratch(pre + ".n1.f", cur))
             sc = fo.conv_fwd(o1, P[pre + ".shortcut.weight"], stride, 0) if blk["shortcut"] else s_in
             c1 = fo.conv_fwd(o1, P[pre + ".conv1.weight"], stride, 1)
-            _, o2, m2, i2, _ = fo.bn_act_fwd(c1, None, P[pre + ".n2.weight"], P[pre + ".n2.bias"], eps)
+            _, o2, m2, i2, _ = fo.bn_act_fwd(c1, None, P[pre + ".n2.weight"], P[pre + ".n2.bias"], eps,
+                                             ws=self._scratch(pre + ".n2.f", c1))
             c2 = fo.conv_fwd(o2, P[pre + ".conv2.weight"], 1, 1)
             saved.append((blk, s_in, o1, m1, i1, c1, o2, m2, i2))
             cur, res = c2, sc
-        s4, y4, m4, i4, _ = fo.bn_act_fwd(cur, res, P["n4.weight"], P["n4.bias"], eps)
+        s4, y4, m4, i4, _ = fo.bn_act_fwd(cur, res, P["n4.weight"], P["n4.bias"], eps, ws=self._scratch("n4.f", cur))
         # ---- head: global average pool -> linear -> masked CE (forward + backward) ----
         N, C, H, W = y4.shape
         Wl, bl = P["linear.weight"], P["linear.bias"]
@@ -102,17 +116,17 @@ class FusedResNet:
             G[pre + ".n2.weight"] = torch.empty_like(P[pre + ".n2.weight"])
             G[pre + ".n2.bias"] = torch.empty_like(P[pre + ".n2.bias"])
             dc1 = fo.bn_act_bwd(do2, None, None, c1, m2, i2, P[pre + ".n2.weight"], P[pre + ".n2.bias"],
-                                G[pre + ".n2.weight"], G[pre + ".n2.bias"])
+                                G[pre + ".n2.weight"], G[pre + ".n2.bias"], ws=self._scratch(pre + ".n2.b", c1))
             do1, G[pre + ".conv1.weight"] = self._conv_bwd(dc1, o1, P[pre + ".conv1.weight"], stride, 1, keep)
             G[pre + ".n1.weight"] = torch.empty_like(P[pre + ".n1.weight"])
             G[pre + ".n1.bias"] = torch.empty_like(P[pre + ".n1.bias"])
             if blk["shortcut"]:
                 do1b, G[pre + ".shortcut.weight"] = self._conv_bwd(ds, o1, P[pre + ".shortcut.weight"], stride, 0, keep)
                 ds = fo.bn_act_bwd(do1, do1b, None, s_in, m1, i1, P[pre + ".n1.weight"], P[pre + ".n1.bias"],
-                                   G[pre + ".n1.weight"], G[pre + ".n1.bias"])
+                                   G[pre + ".n1.weight"], G[pre + ".n1.bias"], ws=self._scratch(pre + ".n1.b", s_in))
             else:
                 ds = fo.bn_act_bwd(do1, None, ds, s_in, m1, i1, P[pre + ".n1.weight"], P[pre + ".n1.bias"],
-                                   G[pre + ".n1.weight"], G[pre + ".n1.bias"])
+                                   G[pre + ".n1.weight"], G[pre + ".n1.bias"], ws=self._scratch(pre + ".n1.b", s_in))
         _, G["conv1.weight"] = self._conv_bwd(ds, x, P["conv1.weight"], 1, 1, keep, need_dx=False)
         if self._side is not None and x.is_cuda:
             torch.cuda.current_stream(x.device).wait_stream(self._side)    # join: all weight gradients are complete

@@ -30,14 +30,14 @@ def _rows(x: torch.Tensor) -> torch.Tensor:
 
 
 def bn_act_fwd(x: torch.Tensor, res: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, eps: float,
-               groups: int = 1, relu: bool = True):
+               groups: int = 1, relu: bool = True, ws: Optional[torch.Tensor] = None):
     """``s = x (+ res)``; per-group batch statistics; ``y = relu(bn(s))``.
 
     Returns ``(s, y, mean[G,C], invstd[G,C], var_unbiased[G,C])`` (``s is x`` when ``res`` is None).
     """
     C = x.shape[1]
     if _use_kernels(x):
-        s, y, mean, invstd, varu = cu.C().bn_act_fwd(x, res, gamma, beta, float(eps), int(groups), int(C), bool(relu))
+        s, y, mean, invstd, varu = cu.C().bn_act_fwd(x, res, gamma, beta, float(eps), int(groups), int(C), bool(relu), ws)
         return (s if res is not None else x), y, mean, invstd, varu
     s = x if res is None else (x + res)
     N = s.shape[0]
@@ -71,7 +71,7 @@ def affine_act(x: torch.Tensor, res: Optional[torch.Tensor], a: torch.Tensor, b:
 def bn_act_bwd(dy: torch.Tensor, dy2: Optional[torch.Tensor], dres: Optional[torch.Tensor], s: torch.Tensor,
                mean: torch.Tensor, invstd: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
                dgamma: torch.Tensor, dbeta: torch.Tensor, hw: int = 0, dy_scale: float = 1.0,
-               relu: bool = True) -> torch.Tensor:
+               relu: bool = True, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Backward of ``y = relu(bn(s))`` for one statistics group.  ``dy`` is the gradient w.r.t. ``y`` (``hw > 0``:
     ``dy`` is ``[N, C]`` and is broadcast over the ``hw`` positions of every sample, scaled by ``dy_scale``);
     ``dy2`` is an optional second gradient w.r.t. ``y``; ``dres`` an optional gradient w.r.t. ``s`` arriving through
@@ -79,7 +79,7 @@ def bn_act_bwd(dy: torch.Tensor, dy2: Optional[torch.Tensor], dres: Optional[tor
     C = s.shape[1]
     if _use_kernels(s):
         return cu.C().bn_act_bwd(dy, dy2, dres, s, mean.reshape(-1), invstd.reshape(-1), gamma, beta, dgamma, dbeta,
-                                 int(C), int(hw), float(dy_scale), bool(relu))
+                                 int(C), int(hw), float(dy_scale), bool(relu), ws)
     shape = (1, C) + (1,) * (s.dim() - 2)
     sf = _f(s)
     m, iv = mean.reshape(shape).float(), invstd.reshape(shape).float()
