@@ -1,8 +1,8 @@
 """Which rank trains which client.
 
-A round's cost is dominated by its widest clients (a level-a step moves/computes ~250x a level-e step), so clients
-are dealt to ranks longest-processing-time-first on an estimated cost ``steps * (c0 + c1 * rate^2)`` -- ``c0`` models
-the launch-latency floor that dominates narrow levels, ``c1 * rate^2`` the FLOP/byte growth of wide ones.
+Clients are dealt to ranks longest-processing-time-first on an estimated cost ``steps * (c0 + c1 * rate)``.  The
+constants come from measured isolated train-step times on a B200 (profiles/step_census.md: ~0.53 ms at level e ...
+~0.85 ms at level a -- a batch-10 step is latency bound, so the cost grows far slower than the rate^2 FLOP count).
 Every rank computes the same assignment from the same inputs; nothing is communicated.
 """
 from __future__ import annotations
@@ -10,8 +10,8 @@ from __future__ import annotations
 from typing import List, Sequence
 
 
-def client_cost(rate: float, n_steps: int, c0: float = 1.0, c1: float = 3.0) -> float:
-    return n_steps * (c0 + c1 * rate * rate)
+def client_cost(rate: float, n_steps: int, c0: float = 0.52, c1: float = 0.33) -> float:
+    return n_steps * (c0 + c1 * rate)
 
 
 def assign_clients(costs: Sequence[float], world: int) -> List[List[int]]:
