@@ -21,7 +21,7 @@ from ..data.pipeline import VisionAugment, lm_windows
 from ..models import Model
 from ..models.fused_resnet import FusedResNet
 from ..ops import cuda as cu
-from ..ops.nn import NormCtx
+from ..ops.nn import NormCtx, masked_cross_entropy
 from ..parallel.dist import DistInfo, all_reduce_sum
 
 
@@ -337,11 +337,25 @@ class Evaluator:
         P = self._params(global_arena)
         ctx = NormCtx("eval")
         r, T = rows_dev.shape
+        bptt = int(self.cfg["bptt"])
         acc = torch.zeros(3, dtype=torch.float64, device=self.device)
-        for wi, (s, l) in enumerate(lm_windows(T, int(self.cfg["bptt"]))):
-            if wi % self.info.world != self.info.rank:
-                continue
-            out = self.model.forward(P, {"label": rows_dev[:, s:s + l].contiguous()}, ctx, None, want_score=False)
+        wins = lm_windows(T, bptt)
+        mine = [w for wi, w in enumerate(wins) if wi % self.info.world == self.info.rank]
+        full = [w for w in mine if w[1] == bptt]
+        WB = 8                                   # windows per forward: the encoder runs once on [r*WB, bptt] tokens
+        for b0 in range(0, len(full), WB):
+            grp = full[b0:b0 + WB]
+            tok = torch.cat([rows_dev[:, s0:s0 + bptt] for s0, _ in grp], dim=0).contiguous()      # [len*r, bptt]
+            z = self.model.forward(P, {"label": tok}, ctx, None, want_score="raw")["logits"]        # [len*r*bptt, V]
+            z = z.view(len(grp), r * bptt, -1)
+            tgt = tok.view(len(grp), r * bptt)
+            for wi in range(len(grp)):           # per-window mean CE (every window weighs r, reference semantics)
+                lf = masked_cross_entropy(z[wi], tgt[wi], None).double()
+                acc[0] += lf * r
+                acc[1] += torch.exp(lf) * r
+                acc[2] += r
+        for s0, l in [w for w in mine if w[1] != bptt]:
+            out = self.model.forward(P, {"label": rows_dev[:, s0:s0 + l].contiguous()}, ctx, None, want_score=False)
             lf = out["loss"].double()
             acc[0] += lf * r
             acc[1] += torch.exp(lf) * r

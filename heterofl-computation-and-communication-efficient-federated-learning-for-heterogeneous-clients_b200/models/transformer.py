@@ -70,6 +70,8 @@ def transformer_forward(spec: ModelSpec, P: Dict[str, torch.Tensor], inp: Dict, 
     d = F.gelu(_linear(x, P["decoder.linear1.weight"], P["decoder.linear1.bias"], inv))
     d = F.layer_norm(d, (E,), P["decoder.norm1.weight"], P["decoder.norm1.bias"])
     logits = _linear(d, P["decoder.linear2.weight"], P["decoder.linear2.bias"]).reshape(N * S, V)
+    if want_score == "raw":            # evaluation: the caller reduces per window
+        return {"logits": logits}
     out = {"loss": masked_cross_entropy(logits, tokens.reshape(-1), label_mask, inp.get("_meter"))}
     if want_score:
         out["score"] = masked_logits(logits.float(), label_mask).view(N, S, V).permute(0, 2, 1)
