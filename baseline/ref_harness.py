@@ -88,7 +88,15 @@ def run(args, data_name: str, model_name: str, control: str, ClockSampler) -> No
         _fabricate_data(data_name)
     if world > 1:
         dist.barrier()
+    # the repo root carries same-named wrapper scripts (train_classifier_fed.py, ...): make sure the reference's own
+    # modules win every `import` from here on
+    sys.path[:] = [REF_SRC] + [p for p in sys.path if os.path.abspath(p or ".") not in (ROOT, REF_SRC)]
+    for name in (entry, "config", "data", "fed", "models", "utils", "logger", "metrics", "modules", "datasets"):
+        mod = sys.modules.get(name)
+        if mod is not None and not str(getattr(mod, "__file__", "")).startswith(REF_SRC):
+            del sys.modules[name]
     T = __import__(entry)                 # runs the reference's argparse/cfg bootstrap at import
+    assert str(T.__file__).startswith(REF_SRC), T.__file__
     cfg = T.cfg
     T.process_control()
     cfg["model_tag"] = "0_%s_label_%s_%s" % (data_name, model_name, control)

@@ -23,13 +23,14 @@ def compat_modules():
     from ..utils.logger import Logger
     Vocab.__module__ = "datasets.lm"
     installed = []
+    swapped = []                       # (module, attr, previous value) -- e.g. the reference's own ``logger`` is imported
 
     def _install(name, **attrs):
         if name in sys.modules:
             mod = sys.modules[name]
             for k, v in attrs.items():
-                if not hasattr(mod, k):
-                    setattr(mod, k, v)
+                swapped.append((mod, k, mod.__dict__.get(k, swapped)))
+                setattr(mod, k, v)
             return
         mod = types.ModuleType(name)
         mod.__dict__.update(attrs)
@@ -46,6 +47,11 @@ def compat_modules():
     finally:
         for name in installed:
             sys.modules.pop(name, None)
+        for mod, k, old in reversed(swapped):
+            if old is swapped:
+                delattr(mod, k)
+            else:
+                setattr(mod, k, old)
 
 
 def save(obj, path, protocol: int = 2, mode: str = "torch") -> None:
