@@ -50,6 +50,9 @@ def build_parser(script: str) -> argparse.ArgumentParser:
     ap.add_argument("--agg_backend", default="auto", type=str)
     ap.add_argument("--rounds", default=0, type=int, help="run at most this many rounds/epochs (0 = full schedule)")
     ap.add_argument("--quiet", default=0, type=int)
+    ap.add_argument("--nvtx", default=0, type=int, help="emit an NVTX range per round phase")
+    ap.add_argument("--fault_drop", default=0.0, type=float,
+                    help="fault injection: probability that an active client's update is lost each round")
     return ap
 
 
@@ -76,7 +79,8 @@ def _options(args: Dict):
     from ..fed.engine import EngineOptions
     return EngineOptions(compute_dtype=args["compute_dtype"], max_concurrent=args["max_concurrent"],
                          agg_backend=args["agg_backend"], out_dir=args["out_dir"], tensorboard=True,
-                         quiet=bool(args["quiet"]))
+                         quiet=bool(args["quiet"]), nvtx=bool(args.get("nvtx", 0)),
+                         fault_drop=float(args.get("fault_drop", 0.0)))
 
 
 def run(script: str, argv: Optional[List[str]] = None) -> None:

@@ -58,17 +58,34 @@ class EngineOptions:
     test_chunk: int = 2500
     async_eval: bool = False             # overlap round r's sBN+test with round r+1's training (run_round/collect_eval)
     threaded_issue: bool = True          # one host thread per active client slot issues its graph replays
+    nvtx: bool = False                   # NVTX range per phase (distribute+train / aggregate / sbn / test) for nsys/ncu
+    fault_drop: float = 0.0              # fault injection: each active client is lost with this probability AFTER its
+    #                                      local training (its update never reaches the aggregation, the coverage
+    #                                      counts shrink accordingly); drawn identically on every rank
 
 
 class PhaseTimer:
     """CUDA-event (or wall-clock on CPU) phase timing; ``result()`` synchronises once."""
 
-    def __init__(self, device):
+    def __init__(self, device, nvtx: bool = False):
         self.cuda = torch.device(device).type == "cuda"
         self.device = device
         self.marks: List = []
+        self.nvtx = bool(nvtx and self.cuda)
+        self._open = False
+
+    def open(self, name: str) -> None:
+        """Begin an NVTX range for the phase that the next :meth:`mark` closes (no-op unless ``nvtx``)."""
+        if self.nvtx:
+            if self._open:
+                torch.cuda.nvtx.range_pop()
+            torch.cuda.nvtx.range_push("hfl/" + name)
+            self._open = True
 
     def mark(self, name: str) -> None:
+        if self.nvtx and self._open:
+            torch.cuda.nvtx.range_pop()
+            self._open = False
         if self.cuda:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record(torch.cuda.current_stream(self.device))
@@ -129,6 +146,7 @@ class Engine:
         self._slots: Dict[int, List[TrainSlot]] = {}
         self._models: Dict[float, Model] = {}
         self._peer = None
+        self._resumed = False
         self._setup_done = False
 
     # ------------------------------------------------------------------------------------------------------
@@ -274,8 +292,9 @@ class Engine:
         cfg, fed, info = self.cfg, self.federation, self.info
         epoch = self.epoch if epoch is None else epoch
         evaluate = (epoch % max(self.opt.eval_every, 1) == 0) if evaluate is None else evaluate
-        timer = PhaseTimer(self.device)
+        timer = PhaseTimer(self.device, self.opt.nvtx)
         timer.mark("start")
+        timer.open("train")
         lr = self.current_lr()
         # 1. sampling (same RNG order as the reference: randperm, then multinomial inside distribute)
         user_idx = fed.sample_users()
@@ -292,15 +311,18 @@ class Engine:
         #    number of ranks or on which rank trains a client)
         results = self._train_clients(user_idx, rates, levels, mine, lr, epoch)
         timer.mark("train")
-        # 4. aggregation
-        self._aggregate(user_idx, levels, mine, results)
+        # 4. aggregation (minus the clients the fault injector lost)
+        timer.open("aggregate")
+        lost = self._lost_clients(M, epoch)
+        self._aggregate(user_idx, levels, mine, results, lost)
         timer.mark("aggregate")
         # train metrics (sums over my clients -> all ranks)
         tm = torch.zeros(4, dtype=torch.float64, device=self.device)
         for r in results.values():
             tm += r["meter"]
         all_reduce_sum(info, tm)
-        out: Dict = {"epoch": epoch, "lr": lr, "num_active": M, "user_idx": user_idx, "rates": rates}
+        out: Dict = {"epoch": epoch, "lr": lr, "num_active": M, "user_idx": user_idx, "rates": rates,
+                     "lost": sorted(lost)}
         # 5. evaluation
         if evaluate and self._async_eval_ok():
             self._launch_eval(epoch)
@@ -309,12 +331,15 @@ class Engine:
         elif evaluate:
             shared = torch.Generator().manual_seed(self.seed * 1000003 + epoch * 7919 + 104729)
             if self.is_lm:
+                timer.open("test")
                 test = self.evaluator.test_lm(self.global_arena, self._h2d(self.test_rows))
                 timer.mark("test")
             else:
+                timer.open("sbn")
                 self.running = self.evaluator.sbn_stats(self.global_arena, self.dataset["train"],
                                                         self._src(self.train_img), shared)
                 timer.mark("sbn")
+                timer.open("test")
                 test = self.evaluator.test_vision(self.global_arena, self.running, self.dataset["test"],
                                                   self._src(self.test_img), self._src(self.test_lab),
                                                   self.test_owner, self.user_masks)
@@ -323,6 +348,8 @@ class Engine:
             out["_test_n"] = {k: v for k, v in test.items() if k.startswith("_")}
         t = tm.tolist()                                       # device -> host read of the round's result
         self.d2h_bytes += 32
+        if self._peer is not None:
+            self._peer.check()                                # a peer that never reached a device barrier -> error
         n = max(t[2], 1.0)
         train = {"Local-Loss": t[0] / n}
         if self.is_lm:
@@ -544,9 +571,21 @@ class Engine:
         return out
 
     # -- aggregation ---------------------------------------------------------------------------------------
-    def _aggregate(self, user_idx, levels, mine, results) -> None:
+    def _lost_clients(self, M: int, epoch: int) -> set:
+        p = float(self.opt.fault_drop)
+        if p <= 0.0:
+            return set()
+        g = torch.Generator().manual_seed(self.seed * 1000003 + epoch * 7919 + 15485863)
+        lost = set(torch.nonzero(torch.rand(M, generator=g) < p).flatten().tolist())
+        if len(lost) == M:                                    # keep one survivor so the round still moves W_g
+            lost.discard(min(lost))
+        return lost
+
+    def _aggregate(self, user_idx, levels, mine, results, lost=()) -> None:
         fed, info = self.federation, self.info
         masks_all = [fed.user_label_mask(u) for u in user_idx]
+        if lost:
+            results = {i: r for i, r in results.items() if i not in lost}
         if self._agg_backend == "local":
             order = sorted(results.keys())
             arenas = [results[i]["arena"] for i in order]
@@ -559,7 +598,8 @@ class Engine:
                               [masks_all[i] for i in order])
         elif self._agg_backend == "p2p":
             from ..parallel.peer import p2p_aggregate
-            p2p_aggregate(self._peer, self.tables, self.global_arena, levels, self._assignment, masks_all, info)
+            p2p_aggregate(self._peer, self.tables, self.global_arena, levels, self._assignment, masks_all, info,
+                          active=[i for i in range(len(levels)) if i not in lost] if lost else None)
         else:
             from ..parallel.baseline import allreduce_aggregate
             allreduce_aggregate(self.tables, self.global_arena, levels, results, masks_all, info)
@@ -571,8 +611,11 @@ class Engine:
         cfg = self.cfg
         last = cfg["num_epochs"]["global"] if num_rounds is None else min(cfg["num_epochs"]["global"],
                                                                           self.epoch + num_rounds - 1)
+        crash_at = int(os.environ.get("HFL_FAULT_CRASH_ROUND", "0") or 0)   # fault injection for the supervisor test
         while self.epoch <= last:
             ep = self.epoch
+            if crash_at and ep == crash_at and not self._resumed:
+                os._exit(17)                                   # simulate a rank dying mid-run (no cleanup, like SIGKILL)
             self.logger.safe(True)
             t0 = time.time()
             res = self.run_round(ep)
@@ -653,6 +696,7 @@ class Engine:
         self.load_state_dict(ck["model_dict"])
         if mode == 1:
             self.epoch = ck["epoch"]
+            self._resumed = True
             self.sched.optimizer.load_state_dict(ck["optimizer_dict"])
             self.sched.scheduler.load_state_dict(ck["scheduler_dict"])
             self.logger = ck["logger"]

@@ -146,8 +146,9 @@ class PeerPool:
 
 
 def p2p_aggregate(pool: PeerPool, tables: FedTables, global_arena: torch.Tensor, levels: List[int],
-                  assignment: List[List[int]], masks_all: List[torch.Tensor], info) -> None:
-    """``assignment[r]`` = client positions trained by rank r, in the order their result arenas were allocated."""
+                  assignment: List[List[int]], masks_all: List[torch.Tensor], info, active=None) -> None:
+    """``assignment[r]`` = client positions trained by rank r, in the order their result arenas were allocated;
+    ``active`` (optional) restricts the average to a subset of the clients (fault injection / stragglers)."""
     from ..ops import fed_ops
     dev = global_arena.device
     dt = fed_ops.device_tables(tables, dev)
@@ -157,6 +158,9 @@ def p2p_aggregate(pool: PeerPool, tables: FedTables, global_arena: torch.Tensor,
         sizes = [tables.level_layouts[levels[i]].size * 4 for i in mine]
         for i, off in zip(mine, PeerPool.round_offsets(pool.round_base, sizes)):
             ptrs[i] = pool.peer_base[r] + off
+    if active is not None:
+        ptrs, levels, masks_all = ([ptrs[i] for i in active], [levels[i] for i in active],
+                                   [masks_all[i] for i in active])
     client_ptr = torch.tensor(ptrs, dtype=torch.int64).to(dev, non_blocking=True)
     client_level = torch.tensor(levels, dtype=torch.int32).to(dev, non_blocking=True)
     masks = torch.stack([m.to(torch.uint8) for m in masks_all]).contiguous().to(dev, non_blocking=True)

@@ -41,7 +41,11 @@ def _client_arena(tables, level, i):
     return torch.randn(tables.level_layouts[level].size, generator=g)
 
 
-def _agg_worker(rank, world, port, ret):
+def _active(rnd, n):
+    return None if rnd % 3 != 1 else [i for i in range(n) if i != rnd % n]
+
+
+def _agg_worker(rank, world, port, ret, rounds=3, jitter=False):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
     from hfl_b200.parallel.dist import init_distributed, shutdown
@@ -53,14 +57,21 @@ def _agg_worker(rank, world, port, ret):
     ga = pool.alloc_persistent(gsize, torch.float32)
     ga.copy_(torch.randn(gsize, generator=torch.Generator().manual_seed(7)).to(info.device))
     pool.exchange()
-    for rnd in range(3):                     # several rounds: buffers are re-used, barriers re-armed
+    gen = torch.Generator().manual_seed(1234 + rank)
+    for rnd in range(rounds):                # several rounds: buffers are re-used, barriers re-armed
         pool.reset_round()
-        for i in assignment[rank]:
+        if jitter:                           # ranks drift apart by up to ~2 ms of device time, no host sync between
+            torch.cuda._sleep(int(torch.randint(0, 4_000_000, (1,), generator=gen)))   # rounds: only the flag
+        for i in assignment[rank]:                                                     # protocol orders them
             a = pool.alloc_round(tables.level_layouts[levels[i]].size, torch.float32)
-            a.copy_((_client_arena(tables, levels[i], i) + rnd).to(info.device))
-        p2p_aggregate(pool, tables, ga, levels, assignment, masks, info)
-        torch.cuda.synchronize()
-        pool.check()
+            a.copy_((_client_arena(tables, levels[i], i) + rnd).to(info.device), non_blocking=True)
+        p2p_aggregate(pool, tables, ga, levels, assignment, masks, info,
+                      active=_active(rnd, len(levels)) if jitter else None)
+        if not jitter:
+            torch.cuda.synchronize()
+            pool.check()
+    torch.cuda.synchronize()
+    pool.check()
     torch.save(ga.float().cpu().clone(), ret + ".%d" % rank)
     torch.distributed.barrier()
     pool.close()
@@ -81,6 +92,25 @@ def test_p2p_aggregate_exact(tmp_path):
     for r in range(2):
         got = torch.load(ret + ".%d" % r)
         assert torch.allclose(got, ref, atol=1e-5, rtol=1e-5), (r, float((got - ref).abs().max()))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_p2p_flag_protocol_stress(tmp_path):
+    """release/acquire flag protocol under randomised per-rank delays, 24 back-to-back rounds with no host
+    synchronisation in between, and a changing subset of surviving clients -- every replica still equals the oracle."""
+    from hfl_b200.fed.federation import combine_torch
+    tables, levels, masks, assignment = _agg_setup()
+    ret = str(tmp_path / "ga.pt")
+    rounds = 24
+    mp.spawn(_agg_worker, args=(2, 29850 + os.getpid() % 100, ret, rounds, True), nprocs=2, join=True)
+    ref = torch.randn(tables.global_layout.size, generator=torch.Generator().manual_seed(7))
+    for rnd in range(rounds):
+        act = _active(rnd, len(levels)) or list(range(len(levels)))
+        combine_torch(tables, ref, [_client_arena(tables, levels[i], i) + rnd for i in act],
+                      [tables.rates[levels[i]] for i in act], [masks[i] for i in act])
+    for r in range(2):
+        got = torch.load(ret + ".%d" % r)
+        assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), (r, float((got - ref).abs().max()))
 
 
 def _worker(rank, world, port, backend, ret, out_dir):
