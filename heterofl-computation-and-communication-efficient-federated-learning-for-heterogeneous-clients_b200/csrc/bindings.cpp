@@ -18,8 +18,8 @@ int hfl_fed_chunk();
 int hfl_fed_max_clients();
 void hfl_sgd_clip_step(float*, void*, void*, int, float*, long, const float*, float, float, float, float*,
                        cudaStream_t);
-void hfl_masked_ce(const void*, int, const long long*, const unsigned char*, int, int, void*, float*, float*, float,
-                   float*, double*, cudaStream_t);
+void hfl_masked_ce(const void*, int, const long long*, const unsigned char*, int, int, int, void*, float*, float*,
+                   float, float*, double*, cudaStream_t);
 void hfl_augment(const unsigned char*, const long long*, const int*, const float*, const float*, int, int, int, int,
                  int, void*, int, cudaStream_t);
 int hfl_bn_act_fwd(const void*, const void*, void*, void*, const void*, const void*, int, float, int, int, int, int,
@@ -30,8 +30,29 @@ int hfl_bn_act_bwd(const void*, const void*, const void*, const void*, const flo
 int hfl_ms_chunk();
 void hfl_multi_sgd_clip_step(const void*, const void*, int, float*, void*, float*, const float*, float, float, float,
                              float*, cudaStream_t);
-int hfl_gemm_bf16_tn(const void*, int, const void*, int, void*, int, int, const float*, float, int, int, int, int,
-                     cudaStream_t);
+int hfl_gemm_bf16_tn(const void*, int, const void*, int, void*, int, int, const float*, const void*, float, int, int,
+                     int, int, cudaStream_t);
+void hfl_gemm_timing(long long*);
+int hfl_lm_max_e();
+int hfl_lm_max_s();
+int hfl_lm_max_dh();
+void hfl_lm_embed_fwd(const long long*, const void*, const void*, const void*, const void*, int, int, int, int, float,
+                      float, float, const long long*, const long long*, unsigned, void*, int*, void*, float*,
+                      unsigned char*, cudaStream_t);
+void hfl_lm_embed_bwd(const void* const*, int, const unsigned char*, float, const void*, const float*, const void*,
+                      const int*, int, int, int, float*, float*, float*, float*, cudaStream_t);
+void hfl_lm_add_ln_fwd(const void*, const void*, const void*, const void*, int, int, float, float, const long long*,
+                       const long long*, unsigned, void*, void*, float*, unsigned char*, cudaStream_t);
+void hfl_lm_add_ln_bwd(const void* const*, int, const void*, const float*, const void*, const unsigned char*, float, int,
+                       int, void*, void*, float*, float*, float*, float, cudaStream_t);
+void hfl_lm_gelu_drop_fwd(const void*, long, float, const long long*, const long long*, unsigned, void*, unsigned char*,
+                          cudaStream_t);
+void hfl_lm_gelu_drop_bwd(const void*, const void*, const unsigned char*, float, int, int, void*, float*, float,
+                          cudaStream_t);
+void hfl_lm_colsum(const void*, int, int, int, float, float*, cudaStream_t);
+void hfl_lm_attn_fwd(const void*, const void*, const void*, int, int, int, int, float, void*, void*, cudaStream_t);
+int hfl_lm_attn_bwd(const void*, const void*, const void*, const void*, const void*, int, int, int, int, float, void*,
+                    void*, void*, float*, float*, float*, float, cudaStream_t);
 int hfl_head_smem_bytes(int, int, int);
 int hfl_head_fwd_bwd(const void*, int, int, int, const void*, const void*, int, int, const long long*,
                      const unsigned char*, float, float*, double*, void*, void*, void*, float*, cudaStream_t);
@@ -120,8 +141,10 @@ void sgd_clip_step(torch::Tensor w, c10::optional<torch::Tensor> wc, torch::Tens
 // returns (loss[1] fp32, dlogits like logits)
 std::vector<torch::Tensor> masked_ce(torch::Tensor logits, torch::Tensor target, c10::optional<torch::Tensor> mask,
                                      double n_weight, c10::optional<torch::Tensor> meter, bool need_grad) {
-  CHECK_CUDA_T(logits); CHECK_CONTIG(logits); CHECK_CONTIG(target);
+  CHECK_CUDA_T(logits); CHECK_CONTIG(target);
   TORCH_CHECK(logits.dim() == 2 && target.scalar_type() == torch::kInt64 && target.numel() == logits.size(0));
+  TORCH_CHECK(logits.stride(1) == 1 && logits.stride(0) >= logits.size(1), "masked_ce: rows must be dense");
+  const int ld = (int)logits.stride(0);
   const bool bf = logits.scalar_type() == torch::kBFloat16;
   TORCH_CHECK(bf || logits.scalar_type() == torch::kFloat32);
   const int rows = logits.size(0), V = logits.size(1);
@@ -136,8 +159,8 @@ std::vector<torch::Tensor> masked_ce(torch::Tensor logits, torch::Tensor target,
   auto fopt = torch::TensorOptions().dtype(torch::kFloat32).device(logits.device());
   auto loss = torch::empty({1}, fopt);
   auto rows_buf = torch::empty({2, rows}, fopt);
-  torch::Tensor dl = need_grad ? torch::empty_like(logits) : torch::Tensor();
-  hfl_masked_ce(logits.data_ptr(), bf ? 1 : 0, (const long long*)target.data_ptr<int64_t>(), mp, rows, V,
+  torch::Tensor dl = need_grad ? torch::empty_strided(logits.sizes(), logits.strides(), logits.options()) : torch::Tensor();
+  hfl_masked_ce(logits.data_ptr(), bf ? 1 : 0, (const long long*)target.data_ptr<int64_t>(), mp, rows, V, ld,
                 need_grad ? dl.data_ptr() : nullptr, rows_buf.data_ptr<float>(), rows_buf.data_ptr<float>() + rows,
                 (float)n_weight, loss.data_ptr<float>(), mt, cur_stream());
   check_launch();
@@ -294,25 +317,38 @@ std::vector<torch::Tensor> head_fwd_bwd(torch::Tensor y4, torch::Tensor W, torch
 // ---- tcgen05 GEMM ----------------------------------------------------------------------------------------
 // y[M,N] = act(alpha * x[M,K] @ w[N,K]^T + bias)   (x, w bf16 with K contiguous; bias fp32; y bf16 or fp32)
 torch::Tensor gemm_bf16_tn(torch::Tensor x, torch::Tensor w, c10::optional<torch::Tensor> bias, double alpha,
-                           bool gelu, bool out_fp32) {
+                           bool gelu, bool out_fp32, bool bias_inside, c10::optional<torch::Tensor> out) {
   CHECK_CUDA_T(x); CHECK_CUDA_T(w);
   TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1), "gemm_bf16_tn: shape mismatch");
   TORCH_CHECK(x.scalar_type() == torch::kBFloat16 && w.scalar_type() == torch::kBFloat16);
   TORCH_CHECK(x.stride(1) == 1 && w.stride(1) == 1, "gemm_bf16_tn: K must be contiguous");
   const int64_t M = x.size(0), K = x.size(1), N = w.size(0);
-  TORCH_CHECK(K % 8 == 0 && x.stride(0) % 8 == 0 && w.stride(0) % 8 == 0, "gemm_bf16_tn: 16-byte row alignment");
+  TORCH_CHECK(x.stride(0) % 8 == 0 && w.stride(0) % 8 == 0, "gemm_bf16_tn: 16-byte row alignment");
   TORCH_CHECK((reinterpret_cast<uintptr_t>(x.data_ptr()) & 15) == 0 && (reinterpret_cast<uintptr_t>(w.data_ptr()) & 15) == 0);
   const float* bp = nullptr;
+  const void* bhp = nullptr;
   torch::Tensor bf;
   if (bias.has_value()) {
-    bf = bias->scalar_type() == torch::kFloat32 ? bias->contiguous() : bias->to(torch::kFloat32).contiguous();
-    TORCH_CHECK(bf.numel() == N);
-    bp = bf.data_ptr<float>();
+    TORCH_CHECK(bias->numel() == N && bias->is_contiguous());
+    if (bias_inside) {               // bf16 bias read in place, y = alpha * (x w^T + b)
+      TORCH_CHECK(bias->scalar_type() == torch::kBFloat16, "gemm_bf16_tn: bias_inside needs a bf16 bias");
+      bhp = bias->data_ptr();
+    } else {
+      bf = bias->scalar_type() == torch::kFloat32 ? *bias : bias->to(torch::kFloat32);
+      bp = bf.data_ptr<float>();
+    }
   }
   c10::cuda::CUDAGuard guard(x.device());
-  auto y = torch::empty({M, N}, torch::TensorOptions().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16).device(x.device()));
-  int e = hfl_gemm_bf16_tn(x.data_ptr(), (int)x.stride(0), w.data_ptr(), (int)w.stride(0), y.data_ptr(), (int)N,
-                           out_fp32 ? 0 : 1, bp, (float)alpha, gelu ? 1 : 0, (int)M, (int)N, (int)K, cur_stream());
+  torch::Tensor y;
+  if (out.has_value()) {             // caller-provided destination (may be a row-padded view: ldc = stride(0))
+    y = *out;
+    TORCH_CHECK(y.is_cuda() && y.dim() == 2 && y.size(0) == M && y.size(1) == N && y.stride(1) == 1 &&
+                y.scalar_type() == (out_fp32 ? torch::kFloat32 : torch::kBFloat16));
+  } else {
+    y = torch::empty({M, N}, torch::TensorOptions().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16).device(x.device()));
+  }
+  int e = hfl_gemm_bf16_tn(x.data_ptr(), (int)x.stride(0), w.data_ptr(), (int)w.stride(0), y.data_ptr(), (int)y.stride(0),
+                           out_fp32 ? 0 : 1, bp, bhp, (float)alpha, gelu ? 1 : 0, (int)M, (int)N, (int)K, cur_stream());
   TORCH_CHECK(e == 0, "gemm_bf16_tn failed with code ", e);
   return y;
 }
@@ -326,7 +362,7 @@ torch::Tensor gemm_bf16_general(torch::Tensor a, bool a_mn, torch::Tensor b, boo
   const int64_t M = a_mn ? a.size(1) : a.size(0), K = a_mn ? a.size(0) : a.size(1);
   const int64_t N = b_mn ? b.size(1) : b.size(0), Kb = b_mn ? b.size(0) : b.size(1);
   TORCH_CHECK(K == Kb, "gemm_bf16_general: reduction dims differ");
-  TORCH_CHECK(a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0 && a.size(1) % 8 == 0 && b.size(1) % 8 == 0);
+  TORCH_CHECK(a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0, "gemm_bf16_general: 16-byte row strides");
   TORCH_CHECK((reinterpret_cast<uintptr_t>(a.data_ptr()) & 15) == 0 && (reinterpret_cast<uintptr_t>(b.data_ptr()) & 15) == 0);
   c10::cuda::CUDAGuard guard(a.device());
   auto y = torch::empty({M, N}, torch::TensorOptions().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16).device(a.device()));
@@ -334,6 +370,170 @@ torch::Tensor gemm_bf16_general(torch::Tensor a, bool a_mn, torch::Tensor b, boo
                                 y.data_ptr(), (int)N, out_fp32 ? 0 : 1, (float)alpha, (int)M, (int)N, (int)K, cur_stream());
   TORCH_CHECK(e == 0, "gemm_bf16_general failed with code ", e);
   return y;
+}
+
+
+// ---- fused masked-LM transformer pieces (csrc/lm_kernels.cu) -----------------------------------------------
+static const long long* i64p(const torch::Tensor& t) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kInt64 && t.numel() >= 1);
+  return reinterpret_cast<const long long*>(t.data_ptr<int64_t>());
+}
+static void check_bf(const torch::Tensor& t, const char* what) {
+  TORCH_CHECK(t.is_cuda() && t.is_contiguous() && t.scalar_type() == torch::kBFloat16, what, ": contiguous CUDA bf16 expected");
+}
+static float* f32p(const torch::Tensor& t, int64_t n) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kFloat32 && t.is_contiguous() && t.numel() == n);
+  return t.data_ptr<float>();
+}
+struct DyList {
+  const void* p[4];
+  int n;
+  DyList(const std::vector<torch::Tensor>& dys, int64_t numel) {
+    TORCH_CHECK(!dys.empty() && dys.size() <= 4, "1..4 gradient branches");
+    n = (int)dys.size();
+    for (int i = 0; i < 4; ++i) p[i] = nullptr;
+    for (int i = 0; i < n; ++i) { check_bf(dys[i], "dy"); TORCH_CHECK(dys[i].numel() == numel); p[i] = dys[i].data_ptr(); }
+  }
+};
+
+std::vector<torch::Tensor> lm_embed_fwd(torch::Tensor tok, torch::Tensor emb, torch::Tensor pos, torch::Tensor gamma,
+                                        torch::Tensor beta, int64_t S, int64_t mask_id, double eps, double p_mask,
+                                        double p_drop, torch::Tensor seed, torch::Tensor step, int64_t site) {
+  check_bf(emb, "emb"); check_bf(pos, "pos"); check_bf(gamma, "gamma"); check_bf(beta, "beta");
+  TORCH_CHECK(tok.is_cuda() && tok.scalar_type() == torch::kInt64 && tok.is_contiguous());
+  const int M = tok.numel(), E = emb.size(1);
+  TORCH_CHECK(E <= hfl_lm_max_e() && pos.size(1) == E && pos.size(0) >= S && gamma.numel() == E && mask_id < emb.size(0));
+  c10::cuda::CUDAGuard guard(tok.device());
+  auto ob = emb.options();
+  auto out = torch::empty({M, E}, ob), xhat = torch::empty({M, E}, ob);
+  auto src = torch::empty({M}, ob.dtype(torch::kInt32));
+  auto rstd = torch::empty({M}, ob.dtype(torch::kFloat32));
+  auto dmask = torch::empty({p_drop > 0 ? M : 0, E}, ob.dtype(torch::kUInt8));
+  hfl_lm_embed_fwd(i64p(tok), emb.data_ptr(), pos.data_ptr(), gamma.data_ptr(), beta.data_ptr(), M, (int)S, E,
+                   (int)mask_id, (float)eps, (float)p_mask, (float)p_drop, i64p(seed), i64p(step), (unsigned)site,
+                   out.data_ptr(), src.data_ptr<int>(), xhat.data_ptr(), rstd.data_ptr<float>(),
+                   p_drop > 0 ? dmask.data_ptr<uint8_t>() : nullptr, cur_stream());
+  check_launch();
+  return {out, src, xhat, rstd, dmask};
+}
+
+void lm_embed_bwd(std::vector<torch::Tensor> dys, torch::Tensor dmask, double p_drop, torch::Tensor xhat,
+                  torch::Tensor rstd, torch::Tensor gamma, torch::Tensor src, int64_t S, torch::Tensor demb,
+                  torch::Tensor dpos, torch::Tensor dgamma, torch::Tensor dbeta) {
+  check_bf(xhat, "xhat"); check_bf(gamma, "gamma");
+  const int M = xhat.size(0), E = xhat.size(1);
+  DyList dl(dys, (int64_t)M * E);
+  TORCH_CHECK(E <= hfl_lm_max_e() && demb.size(1) == E && dpos.size(1) == E && dpos.size(0) >= S);
+  TORCH_CHECK(p_drop <= 0 || dmask.numel() == (int64_t)M * E);
+  c10::cuda::CUDAGuard guard(xhat.device());
+  hfl_lm_embed_bwd(dl.p, dl.n, p_drop > 0 ? dmask.data_ptr<uint8_t>() : nullptr, (float)p_drop, xhat.data_ptr(),
+                   rstd.data_ptr<float>(), gamma.data_ptr(), src.data_ptr<int>(), M, (int)S, E,
+                   f32p(demb, demb.numel()), f32p(dpos, dpos.numel()), f32p(dgamma, E), f32p(dbeta, E), cur_stream());
+  check_launch();
+}
+
+std::vector<torch::Tensor> lm_add_ln_fwd(c10::optional<torch::Tensor> x, torch::Tensor h, torch::Tensor gamma,
+                                         torch::Tensor beta, double eps, double p_drop, torch::Tensor seed,
+                                         torch::Tensor step, int64_t site) {
+  check_bf(h, "h"); check_bf(gamma, "gamma"); check_bf(beta, "beta");
+  TORCH_CHECK(h.dim() == 2);
+  const int M = h.size(0), E = h.size(1);
+  TORCH_CHECK(E <= hfl_lm_max_e() && gamma.numel() == E);
+  if (x.has_value()) { check_bf(*x, "x"); TORCH_CHECK(x->sizes() == h.sizes()); }
+  c10::cuda::CUDAGuard guard(h.device());
+  auto y = torch::empty_like(h), xhat = torch::empty_like(h);
+  auto rstd = torch::empty({M}, h.options().dtype(torch::kFloat32));
+  auto dmask = torch::empty({p_drop > 0 ? M : 0, E}, h.options().dtype(torch::kUInt8));
+  hfl_lm_add_ln_fwd(x.has_value() ? x->data_ptr() : nullptr, h.data_ptr(), gamma.data_ptr(), beta.data_ptr(), M, E,
+                    (float)eps, (float)p_drop, i64p(seed), i64p(step), (unsigned)site, y.data_ptr(), xhat.data_ptr(),
+                    rstd.data_ptr<float>(), p_drop > 0 ? dmask.data_ptr<uint8_t>() : nullptr, cur_stream());
+  check_launch();
+  return {y, xhat, rstd, dmask};
+}
+
+// returns (dz, dh); dh aliases dz when there is no dropout
+std::vector<torch::Tensor> lm_add_ln_bwd(std::vector<torch::Tensor> dys, torch::Tensor xhat, torch::Tensor rstd,
+                                         torch::Tensor gamma, torch::Tensor dmask, double p_drop, torch::Tensor dgamma,
+                                         torch::Tensor dbeta, c10::optional<torch::Tensor> dbias, double bias_alpha) {
+  check_bf(xhat, "xhat"); check_bf(gamma, "gamma");
+  const int M = xhat.size(0), E = xhat.size(1);
+  DyList dl(dys, (int64_t)M * E);
+  TORCH_CHECK(E <= hfl_lm_max_e());
+  TORCH_CHECK(p_drop <= 0 || dmask.numel() == (int64_t)M * E);
+  c10::cuda::CUDAGuard guard(xhat.device());
+  auto dz = torch::empty_like(xhat);
+  auto dh = p_drop > 0 ? torch::empty_like(xhat) : dz;
+  hfl_lm_add_ln_bwd(dl.p, dl.n, xhat.data_ptr(), rstd.data_ptr<float>(), gamma.data_ptr(),
+                    p_drop > 0 ? dmask.data_ptr<uint8_t>() : nullptr, (float)p_drop, M, E, dz.data_ptr(),
+                    p_drop > 0 ? dh.data_ptr() : nullptr, f32p(dgamma, E), f32p(dbeta, E),
+                    dbias.has_value() ? f32p(*dbias, E) : nullptr, (float)bias_alpha, cur_stream());
+  check_launch();
+  return {dz, dh};
+}
+
+std::vector<torch::Tensor> lm_gelu_drop_fwd(torch::Tensor u, double p_drop, torch::Tensor seed, torch::Tensor step,
+                                            int64_t site) {
+  check_bf(u, "u");
+  c10::cuda::CUDAGuard guard(u.device());
+  auto h = torch::empty_like(u);
+  auto dmask = torch::empty({p_drop > 0 ? u.numel() : 0}, u.options().dtype(torch::kUInt8));
+  hfl_lm_gelu_drop_fwd(u.data_ptr(), (long)u.numel(), (float)p_drop, i64p(seed), i64p(step), (unsigned)site,
+                       h.data_ptr(), p_drop > 0 ? dmask.data_ptr<uint8_t>() : nullptr, cur_stream());
+  check_launch();
+  return {h, dmask};
+}
+
+torch::Tensor lm_gelu_drop_bwd(torch::Tensor dh, torch::Tensor u, torch::Tensor dmask, double p_drop,
+                               c10::optional<torch::Tensor> dbias, double bias_alpha) {
+  check_bf(dh, "dh"); check_bf(u, "u");
+  TORCH_CHECK(u.dim() == 2 && dh.numel() == u.numel());
+  const int M = u.size(0), F = u.size(1);
+  TORCH_CHECK(p_drop <= 0 || dmask.numel() == u.numel());
+  c10::cuda::CUDAGuard guard(u.device());
+  auto du = torch::empty_like(u);
+  hfl_lm_gelu_drop_bwd(dh.data_ptr(), u.data_ptr(), p_drop > 0 ? dmask.data_ptr<uint8_t>() : nullptr, (float)p_drop, M, F,
+                       du.data_ptr(), dbias.has_value() ? f32p(*dbias, F) : nullptr, (float)bias_alpha, cur_stream());
+  check_launch();
+  return du;
+}
+
+void lm_colsum(torch::Tensor x, double alpha, torch::Tensor out) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == torch::kBFloat16 && x.dim() == 2 && x.stride(1) == 1);
+  c10::cuda::CUDAGuard guard(x.device());
+  hfl_lm_colsum(x.data_ptr(), (int)x.size(0), (int)x.size(1), (int)x.stride(0), (float)alpha, f32p(out, x.size(1)),
+                cur_stream());
+  check_launch();
+}
+
+std::vector<torch::Tensor> lm_attn_fwd(torch::Tensor q, torch::Tensor k, torch::Tensor v, int64_t N, int64_t S,
+                                       int64_t H, double scale) {
+  check_bf(q, "q"); check_bf(k, "k"); check_bf(v, "v");
+  TORCH_CHECK(q.dim() == 2 && q.size(0) == N * S && q.size(1) % H == 0 && k.sizes() == q.sizes() && v.sizes() == q.sizes());
+  const int dh = q.size(1) / H;
+  TORCH_CHECK(S <= hfl_lm_max_s() && dh <= hfl_lm_max_dh(), "lm_attn: S <= 64 and head dim <= 32 only");
+  c10::cuda::CUDAGuard guard(q.device());
+  auto o = torch::empty_like(q);
+  auto P = torch::empty({N, H, S, S}, q.options());
+  hfl_lm_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), (int)N, (int)S, (int)H, dh, (float)scale, o.data_ptr(),
+                  P.data_ptr(), cur_stream());
+  check_launch();
+  return {o, P};
+}
+
+std::vector<torch::Tensor> lm_attn_bwd(torch::Tensor dO, torch::Tensor q, torch::Tensor k, torch::Tensor v,
+                                       torch::Tensor P, int64_t N, int64_t S, int64_t H, double scale, torch::Tensor dbq,
+                                       torch::Tensor dbk, torch::Tensor dbv, double alpha_v) {
+  check_bf(dO, "dO"); check_bf(q, "q"); check_bf(k, "k"); check_bf(v, "v"); check_bf(P, "P");
+  const int E = q.size(1), dh = E / H;
+  TORCH_CHECK(q.size(0) == N * S && dO.sizes() == q.sizes() && P.numel() == N * H * S * S);
+  TORCH_CHECK(S <= hfl_lm_max_s() && dh <= hfl_lm_max_dh());
+  c10::cuda::CUDAGuard guard(q.device());
+  auto dq = torch::empty_like(q), dk = torch::empty_like(q), dv = torch::empty_like(q);
+  int e = hfl_lm_attn_bwd(dO.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), P.data_ptr(), (int)N, (int)S, (int)H,
+                          dh, (float)scale, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), f32p(dbq, E), f32p(dbk, E),
+                          f32p(dbv, E), (float)alpha_v, cur_stream());
+  TORCH_CHECK(e == 0, "lm_attn_bwd failed with code ", e);
+  return {dq, dk, dv};
 }
 
 // ---- tcgen05 implicit-GEMM convolution (forward) ---------------------------------------------------------
@@ -469,8 +669,20 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ms_chunk", &hfl_ms_chunk);
   m.def("head_fwd_bwd", &head_fwd_bwd);
   m.def("head_smem_bytes", &hfl_head_smem_bytes);
-  m.def("gemm_bf16_tn", &gemm_bf16_tn);
+  m.def("gemm_bf16_tn", &gemm_bf16_tn, py::arg("x"), py::arg("w"), py::arg("bias"), py::arg("alpha"), py::arg("gelu"),
+        py::arg("out_fp32"), py::arg("bias_inside") = false, py::arg("out") = py::none());
   m.def("gemm_bf16_general", &gemm_bf16_general);
+  m.def("gemm_timing", []() { std::vector<long long> v(16); hfl_gemm_timing(v.data()); return v; });
+  m.def("lm_embed_fwd", &lm_embed_fwd);
+  m.def("lm_embed_bwd", &lm_embed_bwd);
+  m.def("lm_add_ln_fwd", &lm_add_ln_fwd);
+  m.def("lm_add_ln_bwd", &lm_add_ln_bwd);
+  m.def("lm_gelu_drop_fwd", &lm_gelu_drop_fwd);
+  m.def("lm_gelu_drop_bwd", &lm_gelu_drop_bwd);
+  m.def("lm_colsum", &lm_colsum);
+  m.def("lm_attn_fwd", &lm_attn_fwd);
+  m.def("lm_attn_bwd", &lm_attn_bwd);
+  m.def("lm_max_e", &hfl_lm_max_e);
   m.def("conv_tc_supported", &conv_tc_supported);
   m.def("conv_fprop_tc", &conv_fprop_tc);
   m.def("conv_dgrad_tc", &conv_dgrad_tc);

@@ -30,14 +30,95 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = GEMM_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TOTAL = GEMM_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BLOCK_N * 4 /*bias tile*/;
 };
 
-template <int BLOCK_N, bool OUT_BF16>
+
+// ---------------------------------------------------------------------------------------------------------
+// Epilogue of one 128 x BLOCK_N fp32 accumulator tile held in TMEM.  Warp q (0..3) owns TMEM lanes [32q, 32q+32),
+// i.e. one accumulator ROW per thread.  Writing C straight from that mapping makes every store instruction touch
+// 32 different rows (32 L1 wavefronts per instruction) -- measured 14 000 cycles per tile, as long as the whole
+// 64-k-block mainloop.  Instead each warp transposes through shared memory (the drained pipeline stages; row pitch
+// +16 B so the 16-byte staging writes are conflict-free) and writes whole row segments with 16-byte stores.
+// `xf(acc, tile_col)` applies alpha / bias / activation.
+// ---------------------------------------------------------------------------------------------------------
+template <int BLOCK_N, bool OUT_BF16, typename XF>
+__device__ __forceinline__ void epilogue_store_tile(uint32_t tmem_base, uint8_t* smem_stage, int q, int lane, void* C,
+                                                    int ldc, int row0, int col0, int M, int N, XF xf) {
+  constexpr int ELT = OUT_BF16 ? 2 : 4;
+  constexpr int ROW_BYTES = BLOCK_N * ELT;
+  constexpr int PITCH = ROW_BYTES + 16;
+  constexpr int LPR = ROW_BYTES / 16;            // lanes per output row in the write-out
+  static_assert(LPR >= 1 && LPR <= 32, "tile row must be 16..512 bytes");
+  constexpr int RPI = 32 / LPR;                  // rows per store instruction
+  uint8_t* my = smem_stage + (size_t)q * 32 * PITCH;
+  uint8_t* myrow = my + lane * PITCH;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = xf(__uint_as_float(v[j]), c0 + j);
+    if (OUT_BF16) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 u;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+        h[0] = __floats2bfloat162_rn(f[j], f[j + 1]);
+        h[1] = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+        h[2] = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+        h[3] = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+        *reinterpret_cast<uint4*>(myrow + (c0 + j) * 2) = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(myrow + (c0 + j) * 4) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    }
+  }
+  __syncwarp();
+  const int rsub = lane / LPR, cb = (lane % LPR) * 16;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (((size_t)ldc * ELT) % 16 == 0);
+  const int gcol = col0 + cb / ELT;
+#pragma unroll 4
+  for (int r0 = 0; r0 < 32; r0 += RPI) {
+    const int r = r0 + rsub;
+    const int grow = row0 + q * 32 + r;
+    if (grow < M && gcol < N) {
+      const uint8_t* src = my + r * PITCH + cb;
+      uint8_t* dst = reinterpret_cast<uint8_t*>(C) + ((size_t)grow * ldc + gcol) * ELT;
+      if (vec_ok && gcol + 16 / ELT <= N) {
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+      } else {
+        for (int e = 0; e < 16 / ELT && gcol + e < N; ++e) {
+          if (OUT_BF16) reinterpret_cast<uint16_t*>(dst)[e] = reinterpret_cast<const uint16_t*>(src)[e];
+          else reinterpret_cast<uint32_t*>(dst)[e] = reinterpret_cast<const uint32_t*>(src)[e];
+        }
+      }
+    }
+  }
+}
+
+#ifdef HFL_GEMM_TIMING
+// phase timestamps of CTA (0,0) (clock64), read back with hfl_gemm_timing(): 0 start, 1 after setup sync, 2 first TMA
+// issued, 3 last TMA issued, 4 first full barrier seen, 5 last MMA committed, 6 accumulator ready (epilogue start),
+// 7 epilogue end, 8 before dealloc
+__device__ long long g_gemm_t[16];
+#define GEMM_T(i) do { if (blockIdx.x == 0 && blockIdx.y == 0) g_gemm_t[i] = clock64(); } while (0)
+#else
+#define GEMM_T(i) do { } while (0)
+#endif
+
+// BIAS: 0 none, 1 fp32 bias added after alpha, 2 bf16 bias added before alpha.  The epilogue variants are compile-time:
+// the four epilogue warps run one per scheduler with nothing to hide latency behind, so a runtime `gelu` flag (which
+// the compiler if-converts into predicated erff code for every element) cost 10 000 cycles per tile.
+template <int BLOCK_N, bool OUT_BF16, int BIAS, bool GELU>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    void* __restrict__ C, const float* __restrict__ bias, float alpha, int gelu, int M, int N, int K,
-                    int ldc) {
+                    void* __restrict__ C, const float* __restrict__ bias, const __nv_bfloat16* __restrict__ bias_h,
+                    float alpha, int M, int N, int K, int ldc) {
   extern __shared__ uint8_t smem_raw[];
   using S = GemmSmem<BLOCK_N>;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -50,6 +131,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int m_blk = blockIdx.x, n_blk = blockIdx.y;
   const int num_k = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  if (threadIdx.x == 0) GEMM_T(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -65,6 +147,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) GEMM_T(1);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -78,7 +161,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
         tma_load_2d(sa, &tmap_a, &full_bar[s], kb * GEMM_BLOCK_K, m_blk * GEMM_BLOCK_M);
         tma_load_2d(sb, &tmap_b, &full_bar[s], kb * GEMM_BLOCK_K, n_blk * BLOCK_N);
+        if (kb == 0) GEMM_T(2);
       }
+      GEMM_T(3);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -88,6 +173,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t ph = (kb / GEMM_STAGES) & 1;
       mbar_wait(&full_bar[s], ph);
       tcgen05_fence_after();
+      if (lane == 0 && kb == 0) GEMM_T(4);
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
         const uint32_t b_addr = a_addr + S::A_BYTES;
@@ -100,63 +186,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         umma_commit(&empty_bar[s]);                       // frees the smem stage once these MMAs retire
         if (kb == num_k - 1) umma_commit(tmem_full_bar);  // accumulator complete -> epilogue
+        if (kb == num_k - 1) GEMM_T(5);
       }
       __syncwarp();
     }
   } else if (warp >= 4) {
     // ===== epilogue =====
     const int q = warp - 4;                                // TMEM lane quadrant
+    float* sbias = reinterpret_cast<float*>(smem + GEMM_STAGES * S::STAGE_BYTES + 256);
+    if (BIAS != 0) {
+      // the tile's bias row goes to shared memory while the mainloop runs: in the element loop every thread (= one
+      // accumulator row) needs all BLOCK_N values, which from global memory was a chain of dependent loads
+      for (int t = threadIdx.x - 128; t < BLOCK_N; t += 128) {
+        const int col = n_blk * BLOCK_N + t;
+        sbias[t] = col < N ? (BIAS == 1 ? bias[col] : __bfloat162float(bias_h[col])) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // epilogue warps only
+    }
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
-    const int row = m_blk * GEMM_BLOCK_M + q * 32 + lane;
-    const bool row_ok = row < M;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + c0, v);
-      tmem_ld_wait();
-      const int col0 = n_blk * BLOCK_N + c0;
-      if (row_ok) {
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]) * alpha;
-          if (bias != nullptr && col0 + j < N) x += bias[col0 + j];
-          if (gelu) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
-          f[j] = x;
-        }
-        if (OUT_BF16) {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(C) + (size_t)row * ldc + col0;
-          if (col0 + 32 <= N && (((uintptr_t)dst) & 15) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-              h[0] = __floats2bfloat162_rn(f[j], f[j + 1]);
-              h[1] = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-              h[2] = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-              h[3] = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(dst + j) = u;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) dst[j] = __float2bfloat16(f[j]);
-          }
-        } else {
-          float* dst = reinterpret_cast<float*>(C) + (size_t)row * ldc + col0;
-          if (col0 + 32 <= N && (((uintptr_t)dst) & 15) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) dst[j] = f[j];
-          }
-        }
-      }
-    }
+    if (threadIdx.x == 128) GEMM_T(6);
+    auto xf = [&](float acc, int jc) -> float {              // jc = column inside the tile
+      float x = acc;
+      if (BIAS == 2) x += sbias[jc];                          // alpha * (acc + b)
+      x *= alpha;
+      if (BIAS == 1) x += sbias[jc];                          // alpha * acc + b
+      if (GELU) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+      return x;
+    };
+    epilogue_store_tile<BLOCK_N, OUT_BF16>(tmem_base, smem, q, lane, C, ldc, m_blk * GEMM_BLOCK_M, n_blk * BLOCK_N, M, N,
+                                           xf);
     tcgen05_fence_before();
+    if (threadIdx.x == 128) GEMM_T(7);
   }
   __syncthreads();
+  if (threadIdx.x == 0) GEMM_T(8);
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -247,23 +311,9 @@ gemm_tcgen05_general_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     const int q = warp - 4;
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
-    const int row = m_blk * GEMM_BLOCK_M + q * 32 + lane;
-    const bool row_ok = row < M;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + c0, v);
-      tmem_ld_wait();
-      const int col0 = n_blk * BLOCK_N + c0;
-      if (row_ok) {
-        for (int j = 0; j < 32; ++j) {
-          if (col0 + j >= N) break;
-          const float x = __uint_as_float(v[j]) * alpha;
-          if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(C)[(size_t)row * ldc + col0 + j] = __float2bfloat16(x);
-          else reinterpret_cast<float*>(C)[(size_t)row * ldc + col0 + j] = x;
-        }
-      }
-    }
+    auto xf = [&](float acc, int) -> float { return acc * alpha; };
+    epilogue_store_tile<BLOCK_N, OUT_BF16>(tmem_base, smem, q, lane, C, ldc, m_blk * GEMM_BLOCK_M, n_blk * BLOCK_N, M, N,
+                                           xf);
     tcgen05_fence_before();
   }
   __syncthreads();
@@ -318,10 +368,10 @@ extern "C" int hfl_gemm_bf16_general(const void* A, int lda, int a_mn, const voi
   return -1;
 }
 
-template <int BLOCK_N, bool OUT_BF16>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const float* bias, float alpha, int gelu,
-                       int M, int N, int K, int ldc, cudaStream_t stream) {
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, OUT_BF16>;
+template <int BLOCK_N, bool OUT_BF16, int BIAS, bool GELU>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const float* bias,
+                       const __nv_bfloat16* bias_h, float alpha, int M, int N, int K, int ldc, cudaStream_t stream) {
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, OUT_BF16, BIAS, GELU>;
   constexpr int smem = GemmSmem<BLOCK_N>::TOTAL;
   static bool configured = false;
   if (!configured) {
@@ -330,14 +380,17 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* C, co
     configured = true;
   }
   dim3 grid((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M, (N + BLOCK_N - 1) / BLOCK_N);
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, C, bias, alpha, gelu, M, N, K, ldc);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, C, bias, bias_h, alpha, M, N, K, ldc);
   count_launch();
   return (int)cudaGetLastError();
 }
 
 // A: [M, K] bf16 row-major (lda elements), B: [N, K] bf16 row-major (ldb elements).  Returns a cudaError / CUresult code.
+// bias (fp32) is added after alpha; bias_h (bf16, e.g. straight from a parameter arena) is added before it.
 extern "C" int hfl_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int out_bf16,
-                                const float* bias, float alpha, int gelu, int M, int N, int K, cudaStream_t stream) {
+                                const float* bias, const void* bias_h_, float alpha, int gelu, int M, int N, int K,
+                                cudaStream_t stream) {
+  const __nv_bfloat16* bias_h = reinterpret_cast<const __nv_bfloat16*>(bias_h_);
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   const int block_n = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
   CUtensorMap ta, tb;
@@ -345,13 +398,28 @@ extern "C" int hfl_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, 
   if (r) return 1000 + r;
   r = make_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, GEMM_BLOCK_K, block_n);
   if (r) return 1000 + r;
+  const int bias_mode = bias_h != nullptr ? 2 : (bias != nullptr ? 1 : 0);
+#define HFL_GEMM_EPI(BN, OB, BI, GE)                                                                          \
+  if (bias_mode == BI && (gelu != 0) == GE)                                                                   \
+    return launch_gemm<BN, OB, BI, GE>(ta, tb, C, bias, bias_h, alpha, M, N, K, ldc, stream);
+#define HFL_GEMM_OUT(BN, OB)                                                                                  \
+  HFL_GEMM_EPI(BN, OB, 0, false) HFL_GEMM_EPI(BN, OB, 1, false) HFL_GEMM_EPI(BN, OB, 2, false)                \
+  HFL_GEMM_EPI(BN, OB, 0, true) HFL_GEMM_EPI(BN, OB, 1, true) HFL_GEMM_EPI(BN, OB, 2, true)
 #define HFL_GEMM_CASE(BN)                                                                                     \
-  if (block_n == BN)                                                                                          \
-    return out_bf16 ? launch_gemm<BN, true>(ta, tb, C, bias, alpha, gelu, M, N, K, ldc, stream)                \
-                    : launch_gemm<BN, false>(ta, tb, C, bias, alpha, gelu, M, N, K, ldc, stream);
+  if (block_n == BN) {                                                                                        \
+    if (out_bf16) { HFL_GEMM_OUT(BN, true) } else { HFL_GEMM_OUT(BN, false) }                                 \
+  }
   HFL_GEMM_CASE(32)
   HFL_GEMM_CASE(64)
   HFL_GEMM_CASE(128)
+#undef HFL_GEMM_EPI
+#undef HFL_GEMM_OUT
 #undef HFL_GEMM_CASE
   return -1;
 }
+
+#ifdef HFL_GEMM_TIMING
+extern "C" void hfl_gemm_timing(long long* out16) { cudaMemcpyFromSymbol(out16, hfl::g_gemm_t, sizeof(long long) * 16); }
+#else
+extern "C" void hfl_gemm_timing(long long* out16) { for (int i = 0; i < 16; ++i) out16[i] = 0; }
+#endif

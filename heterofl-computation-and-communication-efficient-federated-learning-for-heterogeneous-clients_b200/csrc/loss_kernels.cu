@@ -18,12 +18,13 @@ template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p,
 
 template <typename T>
 __global__ void ce_rows_kernel(const T* __restrict__ logits, const long long* __restrict__ target,
-                               const unsigned char* __restrict__ mask, int rows, int V, T* __restrict__ dlogits,
-                               float* __restrict__ row_loss, float* __restrict__ row_correct) {
+                               const unsigned char* __restrict__ mask, int rows, int V, int ld,
+                               T* __restrict__ dlogits, float* __restrict__ row_loss,
+                               float* __restrict__ row_correct) {
   __shared__ float sm[33];
   __shared__ int s_arg;
   const int r = blockIdx.x;
-  const T* z = logits + (size_t)r * V;
+  const T* z = logits + (size_t)r * ld;          // ld >= V: row stride (padded vocabularies)
   const int tgt = (int)target[r];
   // pass 1: max and argmax of the masked logits
   float mx = -INFINITY;
@@ -52,7 +53,7 @@ __global__ void ce_rows_kernel(const T* __restrict__ logits, const long long* __
   // pass 3: gradient of the MEAN loss
   if (dlogits != nullptr) {
     const float inv_rows = 1.f / (float)rows;
-    T* dz = dlogits + (size_t)r * V;
+    T* dz = dlogits + (size_t)r * ld;
     for (int j = threadIdx.x; j < V; j += blockDim.x) {
       const bool on = (mask == nullptr || mask[j]);
       float gsm = 0.f;
@@ -86,15 +87,15 @@ __global__ void ce_finalize_kernel(const float* __restrict__ row_loss, const flo
 using namespace hfl;
 
 extern "C" void hfl_masked_ce(const void* logits, int is_bf16, const long long* target, const unsigned char* mask,
-                              int rows, int V, void* dlogits, float* row_loss, float* row_correct, float n_weight,
+                              int rows, int V, int ld, void* dlogits, float* row_loss, float* row_correct, float n_weight,
                               float* loss_out, double* meter, cudaStream_t stream) {
   const int threads = V <= 64 ? 32 : (V <= 1024 ? 128 : 512);
   if (is_bf16)
-    ce_rows_kernel<__nv_bfloat16><<<rows, threads, 0, stream>>>((const __nv_bfloat16*)logits, target, mask, rows, V,
+    ce_rows_kernel<__nv_bfloat16><<<rows, threads, 0, stream>>>((const __nv_bfloat16*)logits, target, mask, rows, V, ld,
                                                                 (__nv_bfloat16*)dlogits, row_loss, row_correct);
   else
-    ce_rows_kernel<float><<<rows, threads, 0, stream>>>((const float*)logits, target, mask, rows, V, (float*)dlogits,
-                                                        row_loss, row_correct);
+    ce_rows_kernel<float><<<rows, threads, 0, stream>>>((const float*)logits, target, mask, rows, V, ld,
+                                                        (float*)dlogits, row_loss, row_correct);
   ce_finalize_kernel<<<1, 256, 0, stream>>>(row_loss, row_correct, rows, n_weight, loss_out, meter);
   count_launch(2);
 }

@@ -468,7 +468,7 @@ class Engine:
                     s.load_params(a)
             for i, s in zip(batch_pos, slots):
                 u = user_idx[i]
-                s.begin_client(lr, fed.user_label_mask(u))
+                s.begin_client(lr, fed.user_label_mask(u), rng_seed=(self.seed * 1000003 + epoch * 7919) * 4099 + int(u))
                 g = self._client_generator(s, u, epochs, epoch)
                 if self.is_cuda:
                     s.stream.wait_stream(main)

@@ -26,6 +26,7 @@ import torch
 from ..data.pipeline import VisionAugment, lm_windows
 from ..models import Model
 from ..models.fused_resnet import FusedResNet
+from ..models.fused_transformer import EMB, FusedTransformer
 from ..ops import cuda as cu
 from ..ops.nn import NormCtx
 from ..utils.metrics import DeviceMeter
@@ -78,9 +79,15 @@ class TrainSlot:
         self.use_mask = bool(cfg["mask"])
         # manual-backward fused path (bf16 + kernels): no autograd graph, no gradient arena traffic
         self.fused = None
-        if self.use_kernels and self.mixed and compute_dtype == torch.bfloat16 and cfg.get("fused", True) \
-                and FusedResNet.eligible(model.spec):
-            self.fused = FusedResNet(model.spec, model.scale_rate)
+        self.rng_seed = torch.zeros(1, dtype=torch.int64, device=device)     # dropout / [MASK] draws of the fused LM
+        self._clients = 0
+        if self.use_kernels and self.mixed and compute_dtype == torch.bfloat16 and cfg.get("fused", True):
+            if FusedResNet.eligible(model.spec):
+                self.fused = FusedResNet(model.spec, model.scale_rate)
+            elif model.is_lm and FusedTransformer.eligible(model.spec, model.layout.entries[EMB].shape[1]):
+                self.fused = FusedTransformer(model.spec, model.scale_rate, cfg.get("mask_rate", 0.15),
+                                              cfg["transformer"]["dropout"])
+        if self.fused is not None:
             self.Pv = model.layout.views(self.wc)
             self._names = list(model.layout.entries.keys())
             chunk = cu.C().ms_chunk()
@@ -99,8 +106,10 @@ class TrainSlot:
         self.lr = 0.0
 
     # -- per-client setup ----------------------------------------------------------------------------------
-    def begin_client(self, lr: float, label_mask: torch.Tensor) -> None:
+    def begin_client(self, lr: float, label_mask: torch.Tensor, rng_seed: Optional[int] = None) -> None:
         """Parameters are expected in ``w`` (+``wc``) already (distribute kernel); reset optimiser state + meter."""
+        self._clients += 1
+        self.rng_seed.fill_(int(rng_seed) if rng_seed is not None else self._clients * 104729 + 12345)
         self.lr = float(lr)
         self.lr_t.fill_(float(lr))
         self.mask_t.copy_(label_mask.to(self.mask_t.device), non_blocking=True)
@@ -159,6 +168,10 @@ class TrainSlot:
 
     def _fwd_bwd(self, inp: Dict, n_weight: float) -> None:
         mask = self.mask_t if self.use_mask else None
+        if self.fused is not None and self.model.is_lm:
+            _, self._grads = self.fused.train_step(self.Pv, inp["label"], mask, (self.meter.buf, n_weight),
+                                                   self.rng_seed, self.step_ctr)
+            return
         if self.fused is not None:
             _, self._grads = self.fused.train_step(self.Pv, inp["img"], inp["label"], mask, (self.meter.buf, n_weight))
             return
@@ -257,14 +270,16 @@ class TrainSlot:
                     cap["row"].add_(1)
                 self._capture(key, step)
         for ep in range(epochs):
-            if self.use_graph:
-                self.step_ctr.zero_()
+            self.step_ctr.zero_()
+            if ep:
+                self.rng_seed.add_(7919)          # (seed, step) keys the in-kernel dropout / [MASK] draws
             for (s, l) in wins:
                 if self.use_graph and l == bptt:
                     self._replay(("lm", r, bptt))
                 else:
                     self._fwd_bwd({"label": rows[:, s:s + l].contiguous()}, float(r))
                     self._opt_step()
+                    self.step_ctr.add_(1)
                 yield
 
     # -- CUDA graph plumbing -------------------------------------------------------------------------------

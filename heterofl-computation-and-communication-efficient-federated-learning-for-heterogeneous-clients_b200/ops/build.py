@@ -23,7 +23,7 @@ EXT_NAME = "_hfl_C"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
-              "-Xptxas", "-v"] + ARCH_FLAGS
+              "-Xptxas", "-v"] + ARCH_FLAGS + os.environ.get("HFL_NVCC_EXTRA", "").split()
 
 
 def _sources():
