@@ -51,16 +51,17 @@ void hfl_lm_gelu_drop_bwd(const void*, const void*, const unsigned char*, float,
                           cudaStream_t);
 void hfl_lm_colsum(const void*, int, int, int, float, float*, cudaStream_t);
 void hfl_lm_attn_fwd(const void*, const void*, const void*, int, int, int, int, float, void*, void*, cudaStream_t);
-int hfl_lm_attn_bwd(const void*, const void*, const void*, const void*, const void*, int, int, int, int, float, void*,
-                    void*, void*, float*, float*, float*, float, cudaStream_t);
+int hfl_lm_attn_bwd(const void*, const void*, const void*, const void*, const void*, const void*, int, int, int, int,
+                    float, void*, void*, void*, float*, float*, float*, float, cudaStream_t);
 int hfl_head_smem_bytes(int, int, int);
 int hfl_head_fwd_bwd(const void*, int, int, int, const void*, const void*, int, int, const long long*,
                      const unsigned char*, float, float*, double*, void*, void*, void*, float*, cudaStream_t);
 int hfl_conv_tc_supported(int, int, int, int, int, int, int, int);
 int hfl_conv_fprop_tc(const void*, const void*, void*, const void*, float*, int, int, int, int, int, int, int, int,
                       cudaStream_t);
-int hfl_gemm_bf16_general(const void*, int, int, const void*, int, int, void*, int, int, float, int, int, int,
+int hfl_gemm_bf16_general(const void*, int, int, const void*, int, int, void*, int, int, float, int, int, int, int,
                           cudaStream_t);
+int hfl_gemm_general_splits(int, int, int);
 int hfl_conv_dgrad_tc(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, cudaStream_t);
 int hfl_conv_wgrad_tc_supported(int, int, int, int, int, int, int, int);
 int hfl_conv_wgrad_tc(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
@@ -365,10 +366,16 @@ torch::Tensor gemm_bf16_general(torch::Tensor a, bool a_mn, torch::Tensor b, boo
   TORCH_CHECK(a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0, "gemm_bf16_general: 16-byte row strides");
   TORCH_CHECK((reinterpret_cast<uintptr_t>(a.data_ptr()) & 15) == 0 && (reinterpret_cast<uintptr_t>(b.data_ptr()) & 15) == 0);
   c10::cuda::CUDAGuard guard(a.device());
-  auto y = torch::empty({M, N}, torch::TensorOptions().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16).device(a.device()));
+  // skinny output + long reduction: split-K into a zero-filled fp32 buffer (atomics), cast afterwards if bf16 is wanted
+  const int splits = hfl_gemm_general_splits((int)M, (int)N, (int)K);
+  const bool direct = splits == 1;
+  auto y = direct ? torch::empty({M, N}, torch::TensorOptions().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16).device(a.device()))
+                  : torch::zeros({M, N}, torch::TensorOptions().dtype(torch::kFloat32).device(a.device()));
   int e = hfl_gemm_bf16_general(a.data_ptr(), (int)a.stride(0), a_mn ? 1 : 0, b.data_ptr(), (int)b.stride(0), b_mn ? 1 : 0,
-                                y.data_ptr(), (int)N, out_fp32 ? 0 : 1, (float)alpha, (int)M, (int)N, (int)K, cur_stream());
+                                y.data_ptr(), (int)N, (direct && !out_fp32) ? 1 : 0, (float)alpha, (int)M, (int)N, (int)K,
+                                splits, cur_stream());
   TORCH_CHECK(e == 0, "gemm_bf16_general failed with code ", e);
+  if (!direct && !out_fp32) return y.to(torch::kBFloat16);
   return y;
 }
 
@@ -521,16 +528,17 @@ std::vector<torch::Tensor> lm_attn_fwd(torch::Tensor q, torch::Tensor k, torch::
 }
 
 std::vector<torch::Tensor> lm_attn_bwd(torch::Tensor dO, torch::Tensor q, torch::Tensor k, torch::Tensor v,
-                                       torch::Tensor P, int64_t N, int64_t S, int64_t H, double scale, torch::Tensor dbq,
-                                       torch::Tensor dbk, torch::Tensor dbv, double alpha_v) {
-  check_bf(dO, "dO"); check_bf(q, "q"); check_bf(k, "k"); check_bf(v, "v"); check_bf(P, "P");
+                                       torch::Tensor O, torch::Tensor P, int64_t N, int64_t S, int64_t H, double scale,
+                                       torch::Tensor dbq, torch::Tensor dbk, torch::Tensor dbv, double alpha_v) {
+  check_bf(dO, "dO"); check_bf(q, "q"); check_bf(k, "k"); check_bf(v, "v"); check_bf(O, "O"); check_bf(P, "P");
+  TORCH_CHECK(O.sizes() == q.sizes());
   const int E = q.size(1), dh = E / H;
   TORCH_CHECK(q.size(0) == N * S && dO.sizes() == q.sizes() && P.numel() == N * H * S * S);
   TORCH_CHECK(S <= hfl_lm_max_s() && dh <= hfl_lm_max_dh());
   c10::cuda::CUDAGuard guard(q.device());
   auto dq = torch::empty_like(q), dk = torch::empty_like(q), dv = torch::empty_like(q);
-  int e = hfl_lm_attn_bwd(dO.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), P.data_ptr(), (int)N, (int)S, (int)H,
-                          dh, (float)scale, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), f32p(dbq, E), f32p(dbk, E),
+  int e = hfl_lm_attn_bwd(dO.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), O.data_ptr(), P.data_ptr(), (int)N,
+                          (int)S, (int)H, dh, (float)scale, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), f32p(dbq, E), f32p(dbk, E),
                           f32p(dbv, E), (float)alpha_v, cur_stream());
   TORCH_CHECK(e == 0, "lm_attn_bwd failed with code ", e);
   return {dq, dk, dv};

@@ -47,7 +47,10 @@ struct ConvSmem {
 // "x" is then dY (reduction over its K_out channels, geometry fields C/Kout are swapped by the host), the filter taps
 // are visited with mirrored halo offsets, and the B operand -- Wt[k, tap, c-range] with c contiguous -- is consumed
 // MN-major straight from the K,R,S,C filter matrix (no transposed / flipped weight copy).
-template <int BLOCK_N, bool DGRAD>
+// HAS_RES / HAS_STATS are compile-time: the four epilogue warps run one per scheduler with nothing to hide latency
+// behind, so code for an absent residual / statistics pass must not even be issued (predicated-off instructions of a
+// runtime flag cost issue slots; the same lesson as the GEMM epilogue, csrc/gemm_tcgen05.cu).
+template <int BLOCK_N, bool DGRAD, bool HAS_RES, bool HAS_STATS>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                           __nv_bfloat16* __restrict__ Y, const __nv_bfloat16* __restrict__ residual,
@@ -135,6 +138,9 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     const int q = warp - 4;
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
+    // One accumulator row (= one output pixel, K_out contiguous bf16) per thread: 64-byte runs per thread and chunk.
+    // (A shared-memory transposed write-out like the GEMM's was measured 5-10 % SLOWER here -- the fp32 staging traffic
+    // costs more than the row-strided 16-byte stores -- so the direct form stays; profiles/conv_bench.md.)
     const int m = q * 32 + lane;                          // pixel within the brick: ((n_l*bh + h_l)*bw + w_l)
     const int w_l = m % g.bw;
     const int t = m / g.bw;
@@ -153,7 +159,7 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
       for (int j = 0; j < 32; ++j) f[j] = ok ? __uint_as_float(v[j]) : 0.f;
       if (ok) {
         __nv_bfloat16* dst = Y + pix * g.Kout + col0;
-        if (residual != nullptr) {
+        if (HAS_RES) {
           const uint4* rp = reinterpret_cast<const uint4*>(residual + pix * g.Kout + col0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -172,13 +178,13 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
           h[2] = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
           h[3] = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
           *reinterpret_cast<uint4*>(dst + j) = u;
-          if (stats != nullptr) {   // statistics of the bf16-rounded outputs (what a separate BN kernel would read)
+          if (HAS_STATS) {   // statistics of the bf16-rounded outputs (what a separate BN kernel would read)
             f[j] = __low2float(h[0]); f[j + 1] = __high2float(h[0]); f[j + 2] = __low2float(h[1]); f[j + 3] = __high2float(h[1]);
             f[j + 4] = __low2float(h[2]); f[j + 5] = __high2float(h[2]); f[j + 6] = __low2float(h[3]); f[j + 7] = __high2float(h[3]);
           }
         }
       }
-      if (stats != nullptr) {
+      if (HAS_STATS) {
         // column sums over the warp's 32 rows: butterfly where lane j ends up owning column j
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -208,10 +214,10 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
 
 using namespace hfl;
 
-template <int BLOCK_N, bool DGRAD = false>
-static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, const void* residual, float* stats,
-                       const ConvGeom& g, int tiles_m, cudaStream_t stream) {
-  auto kern = conv_fprop_tcgen05_kernel<BLOCK_N, DGRAD>;
+template <int BLOCK_N, bool DGRAD, bool HAS_RES, bool HAS_STATS>
+static int launch_conv_v(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, const void* residual, float* stats,
+                         const ConvGeom& g, int tiles_m, cudaStream_t stream) {
+  auto kern = conv_fprop_tcgen05_kernel<BLOCK_N, DGRAD, HAS_RES, HAS_STATS>;
   constexpr int smem = ConvSmem<BLOCK_N>::TOTAL;
   static bool configured = false;
   if (!configured) {
@@ -223,6 +229,19 @@ static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, co
   kern<<<grid, CV_THREADS, smem, stream>>>(tx, tw, (__nv_bfloat16*)Y, (const __nv_bfloat16*)residual, stats, g);
   count_launch();
   return (int)cudaGetLastError();
+}
+
+template <int BLOCK_N, bool DGRAD = false>
+static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, const void* residual, float* stats,
+                       const ConvGeom& g, int tiles_m, cudaStream_t stream) {
+  if (residual != nullptr && (reinterpret_cast<uintptr_t>(residual) & 15) != 0) return -3;
+  if ((reinterpret_cast<uintptr_t>(Y) & 15) != 0) return -3;
+  if (residual != nullptr) {
+    if (stats != nullptr) return launch_conv_v<BLOCK_N, DGRAD, true, true>(tx, tw, Y, residual, stats, g, tiles_m, stream);
+    return launch_conv_v<BLOCK_N, DGRAD, true, false>(tx, tw, Y, residual, stats, g, tiles_m, stream);
+  }
+  if (stats != nullptr) return launch_conv_v<BLOCK_N, DGRAD, false, true>(tx, tw, Y, residual, stats, g, tiles_m, stream);
+  return launch_conv_v<BLOCK_N, DGRAD, false, false>(tx, tw, Y, residual, stats, g, tiles_m, stream);
 }
 
 // 0 if this problem can run on the tcgen05 path
@@ -386,22 +405,34 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __g
       const int q = warp - 4;
       mbar_wait(tmem_full_bar, 0);
       tcgen05_fence_after();
-      const int k = k_blk * 128 + q * 32 + lane;
+      // stage the warp's 32 x 64 fp32 block in shared memory, then write / accumulate whole 256-byte filter rows
+      // with 16-byte accesses (a row per thread made every store or atomic touch 32 different rows)
+      constexpr int PITCH = 64 * 4 + 16;
+      uint8_t* my = smem + (size_t)q * 32 * PITCH;
+      {
+        uint8_t* myrow = my + lane * PITCH;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + c0, v);
-        tmem_ld_wait();
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(myrow + (c0 + j) * 4) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+      __syncwarp();
+      const int rsub = lane >> 4, cseg = (lane & 15) * 4;     // 16 lanes x 4 floats per 64-channel row, 2 rows / instr
+#pragma unroll 4
+      for (int r0 = 0; r0 < 32; r0 += 2) {
+        const int k = k_blk * 128 + q * 32 + r0 + rsub;
         if (k < g.Kout) {
-          float* dst = dW + ((size_t)k * g.R * g.S + tap) * g.C + c_blk * 64 + c0;
+          const float4 val = *reinterpret_cast<const float4*>(my + (r0 + rsub) * PITCH + cseg * 4);
+          float* dst = dW + ((size_t)k * g.R * g.S + tap) * g.C + c_blk * 64 + cseg;
           if (g.splits == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            *reinterpret_cast<float4*>(dst) = val;
           } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+            atomicAdd(reinterpret_cast<float4*>(dst), val);
           }
         }
       }

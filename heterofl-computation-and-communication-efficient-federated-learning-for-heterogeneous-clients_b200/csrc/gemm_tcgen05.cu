@@ -42,7 +42,7 @@ struct GemmSmem {
 // +16 B so the 16-byte staging writes are conflict-free) and writes whole row segments with 16-byte stores.
 // `xf(acc, tile_col)` applies alpha / bias / activation.
 // ---------------------------------------------------------------------------------------------------------
-template <int BLOCK_N, bool OUT_BF16, typename XF>
+template <int BLOCK_N, bool OUT_BF16, bool ATOMIC = false, typename XF>
 __device__ __forceinline__ void epilogue_store_tile(uint32_t tmem_base, uint8_t* smem_stage, int q, int lane, void* C,
                                                     int ldc, int row0, int col0, int M, int N, XF xf) {
   constexpr int ELT = OUT_BF16 ? 2 : 4;
@@ -89,7 +89,10 @@ __device__ __forceinline__ void epilogue_store_tile(uint32_t tmem_base, uint8_t*
     if (grow < M && gcol < N) {
       const uint8_t* src = my + r * PITCH + cb;
       uint8_t* dst = reinterpret_cast<uint8_t*>(C) + ((size_t)grow * ldc + gcol) * ELT;
-      if (vec_ok && gcol + 16 / ELT <= N) {
+      if (ATOMIC) {                       // split-K partial: fp32 accumulate into a zero-filled C
+        for (int e = 0; e < 4 && gcol + e < N; ++e)
+          atomicAdd(reinterpret_cast<float*>(dst) + e, reinterpret_cast<const float*>(src)[e]);
+      } else if (vec_ok && gcol + 16 / ELT <= N) {
         *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
       } else {
         for (int e = 0; e < 16 / ELT && gcol + e < N; ++e) {
@@ -238,6 +241,9 @@ template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_BF16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_general_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                             void* __restrict__ C, float alpha, int M, int N, int K, int ldc) {
+  // split-K: gridDim.z CTAs share one output tile, each reducing a contiguous range of k-blocks and accumulating its
+  // fp32 partial into a zero-filled C with atomics (skinny problems: dX of the vocabulary projection is 64 x 256
+  // with K = 33 278 -- two CTAs streaming 520 k-blocks each otherwise)
   extern __shared__ uint8_t smem_raw[];
   using S = GemmSmem<BLOCK_N>;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -247,7 +253,11 @@ gemm_tcgen05_general_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_blk = blockIdx.x, n_blk = blockIdx.y;
-  const int num_k = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  const int num_k_all = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  const int per_split = (num_k_all + gridDim.z - 1) / gridDim.z;
+  const int kb_lo = blockIdx.z * per_split;
+  const int num_k = min(per_split, num_k_all - kb_lo);
+  if (num_k <= 0) return;                                  // whole CTA: nothing allocated yet
   constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
   if (warp == 1 && lane == 0) {
@@ -270,17 +280,17 @@ gemm_tcgen05_general_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         uint8_t* sb = sa + S::A_BYTES;
         mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
         if (A_MN) {   // two 64(m) x 64(k) boxes of the [K, M] matrix
-          tma_load_2d(sa, &tmap_a, &full_bar[s], m_blk * GEMM_BLOCK_M, kb * GEMM_BLOCK_K);
-          tma_load_2d(sa + 8192, &tmap_a, &full_bar[s], m_blk * GEMM_BLOCK_M + 64, kb * GEMM_BLOCK_K);
+          tma_load_2d(sa, &tmap_a, &full_bar[s], m_blk * GEMM_BLOCK_M, (kb_lo + kb) * GEMM_BLOCK_K);
+          tma_load_2d(sa + 8192, &tmap_a, &full_bar[s], m_blk * GEMM_BLOCK_M + 64, (kb_lo + kb) * GEMM_BLOCK_K);
         } else {
-          tma_load_2d(sa, &tmap_a, &full_bar[s], kb * GEMM_BLOCK_K, m_blk * GEMM_BLOCK_M);
+          tma_load_2d(sa, &tmap_a, &full_bar[s], (kb_lo + kb) * GEMM_BLOCK_K, m_blk * GEMM_BLOCK_M);
         }
         if (B_MN) {
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
-            tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[s], n_blk * BLOCK_N + j * 64, kb * GEMM_BLOCK_K);
+            tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[s], n_blk * BLOCK_N + j * 64, (kb_lo + kb) * GEMM_BLOCK_K);
         } else {
-          tma_load_2d(sb, &tmap_b, &full_bar[s], kb * GEMM_BLOCK_K, n_blk * BLOCK_N);
+          tma_load_2d(sb, &tmap_b, &full_bar[s], (kb_lo + kb) * GEMM_BLOCK_K, n_blk * BLOCK_N);
         }
       }
     }
@@ -312,8 +322,12 @@ gemm_tcgen05_general_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
     auto xf = [&](float acc, int) -> float { return acc * alpha; };
-    epilogue_store_tile<BLOCK_N, OUT_BF16>(tmem_base, smem, q, lane, C, ldc, m_blk * GEMM_BLOCK_M, n_blk * BLOCK_N, M, N,
-                                           xf);
+    if (!OUT_BF16 && gridDim.z > 1)
+      epilogue_store_tile<BLOCK_N, false, true>(tmem_base, smem, q, lane, C, ldc, m_blk * GEMM_BLOCK_M, n_blk * BLOCK_N,
+                                                M, N, xf);
+    else
+      epilogue_store_tile<BLOCK_N, OUT_BF16>(tmem_base, smem, q, lane, C, ldc, m_blk * GEMM_BLOCK_M, n_blk * BLOCK_N, M,
+                                             N, xf);
     tcgen05_fence_before();
   }
   __syncthreads();
@@ -329,7 +343,7 @@ using namespace hfl;
 
 template <bool A_MN, bool B_MN, bool OUT_BF16>
 static int launch_gemm_general(const CUtensorMap& ta, const CUtensorMap& tb, void* C, float alpha, int M, int N, int K,
-                               int ldc, cudaStream_t stream) {
+                               int ldc, int splits, cudaStream_t stream) {
   auto kern = gemm_tcgen05_general_kernel<128, A_MN, B_MN, OUT_BF16>;
   constexpr int smem = GemmSmem<128>::TOTAL;
   static bool configured = false;
@@ -338,7 +352,7 @@ static int launch_gemm_general(const CUtensorMap& ta, const CUtensorMap& tb, voi
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  dim3 grid((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M, (N + 127) / 128);
+  dim3 grid((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M, (N + 127) / 128, splits);
   kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, C, alpha, M, N, K, ldc);
   count_launch();
   return (int)cudaGetLastError();
@@ -346,9 +360,22 @@ static int launch_gemm_general(const CUtensorMap& ta, const CUtensorMap& tb, voi
 
 // General layouts.  a_mn: A is stored [K, M] (lda = row stride in elements) instead of [M, K]; b_mn: B is stored
 // [K, N] instead of [N, K].  All leading dimensions and the contiguous extents must be multiples of 8 elements.
+// How many K-splits a problem should use: only skinny grids with a long reduction (each split keeps >= 8 k-blocks).
+extern "C" int hfl_gemm_general_splits(int M, int N, int K) {
+  const int tiles = ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((N + 127) / 128);
+  const int num_k = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  if (tiles >= 32 || num_k < 32) return 1;
+  int s = 148 / tiles;
+  if (s > num_k / 8) s = num_k / 8;
+  return s < 1 ? 1 : s;
+}
+
+// splits > 1: C must be fp32 and zero-filled (partials are accumulated with atomics).
 extern "C" int hfl_gemm_bf16_general(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc,
-                                     int out_bf16, float alpha, int M, int N, int K, cudaStream_t stream) {
+                                     int out_bf16, float alpha, int M, int N, int K, int splits, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (splits < 1) splits = 1;
+  if (splits > 1 && out_bf16) return -4;
   CUtensorMap ta, tb;
   int r = a_mn ? make_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, GEMM_BLOCK_K)
                : make_tmap_2d_bf16(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, GEMM_BLOCK_K, GEMM_BLOCK_M);
@@ -358,8 +385,8 @@ extern "C" int hfl_gemm_bf16_general(const void* A, int lda, int a_mn, const voi
   if (r) return 2000 + r;
 #define HFL_GG(AM, BM)                                                                                       \
   if ((a_mn != 0) == AM && (b_mn != 0) == BM)                                                                \
-    return out_bf16 ? launch_gemm_general<AM, BM, true>(ta, tb, C, alpha, M, N, K, ldc, stream)              \
-                    : launch_gemm_general<AM, BM, false>(ta, tb, C, alpha, M, N, K, ldc, stream);
+    return out_bf16 ? launch_gemm_general<AM, BM, true>(ta, tb, C, alpha, M, N, K, ldc, splits, stream)      \
+                    : launch_gemm_general<AM, BM, false>(ta, tb, C, alpha, M, N, K, ldc, splits, stream);
   HFL_GG(false, false)
   HFL_GG(false, true)
   HFL_GG(true, false)

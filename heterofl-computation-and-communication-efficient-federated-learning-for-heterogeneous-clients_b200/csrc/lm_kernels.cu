@@ -319,18 +319,36 @@ lm_colsum_kernel(const bf16* __restrict__ x, int M, int N, int ld, float alpha, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Attention for S <= 64 keys: one CTA per (row n, head h), 256 threads = 64 query rows x 4 key/feature parts.
-// q, k, v, o: [N*S, E] bf16 with head h at columns [h*dh, (h+1)*dh).  P: [N, H, S, S] bf16 (saved for backward).
+// Attention for S <= 64 keys, head dim <= 32.  q, k, v, o: [N*S, E] bf16 with head h at columns [h*dh, (h+1)*dh);
+// P: [N, H, S, S] bf16 (saved for backward).  A federated client batch is ONE row of 64 tokens, i.e. only H = 8
+// (row, head) pairs: the kernels therefore split every pair over several CTAs so the step does not crawl on 8 SMs.
+//   forward : grid (N*H, 4)  -- CTA = 16 query rows x 16 lanes (4 keys and 2 features per lane)
+//   backward: grid (N*H, 8)  -- y < 4: 16 query rows -> dQ;  y >= 4: 16 keys -> dK, dV.  Both roles recompute their
+//             dP block and use delta_i = dO_i . O_i (so no role needs a full row/column of the other).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int AT_S = 64, AT_DH = 32;
+constexpr int AT_S = 64, AT_DH = 32, AT_BLK = 16;
+
+__device__ __forceinline__ float half_warp_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float half_warp_max(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
 
 __global__ void __launch_bounds__(256)
 lm_attn_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, int S, int H,
                    int dh, float scale, bf16* __restrict__ o, bf16* __restrict__ P) {
   __shared__ float sK[AT_S][AT_DH + 1];
   __shared__ float sV[AT_S][AT_DH + 1];
-  __shared__ float sP[AT_S][AT_S + 1];
+  __shared__ float sQ[AT_BLK][AT_DH + 1];
+  __shared__ float sP[AT_BLK][AT_S + 1];
   const int n = blockIdx.x / H, h = blockIdx.x % H, E = H * dh;
+  const int i0 = blockIdx.y * AT_BLK;
+  if (i0 >= S) return;
   const int tid = threadIdx.x;
   const size_t base = (size_t)n * S * E + (size_t)h * dh;
   for (int t = tid; t < AT_S * AT_DH; t += 256) {
@@ -339,138 +357,158 @@ lm_attn_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const
     sK[j][d] = ok ? __bfloat162float(k[base + (size_t)j * E + d]) : 0.f;
     sV[j][d] = ok ? __bfloat162float(v[base + (size_t)j * E + d]) : 0.f;
   }
+  for (int t = tid; t < AT_BLK * AT_DH; t += 256) {
+    const int r = t / AT_DH, d = t % AT_DH;
+    sQ[r][d] = (i0 + r < S && d < dh) ? __bfloat162float(q[base + (size_t)(i0 + r) * E + d]) : 0.f;
+  }
   __syncthreads();
-  const int i = tid >> 2, part = tid & 3;
-  float qv[AT_DH];
-#pragma unroll
-  for (int d = 0; d < AT_DH; ++d) qv[d] = (i < S && d < dh) ? __bfloat162float(q[base + (size_t)i * E + d]) : 0.f;
-  float sc[AT_S / 4];
+  const int r = tid >> 4, l = tid & 15, i = i0 + r;
+  float sc[4];
   float mx = -INFINITY;
 #pragma unroll
-  for (int jj = 0; jj < AT_S / 4; ++jj) {
-    const int j = part * (AT_S / 4) + jj;
+  for (int t = 0; t < 4; ++t) {
+    const int j = l + 16 * t;
     float a = 0.f;
-    if (j < S) {
 #pragma unroll
-      for (int d = 0; d < AT_DH; ++d) a += qv[d] * sK[j][d];      // sK columns >= dh are never read as non-zero q
-      a *= scale;
-      mx = fmaxf(mx, a);
-    }
-    sc[jj] = j < S ? a : -INFINITY;
+    for (int d = 0; d < AT_DH; ++d) a += sQ[r][d] * sK[j][d];
+    sc[t] = j < S ? a * scale : -INFINITY;
+    mx = fmaxf(mx, sc[t]);
   }
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  mx = half_warp_max(mx);
   float sum = 0.f;
 #pragma unroll
-  for (int jj = 0; jj < AT_S / 4; ++jj) {
-    sc[jj] = sc[jj] == -INFINITY ? 0.f : __expf(sc[jj] - mx);
-    sum += sc[jj];
+  for (int t = 0; t < 4; ++t) {
+    sc[t] = sc[t] == -INFINITY ? 0.f : __expf(sc[t] - mx);
+    sum += sc[t];
   }
-  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-  const float inv = 1.f / sum;
+  const float inv = 1.f / half_warp_sum(sum);
   bf16* Prow = P + (((size_t)n * H + h) * S + i) * S;
 #pragma unroll
-  for (int jj = 0; jj < AT_S / 4; ++jj) {
-    const int j = part * (AT_S / 4) + jj;
-    if (i < S && j < S) {
-      const bf16 pb = __float2bfloat16(sc[jj] * inv);
-      Prow[j] = pb;
-      sP[i][j] = __bfloat162float(pb);        // the saved (rounded) probabilities are the ones used for P.V
-    }
+  for (int t = 0; t < 4; ++t) {
+    const int j = l + 16 * t;
+    const bf16 pb = __float2bfloat16(sc[t] * inv);
+    sP[r][j] = __bfloat162float(pb);            // the saved (rounded) probabilities are the ones used for P.V
+    if (i < S && j < S) Prow[j] = pb;
   }
-  __syncthreads();
+  __syncwarp();                                  // a row's 16 lanes live in one warp
   if (i < S) {
-    for (int d = part; d < dh; d += 4) {
+    for (int d = l; d < dh; d += 16) {
       float a = 0.f;
-      for (int j = 0; j < S; ++j) a += sP[i][j] * sV[j][d];
+#pragma unroll 8
+      for (int j = 0; j < AT_S; ++j) a += sP[r][j] * sV[j][d];
       o[base + (size_t)i * E + d] = __float2bfloat16(a);
     }
   }
 }
 
-// dynamic smem: sQ, sK, sV, sO [S][DH+1] floats, sP, sS [S][S+1] floats
 __global__ void __launch_bounds__(256)
 lm_attn_bwd_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ q, const bf16* __restrict__ k,
-                   const bf16* __restrict__ v, const bf16* __restrict__ P, int S, int H, int dh, float scale,
-                   bf16* __restrict__ dq, bf16* __restrict__ dk, bf16* __restrict__ dv, float* __restrict__ dbq,
-                   float* __restrict__ dbk, float* __restrict__ dbv, float alpha_v) {
-  extern __shared__ float smf[];
-  float (*sQ)[AT_DH + 1] = reinterpret_cast<float (*)[AT_DH + 1]>(smf);
-  float (*sK)[AT_DH + 1] = sQ + AT_S;
-  float (*sV)[AT_DH + 1] = sK + AT_S;
-  float (*sO)[AT_DH + 1] = sV + AT_S;
-  float (*sP)[AT_S + 1] = reinterpret_cast<float (*)[AT_S + 1]>(&sO[AT_S][0]);
-  float (*sS)[AT_S + 1] = sP + AT_S;
-  float* sB = &sS[AT_S][0];                              // [3][AT_DH] bias partials
+                   const bf16* __restrict__ v, const bf16* __restrict__ O, const bf16* __restrict__ P, int S, int H,
+                   int dh, float scale, bf16* __restrict__ dq, bf16* __restrict__ dk, bf16* __restrict__ dv,
+                   float* __restrict__ dbq, float* __restrict__ dbk, float* __restrict__ dbv, float alpha_v) {
+  __shared__ float sA[AT_S][AT_DH + 1];          // role Q: K      role K: Q
+  __shared__ float sB[AT_S][AT_DH + 1];          // role Q: V      role K: dO
+  __shared__ float sC[AT_BLK][AT_DH + 1];        // role Q: dO_i   role K: V_j
+  __shared__ float sS[AT_BLK][AT_S + 1];         // dS block (role K: transposed, [key][query])
+  __shared__ float sPb[AT_BLK][AT_S + 1];        // role K: P block transposed
+  __shared__ float sDelta[AT_S];
+  __shared__ float sBias[2][AT_DH];
   const int n = blockIdx.x / H, h = blockIdx.x % H, E = H * dh;
+  const bool role_q = blockIdx.y < 4;
+  const int b0 = (blockIdx.y & 3) * AT_BLK;      // first query (role Q) / key (role K) of this CTA
+  if (b0 >= S) return;
   const int tid = threadIdx.x;
   const size_t base = (size_t)n * S * E + (size_t)h * dh;
+  const bf16* Pb = P + ((size_t)n * H + h) * S * S;
+  const bf16* gA = role_q ? k : q;
+  const bf16* gB = role_q ? v : dO;
+  const bf16* gC = role_q ? dO : v;
   for (int t = tid; t < AT_S * AT_DH; t += 256) {
     const int j = t / AT_DH, d = t % AT_DH;
     const bool ok = j < S && d < dh;
     const size_t g = base + (size_t)j * E + d;
-    sQ[j][d] = ok ? __bfloat162float(q[g]) : 0.f;
-    sK[j][d] = ok ? __bfloat162float(k[g]) : 0.f;
-    sV[j][d] = ok ? __bfloat162float(v[g]) : 0.f;
-    sO[j][d] = ok ? __bfloat162float(dO[g]) : 0.f;
+    sA[j][d] = ok ? __bfloat162float(gA[g]) : 0.f;
+    sB[j][d] = ok ? __bfloat162float(gB[g]) : 0.f;
   }
-  const bf16* Pb = P + ((size_t)n * H + h) * S * S;
-  for (int t = tid; t < AT_S * AT_S; t += 256) {
-    const int i = t / AT_S, j = t % AT_S;
-    sP[i][j] = (i < S && j < S) ? __bfloat162float(Pb[(size_t)i * S + j]) : 0.f;
+  for (int t = tid; t < AT_BLK * AT_DH; t += 256) {
+    const int r = t / AT_DH, d = t % AT_DH;
+    sC[r][d] = (b0 + r < S && d < dh) ? __bfloat162float(gC[base + (size_t)(b0 + r) * E + d]) : 0.f;
   }
-  if (tid < 3 * AT_DH) sB[tid] = 0.f;
+  if (tid < 2 * AT_DH) (&sBias[0][0])[tid] = 0.f;
+  {  // delta_i = dO_i . O_i for every query: 4 threads per query, 8 features each
+    const int i = tid >> 2, part = tid & 3;
+    float a = 0.f;
+    if (i < S) {
+      for (int d = part * 8; d < min(dh, part * 8 + 8); ++d) {
+        const size_t g = base + (size_t)i * E + d;
+        a += __bfloat162float(dO[g]) * __bfloat162float(O[g]);
+      }
+    }
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    if (part == 0) sDelta[i] = a;
+  }
   __syncthreads();
-  const int i = tid >> 2, part = tid & 3;
-  {
-    float dp[AT_S / 4];
-    float delta = 0.f;
+  const int r = tid >> 4, l = tid & 15;
+  if (role_q) {
+    const int i = b0 + r;
+    // dS_ij = P_ij (dO_i . V_j - delta_i) * scale for the lane's 4 keys
 #pragma unroll
-    for (int jj = 0; jj < AT_S / 4; ++jj) {
-      const int j = part * (AT_S / 4) + jj;
+    for (int t = 0; t < 4; ++t) {
+      const int j = l + 16 * t;
       float a = 0.f;
 #pragma unroll
-      for (int d = 0; d < AT_DH; ++d) a += sO[i][d] * sV[j][d];
-      dp[jj] = a;
-      delta += a * sP[i][j];
+      for (int d = 0; d < AT_DH; ++d) a += sC[r][d] * sB[j][d];
+      const float p = (i < S && j < S) ? __bfloat162float(Pb[(size_t)i * S + j]) : 0.f;
+      sS[r][j] = p * (a - sDelta[min(i, AT_S - 1)]) * scale;
     }
-    delta += __shfl_xor_sync(0xffffffffu, delta, 1);
-    delta += __shfl_xor_sync(0xffffffffu, delta, 2);
-#pragma unroll
-    for (int jj = 0; jj < AT_S / 4; ++jj) {
-      const int j = part * (AT_S / 4) + jj;
-      sS[i][j] = sP[i][j] * (dp[jj] - delta) * scale;
-    }
-  }
-  __syncthreads();
-  // row index r = i plays "query i" for dQ and "key j" for dK / dV
-  if (i < S) {
-    for (int d = part; d < dh; d += 4) {
-      float aq = 0.f, ak = 0.f, av = 0.f;
-      for (int j = 0; j < S; ++j) {
-        aq += sS[i][j] * sK[j][d];
-        ak += sS[j][i] * sQ[j][d];
-        av += sP[j][i] * sO[j][d];
+    __syncwarp();
+    if (i < S) {
+      for (int d = l; d < dh; d += 16) {
+        float a = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < AT_S; ++j) a += sS[r][j] * sA[j][d];
+        dq[base + (size_t)i * E + d] = __float2bfloat16(a);
+        atomicAdd(&sBias[0][d], a);
       }
-      const size_t g = base + (size_t)i * E + d;
-      dq[g] = __float2bfloat16(aq);
-      dk[g] = __float2bfloat16(ak);
-      dv[g] = __float2bfloat16(av);
-      atomicAdd(&sB[d], aq);
-      atomicAdd(&sB[AT_DH + d], ak);
-      atomicAdd(&sB[2 * AT_DH + d], av);
     }
-  }
-  __syncthreads();
-  if (tid < dh) {
-    atomicAdd(&dbq[h * dh + tid], sB[tid]);
-    atomicAdd(&dbk[h * dh + tid], sB[AT_DH + tid]);
-    atomicAdd(&dbv[h * dh + tid], sB[2 * AT_DH + tid] * alpha_v);
+    __syncthreads();
+    if (tid < dh) atomicAdd(&dbq[h * dh + tid], sBias[0][tid]);
+  } else {
+    const int j = b0 + r;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int i = l + 16 * t;
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < AT_DH; ++d) a += sB[i][d] * sC[r][d];           // dO_i . V_j
+      const float p = (i < S && j < S) ? __bfloat162float(Pb[(size_t)i * S + j]) : 0.f;
+      sPb[r][i] = p;
+      sS[r][i] = p * (a - sDelta[i]) * scale;
+    }
+    __syncwarp();
+    if (j < S) {
+      for (int d = l; d < dh; d += 16) {
+        float ak = 0.f, av = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < AT_S; ++i) {
+          ak += sS[r][i] * sA[i][d];             // dS_ij Q_i
+          av += sPb[r][i] * sB[i][d];            // P_ij dO_i
+        }
+        const size_t g = base + (size_t)j * E + d;
+        dk[g] = __float2bfloat16(ak);
+        dv[g] = __float2bfloat16(av);
+        atomicAdd(&sBias[0][d], ak);
+        atomicAdd(&sBias[1][d], av);
+      }
+    }
+    __syncthreads();
+    if (tid < dh) {
+      atomicAdd(&dbk[h * dh + tid], sBias[0][tid]);
+      atomicAdd(&dbv[h * dh + tid], sBias[1][tid] * alpha_v);
+    }
   }
 }
-
-constexpr int ATTN_BWD_SMEM = (4 * AT_S * (AT_DH + 1) + 2 * AT_S * (AT_S + 1) + 3 * AT_DH) * 4;
 
 }  // namespace hfl
 
@@ -550,23 +588,17 @@ extern "C" void hfl_lm_colsum(const void* x, int M, int N, int ld, float alpha, 
 
 extern "C" void hfl_lm_attn_fwd(const void* q, const void* k, const void* v, int N, int S, int H, int dh, float scale,
                                 void* o, void* P, cudaStream_t st) {
-  lm_attn_fwd_kernel<<<N * H, 256, 0, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, S, H, dh, scale, (bf16*)o,
-                                            (bf16*)P);
+  lm_attn_fwd_kernel<<<dim3(N * H, 4), 256, 0, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, S, H, dh, scale,
+                                                     (bf16*)o, (bf16*)P);
   count_launch();
 }
 
-extern "C" int hfl_lm_attn_bwd(const void* dO, const void* q, const void* k, const void* v, const void* P, int N, int S,
-                               int H, int dh, float scale, void* dq, void* dk, void* dv, float* dbq, float* dbk,
-                               float* dbv, float alpha_v, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(lm_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_BWD_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
-  lm_attn_bwd_kernel<<<N * H, 256, ATTN_BWD_SMEM, st>>>((const bf16*)dO, (const bf16*)q, (const bf16*)k, (const bf16*)v,
-                                                        (const bf16*)P, S, H, dh, scale, (bf16*)dq, (bf16*)dk, (bf16*)dv,
-                                                        dbq, dbk, dbv, alpha_v);
+extern "C" int hfl_lm_attn_bwd(const void* dO, const void* q, const void* k, const void* v, const void* O, const void* P,
+                               int N, int S, int H, int dh, float scale, void* dq, void* dk, void* dv, float* dbq,
+                               float* dbk, float* dbv, float alpha_v, cudaStream_t st) {
+  lm_attn_bwd_kernel<<<dim3(N * H, 8), 256, 0, st>>>((const bf16*)dO, (const bf16*)q, (const bf16*)k, (const bf16*)v,
+                                                     (const bf16*)O, (const bf16*)P, S, H, dh, scale, (bf16*)dq,
+                                                     (bf16*)dk, (bf16*)dv, dbq, dbk, dbv, alpha_v);
   count_launch();
   return (int)cudaGetLastError();
 }

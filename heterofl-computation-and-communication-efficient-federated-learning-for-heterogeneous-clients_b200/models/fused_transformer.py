@@ -199,7 +199,7 @@ class FusedTransformer:
                                        sg[pre + ".mha.linear_o.bias"], inv)
             G[pre + ".mha.linear_o.weight"] = self._dw(doo, sv["o"], inv)
             do = self._dx(doo, P[pre + ".mha.linear_o.weight"], inv)
-            dq, dk, dv = C.lm_attn_bwd(do, sv["q"], sv["k"], sv["v"], sv["pr"], N, S, H, att_scale,
+            dq, dk, dv = C.lm_attn_bwd(do, sv["q"], sv["k"], sv["v"], sv["o"], sv["pr"], N, S, H, att_scale,
                                        sg[pre + ".mha.linear_q.bias"], sg[pre + ".mha.linear_k.bias"],
                                        sg[pre + ".mha.linear_v.bias"], inv)
             xin = sv["x"]

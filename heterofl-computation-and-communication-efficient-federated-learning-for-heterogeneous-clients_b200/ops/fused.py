@@ -134,8 +134,8 @@ def conv_fwd(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> torch.T
     return F.conv2d(x, w, None, stride, pad)
 
 
-# backward convolutions on the tcgen05 kernels: "off" | "on" | "auto" (table from profiles/conv_bwd_bench.md)
-CONV_BWD_TC_MODE = os.environ.get("HFL_CONV_BWD_TC", "off")
+# backward convolutions on the tcgen05 kernels: "off" | "on" (dgrad + wgrad) | "wgrad" (weight gradient only)
+CONV_BWD_TC_MODE = os.environ.get("HFL_CONV_BWD_TC", "wgrad")
 
 
 def _tc_bwd_ok(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> bool:
@@ -151,7 +151,7 @@ def conv_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int, pa
     an implicit GEMM with mirrored taps + MN-major filter operand, wgrad with both operands MN-major and split-K;
     ``dw`` then comes back as fp32 (the multi-tensor optimiser reads either precision)."""
     if not need_dw:
-        if _tc_bwd_ok(dy, x, w, stride, pad) and stride == 1 and cu.C().conv_tc_supported(
+        if CONV_BWD_TC_MODE == "on" and _tc_bwd_ok(dy, x, w, stride, pad) and stride == 1 and cu.C().conv_tc_supported(
                 x.shape[0], x.shape[2], x.shape[3], w.shape[0], x.shape[1], w.shape[2], w.shape[3], 1):
             return cu.C().conv_dgrad_tc(dy, w, None), None
         dx, _, _ = torch.ops.aten.convolution_backward(dy, x, w, None, (stride, stride), (pad, pad), (1, 1), False,
@@ -162,7 +162,7 @@ def conv_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int, pa
         K, _, R, S = w.shape
         C_ = cu.C()
         dx = dw = None
-        if need_dx and stride == 1 and C_.conv_tc_supported(N, H, W, K, C, R, S, 1):
+        if CONV_BWD_TC_MODE == "on" and need_dx and stride == 1 and C_.conv_tc_supported(N, H, W, K, C, R, S, 1):
             dx = C_.conv_dgrad_tc(dy, w, None)
         if C_.conv_wgrad_tc_supported(N, H, W, C, K, R, S, stride):
             dw = C_.conv_wgrad_tc(dy, x, R, stride)
