@@ -55,5 +55,17 @@ if which in ("all", "norm"):
         for _ in range(reps):
             s, y, m, iv, _ = fo.bn_act_fwd(x, None, ga, be, 1e-5)
             fo.bn_act_bwd(y, None, None, x, m, iv, ga, be, torch.empty_like(ga), torch.empty_like(be))
+if which in ("all", "lm"):
+    import math
+    N_, S_, H_, E_ = 1, 64, 8, 256
+    q, k, v, do = [torch.randn(N_ * S_, E_, device=dev).bfloat16() for _ in range(4)]
+    ga = torch.ones(E_, device=dev).bfloat16()
+    seed = torch.zeros(1, dtype=torch.int64, device=dev)
+    dbs = [torch.zeros(E_, device=dev) for _ in range(3)]
+    for _ in range(reps):
+        o, P = C.lm_attn_fwd(q, k, v, N_, S_, H_, 1.0 / math.sqrt(32))
+        C.lm_attn_bwd(do, q, k, v, o, P, N_, S_, H_, 1.0 / math.sqrt(32), dbs[0], dbs[1], dbs[2], 1.0)
+        y, xh, rs, dm = C.lm_add_ln_fwd(q, k, ga, ga, 1e-5, 0.2, seed, seed, 3)
+        C.lm_add_ln_bwd([do, q], xh, rs, ga, dm, 0.2, dbs[0], dbs[1], dbs[2], 1.0)
 torch.cuda.synchronize()
 print("done", which)
