@@ -1,5 +1,6 @@
 // Python bindings (pybind11 / ATen) for the hfl_b200 sm_100a kernels and the peer-memory runtime.
 #include <torch/extension.h>
+#include <cstdlib>
 #include <c10/cuda/CUDAStream.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <cuda_runtime.h>
@@ -33,6 +34,9 @@ void hfl_multi_sgd_clip_step(const void*, const void*, int, float*, void*, float
 int hfl_gemm_bf16_tn(const void*, int, const void*, int, void*, int, int, const float*, const void*, float, int, int,
                      int, int, cudaStream_t);
 void hfl_gemm_timing(long long*);
+int hfl_gemm_mc_wanted(int, int, int);
+int hfl_gemm_bf16_tn_mc(const void*, int, const void*, int, void*, int, const float*, const void*, float, int, int, int, int,
+                        cudaStream_t);
 int hfl_lm_max_e();
 int hfl_lm_max_s();
 int hfl_lm_max_dh();
@@ -347,6 +351,14 @@ torch::Tensor gemm_bf16_tn(torch::Tensor x, torch::Tensor w, c10::optional<torch
                 y.scalar_type() == (out_fp32 ? torch::kFloat32 : torch::kBFloat16));
   } else {
     y = torch::empty({M, N}, torch::TensorOptions().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16).device(x.device()));
+  }
+  // big problems: 2-CTA clusters with TMA multicast of the shared operand + 128x256 tiles (csrc/gemm_mc_tcgen05.cu)
+  static const bool mc_enabled = []() { const char* e = std::getenv("HFL_GEMM_MC"); return !(e && e[0] == '0'); }();
+  if (mc_enabled && !out_fp32 && hfl_gemm_mc_wanted((int)M, (int)N, (int)K)) {
+    int e2 = hfl_gemm_bf16_tn_mc(x.data_ptr(), (int)x.stride(0), w.data_ptr(), (int)w.stride(0), y.data_ptr(),
+                                 (int)y.stride(0), bp, bhp, (float)alpha, gelu ? 1 : 0, (int)M, (int)N, (int)K, cur_stream());
+    TORCH_CHECK(e2 == 0, "gemm_bf16_tn_mc failed with code ", e2);
+    return y;
   }
   int e = hfl_gemm_bf16_tn(x.data_ptr(), (int)x.stride(0), w.data_ptr(), (int)w.stride(0), y.data_ptr(), (int)y.stride(0),
                            out_fp32 ? 0 : 1, bp, bhp, (float)alpha, gelu ? 1 : 0, (int)M, (int)N, (int)K, cur_stream());

@@ -371,3 +371,28 @@ def test_tcgen05_conv_wgrad_matches_autograd(N, C, H, K, R, stride):
     ref = w.grad
     assert dw.shape == ref.shape
     assert float((dw - ref).abs().max()) < 2e-2 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 1024, 256), (1100, 1032, 320), (1152, 33278, 256), (2048, 1024, 1024)])
+def test_cluster_multicast_gemm(M, N, K):
+    """2-CTA cluster + TMA multicast + 128x256 tiles (csrc/gemm_mc_tcgen05.cu): odd tile counts (padding CTA of the pair),
+    ragged N, row-padded output, every epilogue variant; agrees with fp32 torch and with the single-CTA kernel."""
+    cu = _cu()
+    C = cu.C()
+    dev = torch.device("cuda")
+    torch.manual_seed(M + K)
+    x = torch.randn(M, K, device=dev).bfloat16()
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device=dev).bfloat16()
+    ref = x.float() @ w.float().t()
+    y = C.gemm_bf16_tn(x, w, None, 1.0, False, False, False, None)
+    assert torch.allclose(y.float(), ref, atol=3e-2, rtol=3e-2), float((y.float() - ref).abs().max())
+    Np = (N + 7) // 8 * 8
+    buf = torch.full((M, Np), 3.0, device=dev).bfloat16()
+    y2 = C.gemm_bf16_tn(x, w, b, 0.5, True, False, True, buf[:, :N])
+    ref2 = torch.nn.functional.gelu(0.5 * (ref + b.float()))
+    assert torch.allclose(y2.float(), ref2, atol=3e-2, rtol=3e-2)
+    if Np > N:
+        assert bool((buf[:, N:] == 3.0).all())
+    y3 = C.gemm_bf16_tn(x, w, b.float(), 2.0, False, False, False, None)
+    assert torch.allclose(y3.float(), 2.0 * ref + b.float(), atol=6e-2, rtol=3e-2)
