@@ -5,7 +5,8 @@
 //   then spins until its own flags[q] >= epoch for every q       (ld.acquire.sys)
 // The kernel is enqueued on the compute stream, so "all ranks finished local training" / "new W_g published" are
 // device-side events: no host synchronisation and no NCCL call sits between the phases of a round.
-// A bounded spin (~4 s) turns a lost peer into an error flag instead of a hung GPU.
+// A bounded spin (~60 s: a peer may legitimately be busy capturing CUDA graphs on a cold start) turns a lost peer into
+// an error flag (PeerPool.check) instead of a hung GPU.
 #include <atomic>
 #include "common.cuh"
 
@@ -27,7 +28,7 @@ __global__ void peer_barrier_kernel(const unsigned long long* __restrict__ flag_
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
       if (v >= epoch) break;
-      if (clock64() - t0 > 8000000000LL) { if (err) atomicExch(err, 1); break; }
+      if (clock64() - t0 > 120000000000LL) { if (err) atomicExch(err, 1); break; }
       __nanosleep(200);
     } while (true);
   }
