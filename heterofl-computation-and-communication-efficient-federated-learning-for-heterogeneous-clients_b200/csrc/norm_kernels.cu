@@ -14,6 +14,7 @@
 // statistics pass: G train-mode batches per launch).  The Scaler is folded into `eps` by the caller.
 // Activations are NHWC bf16, viewed as [rows, C]; C is a power of two (4..4096).
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -645,9 +646,25 @@ using namespace hfl;
 
 // Choose (cluster size K, vectors per thread NV) so that K * NT * NV vectors cover one statistics group.
 // NV == 0 selects the looping kernel (very large groups only).
+static int bn_shape_policy() {
+  static const int p = []() { const char* e = getenv("HFL_BN_SHAPE"); return e ? atoi(e) : 0; }();
+  return p;
+}
 static void pick_shape(long elems, int& K, int& NV) {
   const long nvec = elems / 8;
   const int nvs[4] = {1, 2, 4, 10};   // NV=10 only reachable for multi-group (ghost batch) launches
+  if (bn_shape_policy() == 1) {
+    // fewest CTAs first: tiny tensors are latency-bound, a 1-2 CTA launch skips most of the cluster scheduling and
+    // DSMEM round trips of an 8-CTA cluster
+    for (int ki = 0; ki < 5; ++ki) {
+      const int kk = 1 << ki;
+      for (int ni = 0; ni < 4; ++ni)
+        if ((long)kk * NT * nvs[ni] >= nvec) { K = kk; NV = nvs[ni]; return; }
+    }
+    K = 8;
+    NV = 0;
+    return;
+  }
   for (int ki = 0; ki < 5; ++ki) {
     const int kk = 1 << ki;                       // 1, 2, 4, 8, 16
     for (int ni = 0; ni < 4; ++ni) {

@@ -134,6 +134,12 @@ def conv_fwd(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> torch.T
     return F.conv2d(x, w, None, stride, pad)
 
 
+# library convolutions: let cuDNN time its candidate kernels per shape (the reference does the same,
+# src/train_classifier_fed.py:19).  The heuristic picks are poor for the narrow levels (C = 4..32: e.g. a 41 us
+# wgrad2d_grouped_direct_kernel); the search runs in the warm-up steps that precede every graph capture.
+if os.environ.get("HFL_CUDNN_BENCHMARK", "1") != "0":
+    torch.backends.cudnn.benchmark = True
+
 # backward convolutions on the tcgen05 kernels: "off" | "on" (dgrad + wgrad) | "wgrad" (weight gradient only)
 CONV_BWD_TC_MODE = os.environ.get("HFL_CONV_BWD_TC", "wgrad")
 
