@@ -54,8 +54,8 @@ class EngineOptions:
     tensorboard: bool = False
     quiet: bool = False
     save: bool = True
-    stats_chunk_groups: int = 256
-    test_chunk: int = 2500
+    stats_chunk_groups: int = int(os.environ.get("HFL_STATS_CHUNK", "1000"))   # ghost batches per sBN launch
+    test_chunk: int = int(os.environ.get("HFL_TEST_CHUNK", "2500"))
     async_eval: bool = False             # overlap round r's sBN+test with round r+1's training (run_round/collect_eval)
     threaded_issue: bool = True          # one host thread per active client slot issues its graph replays
     nvtx: bool = False                   # NVTX range per phase (distribute+train / aggregate / sbn / test) for nsys/ncu

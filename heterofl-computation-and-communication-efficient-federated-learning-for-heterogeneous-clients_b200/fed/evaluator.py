@@ -27,7 +27,7 @@ from ..parallel.dist import DistInfo, all_reduce_sum
 
 class Evaluator:
     def __init__(self, model: Model, cfg: Dict, info: DistInfo, compute_dtype=torch.float32,
-                 stats_chunk_groups: int = 256, test_chunk: int = 2500):
+                 stats_chunk_groups: int = 1000, test_chunk: int = 2500):
         self.model, self.cfg, self.info = model, cfg, info
         self.device, self.dtype = info.device, compute_dtype
         self.stats_chunk_groups, self.test_chunk = stats_chunk_groups, test_chunk
