@@ -137,7 +137,11 @@ def conv_fwd(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> torch.T
 # library convolutions: let cuDNN time its candidate kernels per shape (the reference does the same,
 # src/train_classifier_fed.py:19).  The heuristic picks are poor for the narrow levels (C = 4..32: e.g. a 41 us
 # wgrad2d_grouped_direct_kernel); the search runs in the warm-up steps that precede every graph capture.
-if os.environ.get("HFL_CUDNN_BENCHMARK", "1") != "0":
+# On an 8-rank box the search (8 processes timing ~400 conv configurations each while they also capture graphs) took
+# 180 s of start-up against 5 s on one GPU, and the 8-GPU round is bound by the widest client's sequential chain where
+# the tuned kernels gain little (252 vs 271 ms): default off from 8 ranks up, `HFL_CUDNN_BENCHMARK=1` forces it.
+_default_bench = "0" if int(os.environ.get("WORLD_SIZE", "1") or 1) >= 8 else "1"
+if os.environ.get("HFL_CUDNN_BENCHMARK", _default_bench) != "0":
     torch.backends.cudnn.benchmark = True
 
 # backward convolutions on the tcgen05 kernels: "off" | "on" (dgrad + wgrad) | "wgrad" (weight gradient only)
