@@ -18,12 +18,13 @@ def _cfg(control=CONTROL, rounds=2, **kw):
     return cfg
 
 
-def _run(rank, world, port, out_dir, control, ret):
+def _run(rank, world, port, out_dir, control, ret, fault_drop=0.0):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
     from hfl_b200.parallel.dist import init_distributed, shutdown
     info = init_distributed("cpu")
-    eng = Engine(_cfg(control), info, options=EngineOptions(out_dir=out_dir, quiet=True, save=(rank == 0)))
+    eng = Engine(_cfg(control), info, options=EngineOptions(out_dir=out_dir, quiet=True, save=(rank == 0),
+                                                           fault_drop=fault_drop))
     eng.fit()
     if rank == 0:
         torch.save({"arena": eng.global_arena.clone(), "hist": dict(eng.logger.history)}, ret)
@@ -42,6 +43,26 @@ def test_gloo_two_ranks_match_single(tmp_path, control):
     assert torch.allclose(got["arena"], single.global_arena, atol=1e-5, rtol=1e-4)
     for k, v in single.logger.history.items():
         assert got["hist"][k] == pytest.approx(v, rel=1e-4, abs=1e-5), k
+
+
+def test_fault_injection_is_rank_consistent(tmp_path):
+    """Lost clients are drawn identically on every rank: two gloo ranks with fault_drop reproduce the single-process
+    run with the same drop probability (the shared-seed contract that replaces a broadcast of the survivor list)."""
+    control = "1_10_0.5_non-iid-2_dynamic_a1-c1-e1_bn_1_1"
+    single = Engine(_cfg(control), options=EngineOptions(out_dir=str(tmp_path / "s"), quiet=True, fault_drop=0.4))
+    single.fit()
+    ret = str(tmp_path / "ret.pt")
+    port = 29910 + (os.getpid() % 80)
+    mp.spawn(_run, args=(2, port, str(tmp_path / "d"), control, ret, 0.4), nprocs=2, join=True)
+    got = torch.load(ret, weights_only=False)
+    assert torch.allclose(got["arena"], single.global_arena, atol=1e-5, rtol=1e-4)
+
+
+def test_supervisor_resume_flag_rewrite():
+    from hfl_b200.cli.supervise import with_resume
+    assert with_resume(["python", "t.py", "--x", "1"]) == ["python", "t.py", "--x", "1", "--resume_mode", "1"]
+    assert with_resume(["t.py", "--resume_mode", "0", "--y"]) == ["t.py", "--y", "--resume_mode", "1"]
+    assert with_resume(["t.py", "--resume_mode=2"]) == ["t.py", "--resume_mode", "1"]
 
 
 def test_checkpoint_resume_roundtrip(tmp_path):
