@@ -34,6 +34,8 @@ void hfl_multi_sgd_clip_step(const void*, const void*, int, float*, void*, float
 int hfl_gemm_bf16_tn(const void*, int, const void*, int, void*, int, int, const float*, const void*, float, int, int,
                      int, int, cudaStream_t);
 void hfl_gemm_timing(long long*);
+int hfl_conv_halo_supported(int, int, int, int, int, int, int, int);
+int hfl_conv_halo_fprop(const void*, const void*, void*, const void*, float*, int, int, int, int, int, cudaStream_t);
 int hfl_conv_direct_supported(int, int, int, int, int, int, int, int);
 int hfl_conv_direct_fprop(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t);
 int hfl_conv_direct_dgrad(const void*, const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t);
@@ -698,6 +700,35 @@ torch::Tensor conv_direct_wgrad(torch::Tensor dy, torch::Tensor x, int64_t R, in
   return dw.permute({0, 3, 1, 2});
 }
 
+
+// ---- halo-reusing 3x3 convolution (csrc/conv_halo_tcgen05.cu; experimental, HFL_CONV_HALO=1) -----------------------
+bool conv_halo_supported(int64_t N, int64_t H, int64_t W, int64_t C, int64_t K, int64_t R, int64_t S, int64_t stride) {
+  return hfl_conv_halo_supported((int)N, (int)H, (int)W, (int)C, (int)K, (int)R, (int)S, (int)stride) == 0;
+}
+
+torch::Tensor conv_halo_fprop(torch::Tensor x, torch::Tensor w, c10::optional<torch::Tensor> residual,
+                              c10::optional<torch::Tensor> stats) {
+  CHECK_CUDA_T(x); CHECK_CUDA_T(w);
+  TORCH_CHECK(x.dim() == 4 && w.dim() == 4 && x.scalar_type() == torch::kBFloat16 && w.scalar_type() == torch::kBFloat16);
+  TORCH_CHECK(x.is_contiguous(torch::MemoryFormat::ChannelsLast) && w.permute({0, 2, 3, 1}).is_contiguous());
+  const int N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3), K = w.size(0);
+  TORCH_CHECK(w.size(1) == C && w.size(2) == 3 && w.size(3) == 3);
+  TORCH_CHECK(hfl_conv_halo_supported(N, H, W, C, K, 3, 3, 1) == 0, "conv_halo_fprop: unsupported problem");
+  c10::cuda::CUDAGuard guard(x.device());
+  auto y = torch::empty({N, K, H, W}, x.options().memory_format(torch::MemoryFormat::ChannelsLast));
+  const void* rp = nullptr;
+  if (residual.has_value()) {
+    TORCH_CHECK(residual->sizes() == y.sizes() && residual->is_contiguous(torch::MemoryFormat::ChannelsLast) &&
+                residual->scalar_type() == torch::kBFloat16);
+    rp = residual->data_ptr();
+  }
+  float* sp = nullptr;
+  if (stats.has_value()) { TORCH_CHECK(stats->scalar_type() == torch::kFloat32 && stats->numel() == 2 * K && stats->is_contiguous()); sp = stats->data_ptr<float>(); }
+  int e = hfl_conv_halo_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), rp, sp, N, H, W, C, K, cur_stream());
+  TORCH_CHECK(e == 0, "conv_halo_fprop failed with code ", e);
+  return y;
+}
+
 // ---- peer memory runtime (cudaMalloc + CUDA IPC) ---------------------------------------------------------
 int64_t peer_alloc(int64_t bytes) {
   void* p = nullptr;
@@ -760,6 +791,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("out_fp32"), py::arg("bias_inside") = false, py::arg("out") = py::none());
   m.def("gemm_bf16_general", &gemm_bf16_general);
   m.def("gemm_timing", []() { std::vector<long long> v(16); hfl_gemm_timing(v.data()); return v; });
+  m.def("conv_halo_supported", &conv_halo_supported);
+  m.def("conv_halo_fprop", &conv_halo_fprop);
   m.def("conv_direct_supported", &conv_direct_supported);
   m.def("conv_direct_fprop", &conv_direct_fprop);
   m.def("conv_direct_dgrad", &conv_direct_dgrad);

@@ -146,9 +146,26 @@ def _direct_conv_ok(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> 
     return bool(cu.C().conv_direct_supported(N, H, W, C, K, R, S, stride))
 
 
+# EXPERIMENTAL halo-reusing tcgen05 convolution (csrc/conv_halo_tcgen05.cu): "0" (default) | "1"
+CONV_HALO_MODE = os.environ.get("HFL_CONV_HALO", "0")
+
+
+def _halo_conv_ok(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> bool:
+    if CONV_HALO_MODE != "1" or not _use_kernels(x) or w.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
+        return False
+    if stride != 1 or pad != 1 or tuple(w.shape[2:]) != (3, 3):
+        return False
+    if not (x.is_contiguous(memory_format=torch.channels_last) and w.permute(0, 2, 3, 1).is_contiguous()):
+        return False
+    N, C, H, W = x.shape
+    return bool(cu.C().conv_halo_supported(N, H, W, C, w.shape[0], 3, 3, 1))
+
+
 def conv_fwd(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> torch.Tensor:
     if _direct_conv_ok(x, w, stride, pad):
         return cu.C().conv_direct_fprop(x, w, None, stride)
+    if _halo_conv_ok(x, w, stride, pad):
+        return cu.C().conv_halo_fprop(x, w, None, None)
     if _tc_conv_ok(x, w, stride, pad):
         return cu.C().conv_fprop_tc(x, w, None, None, stride)
     return F.conv2d(x, w, None, stride, pad)
