@@ -153,6 +153,15 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        comm = {}
+        try:      # aggregate GB/s vs the NVLink / HBM roofline for the last timed round (BASELINE.json's second metric)
+            from hfl_b200.utils.commstats import aggregate_traffic
+            lv = [eng.tables.level_id(float(r)) for r in last["rates"]]
+            comm = aggregate_traffic([l.size for l in eng.tables.level_layouts], lv, eng.tables.global_layout.size,
+                                     info.world, float(last["timings_ms"].get("aggregate", 0.0)),
+                                     float(peaks.get("hbm_gbs") or 0.0))
+        except Exception as e:      # never let the side metric break the benchmark line
+            comm = {"error": repr(e)}
         line = {
             "metric": "federated_train_samples_per_sec", "value": samples / (ms / 1e3), "unit": "samples/s",
             "rounds_per_sec": args.steps / (ms / 1e3), "n_gpus": info.world, "steps": args.steps,
@@ -171,6 +180,7 @@ def run_ours(args):
             "e2e": {"value": samples_e / (ms_e / 1e3), "unit": "samples/s", "rounds_per_sec": args.steps / (ms_e / 1e3),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
+            "aggregate_comm": comm,
             "last_round": {"train": last["train"], "test": last.get("test"), "timings_ms": last["timings_ms"]},
             "measured_peaks": {k: peaks.get(k) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained")},
         }

@@ -119,3 +119,12 @@ def test_process_control_matches_reference(ref, data, model, control):
         assert cfg[k] == rcfg[k], k
     if control.split("_")[4] == "dynamic":
         assert cfg["proportion"] == pytest.approx(rcfg["proportion"])
+
+
+def test_aggregate_traffic_summary():
+    from hfl_b200.utils.commstats import aggregate_traffic
+    r = aggregate_traffic([1000, 250], [0, 1, 1], 1000, 1, 0.5, hbm_gbs=6478.0)
+    assert r["client_bytes"] == 4 * 1500 and r["publish_bytes"] == 4000 and "hbm_roofline_frac" in r
+    r8 = aggregate_traffic([1000, 250], [0, 1, 1], 1000, 8, 1.0)
+    assert r8["publish_bytes"] == 32000 and 0 < r8["nvlink_roofline_frac"] < 1
+    assert "gbs" not in aggregate_traffic([10], [0], 10, 2, 0.0)
