@@ -641,6 +641,11 @@ class Engine:
                          "Learning rate: {}".format(res["lr"]),
                          "Round time: {:.3f}s".format(dt),
                          "Experiment Finished Time: {:.0f}s".format(left)]}
+        tms = res.get("timings_ms") or {}
+        if tms:     # observability beyond the reference's wall-clock ETA: per-phase device time and throughput
+            info["info"].append("Phases(ms): " + " ".join("{}={:.1f}".format(k, v) for k, v in tms.items()))
+            if dt > 0:
+                info["info"].append("Samples/s: {:.0f}".format(res["train_n"] / dt))
         lg.append(info, "train", mean=False)
         quiet = self.opt.quiet or not self.info.is_main
         lg.write("train", names["train"]["Local"], quiet=quiet)
