@@ -1,5 +1,4 @@
 """Correctness + throughput of the cluster/multicast GEMM (csrc/gemm_mc_tcgen05.cu) vs the single-CTA kernel and cuBLAS."""
-import json
 import os
 import sys
 
