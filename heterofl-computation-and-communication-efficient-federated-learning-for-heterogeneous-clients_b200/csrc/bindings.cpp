@@ -75,6 +75,12 @@ int hfl_gemm_general_splits(int, int, int);
 int hfl_conv_dgrad_tc(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, cudaStream_t);
 int hfl_conv_wgrad_tc_supported(int, int, int, int, int, int, int, int);
 int hfl_conv_wgrad_tc(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int hfl_mega_phase_bytes();
+int hfl_mega_smem_bytes();
+int hfl_mega_max_grid();
+int hfl_mega_launch(const void*, int, int, void*, const int*, int, cudaStream_t);
+int hfl_mega_encode_tmap(void*, const void*, int, const unsigned long long*, const unsigned long long*, const unsigned*,
+                         const unsigned*);
 long hfl_launch_count();
 void hfl_launch_count_add(long);
 void hfl_peer_barrier(const void*, int, int, unsigned, int*, cudaStream_t);
@@ -771,6 +777,41 @@ void peer_barrier(torch::Tensor flag_ptrs, int64_t rank, int64_t world, int64_t 
   check_launch();
 }
 
+
+// ---- resident client-training megakernel (csrc/mega_kernel.cu) ------------------------------------------
+void mega_launch(torch::Tensor prog, int64_t nphase, int64_t nsteps, torch::Tensor ctl,
+                 c10::optional<torch::Tensor> nvalid_tab, int64_t grid) {
+  CHECK_CUDA_T(prog); CHECK_CUDA_T(ctl); CHECK_CONTIG(prog);
+  TORCH_CHECK(prog.scalar_type() == torch::kUInt8 && prog.numel() >= nphase * hfl_mega_phase_bytes());
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(prog.data_ptr()) & 63) == 0, "mega program must be 64-byte aligned");
+  TORCH_CHECK(ctl.scalar_type() == torch::kInt32 && ctl.numel() >= 16);
+  const int* nv = nullptr;
+  if (nvalid_tab.has_value()) {
+    CHECK_CUDA_T(*nvalid_tab);
+    TORCH_CHECK(nvalid_tab->scalar_type() == torch::kInt32 && nvalid_tab->numel() >= nsteps && nvalid_tab->is_contiguous());
+    nv = nvalid_tab->data_ptr<int>();
+  }
+  c10::cuda::CUDAGuard guard(prog.device());
+  int e = hfl_mega_launch(prog.data_ptr(), (int)nphase, (int)nsteps, ctl.data_ptr(), nv, (int)grid, cur_stream());
+  TORCH_CHECK(e == 0, "mega_launch failed with code ", e, " (", cudaGetErrorString((cudaError_t)e), ")");
+}
+
+// 128-byte CUtensorMap (bf16, 128B swizzle, zero OOB fill) for a device pointer; dims/box/estr innermost first
+torch::Tensor mega_encode_tmap(int64_t base_ptr, std::vector<int64_t> dims, std::vector<int64_t> strides_bytes,
+                               std::vector<int64_t> box, std::vector<int64_t> estr) {
+  const int rank = (int)dims.size();
+  TORCH_CHECK(rank >= 2 && rank <= 5 && (int)strides_bytes.size() == rank - 1 && (int)box.size() == rank &&
+              (int)estr.size() == rank);
+  unsigned long long d[5], s[4];
+  unsigned b[5], e[5];
+  for (int i = 0; i < rank; ++i) { d[i] = (unsigned long long)dims[i]; b[i] = (unsigned)box[i]; e[i] = (unsigned)estr[i]; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = (unsigned long long)strides_bytes[i];
+  auto out = torch::empty({128}, torch::dtype(torch::kUInt8));
+  int r = hfl_mega_encode_tmap(out.data_ptr(), reinterpret_cast<const void*>(base_ptr), rank, d, s, b, e);
+  TORCH_CHECK(r == 0, "cuTensorMapEncodeTiled failed with code ", r);
+  return out;
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("aggregate", &aggregate);
   m.def("distribute", &distribute);
@@ -812,6 +853,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv_dgrad_tc", &conv_dgrad_tc);
   m.def("conv_wgrad_tc", &conv_wgrad_tc);
   m.def("conv_wgrad_tc_supported", &conv_wgrad_tc_supported);
+  m.def("mega_launch", &mega_launch);
+  m.def("mega_encode_tmap", &mega_encode_tmap);
+  m.def("mega_phase_bytes", &hfl_mega_phase_bytes);
+  m.def("mega_smem_bytes", &hfl_mega_smem_bytes);
+  m.def("mega_max_grid", &hfl_mega_max_grid);
   m.def("launch_count", &hfl_launch_count);
   m.def("launch_count_add", &hfl_launch_count_add);
   m.def("peer_alloc", &peer_alloc);

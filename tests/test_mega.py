@@ -1,0 +1,298 @@
+"""Resident-training megakernel (csrc/mega_kernel.cu): every phase type against a plain PyTorch fp32 reference, then
+a whole train step / sBN pass / eval pass against the functional model."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from hfl_b200.config.control import make_cfg
+from hfl_b200.models import make_model
+from hfl_b200.models import mega_resnet as mr
+from hfl_b200.ops import cuda as cu
+from hfl_b200.ops.nn import NormCtx
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _run(prog, grid=32, nsteps=1, nvalid=None):
+    pd = prog.finalize(DEV)
+    ctl = torch.zeros(mr.CTL_WORDS, dtype=torch.int32, device=DEV)
+    cu.C().mega_launch(pd, len(prog), nsteps, ctl, nvalid, grid)
+    torch.cuda.synchronize()
+    c = ctl.tolist()
+    assert c[1] == 0, "megakernel aborted: code %d" % c[1]
+    return c
+
+
+def _act(N, H, W, C, Cp=None, scale=1.0):
+    Cp = Cp or mr.rup(C, 8)
+    t = torch.zeros(N, H, W, Cp, dtype=torch.bfloat16, device=DEV)
+    t[..., :C] = (torch.randn(N, H, W, C, device=DEV) * scale).to(torch.bfloat16)
+    return t
+
+
+def _filt(K, R, C, Cp=None):
+    Cp = Cp or mr.rup(C, 8)
+    w = torch.zeros(K, R * R, Cp, dtype=torch.bfloat16, device=DEV)
+    w[..., :C] = (torch.randn(K, R * R, C, device=DEV) * (1.0 / (R * R * C) ** 0.5)).to(torch.bfloat16)
+    return w
+
+
+def _w_nchw(w, K, R, C):
+    return w[..., :C].reshape(K, R, R, C).permute(0, 3, 1, 2).float()
+
+
+def _nchw(t, C):
+    return t[..., :C].permute(0, 3, 1, 2).float()
+
+
+def _close(a, b, tol):
+    err = (a.float() - b.float()).abs().max().item()
+    ref = b.float().abs().max().item() + 1e-6
+    assert err <= tol * ref, "max err %.4g vs ref scale %.4g" % (err, ref)
+
+
+FPROP_CASES = [
+    # N, H, Cin, Cout, R, stride
+    (10, 32, 64, 64, 3, 1), (10, 32, 64, 128, 3, 2), (10, 32, 64, 128, 1, 2), (10, 16, 128, 128, 3, 1),
+    (10, 8, 256, 512, 3, 2), (10, 4, 512, 512, 3, 1), (10, 32, 3, 64, 3, 1), (10, 32, 4, 4, 3, 1),
+    (10, 16, 8, 16, 3, 2), (7, 8, 32, 32, 3, 1), (20, 4, 64, 64, 3, 1),
+]
+
+
+@pytest.mark.parametrize("N,H,Cin,Cout,R,stride", FPROP_CASES)
+def test_conv_fprop(N, H, Cin, Cout, R, stride):
+    torch.manual_seed(1)
+    x, w = _act(N, H, H, Cin), _filt(Cout, R, Cin)
+    OH = H // stride
+    out = torch.zeros(N, OH, OH, mr.rup(Cout, 8), dtype=torch.bfloat16, device=DEV)
+    res = _act(N, OH, OH, Cout)
+    stats = torch.zeros(2 * out.shape[3], dtype=torch.float32, device=DEV)
+    prog = mr.Program()
+    wd = mr.WDesc(w.data_ptr(), Cout, R * R, Cin, w.shape[2])
+    mr.conv_fprop(prog, x, wd, out, R, stride, res=res, stats=stats)
+    _run(prog)
+    ref = F.conv2d(_nchw(x, Cin), _w_nchw(w, Cout, R, Cin), None, stride, R // 2) + _nchw(res, Cout)
+    _close(_nchw(out, Cout), ref, 2e-2)
+    assert out[..., Cout:].abs().max().item() == 0 if out.shape[3] > Cout else True
+    o = out[..., :Cout].float().reshape(-1, Cout)
+    _close(stats[:Cout], o.sum(0), 2e-3)
+    _close(stats[out.shape[3]:out.shape[3] + Cout], (o * o).sum(0), 2e-3)
+
+
+@pytest.mark.parametrize("N,H,C,K,R,stride,sc", [
+    (10, 32, 64, 64, 3, 1, False), (10, 16, 128, 128, 3, 1, False), (10, 4, 512, 512, 3, 1, False),
+    (10, 32, 64, 128, 3, 2, True), (10, 8, 256, 512, 3, 2, True), (10, 32, 64, 128, 3, 2, False),
+    (10, 32, 4, 4, 3, 1, False), (10, 32, 8, 16, 3, 2, True), (10, 16, 32, 32, 1, 1, False)])
+def test_conv_dgrad(N, H, C, K, R, stride, sc):
+    torch.manual_seed(2)
+    OH = H // stride
+    dy, w = _act(N, OH, OH, K), _filt(K, R, C)
+    dx = torch.zeros(N, H, H, mr.rup(C, 8), dtype=torch.bfloat16, device=DEV)
+    prog = mr.Program()
+    wd = mr.WDesc(w.data_ptr(), K, R * R, C, w.shape[2])
+    ref = torch.nn.grad.conv2d_input((N, C, H, H), _w_nchw(w, K, R, C), _nchw(dy, K), stride, R // 2)
+    if sc:
+        dy2, w2 = _act(N, OH, OH, K), _filt(K, 1, C)
+        mr.conv_dgrad(prog, dy, wd, dx, R, stride, dy2=dy2, w2=mr.WDesc(w2.data_ptr(), K, 1, C, w2.shape[2]))
+        ref = ref + torch.nn.grad.conv2d_input((N, C, H, H), _w_nchw(w2, K, 1, C), _nchw(dy2, K), stride, 0)
+    else:
+        mr.conv_dgrad(prog, dy, wd, dx, R, stride)
+    _run(prog)
+    _close(_nchw(dx, C), ref, 2e-2)
+
+
+@pytest.mark.parametrize("N,H,C,K,R,stride", [
+    (10, 32, 64, 64, 3, 1), (10, 32, 64, 128, 3, 2), (10, 32, 64, 128, 1, 2), (10, 16, 128, 128, 3, 1),
+    (10, 8, 256, 256, 3, 1), (10, 4, 512, 512, 3, 1), (10, 32, 3, 64, 3, 1), (10, 32, 4, 4, 3, 1), (10, 8, 16, 32, 3, 2)])
+def test_conv_wgrad(N, H, C, K, R, stride):
+    torch.manual_seed(3)
+    OH = H // stride
+    x, dy = _act(N, H, H, C), _act(N, OH, OH, K, scale=0.1)
+    dW = torch.zeros(K, R * R, C, dtype=torch.float32, device=DEV)
+    prog = mr.Program()
+    mr.conv_wgrad(prog, dy, x, dW.data_ptr(), K, C, R, stride, target_items=64, sync=1)
+    _run(prog)
+    ref = torch.nn.grad.conv2d_weight(_nchw(x, C), (K, C, R, R), _nchw(dy, K), stride, R // 2)
+    _close(dW.reshape(K, R, R, C).permute(0, 3, 1, 2), ref, 1e-2)
+
+
+def test_norm_phases():
+    torch.manual_seed(4)
+    N, H, C = 10, 8, 32
+    y = _act(N, H, H, C, scale=2.0)
+    z = torch.zeros_like(y)
+    gam = (1 + 0.2 * torch.randn(C, device=DEV)).to(torch.bfloat16)
+    bet = (0.2 * torch.randn(C, device=DEV)).to(torch.bfloat16)
+    yf = y.float().reshape(-1, C)
+    S = torch.cat([yf.sum(0), (yf * yf).sum(0)]).contiguous()
+    eps = 1e-5
+    prog = mr.Program()
+    mr.norm_apply(prog, y, z, C, stats=S, gamma=gam.data_ptr(), beta=bet.data_ptr(), eps=eps)
+    dz = _act(N, H, H, C, scale=0.1)
+    dres = _act(N, H, H, C, scale=0.1)
+    dy = torch.zeros_like(y)
+    T = torch.zeros(2 * C, dtype=torch.float32, device=DEV)
+    dga = torch.zeros(C, dtype=torch.float32, device=DEV)
+    dbe = torch.zeros(C, dtype=torch.float32, device=DEV)
+    mr.norm_bwd(prog, y, dz, dy, C, stats=S, gamma=gam.data_ptr(), beta=bet.data_ptr(), T=T, dgamma=dga.data_ptr(),
+                dbeta=dbe.data_ptr(), eps=eps, dres=dres, use_nvalid=0)
+    _run(prog, grid=8)
+    yr = yf.clone().requires_grad_()
+    zr = F.relu(F.batch_norm(yr, None, None, gam.float(), bet.float(), True, 0.0, eps))
+    _close(z.reshape(-1, C), zr, 1e-2)
+    gr = torch.autograd.grad(zr, yr, dz.float().reshape(-1, C))[0] + dres.float().reshape(-1, C)
+    _close(dy.reshape(-1, C), gr, 2e-2)
+    gp = gam.float().clone().requires_grad_()
+    bp = bet.float().clone().requires_grad_()
+    z2 = F.relu(F.batch_norm(yf, None, None, gp, bp, True, 0.0, eps))
+    z2.backward(dz.float().reshape(-1, C))
+    _close(dga, gp.grad, 1e-2)
+    _close(dbe, bp.grad, 1e-2)
+
+
+def _setup(rate, scale=1, mask=1):
+    cfg = make_cfg("CIFAR10", "resnet18", "1_10_0.5_iid_fix_a1-c1_bn_%d_%d" % (scale, mask), classes_size=10)
+    model = make_model(cfg, rate, channels_last=True)
+    torch.manual_seed(0)
+    arena = model.new_arena("cpu", torch.float32)
+    for k, v in model.layout.views(arena).items():
+        if ".n" in k or k.startswith("n4"):
+            v.add_(torch.randn_like(v) * 0.2)
+    return cfg, model, arena
+
+
+def _train_state(model, arena, n_img, steps, B, lr=0.05):
+    n = model.layout.size
+    w = arena.to(DEV)
+    st = dict(w=w, wc=w.to(torch.bfloat16), g=torch.zeros(n, device=DEV), mom=torch.zeros(n, device=DEV),
+              src=torch.randint(0, 256, (n_img, 32, 32, 3), dtype=torch.uint8, device=DEV),
+              labels=torch.randint(0, 10, (n_img,), device=DEV),
+              idx=torch.stack([torch.randperm(n_img)[:B] for _ in range(steps)]).to(DEV),
+              par=torch.cat([torch.randint(0, 9, (steps, B, 2)), torch.randint(0, 2, (steps, B, 1))], 2).int().to(DEV),
+              mean=torch.tensor([0.49, 0.48, 0.45], device=DEV), istd=1.0 / torch.tensor([0.25, 0.24, 0.26], device=DEV),
+              mask=torch.ones(10, dtype=torch.uint8, device=DEV), meter=torch.zeros(4, dtype=torch.float64, device=DEV),
+              lr=lr, momentum=0.9, wd=5e-4, max_norm=1.0)
+    return st
+
+
+def _ref_batch(st, step, B, nv):
+    """the augmented batch of `step` as fp64 NCHW (torch re-implementation of the PREP phase)"""
+    idx, par = st["idx"][step, :nv].cpu(), st["par"][step, :nv].cpu()
+    src = st["src"].cpu()
+    x = torch.zeros(nv, 3, 32, 32, dtype=torch.float64)
+    mean, istd = st["mean"].cpu().double(), st["istd"].cpu().double()
+    for b in range(nv):
+        img = src[idx[b]].double() / 255.0
+        pad = torch.zeros(40, 40, 3, dtype=torch.float64)
+        pad[4:36, 4:36] = img
+        dy, dx, fl = [int(v) for v in par[b]]
+        crop = pad[dy:dy + 32, dx:dx + 32]
+        if fl:
+            crop = crop.flip(1)
+        x[b] = ((crop - mean) * istd).permute(2, 0, 1)
+    return x.to(torch.bfloat16).double(), st["labels"][idx.to(DEV)].cpu()
+
+
+@pytest.mark.parametrize("rate,nv", [(1.0, 10), (0.25, 10), (0.0625, 7), (0.5, 10)])
+def test_train_step_gradients(rate, nv):
+    cfg, model, arena = _setup(rate)
+    B = 10
+    st = _train_state(model, arena, 64, 1, B)
+    st["mask"][[0, 5]] = 0
+    st["labels"].clamp_(1, 4)
+    net = mr.MegaResNet(model, DEV, 32)
+    prog = net.build_train(st, B, with_opt=False)
+    nvt = torch.tensor([nv], dtype=torch.int32, device=DEV)
+    _run(prog, grid=32, nvalid=nvt)
+    # fp64 reference on the bf16-rounded weights and batch
+    P = {k: v.detach().double().requires_grad_() for k, v in model.layout.views(st["wc"].float().cpu()).items()}
+    x, y = _ref_batch(st, 0, B, nv)
+    out = model.forward(P, {"img": x, "label": y}, NormCtx("train"), st["mask"].cpu())
+    out["loss"].backward()
+    loss = st["loss"][0].item()
+    assert abs(loss - out["loss"].item()) < 3e-2 * max(1.0, abs(out["loss"].item())), (loss, out["loss"].item())
+    G = model.layout.views(st["g"].cpu())
+    bad = []
+    for k in P:
+        a, b = G[k].double().flatten(), P[k].grad.flatten()
+        cos = (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+        rel = ((a - b).norm() / (b.norm() + 1e-12)).item()
+        if not (cos > 0.97 and rel < 0.25):
+            bad.append((k, round(cos, 4), round(rel, 4)))
+    assert not bad, bad
+    m = st["meter"].tolist()
+    assert m[2] == nv and abs(m[0] / nv - out["loss"].item()) < 3e-2 * max(1.0, out["loss"].item())
+
+
+@pytest.mark.parametrize("rate", [1.0, 0.125])
+def test_train_two_steps_update(rate):
+    """full program incl. clip + SGD over 2 steps == torch loop on the same batches (weights after the steps)"""
+    cfg, model, arena = _setup(rate)
+    B, steps = 10, 2
+    st = _train_state(model, arena, 64, steps, B)
+    net = mr.MegaResNet(model, DEV, 32)
+    prog = net.build_train(st, B)
+    w0 = st["w"].clone().cpu()
+    _run(prog, grid=32, nsteps=steps, nvalid=torch.full((steps,), B, dtype=torch.int32, device=DEV))
+    w = w0.double().clone()
+    mom = torch.zeros_like(w)
+    for s in range(steps):
+        wc = w.float().to(torch.bfloat16).double()
+        P = {k: v.detach().requires_grad_() for k, v in model.layout.views(wc).items()}
+        x, y = _ref_batch(st, s, B, B)
+        out = model.forward(P, {"img": x, "label": y}, NormCtx("train"), st["mask"].cpu())
+        out["loss"].backward()
+        g = torch.zeros_like(w)
+        for k, v in model.layout.views(g).items():
+            v.copy_(P[k].grad)
+        coef = min(1.0, 1.0 / (g.norm().item() + 1e-6))
+        gg = g * coef + 5e-4 * w
+        mom = 0.9 * mom + gg
+        w = w - st["lr"] * mom
+    dw_ref = (w - w0.double())
+    dw = (st["w"].cpu().double() - w0.double())
+    cos = (dw @ dw_ref / (dw.norm() * dw_ref.norm())).item()
+    assert cos > 0.98, cos
+    assert abs(dw.norm().item() / dw_ref.norm().item() - 1) < 0.05
+    assert torch.equal(st["wc"].cpu(), st["w"].cpu().to(torch.bfloat16))
+    assert st["g"].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("rate", [1.0, 0.0625])
+def test_stats_and_eval_programs(rate):
+    cfg, model, arena = _setup(rate)
+    n = model.layout.size
+    N, gn = 40, 10
+    w = arena.to(DEV)
+    src = torch.randint(0, 256, (N, 32, 32, 3), dtype=torch.uint8, device=DEV)
+    base = dict(w=w, wc=w.to(torch.bfloat16), src=src, idx=torch.arange(N, device=DEV).view(1, N),
+                mean=torch.tensor([0.49, 0.48, 0.45], device=DEV), istd=1.0 / torch.tensor([0.25, 0.24, 0.26], device=DEV))
+    net = mr.MegaResNet(model, DEV, 32)
+    st = dict(base)
+    prog = net.build_forward(st, N, "stats", gn)
+    _run(prog, grid=32, nvalid=torch.tensor([N], dtype=torch.int32, device=DEV))
+    x = ((src.float() / 255.0 - base["mean"]) * base["istd"]).permute(0, 3, 1, 2).to(torch.bfloat16).float().cpu()
+    P = model.layout.views(base["wc"].float().cpu())
+    ctx = NormCtx("stats", group=gn)
+    with torch.no_grad():
+        model.forward(P, {"img": x}, ctx, None, want_score="raw")
+    ctx.n_groups = N // gn
+    run = ctx.finalize()
+    for name, C in net.norm_sites():
+        am, av = st["acc"][name]
+        _close(am[:C].cpu() / (N // gn), run[name][0], 3e-2)
+        _close(av[:C].cpu() / (N // gn), run[name][1], 5e-2)
+    # eval with those running statistics
+    st2 = dict(base)
+    prog2 = net.build_forward(st2, N, "eval")
+    for name, C in net.norm_sites():
+        rm, rv = run[name]
+        a = P[name + ".weight"].float() * torch.rsqrt(rv.float() + 1e-5)
+        b = P[name + ".bias"].float() - rm.float() * a
+        st2["affine"][name][0][:C].copy_(a)
+        st2["affine"][name][1][:C].copy_(b)
+    _run(prog2, grid=32)
+    with torch.no_grad():
+        ref = model.forward(P, {"img": x}, NormCtx("eval", running=run), None, want_score="raw")["logits"]
+    _close(st2["logits"].cpu(), ref, 5e-2)
