@@ -58,13 +58,27 @@ def save(obj, path, protocol: int = 2, mode: str = "torch") -> None:
     d = os.path.dirname(path)
     if d:
         os.makedirs(d, exist_ok=True)
+    # write-then-rename: a kill during the write must never truncate the only resume point (cli/supervise.py restarts
+    # from this file); os.replace is atomic on POSIX
+    tmp = path + ".tmp"
     if mode == "torch":
         with compat_modules():
-            torch.save(obj, path, pickle_protocol=protocol)
+            torch.save(obj, tmp, pickle_protocol=protocol)
+        os.replace(tmp, path)
     elif mode == "numpy":
-        np.save(path, obj, allow_pickle=True)
+        with open(tmp, "wb") as f:
+            np.save(f, obj, allow_pickle=True)
+        os.replace(tmp, path)
     else:
         raise ValueError("Not valid save mode")
+
+
+def atomic_copy(src: str, dst: str) -> None:
+    """Copy ``src`` over ``dst`` without ever exposing a partially written ``dst``."""
+    import shutil
+    tmp = dst + ".tmp"
+    shutil.copy(src, tmp)
+    os.replace(tmp, dst)
 
 
 def load(path, mode: str = "torch"):

@@ -43,7 +43,9 @@ def build_parser(script: str) -> argparse.ArgumentParser:
         else:
             ap.add_argument("--" + k, default=v, type=type(v))
     ap.add_argument("--control_name", default=None, type=str)
-    ap.add_argument("--synthetic", default="auto", type=str)
+    # like the reference, a missing dataset is an error by default: synthetic data must be asked for (--synthetic 1;
+    # "auto" = fall back with a loud warning, recorded as cfg["synthetic_data"])
+    ap.add_argument("--synthetic", default="0", type=str)
     ap.add_argument("--out_dir", default="./output", type=str)
     ap.add_argument("--compute_dtype", default="auto", type=str)
     ap.add_argument("--max_concurrent", default=16, type=int)

@@ -928,6 +928,9 @@ static int mega_configure() {
   static int configured = -1;
   if (configured < 0) {
     cudaError_t e = cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
+    // two CTAs per SM (2 x ~100 KB): ask for the largest shared-memory carve-out
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(mega_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = (e == cudaSuccess) ? 0 : (int)e;
   }
   return configured;

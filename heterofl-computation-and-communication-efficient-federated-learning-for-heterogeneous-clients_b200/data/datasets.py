@@ -238,6 +238,7 @@ def fetch_dataset(cfg: Dict, root: str = "./data") -> Dict[str, object]:
     if not sizes and os.environ.get("HFL_SYNTH_SIZES"):          # "train,test" override for smoke tests
         a, b = os.environ["HFL_SYNTH_SIZES"].split(",")
         sizes = {"train": int(a), "test": int(b)}
+    origin = {}
     for split in ("train", "test"):
         if name in DATA_SIZES:
             got = None
@@ -250,6 +251,7 @@ def fetch_dataset(cfg: Dict, root: str = "./data") -> Dict[str, object]:
                                         torch.from_numpy(tgt).long(), int(tgt.max()) + 1, mean, std)
             elif synth in (True, "auto"):
                 out[split] = synth_vision(name, split, sizes.get(split), cfg.get("init_seed", 0))
+                origin[split] = "synthetic"
             else:
                 raise FileNotFoundError("no data for %s under %s and synthetic data disabled" % (name, droot))
         elif name in LM_SIZES:
@@ -262,10 +264,22 @@ def fetch_dataset(cfg: Dict, root: str = "./data") -> Dict[str, object]:
             elif synth in (True, "auto"):
                 out[split] = synth_lm(name, split, sizes.get(split), cfg.get("synthetic_vocab"),
                                       cfg.get("init_seed", 0))
+                origin[split] = "synthetic"
             else:
                 raise FileNotFoundError("no data for %s under %s and synthetic data disabled" % (name, droot))
         else:
             raise ValueError("Not valid dataset name")
+        origin.setdefault(split, "real")
+    kinds = set(origin.values())
+    if len(kinds) > 1:
+        raise FileNotFoundError("refusing to mix real and synthetic splits of %s (%s); pass --synthetic 1 or provide "
+                                "both splits under %s" % (name, origin, droot))
+    cfg["synthetic_data"] = kinds == {"synthetic"}
+    if cfg["synthetic_data"] and synth == "auto":
+        import warnings
+        warnings.warn("%s not found under %s: training on SYNTHETIC data of the same shape (results are not %s "
+                      "results; recorded as cfg['synthetic_data']=True in checkpoints)" % (name, droot, name),
+                      stacklevel=2)
     return out
 
 

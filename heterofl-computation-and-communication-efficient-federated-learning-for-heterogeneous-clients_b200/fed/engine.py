@@ -172,7 +172,7 @@ class Engine:
         if self.info.world == 1:
             return "local"
         if b == "auto":
-            b = "p2p" if self.is_cuda else "allreduce"
+            b = "p2p" if (self.is_cuda and self._peer_ok()) else "allreduce"
         if b == "p2p":
             from ..parallel.peer import PeerPool
             need = self._round_arena_bytes()
@@ -187,6 +187,18 @@ class Engine:
             from ..parallel.dist import set_peer_pool
             set_peer_pool(self._peer)       # sBN statistic merge goes over peer memory too (fp32 vectors)
         return b
+
+    def _peer_ok(self) -> bool:
+        """P2P aggregation needs every rank on ONE node with peer access between all local GPUs."""
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", self.info.world) or self.info.world)
+        if local_world != self.info.world:
+            return False
+        try:
+            n = torch.cuda.device_count()
+            me = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            return all(torch.cuda.can_device_access_peer(me, j) for j in range(min(n, self.info.world)) if j != me)
+        except Exception:
+            return False
 
     def _round_arena_bytes(self) -> int:
         n_act = int(np.ceil(self.cfg["frac"] * self.cfg["num_users"]))
@@ -621,7 +633,11 @@ class Engine:
             res = self.run_round(ep)
             dt = time.time() - t0
             self._log_round(res, dt)
-            self.sched.step()
+            # ReduceLROnPlateau needs the monitored value (reference passes logger.mean['train/<pivot>'])
+            pm = str(cfg.get("pivot_metric", ""))
+            mean = getattr(self.logger, "mean", {})
+            metric = mean.get("train/" + pm, mean.get("test/" + pm, mean.get("train/Local-Loss")))
+            self.sched.step(metric=metric)
             self.logger.safe(False)
             if self.opt.save and self.info.is_main:
                 self.save_checkpoint(ep + 1, res)
@@ -686,7 +702,7 @@ class Engine:
             better = cur > cfg["pivot"] if cfg["pivot_metric"].endswith("Accuracy") else cur < cfg["pivot"]
             if better:
                 cfg["pivot"] = cur
-                shutil.copy(path, os.path.join(self.opt.out_dir, "model", "%s_best.pt" % cfg["model_tag"]))
+                ckpt.atomic_copy(path, os.path.join(self.opt.out_dir, "model", "%s_best.pt" % cfg["model_tag"]))
         return path
 
     def _resume(self, mode: int, load_tag: str = "checkpoint") -> None:
@@ -696,7 +712,18 @@ class Engine:
             if self.info.is_main and not self.opt.quiet:
                 print("Not exists model tag: {}, start from scratch".format(cfg["model_tag"]))
             return
-        ck = ckpt.load(path)
+        ck = None
+        for cand in (path, os.path.join(self.opt.out_dir, "model", "%s_best.pt" % cfg["model_tag"])):
+            try:
+                ck = ckpt.load(cand)
+                break
+            except Exception as e:      # truncated / corrupt file (e.g. a crash before the atomic-rename fix)
+                if self.info.is_main:
+                    print("Could not load checkpoint {}: {}".format(cand, e))
+        if ck is None:
+            if self.info.is_main:
+                print("No loadable checkpoint for {}, start from scratch".format(cfg["model_tag"]))
+            return
         self.data_split, self.label_split = ck["data_split"], ck["label_split"]
         self.load_state_dict(ck["model_dict"])
         if mode == 1:
