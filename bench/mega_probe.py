@@ -1,6 +1,8 @@
-"""Per-step time of the resident training megakernel by level and grid size (CUDA events, 1 launch = `steps` steps)."""
-import sys
+"""Resident training megakernel probes: us/step by level and grid size, per-phase cycle profile (CTA 0), and the
+aggregate throughput of 10 concurrently training clients (2 per level) -- CUDA events, one launch = all steps."""
 import os
+import sys
+import time
 
 import torch
 
@@ -14,6 +16,11 @@ from hfl_b200.ops import cuda as cu                             # noqa: E402
 from hfl_b200.plan.spec import build_spec                       # noqa: E402
 
 
+def run(slot, imgs, labs, aug, epochs, gen):
+    for _ in slot.train_vision(imgs, labs, aug, epochs, 10, gen):
+        pass
+
+
 def main():
     dev = torch.device("cuda", 0)
     cfg = make_cfg("CIFAR10", "resnet18", "1_100_0.1_non-iid-2_dynamic_a1-b1-c1-d1-e1_bn_1_1", synthetic=True,
@@ -24,32 +31,83 @@ def main():
     aug = VisionAugment(ds["train"], True, dev, torch.bfloat16)
     imgs = ds["train"].img[:500].to(dev)
     labs = ds["train"].target[:500].to(dev)
-    print("max co-resident CTAs:", cu.C().mega_max_grid())
-    grids = {1.0: [16, 32, 48, 64, 96, 128, 148], 0.5: [8, 16, 32, 64, 128], 0.25: [4, 8, 16, 32], 0.125: [2, 4, 8, 16],
-             0.0625: [1, 2, 4, 8]}
-    only = [float(a) for a in sys.argv[1:]] or list(grids)
-    for rate in only:
+    cap = cu.C().mega_max_grid()
+    print("max co-resident CTAs:", cap, flush=True)
+    grids = {1.0: [32, 64, 148], 0.5: [16, 32, 64, 148], 0.25: [8, 16, 32], 0.125: [4, 8, 16], 0.0625: [2, 4, 8]}
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    gen = torch.Generator().manual_seed(1)
+    slots = {}
+    for rate in grids:
+        t0 = time.time()
         model = Model(spec, cfg, rate, True)
-        for grid in grids[rate]:
-            slot = MegaSlot(model, cfg, dev, 10, grid=grid)
-            slot.load_params(model.new_arena(dev))
-            slot.begin_client(0.05, torch.ones(10, dtype=torch.uint8))
-            gen = torch.Generator().manual_seed(1)
-            for _ in slot.train_vision(imgs, labs, aug, 1, 10, gen):     # warm-up launch (50 steps)
-                pass
+        slot = MegaSlot(model, cfg, dev, 10, grid=grids[rate][0])
+        slot.load_params(torch.randn(model.layout.size, device=dev) * 0.05)
+        slot.begin_client(0.05, torch.ones(10, dtype=torch.uint8))
+        run(slot, imgs, labs, aug, 1, gen)
+        torch.cuda.synchronize()
+        slot.check()
+        slots[rate] = slot
+        print("rate %g: slot ready in %.1f s, %d phases, %d barriers" % (rate, time.time() - t0, len(slot.prog),
+                                                                      slot.prog.n_barriers()), flush=True)
+    if what in ("all", "grid"):
+        for rate, slot in slots.items():
+            for grid in grids[rate]:
+                slot.grid = min(grid, cap)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                run(slot, imgs, labs, aug, 2, gen)
+                e1.record()
+                torch.cuda.synchronize()
+                slot.check()
+                print("rate %-7g grid %3d  %.1f us/step" % (rate, slot.grid, 1000.0 * e0.elapsed_time(e1) / 100), flush=True)
+    if what in ("all", "prof"):
+        for rate, grid in ((1.0, 64), (0.0625, 4)):
+            slot = slots[rate]
+            slot.grid = grid
+            slot.prof = torch.zeros(2 * len(slot.prog), dtype=torch.int64, device=dev)
+            run(slot, imgs, labs, aug, 1, gen)
             torch.cuda.synchronize()
-            slot.check()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in slot.train_vision(imgs, labs, aug, 2, 10, gen):     # 100 steps, one launch
-                pass
-            e1.record()
+            pr = slot.prof.view(-1, 2).cpu().double() / 50.0 / 1965.0       # us per step at 1965 MHz
+            slot.prof = None
+            rows = sorted(zip(slot.prog.names, pr[:, 0].tolist(), pr[:, 1].tolist()), key=lambda r: -(r[1] + r[2]))
+            print("== per-phase profile rate %g grid %d: total %.1f us/step (work %.1f, barrier %.1f)" % (
+                rate, grid, float(pr.sum()), float(pr[:, 0].sum()), float(pr[:, 1].sum())))
+            by = {}
+            for nm, a, b in zip(slot.prog.names, pr[:, 0].tolist(), pr[:, 1].tolist()):
+                k = nm.split(".")[-1] if not nm.startswith("sgd") else nm
+                if "dgrad" in nm:
+                    k = "dgrad"
+                by.setdefault(k, [0, 0.0, 0.0])
+                by[k][0] += 1
+                by[k][1] += a
+                by[k][2] += b
+            for k, v in sorted(by.items(), key=lambda kv: -(kv[1][1] + kv[1][2])):
+                print("   %-12s x%3d  work %7.1f us  barrier %7.1f us" % (k, v[0], v[1], v[2]))
+            for nm, a, b in rows[:12]:
+                print("   top %-28s work %6.1f barrier %6.1f" % (nm, a, b))
+    if what in ("all", "conc"):
+        # 10 concurrent clients, 2 per level, grids scaled to the 148-SM budget
+        plan = {1.0: 40, 0.5: 20, 0.25: 8, 0.125: 4, 0.0625: 2}
+        twins = []
+        for rate, g in plan.items():
+            model = Model(spec, cfg, rate, True)
+            s2 = MegaSlot(model, cfg, dev, 10, grid=g)
+            s2.load_params(torch.randn(model.layout.size, device=dev) * 0.05)
+            s2.begin_client(0.05, torch.ones(10, dtype=torch.uint8))
+            slots[rate].grid = g
+            twins += [slots[rate], s2]
+        for rep in range(2):
             torch.cuda.synchronize()
-            slot.check()
-            ms = e0.elapsed_time(e1)
-            print("rate %-7g grid %3d  phases %d  %.1f us/step  loss %.3f" % (
-                rate, grid, len(slot.prog), 1000.0 * ms / 100, slot.metrics()["Local-Loss"]), flush=True)
-            del slot
+            t0 = time.time()
+            for s in twins:
+                with torch.cuda.stream(s.stream):
+                    run(s, imgs, labs, aug, 5 if rep else 1, gen)
+            torch.cuda.synchronize()
+            dt = time.time() - t0
+            for s in twins:
+                s.check()
+            print("10 concurrent clients x %d steps: %.1f ms wall (%.1f us per client-step aggregate)" % (
+                250 if rep else 50, dt * 1e3, dt * 1e6 / (10 * (250 if rep else 50))), flush=True)
 
 
 if __name__ == "__main__":

@@ -30,7 +30,7 @@ namespace hfl {
 namespace mega {
 
 constexpr int MG_THREADS = 256;
-constexpr int MG_STAGES = 3;
+constexpr int MG_STAGES = 6;
 constexpr int MG_A_BYTES = 16384;
 constexpr int MG_STAGE_BYTES = 32768;
 constexpr int MG_SMEM = MG_STAGES * MG_STAGE_BYTES + 1024 + 256;
@@ -70,8 +70,8 @@ __device__ __forceinline__ void grid_sync(unsigned* ctl, unsigned& epoch) {
   __syncthreads();
   if (threadIdx.x == 0) {
     epoch += 1;
-    __threadfence();
-    atomicAdd(ctl + CTL_ARRIVE, 1u);
+    // release: every global write of this CTA (made visible to thread 0 by the bar.sync above) happens-before the add
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctl + CTL_ARRIVE), "r"(1u) : "memory");
     const unsigned target = epoch * gridDim.x;
     const long long t0 = clock64();
     unsigned spins = 0;
@@ -84,7 +84,6 @@ __device__ __forceinline__ void grid_sync(unsigned* ctl, unsigned& epoch) {
         if (clock64() - t0 > 6000000000LL) { atomicExch(ctl + CTL_ABORT, 1u); break; }
       }
     }
-    __threadfence();
   }
   __syncthreads();
   fence_proxy_async();
@@ -466,6 +465,7 @@ __device__ __noinline__ void napply_item(const Phase& P, Ctx& cx, int item) {
   const bf16* Y = reinterpret_cast<const bf16*>(P.pv[0]);
   bf16* Z = reinterpret_cast<bf16*>(P.pv[1]);
   const bool relu = iv[5] != 0;
+#pragma unroll 4
   for (int row = row_lo + r0; row < row_hi; row += rstep) {
     float y[8];
     ld8(Y + (size_t)row * Cp + c0, y);
@@ -501,6 +501,7 @@ __device__ __noinline__ void nbwd_item(const Phase& P, Ctx& cx, int item, bool a
     float sb[8], sg[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { sb[e] = 0.f; sg[e] = 0.f; }
+#pragma unroll 2
     for (int row = row_lo + r0; row < min(row_hi, row_lim); row += rstep) {
       float y[8], dz[8];
       ld8(Y + (size_t)row * Cp + c0, y);
@@ -593,7 +594,7 @@ __device__ __noinline__ void nbwd_item(const Phase& P, Ctx& cx, int item, bool a
 }
 
 // ------------------------------------------------------------------------------------------------------------ OP_HEAD
-// iv: 0 N  1 HW  2 Cp  3 C_real  4 Kc  5 train  9 use_nvalid
+// iv: 0 N  1 HW  2 Cp  3 C_real  4 Kc  5 train  6 step-strided logits (eval)  9 use_nvalid
 // pv: 0 z  1 W (bf16 [Kc][C_real])  2 bias  3 labels (int32)  4 mask (u8)  5 meter (double[4])  6 dW  7 db  8 dz out
 //     9 logits out (fp32 [N][Kc], eval)  10 loss out (float)
 __device__ __noinline__ void head_train(const Phase& P, Ctx& cx) {
@@ -702,7 +703,7 @@ __device__ __noinline__ void head_eval_item(const Phase& P, Ctx& cx, int n) {
   const bf16* Z = reinterpret_cast<const bf16*>(P.pv[0]);
   const bf16* W = reinterpret_cast<const bf16*>(P.pv[1]);
   const bf16* Bv = reinterpret_cast<const bf16*>(P.pv[2]);
-  float* out = reinterpret_cast<float*>(P.pv[9]);
+  float* out = reinterpret_cast<float*>(P.pv[9]) + (iv[6] ? (size_t)cx.step * iv[0] * Kc : (size_t)0);
   for (int c = tid; c < C; c += MG_THREADS) {
     const bf16* p = Z + ((size_t)n * HW) * Cp + c;
     float s = 0.f;
@@ -727,14 +728,14 @@ __device__ __noinline__ void sgd_norm_item(const Phase& P, Ctx& cx, int item) {
   const float4* g = reinterpret_cast<const float4*>(P.pv[0]);
   float acc = 0.f;
   const int lo = item * (MG_THREADS * 8);
+  float4 v[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int i = lo + k * MG_THREADS + threadIdx.x;
-    if (i < n4) {
-      const float4 v = __ldcg(g + i);
-      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    }
+    v[k] = (i < n4) ? __ldcg(g + i) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
   acc = block_sum(acc, sm);
   if (threadIdx.x == 0) atomicAdd(reinterpret_cast<float*>(cx.ctl + CTL_GNORM2), acc);
 }
@@ -762,29 +763,36 @@ __device__ __noinline__ void sgd_update_item(const Phase& P, Ctx& cx, int item) 
   float4* g = reinterpret_cast<float4*>(P.pv[2]);
   float4* mom = reinterpret_cast<float4*>(P.pv[3]);
   const int lo = item * (MG_THREADS * 8);
-#pragma unroll 2
-  for (int k = 0; k < 8; ++k) {
-    const int i = lo + k * MG_THREADS + threadIdx.x;
-    if (i < n4) {
-      const float4 gv = __ldcg(g + i);
-      float4 wv = __ldcg(w + i), mv = __ldcg(mom + i);
-      const float* gp = reinterpret_cast<const float*>(&gv);
-      float* wp = reinterpret_cast<float*>(&wv);
-      float* mp = reinterpret_cast<float*>(&mv);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float gg = gp[e] * coef + wd * wp[e];
-        mp[e] = mu * mp[e] + gg;
-        wp[e] -= lr * mp[e];
+  for (int kk = 0; kk < 8; kk += 4) {
+    float4 gv[4], wv[4], mv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {       // 12 independent 16-byte loads in flight per thread
+      const int i = lo + (kk + k) * MG_THREADS + threadIdx.x;
+      if (i < n4) { gv[k] = __ldcg(g + i); wv[k] = __ldcg(w + i); mv[k] = __ldcg(mom + i); }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = lo + (kk + k) * MG_THREADS + threadIdx.x;
+      if (i < n4) {
+        const float* gp = reinterpret_cast<const float*>(&gv[k]);
+        float* wp = reinterpret_cast<float*>(&wv[k]);
+        float* mp = reinterpret_cast<float*>(&mv[k]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float gg = gp[e] * coef + wd * wp[e];
+          mp[e] = mu * mp[e] + gg;
+          wp[e] -= lr * mp[e];
+        }
+        w[i] = wv[k];
+        mom[i] = mv[k];
+        const __nv_bfloat162 a = __floats2bfloat162_rn(wp[0], wp[1]), b = __floats2bfloat162_rn(wp[2], wp[3]);
+        uint2 tt;
+        tt.x = *reinterpret_cast<const unsigned*>(&a);
+        tt.y = *reinterpret_cast<const unsigned*>(&b);
+        wc[i] = tt;
+        g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      w[i] = wv;
-      mom[i] = mv;
-      const __nv_bfloat162 a = __floats2bfloat162_rn(wp[0], wp[1]), b = __floats2bfloat162_rn(wp[2], wp[3]);
-      uint2 tt;
-      tt.x = *reinterpret_cast<const unsigned*>(&a);
-      tt.y = *reinterpret_cast<const unsigned*>(&b);
-      wc[i] = tt;
-      g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   if (item == 0 && threadIdx.x == 0) reinterpret_cast<float*>(cx.ctl)[CTL_LAST_GNORM] = total;
@@ -842,11 +850,11 @@ __device__ __noinline__ void prep_item(const Phase& P, Ctx& cx, int item) {
 }
 
 // ------------------------------------------------------------------------------------------------------------- kernel
-__global__ void __launch_bounds__(MG_THREADS, 2)
+__global__ void __launch_bounds__(MG_THREADS, 1)
 mega_kernel(const Phase* __restrict__ prog, int nphase, int nsteps, unsigned* __restrict__ ctl,
-            const int* __restrict__ nvalid_tab) {
+            const int* __restrict__ nvalid_tab, unsigned long long* __restrict__ prof) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ Phase sP;                                     // header words only (tensor maps stay in global memory)
+  __shared__ Phase sPh[2];                                 // double-buffered headers (tensor maps stay in global memory)
   __shared__ uint32_t tmem_slot;
   Ctx cx;
   cx.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -863,6 +871,10 @@ mega_kernel(const Phase* __restrict__ prog, int nphase, int nsteps, unsigned* __
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_slot, MG_TMEM_COLS);
+  if (warp == 3 && nphase > 0) {                            // header of phase 0
+    for (int i = lane; i < HDR_WORDS; i += 32)
+      reinterpret_cast<uint32_t*>(&sPh[0])[i] = __ldcg(reinterpret_cast<const uint32_t*>(&prog[0]) + i);
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -872,14 +884,23 @@ mega_kernel(const Phase* __restrict__ prog, int nphase, int nsteps, unsigned* __
   unsigned rot = 0;
   const unsigned G = gridDim.x;
   bool dead = false;
+  int buf = 0;
+  const bool do_prof = (prof != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
   for (int step = 0; step < nsteps && !dead; ++step) {
     cx.step = step;
     cx.nvalid = nvalid_tab != nullptr ? nvalid_tab[step] : 0x7fffffff;
     for (int p = 0; p < nphase; ++p) {
-      __syncthreads();
-      if (threadIdx.x < HDR_WORDS)
-        reinterpret_cast<uint32_t*>(&sP)[threadIdx.x] = __ldcg(reinterpret_cast<const uint32_t*>(&prog[p]) + threadIdx.x);
-      __syncthreads();
+      const Phase& sP = sPh[buf];
+      // prefetch the next phase's header into the other buffer (its last readers finished before the barrier / sync
+      // that ended the previous phase); it is consumed after the __syncthreads at the end of this iteration
+      {
+        const int pn = (p + 1 < nphase) ? p + 1 : 0;
+        if (warp == 3)
+          for (int i = lane; i < HDR_WORDS; i += 32)
+            reinterpret_cast<uint32_t*>(&sPh[buf ^ 1])[i] = __ldcg(reinterpret_cast<const uint32_t*>(&prog[pn]) + i);
+      }
+      long long t0 = 0;
+      if (do_prof) t0 = clock64();
       const int nt = sP.ntiles, op = sP.op;
       const Phase* Pg = &prog[p];
       const unsigned start = (blockIdx.x + G - (rot % G)) % G;
@@ -900,10 +921,21 @@ mega_kernel(const Phase* __restrict__ prog, int nphase, int nsteps, unsigned* __
         }
       }
       rot = (rot + (unsigned)nt) % G;
-      if (sP.sync_after) {
+      long long t1 = 0;
+      if (do_prof) t1 = clock64();
+      const int sync_after = sP.sync_after;
+      if (sync_after) {
         grid_sync(ctl, epoch);
         if (aborted(ctl)) { dead = true; break; }
+      } else {
+        __syncthreads();
       }
+      if (do_prof) {
+        const long long t2 = clock64();
+        prof[2 * p] += (unsigned long long)(t1 - t0);
+        prof[2 * p + 1] += (unsigned long long)(t2 - t1);
+      }
+      buf ^= 1;
     }
   }
   __syncthreads();
@@ -947,14 +979,15 @@ extern "C" int hfl_mega_max_grid() {
 }
 
 extern "C" int hfl_mega_launch(const void* prog, int nphase, int nsteps, void* ctl, const int* nvalid_tab, int grid,
-                               cudaStream_t stream) {
+                               void* prof, cudaStream_t stream) {
   int e0 = mega_configure();
   if (e0 != 0) return e0;
   cudaError_t e = cudaMemsetAsync(ctl, 0, CTL_WORDS * sizeof(unsigned), stream);
   if (e != cudaSuccess) return (int)e;
   const Phase* p = reinterpret_cast<const Phase*>(prog);
   unsigned* c = reinterpret_cast<unsigned*>(ctl);
-  void* args[] = {(void*)&p, (void*)&nphase, (void*)&nsteps, (void*)&c, (void*)&nvalid_tab};
+  unsigned long long* pr = reinterpret_cast<unsigned long long*>(prof);
+  void* args[] = {(void*)&p, (void*)&nphase, (void*)&nsteps, (void*)&c, (void*)&nvalid_tab, (void*)&pr};
   e = cudaLaunchCooperativeKernel((const void*)mega_kernel, dim3(grid), dim3(MG_THREADS), args, (size_t)MG_SMEM, stream);
   hfl::count_launch();
   return (int)e;

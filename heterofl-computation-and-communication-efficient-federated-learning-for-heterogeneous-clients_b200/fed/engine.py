@@ -256,9 +256,48 @@ class Engine:
             if id(s) not in busy:
                 return s
         rate = self.tables.rates[level]
-        s = TrainSlot(self._model_for(rate), self.cfg, self.device, self.dtype, self.use_graph)
+        model = self._model_for(rate)
+        if self._use_mega(model):
+            from .mega_trainer import MegaSlot
+            s = MegaSlot(model, self.cfg, self.device, int(self.cfg["batch_size"]["train"]))
+        else:
+            s = TrainSlot(model, self.cfg, self.device, self.dtype, self.use_graph)
         pool.append(s)
         return s
+
+    def _use_mega(self, model: Model) -> bool:
+        """Resident-kernel training (fed/mega_trainer.py): BatchNorm Block-ResNets in bf16 on a GPU."""
+        if not (self.is_cuda and cu.available() and self.dtype == torch.bfloat16 and not self.is_lm):
+            return False
+        if os.environ.get("HFL_MEGA", "1") == "0" or not self.cfg.get("fused", True):
+            return False
+        from .mega_trainer import MegaSlot
+        return MegaSlot.eligible(model, self.cfg)
+
+    def _mega_grids(self, slots: List) -> None:
+        """Split the co-resident CTA budget over the wave's clients: every cooperative grid must fit next to the others
+        (a grid that does not fit simply waits for SMs), wide clients get proportionally more CTAs."""
+        mega = [s for s in slots if getattr(s, "is_mega", False)]
+        if not mega:
+            return
+        from .mega_trainer import DEFAULT_GRIDS, grid_for_rate
+        cap = mega[0].cap
+        want = [grid_for_rate(s.model.rate, cap) for s in mega]
+        tot = sum(want)
+        budget = int(cap * float(os.environ.get("HFL_MEGA_FILL", "0.95")))
+        if tot > budget:
+            scale = budget / tot
+            want = [max(1, int(w * scale)) for w in want]
+        elif tot < budget:
+            # spare SMs go to the clients by width (more tiles in flight per phase), bounded by what a level can use
+            top = {1.0: 148, 0.5: 96, 0.25: 32, 0.125: 12, 0.0625: 6}
+            spare = budget - tot
+            room = [max(0, top.get(min(top, key=lambda r: abs(r - s.model.rate)), 8) - w) for s, w in zip(mega, want)]
+            rt = sum(room)
+            if rt > 0:
+                want = [w + int(spare * r / rt) if spare < rt else w + r for w, r in zip(want, room)]
+        for s, w in zip(mega, want):
+            s.grid = int(max(1, min(w, cap)))
 
     def prewarm(self, slots_per_level: Optional[int] = None) -> int:
         """Create the resident slots and capture their train-step graphs up front (one dummy step each), so no
@@ -478,6 +517,7 @@ class Engine:
                 arenas = fed.distribute([user_idx[i] for i in batch_pos], redraw=False)
                 for s, a in zip(slots, arenas):
                     s.load_params(a)
+            self._mega_grids(slots)
             for i, s in zip(batch_pos, slots):
                 u = user_idx[i]
                 s.begin_client(lr, fed.user_label_mask(u), rng_seed=(self.seed * 1000003 + epoch * 7919) * 4099 + int(u))

@@ -11,6 +11,7 @@ CIFAR-10) and ``test()`` (``:141-169``) runs 100 per-user loaders plus one globa
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -39,6 +40,18 @@ class Evaluator:
         if self.device.type == "cuda" and compute_dtype == torch.bfloat16 and cu.available() \
                 and cfg.get("fused", True) and FusedResNet.eligible(model.spec):
             self.fused = FusedResNet(model.spec, model.scale_rate)
+        # resident-kernel programs (models/mega_resnet.py): the whole sBN pass / test pass of this rank is ONE launch
+        self.mega = None
+        self._mega_sbn = None
+        self._mega_test = None
+        if self.fused is not None and os.environ.get("HFL_MEGA", "1") != "0":
+            from .mega_trainer import MegaSlot
+            if MegaSlot.eligible(model, cfg):
+                from ..models.mega_resnet import MegaResNet
+                self.mega_grid = int(os.environ.get("HFL_MEGA_EVAL_GRID", "0")) or int(cu.C().mega_max_grid())
+                self.mega = MegaResNet(model, self.device, self.mega_grid)
+                self.mega_stats_groups = int(os.environ.get("HFL_MEGA_STATS_GROUPS", "200"))
+                self.mega_test_chunk = int(os.environ.get("HFL_MEGA_TEST_CHUNK", "2000"))
 
     def _params(self, global_arena: torch.Tensor) -> Dict[str, torch.Tensor]:
         wc = global_arena if self.dtype == torch.float32 else global_arena.to(self.dtype)
@@ -60,6 +73,10 @@ class Evaluator:
             return {}
         B = int(self.cfg["batch_size"]["train"])
         N = imgs_dev.shape[0]
+        if self.mega is not None and N % B == 0:
+            plan = self._chunk_plan(N // B, self.mega_stats_groups)
+            if plan is not None:
+                return self._sbn_mega(global_arena, ds, imgs_dev, generator, B, plan)
         if self.fused is not None and self.use_graph and N % B == 0:
             plan = self._chunk_plan(N // B, self.stats_chunk_groups)
             if plan is not None:
@@ -203,12 +220,103 @@ class Evaluator:
             cu.launch_count_add(st["kernels"])
         return self._merge_stats(bn, st["ctx"].acc, per_rank * Gc)
 
+
+    # -- resident-kernel evaluation (one launch per pass) -----------------------------------------------------
+    def _mega_state(self, key, imgs_src, steps: int, Nc: int, aug) -> Dict:
+        n = self.model.layout.size
+        dev = self.device
+        return {"key": key, "w": torch.empty(n, dtype=torch.float32, device=dev),
+                "wc": torch.empty(n, dtype=torch.bfloat16, device=dev),
+                "src": torch.empty(imgs_src.shape, dtype=torch.uint8, device=dev),
+                "idx": torch.zeros(steps, Nc, dtype=torch.int64, device=dev),
+                "par": torch.zeros(steps, Nc, 3, dtype=torch.int32, device=dev),
+                "nvalid": torch.full((steps,), Nc, dtype=torch.int32, device=dev),
+                "mean": aug.mean.reshape(-1).float().contiguous(), "istd": aug.inv_std.reshape(-1).float().contiguous(),
+                "ctl": torch.zeros(16, dtype=torch.int32, device=dev)}
+
+    def _sbn_mega(self, global_arena, ds, imgs_src, generator, B, plan) -> Dict:
+        """sBN pass: ``per_rank`` chunks of ``Gc`` ghost batches, all inside ONE launch of the phase program (tcgen05
+        convolutions with per-ghost-batch statistics in their epilogue; running sums accumulated on the device)."""
+        Gc, per_rank = plan
+        bn = self.model.bn_layers()
+        N = imgs_src.shape[0]
+        aug = self._augment(ds, True)
+        st = self._mega_sbn
+        if st is None or st["key"] != (N, B, Gc, per_rank):
+            st = self._mega_state((N, B, Gc, per_rank), imgs_src, per_rank, Gc * B, aug)
+            st["prog"] = self.mega.build_forward(st, Gc * B, "stats", group_n=B, augment=aug.augment)
+            st["prog_dev"] = st["prog"].finalize(self.device)
+            self._mega_sbn = st
+        perm = torch.randperm(N, generator=generator)
+        params = aug.draw(N, generator)
+        w_, r_ = self.info.world, self.info.rank
+        rows = [ci for ci in range(per_rank * w_) if ci % w_ == r_]
+        st["idx"].copy_(perm.view(per_rank * w_, Gc * B)[rows].contiguous().to(self.device, non_blocking=True))
+        st["par"].copy_(params.view(per_rank * w_, Gc * B, 3)[torch.as_tensor(rows, device=params.device)])
+        st["src"].copy_(imgs_src, non_blocking=True)
+        st["w"].copy_(global_arena)
+        st["wc"].copy_(global_arena)
+        for a, b in st["acc"].values():
+            a.zero_()
+            b.zero_()
+        cu.C().mega_launch(st["prog_dev"], len(st["prog"]), per_rank, st["ctl"], st["nvalid"], self.mega_grid)
+        acc = {name: (st["acc"][name][0][:w], st["acc"][name][1][:w]) for name, w in bn}
+        return self._merge_stats(bn, acc, per_rank * Gc)
+
+    def _test_mega(self, global_arena, running, ds, imgs_src, labels_src, owner_dev, user_masks_dev, plan):
+        """Logits of this rank's share of the test set in ONE launch; Global metrics use them as they are, Local
+        metrics apply each sample's owner's label mask to the same logits."""
+        Nc, per_rank = plan
+        N = imgs_src.shape[0]
+        bn = self.model.bn_layers()
+        aug = self._augment(ds, False)
+        st = self._mega_test
+        if st is None or st["key"] != (N, Nc, per_rank):
+            st = self._mega_state((N, Nc, per_rank), imgs_src, per_rank, Nc, aug)
+            st["prog"] = self.mega.build_forward(st, Nc, "eval", steps=per_rank)
+            st["prog_dev"] = st["prog"].finalize(self.device)
+            w_, r_ = self.info.world, self.info.rank
+            rows = [ci for ci in range(per_rank * w_) if ci % w_ == r_]
+            st["idx"].copy_(torch.arange(N).view(per_rank * w_, Nc)[rows].to(self.device))
+            st["P"] = self.model.layout.views(st["wc"])
+            self._mega_test = st
+        st["src"].copy_(imgs_src, non_blocking=True)
+        st["w"].copy_(global_arena)
+        st["wc"].copy_(global_arena)
+        for name, (a, b) in self.fused.eval_affine(st["P"], running).items():
+            st["affine"][name][0][:a.numel()].copy_(a)
+            st["affine"][name][1][:b.numel()].copy_(b)
+        cu.C().mega_launch(st["prog_dev"], len(st["prog"]), per_rank, st["ctl"], None, self.mega_grid)
+        idx = st["idx"].view(-1)
+        z = st["logits"]
+        y = labels_src.to(self.device, non_blocking=True).index_select(0, idx)
+        acc = torch.zeros(6, dtype=torch.float64, device=self.device)
+        acc[3] = F.cross_entropy(z, y, reduction="sum").double()
+        acc[4] = (z.argmax(1) == y).sum()
+        acc[5] = idx.numel()
+        own = owner_dev.index_select(0, idx)
+        sel = own >= 0
+        use_mask = bool(self.cfg["mask"]) and user_masks_dev is not None
+        zl = z.masked_fill(~user_masks_dev[own.clamp(min=0)].bool(), 0.0) if use_mask else z
+        ce = F.cross_entropy(zl, y, reduction="none")
+        acc[0] = (ce * sel).sum().double()
+        acc[1] = ((zl.argmax(1) == y) & sel).sum()
+        acc[2] = sel.sum()
+        all_reduce_sum(self.info, acc)
+        return ("vision", acc, True)
+
     # -- test --------------------------------------------------------------------------------------------
     @torch.no_grad()
     def test_vision(self, global_arena: torch.Tensor, running: Dict, ds: VisionData, imgs_dev: torch.Tensor,
                     labels_dev: torch.Tensor, owner_dev: Optional[torch.Tensor],
                     user_masks_dev: Optional[torch.Tensor], sync: bool = True):
         """``owner_dev[i]`` = user whose test split holds sample i (-1: none); ``user_masks_dev [U, classes]``."""
+        if self.mega is not None and owner_dev is not None:
+            plan = self._chunk_plan(imgs_dev.shape[0], self.mega_test_chunk)
+            if plan is not None:
+                pending = self._test_mega(global_arena, running, ds, imgs_dev, labels_dev, owner_dev, user_masks_dev,
+                                          plan)
+                return self.finish(pending) if sync else pending
         if self.fused is not None and self.use_graph and owner_dev is not None:
             plan = self._chunk_plan(imgs_dev.shape[0], self.test_chunk)
             if plan is not None:

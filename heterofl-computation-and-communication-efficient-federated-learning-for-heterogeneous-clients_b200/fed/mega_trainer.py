@@ -145,7 +145,8 @@ class MegaSlot:
         st["par"][:steps].copy_(params.view(steps, batch, 3), non_blocking=True)
         st["nvalid"][:steps].copy_(nv.view(-1), non_blocking=True)
         self._set_lr(self.lr)
-        cu.C().mega_launch(self.prog_dev, len(self.prog), steps, self.ctl, st["nvalid"], self.grid)
+        cu.C().mega_launch(self.prog_dev, len(self.prog), steps, self.ctl, st["nvalid"], self.grid,
+                           getattr(self, "prof", None))
         self.launches += 1
         yield
 

@@ -512,7 +512,8 @@ class MegaResNet:
         zero_phase(prog, tbuf, sync=1, name="zero.T")
         return prog
 
-    def build_forward(self, st: Dict, N: int, mode: str, group_n: int = 0) -> Program:
+    def build_forward(self, st: Dict, N: int, mode: str, group_n: int = 0, augment: bool = False,
+                      steps: int = 1) -> Program:
         """``mode``: "stats" (sBN pass over ghost batches of ``group_n`` images; accumulates running mean / unbiased
         variance sums into ``st['acc']``) or "eval" (affine from running statistics, logits into ``st['logits']``)."""
         assert mode in ("stats", "eval")
@@ -532,12 +533,12 @@ class MegaResNet:
         else:
             st["affine"] = {name: (torch.zeros(rup(C, 8), dtype=torch.float32, device=dev),
                                    torch.zeros(rup(C, 8), dtype=torch.float32, device=dev)) for name, C in sites}
-        self._prep(prog, st, N, augment=False, with_pack=True)
+        self._prep(prog, st, N, augment=augment, with_pack=True)
         z4 = self._forward(prog, st, N, mode, group_n if mode == "stats" else 0, 1 if mode == "stats" else 0)
         if mode == "eval":
             C4, (H4, W4) = st["c_last"], st["hw_last"]
-            st["logits"] = torch.zeros(N, self.classes, dtype=torch.float32, device=dev)
-            iv = [N, H4 * W4, z4.shape[3], C4, self.classes, 0]
+            st["logits"] = torch.zeros(steps * N, self.classes, dtype=torch.float32, device=dev)   # row = step * N + n
+            iv = [N, H4 * W4, z4.shape[3], C4, self.classes, 0, int(steps > 1)]
             pv = [_ptr(z4), self._pptr(st["wc"], "linear.weight"), self._pptr(st["wc"], "linear.bias"), 0, 0, 0, 0, 0, 0,
                   _ptr(st["logits"]), 0]
             prog.add(OP_HEAD, N, 1, iv=iv, pv=pv, name="head.eval")
