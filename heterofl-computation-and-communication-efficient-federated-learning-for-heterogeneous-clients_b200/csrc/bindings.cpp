@@ -16,6 +16,9 @@ void hfl_distribute(const void*, const void*, int, const void*, const void*, int
                     const void*, const void*, const void*, int, cudaStream_t);
 void hfl_peer_sum(const void*, int, float*, int, cudaStream_t);
 int hfl_fed_chunk();
+int hfl_fed2_chunk();
+void hfl_aggregate_v2(const void*, const void*, int, const int*, const void*, int, int, const void*, const int*, int,
+                      const void*, int, const void*, int, const void*, int, float*, int, cudaStream_t);
 int hfl_fed_max_clients();
 void hfl_sgd_clip_step(float*, void*, void*, int, float*, long, const float*, float, float, float, float*,
                        cudaStream_t);
@@ -110,6 +113,31 @@ void aggregate(torch::Tensor tensor_tab, torch::Tensor level_tab, torch::Tensor 
   hfl_aggregate(tensor_tab.data_ptr(), level_tab.data_ptr(), T, block_tab.data_ptr(), (int)block_lo, (int)n_blocks,
                 client_ptr.data_ptr(), client_level.data_ptr(), client_mask.data_ptr(), (int)client_mask.size(1), M,
                 out_ptr.data_ptr(), (int)out_ptr.size(0), cur_stream());
+  check_launch();
+}
+
+
+// clients sorted by level: lvl_start[L+1]; optional fused small all-reduce (red_src pointers -> red_dst)
+void aggregate_v2(torch::Tensor tensor_tab, torch::Tensor level_tab, torch::Tensor vec4, torch::Tensor block_tab,
+                  int64_t block_lo, int64_t n_blocks, torch::Tensor client_ptr, torch::Tensor lvl_start,
+                  torch::Tensor client_mask, torch::Tensor out_ptr, c10::optional<torch::Tensor> red_src,
+                  c10::optional<torch::Tensor> red_dst) {
+  CHECK_CUDA_T(tensor_tab); CHECK_CUDA_T(level_tab); CHECK_CUDA_T(block_tab); CHECK_CUDA_T(client_ptr);
+  CHECK_CUDA_T(lvl_start); CHECK_CUDA_T(client_mask); CHECK_CUDA_T(out_ptr); CHECK_CUDA_T(vec4);
+  const int T = tensor_tab.size(0), M = client_ptr.size(0), L = lvl_start.numel() - 1;
+  TORCH_CHECK(client_mask.dim() == 2 && client_mask.size(0) == M && client_mask.is_contiguous());
+  TORCH_CHECK(lvl_start.scalar_type() == torch::kInt32 && vec4.scalar_type() == torch::kInt32 && vec4.numel() == T);
+  const void* rs = nullptr; float* rd = nullptr; int rn = 0, rns = 0;
+  if (red_src.has_value() && red_dst.has_value()) {
+    CHECK_CUDA_T(*red_src); CHECK_CUDA_T(*red_dst);
+    TORCH_CHECK(red_dst->scalar_type() == torch::kFloat32);
+    rs = red_src->data_ptr(); rd = red_dst->data_ptr<float>(); rn = (int)red_dst->numel(); rns = (int)red_src->numel();
+  }
+  c10::cuda::CUDAGuard guard(tensor_tab.device());
+  hfl_aggregate_v2(tensor_tab.data_ptr(), level_tab.data_ptr(), T, vec4.data_ptr<int>(), block_tab.data_ptr(),
+                   (int)block_lo, (int)n_blocks, client_ptr.data_ptr(), lvl_start.data_ptr<int>(), L,
+                   client_mask.data_ptr(), (int)client_mask.size(1), out_ptr.data_ptr(), (int)out_ptr.size(0), rs, rns,
+                   rd, rn, cur_stream());
   check_launch();
 }
 
@@ -820,6 +848,8 @@ torch::Tensor mega_encode_tmap(int64_t base_ptr, std::vector<int64_t> dims, std:
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("aggregate", &aggregate);
+  m.def("aggregate_v2", &aggregate_v2);
+  m.def("fed2_chunk", &hfl_fed2_chunk);
   m.def("distribute", &distribute);
   m.def("peer_sum", &peer_sum);
   m.def("fed_chunk", &hfl_fed_chunk);

@@ -93,6 +93,107 @@ aggregate_kernel(const TensorDesc* __restrict__ tensors, const LevelDesc* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// aggregate v2: row-wise, 16-byte accesses, clients grouped by level, no client-count limit.
+//
+// A thread owns 4 consecutive coordinates along a tensor's innermost axis.  Slices are (per-head) prefixes whose
+// extents are multiples of 4 on every level (checked on the host: `vec4[t]`), so the 4 coordinates are covered by
+// exactly the same clients and map to 4 consecutive local coordinates: the (row, col, tap) decode and the
+// global -> local map run once per LEVEL (<= 8 per model) instead of once per client and element, and every client
+// value arrives as one float4 (local or NVLink peer load).  Clients are sorted by level (`lvl_start`); the per-client
+// state is just (pointer, mask row) read through the read-only path, so M is unbounded.  Tensors that do not qualify
+// (3 input channels, odd label rows, ...) take the scalar loop below with the same tables.
+// An optional small all-reduce (every rank's metric slab -> `red_dst`) rides in block 0 of the same launch, so the
+// round's metric merge needs no extra kernel and no extra flag barrier.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int FED2_CHUNK = 4096;     // elements per block (4 float4 passes of 256 threads)
+
+__global__ void __launch_bounds__(FED_THREADS)
+aggregate_v2_kernel(const TensorDesc* __restrict__ tensors, const LevelDesc* __restrict__ levels, int T,
+                    const int* __restrict__ vec4, const int2* __restrict__ block_tab, int block_lo,
+                    const unsigned long long* __restrict__ client_ptr, const int* __restrict__ lvl_start, int L,
+                    const unsigned char* __restrict__ client_mask, int mask_stride,
+                    const unsigned long long* __restrict__ out_ptr, int n_out,
+                    const unsigned long long* __restrict__ red_src, int red_n_src, float* __restrict__ red_dst,
+                    int red_n) {
+  if (blockIdx.x == 0 && red_n > 0) {
+    for (int i = threadIdx.x; i < red_n; i += FED_THREADS) {
+      float acc = 0.f;
+      for (int s = 0; s < red_n_src; ++s) acc += reinterpret_cast<const float*>(red_src[s])[i];
+      red_dst[i] = acc;
+    }
+  }
+  const int2 bt = block_tab[block_lo + blockIdx.x];
+  const TensorDesc d = tensors[bt.x];
+  const int numel = d.R * d.C * d.inner;
+  const int end = min(bt.y + FED2_CHUNK, numel);
+  if (vec4[bt.x]) {
+    for (int e = bt.y + 4 * threadIdx.x; e < end; e += 4 * FED_THREADS) {
+      int row, col, t;
+      decode(d, d.C, e, row, col, t);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int cnt = 0;
+      for (int lv = 0; lv < L; ++lv) {
+        const int m0 = lvl_start[lv], m1 = lvl_start[lv + 1];
+        if (m0 == m1) continue;
+        const LevelDesc l = levels[lv * T + bt.x];
+        const int lr = to_local(row, d.rH, l.r_dl, l.r_dg);
+        const int lc = to_local(col, d.cH, l.c_dl, l.c_dg);
+        if ((lr < 0) | (lc < 0)) continue;
+        const int li = l.l_off + (d.col_inner ? (lr * d.inner + t) * l.c_loc + lc : (lr * l.c_loc + lc) * d.inner + t);
+        if (d.label_rows) {
+#pragma unroll 4
+          for (int m = m0; m < m1; ++m) {
+            if (client_mask[(size_t)m * mask_stride + row]) {
+              const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(client_ptr[m]) + li);
+              acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+              ++cnt;
+            }
+          }
+        } else {
+#pragma unroll 4
+          for (int m = m0; m < m1; ++m) {
+            const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(client_ptr[m]) + li);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+          cnt += m1 - m0;
+        }
+      }
+      if (cnt > 0) {
+        const float inv = 1.f / (float)cnt;
+        const float4 v = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+        for (int o = 0; o < n_out; ++o)
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_ptr[o]) + d.g_off + e) = v;
+      }
+    }
+    return;
+  }
+  for (int e = bt.y + threadIdx.x; e < end; e += FED_THREADS) {
+    int row, col, t;
+    decode(d, d.C, e, row, col, t);
+    float acc = 0.f;
+    int cnt = 0;
+    for (int lv = 0; lv < L; ++lv) {
+      const int m0 = lvl_start[lv], m1 = lvl_start[lv + 1];
+      if (m0 == m1) continue;
+      const LevelDesc l = levels[lv * T + bt.x];
+      const int lr = to_local(row, d.rH, l.r_dl, l.r_dg);
+      const int lc = to_local(col, d.cH, l.c_dl, l.c_dg);
+      if ((lr < 0) | (lc < 0)) continue;
+      const int li = l.l_off + (d.col_inner ? (lr * d.inner + t) * l.c_loc + lc : (lr * l.c_loc + lc) * d.inner + t);
+      for (int m = m0; m < m1; ++m) {
+        if (d.label_rows && !client_mask[(size_t)m * mask_stride + row]) continue;
+        acc += reinterpret_cast<const float*>(client_ptr[m])[li];
+        ++cnt;
+      }
+    }
+    if (cnt > 0) {
+      const float v = acc / (float)cnt;
+      for (int o = 0; o < n_out; ++o) reinterpret_cast<float*>(out_ptr[o])[d.g_off + e] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // distribute: one launch prepares every client's optimiser-ready state
 //   w  (fp32 master)  <- slice of W_g        wc (bf16 compute copy, optional) <- same
 //   mom (fp32 momentum, optional) <- 0
@@ -179,5 +280,18 @@ extern "C" void hfl_peer_sum(const void* src_ptr, int n_src, float* dst, int n, 
   count_launch();
 }
 
+extern "C" void hfl_aggregate_v2(const void* tensors, const void* levels, int T, const int* vec4, const void* block_tab,
+                                 int block_lo, int n_blocks, const void* client_ptr, const int* lvl_start, int L,
+                                 const void* client_mask, int mask_stride, const void* out_ptr, int n_out,
+                                 const void* red_src, int red_n_src, float* red_dst, int red_n, cudaStream_t stream) {
+  if (n_blocks <= 0) return;
+  aggregate_v2_kernel<<<n_blocks, FED_THREADS, 0, stream>>>(
+      (const TensorDesc*)tensors, (const LevelDesc*)levels, T, vec4, (const int2*)block_tab, block_lo,
+      (const unsigned long long*)client_ptr, lvl_start, L, (const unsigned char*)client_mask, mask_stride,
+      (const unsigned long long*)out_ptr, n_out, (const unsigned long long*)red_src, red_n_src, red_dst, red_n);
+  count_launch();
+}
+
+extern "C" int hfl_fed2_chunk() { return FED2_CHUNK; }
 extern "C" int hfl_fed_chunk() { return FED_CHUNK; }
 extern "C" int hfl_fed_max_clients() { return MAX_CLIENTS_SMEM; }

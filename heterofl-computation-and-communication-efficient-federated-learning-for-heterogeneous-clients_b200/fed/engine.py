@@ -365,13 +365,13 @@ class Engine:
         # 4. aggregation (minus the clients the fault injector lost)
         timer.open("aggregate")
         lost = self._lost_clients(M, epoch)
-        self._aggregate(user_idx, levels, mine, results, lost)
-        timer.mark("aggregate")
-        # train metrics (sums over my clients -> all ranks)
+        # train metrics (sums over my clients -> all ranks): on the P2P path the merge rides in the aggregation launch
         tm = torch.zeros(4, dtype=torch.float64, device=self.device)
         for r in results.values():
             tm += r["meter"]
-        all_reduce_sum(info, tm)
+        if not self._aggregate(user_idx, levels, mine, results, lost, reduce=tm):
+            all_reduce_sum(info, tm)
+        timer.mark("aggregate")
         out: Dict = {"epoch": epoch, "lr": lr, "num_active": M, "user_idx": user_idx, "rates": rates,
                      "lost": sorted(lost)}
         # 5. evaluation
@@ -633,7 +633,8 @@ class Engine:
             lost.discard(min(lost))
         return lost
 
-    def _aggregate(self, user_idx, levels, mine, results, lost=()) -> None:
+    def _aggregate(self, user_idx, levels, mine, results, lost=(), reduce=None) -> bool:
+        """Returns True when ``reduce`` (the round's metric vector) was summed over the ranks by the aggregation itself."""
         fed, info = self.federation, self.info
         masks_all = [fed.user_label_mask(u) for u in user_idx]
         if lost:
@@ -651,10 +652,12 @@ class Engine:
         elif self._agg_backend == "p2p":
             from ..parallel.peer import p2p_aggregate
             p2p_aggregate(self._peer, self.tables, self.global_arena, levels, self._assignment, masks_all, info,
-                          active=[i for i in range(len(levels)) if i not in lost] if lost else None)
+                          active=[i for i in range(len(levels)) if i not in lost] if lost else None, reduce=reduce)
+            return reduce is not None
         else:
             from ..parallel.baseline import allreduce_aggregate
             allreduce_aggregate(self.tables, self.global_arena, levels, results, masks_all, info)
+        return False
 
     # -- full training loop --------------------------------------------------------------------------------
     def fit(self, num_rounds: Optional[int] = None) -> None:

@@ -146,9 +146,11 @@ class PeerPool:
 
 
 def p2p_aggregate(pool: PeerPool, tables: FedTables, global_arena: torch.Tensor, levels: List[int],
-                  assignment: List[List[int]], masks_all: List[torch.Tensor], info, active=None) -> None:
+                  assignment: List[List[int]], masks_all: List[torch.Tensor], info, active=None,
+                  reduce: Optional[torch.Tensor] = None) -> None:
     """``assignment[r]`` = client positions trained by rank r, in the order their result arenas were allocated;
-    ``active`` (optional) restricts the average to a subset of the clients (fault injection / stragglers)."""
+    ``active`` (optional) restricts the average to a subset of the clients (fault injection / stragglers);
+    ``reduce`` (optional, small fp32/fp64 vector) is summed over all ranks in place by the same launch."""
     from ..ops import fed_ops
     dev = global_arena.device
     dt = fed_ops.device_tables(tables, dev)
@@ -161,13 +163,24 @@ def p2p_aggregate(pool: PeerPool, tables: FedTables, global_arena: torch.Tensor,
     if active is not None:
         ptrs, levels, masks_all = ([ptrs[i] for i in active], [levels[i] for i in active],
                                    [masks_all[i] for i in active])
-    client_ptr = torch.tensor(ptrs, dtype=torch.int64).to(dev, non_blocking=True)
-    client_level = torch.tensor(levels, dtype=torch.int32).to(dev, non_blocking=True)
-    masks = torch.stack([m.to(torch.uint8) for m in masks_all]).contiguous().to(dev, non_blocking=True)
     g_off = global_arena._hfl_pool_offset
     out_ptr = torch.tensor([b + g_off for b in pool.peer_base], dtype=torch.int64).to(dev, non_blocking=True)
-    nb = dt.n_global_blocks
+    nb = dt.n_global_blocks2
     lo, hi = info.rank * nb // info.world, (info.rank + 1) * nb // info.world
-    pool.barrier()                       # every rank's finished client arenas are in place
-    fed_ops.aggregate_raw(dt, client_ptr, client_level, masks, out_ptr, lo, hi - lo)
+    red_src = red_dst = None
+    if reduce is not None:
+        # the round's metric vector rides along: published into this rank's slab before the barrier, summed over all
+        # peers' slabs by block 0 of the aggregation launch (no peer_sum launch, no extra barrier pair)
+        n = reduce.numel()
+        ch = 3                                        # dedicated slab: never used by the evaluation streams
+        if pool._scratch_ptrs[ch] is None:
+            off = pool._scratch[ch]._hfl_pool_offset
+            pool._scratch_ptrs[ch] = torch.tensor([b + off for b in pool.peer_base], dtype=torch.int64).to(dev)
+        pool._scratch[ch][:n].copy_(reduce.reshape(-1).to(torch.float32))
+        red_src = pool._scratch_ptrs[ch]
+        red_dst = torch.empty(n, dtype=torch.float32, device=dev)
+    pool.barrier()                       # every rank's finished client arenas (and metric slab) are in place
+    fed_ops.aggregate_ptrs(dt, ptrs, levels, masks_all, out_ptr, lo, hi - lo, red_src, red_dst)
     pool.barrier()                       # every shard of the new W_g has been published everywhere
+    if reduce is not None:
+        reduce.copy_(red_dst.to(reduce.dtype).view_as(reduce))

@@ -71,6 +71,42 @@ def test_distribute_aggregate_match_torch(data, model, control, extra, cl):
     assert not torch.equal(g_k, g)
 
 
+def test_aggregate_many_clients_and_fused_reduce():
+    """aggregate v2: no client-count limit (reference handles any M, src/fed.py:180-297) + the small all-reduce that
+    rides in block 0 of the same launch."""
+    _cu()
+    from hfl_b200.fed.federation import combine_torch
+    from hfl_b200.ops import fed_ops
+    cfg = make_cfg("CIFAR10", "resnet18", "1_800_0.5_non-iid-2_fix_c2-e8_bn_1_1", classes_size=10)
+    spec = build_spec(cfg)
+    rates = sorted(set(cfg["model_rate"]), reverse=True)
+    tables = build_tables(spec, cfg["global_model_rate"], rates, channels_last=True)
+    dev = torch.device("cuda")
+    g = torch.randn(tables.global_layout.size, device=dev)
+    M = 300
+    client_rates = [rates[(i * 7) % len(rates)] for i in range(M)]
+    levels = [tables.level_id(r) for r in client_rates]
+    rng = np.random.RandomState(1)
+    masks = []
+    for _ in levels:
+        m = torch.zeros(10, dtype=torch.uint8)
+        m[torch.as_tensor(rng.choice(10, size=2, replace=False))] = 1
+        masks.append(m)
+    local = [torch.randn(tables.level_layouts[l].size, device=dev) for l in levels]
+    g_ref, g_k = g.clone(), g.clone()
+    combine_torch(tables, g_ref, local, client_rates, masks)
+    dt = fed_ops.device_tables(tables, dev)
+    slabs = [torch.arange(6, dtype=torch.float32, device=dev) * (i + 1) for i in range(3)]
+    red_src = torch.tensor([t.data_ptr() for t in slabs], dtype=torch.int64, device=dev)
+    red_dst = torch.zeros(6, dtype=torch.float32, device=dev)
+    out_ptr = torch.tensor([g_k.data_ptr()], dtype=torch.int64, device=dev)
+    fed_ops.aggregate_ptrs(dt, [a.data_ptr() for a in local], levels, masks, out_ptr, 0, dt.n_global_blocks2, red_src,
+                           red_dst)
+    torch.cuda.synchronize()
+    assert torch.allclose(g_ref, g_k, atol=2e-5, rtol=1e-4)
+    assert torch.equal(red_dst, torch.arange(6, dtype=torch.float32, device=dev) * 6)
+
+
 @pytest.mark.parametrize("gdtype", [torch.float32, torch.bfloat16])
 def test_sgd_clip_step(gdtype):
     cu = _cu()
