@@ -81,6 +81,7 @@ int hfl_conv_wgrad_tc(const void*, const void*, float*, int, int, int, int, int,
 int hfl_mega_phase_bytes();
 int hfl_mega_smem_bytes();
 int hfl_mega_max_grid();
+void hfl_mega_occupancy_probe(int*);
 int hfl_mega_launch(const void*, int, int, void*, const int*, int, void*, cudaStream_t);
 int hfl_mega_encode_tmap(void*, const void*, int, const unsigned long long*, const unsigned long long*, const unsigned*,
                          const unsigned*);
@@ -895,6 +896,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mega_phase_bytes", &hfl_mega_phase_bytes);
   m.def("mega_smem_bytes", &hfl_mega_smem_bytes);
   m.def("mega_max_grid", &hfl_mega_max_grid);
+  m.def("mega_occupancy_probe", []() { std::vector<int> v(16); hfl_mega_occupancy_probe(v.data()); return v; });
   m.def("launch_count", &hfl_launch_count);
   m.def("launch_count_add", &hfl_launch_count_add);
   m.def("peer_alloc", &peer_alloc);

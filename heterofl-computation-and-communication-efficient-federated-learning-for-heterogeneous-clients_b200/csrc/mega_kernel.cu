@@ -43,7 +43,7 @@ struct Ctx {
   uint32_t tmem;
   unsigned* ctl;
   uint32_t kctr, tctr;   // running k-block / accumulator-tile counters: every warp advances them identically
-  int nvalid, step;
+  int nvalid, step, phase;
 };
 
 // ------------------------------------------------------------------------------------------- bounded waits / barrier
@@ -87,6 +87,20 @@ __device__ __forceinline__ void grid_sync(unsigned* ctl, unsigned& epoch) {
   }
   __syncthreads();
   fence_proxy_async();
+}
+
+// Producer-side sanity check before the first TMA of a tile: the header this CTA works from must be the record the
+// tensor maps are read from, and the map must have been encoded (a zero descriptor is an illegal instruction).  Turns a
+// would-be device fault into an abort code + diagnostics in the control block (words 8..13).
+__device__ __noinline__ bool tile_guard(const Phase* __restrict__ Pg, const Phase& P, Ctx& cx, int tile, int map) {
+  const int gop = __ldcg(reinterpret_cast<const int*>(&Pg->op));
+  const unsigned long long d0 = __ldcg(reinterpret_cast<const unsigned long long*>(&Pg->tm[map]));
+  if (gop == P.op && d0 != 0ull) return true;
+  if (atomicCAS(cx.ctl + CTL_ABORT, 0u, 4u) == 0u) {
+    cx.ctl[8] = (unsigned)cx.phase; cx.ctl[9] = (unsigned)tile; cx.ctl[10] = (unsigned)P.op; cx.ctl[11] = (unsigned)gop;
+    cx.ctl[12] = blockIdx.x; cx.ctl[13] = (unsigned)cx.step;
+  }
+  return false;
 }
 
 // ----------------------------------------------------------------------------------------------------- small helpers
@@ -152,7 +166,7 @@ __device__ __noinline__ void conv_tile(const Phase* __restrict__ Pg, const Phase
       uint32_t kc = k0;
       const int ntaps = iv[18], in_stride = iv[16];
       const uint32_t tx = (uint32_t)(iv[23] + iv[24]);
-      bool live = true;
+      bool live = tile_guard(Pg, P, cx, tile, 0) && tile_guard(Pg, P, cx, tile, 2);
       for (int t = 0; t < ntaps && live; ++t) {
         const int w0 = iv[26 + 2 * t], w1 = iv[27 + 2 * t];
         const int a_map = w0 & 15, b_map = (w0 >> 4) & 15, b_tap = (w0 >> 8) & 255, kb_t = (w0 >> 16) & 0xffff;
@@ -301,7 +315,8 @@ __device__ __noinline__ void wgrad_tile(const Phase* __restrict__ Pg, const Phas
       uint32_t kc = k0;
       const int bricks_h = iv[6], bn = iv[3], bh = iv[4], stride = iv[13], pad = iv[14];
       const uint32_t tx = (uint32_t)(a_boxes * 8192 + 8192);
-      for (int kb = 0; kb < num_k; ++kb, ++kc) {
+      const bool live = tile_guard(Pg, P, cx, tile, 0) && tile_guard(Pg, P, cx, tile, 1);
+      for (int kb = 0; kb < num_k && live; ++kb, ++kc) {
         const int st = kc % MG_STAGES;
         const uint32_t ph = (kc / MG_STAGES) & 1;
         const int brick = b0 + kb;
@@ -890,6 +905,7 @@ mega_kernel(const Phase* __restrict__ prog, int nphase, int nsteps, unsigned* __
     cx.step = step;
     cx.nvalid = nvalid_tab != nullptr ? nvalid_tab[step] : 0x7fffffff;
     for (int p = 0; p < nphase; ++p) {
+      cx.phase = p;
       const Phase& sP = sPh[buf];
       // prefetch the next phase's header into the other buffer (its last readers finished before the barrier / sync
       // that ended the previous phase); it is consumed after the __syncthreads at the end of this iteration
@@ -976,6 +992,28 @@ extern "C" int hfl_mega_max_grid() {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return per_sm * sms;
+}
+
+// debugging aid: kernel attributes + occupancy for a few dynamic shared-memory sizes
+extern "C" void hfl_mega_occupancy_probe(int* out /* [16] */) {
+  mega_configure();
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, mega_kernel);
+  out[0] = a.numRegs; out[1] = (int)a.sharedSizeBytes; out[2] = a.maxDynamicSharedSizeBytes; out[3] = a.maxThreadsPerBlock;
+  out[4] = a.preferredShmemCarveout; out[5] = (int)a.localSizeBytes;
+  const int sizes[5] = {0, 48 * 1024, 96 * 1024, 110 * 1024, MG_SMEM};
+  for (int i = 0; i < 5; ++i) {
+    int n = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mega_kernel, MG_THREADS, sizes[i]);
+    out[6 + i] = n;
+  }
+  int dev = 0, v = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev); out[11] = v;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMaxRegistersPerMultiprocessor, dev); out[12] = v;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMaxBlocksPerMultiprocessor, dev); out[13] = v;
+  cudaDeviceGetAttribute(&v, cudaDevAttrReservedSharedMemoryPerBlock, dev); out[14] = v;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); out[15] = v;
 }
 
 extern "C" int hfl_mega_launch(const void* prog, int nphase, int nsteps, void* ctl, const int* nvalid_tab, int grid,

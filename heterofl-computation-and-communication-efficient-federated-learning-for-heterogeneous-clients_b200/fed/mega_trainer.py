@@ -154,7 +154,8 @@ class MegaSlot:
         """Raise if the last launch aborted on a device-side timeout (host sync)."""
         c = self.ctl.tolist()
         if c[1] != 0:
-            raise RuntimeError("megakernel aborted (code %d) at step %d" % (c[1], c[2]))
+            nm = self.prog.names[c[8]] if 0 <= c[8] < len(self.prog.names) else "?"
+            raise RuntimeError("megakernel aborted (code %d): diag %s phase %s" % (c[1], c[8:14], nm))
 
     def metrics(self) -> Dict[str, float]:
         return self.meter.result("Local-", lm=False)

@@ -121,6 +121,10 @@ class Program:
     def n_barriers(self) -> int:
         return sum(int(r["sync"]) for r in self.recs)
 
+    def hold(self, *objs) -> None:
+        """Keep buffers referenced by raw pointers alive as long as the program."""
+        self.keep.extend(objs)
+
     def finalize(self, device) -> torch.Tensor:
         arr = np.stack(self.recs) if self.recs else np.zeros((0,), dtype=PHASE_DT)
         t = torch.from_numpy(arr.view(np.uint8).reshape(-1).copy())
@@ -446,11 +450,11 @@ class MegaResNet:
         prog.add(OP_HEAD, 1, 1, iv=iv, pv=pv, name="head")
         # ---- backward ----
         acts = st["acts"]
-        ds = self._act(N, H4, W4, C4)
+        bk = st.setdefault("bwd", {})
+        ds = bk.setdefault("n4.ds", self._act(N, H4, W4, C4))      # every buffer a phase points at must outlive the build
         norm_bwd(prog, y_last, dz4, ds, C4, stats=st["S"]["n4"], gamma=self._pptr(wc, "n4.weight"),
                  beta=self._pptr(wc, "n4.bias"), T=st["T"]["n4"], dgamma=self._pptr(g, "n4.weight"),
                  dbeta=self._pptr(g, "n4.bias"), eps=self.eps, name="n4.bwd")
-        bk = st.setdefault("bwd", {})
         H, W = H4, W4
         for blk in reversed(self.blocks):
             pre, stride = blk["prefix"], blk["stride"]
@@ -497,7 +501,7 @@ class MegaResNet:
             ds, H, W = ds_prev, IH, IW
         C0 = self.lay.entries["conv1.weight"].shape[0]
         conv_wgrad(prog, ds, st["x"], self._pptr(g, "conv1.weight"), C0, self.Cin, 3, 1, tgt, sync=1, name="stem.wgrad")
-        prog.keep += [sbuf, tbuf, dz4]
+        prog.keep += [sbuf, tbuf, dz4, st]
         if not with_opt:         # debugging / tests: gradients stay in ``g``, statistics slabs are not re-armed
             return prog
         # ---- optimiser ----
@@ -542,4 +546,5 @@ class MegaResNet:
             pv = [_ptr(z4), self._pptr(st["wc"], "linear.weight"), self._pptr(st["wc"], "linear.bias"), 0, 0, 0, 0, 0, 0,
                   _ptr(st["logits"]), 0]
             prog.add(OP_HEAD, N, 1, iv=iv, pv=pv, name="head.eval")
+        prog.hold(st)
         return prog

@@ -20,7 +20,8 @@ def _run(prog, grid=32, nsteps=1, nvalid=None):
     cu.C().mega_launch(pd, len(prog), nsteps, ctl, nvalid, grid)
     torch.cuda.synchronize()
     c = ctl.tolist()
-    assert c[1] == 0, "megakernel aborted: code %d" % c[1]
+    assert c[1] == 0, "megakernel aborted: code %d, diag %s, phase name %s" % (
+        c[1], c[8:14], prog.names[c[8]] if c[8] < len(prog.names) else "?")
     return c
 
 
