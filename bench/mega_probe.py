@@ -86,28 +86,46 @@ def main():
             for nm, a, b in rows[:12]:
                 print("   top %-28s work %6.1f barrier %6.1f" % (nm, a, b))
     if what in ("all", "conc"):
-        # 10 concurrent clients, 2 per level, grids scaled to the 148-SM budget
-        plan = {1.0: 40, 0.5: 20, 0.25: 8, 0.125: 4, 0.0625: 2}
+        # one wave of 10 clients (2 per level) inside ONE launch: lock-step phases, shared barriers, all SMs
+        from hfl_b200.fed.mega_trainer import launch_wave
         twins = []
-        for rate, g in plan.items():
+        for rate in grids:
             model = Model(spec, cfg, rate, True)
-            s2 = MegaSlot(model, cfg, dev, 10, grid=g)
+            s2 = MegaSlot(model, cfg, dev, 10)
             s2.load_params(torch.randn(model.layout.size, device=dev) * 0.05)
             s2.begin_client(0.05, torch.ones(10, dtype=torch.uint8))
-            slots[rate].grid = g
             twins += [slots[rate], s2]
-        for rep in range(2):
-            torch.cuda.synchronize()
-            t0 = time.time()
-            for s in twins:
-                with torch.cuda.stream(s.stream):
-                    run(s, imgs, labs, aug, 5 if rep else 1, gen)
-            torch.cuda.synchronize()
-            dt = time.time() - t0
-            for s in twins:
-                s.check()
-            print("10 concurrent clients x %d steps: %.1f ms wall (%.1f us per client-step aggregate)" % (
-                250 if rep else 50, dt * 1e3, dt * 1e6 / (10 * (250 if rep else 50))), flush=True)
+        ctl = torch.zeros(16, dtype=torch.int32, device=dev)
+        for grid in (148, 96):
+            for rep, epochs in enumerate((1, 5)):
+                for s in twins:
+                    s.prepare_client(imgs, labs, aug, epochs, 10, gen)
+                prof = torch.zeros(2 * len(twins[0].prog), dtype=torch.int64, device=dev) if rep else None
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                launch_wave(twins, min(grid, cap), ctl, prof)
+                e1.record()
+                torch.cuda.synchronize()
+                assert ctl.tolist()[1] == 0, ctl.tolist()
+                ms = e0.elapsed_time(e1)
+                steps = 50 * epochs
+                print("wave of 10 clients (2 per level), grid %d, %d steps each: %.1f ms = %.1f us per lock-step "
+                      "(%.1f us per client-step)" % (grid, steps, ms, 1e3 * ms / steps, 1e2 * ms / steps), flush=True)
+                if prof is not None:
+                    pr = prof.view(-1, 2).cpu().double() / steps / 1965.0
+                    by = {}
+                    for nm, a, b in zip(twins[0].prog.names, pr[:, 0].tolist(), pr[:, 1].tolist()):
+                        k = nm.split(".")[-1] if not nm.startswith("sgd") else nm
+                        if "dgrad" in nm:
+                            k = "dgrad"
+                        by.setdefault(k, [0, 0.0, 0.0])
+                        by[k][0] += 1
+                        by[k][1] += a
+                        by[k][2] += b
+                    print("   CTA0 per lock-step: work %.1f us, barrier-wait %.1f us" % (float(pr[:, 0].sum()), float(pr[:, 1].sum())))
+                    for k, v in sorted(by.items(), key=lambda kv: -(kv[1][1] + kv[1][2])):
+                        print("      %-12s x%3d  work %7.1f us  barrier %7.1f us" % (k, v[0], v[1], v[2]))
 
 
 if __name__ == "__main__":

@@ -82,7 +82,8 @@ int hfl_mega_phase_bytes();
 int hfl_mega_smem_bytes();
 int hfl_mega_max_grid();
 void hfl_mega_occupancy_probe(int*);
-int hfl_mega_launch(const void*, int, int, void*, const int*, int, void*, cudaStream_t);
+int hfl_mega_launch(const void*, int, int, int, void*, int, void*, cudaStream_t);
+int hfl_mega_max_jobs();
 int hfl_mega_encode_tmap(void*, const void*, int, const unsigned long long*, const unsigned long long*, const unsigned*,
                          const unsigned*);
 long hfl_launch_count();
@@ -808,26 +809,22 @@ void peer_barrier(torch::Tensor flag_ptrs, int64_t rank, int64_t world, int64_t 
 
 
 // ---- resident client-training megakernel (csrc/mega_kernel.cu) ------------------------------------------
-void mega_launch(torch::Tensor prog, int64_t nphase, int64_t nsteps, torch::Tensor ctl,
-                 c10::optional<torch::Tensor> nvalid_tab, int64_t grid, c10::optional<torch::Tensor> prof) {
-  CHECK_CUDA_T(prog); CHECK_CUDA_T(ctl); CHECK_CONTIG(prog);
-  TORCH_CHECK(prog.scalar_type() == torch::kUInt8 && prog.numel() >= nphase * hfl_mega_phase_bytes());
-  TORCH_CHECK((reinterpret_cast<uintptr_t>(prog.data_ptr()) & 63) == 0, "mega program must be 64-byte aligned");
+// jobs: int64 [K, 4] device tensor of {program ptr, nvalid-table ptr (0: none), per-job ctl ptr, nsteps}
+void mega_launch(torch::Tensor jobs, int64_t nphase, int64_t nsteps, torch::Tensor ctl, int64_t grid,
+                 c10::optional<torch::Tensor> prof) {
+  CHECK_CUDA_T(jobs); CHECK_CUDA_T(ctl); CHECK_CONTIG(jobs);
+  TORCH_CHECK(jobs.scalar_type() == torch::kInt64 && jobs.dim() == 2 && jobs.size(1) == 4);
+  TORCH_CHECK(jobs.size(0) >= 1 && jobs.size(0) <= hfl_mega_max_jobs(), "mega_launch: 1..", hfl_mega_max_jobs(), " jobs");
   TORCH_CHECK(ctl.scalar_type() == torch::kInt32 && ctl.numel() >= 16);
-  const int* nv = nullptr;
-  if (nvalid_tab.has_value()) {
-    CHECK_CUDA_T(*nvalid_tab);
-    TORCH_CHECK(nvalid_tab->scalar_type() == torch::kInt32 && nvalid_tab->numel() >= nsteps && nvalid_tab->is_contiguous());
-    nv = nvalid_tab->data_ptr<int>();
-  }
-  c10::cuda::CUDAGuard guard(prog.device());
   void* pr = nullptr;
   if (prof.has_value()) {   // per-phase (work, barrier) cycle counters of CTA 0: int64 [2 * nphase]
     CHECK_CUDA_T(*prof);
     TORCH_CHECK(prof->scalar_type() == torch::kInt64 && prof->numel() >= 2 * nphase && prof->is_contiguous());
     pr = prof->data_ptr();
   }
-  int e = hfl_mega_launch(prog.data_ptr(), (int)nphase, (int)nsteps, ctl.data_ptr(), nv, (int)grid, pr, cur_stream());
+  c10::cuda::CUDAGuard guard(jobs.device());
+  int e = hfl_mega_launch(jobs.data_ptr(), (int)jobs.size(0), (int)nphase, (int)nsteps, ctl.data_ptr(), (int)grid, pr,
+                          cur_stream());
   TORCH_CHECK(e == 0, "mega_launch failed with code ", e, " (", cudaGetErrorString((cudaError_t)e), ")");
 }
 
@@ -890,8 +887,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv_dgrad_tc", &conv_dgrad_tc);
   m.def("conv_wgrad_tc", &conv_wgrad_tc);
   m.def("conv_wgrad_tc_supported", &conv_wgrad_tc_supported);
-  m.def("mega_launch", &mega_launch, py::arg("prog"), py::arg("nphase"), py::arg("nsteps"), py::arg("ctl"),
-        py::arg("nvalid_tab"), py::arg("grid"), py::arg("prof") = py::none());
+  m.def("mega_launch", &mega_launch, py::arg("jobs"), py::arg("nphase"), py::arg("nsteps"), py::arg("ctl"), py::arg("grid"),
+        py::arg("prof") = py::none());
+  m.def("mega_max_jobs", &hfl_mega_max_jobs);
   m.def("mega_encode_tmap", &mega_encode_tmap);
   m.def("mega_phase_bytes", &hfl_mega_phase_bytes);
   m.def("mega_smem_bytes", &hfl_mega_smem_bytes);

@@ -34,6 +34,18 @@ enum Op : int {
   OP_SGD_UPDATE = 9,  // clip + weight decay + momentum + update, bf16 copy, gradient / scratch zeroing
 };
 
+// One client (or one evaluation pass) of a launch.  All jobs of a launch share the phase structure (same ops / barriers
+// per phase index); a job is idle once `step >= nsteps`.
+struct alignas(16) Job {
+  const Phase* prog;
+  const int* nvalid_tab;      // [nsteps] valid samples per step (nullptr: all)
+  unsigned* jctl;             // per-job scalars: CTL_GNORM2 / CTL_LAST_GNORM words
+  int nsteps;
+  int pad;
+};
+static_assert(sizeof(Job) == 32, "Job ABI");
+constexpr int MAX_JOBS = 16;
+
 // control block (uint32 words)
 constexpr int CTL_ARRIVE = 0, CTL_ABORT = 1, CTL_STEP = 2, CTL_PHASE = 3, CTL_GNORM2 = 4, CTL_LAST_GNORM = 5,
               CTL_WORDS = 16;

@@ -41,7 +41,8 @@ struct Ctx {
   uint8_t* smem;
   uint64_t *full, *empty, *tfull;
   uint32_t tmem;
-  unsigned* ctl;
+  unsigned* ctl;          // launch-wide: barrier counter, abort flag, diagnostics
+  unsigned* jctl;         // per job: gradient-norm accumulator
   uint32_t kctr, tctr;   // running k-block / accumulator-tile counters: every warp advances them identically
   int nvalid, step, phase;
 };
@@ -752,7 +753,7 @@ __device__ __noinline__ void sgd_norm_item(const Phase& P, Ctx& cx, int item) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
   acc = block_sum(acc, sm);
-  if (threadIdx.x == 0) atomicAdd(reinterpret_cast<float*>(cx.ctl + CTL_GNORM2), acc);
+  if (threadIdx.x == 0) atomicAdd(reinterpret_cast<float*>(cx.jctl + CTL_GNORM2), acc);
 }
 
 // OP_SGD_UPDATE  iv: 0 n4  1 upd_items  2 zero_n4;  pv: 0 w  1 wc  2 g  3 mom  4 zero_ptr;  fv: 0 lr 1 mu 2 wd 3 max_norm
@@ -770,7 +771,7 @@ __device__ __noinline__ void sgd_update_item(const Phase& P, Ctx& cx, int item) 
     return;
   }
   const int n4 = P.iv[0];
-  const float total = sqrtf(__ldcg(reinterpret_cast<const float*>(cx.ctl + CTL_GNORM2)));
+  const float total = sqrtf(__ldcg(reinterpret_cast<const float*>(cx.jctl + CTL_GNORM2)));
   const float coef = fminf(1.f, P.fv[3] / (total + 1e-6f));
   const float lr = P.fv[0], mu = P.fv[1], wd = P.fv[2];
   float4* w = reinterpret_cast<float4*>(P.pv[0]);
@@ -810,7 +811,7 @@ __device__ __noinline__ void sgd_update_item(const Phase& P, Ctx& cx, int item) 
       }
     }
   }
-  if (item == 0 && threadIdx.x == 0) reinterpret_cast<float*>(cx.ctl)[CTL_LAST_GNORM] = total;
+  if (item == 0 && threadIdx.x == 0) reinterpret_cast<float*>(cx.jctl)[CTL_LAST_GNORM] = total;
 }
 
 // ------------------------------------------------------------------------------------------------------------ OP_PREP
@@ -820,7 +821,7 @@ __device__ __noinline__ void sgd_update_item(const Phase& P, Ctx& cx, int item) 
 __device__ __noinline__ void prep_item(const Phase& P, Ctx& cx, int item) {
   const int* iv = P.iv;
   const int B = iv[0];
-  if (item == 0 && threadIdx.x == 0) reinterpret_cast<float*>(cx.ctl)[CTL_GNORM2] = 0.f;
+  if (item == 0 && threadIdx.x == 0) reinterpret_cast<float*>(cx.jctl)[CTL_GNORM2] = 0.f;
   if (item < B) {
     const int H = iv[1], W = iv[2], Cs = iv[3], pad = iv[4], Cx = iv[7];
     const unsigned char* src = reinterpret_cast<const unsigned char*>(P.pv[0]);
@@ -866,10 +867,13 @@ __device__ __noinline__ void prep_item(const Phase& P, Ctx& cx, int item) {
 
 // ------------------------------------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(MG_THREADS, 1)
-mega_kernel(const Phase* __restrict__ prog, int nphase, int nsteps, unsigned* __restrict__ ctl,
-            const int* __restrict__ nvalid_tab, unsigned long long* __restrict__ prof) {
+mega_kernel(const Job* __restrict__ jobs, int njobs, int nphase, int nsteps, unsigned* __restrict__ ctl,
+            unsigned long long* __restrict__ prof) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ Phase sPh[2];                                 // double-buffered headers (tensor maps stay in global memory)
+  // headers of the current / next phase for every job (tensor maps stay in global memory), double buffered
+  __shared__ __align__(16) uint32_t sHdr[2][MAX_JOBS][HDR_WORDS];
+  __shared__ Job sJob[MAX_JOBS];
+  __shared__ int sPre[MAX_JOBS + 1];
   __shared__ uint32_t tmem_slot;
   Ctx cx;
   cx.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -880,20 +884,24 @@ mega_kernel(const Phase* __restrict__ prog, int nphase, int nsteps, unsigned* __
   cx.kctr = 0;
   cx.tctr = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (njobs > MAX_JOBS) njobs = MAX_JOBS;
+  if (threadIdx.x < njobs) sJob[threadIdx.x] = jobs[threadIdx.x];
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < MG_STAGES; ++s) { mbar_init(&cx.full[s], 1); mbar_init(&cx.empty[s], 1); }
     mbar_init(cx.tfull, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_slot, MG_TMEM_COLS);
-  if (warp == 3 && nphase > 0) {                            // header of phase 0
-    for (int i = lane; i < HDR_WORDS; i += 32)
-      reinterpret_cast<uint32_t*>(&sPh[0])[i] = __ldcg(reinterpret_cast<const uint32_t*>(&prog[0]) + i);
-  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   cx.tmem = tmem_slot;
+  // headers of phase 0
+  for (int i = threadIdx.x; i < njobs * HDR_WORDS; i += MG_THREADS) {
+    const int k = i / HDR_WORDS, wd = i - k * HDR_WORDS;
+    sHdr[0][k][wd] = __ldcg(reinterpret_cast<const uint32_t*>(sJob[k].prog) + wd);
+  }
+  __syncthreads();
 
   unsigned epoch = 0;
   unsigned rot = 0;
@@ -903,43 +911,59 @@ mega_kernel(const Phase* __restrict__ prog, int nphase, int nsteps, unsigned* __
   const bool do_prof = (prof != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
   for (int step = 0; step < nsteps && !dead; ++step) {
     cx.step = step;
-    cx.nvalid = nvalid_tab != nullptr ? nvalid_tab[step] : 0x7fffffff;
     for (int p = 0; p < nphase; ++p) {
       cx.phase = p;
-      const Phase& sP = sPh[buf];
-      // prefetch the next phase's header into the other buffer (its last readers finished before the barrier / sync
-      // that ended the previous phase); it is consumed after the __syncthreads at the end of this iteration
+      // prefetch the next phase's headers into the other buffer (its last readers passed the sync that ended the
+      // previous phase); consumed after the sync at the end of this iteration
       {
         const int pn = (p + 1 < nphase) ? p + 1 : 0;
-        if (warp == 3)
-          for (int i = lane; i < HDR_WORDS; i += 32)
-            reinterpret_cast<uint32_t*>(&sPh[buf ^ 1])[i] = __ldcg(reinterpret_cast<const uint32_t*>(&prog[pn]) + i);
+        if (warp >= 2 && warp < 4)
+          for (int i = threadIdx.x - 64; i < njobs * HDR_WORDS; i += 64) {
+            const int k = i / HDR_WORDS, wd = i - k * HDR_WORDS;
+            sHdr[buf ^ 1][k][wd] = __ldcg(reinterpret_cast<const uint32_t*>(sJob[k].prog + pn) + wd);
+          }
       }
+      // tile space of this phase: the active jobs' tiles back to back (jobs are sorted heaviest first on the host)
+      if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int k = 0; k < njobs; ++k) {
+          sPre[k] = acc;
+          if (step < sJob[k].nsteps) acc += reinterpret_cast<const Phase*>(sHdr[buf][k])->ntiles;
+        }
+        sPre[njobs] = acc;
+      }
+      __syncthreads();
       long long t0 = 0;
       if (do_prof) t0 = clock64();
-      const int nt = sP.ntiles, op = sP.op;
-      const Phase* Pg = &prog[p];
+      const int nt = sPre[njobs];
       const unsigned start = (blockIdx.x + G - (rot % G)) % G;
+      int k = 0;
       for (int t = (int)start; t < nt; t += (int)G) {
-        switch (op) {
-          case OP_PREP: prep_item(sP, cx, t); break;
-          case OP_CONV: conv_tile(Pg, sP, cx, t); break;
-          case OP_WGRAD: wgrad_tile(Pg, sP, cx, t); break;
-          case OP_NAPPLY: napply_item(sP, cx, t); break;
-          case OP_NBWD_RED: nbwd_item(sP, cx, t, false); break;
-          case OP_NBWD_APPLY: nbwd_item(sP, cx, t, true); break;
+        while (t >= sPre[k + 1]) ++k;
+        const Phase& sP = *reinterpret_cast<const Phase*>(sHdr[buf][k]);
+        const Phase* Pg = sJob[k].prog + p;
+        const int lt = t - sPre[k];
+        cx.jctl = sJob[k].jctl;
+        cx.nvalid = sJob[k].nvalid_tab != nullptr ? __ldg(sJob[k].nvalid_tab + step) : 0x7fffffff;
+        switch (sP.op) {
+          case OP_PREP: prep_item(sP, cx, lt); break;
+          case OP_CONV: conv_tile(Pg, sP, cx, lt); break;
+          case OP_WGRAD: wgrad_tile(Pg, sP, cx, lt); break;
+          case OP_NAPPLY: napply_item(sP, cx, lt); break;
+          case OP_NBWD_RED: nbwd_item(sP, cx, lt, false); break;
+          case OP_NBWD_APPLY: nbwd_item(sP, cx, lt, true); break;
           case OP_HEAD:
-            if (sP.iv[5]) head_train(sP, cx); else head_eval_item(sP, cx, t);
+            if (sP.iv[5]) head_train(sP, cx); else head_eval_item(sP, cx, lt);
             break;
-          case OP_SGD_NORM: sgd_norm_item(sP, cx, t); break;
-          case OP_SGD_UPDATE: sgd_update_item(sP, cx, t); break;
+          case OP_SGD_NORM: sgd_norm_item(sP, cx, lt); break;
+          case OP_SGD_UPDATE: sgd_update_item(sP, cx, lt); break;
           default: break;
         }
       }
       rot = (rot + (unsigned)nt) % G;
       long long t1 = 0;
       if (do_prof) t1 = clock64();
-      const int sync_after = sP.sync_after;
+      const int sync_after = reinterpret_cast<const Phase*>(sHdr[buf][0])->sync_after;
       if (sync_after) {
         grid_sync(ctl, epoch);
         if (aborted(ctl)) { dead = true; break; }
@@ -1016,20 +1040,24 @@ extern "C" void hfl_mega_occupancy_probe(int* out /* [16] */) {
   cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); out[15] = v;
 }
 
-extern "C" int hfl_mega_launch(const void* prog, int nphase, int nsteps, void* ctl, const int* nvalid_tab, int grid,
-                               void* prof, cudaStream_t stream) {
+// jobs: device array of `Job` records (all sharing one phase structure); ctl: launch-wide control block (zeroed here).
+extern "C" int hfl_mega_launch(const void* jobs, int njobs, int nphase, int nsteps, void* ctl, int grid, void* prof,
+                               cudaStream_t stream) {
   int e0 = mega_configure();
   if (e0 != 0) return e0;
+  if (njobs < 1 || njobs > MAX_JOBS) return -7;
   cudaError_t e = cudaMemsetAsync(ctl, 0, CTL_WORDS * sizeof(unsigned), stream);
   if (e != cudaSuccess) return (int)e;
-  const Phase* p = reinterpret_cast<const Phase*>(prog);
+  const Job* j = reinterpret_cast<const Job*>(jobs);
   unsigned* c = reinterpret_cast<unsigned*>(ctl);
   unsigned long long* pr = reinterpret_cast<unsigned long long*>(prof);
-  void* args[] = {(void*)&p, (void*)&nphase, (void*)&nsteps, (void*)&c, (void*)&nvalid_tab, (void*)&pr};
+  void* args[] = {(void*)&j, (void*)&njobs, (void*)&nphase, (void*)&nsteps, (void*)&c, (void*)&pr};
   e = cudaLaunchCooperativeKernel((const void*)mega_kernel, dim3(grid), dim3(MG_THREADS), args, (size_t)MG_SMEM, stream);
   hfl::count_launch();
   return (int)e;
 }
+
+extern "C" int hfl_mega_max_jobs() { return MAX_JOBS; }
 
 // Encode a bf16 tiled tensor map (rank 2..5, 128-byte swizzle, zero OOB fill) into `out` (128 bytes, host memory).
 extern "C" int hfl_mega_encode_tmap(void* out, const void* base, int rank, const unsigned long long* dims,

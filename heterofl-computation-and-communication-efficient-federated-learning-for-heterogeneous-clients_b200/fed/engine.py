@@ -306,6 +306,8 @@ class Engine:
             self.setup()
         if not self.use_graph:
             return 0
+        if self._use_mega(self._model_for(self.tables.rates[0])):
+            return 0            # resident-kernel training: nothing to capture
         cfg = self.cfg
         n_act = int(np.ceil(cfg["frac"] * cfg["num_users"]))
         per_rank = int(np.ceil(n_act / self.info.world))
@@ -399,6 +401,10 @@ class Engine:
             out["_test_n"] = {k: v for k, v in test.items() if k.startswith("_")}
         t = tm.tolist()                                       # device -> host read of the round's result
         self.d2h_bytes += 32
+        if getattr(self, "_mega_launched", False):
+            c = self._mega_ctl.tolist()
+            if c[1] != 0:
+                raise RuntimeError("training megakernel aborted (code %d, diag %s)" % (c[1], c[8:14]))
         if self._peer is not None:
             self._peer.check()                                # a peer that never reached a device barrier -> error
         n = max(t[2], 1.0)
@@ -491,6 +497,8 @@ class Engine:
     # -- local training ------------------------------------------------------------------------------------
     def _train_clients(self, user_idx, rates, levels, mine, lr, epoch) -> Dict[int, Dict]:
         cfg, fed = self.cfg, self.federation
+        if mine and all(self._use_mega(self._model_for(rates[i])) for i in mine):
+            return self._train_clients_mega(user_idx, rates, levels, mine, lr, epoch)
         main = torch.cuda.current_stream(self.device) if self.is_cuda else None
         order = sorted(mine, key=lambda i: -client_cost(rates[i], self._client_steps(user_idx[i])))
         pending = deque(order)
@@ -599,6 +607,12 @@ class Engine:
             else:
                 rows = self._h2d(self.train_rows[ridx].pin_memory() if self.is_cuda else self.train_rows[ridx])
             return s.train_lm(rows, epochs, int(cfg["bptt"]))
+        imgs, labs, gen = self._client_data(u, epoch)
+        return s.train_vision(imgs, labs, self.aug_train, epochs, int(cfg["batch_size"]["train"]), gen,
+                              max_n=self._max_shard, max_epochs=int(cfg["num_epochs"]["local"]))
+
+    def _client_data(self, u: int, epoch: int):
+        """(images uint8 [n,H,W,C], labels, per-client RNG) of user ``u`` on the device (H2D bytes accounted)."""
         idx = torch.as_tensor(self.data_split["train"][u], dtype=torch.long)
         if self.train_img.device == self.device:
             di = idx.to(self.device)
@@ -607,8 +621,45 @@ class Engine:
             imgs = self._h2d(self.train_img[idx].pin_memory() if self.is_cuda else self.train_img[idx])
             labs = self._h2d(self.train_lab[idx].pin_memory() if self.is_cuda else self.train_lab[idx])
         gen = torch.Generator().manual_seed((self.seed * 1000003 + epoch * 7919) * 4099 + int(u))
-        return s.train_vision(imgs, labs, self.aug_train, epochs, int(cfg["batch_size"]["train"]), gen,
-                              max_n=self._max_shard, max_epochs=int(cfg["num_epochs"]["local"]))
+        return imgs, labs, gen
+
+    def _train_clients_mega(self, user_idx, rates, levels, mine, lr, epoch) -> Dict[int, Dict]:
+        """Resident-kernel path: the clients of a wave (up to 16) train inside ONE cooperative launch -- lock-step
+        phase programs, shared grid barriers, tiles of all clients interleaved over all SMs (csrc/mega_kernel.cu)."""
+        from .mega_trainer import launch_wave
+        from ..ops import fed_ops
+        cfg, fed = self.cfg, self.federation
+        results: Dict[int, Dict] = {}
+        result_arenas = self._result_arenas([levels[i] for i in mine], mine)
+        order = sorted(mine, key=lambda i: -client_cost(rates[i], self._client_steps(user_idx[i])))
+        epochs, batch = int(cfg["num_epochs"]["local"]), int(cfg["batch_size"]["train"])
+        K = min(int(cu.C().mega_max_jobs()), max(int(self.opt.max_concurrent), 1))
+        if getattr(self, "_mega_ctl", None) is None:
+            self._mega_ctl = torch.zeros(16, dtype=torch.int32, device=self.device)
+            self._mega_cap = int(cu.C().mega_max_grid())
+        for w0 in range(0, len(order), K):
+            wave = order[w0:w0 + K]
+            busy: set = set()
+            slots = []
+            for i in wave:
+                s = self._acquire_slot(levels[i], busy)
+                busy.add(id(s))
+                slots.append(s)
+            fed_ops.distribute(self.tables, self.global_arena, [s.w for s in slots], [levels[i] for i in wave],
+                               [s.wc for s in slots], [s.mom for s in slots])
+            for i, s in zip(wave, slots):
+                u = user_idx[i]
+                s.g.zero_()
+                s.begin_client(lr, fed.user_label_mask(u))
+                imgs, labs, gen = self._client_data(u, epoch)
+                s.prepare_client(imgs, labs, self.aug_train, epochs, batch, gen, max_n=self._max_shard,
+                                 max_epochs=epochs)
+            launch_wave(slots, int(os.environ.get("HFL_MEGA_GRID", "0")) or self._mega_cap, self._mega_ctl)
+            self._mega_launched = True
+            for i, s in zip(wave, slots):
+                result_arenas[i].copy_(s.w, non_blocking=True)
+                results[i] = {"arena": result_arenas[i], "meter": s.meter.buf.clone(), "level": levels[i]}
+        return results
 
     def _result_arenas(self, my_levels: List[int], mine: List[int]) -> Dict[int, torch.Tensor]:
         out = {}

@@ -232,7 +232,8 @@ class Evaluator:
                 "par": torch.zeros(steps, Nc, 3, dtype=torch.int32, device=dev),
                 "nvalid": torch.full((steps,), Nc, dtype=torch.int32, device=dev),
                 "mean": aug.mean.reshape(-1).float().contiguous(), "istd": aug.inv_std.reshape(-1).float().contiguous(),
-                "ctl": torch.zeros(16, dtype=torch.int32, device=dev)}
+                "ctl": torch.zeros(16, dtype=torch.int32, device=dev),
+                "jctl": torch.zeros(16, dtype=torch.int32, device=dev)}
 
     def _sbn_mega(self, global_arena, ds, imgs_src, generator, B, plan) -> Dict:
         """sBN pass: ``per_rank`` chunks of ``Gc`` ghost batches, all inside ONE launch of the phase program (tcgen05
@@ -259,7 +260,8 @@ class Evaluator:
         for a, b in st["acc"].values():
             a.zero_()
             b.zero_()
-        cu.C().mega_launch(st["prog_dev"], len(st["prog"]), per_rank, st["ctl"], st["nvalid"], self.mega_grid)
+        from ..models import mega_resnet as mr
+        mr.launch([(st["prog_dev"], st["nvalid"], st["jctl"], per_rank)], len(st["prog"]), self.mega_grid, st["ctl"])
         acc = {name: (st["acc"][name][0][:w], st["acc"][name][1][:w]) for name, w in bn}
         return self._merge_stats(bn, acc, per_rank * Gc)
 
@@ -286,7 +288,8 @@ class Evaluator:
         for name, (a, b) in self.fused.eval_affine(st["P"], running).items():
             st["affine"][name][0][:a.numel()].copy_(a)
             st["affine"][name][1][:b.numel()].copy_(b)
-        cu.C().mega_launch(st["prog_dev"], len(st["prog"]), per_rank, st["ctl"], None, self.mega_grid)
+        from ..models import mega_resnet as mr
+        mr.launch([(st["prog_dev"], None, st["jctl"], per_rank)], len(st["prog"]), self.mega_grid, st["ctl"])
         idx = st["idx"].view(-1)
         z = st["logits"]
         y = labels_src.to(self.device, non_blocking=True).index_select(0, idx)

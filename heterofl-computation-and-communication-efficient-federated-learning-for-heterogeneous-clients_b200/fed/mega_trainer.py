@@ -18,6 +18,7 @@ import torch
 
 from ..data.pipeline import VisionAugment
 from ..models import Model
+from ..models import mega_resnet as mr
 from ..models.mega_resnet import CTL_WORDS, PHASE_DT, MegaResNet
 from ..ops import cuda as cu
 from ..utils.metrics import DeviceMeter
@@ -56,7 +57,9 @@ class MegaSlot:
         classes = self.net.classes
         self.mask_t = torch.ones(classes, dtype=torch.uint8, device=device)
         self.use_mask = bool(cfg["mask"])
-        self.ctl = torch.zeros(CTL_WORDS, dtype=torch.int32, device=device)
+        self.ctl = torch.zeros(CTL_WORDS, dtype=torch.int32, device=device)      # launch-wide block of solo launches
+        self.jctl = torch.zeros(CTL_WORDS, dtype=torch.int32, device=device)     # per-job scalars (gradient norm)
+        self.pending = None
         self.lr = 0.0
         self._cap_n = 0
         self._cap_steps = 0
@@ -120,9 +123,10 @@ class MegaSlot:
         self.mom.zero_()
         self.g.zero_()
 
-    def train_vision(self, imgs_u8: torch.Tensor, labels: torch.Tensor, aug: VisionAugment, epochs: int, batch: int,
-                     generator: Optional[torch.Generator] = None, max_n: int = 0, max_epochs: int = 0):
-        """Generator with a single step: uploads the step tables and launches the resident kernel once."""
+    def prepare_client(self, imgs_u8: torch.Tensor, labels: torch.Tensor, aug: VisionAugment, epochs: int, batch: int,
+                       generator: Optional[torch.Generator] = None, max_n: int = 0, max_epochs: int = 0):
+        """Upload the step tables of one client (same RNG draws as ``TrainSlot.train_vision``) and return the job tuple
+        ``(program, nvalid table, per-job ctl, nsteps)`` for :func:`mega_resnet.launch`."""
         assert batch == self.batch
         n = imgs_u8.shape[0]
         spe = (n + batch - 1) // batch
@@ -145,8 +149,15 @@ class MegaSlot:
         st["par"][:steps].copy_(params.view(steps, batch, 3), non_blocking=True)
         st["nvalid"][:steps].copy_(nv.view(-1), non_blocking=True)
         self._set_lr(self.lr)
-        cu.C().mega_launch(self.prog_dev, len(self.prog), steps, self.ctl, st["nvalid"], self.grid,
-                           getattr(self, "prof", None))
+        self.pending = (self.prog_dev, st["nvalid"], self.jctl, steps)
+        return self.pending
+
+    def train_vision(self, imgs_u8: torch.Tensor, labels: torch.Tensor, aug: VisionAugment, epochs: int, batch: int,
+                     generator: Optional[torch.Generator] = None, max_n: int = 0, max_epochs: int = 0):
+        """Generator with a single step: uploads the step tables and launches the resident kernel for this client alone
+        (the engine batches the clients of a wave into one launch instead: :func:`launch_wave`)."""
+        job = self.prepare_client(imgs_u8, labels, aug, epochs, batch, generator, max_n, max_epochs)
+        mr.launch([job], len(self.prog), self.grid, self.ctl, getattr(self, "prof", None))
         self.launches += 1
         yield
 
@@ -159,3 +170,14 @@ class MegaSlot:
 
     def metrics(self) -> Dict[str, float]:
         return self.meter.result("Local-", lm=False)
+
+
+def launch_wave(slots, grid: int, ctl: torch.Tensor, prof: Optional[torch.Tensor] = None) -> None:
+    """Train the prepared clients of ``slots`` in ONE cooperative launch (lock-step phases, shared grid barriers)."""
+    order = sorted(slots, key=lambda s: -s.model.rate)            # heaviest tiles first
+    nph = len(order[0].prog)
+    assert all(len(s.prog) == nph and s.pending is not None for s in order)
+    mr.launch([s.pending for s in order], nph, grid, ctl, prof)
+    for s in order:
+        s.pending = None
+        s.launches += 1

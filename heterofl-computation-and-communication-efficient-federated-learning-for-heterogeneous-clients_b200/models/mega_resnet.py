@@ -131,6 +131,16 @@ class Program:
         return t.to(device)
 
 
+def launch(jobs, nphase: int, grid: int, ctl: torch.Tensor, prof: Optional[torch.Tensor] = None) -> None:
+    """One cooperative launch of ``csrc/mega_kernel.cu`` over ``jobs`` = [(prog_dev, nvalid_tab | None, jctl, nsteps)]:
+    the jobs advance through their (structurally identical) phase programs in lock step and share every grid barrier;
+    a job idles once its own ``nsteps`` are done.  Heaviest job first gives the best tile balance."""
+    rows = [[int(pd.data_ptr()), 0 if nv is None else int(nv.data_ptr()), int(jc.data_ptr()), int(ns)]
+            for (pd, nv, jc, ns) in jobs]
+    jt = torch.tensor(rows, dtype=torch.int64).to(ctl.device, non_blocking=True)
+    cu.C().mega_launch(jt, int(nphase), max(int(r[3]) for r in rows), ctl, int(grid), prof)
+
+
 # --------------------------------------------------------------------------------------------------------------
 # phase emitters
 # --------------------------------------------------------------------------------------------------------------
