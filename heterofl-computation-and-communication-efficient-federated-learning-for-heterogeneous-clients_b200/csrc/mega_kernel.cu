@@ -30,16 +30,19 @@ namespace hfl {
 namespace mega {
 
 constexpr int MG_THREADS = 256;
-constexpr int MG_STAGES = 6;
+constexpr int MG_STAGES = 5;
 constexpr int MG_A_BYTES = 16384;
 constexpr int MG_STAGE_BYTES = 32768;
-constexpr int MG_SMEM = MG_STAGES * MG_STAGE_BYTES + 1024 + 256;
-constexpr uint32_t MG_TMEM_COLS = 128;
+constexpr int MG_WG_PITCH = 64 * 4 + 16;                       // wgrad epilogue staging row pitch (bytes)
+constexpr int MG_WG_STAGING = 4 * 32 * MG_WG_PITCH;            // dedicated: the TMA producer runs ahead of the epilogue
+constexpr int MG_SMEM = MG_STAGES * MG_STAGE_BYTES + MG_WG_STAGING + 1024 + 256;
+constexpr uint32_t MG_TMEM_COLS = 256;                         // two 128-column accumulators (epilogue / MMA overlap)
 constexpr int HDR_WORDS = 96;   // op..pv = 384 bytes of a Phase (the tensor maps are read in place from global memory)
 
 struct Ctx {
   uint8_t* smem;
-  uint64_t *full, *empty, *tfull;
+  uint64_t *full, *empty, *tfull, *tempty;   // smem ring; TMEM accumulator full / empty (x2)
+  uint8_t* wg_stage;
   uint32_t tmem;
   unsigned* ctl;          // launch-wide: barrier counter, abort flag, diagnostics
   unsigned* jctl;         // per job: gradient-norm accumulator
@@ -128,6 +131,14 @@ __device__ __forceinline__ void ld8f(const float* p, float (&f)[8]) {
 __device__ __forceinline__ float ldbf(const bf16* p) {
   return __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(p))));
 }
+// fire-and-forget fp32 reductions on GLOBAL addresses (atomicAdd on a generic pointer compiles to a shared/global
+// dispatch with a CAS loop for the shared case)
+__device__ __forceinline__ void red_add(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add4(float* p, const float4& v) {
+  asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ float bfr(float v) { return __bfloat162float(__float2bfloat16(v)); }
 
 // Column sums over the 32 lanes of a warp: on return lane j holds sum_over_lanes(v[j]) in v[0]  (31 shuffles).
@@ -147,259 +158,386 @@ __device__ __forceinline__ void warp_col_reduce(float (&v)[32], int lane) {
 // ------------------------------------------------------------------------------------------------------------ OP_CONV
 // iv: 0 N  1 OH  2 OW  3 bn  4 bh  5 bw  6 tiles_h  7 m_tiles  8 n_tiles  9 block_n  10 Cy  11 out_H  12 out_W
 //     13 out_s  14 out_ph  15 out_pw  16 in_stride  17 b_mn  18 ntaps  19 has_res  20 has_stats  21 group_n
-//     22 num_k  23 a_bytes  24 b_bytes  25 use_nvalid  26.. taps (2 words each)
-// pv: 0 out  1 residual  2 stats [G][2][Cy];   tm: 0,1 activation maps   2,3 filter maps
-__device__ __noinline__ void conv_tile(const Phase* __restrict__ Pg, const Phase& P, Ctx& cx, int tile) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+//     22 num_k  23 a_bytes  24 b_bytes  25 use_nvalid  26..43 taps (2 words each: 9 taps);  header word `flags` = ksplit
+// pv: 0 out  1 residual  2 stats [G][2][Cy]  3 split-K scratch (fp32, same indexing as out)  11 split-K tile counters
+// tm: 0,1 activation maps   2,3 filter maps
+//
+// The three roles (TMA producer = warp 0, MMA issuer = warp 1, epilogue = warps 4-7) each walk the CTA's tile sequence
+// of the phase on their own: the producer runs ahead through the smem ring, the MMA warp alternates between two TMEM
+// accumulators, so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
+// Split-K (flags > 1): the k-blocks of one output tile are dealt to `ksplit` work items; each adds its partial
+// accumulator to an fp32 scratch with 16-byte reductions, and the LAST item to arrive (per-tile counter) re-reads the
+// sum, re-zeroes the scratch and runs the normal epilogue -- no extra phase, no extra grid barrier.
+struct ConvTileId { int n_blk, n0, oh0, kb0, kb1, mn; };
+
+__device__ __forceinline__ ConvTileId conv_decode(const Phase& P, int lt) {
+  ConvTileId c;
   const int* iv = P.iv;
-  const int n_tiles = iv[8], BN = iv[9];
-  const int n_blk = tile % n_tiles, m_tile = tile / n_tiles;
+  const int ksplit = P.flags > 1 ? P.flags : 1;
+  const int ks = lt % ksplit;
+  c.mn = lt / ksplit;
+  const int n_tiles = iv[8];
+  c.n_blk = c.mn % n_tiles;
+  const int m_tile = c.mn / n_tiles;
   const int tiles_h = iv[6];
   const int tile_n = m_tile / tiles_h, tile_h = m_tile - tile_n * tiles_h;
-  const int bn = iv[3], bh = iv[4], bw = iv[5];
-  const int n0 = tile_n * bn, oh0 = tile_h * bh;
+  c.n0 = tile_n * iv[3];
+  c.oh0 = tile_h * iv[4];
   const int num_k = iv[22];
-  const int b_mn = iv[17];
-  const uint32_t k0 = cx.kctr;
+  const int per = (num_k + ksplit - 1) / ksplit;
+  c.kb0 = ks * per;
+  c.kb1 = min(num_k, c.kb0 + per);
+  return c;
+}
 
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t kc = k0;
-      const int ntaps = iv[18], in_stride = iv[16];
-      const uint32_t tx = (uint32_t)(iv[23] + iv[24]);
-      bool live = tile_guard(Pg, P, cx, tile, 0) && tile_guard(Pg, P, cx, tile, 2);
-      for (int t = 0; t < ntaps && live; ++t) {
-        const int w0 = iv[26 + 2 * t], w1 = iv[27 + 2 * t];
-        const int a_map = w0 & 15, b_map = (w0 >> 4) & 15, b_tap = (w0 >> 8) & 255, kb_t = (w0 >> 16) & 0xffff;
-        const int dh = (int)(short)(w1 & 0xffff), dw = (int)(short)((w1 >> 16) & 0xffff);
-        const CUtensorMap* am = &Pg->tm[a_map];
-        const CUtensorMap* bm = &Pg->tm[2 + b_map];
-        for (int cb = 0; cb < kb_t; ++cb, ++kc) {
-          const int st = kc % MG_STAGES;
-          const uint32_t ph = (kc / MG_STAGES) & 1;
-          if (!mbar_wait_b(&cx.empty[st], ph ^ 1, cx.ctl)) { live = false; break; }
-          uint8_t* sa = cx.smem + st * MG_STAGE_BYTES;
-          uint8_t* sb = sa + MG_A_BYTES;
-          mbar_expect_tx(&cx.full[st], tx);
-          tma_load_4d(sa, am, &cx.full[st], cb * 64, dw, oh0 * in_stride + dh, n0);
-          if (!b_mn) {
-            tma_load_3d(sb, bm, &cx.full[st], cb * 64, b_tap, n_blk * BN);
-          } else {
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_3d(sb + j * 8192, bm, &cx.full[st], n_blk * BN + j * 64, b_tap, cb * 64);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(128, BN, false, b_mn != 0);
-    uint32_t kc = k0;
-    for (int kb = 0; kb < num_k; ++kb, ++kc) {
+// warp 0, lane 0
+__device__ __noinline__ bool conv_produce(const Phase* __restrict__ Pg, const Phase& P, Ctx& cx, int lt) {
+  const int* iv = P.iv;
+  const ConvTileId c = conv_decode(P, lt);
+  const int BN = iv[9], b_mn = iv[17], ntaps = iv[18], in_stride = iv[16];
+  const uint32_t tx = (uint32_t)(iv[23] + iv[24]);
+  if (cx.step == 0 && !(tile_guard(Pg, P, cx, lt, 0) && tile_guard(Pg, P, cx, lt, 2))) return false;
+  int kb = 0;
+  for (int t = 0; t < ntaps; ++t) {
+    const int w0 = iv[26 + 2 * t], w1 = iv[27 + 2 * t];
+    const int a_map = w0 & 15, b_map = (w0 >> 4) & 15, b_tap = (w0 >> 8) & 255, kb_t = (w0 >> 16) & 0xffff;
+    if (kb + kb_t <= c.kb0 || kb >= c.kb1) { kb += kb_t; continue; }
+    const int dh = (int)(short)(w1 & 0xffff), dw = (int)(short)((w1 >> 16) & 0xffff);
+    const CUtensorMap* am = &Pg->tm[a_map];
+    const CUtensorMap* bm = &Pg->tm[2 + b_map];
+    for (int cb = 0; cb < kb_t; ++cb, ++kb) {
+      if (kb < c.kb0 || kb >= c.kb1) continue;
+      const uint32_t kc = cx.kctr++;
       const int st = kc % MG_STAGES;
       const uint32_t ph = (kc / MG_STAGES) & 1;
-      if (!mbar_wait_b(&cx.full[st], ph, cx.ctl)) break;
-      tcgen05_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(cx.smem + st * MG_STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc_sw128(a_addr);
-        const uint64_t bdesc = b_mn ? make_smem_desc_sw128_mn(a_addr + MG_A_BYTES) : make_smem_desc_sw128(a_addr + MG_A_BYTES);
-        const uint64_t b_step = b_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(cx.tmem, adesc + 2 * k, bdesc + b_step * k, idesc, (kb | k) != 0);
-        umma_commit(&cx.empty[st]);
-        if (kb == num_k - 1) umma_commit(cx.tfull);
+      if (!mbar_wait_b(&cx.empty[st], ph ^ 1, cx.ctl)) return false;
+      uint8_t* sa = cx.smem + st * MG_STAGE_BYTES;
+      uint8_t* sb = sa + MG_A_BYTES;
+      mbar_expect_tx(&cx.full[st], tx);
+      tma_load_4d(sa, am, &cx.full[st], cb * 64, dw, c.oh0 * in_stride + dh, c.n0);
+      if (!b_mn) {
+        tma_load_3d(sb, bm, &cx.full[st], cb * 64, b_tap, c.n_blk * BN);
+      } else {
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_3d(sb + j * 8192, bm, &cx.full[st], c.n_blk * BN + j * 64, b_tap, cb * 64);
       }
-      __syncwarp();
-    }
-  } else if (warp >= 4) {
-    const int q = warp - 4;
-    if (mbar_wait_b(cx.tfull, cx.tctr & 1, cx.ctl)) {
-      tcgen05_fence_after();
-      const int m = q * 32 + lane;                       // pixel within the brick: ((n_l*bh + h_l)*bw + w_l)
-      const int w_l = m % bw;
-      const int t = m / bw;
-      const int h_l = t % bh, n_l = t / bh;
-      const int n = n0 + n_l, oh = oh0 + h_l;
-      const int nlim = iv[25] ? min(iv[0], cx.nvalid) : iv[0];
-      const bool ok = (m < bn * bh * bw) && (n < nlim) && (oh < iv[1]);
-      const int Cy = iv[10];
-      const size_t pix = ((size_t)n * iv[11] + (size_t)(oh * iv[13] + iv[14])) * iv[12] + (size_t)(w_l * iv[13] + iv[15]);
-      bf16* Y = reinterpret_cast<bf16*>(P.pv[0]);
-      const bf16* res = iv[19] ? reinterpret_cast<const bf16*>(P.pv[1]) : nullptr;
-      float* stats = nullptr;
-      if (iv[20]) {
-        const int g = iv[21] > 0 ? n0 / iv[21] : 0;
-        stats = reinterpret_cast<float*>(P.pv[2]) + (size_t)g * 2 * Cy;
-      }
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int col0 = n_blk * BN + c0;
-        if (col0 >= Cy) break;                           // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(cx.tmem + (uint32_t(q * 32) << 16) + c0, v);
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = ok ? __uint_as_float(v[j]) : 0.f;
-        const int ncol = min(32, Cy - col0);             // multiple of 8
-        if (ok) {
-          bf16* dst = Y + pix * Cy + col0;
-          if (res != nullptr) {
-            const bf16* rp = res + pix * Cy + col0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (8 * j < ncol) {
-                float r8[8];
-                ld8(rp + 8 * j, r8);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[8 * j + e] += r8[e];
-              }
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float o8[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o8[e] = f[8 * j + e];
-            const uint4 u = pack8(o8);
-            if (8 * j < ncol) *reinterpret_cast<uint4*>(dst + 8 * j) = u;
-            float b8[8];
-            unpack8(u, b8);                              // statistics of the bf16-rounded values (what a reader sees)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[8 * j + e] = b8[e];
-          }
-        }
-        if (stats != nullptr) {
-          float s2[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) s2[j] = f[j] * f[j];
-          warp_col_reduce(f, lane);
-          warp_col_reduce(s2, lane);
-          if (lane < ncol) {
-            atomicAdd(&stats[col0 + lane], f[0]);
-            atomicAdd(&stats[Cy + col0 + lane], s2[0]);
-          }
-        }
-      }
-      tcgen05_fence_before();
     }
   }
-  cx.kctr = k0 + (uint32_t)num_k;
-  cx.tctr += 1;
-  __syncthreads();
+  return true;
+}
+
+// warp 1 (all lanes; lane 0 issues)
+__device__ __noinline__ bool conv_mma(const Phase& P, Ctx& cx, int lt) {
+  const int* iv = P.iv;
+  const ConvTileId c = conv_decode(P, lt);
+  const int lane = threadIdx.x & 31;
+  const int BN = iv[9], b_mn = iv[17];
+  const int nk = c.kb1 - c.kb0;
+  const uint32_t idesc = make_idesc_bf16(128, BN, false, b_mn != 0);
+  const uint32_t tc = cx.tctr++;
+  const uint32_t acc = tc & 1u, use = tc >> 1;
+  if (!mbar_wait_b(&cx.tempty[acc], (use & 1u) ^ 1u, cx.ctl)) return false;   // epilogue drained this accumulator
+  tcgen05_fence_after();
+  const uint32_t tmem_d = cx.tmem + acc * 128u;
+  for (int i = 0; i < nk; ++i) {
+    const uint32_t kc = cx.kctr++;
+    const int st = kc % MG_STAGES;
+    const uint32_t ph = (kc / MG_STAGES) & 1;
+    if (!mbar_wait_b(&cx.full[st], ph, cx.ctl)) return false;
+    tcgen05_fence_after();
+    if (lane == 0) {
+      const uint32_t a_addr = smem_u32(cx.smem + st * MG_STAGE_BYTES);
+      const uint64_t adesc = make_smem_desc_sw128(a_addr);
+      const uint64_t bdesc = b_mn ? make_smem_desc_sw128_mn(a_addr + MG_A_BYTES) : make_smem_desc_sw128(a_addr + MG_A_BYTES);
+      const uint64_t b_step = b_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + b_step * k, idesc, (i | k) != 0);
+      umma_commit(&cx.empty[st]);
+      if (i == nk - 1) umma_commit(&cx.tfull[acc]);
+    }
+    __syncwarp();
+  }
+  return true;
+}
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// warps 4..7
+__device__ __noinline__ bool conv_epilogue(const Phase& P, Ctx& cx, int lt, int* s_flag) {
+  const int* iv = P.iv;
+  const ConvTileId c = conv_decode(P, lt);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp - 4;
+  const int BN = iv[9];
+  const int bn = iv[3], bh = iv[4], bw = iv[5];
+  const uint32_t tc = cx.tctr++;
+  const uint32_t acc = tc & 1u, use = tc >> 1;
+  if (!mbar_wait_b(&cx.tfull[acc], use & 1u, cx.ctl)) return false;
+  tcgen05_fence_after();
+  const uint32_t tmem_d = cx.tmem + acc * 128u;
+  const int m = q * 32 + lane;                       // pixel within the brick: ((n_l*bh + h_l)*bw + w_l)
+  const int w_l = m % bw;
+  const int t = m / bw;
+  const int h_l = t % bh, n_l = t / bh;
+  const int n = c.n0 + n_l, oh = c.oh0 + h_l;
+  const int nlim = iv[25] ? min(iv[0], cx.nvalid) : iv[0];
+  const bool ok = (m < bn * bh * bw) && (n < nlim) && (oh < iv[1]);
+  const int Cy = iv[10];
+  const size_t pix = ((size_t)n * iv[11] + (size_t)(oh * iv[13] + iv[14])) * iv[12] + (size_t)(w_l * iv[13] + iv[15]);
+  bf16* Y = reinterpret_cast<bf16*>(P.pv[0]);
+  const bf16* res = iv[19] ? reinterpret_cast<const bf16*>(P.pv[1]) : nullptr;
+  float* stats = nullptr;
+  if (iv[20]) {
+    const int g = iv[21] > 0 ? c.n0 / iv[21] : 0;
+    stats = reinterpret_cast<float*>(P.pv[2]) + (size_t)g * 2 * Cy;
+  }
+  const int ksplit = P.flags > 1 ? P.flags : 1;
+  float* scratch = reinterpret_cast<float*>(P.pv[3]);
+  bool finalize = true;
+  if (ksplit > 1) {
+    // ---- partial accumulator -> fp32 scratch
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      const int col0 = c.n_blk * BN + c0;
+      if (col0 >= Cy) break;
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_d + (uint32_t(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      if (ok) {
+        float* dst = scratch + pix * Cy + col0;
+        const int ncol = min(32, Cy - col0);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (j < ncol)
+            red_add4(dst + j, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                          __uint_as_float(v[j + 3])));
+      }
+    }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&cx.tempty[acc]);
+    __threadfence();
+    epi_bar();
+    if (threadIdx.x == 128) {
+      int* ctr = reinterpret_cast<int*>(P.pv[11]) + c.mn;
+      const int old = atomicAdd(ctr, 1);
+      const int last = (old == ksplit - 1) ? 1 : 0;
+      if (last) *ctr = 0;
+      *s_flag = last;
+    }
+    epi_bar();
+    finalize = (*s_flag != 0);
+    epi_bar();                                        // everyone has read the flag before the next tile rewrites it
+    if (finalize) __threadfence();
+  }
+  if (finalize) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      const int col0 = c.n_blk * BN + c0;
+      if (col0 >= Cy) break;                           // warp-uniform
+      const int ncol = min(32, Cy - col0);             // multiple of 8
+      float f[32];
+      if (ksplit == 1) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_d + (uint32_t(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = ok ? __uint_as_float(v[j]) : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = 0.f;
+        if (ok) {
+          float4* sp = reinterpret_cast<float4*>(scratch + pix * Cy + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (4 * j < ncol) {
+              const float4 a = __ldcg(sp + j);
+              f[4 * j] = a.x; f[4 * j + 1] = a.y; f[4 * j + 2] = a.z; f[4 * j + 3] = a.w;
+              sp[j] = make_float4(0.f, 0.f, 0.f, 0.f);     // re-arm the scratch for the next step
+            }
+          }
+        }
+      }
+      if (ok) {
+        bf16* dst = Y + pix * Cy + col0;
+        if (res != nullptr) {
+          const bf16* rp = res + pix * Cy + col0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (8 * j < ncol) {
+              float r8[8];
+              ld8(rp + 8 * j, r8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[8 * j + e] += r8[e];
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float o8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o8[e] = f[8 * j + e];
+          const uint4 u = pack8(o8);
+          if (8 * j < ncol) *reinterpret_cast<uint4*>(dst + 8 * j) = u;
+          float b8[8];
+          unpack8(u, b8);                              // statistics of the bf16-rounded values (what a reader sees)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[8 * j + e] = b8[e];
+        }
+      }
+      if (stats != nullptr) {
+        float s2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s2[j] = f[j] * f[j];
+        warp_col_reduce(f, lane);
+        warp_col_reduce(s2, lane);
+        if (lane < ncol) {
+          red_add(&stats[col0 + lane], f[0]);
+          red_add(&stats[Cy + col0 + lane], s2[0]);
+        }
+      }
+    }
+  }
+  if (ksplit == 1) {
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&cx.tempty[acc]);
+  }
+  return true;
 }
 
 // ----------------------------------------------------------------------------------------------------------- OP_WGRAD
 // iv: 0 N  1 OH  2 OW  3 bn  4 bh  5 bw  6 bricks_h  7 bricks  8 splits  9 C_real  10 Kout_real  11 taps  12 S
 //     13 stride  14 pad  15 k_blks  16 c_blks  17 a_boxes
 // pv: 0 dW (fp32 [Kout][taps][C_real]);   tm: 0 dY map, 1 X map
-__device__ __noinline__ void wgrad_tile(const Phase* __restrict__ Pg, const Phase& P, Ctx& cx, int tile) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int* iv = P.iv;
+struct WgTileId { int k_blk, c_blk, tap, r, s, b0, num_k; };
+
+__device__ __forceinline__ WgTileId wg_decode(const int* iv, int lt) {
+  WgTileId w;
   const int splits = iv[8], taps = iv[11], c_blks = iv[16];
-  int t = tile;
+  int t = lt;
   const int split = t % splits; t /= splits;
-  const int tap = t % taps; t /= taps;
-  const int c_blk = t % c_blks;
-  const int k_blk = t / c_blks;
-  const int r = tap / iv[12], s = tap - r * iv[12];
+  w.tap = t % taps; t /= taps;
+  w.c_blk = t % c_blks;
+  w.k_blk = t / c_blks;
+  w.r = w.tap / iv[12];
+  w.s = w.tap - w.r * iv[12];
   const int bricks = iv[7];
   const int per = (bricks + splits - 1) / splits;
-  const int b0 = split * per, b1 = min(b0 + per, bricks);
-  const int num_k = b1 - b0;
-  if (num_k <= 0) return;                                // uniform over the CTA
-  const uint32_t k0 = cx.kctr;
-  const int a_boxes = iv[17];
+  w.b0 = split * per;
+  w.num_k = max(0, min(w.b0 + per, bricks) - w.b0);
+  return w;
+}
 
-  if (warp == 0) {
+__device__ __noinline__ bool wgrad_produce(const Phase* __restrict__ Pg, const Phase& P, Ctx& cx, int lt) {
+  const int* iv = P.iv;
+  const WgTileId w = wg_decode(iv, lt);
+  if (w.num_k <= 0) return true;
+  if (cx.step == 0 && !(tile_guard(Pg, P, cx, lt, 0) && tile_guard(Pg, P, cx, lt, 1))) return false;
+  const int a_boxes = iv[17];
+  const int bricks_h = iv[6], bn = iv[3], bh = iv[4], stride = iv[13], pad = iv[14];
+  const uint32_t tx = (uint32_t)(a_boxes * 8192 + 8192);
+  for (int kb = 0; kb < w.num_k; ++kb) {
+    const uint32_t kc = cx.kctr++;
+    const int st = kc % MG_STAGES;
+    const uint32_t ph = (kc / MG_STAGES) & 1;
+    const int brick = w.b0 + kb;
+    const int tn = brick / bricks_h, th = brick - tn * bricks_h;
+    const int n0 = tn * bn, oh0 = th * bh;
+    if (!mbar_wait_b(&cx.empty[st], ph ^ 1, cx.ctl)) return false;
+    uint8_t* sa = cx.smem + st * MG_STAGE_BYTES;
+    uint8_t* sb = sa + MG_A_BYTES;
+    mbar_expect_tx(&cx.full[st], tx);
+    tma_load_4d(sa, &Pg->tm[0], &cx.full[st], w.k_blk * 128, 0, oh0, n0);
+    if (a_boxes == 2) tma_load_4d(sa + 8192, &Pg->tm[0], &cx.full[st], w.k_blk * 128 + 64, 0, oh0, n0);
+    tma_load_4d(sb, &Pg->tm[1], &cx.full[st], w.c_blk * 64, w.s - pad, oh0 * stride + w.r - pad, n0);
+  }
+  return true;
+}
+
+__device__ __noinline__ bool wgrad_mma(const Phase& P, Ctx& cx, int lt) {
+  const WgTileId w = wg_decode(P.iv, lt);
+  if (w.num_k <= 0) return true;
+  const int lane = threadIdx.x & 31;
+  const uint32_t idesc = make_idesc_bf16(128, 64, true, true);
+  const uint32_t tc = cx.tctr++;
+  const uint32_t acc = tc & 1u, use = tc >> 1;
+  if (!mbar_wait_b(&cx.tempty[acc], (use & 1u) ^ 1u, cx.ctl)) return false;
+  tcgen05_fence_after();
+  const uint32_t tmem_d = cx.tmem + acc * 128u;
+  for (int kb = 0; kb < w.num_k; ++kb) {
+    const uint32_t kc = cx.kctr++;
+    const int st = kc % MG_STAGES;
+    const uint32_t ph = (kc / MG_STAGES) & 1;
+    if (!mbar_wait_b(&cx.full[st], ph, cx.ctl)) return false;
+    tcgen05_fence_after();
     if (lane == 0) {
-      uint32_t kc = k0;
-      const int bricks_h = iv[6], bn = iv[3], bh = iv[4], stride = iv[13], pad = iv[14];
-      const uint32_t tx = (uint32_t)(a_boxes * 8192 + 8192);
-      const bool live = tile_guard(Pg, P, cx, tile, 0) && tile_guard(Pg, P, cx, tile, 1);
-      for (int kb = 0; kb < num_k && live; ++kb, ++kc) {
-        const int st = kc % MG_STAGES;
-        const uint32_t ph = (kc / MG_STAGES) & 1;
-        const int brick = b0 + kb;
-        const int tn = brick / bricks_h, th = brick - tn * bricks_h;
-        const int n0 = tn * bn, oh0 = th * bh;
-        if (!mbar_wait_b(&cx.empty[st], ph ^ 1, cx.ctl)) break;
-        uint8_t* sa = cx.smem + st * MG_STAGE_BYTES;
-        uint8_t* sb = sa + MG_A_BYTES;
-        mbar_expect_tx(&cx.full[st], tx);
-        tma_load_4d(sa, &Pg->tm[0], &cx.full[st], k_blk * 128, 0, oh0, n0);
-        if (a_boxes == 2) tma_load_4d(sa + 8192, &Pg->tm[0], &cx.full[st], k_blk * 128 + 64, 0, oh0, n0);
-        tma_load_4d(sb, &Pg->tm[1], &cx.full[st], c_blk * 64, s - pad, oh0 * stride + r - pad, n0);
-      }
-    }
-  } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(128, 64, true, true);
-    uint32_t kc = k0;
-    for (int kb = 0; kb < num_k; ++kb, ++kc) {
-      const int st = kc % MG_STAGES;
-      const uint32_t ph = (kc / MG_STAGES) & 1;
-      if (!mbar_wait_b(&cx.full[st], ph, cx.ctl)) break;
-      tcgen05_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(cx.smem + st * MG_STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc_sw128_mn(a_addr);
-        const uint64_t bdesc = make_smem_desc_sw128_mn(a_addr + MG_A_BYTES);
+      const uint32_t a_addr = smem_u32(cx.smem + st * MG_STAGE_BYTES);
+      const uint64_t adesc = make_smem_desc_sw128_mn(a_addr);
+      const uint64_t bdesc = make_smem_desc_sw128_mn(a_addr + MG_A_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)      // 64 pixels = 4 x UMMA_K(16); +16 k-rows = +2048 B
-          umma_bf16(cx.tmem, adesc + (2048 >> 4) * k, bdesc + (2048 >> 4) * k, idesc, (kb | k) != 0);
-        umma_commit(&cx.empty[st]);
-        if (kb == num_k - 1) umma_commit(cx.tfull);
-      }
-      __syncwarp();
+      for (int k = 0; k < 4; ++k)      // 64 pixels = 4 x UMMA_K(16); +16 k-rows = +2048 B
+        umma_bf16(tmem_d, adesc + (2048 >> 4) * k, bdesc + (2048 >> 4) * k, idesc, (kb | k) != 0);
+      umma_commit(&cx.empty[st]);
+      if (kb == w.num_k - 1) umma_commit(&cx.tfull[acc]);
     }
-  } else if (warp >= 4) {
-    const int q = warp - 4;
-    if (mbar_wait_b(cx.tfull, cx.tctr & 1, cx.ctl)) {
-      tcgen05_fence_after();
-      // stage the warp's 32 x 64 fp32 block in shared memory (the pipeline stages are idle: every TMA load of this tile
-      // has been consumed), then accumulate whole filter rows with 16-byte atomics
-      constexpr int PITCH = 64 * 4 + 16;
-      uint8_t* my = cx.smem + (size_t)q * 32 * PITCH;
-      {
-        uint8_t* myrow = my + lane * PITCH;
+    __syncwarp();
+  }
+  return true;
+}
+
+__device__ __noinline__ bool wgrad_epilogue(const Phase& P, Ctx& cx, int lt) {
+  const int* iv = P.iv;
+  const WgTileId w = wg_decode(iv, lt);
+  if (w.num_k <= 0) return true;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp - 4;
+  const uint32_t tc = cx.tctr++;
+  const uint32_t acc = tc & 1u, use = tc >> 1;
+  if (!mbar_wait_b(&cx.tfull[acc], use & 1u, cx.ctl)) return false;
+  tcgen05_fence_after();
+  const uint32_t tmem_d = cx.tmem + acc * 128u;
+  // stage the warp's 32 x 64 fp32 block in (dedicated) shared memory, then accumulate whole filter rows with 16-byte
+  // reductions (a row per thread would touch 32 different rows per instruction)
+  uint8_t* my = cx.wg_stage + (size_t)q * 32 * MG_WG_PITCH;
+  {
+    uint8_t* myrow = my + lane * MG_WG_PITCH;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(cx.tmem + (uint32_t(q * 32) << 16) + c0, v);
-          tmem_ld_wait();
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_d + (uint32_t(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<uint4*>(myrow + (c0 + j) * 4) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-      }
-      __syncwarp();
-      const int C = iv[9], Kout = iv[10];
-      float* dW = reinterpret_cast<float*>(P.pv[0]);
-      const int rsub = lane >> 4, cseg = (lane & 15) * 4;
-      const bool vec = (C & 3) == 0;
-#pragma unroll 4
-      for (int r0 = 0; r0 < 32; r0 += 2) {
-        const int k = k_blk * 128 + q * 32 + r0 + rsub;
-        const int c = c_blk * 64 + cseg;
-        if (k < Kout && c < C) {
-          const float4 val = *reinterpret_cast<const float4*>(my + (r0 + rsub) * PITCH + cseg * 4);
-          float* dst = dW + ((size_t)k * taps + tap) * C + c;
-          if (vec) {
-            atomicAdd(reinterpret_cast<float4*>(dst), val);
-          } else {
-            atomicAdd(dst, val.x);
-            if (c + 1 < C) atomicAdd(dst + 1, val.y);
-            if (c + 2 < C) atomicAdd(dst + 2, val.z);
-            if (c + 3 < C) atomicAdd(dst + 3, val.w);
-          }
-        }
-      }
-      tcgen05_fence_before();
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<uint4*>(myrow + (c0 + j) * 4) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
   }
-  cx.kctr = k0 + (uint32_t)num_k;
-  cx.tctr += 1;
-  __syncthreads();
+  tcgen05_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&cx.tempty[acc]);          // the accumulator is free: the next tile's MMAs may start
+  const int C = iv[9], Kout = iv[10], taps = iv[11];
+  float* dW = reinterpret_cast<float*>(P.pv[0]);
+  const int rsub = lane >> 4, cseg = (lane & 15) * 4;
+  const bool vec = (C & 3) == 0;
+#pragma unroll 4
+  for (int r0 = 0; r0 < 32; r0 += 2) {
+    const int k = w.k_blk * 128 + q * 32 + r0 + rsub;
+    const int cc = w.c_blk * 64 + cseg;
+    if (k < Kout && cc < C) {
+      const float4 val = *reinterpret_cast<const float4*>(my + (r0 + rsub) * MG_WG_PITCH + cseg * 4);
+      float* dst = dW + ((size_t)k * taps + w.tap) * C + cc;
+      if (vec) {
+        red_add4(dst, val);
+      } else {
+        red_add(dst, val.x);
+        if (cc + 1 < C) red_add(dst + 1, val.y);
+        if (cc + 2 < C) red_add(dst + 2, val.z);
+        if (cc + 3 < C) red_add(dst + 3, val.w);
+      }
+    }
+  }
+  __syncwarp();                                          // staging rows are rewritten by the next tile
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------- normalisation phases
@@ -469,8 +607,8 @@ __device__ __noinline__ void napply_item(const Phase& P, Ctx& cx, int item) {
         if (c0 + e < iv[2]) {
           const float mean = nc.mean[e];
           const float var = fmaxf(__ldcg(S + Cp + c0 + e) / cnt - mean * mean, 0.f);
-          atomicAdd(am + c0 + e, mean * P.fv[1]);
-          atomicAdd(av + c0 + e, var * (cnt / fmaxf(cnt - 1.f, 1.f)) * P.fv[2]);
+          red_add(am + c0 + e, mean * P.fv[1]);
+          red_add(av + c0 + e, var * (cnt / fmaxf(cnt - 1.f, 1.f)) * P.fv[2]);
         }
       }
     }
@@ -555,8 +693,8 @@ __device__ __noinline__ void nbwd_item(const Phase& P, Ctx& cx, int item, bool a
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         if (c0 + e < Cr) {
-          atomicAdd(T + c0 + e, red[threadIdx.x * 16 + e]);
-          atomicAdd(T + Cp + c0 + e, red[threadIdx.x * 16 + 8 + e]);
+          red_add(T + c0 + e, red[threadIdx.x * 16 + e]);
+          red_add(T + Cp + c0 + e, red[threadIdx.x * 16 + 8 + e]);
         }
       }
     }
@@ -617,32 +755,49 @@ __device__ __noinline__ void head_train(const Phase& P, Ctx& cx) {
   const int* iv = P.iv;
   const int N = iv[9] ? min(iv[0], cx.nvalid) : iv[0], Nal = iv[0], HW = iv[1], Cp = iv[2], C = iv[3], Kc = iv[4];
   const int tid = threadIdx.x, nt = MG_THREADS, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-  float* pooled = reinterpret_cast<float*>(cx.smem);        // [Nal][C]
-  float* logit = pooled + Nal * C;                          // [Nal][Kc]  (becomes dlogits)
+  // everything the head touches more than once is staged in shared memory with 16-byte loads: the pooled activations,
+  // the classifier weights, the logits / dlogits
+  float* pooled = reinterpret_cast<float*>(cx.smem);        // [Nal][Cp]
+  float* logit = pooled + Nal * Cp;                         // [Nal][Kc]  (becomes dlogits)
   float* red = logit + Nal * Kc;                            // [2*Nal]
+  bf16* Ws = reinterpret_cast<bf16*>(red + 2 * Nal + ((2 * Nal) & 1) + 2);   // [Kc][Cp] classifier weights (8 B aligned)
   const bf16* Z = reinterpret_cast<const bf16*>(P.pv[0]);
   const bf16* W = reinterpret_cast<const bf16*>(P.pv[1]);
   const bf16* Bv = reinterpret_cast<const bf16*>(P.pv[2]);
   const int* lab = reinterpret_cast<const int*>(P.pv[3]);
   const unsigned char* mask = reinterpret_cast<const unsigned char*>(P.pv[4]);
   const float inv_hw = 1.f / (float)HW;
-  for (int i = tid; i < Nal * C; i += nt) {
-    const int n = i / C, c = i - n * C;
-    float s = 0.f;
+  const int nvec = Cp >> 3;
+  for (int i = tid; i < Nal * nvec; i += nt) {
+    const int n = i / nvec, c0 = (i - n * nvec) * 8;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
     if (n < N) {
-      const bf16* p = Z + ((size_t)n * HW) * Cp + c;
-      for (int h = 0; h < HW; ++h) s += ldbf(p + (size_t)h * Cp);
+      const bf16* pz = Z + ((size_t)n * HW) * Cp + c0;
+#pragma unroll 4
+      for (int h = 0; h < HW; ++h) {
+        float v[8];
+        ld8(pz + (size_t)h * Cp, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += v[e];
+      }
     }
-    pooled[i] = bfr(s * inv_hw);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) pooled[n * Cp + c0 + e] = bfr(acc[e] * inv_hw);
+  }
+  for (int i = tid; i < Kc * Cp; i += nt) {
+    const int k = i / Cp, c = i - k * Cp;
+    Ws[i] = c < C ? __ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(W + (size_t)k * C + c))) : __float2bfloat16(0.f);
   }
   __syncthreads();
   for (int o = warp; o < N * Kc; o += nw) {
     const int n = o / Kc, k = o - n * Kc;
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += pooled[n * C + c] * __bfloat162float(W[(size_t)k * C + c]);
+    for (int c = lane; c < C; c += 32) s += pooled[n * Cp + c] * __bfloat162float(Ws[k * Cp + c]);
     s = warp_sum(s);
     if (lane == 0) {
-      float z = bfr(s + __bfloat162float(Bv[k]));
+      float z = bfr(s + ldbf(Bv + k));
       if (mask != nullptr && !mask[k]) z = 0.f;
       logit[o] = z;
     }
@@ -693,19 +848,26 @@ __device__ __noinline__ void head_train(const Phase& P, Ctx& cx) {
   for (int i = tid; i < Kc * C; i += nt) {
     const int k = i / C, c = i - k * C;
     float s = 0.f;
-    for (int n = 0; n < N; ++n) s += logit[n * Kc + k] * pooled[n * C + c];
+    for (int n = 0; n < N; ++n) s += logit[n * Kc + k] * pooled[n * Cp + c];
     dW[i] = s;
   }
+  // dpooled -> dz (broadcast over the HW positions), 8 channels per thread, 16-byte stores
   bf16* DZ = reinterpret_cast<bf16*>(P.pv[8]);
-  for (int i = tid; i < Nal * Cp; i += nt) {
-    const int n = i / Cp, c = i - n * Cp;
-    float s = 0.f;
-    if (n < N && c < C) {
-      for (int k = 0; k < Kc; ++k) s += logit[n * Kc + k] * __bfloat162float(W[(size_t)k * C + c]);
-      s = bfr(s) * inv_hw;
+  for (int i = tid; i < Nal * nvec; i += nt) {
+    const int n = i / nvec, c0 = (i - n * nvec) * 8;
+    float o8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float sacc = 0.f;
+      if (n < N && c0 + e < C) {
+        for (int k = 0; k < Kc; ++k) sacc += logit[n * Kc + k] * __bfloat162float(Ws[k * Cp + c0 + e]);
+        sacc = bfr(sacc) * inv_hw;
+      }
+      o8[e] = sacc;
     }
-    const bf16 v = __float2bfloat16(s);
-    for (int h = 0; h < HW; ++h) DZ[((size_t)n * HW + h) * Cp + c] = v;
+    const uint4 u = pack8(o8);
+    bf16* pd = DZ + ((size_t)n * HW) * Cp + c0;
+    for (int h = 0; h < HW; ++h) *reinterpret_cast<uint4*>(pd + (size_t)h * Cp) = u;
   }
   __syncthreads();
 }
@@ -753,7 +915,7 @@ __device__ __noinline__ void sgd_norm_item(const Phase& P, Ctx& cx, int item) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
   acc = block_sum(acc, sm);
-  if (threadIdx.x == 0) atomicAdd(reinterpret_cast<float*>(cx.jctl + CTL_GNORM2), acc);
+  if (threadIdx.x == 0) red_add(reinterpret_cast<float*>(cx.jctl + CTL_GNORM2), acc);
 }
 
 // OP_SGD_UPDATE  iv: 0 n4  1 upd_items  2 zero_n4;  pv: 0 w  1 wc  2 g  3 mom  4 zero_ptr;  fv: 0 lr 1 mu 2 wd 3 max_norm
@@ -875,11 +1037,14 @@ mega_kernel(const Job* __restrict__ jobs, int njobs, int nphase, int nsteps, uns
   __shared__ Job sJob[MAX_JOBS];
   __shared__ int sPre[MAX_JOBS + 1];
   __shared__ uint32_t tmem_slot;
+  __shared__ int s_flag;
   Ctx cx;
   cx.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  cx.full = reinterpret_cast<uint64_t*>(cx.smem + MG_STAGES * MG_STAGE_BYTES);
+  cx.wg_stage = cx.smem + MG_STAGES * MG_STAGE_BYTES;
+  cx.full = reinterpret_cast<uint64_t*>(cx.wg_stage + MG_WG_STAGING);
   cx.empty = cx.full + MG_STAGES;
   cx.tfull = cx.empty + MG_STAGES;
+  cx.tempty = cx.tfull + 2;
   cx.ctl = ctl;
   cx.kctr = 0;
   cx.tctr = 0;
@@ -888,7 +1053,7 @@ mega_kernel(const Job* __restrict__ jobs, int njobs, int nphase, int nsteps, uns
   if (threadIdx.x < njobs) sJob[threadIdx.x] = jobs[threadIdx.x];
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < MG_STAGES; ++s) { mbar_init(&cx.full[s], 1); mbar_init(&cx.empty[s], 1); }
-    mbar_init(cx.tfull, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&cx.tfull[a], 1); mbar_init(&cx.tempty[a], 4); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_slot, MG_TMEM_COLS);
@@ -937,27 +1102,50 @@ mega_kernel(const Job* __restrict__ jobs, int njobs, int nphase, int nsteps, uns
       if (do_prof) t0 = clock64();
       const int nt = sPre[njobs];
       const unsigned start = (blockIdx.x + G - (rot % G)) % G;
-      int k = 0;
-      for (int t = (int)start; t < nt; t += (int)G) {
-        while (t >= sPre[k + 1]) ++k;
-        const Phase& sP = *reinterpret_cast<const Phase*>(sHdr[buf][k]);
-        const Phase* Pg = sJob[k].prog + p;
-        const int lt = t - sPre[k];
-        cx.jctl = sJob[k].jctl;
-        cx.nvalid = sJob[k].nvalid_tab != nullptr ? __ldg(sJob[k].nvalid_tab + step) : 0x7fffffff;
-        switch (sP.op) {
-          case OP_PREP: prep_item(sP, cx, lt); break;
-          case OP_CONV: conv_tile(Pg, sP, cx, lt); break;
-          case OP_WGRAD: wgrad_tile(Pg, sP, cx, lt); break;
-          case OP_NAPPLY: napply_item(sP, cx, lt); break;
-          case OP_NBWD_RED: nbwd_item(sP, cx, lt, false); break;
-          case OP_NBWD_APPLY: nbwd_item(sP, cx, lt, true); break;
-          case OP_HEAD:
-            if (sP.iv[5]) head_train(sP, cx); else head_eval_item(sP, cx, lt);
-            break;
-          case OP_SGD_NORM: sgd_norm_item(sP, cx, lt); break;
-          case OP_SGD_UPDATE: sgd_update_item(sP, cx, lt); break;
-          default: break;
+      const int op0 = reinterpret_cast<const Phase*>(sHdr[buf][0])->op;
+      if (op0 == OP_CONV || op0 == OP_WGRAD) {
+        // tensor-core phases: every role walks the CTA's tile sequence on its own (software pipeline across tiles)
+        const bool role = (warp == 0 && lane == 0) || warp == 1 || warp >= 4;
+        if (role) {
+          int k = 0;
+          bool live = true;
+          for (int t = (int)start; t < nt && live; t += (int)G) {
+            while (t >= sPre[k + 1]) ++k;
+            const Phase& sP = *reinterpret_cast<const Phase*>(sHdr[buf][k]);
+            const Phase* Pg = sJob[k].prog + p;
+            const int lt = t - sPre[k];
+            const bool conv = sP.op == OP_CONV;
+            if (warp == 0) {
+              live = conv ? conv_produce(Pg, sP, cx, lt) : wgrad_produce(Pg, sP, cx, lt);
+            } else if (warp == 1) {
+              live = conv ? conv_mma(sP, cx, lt) : wgrad_mma(sP, cx, lt);
+            } else {
+              cx.jctl = sJob[k].jctl;
+              cx.nvalid = sJob[k].nvalid_tab != nullptr ? __ldg(sJob[k].nvalid_tab + step) : 0x7fffffff;
+              live = conv ? conv_epilogue(sP, cx, lt, &s_flag) : wgrad_epilogue(sP, cx, lt);
+            }
+          }
+        }
+      } else {
+        int k = 0;
+        for (int t = (int)start; t < nt; t += (int)G) {
+          while (t >= sPre[k + 1]) ++k;
+          const Phase& sP = *reinterpret_cast<const Phase*>(sHdr[buf][k]);
+          const int lt = t - sPre[k];
+          cx.jctl = sJob[k].jctl;
+          cx.nvalid = sJob[k].nvalid_tab != nullptr ? __ldg(sJob[k].nvalid_tab + step) : 0x7fffffff;
+          switch (sP.op) {
+            case OP_PREP: prep_item(sP, cx, lt); break;
+            case OP_NAPPLY: napply_item(sP, cx, lt); break;
+            case OP_NBWD_RED: nbwd_item(sP, cx, lt, false); break;
+            case OP_NBWD_APPLY: nbwd_item(sP, cx, lt, true); break;
+            case OP_HEAD:
+              if (sP.iv[5]) head_train(sP, cx); else head_eval_item(sP, cx, lt);
+              break;
+            case OP_SGD_NORM: sgd_norm_item(sP, cx, lt); break;
+            case OP_SGD_UPDATE: sgd_update_item(sP, cx, lt); break;
+            default: break;
+          }
         }
       }
       rot = (rot + (unsigned)nt) % G;

@@ -99,9 +99,9 @@ class Program:
         self.keep: List[torch.Tensor] = []
         self.names: List[str] = []
 
-    def add(self, op: int, ntiles: int, sync: int = 1, iv=(), fv=(), pv=(), tm=(), name: str = "") -> None:
+    def add(self, op: int, ntiles: int, sync: int = 1, iv=(), fv=(), pv=(), tm=(), name: str = "", flags: int = 0) -> None:
         r = np.zeros((), dtype=PHASE_DT)
-        r["op"], r["ntiles"], r["sync"] = op, int(ntiles), int(sync)
+        r["op"], r["ntiles"], r["sync"], r["flags"] = op, int(ntiles), int(sync), int(flags)
         assert len(iv) <= NIV and len(fv) <= NFV and len(pv) <= NPV and len(tm) <= NTM
         for i, v in enumerate(iv):
             r["iv"][i] = int(v)
@@ -153,7 +153,7 @@ def _conv_phase(prog: Program, *, N: int, OH: int, OW: int, out: torch.Tensor, t
                 a_maps: List[np.ndarray], b_maps: List[np.ndarray], bnhw: Tuple[int, int, int], block_n: int, b_mn: int,
                 in_stride: int, out_s: int = 1, out_ph: int = 0, out_pw: int = 0, res: Optional[torch.Tensor] = None,
                 stats: Optional[torch.Tensor] = None, group_n: int = 0, use_nvalid: int = 0, sync: int = 1,
-                name: str = "conv") -> None:
+                name: str = "conv", split_target: int = 0) -> None:
     bn, bh, bw = bnhw
     Cy = out.shape[3]
     out_H, out_W = out.shape[1], out.shape[2]
@@ -173,7 +173,20 @@ def _conv_phase(prog: Program, *, N: int, OH: int, OW: int, out: torch.Tensor, t
     if res is not None:
         assert res.shape == out.shape
     tm = [a_maps[0], a_maps[1] if len(a_maps) > 1 else None, b_maps[0], b_maps[1] if len(b_maps) > 1 else None]
-    prog.add(OP_CONV, m_tiles * n_tiles, sync, iv=iv, pv=[_ptr(out), _ptr(res), _ptr(stats)], tm=tm, name=name)
+    # split-K: too few output tiles to occupy the grid -> deal the k-blocks of a tile to several work items; partial sums
+    # meet in an fp32 scratch and the last arrival (per-tile counter) runs the epilogue (csrc/mega_kernel.cu)
+    base = m_tiles * n_tiles
+    ksplit, scratch, counters = 1, None, None
+    if split_target and base * 2 <= split_target and num_k >= 4:
+        want = min(num_k // 2, -(-split_target // base))
+        per = -(-num_k // max(want, 1))
+        ksplit = -(-num_k // per)
+    if ksplit > 1:
+        scratch = torch.zeros(N * out_H * out_W * Cy, dtype=torch.float32, device=out.device)
+        counters = torch.zeros(base, dtype=torch.int32, device=out.device)
+        prog.keep += [scratch, counters]
+    pv = [_ptr(out), _ptr(res), _ptr(stats), _ptr(scratch), 0, 0, 0, 0, 0, 0, 0, _ptr(counters)]
+    prog.add(OP_CONV, base * ksplit, sync, iv=iv, pv=pv, tm=tm, name=name, flags=ksplit)
 
 
 def _block_n(Cy: int) -> int:
@@ -182,7 +195,7 @@ def _block_n(Cy: int) -> int:
 
 def conv_fprop(prog: Program, x: torch.Tensor, w: WDesc, out: torch.Tensor, R: int, stride: int,
                res: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None, group_n: int = 0,
-               use_nvalid: int = 0, sync: int = 1, rows: int = 128, name: str = "fprop") -> None:
+               use_nvalid: int = 0, sync: int = 1, rows: int = 128, name: str = "fprop", split_target: int = 0) -> None:
     """``out = conv(x, w) (+ res)``, optional per-channel (sum, sumsq) of the bf16 outputs into ``stats``."""
     N, H, W_, Cxp = x.shape
     _, OH, OW, Cy = out.shape
@@ -195,12 +208,12 @@ def conv_fprop(prog: Program, x: torch.Tensor, w: WDesc, out: torch.Tensor, R: i
     taps = [_tap(0, 0, r * R + s, kb, r - pad, s - pad) for r in range(R) for s in range(R)]
     _conv_phase(prog, N=N, OH=OH, OW=OW, out=out, taps=taps, a_maps=[act_map(x, bw, bh, bn, stride)],
                 b_maps=[w.kmajor_map(bnk)], bnhw=bnhw, block_n=bnk, b_mn=0, in_stride=stride, res=res, stats=stats,
-                group_n=group_n, use_nvalid=use_nvalid, sync=sync, name=name)
+                group_n=group_n, use_nvalid=use_nvalid, sync=sync, name=name, split_target=split_target)
 
 
 def conv_dgrad(prog: Program, dy: torch.Tensor, w: WDesc, dx: torch.Tensor, R: int, stride: int,
                dy2: Optional[torch.Tensor] = None, w2: Optional[WDesc] = None, sync: int = 1,
-               name: str = "dgrad") -> None:
+               name: str = "dgrad", split_target: int = 0) -> None:
     """``dx = conv_transpose(dy, w)`` for a 3x3 / pad-1 (or 1x1 / pad-0) filter of stride 1 or 2; for stride 2 an optional
     second gradient ``dy2`` through a 1x1 stride-2 filter ``w2`` (the block shortcut) is accumulated in the same pass."""
     N, OH, OW, Kp = dy.shape
@@ -214,7 +227,7 @@ def conv_dgrad(prog: Program, dy: torch.Tensor, w: WDesc, dx: torch.Tensor, R: i
         bn, bh, bw = bnhw
         taps = [_tap(0, 0, r * R + s, kb, pad - r, pad - s) for r in range(R) for s in range(R)]
         _conv_phase(prog, N=N, OH=H, OW=W_, out=dx, taps=taps, a_maps=[act_map(dy, bw, bh, bn)], b_maps=[w.mn_map()],
-                    bnhw=bnhw, block_n=bnk, b_mn=1, in_stride=1, sync=sync, name=name)
+                    bnhw=bnhw, block_n=bnk, b_mn=1, in_stride=1, sync=sync, name=name, split_target=split_target)
         return
     assert stride == 2 and R == 3
     bnhw = brick(OH, OW, 128)
@@ -234,7 +247,7 @@ def conv_dgrad(prog: Program, dy: torch.Tensor, w: WDesc, dx: torch.Tensor, R: i
             last = (ph == 1 and pw == 1)
             _conv_phase(prog, N=N, OH=OH, OW=OW, out=dx, taps=taps, a_maps=a_maps, b_maps=b_maps, bnhw=bnhw,
                         block_n=bnk, b_mn=1, in_stride=1, out_s=2, out_ph=ph, out_pw=pw, sync=(sync if last else 0),
-                        name="%s.p%d%d" % (name, ph, pw))
+                        name="%s.p%d%d" % (name, ph, pw), split_target=split_target // 4)
 
 
 def conv_wgrad(prog: Program, dy: torch.Tensor, x: torch.Tensor, dW_ptr: int, Kout: int, C: int, R: int, stride: int,
@@ -381,6 +394,7 @@ class MegaResNet:
         C0 = self.lay.entries["conv1.weight"].shape[0]
         first = self.blocks[0]["prefix"] + ".n1"
         y = keep.setdefault("y0", self._act(N, H, W, C0))
+        split = int(st.get("split", 0)) if mode == "train" else 0
         conv_fprop(prog, x, self._wdesc(wc, packbuf, "conv1.weight"), y, 3, 1, stats=stats_for(first, C0),
                    group_n=group_n, use_nvalid=use_nvalid, name="stem")
         cin = C0
@@ -399,13 +413,15 @@ class MegaResNet:
                 res = y
             c1 = keep.setdefault(pre + ".c1", self._act(N, OH, OW, planes))
             conv_fprop(prog, z1, self._wdesc(wc, packbuf, pre + ".conv1.weight"), c1, 3, stride,
-                       stats=stats_for(pre + ".n2", planes), group_n=group_n, use_nvalid=use_nvalid, name=pre + ".conv1")
+                       stats=stats_for(pre + ".n2", planes), group_n=group_n, use_nvalid=use_nvalid, name=pre + ".conv1",
+                       split_target=split)
             z2 = keep.setdefault(pre + ".z2", self._act(N, OH, OW, planes))
             napply(pre + ".n2", c1, z2, planes)
             nxt = (self.blocks[bi + 1]["prefix"] + ".n1") if bi + 1 < len(self.blocks) else "n4"
             yo = keep.setdefault(pre + ".out", self._act(N, OH, OW, planes))
             conv_fprop(prog, z2, self._wdesc(wc, packbuf, pre + ".conv2.weight"), yo, 3, 1, res=res,
-                       stats=stats_for(nxt, planes), group_n=group_n, use_nvalid=use_nvalid, name=pre + ".conv2")
+                       stats=stats_for(nxt, planes), group_n=group_n, use_nvalid=use_nvalid, name=pre + ".conv2",
+                       split_target=split)
             st.setdefault("yin", {})[pre] = y
             y, cin, H, W = yo, planes, OH, OW
         z4 = keep.setdefault("z4", self._act(N, H, W, cin))
@@ -446,6 +462,8 @@ class MegaResNet:
         st["scr"] = (sbuf, tbuf)
         wc, w, g = st["wc"], st["w"], st["g"]
         tgt = 2 * self.grid
+        st.setdefault("split", self.grid)
+        split = int(st["split"])
         self._prep(prog, st, N, augment=True, with_pack=True)
         z4 = self._forward(prog, st, N, "train", 0, 1)
         y_last, C4, (H4, W4) = st["y_last"], st["c_last"], st["hw_last"]
@@ -456,7 +474,8 @@ class MegaResNet:
         pv = [_ptr(z4), self._pptr(wc, "linear.weight"), self._pptr(wc, "linear.bias"), _ptr(st["lab"]),
               _ptr(st.get("mask")), _ptr(st.get("meter")), self._pptr(g, "linear.weight"), self._pptr(g, "linear.bias"),
               _ptr(dz4), 0, _ptr(st["loss"])]
-        assert (N * C4 + N * self.classes + 2 * N) * 4 <= 96 * 1024
+        Cp4 = z4.shape[3]
+        assert (N * Cp4 + N * self.classes + 2 * N + 4) * 4 + self.classes * Cp4 * 2 <= 180 * 1024, "head does not fit"
         prog.add(OP_HEAD, 1, 1, iv=iv, pv=pv, name="head")
         # ---- backward ----
         acts = st["acts"]
@@ -476,7 +495,8 @@ class MegaResNet:
             # conv2: wgrad (off the critical path) + dgrad
             conv_wgrad(prog, ds, z2, self._pptr(g, pre + ".conv2.weight"), planes, planes, 3, 1, tgt, name=pre + ".conv2.wgrad")
             dz2 = bk.setdefault(pre + ".dz2", self._act(N, H, W, planes))
-            conv_dgrad(prog, ds, self._wdesc(wc, st["packbuf"], pre + ".conv2.weight"), dz2, 3, 1, name=pre + ".conv2.dgrad")
+            conv_dgrad(prog, ds, self._wdesc(wc, st["packbuf"], pre + ".conv2.weight"), dz2, 3, 1, name=pre + ".conv2.dgrad",
+                       split_target=split)
             dc1 = bk.setdefault(pre + ".dc1", self._act(N, H, W, planes))
             norm_bwd(prog, c1, dz2, dc1, planes, stats=st["S"][pre + ".n2"], gamma=self._pptr(wc, pre + ".n2.weight"),
                      beta=self._pptr(wc, pre + ".n2.bias"), T=st["T"][pre + ".n2"],
@@ -491,7 +511,7 @@ class MegaResNet:
                 wsc = self._wdesc(wc, st["packbuf"], pre + ".shortcut.weight")
                 if stride == 2:
                     conv_dgrad(prog, dc1, self._wdesc(wc, st["packbuf"], pre + ".conv1.weight"), dz1, 3, 2, dy2=ds,
-                               w2=wsc, name=pre + ".conv1.dgrad")
+                               w2=wsc, name=pre + ".conv1.dgrad", split_target=split)
                     dz1b = None
                 else:        # widening block without down-sampling (not in resnet18/34, kept for completeness)
                     conv_dgrad(prog, dc1, self._wdesc(wc, st["packbuf"], pre + ".conv1.weight"), dz1, 3, 1, sync=0,
@@ -501,7 +521,7 @@ class MegaResNet:
                 dres = None
             else:
                 conv_dgrad(prog, dc1, self._wdesc(wc, st["packbuf"], pre + ".conv1.weight"), dz1, 3, stride,
-                           name=pre + ".conv1.dgrad")
+                           name=pre + ".conv1.dgrad", split_target=split)
                 dz1b, dres = None, ds
             ds_prev = bk.setdefault(pre + ".ds", self._act(N, IH, IW, cin))
             norm_bwd(prog, y_in, dz1, ds_prev, cin, stats=st["S"][pre + ".n1"], gamma=self._pptr(wc, pre + ".n1.weight"),
