@@ -160,14 +160,16 @@ __device__ __forceinline__ void warp_col_reduce(float (&v)[32], int lane) {
 //     13 out_s  14 out_ph  15 out_pw  16 in_stride  17 b_mn  18 ntaps  19 has_res  20 has_stats  21 group_n
 //     22 num_k  23 a_bytes  24 b_bytes  25 use_nvalid  26..43 taps (2 words each: 9 taps);  header word `flags` = ksplit
 // pv: 0 out  1 residual  2 stats [G][2][Cy]  3 split-K scratch (fp32, same indexing as out)  11 split-K tile counters
+//     4 y  5 S  6 gamma  7 beta  8 T   (dgrad only, pv[4] != 0: the BatchNorm backward reductions of the layer that
+//     produced y run in this epilogue -- out = dz * [bn(y) > 0], T += (sum out, sum out * xhat));  fv: 0 eps
 // tm: 0,1 activation maps   2,3 filter maps
 //
 // The three roles (TMA producer = warp 0, MMA issuer = warp 1, epilogue = warps 4-7) each walk the CTA's tile sequence
 // of the phase on their own: the producer runs ahead through the smem ring, the MMA warp alternates between two TMEM
 // accumulators, so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
-// Split-K (flags > 1): the k-blocks of one output tile are dealt to `ksplit` work items; each adds its partial
-// accumulator to an fp32 scratch with 16-byte reductions, and the LAST item to arrive (per-tile counter) re-reads the
-// sum, re-zeroes the scratch and runs the normal epilogue -- no extra phase, no extra grid barrier.
+// Split-K (flags > 1): the k-blocks of one output tile are dealt to `ksplit` work items; each stores its partial
+// accumulator into its own fp32 slice with 16-byte stores, and the LAST item to arrive (per-tile counter) sums the
+// slices and runs the normal epilogue -- no extra phase, no extra grid barrier, no contended atomics.
 struct ConvTileId { int n_blk, n0, oh0, kb0, kb1, mn; };
 
 __device__ __forceinline__ ConvTileId conv_decode(const Phase& P, int lt) {
@@ -263,7 +265,7 @@ __device__ __noinline__ bool conv_mma(const Phase& P, Ctx& cx, int lt) {
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // warps 4..7
-__device__ __noinline__ bool conv_epilogue(const Phase& P, Ctx& cx, int lt, int* s_flag) {
+__device__ __noinline__ bool conv_epilogue(const Phase& P, Ctx& cx, int lt, int* s_flag, float* s_bn /* [4][4][32] */) {
   const int* iv = P.iv;
   const ConvTileId c = conv_decode(P, lt);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -293,9 +295,17 @@ __device__ __noinline__ bool conv_epilogue(const Phase& P, Ctx& cx, int lt, int*
   }
   const int ksplit = P.flags > 1 ? P.flags : 1;
   float* scratch = reinterpret_cast<float*>(P.pv[3]);
+  const bf16* bn_y = reinterpret_cast<const bf16*>(P.pv[4]);
+  const float* bn_S = reinterpret_cast<const float*>(P.pv[5]);
+  const bf16* bn_g = reinterpret_cast<const bf16*>(P.pv[6]);
+  const bf16* bn_b = reinterpret_cast<const bf16*>(P.pv[7]);
+  float* bn_T = reinterpret_cast<float*>(P.pv[8]);
+  const float bn_cnt = (float)nlim * (float)(iv[11] * iv[12]);
   bool finalize = true;
+  const size_t slice = (size_t)iv[0] * iv[11] * iv[12] * Cy;      // one fp32 partial slice = the output tensor's extent
   if (ksplit > 1) {
-    // ---- partial accumulator -> fp32 scratch
+    // ---- partial accumulator -> this split's fp32 slice (plain 16-byte stores: no contended atomics)
+    const int ks = lt % ksplit;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       const int col0 = c.n_blk * BN + c0;
@@ -304,13 +314,11 @@ __device__ __noinline__ bool conv_epilogue(const Phase& P, Ctx& cx, int lt, int*
       tmem_ld_32x32b_x32(tmem_d + (uint32_t(q * 32) << 16) + c0, v);
       tmem_ld_wait();
       if (ok) {
-        float* dst = scratch + pix * Cy + col0;
+        uint4* dst = reinterpret_cast<uint4*>(scratch + (size_t)ks * slice + pix * Cy + col0);
         const int ncol = min(32, Cy - col0);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          if (j < ncol)
-            red_add4(dst + j, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                          __uint_as_float(v[j + 3])));
+        for (int j = 0; j < 8; ++j)
+          if (4 * j < ncol) __stcg(dst + j, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
       }
     }
     tcgen05_fence_before();
@@ -347,16 +355,73 @@ __device__ __noinline__ bool conv_epilogue(const Phase& P, Ctx& cx, int lt, int*
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = 0.f;
         if (ok) {
-          float4* sp = reinterpret_cast<float4*>(scratch + pix * Cy + col0);
+          // sum the ksplit partial slices (all loads of a slice are issued before they are consumed)
+          for (int sl = 0; sl < ksplit; ++sl) {
+            const float4* sp = reinterpret_cast<const float4*>(scratch + (size_t)sl * slice + pix * Cy + col0);
+            float4 a[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (4 * j < ncol) {
-              const float4 a = __ldcg(sp + j);
-              f[4 * j] = a.x; f[4 * j + 1] = a.y; f[4 * j + 2] = a.z; f[4 * j + 3] = a.w;
-              sp[j] = make_float4(0.f, 0.f, 0.f, 0.f);     // re-arm the scratch for the next step
+            for (int j = 0; j < 8; ++j) a[j] = (4 * j < ncol) ? __ldcg(sp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { f[4 * j] += a[j].x; f[4 * j + 1] += a[j].y; f[4 * j + 2] += a[j].z; f[4 * j + 3] += a[j].w; }
+          }
+        }
+      }
+      if (bn_y != nullptr) {
+        // BatchNorm-backward reductions fused into the dgrad epilogue
+        float* tb = s_bn + q * 128;
+        {
+          const int col = col0 + lane;
+          float a = 0.f, bsh = 0.f, mean = 0.f, inv = 0.f;
+          if (lane < ncol && bn_cnt > 0.f) {
+            const float sm = __ldcg(bn_S + col), sq = __ldcg(bn_S + Cy + col);
+            mean = sm / bn_cnt;
+            inv = rsqrtf(fmaxf(sq / bn_cnt - mean * mean, 0.f) + P.fv[0]);
+            a = ldbf(bn_g + col) * inv;
+            bsh = ldbf(bn_b + col) - mean * a;
+          }
+          __syncwarp();
+          tb[lane] = a; tb[32 + lane] = bsh; tb[64 + lane] = mean; tb[96 + lane] = inv;
+          __syncwarp();
+        }
+        float sx[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sx[j] = 0.f;
+        if (ok) {
+          const bf16* yp = bn_y + pix * Cy + col0;
+          bf16* dst = Y + pix * Cy + col0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (8 * j < ncol) {
+              float y8[8], o8[8];
+              ld8(yp + 8 * j, y8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int c = 8 * j + e;
+                const float pre = fmaf(tb[c], y8[e], tb[32 + c]);
+                o8[e] = pre > 0.f ? f[c] : 0.f;
+              }
+              const uint4 u = pack8(o8);
+              *reinterpret_cast<uint4*>(dst + 8 * j) = u;
+              unpack8(u, o8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int c = 8 * j + e;
+                f[c] = o8[e];
+                sx[c] = o8[e] * (y8[e] - tb[64 + c]) * tb[96 + c];
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[8 * j + e] = 0.f;
             }
           }
         }
+        warp_col_reduce(f, lane);
+        warp_col_reduce(sx, lane);
+        if (lane < ncol) {
+          red_add(&bn_T[col0 + lane], f[0]);
+          red_add(&bn_T[Cy + col0 + lane], sx[0]);
+        }
+        continue;
       }
       if (ok) {
         bf16* dst = Y + pix * Cy + col0;
@@ -619,16 +684,27 @@ __device__ __noinline__ void napply_item(const Phase& P, Ctx& cx, int item) {
   const bf16* Y = reinterpret_cast<const bf16*>(P.pv[0]);
   bf16* Z = reinterpret_cast<bf16*>(P.pv[1]);
   const bool relu = iv[5] != 0;
-#pragma unroll 4
-  for (int row = row_lo + r0; row < row_hi; row += rstep) {
-    float y[8];
-    ld8(Y + (size_t)row * Cp + c0, y);
+  for (int row = row_lo + r0; row < row_hi; row += 4 * rstep) {
+    uint4 u[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float z = fmaf(a[e], y[e], b[e]);
-      y[e] = relu ? fmaxf(z, 0.f) : z;
+    for (int k = 0; k < 4; ++k) {                       // 4 independent 16-byte loads in flight per thread
+      const int r = row + k * rstep;
+      u[k] = r < row_hi ? __ldcg(reinterpret_cast<const uint4*>(Y + (size_t)r * Cp + c0)) : make_uint4(0, 0, 0, 0);
     }
-    st8(Z + (size_t)row * Cp + c0, y);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = row + k * rstep;
+      if (r < row_hi) {
+        float y[8];
+        unpack8(u[k], y);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float z = fmaf(a[e], y[e], b[e]);
+          y[e] = relu ? fmaxf(z, 0.f) : z;
+        }
+        st8(Z + (size_t)r * Cp + c0, y);
+      }
+    }
   }
 }
 
@@ -713,36 +789,43 @@ __device__ __noinline__ void nbwd_item(const Phase& P, Ctx& cx, int item, bool a
       for (int e = 0; e < 8; ++e)
         if (c0 + e < Cr) { dga[c0 + e] = sg[e]; dbe[c0 + e] = sb[e]; }
     }
-    for (int row = row_lo + r0; row < row_hi; row += rstep) {
-      float o[8];
-      if (row < row_lim) {
-        float y[8], dz[8];
-        ld8(Y + (size_t)row * Cp + c0, y);
-        ld8(DZ + (size_t)row * Cp + c0, dz);
-        if (DZ2 != nullptr) {
-          float d2[8];
-          ld8(DZ2 + (size_t)row * Cp + c0, d2);
+    for (int row = row_lo + r0; row < row_hi; row += 2 * rstep) {
+      uint4 uy[2], ud[2], u2[2], ur[2];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) dz[e] += d2[e];
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float pre = fmaf(nc.a[e], y[e], nc.b[e]);
-          const float g = (relu && !(pre > 0.f)) ? 0.f : dz[e];
-          const float xh = (y[e] - nc.mean[e]) * nc.inv[e];
-          o[e] = nc.a[e] * (g - sb[e] * inv_n - xh * sg[e] * inv_n);
-        }
-        if (DR != nullptr) {
-          float dr[8];
-          ld8(DR + (size_t)row * Cp + c0, dr);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] += dr[e];
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = 0.f;
+      for (int k = 0; k < 2; ++k) {                     // all loads of two rows in flight before any is consumed
+        const int r = row + k * rstep;
+        const bool in = r < row_hi && r < row_lim;
+        const size_t off = (size_t)r * Cp + c0;
+        uy[k] = in ? __ldcg(reinterpret_cast<const uint4*>(Y + off)) : make_uint4(0, 0, 0, 0);
+        ud[k] = in ? __ldcg(reinterpret_cast<const uint4*>(DZ + off)) : make_uint4(0, 0, 0, 0);
+        u2[k] = (in && DZ2 != nullptr) ? __ldcg(reinterpret_cast<const uint4*>(DZ2 + off)) : make_uint4(0, 0, 0, 0);
+        ur[k] = (in && DR != nullptr) ? __ldcg(reinterpret_cast<const uint4*>(DR + off)) : make_uint4(0, 0, 0, 0);
       }
-      st8(DY + (size_t)row * Cp + c0, o);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int r = row + k * rstep;
+        if (r >= row_hi) continue;
+        float o[8];
+        if (r < row_lim) {
+          float y[8], dz[8], d2[8], dr[8];
+          unpack8(uy[k], y);
+          unpack8(ud[k], dz);
+          unpack8(u2[k], d2);
+          unpack8(ur[k], dr);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float dzz = dz[e] + d2[e];
+            const float pre = fmaf(nc.a[e], y[e], nc.b[e]);
+            const float g = (relu && !(pre > 0.f)) ? 0.f : dzz;
+            const float xh = (y[e] - nc.mean[e]) * nc.inv[e];
+            o[e] = nc.a[e] * (g - sb[e] * inv_n - xh * sg[e] * inv_n) + dr[e];
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = 0.f;
+        }
+        st8(DY + (size_t)r * Cp + c0, o);
+      }
     }
   }
 }
@@ -757,10 +840,10 @@ __device__ __noinline__ void head_train(const Phase& P, Ctx& cx) {
   const int tid = threadIdx.x, nt = MG_THREADS, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   // everything the head touches more than once is staged in shared memory with 16-byte loads: the pooled activations,
   // the classifier weights, the logits / dlogits
-  float* pooled = reinterpret_cast<float*>(cx.smem);        // [Nal][Cp]
+  bf16* Ws = reinterpret_cast<bf16*>(cx.smem);              // [Kc][Cp] classifier weights (16-byte aligned rows)
+  float* pooled = reinterpret_cast<float*>(cx.smem + (((size_t)Kc * Cp * 2 + 15) & ~(size_t)15));   // [Nal][Cp]
   float* logit = pooled + Nal * Cp;                         // [Nal][Kc]  (becomes dlogits)
   float* red = logit + Nal * Kc;                            // [2*Nal]
-  bf16* Ws = reinterpret_cast<bf16*>(red + 2 * Nal + ((2 * Nal) & 1) + 2);   // [Kc][Cp] classifier weights (8 B aligned)
   const bf16* Z = reinterpret_cast<const bf16*>(P.pv[0]);
   const bf16* W = reinterpret_cast<const bf16*>(P.pv[1]);
   const bf16* Bv = reinterpret_cast<const bf16*>(P.pv[2]);
@@ -768,6 +851,20 @@ __device__ __noinline__ void head_train(const Phase& P, Ctx& cx) {
   const unsigned char* mask = reinterpret_cast<const unsigned char*>(P.pv[4]);
   const float inv_hw = 1.f / (float)HW;
   const int nvec = Cp >> 3;
+  // classifier weights -> shared memory (16-byte loads when the rows allow it)
+  if ((C & 7) == 0) {
+    const int wv = C >> 3;
+    for (int i = tid; i < Kc * wv; i += nt) {
+      const int k = i / wv, v = i - k * wv;
+      *reinterpret_cast<uint4*>(Ws + (size_t)k * Cp + v * 8) = __ldcg(reinterpret_cast<const uint4*>(W + (size_t)k * C) + v);
+    }
+  } else {
+    for (int i = tid; i < Kc * Cp; i += nt) {
+      const int k = i / Cp, c = i - k * Cp;
+      Ws[i] = c < C ? __ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(W + (size_t)k * C + c)))
+                    : __float2bfloat16(0.f);
+    }
+  }
   for (int i = tid; i < Nal * nvec; i += nt) {
     const int n = i / nvec, c0 = (i - n * nvec) * 8;
     float acc[8];
@@ -775,20 +872,22 @@ __device__ __noinline__ void head_train(const Phase& P, Ctx& cx) {
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
     if (n < N) {
       const bf16* pz = Z + ((size_t)n * HW) * Cp + c0;
-#pragma unroll 4
-      for (int h = 0; h < HW; ++h) {
-        float v[8];
-        ld8(pz + (size_t)h * Cp, v);
+      for (int h0 = 0; h0 < HW; h0 += 16) {
+        uint4 u[16];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] += v[e];
+        for (int h = 0; h < 16; ++h)
+          u[h] = (h0 + h < HW) ? __ldcg(reinterpret_cast<const uint4*>(pz + (size_t)(h0 + h) * Cp)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+          float v[8];
+          unpack8(u[h], v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += v[e];
+        }
       }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) pooled[n * Cp + c0 + e] = bfr(acc[e] * inv_hw);
-  }
-  for (int i = tid; i < Kc * Cp; i += nt) {
-    const int k = i / Cp, c = i - k * Cp;
-    Ws[i] = c < C ? __ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(W + (size_t)k * C + c))) : __float2bfloat16(0.f);
   }
   __syncthreads();
   for (int o = warp; o < N * Kc; o += nw) {
@@ -1038,6 +1137,7 @@ mega_kernel(const Job* __restrict__ jobs, int njobs, int nphase, int nsteps, uns
   __shared__ int sPre[MAX_JOBS + 1];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_flag;
+  __shared__ float s_bn[4 * 128];
   Ctx cx;
   cx.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   cx.wg_stage = cx.smem + MG_STAGES * MG_STAGE_BYTES;
@@ -1122,7 +1222,7 @@ mega_kernel(const Job* __restrict__ jobs, int njobs, int nphase, int nsteps, uns
             } else {
               cx.jctl = sJob[k].jctl;
               cx.nvalid = sJob[k].nvalid_tab != nullptr ? __ldg(sJob[k].nvalid_tab + step) : 0x7fffffff;
-              live = conv ? conv_epilogue(sP, cx, lt, &s_flag) : wgrad_epilogue(sP, cx, lt);
+              live = conv ? conv_epilogue(sP, cx, lt, &s_flag, s_bn) : wgrad_epilogue(sP, cx, lt);
             }
           }
         }

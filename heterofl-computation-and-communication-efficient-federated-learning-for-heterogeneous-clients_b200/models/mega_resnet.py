@@ -153,7 +153,7 @@ def _conv_phase(prog: Program, *, N: int, OH: int, OW: int, out: torch.Tensor, t
                 a_maps: List[np.ndarray], b_maps: List[np.ndarray], bnhw: Tuple[int, int, int], block_n: int, b_mn: int,
                 in_stride: int, out_s: int = 1, out_ph: int = 0, out_pw: int = 0, res: Optional[torch.Tensor] = None,
                 stats: Optional[torch.Tensor] = None, group_n: int = 0, use_nvalid: int = 0, sync: int = 1,
-                name: str = "conv", split_target: int = 0) -> None:
+                name: str = "conv", split_target: int = 0, bnred: Optional[Dict] = None) -> None:
     bn, bh, bw = bnhw
     Cy = out.shape[3]
     out_H, out_W = out.shape[1], out.shape[2]
@@ -178,15 +178,20 @@ def _conv_phase(prog: Program, *, N: int, OH: int, OW: int, out: torch.Tensor, t
     base = m_tiles * n_tiles
     ksplit, scratch, counters = 1, None, None
     if split_target and base * 2 <= split_target and num_k >= 4:
-        want = min(num_k // 2, -(-split_target // base))
+        want = min(num_k // 2, -(-split_target // base), 6)     # the last arrival re-reads `ksplit` slices: keep it small
         per = -(-num_k // max(want, 1))
         ksplit = -(-num_k // per)
     if ksplit > 1:
-        scratch = torch.zeros(N * out_H * out_W * Cy, dtype=torch.float32, device=out.device)
+        scratch = torch.zeros(ksplit * N * out_H * out_W * Cy, dtype=torch.float32, device=out.device)
         counters = torch.zeros(base, dtype=torch.int32, device=out.device)
         prog.keep += [scratch, counters]
     pv = [_ptr(out), _ptr(res), _ptr(stats), _ptr(scratch), 0, 0, 0, 0, 0, 0, 0, _ptr(counters)]
-    prog.add(OP_CONV, base * ksplit, sync, iv=iv, pv=pv, tm=tm, name=name, flags=ksplit)
+    fv = []
+    if bnred is not None:       # BatchNorm-backward reductions of the layer that produced bnred["y"], in this epilogue
+        assert res is None and stats is None and bnred["y"].shape == out.shape
+        pv[4:9] = [_ptr(bnred["y"]), _ptr(bnred["S"]), bnred["gamma"], bnred["beta"], _ptr(bnred["T"])]
+        fv = [bnred["eps"]]
+    prog.add(OP_CONV, base * ksplit, sync, iv=iv, fv=fv, pv=pv, tm=tm, name=name, flags=ksplit)
 
 
 def _block_n(Cy: int) -> int:
@@ -213,7 +218,7 @@ def conv_fprop(prog: Program, x: torch.Tensor, w: WDesc, out: torch.Tensor, R: i
 
 def conv_dgrad(prog: Program, dy: torch.Tensor, w: WDesc, dx: torch.Tensor, R: int, stride: int,
                dy2: Optional[torch.Tensor] = None, w2: Optional[WDesc] = None, sync: int = 1,
-               name: str = "dgrad", split_target: int = 0) -> None:
+               name: str = "dgrad", split_target: int = 0, bnred: Optional[Dict] = None) -> None:
     """``dx = conv_transpose(dy, w)`` for a 3x3 / pad-1 (or 1x1 / pad-0) filter of stride 1 or 2; for stride 2 an optional
     second gradient ``dy2`` through a 1x1 stride-2 filter ``w2`` (the block shortcut) is accumulated in the same pass."""
     N, OH, OW, Kp = dy.shape
@@ -227,7 +232,8 @@ def conv_dgrad(prog: Program, dy: torch.Tensor, w: WDesc, dx: torch.Tensor, R: i
         bn, bh, bw = bnhw
         taps = [_tap(0, 0, r * R + s, kb, pad - r, pad - s) for r in range(R) for s in range(R)]
         _conv_phase(prog, N=N, OH=H, OW=W_, out=dx, taps=taps, a_maps=[act_map(dy, bw, bh, bn)], b_maps=[w.mn_map()],
-                    bnhw=bnhw, block_n=bnk, b_mn=1, in_stride=1, sync=sync, name=name, split_target=split_target)
+                    bnhw=bnhw, block_n=bnk, b_mn=1, in_stride=1, sync=sync, name=name, split_target=split_target,
+                    bnred=bnred)
         return
     assert stride == 2 and R == 3
     bnhw = brick(OH, OW, 128)
@@ -247,7 +253,7 @@ def conv_dgrad(prog: Program, dy: torch.Tensor, w: WDesc, dx: torch.Tensor, R: i
             last = (ph == 1 and pw == 1)
             _conv_phase(prog, N=N, OH=OH, OW=OW, out=dx, taps=taps, a_maps=a_maps, b_maps=b_maps, bnhw=bnhw,
                         block_n=bnk, b_mn=1, in_stride=1, out_s=2, out_ph=ph, out_pw=pw, sync=(sync if last else 0),
-                        name="%s.p%d%d" % (name, ph, pw), split_target=split_target // 4)
+                        name="%s.p%d%d" % (name, ph, pw), split_target=split_target // 4, bnred=bnred)
 
 
 def conv_wgrad(prog: Program, dy: torch.Tensor, x: torch.Tensor, dW_ptr: int, Kout: int, C: int, R: int, stride: int,
@@ -296,14 +302,15 @@ def norm_apply(prog: Program, y: torch.Tensor, z: torch.Tensor, C: int, *, stats
 
 def norm_bwd(prog: Program, y: torch.Tensor, dz: torch.Tensor, dy: torch.Tensor, C: int, *, stats, gamma: int,
              beta: int, T: torch.Tensor, dgamma: int, dbeta: int, eps: float, dz2=None, dres=None, relu: bool = True,
-             use_nvalid: int = 1, name: str = "nbwd") -> None:
+             use_nvalid: int = 1, name: str = "nbwd", fused_red: bool = False) -> None:
     N, H, W_, Cp = y.shape
     M, HW = N * H * W_, H * W_
     rpi = _rows_per_item(M, Cp)
     iv = [M, Cp, C, HW, 0, int(relu), 0, 0, rpi, use_nvalid, N]
     pv = [_ptr(y), _ptr(dz), _ptr(stats), gamma, beta, _ptr(dz2), _ptr(T), _ptr(dres), _ptr(dy), dgamma, dbeta]
     items = (M + rpi - 1) // rpi
-    prog.add(OP_NBWD_RED, items, 1, iv=iv, fv=[eps], pv=pv, name=name + ".red")
+    if not fused_red:        # otherwise the producing dgrad's epilogue already masked dz and accumulated T
+        prog.add(OP_NBWD_RED, items, 1, iv=iv, fv=[eps], pv=pv, name=name + ".red")
     prog.add(OP_NBWD_APPLY, items, 1, iv=iv, fv=[eps], pv=pv, name=name + ".apply")
 
 
@@ -462,7 +469,9 @@ class MegaResNet:
         st["scr"] = (sbuf, tbuf)
         wc, w, g = st["wc"], st["w"], st["g"]
         tgt = 2 * self.grid
-        st.setdefault("split", self.grid)
+        import os as _os
+        st.setdefault("split", int(_os.environ.get("HFL_MEGA_SPLIT", self.grid)))
+        st.setdefault("fuse_red", _os.environ.get("HFL_MEGA_FUSE_RED", "1") != "0")
         split = int(st["split"])
         self._prep(prog, st, N, augment=True, with_pack=True)
         z4 = self._forward(prog, st, N, "train", 0, 1)
@@ -495,13 +504,19 @@ class MegaResNet:
             # conv2: wgrad (off the critical path) + dgrad
             conv_wgrad(prog, ds, z2, self._pptr(g, pre + ".conv2.weight"), planes, planes, 3, 1, tgt, name=pre + ".conv2.wgrad")
             dz2 = bk.setdefault(pre + ".dz2", self._act(N, H, W, planes))
+            fuse = bool(st.get("fuse_red", True))
+
+            def red_of(site: str, ybuf: torch.Tensor):
+                return dict(y=ybuf, S=st["S"][site], gamma=self._pptr(wc, site + ".weight"),
+                            beta=self._pptr(wc, site + ".bias"), T=st["T"][site], eps=self.eps) if fuse else None
+
             conv_dgrad(prog, ds, self._wdesc(wc, st["packbuf"], pre + ".conv2.weight"), dz2, 3, 1, name=pre + ".conv2.dgrad",
-                       split_target=split)
+                       split_target=split, bnred=red_of(pre + ".n2", c1))
             dc1 = bk.setdefault(pre + ".dc1", self._act(N, H, W, planes))
             norm_bwd(prog, c1, dz2, dc1, planes, stats=st["S"][pre + ".n2"], gamma=self._pptr(wc, pre + ".n2.weight"),
                      beta=self._pptr(wc, pre + ".n2.bias"), T=st["T"][pre + ".n2"],
                      dgamma=self._pptr(g, pre + ".n2.weight"), dbeta=self._pptr(g, pre + ".n2.bias"), eps=self.eps,
-                     name=pre + ".n2.bwd")
+                     name=pre + ".n2.bwd", fused_red=fuse)
             conv_wgrad(prog, dc1, z1, self._pptr(g, pre + ".conv1.weight"), planes, cin, 3, stride, tgt,
                        name=pre + ".conv1.wgrad")
             dz1 = bk.setdefault(pre + ".dz1", self._act(N, IH, IW, cin))
@@ -511,23 +526,25 @@ class MegaResNet:
                 wsc = self._wdesc(wc, st["packbuf"], pre + ".shortcut.weight")
                 if stride == 2:
                     conv_dgrad(prog, dc1, self._wdesc(wc, st["packbuf"], pre + ".conv1.weight"), dz1, 3, 2, dy2=ds,
-                               w2=wsc, name=pre + ".conv1.dgrad", split_target=split)
+                               w2=wsc, name=pre + ".conv1.dgrad", split_target=split, bnred=red_of(pre + ".n1", y_in))
                     dz1b = None
+                    fuse1 = fuse
                 else:        # widening block without down-sampling (not in resnet18/34, kept for completeness)
                     conv_dgrad(prog, dc1, self._wdesc(wc, st["packbuf"], pre + ".conv1.weight"), dz1, 3, 1, sync=0,
                                name=pre + ".conv1.dgrad")
                     dz1b = bk.setdefault(pre + ".dz1b", self._act(N, IH, IW, cin))
                     conv_dgrad(prog, ds, wsc, dz1b, 1, 1, name=pre + ".shortcut.dgrad")
+                    fuse1 = False
                 dres = None
             else:
                 conv_dgrad(prog, dc1, self._wdesc(wc, st["packbuf"], pre + ".conv1.weight"), dz1, 3, stride,
-                           name=pre + ".conv1.dgrad", split_target=split)
-                dz1b, dres = None, ds
+                           name=pre + ".conv1.dgrad", split_target=split, bnred=red_of(pre + ".n1", y_in))
+                dz1b, dres, fuse1 = None, ds, fuse
             ds_prev = bk.setdefault(pre + ".ds", self._act(N, IH, IW, cin))
             norm_bwd(prog, y_in, dz1, ds_prev, cin, stats=st["S"][pre + ".n1"], gamma=self._pptr(wc, pre + ".n1.weight"),
                      beta=self._pptr(wc, pre + ".n1.bias"), T=st["T"][pre + ".n1"],
                      dgamma=self._pptr(g, pre + ".n1.weight"), dbeta=self._pptr(g, pre + ".n1.bias"), eps=self.eps,
-                     dz2=dz1b, dres=dres, name=pre + ".n1.bwd")
+                     dz2=dz1b, dres=dres, name=pre + ".n1.bwd", fused_red=fuse1)
             ds, H, W = ds_prev, IH, IW
         C0 = self.lay.entries["conv1.weight"].shape[0]
         conv_wgrad(prog, ds, st["x"], self._pptr(g, "conv1.weight"), C0, self.Cin, 3, 1, tgt, sync=1, name="stem.wgrad")

