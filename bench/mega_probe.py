@@ -49,6 +49,24 @@ def main():
         slots[rate] = slot
         print("rate %g: slot ready in %.1f s, %d phases, %d barriers" % (rate, time.time() - t0, len(slot.prog),
                                                                       slot.prog.n_barriers()), flush=True)
+    if what in ("all", "bar"):
+        # pure grid-barrier cost: a program of empty phases
+        from hfl_b200.models import mega_resnet as mr
+        prog = mr.Program()
+        for _ in range(200):
+            prog.add(mr.OP_NOP, 0, 1, name="nop")
+        pd = prog.finalize(dev)
+        ctl = torch.zeros(16, dtype=torch.int32, device=dev)
+        jctl = torch.zeros(16, dtype=torch.int32, device=dev)
+        for grid in (8, 32, 64, 148):
+            mr.launch([(pd, None, jctl, 10)], len(prog), grid, ctl)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            mr.launch([(pd, None, jctl, 50)], len(prog), grid, ctl)
+            e1.record()
+            torch.cuda.synchronize()
+            print("grid %3d: %.2f us per empty phase + barrier" % (grid, 1e3 * e0.elapsed_time(e1) / (50 * 200)), flush=True)
     if what in ("all", "grid"):
         for rate, slot in slots.items():
             for grid in grids[rate]:

@@ -844,6 +844,9 @@ __device__ __noinline__ void head_train(const Phase& P, Ctx& cx) {
   float* pooled = reinterpret_cast<float*>(cx.smem + (((size_t)Kc * Cp * 2 + 15) & ~(size_t)15));   // [Nal][Cp]
   float* logit = pooled + Nal * Cp;                         // [Nal][Kc]  (becomes dlogits)
   float* red = logit + Nal * Kc;                            // [2*Nal]
+  float* biasS = red + 2 * Nal;                             // [Kc]
+  int* maskS = reinterpret_cast<int*>(biasS + Kc);          // [Kc]
+  int* labS = maskS + Kc;                                   // [Nal]
   const bf16* Z = reinterpret_cast<const bf16*>(P.pv[0]);
   const bf16* W = reinterpret_cast<const bf16*>(P.pv[1]);
   const bf16* Bv = reinterpret_cast<const bf16*>(P.pv[2]);
@@ -851,6 +854,11 @@ __device__ __noinline__ void head_train(const Phase& P, Ctx& cx) {
   const unsigned char* mask = reinterpret_cast<const unsigned char*>(P.pv[4]);
   const float inv_hw = 1.f / (float)HW;
   const int nvec = Cp >> 3;
+  for (int k = tid; k < Kc; k += nt) {
+    biasS[k] = ldbf(Bv + k);
+    maskS[k] = (mask == nullptr || mask[k]) ? 1 : 0;
+  }
+  for (int n = tid; n < Nal; n += nt) labS[n] = n < N ? __ldcg(lab + n) : 0;
   // classifier weights -> shared memory (16-byte loads when the rows allow it)
   if ((C & 7) == 0) {
     const int wv = C >> 3;
@@ -896,8 +904,8 @@ __device__ __noinline__ void head_train(const Phase& P, Ctx& cx) {
     for (int c = lane; c < C; c += 32) s += pooled[n * Cp + c] * __bfloat162float(Ws[k * Cp + c]);
     s = warp_sum(s);
     if (lane == 0) {
-      float z = bfr(s + ldbf(Bv + k));
-      if (mask != nullptr && !mask[k]) z = 0.f;
+      float z = bfr(s + biasS[k]);
+      if (!maskS[k]) z = 0.f;
       logit[o] = z;
     }
   }
@@ -914,27 +922,25 @@ __device__ __noinline__ void head_train(const Phase& P, Ctx& cx) {
     for (int k = lane; k < Kc; k += 32) se += __expf(logit[n * Kc + k] - bmx);
     se = warp_sum(se);
     const float lse = __logf(se) + bmx;
-    const int tg = lab[n];
+    const int tg = labS[n];
     if (lane == 0) { red[n] = lse - logit[n * Kc + tg]; red[Nal + n] = (cand == tg) ? 1.f : 0.f; }
     __syncwarp();
     for (int k = lane; k < Kc; k += 32) {
-      const bool on = (mask == nullptr || mask[k]);
-      const float g = on ? (__expf(logit[n * Kc + k] - lse) - (k == tg ? 1.f : 0.f)) / (float)N : 0.f;
+      const float g = maskS[k] ? (__expf(logit[n * Kc + k] - lse) - (k == tg ? 1.f : 0.f)) / (float)N : 0.f;
       logit[n * Kc + k] = bfr(g);
     }
   }
   __syncthreads();
-  if (tid == 0 && N > 0) {
+  if (tid < 4 && N > 0) {     // the 4 meter words are updated by 4 threads (only this CTA touches them in this phase)
     float a = 0.f, c = 0.f;
     for (int n = 0; n < N; ++n) { a += red[n]; c += red[Nal + n]; }
     const float loss = a / (float)N;
-    if (P.pv[10]) *reinterpret_cast<float*>(P.pv[10]) = loss;
+    if (tid == 0 && P.pv[10]) *reinterpret_cast<float*>(P.pv[10]) = loss;
     double* meter = reinterpret_cast<double*>(P.pv[5]);
     if (meter != nullptr) {
-      meter[0] += (double)loss * (double)N;
-      meter[1] += (double)c;
-      meter[2] += (double)N;
-      meter[3] += (double)__expf(loss) * (double)N;
+      const double add = tid == 0 ? (double)loss * (double)N : tid == 1 ? (double)c : tid == 2 ? (double)N
+                                                                                        : (double)__expf(loss) * (double)N;
+      meter[tid] += add;
     }
   }
   float* dW = reinterpret_cast<float*>(P.pv[6]);
@@ -1126,6 +1132,30 @@ __device__ __noinline__ void prep_item(const Phase& P, Ctx& cx, int item) {
   }
 }
 
+// Headers of phase `pn` for every job -> shared memory (warps 2-3: 64 threads; 24 uint4 per header; every load of a
+// thread is in flight before its first store, i.e. one L2 round trip per phase).
+__device__ __noinline__ void prefetch_headers(const Job* sJob, int njobs, int pn, uint32_t* dst /* [MAX_JOBS][HDR_WORDS] */) {
+  constexpr int Q = HDR_WORDS / 4, R = (MAX_JOBS * Q + 63) / 64;
+  const int i0 = threadIdx.x - 64, nvq = njobs * Q;
+  uint4 hv[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = i0 + r * 64;
+    if (i < nvq) {
+      const int k = i / Q, q4 = i - k * Q;
+      hv[r] = __ldcg(reinterpret_cast<const uint4*>(sJob[k].prog + pn) + q4);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = i0 + r * 64;
+    if (i < nvq) {
+      const int k = i / Q, q4 = i - k * Q;
+      reinterpret_cast<uint4*>(dst + k * HDR_WORDS)[q4] = hv[r];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(MG_THREADS, 1)
 mega_kernel(const Job* __restrict__ jobs, int njobs, int nphase, int nsteps, unsigned* __restrict__ ctl,
@@ -1135,6 +1165,7 @@ mega_kernel(const Job* __restrict__ jobs, int njobs, int nphase, int nsteps, uns
   __shared__ __align__(16) uint32_t sHdr[2][MAX_JOBS][HDR_WORDS];
   __shared__ Job sJob[MAX_JOBS];
   __shared__ int sPre[MAX_JOBS + 1];
+  __shared__ int sNv[MAX_JOBS];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_flag;
   __shared__ float s_bn[4 * 128];
@@ -1176,17 +1207,18 @@ mega_kernel(const Job* __restrict__ jobs, int njobs, int nphase, int nsteps, uns
   const bool do_prof = (prof != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
   for (int step = 0; step < nsteps && !dead; ++step) {
     cx.step = step;
+    if (threadIdx.x < njobs) {
+      const Job& jb = sJob[threadIdx.x];
+      sNv[threadIdx.x] = (jb.nvalid_tab != nullptr && step < jb.nsteps) ? __ldcg(jb.nvalid_tab + step) : 0x7fffffff;
+    }
+    __syncthreads();
     for (int p = 0; p < nphase; ++p) {
       cx.phase = p;
       // prefetch the next phase's headers into the other buffer (its last readers passed the sync that ended the
       // previous phase); consumed after the sync at the end of this iteration
       {
         const int pn = (p + 1 < nphase) ? p + 1 : 0;
-        if (warp >= 2 && warp < 4)
-          for (int i = threadIdx.x - 64; i < njobs * HDR_WORDS; i += 64) {
-            const int k = i / HDR_WORDS, wd = i - k * HDR_WORDS;
-            sHdr[buf ^ 1][k][wd] = __ldcg(reinterpret_cast<const uint32_t*>(sJob[k].prog + pn) + wd);
-          }
+        if (warp >= 2 && warp < 4) prefetch_headers(sJob, njobs, pn, &sHdr[buf ^ 1][0][0]);
       }
       // tile space of this phase: the active jobs' tiles back to back (jobs are sorted heaviest first on the host)
       if (threadIdx.x == 0) {
@@ -1221,7 +1253,7 @@ mega_kernel(const Job* __restrict__ jobs, int njobs, int nphase, int nsteps, uns
               live = conv ? conv_mma(sP, cx, lt) : wgrad_mma(sP, cx, lt);
             } else {
               cx.jctl = sJob[k].jctl;
-              cx.nvalid = sJob[k].nvalid_tab != nullptr ? __ldg(sJob[k].nvalid_tab + step) : 0x7fffffff;
+              cx.nvalid = sNv[k];
               live = conv ? conv_epilogue(sP, cx, lt, &s_flag, s_bn) : wgrad_epilogue(sP, cx, lt);
             }
           }
@@ -1233,7 +1265,7 @@ mega_kernel(const Job* __restrict__ jobs, int njobs, int nphase, int nsteps, uns
           const Phase& sP = *reinterpret_cast<const Phase*>(sHdr[buf][k]);
           const int lt = t - sPre[k];
           cx.jctl = sJob[k].jctl;
-          cx.nvalid = sJob[k].nvalid_tab != nullptr ? __ldg(sJob[k].nvalid_tab + step) : 0x7fffffff;
+          cx.nvalid = sNv[k];
           switch (sP.op) {
             case OP_PREP: prep_item(sP, cx, lt); break;
             case OP_NAPPLY: napply_item(sP, cx, lt); break;

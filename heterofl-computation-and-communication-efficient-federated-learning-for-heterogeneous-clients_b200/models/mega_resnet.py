@@ -178,7 +178,7 @@ def _conv_phase(prog: Program, *, N: int, OH: int, OW: int, out: torch.Tensor, t
     base = m_tiles * n_tiles
     ksplit, scratch, counters = 1, None, None
     if split_target and base * 2 <= split_target and num_k >= 4:
-        want = min(num_k // 2, -(-split_target // base), 6)     # the last arrival re-reads `ksplit` slices: keep it small
+        want = min(num_k // 2, -(-split_target // base), 3)     # the last arrival re-reads `ksplit` slices: keep it small
         per = -(-num_k // max(want, 1))
         ksplit = -(-num_k // per)
     if ksplit > 1:
@@ -218,7 +218,7 @@ def conv_fprop(prog: Program, x: torch.Tensor, w: WDesc, out: torch.Tensor, R: i
 
 def conv_dgrad(prog: Program, dy: torch.Tensor, w: WDesc, dx: torch.Tensor, R: int, stride: int,
                dy2: Optional[torch.Tensor] = None, w2: Optional[WDesc] = None, sync: int = 1,
-               name: str = "dgrad", split_target: int = 0, bnred: Optional[Dict] = None) -> None:
+               name: str = "dgrad", split_target: int = 0, bnred: Optional[Dict] = None, use_nvalid: int = 1) -> None:
     """``dx = conv_transpose(dy, w)`` for a 3x3 / pad-1 (or 1x1 / pad-0) filter of stride 1 or 2; for stride 2 an optional
     second gradient ``dy2`` through a 1x1 stride-2 filter ``w2`` (the block shortcut) is accumulated in the same pass."""
     N, OH, OW, Kp = dy.shape
@@ -233,7 +233,7 @@ def conv_dgrad(prog: Program, dy: torch.Tensor, w: WDesc, dx: torch.Tensor, R: i
         taps = [_tap(0, 0, r * R + s, kb, pad - r, pad - s) for r in range(R) for s in range(R)]
         _conv_phase(prog, N=N, OH=H, OW=W_, out=dx, taps=taps, a_maps=[act_map(dy, bw, bh, bn)], b_maps=[w.mn_map()],
                     bnhw=bnhw, block_n=bnk, b_mn=1, in_stride=1, sync=sync, name=name, split_target=split_target,
-                    bnred=bnred)
+                    bnred=bnred, use_nvalid=use_nvalid)
         return
     assert stride == 2 and R == 3
     bnhw = brick(OH, OW, 128)
@@ -253,7 +253,8 @@ def conv_dgrad(prog: Program, dy: torch.Tensor, w: WDesc, dx: torch.Tensor, R: i
             last = (ph == 1 and pw == 1)
             _conv_phase(prog, N=N, OH=OH, OW=OW, out=dx, taps=taps, a_maps=a_maps, b_maps=b_maps, bnhw=bnhw,
                         block_n=bnk, b_mn=1, in_stride=1, out_s=2, out_ph=ph, out_pw=pw, sync=(sync if last else 0),
-                        name="%s.p%d%d" % (name, ph, pw), split_target=split_target // 4, bnred=bnred)
+                        name="%s.p%d%d" % (name, ph, pw), split_target=split_target // 4, bnred=bnred,
+                        use_nvalid=use_nvalid)
 
 
 def conv_wgrad(prog: Program, dy: torch.Tensor, x: torch.Tensor, dW_ptr: int, Kout: int, C: int, R: int, stride: int,
@@ -484,7 +485,8 @@ class MegaResNet:
               _ptr(st.get("mask")), _ptr(st.get("meter")), self._pptr(g, "linear.weight"), self._pptr(g, "linear.bias"),
               _ptr(dz4), 0, _ptr(st["loss"])]
         Cp4 = z4.shape[3]
-        assert (N * Cp4 + N * self.classes + 2 * N + 4) * 4 + self.classes * Cp4 * 2 <= 180 * 1024, "head does not fit"
+        assert (N * Cp4 + N * self.classes + 3 * N + 2 * self.classes + 8) * 4 + self.classes * Cp4 * 2 <= 150 * 1024, \
+            "head does not fit"
         prog.add(OP_HEAD, 1, 1, iv=iv, pv=pv, name="head")
         # ---- backward ----
         acts = st["acts"]
