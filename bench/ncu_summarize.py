@@ -48,14 +48,22 @@ def main():
                 if k in rec:
                     lines.append("| %s | %s | %s |" % (k, rec[k][0], rec[k][1]))
             try:
-                t_ns = float(rec["gpu__time_duration.sum"][0].replace(",", ""))
-                rd = float(rec["dram__bytes_read.sum"][0].replace(",", ""))
-                wr = float(rec["dram__bytes_write.sum"][0].replace(",", ""))
-                unit = rec["dram__bytes_read.sum"][1]
-                scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
-                tunit = {"ns": 1e-9, "us": 1e-6, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9}.get(rec["gpu__time_duration.sum"][1], 1e-9)
-                gbs = (rd + wr) * scale / (t_ns * tunit) / 1e9
-                lines.append("| derived DRAM GB/s | %.1f (%.2f of measured copy peak) | |" % (gbs, gbs / peaks.get("hbm_gbs", 6478.3)))
+                BY = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+                TM = {"ns": 1e-9, "nsecond": 1e-9, "us": 1e-6, "usecond": 1e-6, "ms": 1e-3, "msecond": 1e-3, "s": 1.0,
+                      "second": 1.0}
+
+                def qty(key, table):           # every metric carries its OWN unit (read and write often differ)
+                    val, unit = rec[key][0], rec[key][1]
+                    if unit not in table:
+                        raise KeyError(unit)
+                    return float(val.replace(",", "")) * table[unit]
+
+                secs = qty("gpu__time_duration.sum", TM)
+                nbytes = qty("dram__bytes_read.sum", BY) + qty("dram__bytes_write.sum", BY)
+                gbs = nbytes / secs / 1e9
+                peak = float(peaks.get("hbm_gbs", 6478.3))
+                if 0.0 < gbs < 20.0 * peak:
+                    lines.append("| derived DRAM GB/s | %.1f (%.3f of measured copy peak %.0f GB/s) | |" % (gbs, gbs / peak, peak))
             except Exception:
                 pass
             lines.append("")

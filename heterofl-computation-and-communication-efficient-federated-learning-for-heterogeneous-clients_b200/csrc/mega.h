@@ -32,6 +32,7 @@ enum Op : int {
   OP_HEAD = 7,        // pool + linear + masked CE (+ backward) / eval logits
   OP_SGD_NORM = 8,    // ||g||^2 over the flat arena
   OP_SGD_UPDATE = 9,  // clip + weight decay + momentum + update, bf16 copy, gradient / scratch zeroing
+  OP_CFIN = 10,       // split-K finalisation: sum the fp32 partial slices, residual, bf16 store, BN statistics
 };
 
 // One client (or one evaluation pass) of a launch.  All jobs of a launch share the phase structure (same ops / barriers

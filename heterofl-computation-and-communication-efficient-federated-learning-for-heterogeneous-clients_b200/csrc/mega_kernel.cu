@@ -167,9 +167,11 @@ __device__ __forceinline__ void warp_col_reduce(float (&v)[32], int lane) {
 // The three roles (TMA producer = warp 0, MMA issuer = warp 1, epilogue = warps 4-7) each walk the CTA's tile sequence
 // of the phase on their own: the producer runs ahead through the smem ring, the MMA warp alternates between two TMEM
 // accumulators, so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
-// Split-K (flags > 1): the k-blocks of one output tile are dealt to `ksplit` work items; each stores its partial
-// accumulator into its own fp32 slice with 16-byte stores, and the LAST item to arrive (per-tile counter) sums the
-// slices and runs the normal epilogue -- no extra phase, no extra grid barrier, no contended atomics.
+// Split-K (flags > 1): one SM pulls ~60-80 GB/s from L2 / HBM, so a 128 x 128 tile with 72 k-blocks (2.3 MB of operands,
+// the 512-channel layers at batch 10) takes 36-70 us on its own.  The k-blocks of such a tile are dealt to `ksplit` work
+// items; each stores its partial accumulator into its own fp32 slice with 16-byte stores and the OP_CFIN phase that
+// follows sums the slices with every CTA of the grid (coalesced, no atomics, no serial last-arrival reduction:
+// bench/mega_conv_probe.py has the measurements that ruled those out).
 struct ConvTileId { int n_blk, n0, oh0, kb0, kb1, mn; };
 
 __device__ __forceinline__ ConvTileId conv_decode(const Phase& P, int lt) {
@@ -301,7 +303,7 @@ __device__ __noinline__ bool conv_epilogue(const Phase& P, Ctx& cx, int lt, int*
   const bf16* bn_b = reinterpret_cast<const bf16*>(P.pv[7]);
   float* bn_T = reinterpret_cast<float*>(P.pv[8]);
   const float bn_cnt = (float)nlim * (float)(iv[11] * iv[12]);
-  bool finalize = true;
+  const bool finalize = true;
   const size_t slice = (size_t)iv[0] * iv[11] * iv[12] * Cy;      // one fp32 partial slice = the output tensor's extent
   if (ksplit > 1) {
     // ---- partial accumulator -> this split's fp32 slice (plain 16-byte stores: no contended atomics)
@@ -324,19 +326,7 @@ __device__ __noinline__ bool conv_epilogue(const Phase& P, Ctx& cx, int lt, int*
     tcgen05_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&cx.tempty[acc]);
-    __threadfence();
-    epi_bar();
-    if (threadIdx.x == 128) {
-      int* ctr = reinterpret_cast<int*>(P.pv[11]) + c.mn;
-      const int old = atomicAdd(ctr, 1);
-      const int last = (old == ksplit - 1) ? 1 : 0;
-      if (last) *ctr = 0;
-      *s_flag = last;
-    }
-    epi_bar();
-    finalize = (*s_flag != 0);
-    epi_bar();                                        // everyone has read the flag before the next tile rewrites it
-    if (finalize) __threadfence();
+    return true;                                       // the OP_CFIN phase that follows sums the slices
   }
   if (finalize) {
 #pragma unroll 1
@@ -345,26 +335,12 @@ __device__ __noinline__ bool conv_epilogue(const Phase& P, Ctx& cx, int lt, int*
       if (col0 >= Cy) break;                           // warp-uniform
       const int ncol = min(32, Cy - col0);             // multiple of 8
       float f[32];
-      if (ksplit == 1) {
+      {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_d + (uint32_t(q * 32) << 16) + c0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = ok ? __uint_as_float(v[j]) : 0.f;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = 0.f;
-        if (ok) {
-          // sum the ksplit partial slices (all loads of a slice are issued before they are consumed)
-          for (int sl = 0; sl < ksplit; ++sl) {
-            const float4* sp = reinterpret_cast<const float4*>(scratch + (size_t)sl * slice + pix * Cy + col0);
-            float4 a[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = (4 * j < ncol) ? __ldcg(sp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { f[4 * j] += a[j].x; f[4 * j + 1] += a[j].y; f[4 * j + 2] += a[j].z; f[4 * j + 3] += a[j].w; }
-          }
-        }
       }
       if (bn_y != nullptr) {
         // BatchNorm-backward reductions fused into the dgrad epilogue
@@ -463,11 +439,9 @@ __device__ __noinline__ bool conv_epilogue(const Phase& P, Ctx& cx, int lt, int*
       }
     }
   }
-  if (ksplit == 1) {
-    tcgen05_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&cx.tempty[acc]);
-  }
+  tcgen05_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&cx.tempty[acc]);
   return true;
 }
 
@@ -828,6 +802,121 @@ __device__ __noinline__ void nbwd_item(const Phase& P, Ctx& cx, int item, bool a
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------ OP_CFIN
+// iv: 0 M_alloc  1 Cp  2 C_real  3 HW  4 ksplit  5 has_res  6 bnred  7 has_stats  8 rows_per_item  9 use_nvalid  10 N
+// pv: 0 out  1 residual  2 stats [2][Cp]  3 slices (fp32 [ksplit][M][Cp])  4 y  5 S  6 gamma  7 beta  8 T;  fv: 0 eps
+__device__ __noinline__ void cfin_item(const Phase& P, Ctx& cx, int item) {
+  const int* iv = P.iv;
+  const int M = iv[0], Cp = iv[1], HW = iv[3], ksplit = iv[4];
+  const int nvec = Cp >> 3, rstep = MG_THREADS / nvec;
+  const int cv = threadIdx.x % nvec, r0 = threadIdx.x / nvec;
+  const int c0 = cv * 8;
+  const int rpi = iv[8];
+  const int row_lo = item * rpi, row_hi = min(row_lo + rpi, M);
+  const int nlim = iv[9] ? min(iv[10], cx.nvalid) : iv[10];
+  const int row_lim = nlim * HW;
+  const float* SL = reinterpret_cast<const float*>(P.pv[3]);
+  const size_t slice = (size_t)M * Cp;
+  bf16* Y = reinterpret_cast<bf16*>(P.pv[0]);
+  const bf16* RES = iv[5] ? reinterpret_cast<const bf16*>(P.pv[1]) : nullptr;
+  const bool bnred = iv[6] != 0, has_stats = iv[7] != 0;
+  NormCol nc;
+  const bf16* BY = nullptr;
+  if (bnred) {
+    // BatchNorm-backward reductions of the layer whose input is pv[4]: out = dz * [bn(y) > 0];  T += (sum, sum * xhat)
+    Phase const& Q = P;       // norm_setup reads S / gamma / beta from pv[2..4]: remap below
+    (void)Q;
+    BY = reinterpret_cast<const bf16*>(P.pv[4]);
+    const float cnt = (float)nlim * (float)HW;
+    const float* S = reinterpret_cast<const float*>(P.pv[5]);
+    const bf16* gp = reinterpret_cast<const bf16*>(P.pv[6]);
+    const bf16* bp = reinterpret_cast<const bf16*>(P.pv[7]);
+    float sm[8], sq[8];
+    ld8f(S + c0, sm);
+    ld8f(S + Cp + c0, sq);
+    const float ic = cnt > 0.f ? 1.f / cnt : 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const bool real = (c0 + e) < iv[2] && cnt > 0.f;
+      const float ga = real ? ldbf(gp + c0 + e) : 0.f, be = real ? ldbf(bp + c0 + e) : 0.f;
+      const float mean = sm[e] * ic;
+      const float inv = real ? rsqrtf(fmaxf(sq[e] * ic - mean * mean, 0.f) + P.fv[0]) : 0.f;
+      nc.mean[e] = mean; nc.inv[e] = inv; nc.a[e] = ga * inv; nc.b[e] = be - mean * nc.a[e];
+    }
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
+  for (int row = row_lo + r0; row < row_hi; row += rstep) {
+    if (row >= row_lim) continue;
+    const size_t off = (size_t)row * Cp + c0;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    for (int s0 = 0; s0 < ksplit; s0 += 6) {            // up to 12 independent 16-byte loads in flight
+      float4 a[12];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const bool in = s0 + j < ksplit;
+        const float4* sp = reinterpret_cast<const float4*>(SL + (size_t)(s0 + j) * slice + off);
+        a[2 * j] = in ? __ldcg(sp) : make_float4(0.f, 0.f, 0.f, 0.f);
+        a[2 * j + 1] = in ? __ldcg(sp + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        v[0] += a[2 * j].x; v[1] += a[2 * j].y; v[2] += a[2 * j].z; v[3] += a[2 * j].w;
+        v[4] += a[2 * j + 1].x; v[5] += a[2 * j + 1].y; v[6] += a[2 * j + 1].z; v[7] += a[2 * j + 1].w;
+      }
+    }
+    if (RES != nullptr) {
+      float r8[8];
+      ld8(RES + off, r8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += r8[e];
+    }
+    if (bnred) {
+      float y8[8];
+      ld8(BY + off, y8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(nc.a[e], y8[e], nc.b[e]) > 0.f ? v[e] : 0.f;
+      const uint4 u = pack8(v);
+      *reinterpret_cast<uint4*>(Y + off) = u;
+      unpack8(u, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s1[e] += v[e]; s2[e] = fmaf(v[e], (y8[e] - nc.mean[e]) * nc.inv[e], s2[e]); }
+    } else {
+      const uint4 u = pack8(v);
+      *reinterpret_cast<uint4*>(Y + off) = u;
+      unpack8(u, v);                                    // statistics of the bf16-rounded values
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s1[e] += v[e]; s2[e] = fmaf(v[e], v[e], s2[e]); }
+    }
+  }
+  if (!(bnred || has_stats)) return;                    // uniform over the CTA
+  float* red = reinterpret_cast<float*>(cx.smem);       // [256][16]
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { red[threadIdx.x * 16 + e] = s1[e]; red[threadIdx.x * 16 + 8 + e] = s2[e]; }
+  __syncthreads();
+  for (int half = rstep >> 1; half >= 1; half >>= 1) {
+    if (r0 < half) {
+      float* mine = red + threadIdx.x * 16;
+      const float* other = red + (threadIdx.x + half * nvec) * 16;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) mine[e] += other[e];
+    }
+    __syncthreads();
+  }
+  if (r0 == 0) {
+    float* dst = reinterpret_cast<float*>(bnred ? P.pv[8] : P.pv[2]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      red_add(dst + c0 + e, red[threadIdx.x * 16 + e]);
+      red_add(dst + Cp + c0 + e, red[threadIdx.x * 16 + 8 + e]);
+    }
+  }
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------------------ OP_HEAD
@@ -1202,7 +1291,7 @@ mega_kernel(const Job* __restrict__ jobs, int njobs, int nphase, int nsteps, uns
   unsigned epoch = 0;
   unsigned rot = 0;
   const unsigned G = gridDim.x;
-  bool dead = false;
+  bool dead = false, synced = true;
   int buf = 0;
   const bool do_prof = (prof != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
   for (int step = 0; step < nsteps && !dead; ++step) {
@@ -1269,6 +1358,7 @@ mega_kernel(const Job* __restrict__ jobs, int njobs, int nphase, int nsteps, uns
           switch (sP.op) {
             case OP_PREP: prep_item(sP, cx, lt); break;
             case OP_NAPPLY: napply_item(sP, cx, lt); break;
+            case OP_CFIN: cfin_item(sP, cx, lt); break;
             case OP_NBWD_RED: nbwd_item(sP, cx, lt, false); break;
             case OP_NBWD_APPLY: nbwd_item(sP, cx, lt, true); break;
             case OP_HEAD:
@@ -1284,11 +1374,14 @@ mega_kernel(const Job* __restrict__ jobs, int njobs, int nphase, int nsteps, uns
       long long t1 = 0;
       if (do_prof) t1 = clock64();
       const int sync_after = reinterpret_cast<const Phase*>(sHdr[buf][0])->sync_after;
-      if (sync_after) {
+      // an empty phase right after a barrier has nothing to order: its own barrier is skipped (structural placeholders)
+      if (sync_after && !(nt == 0 && synced)) {
         grid_sync(ctl, epoch);
         if (aborted(ctl)) { dead = true; break; }
+        synced = true;
       } else {
         __syncthreads();
+        if (nt != 0) synced = false;
       }
       if (do_prof) {
         const long long t2 = clock64();

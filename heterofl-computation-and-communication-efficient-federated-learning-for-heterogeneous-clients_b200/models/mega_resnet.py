@@ -28,8 +28,9 @@ PHASE_DT = np.dtype([("op", "<i4"), ("ntiles", "<i4"), ("sync", "<i4"), ("flags"
                      ("fv", "<f4", (NFV,)), ("pv", "<u8", (NPV,)), ("tm", "u1", (NTM, 128))])
 assert PHASE_DT.itemsize == 896
 
-OP_NOP, OP_PREP, OP_CONV, OP_WGRAD, OP_NAPPLY, OP_NBWD_RED, OP_NBWD_APPLY, OP_HEAD, OP_SGD_NORM, OP_SGD_UPDATE = range(10)
-OP_NAMES = ["nop", "prep", "conv", "wgrad", "napply", "nbwd_red", "nbwd_apply", "head", "sgd_norm", "sgd_update"]
+(OP_NOP, OP_PREP, OP_CONV, OP_WGRAD, OP_NAPPLY, OP_NBWD_RED, OP_NBWD_APPLY, OP_HEAD, OP_SGD_NORM, OP_SGD_UPDATE,
+ OP_CFIN) = range(11)
+OP_NAMES = ["nop", "prep", "conv", "wgrad", "napply", "nbwd_red", "nbwd_apply", "head", "sgd_norm", "sgd_update", "cfin"]
 CTL_WORDS = 16
 ITEM_ELEMS4 = 256 * 8          # float4 elements per optimiser work item
 
@@ -153,7 +154,8 @@ def _conv_phase(prog: Program, *, N: int, OH: int, OW: int, out: torch.Tensor, t
                 a_maps: List[np.ndarray], b_maps: List[np.ndarray], bnhw: Tuple[int, int, int], block_n: int, b_mn: int,
                 in_stride: int, out_s: int = 1, out_ph: int = 0, out_pw: int = 0, res: Optional[torch.Tensor] = None,
                 stats: Optional[torch.Tensor] = None, group_n: int = 0, use_nvalid: int = 0, sync: int = 1,
-                name: str = "conv", split_target: int = 0, bnred: Optional[Dict] = None) -> None:
+                name: str = "conv", bnred: Optional[Dict] = None, ksplit: int = 1,
+                slices: Optional[torch.Tensor] = None) -> None:
     bn, bh, bw = bnhw
     Cy = out.shape[3]
     out_H, out_W = out.shape[1], out.shape[2]
@@ -173,25 +175,49 @@ def _conv_phase(prog: Program, *, N: int, OH: int, OW: int, out: torch.Tensor, t
     if res is not None:
         assert res.shape == out.shape
     tm = [a_maps[0], a_maps[1] if len(a_maps) > 1 else None, b_maps[0], b_maps[1] if len(b_maps) > 1 else None]
-    # split-K: too few output tiles to occupy the grid -> deal the k-blocks of a tile to several work items; partial sums
-    # meet in an fp32 scratch and the last arrival (per-tile counter) runs the epilogue (csrc/mega_kernel.cu)
     base = m_tiles * n_tiles
-    ksplit, scratch, counters = 1, None, None
-    if split_target and base * 2 <= split_target and num_k >= 4:
-        want = min(num_k // 2, -(-split_target // base), 3)     # the last arrival re-reads `ksplit` slices: keep it small
-        per = -(-num_k // max(want, 1))
-        ksplit = -(-num_k // per)
-    if ksplit > 1:
-        scratch = torch.zeros(ksplit * N * out_H * out_W * Cy, dtype=torch.float32, device=out.device)
-        counters = torch.zeros(base, dtype=torch.int32, device=out.device)
-        prog.keep += [scratch, counters]
-    pv = [_ptr(out), _ptr(res), _ptr(stats), _ptr(scratch), 0, 0, 0, 0, 0, 0, 0, _ptr(counters)]
+    pv = [_ptr(out), _ptr(res), _ptr(stats), _ptr(slices), 0, 0, 0, 0, 0, 0, 0, 0]
     fv = []
+    if ksplit > 1:               # partial sums go to `slices`; residual / statistics / BN-backward run in OP_CFIN
+        assert res is None and stats is None and bnred is None and slices is not None
+        per = -(-num_k // ksplit)
+        assert (ksplit - 1) * per < num_k, (num_k, ksplit)
     if bnred is not None:       # BatchNorm-backward reductions of the layer that produced bnred["y"], in this epilogue
         assert res is None and stats is None and bnred["y"].shape == out.shape
         pv[4:9] = [_ptr(bnred["y"]), _ptr(bnred["S"]), bnred["gamma"], bnred["beta"], _ptr(bnred["T"])]
         fv = [bnred["eps"]]
     prog.add(OP_CONV, base * ksplit, sync, iv=iv, fv=fv, pv=pv, tm=tm, name=name, flags=ksplit)
+
+
+def pick_ksplit(base_tiles: int, num_ks: List[int], split_target: int) -> int:
+    """Split-K factor for a (group of) conv phase(s) with `base_tiles` output tiles and `num_ks` k-blocks per tile."""
+    import os as _os
+    if not split_target or base_tiles * 2 > split_target or min(num_ks) < 8:
+        return 1
+    k = min(-(-split_target // base_tiles), min(num_ks) // 2, int(_os.environ.get("HFL_MEGA_KSPLIT_MAX", "12")))
+    while k > 1 and any((k - 1) * (-(-nk // k)) >= nk for nk in num_ks):
+        k -= 1
+    return max(k, 1)
+
+
+def conv_finalize(prog: Program, slices: torch.Tensor, ksplit: int, out: torch.Tensor, C: int, *, res=None, stats=None,
+                  bnred: Optional[Dict] = None, use_nvalid: int = 0, sync: int = 1, name: str = "cfin") -> None:
+    """Sum the split-K partial slices into ``out`` (+ residual), with the BatchNorm statistics (or the BatchNorm-backward
+    reductions) the conv epilogue would have produced."""
+    N, H, W_, Cp = out.shape
+    M, HW = N * H * W_, H * W_
+    if ksplit <= 1:              # structural placeholder (phase programs of all widths must line up): no work, and the
+        prog.add(OP_CFIN, 0, sync, name=name)      # kernel skips the barrier of an empty phase that follows a barrier
+        return
+    rstep = 256 // (Cp // 8)
+    rpi = max(rstep, -(-M // 96) // rstep * rstep)
+    iv = [M, Cp, C, HW, ksplit, int(res is not None), int(bnred is not None), int(stats is not None), rpi, use_nvalid, N]
+    pv = [_ptr(out), _ptr(res), _ptr(stats), _ptr(slices), 0, 0, 0, 0, 0]
+    fv = [0.0]
+    if bnred is not None:
+        pv[4:9] = [_ptr(bnred["y"]), _ptr(bnred["S"]), bnred["gamma"], bnred["beta"], _ptr(bnred["T"])]
+        fv = [bnred["eps"]]
+    prog.add(OP_CFIN, (M + rpi - 1) // rpi, sync, iv=iv, fv=fv, pv=pv, name=name)
 
 
 def _block_n(Cy: int) -> int:
@@ -200,7 +226,8 @@ def _block_n(Cy: int) -> int:
 
 def conv_fprop(prog: Program, x: torch.Tensor, w: WDesc, out: torch.Tensor, R: int, stride: int,
                res: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None, group_n: int = 0,
-               use_nvalid: int = 0, sync: int = 1, rows: int = 128, name: str = "fprop", split_target: int = 0) -> None:
+               use_nvalid: int = 0, sync: int = 1, rows: int = 128, name: str = "fprop", split_target: int = 0,
+               splittable: bool = False) -> None:
     """``out = conv(x, w) (+ res)``, optional per-channel (sum, sumsq) of the bf16 outputs into ``stats``."""
     N, H, W_, Cxp = x.shape
     _, OH, OW, Cy = out.shape
@@ -211,14 +238,29 @@ def conv_fprop(prog: Program, x: torch.Tensor, w: WDesc, out: torch.Tensor, R: i
     bnk = _block_n(Cy)
     kb = (Cxp + 63) // 64
     taps = [_tap(0, 0, r * R + s, kb, r - pad, s - pad) for r in range(R) for s in range(R)]
-    _conv_phase(prog, N=N, OH=OH, OW=OW, out=out, taps=taps, a_maps=[act_map(x, bw, bh, bn, stride)],
-                b_maps=[w.kmajor_map(bnk)], bnhw=bnhw, block_n=bnk, b_mn=0, in_stride=stride, res=res, stats=stats,
-                group_n=group_n, use_nvalid=use_nvalid, sync=sync, name=name, split_target=split_target)
+    base = ((N + bn - 1) // bn) * (OH // bh) * ((Cy + bnk - 1) // bnk)
+    ksplit = pick_ksplit(base, [kb * R * R], split_target) if splittable else 1
+    common = dict(N=N, OH=OH, OW=OW, out=out, taps=taps, a_maps=[act_map(x, bw, bh, bn, stride)],
+                  b_maps=[w.kmajor_map(bnk)], bnhw=bnhw, block_n=bnk, b_mn=0, in_stride=stride, group_n=group_n,
+                  use_nvalid=use_nvalid, name=name)
+    if ksplit == 1:
+        _conv_phase(prog, res=res, stats=stats, sync=sync, **common)
+        if splittable:
+            assert sync == 1
+            conv_finalize(prog, None, 1, out, w.Kout, sync=1, name=name + ".fin")
+        return
+    assert splittable
+    slices = torch.zeros(ksplit, N * OH * OW * Cy, dtype=torch.float32, device=out.device)
+    prog.keep.append(slices)
+    _conv_phase(prog, sync=1, ksplit=ksplit, slices=slices, **common)
+    conv_finalize(prog, slices, ksplit, out, w.Kout, res=res, stats=stats, use_nvalid=use_nvalid, sync=sync,
+                  name=name + ".fin")
 
 
 def conv_dgrad(prog: Program, dy: torch.Tensor, w: WDesc, dx: torch.Tensor, R: int, stride: int,
                dy2: Optional[torch.Tensor] = None, w2: Optional[WDesc] = None, sync: int = 1,
-               name: str = "dgrad", split_target: int = 0, bnred: Optional[Dict] = None, use_nvalid: int = 1) -> None:
+               name: str = "dgrad", split_target: int = 0, bnred: Optional[Dict] = None, use_nvalid: int = 1,
+               splittable: bool = False) -> None:
     """``dx = conv_transpose(dy, w)`` for a 3x3 / pad-1 (or 1x1 / pad-0) filter of stride 1 or 2; for stride 2 an optional
     second gradient ``dy2`` through a 1x1 stride-2 filter ``w2`` (the block shortcut) is accumulated in the same pass."""
     N, OH, OW, Kp = dy.shape
@@ -227,13 +269,27 @@ def conv_dgrad(prog: Program, dy: torch.Tensor, w: WDesc, dx: torch.Tensor, R: i
     assert w.Cin_p == Cxp and H == OH * stride and W_ == OW * stride
     bnk = _block_n(Cxp)
     kb = (Kp + 63) // 64
+    n_tiles = (Cxp + bnk - 1) // bnk
     if stride == 1:
         bnhw = brick(H, W_, 128)
         bn, bh, bw = bnhw
         taps = [_tap(0, 0, r * R + s, kb, pad - r, pad - s) for r in range(R) for s in range(R)]
-        _conv_phase(prog, N=N, OH=H, OW=W_, out=dx, taps=taps, a_maps=[act_map(dy, bw, bh, bn)], b_maps=[w.mn_map()],
-                    bnhw=bnhw, block_n=bnk, b_mn=1, in_stride=1, sync=sync, name=name, split_target=split_target,
-                    bnred=bnred, use_nvalid=use_nvalid)
+        base = ((N + bn - 1) // bn) * (H // bh) * n_tiles
+        ksplit = pick_ksplit(base, [kb * R * R], split_target) if splittable else 1
+        common = dict(N=N, OH=H, OW=W_, out=dx, taps=taps, a_maps=[act_map(dy, bw, bh, bn)], b_maps=[w.mn_map()],
+                      bnhw=bnhw, block_n=bnk, b_mn=1, in_stride=1, use_nvalid=use_nvalid, name=name)
+        if ksplit == 1:
+            _conv_phase(prog, sync=sync, bnred=bnred, **common)
+            if splittable:
+                assert sync == 1
+                conv_finalize(prog, None, 1, dx, w.Cin, sync=1, name=name + ".fin")
+        else:
+            assert splittable
+            slices = torch.zeros(ksplit, dx.numel(), dtype=torch.float32, device=dx.device)
+            prog.keep.append(slices)
+            _conv_phase(prog, sync=1, ksplit=ksplit, slices=slices, **common)
+            conv_finalize(prog, slices, ksplit, dx, w.Cin, bnred=bnred, use_nvalid=use_nvalid, sync=sync,
+                          name=name + ".fin")
         return
     assert stride == 2 and R == 3
     bnhw = brick(OH, OW, 128)
@@ -245,16 +301,30 @@ def conv_dgrad(prog: Program, dy: torch.Tensor, w: WDesc, dx: torch.Tensor, R: i
         a_maps.append(act_map(dy2, bw, bh, bn))
         b_maps.append(w2.mn_map())
     sel = {0: [(1, 0)], 1: [(0, 1), (2, 0)]}      # parity -> [(filter index, dY offset)]
+    groups = []
     for ph in (0, 1):
         for pw in (0, 1):
             taps = [_tap(0, 0, r * 3 + s, kb, di, dj) for (r, di) in sel[ph] for (s, dj) in sel[pw]]
             if dy2 is not None and ph == 0 and pw == 0:
                 taps.append(_tap(1, 1, 0, (dy2.shape[3] + 63) // 64, 0, 0))
-            last = (ph == 1 and pw == 1)
-            _conv_phase(prog, N=N, OH=OH, OW=OW, out=dx, taps=taps, a_maps=a_maps, b_maps=b_maps, bnhw=bnhw,
-                        block_n=bnk, b_mn=1, in_stride=1, out_s=2, out_ph=ph, out_pw=pw, sync=(sync if last else 0),
-                        name="%s.p%d%d" % (name, ph, pw), split_target=split_target // 4, bnred=bnred,
-                        use_nvalid=use_nvalid)
+            groups.append((ph, pw, taps))
+    base = ((N + bn - 1) // bn) * (OH // bh) * n_tiles
+    # the four parity classes write disjoint pixels of dx: one split factor, one slice buffer, one finalisation
+    ksplit = pick_ksplit(4 * base, [sum((t[0] >> 16) & 0xFFFF for t in g[2]) for g in groups], split_target) \
+        if splittable else 1
+    slices = None
+    if ksplit > 1:
+        slices = torch.zeros(ksplit, dx.numel(), dtype=torch.float32, device=dx.device)
+        prog.keep.append(slices)
+    for gi, (ph, pw, taps) in enumerate(groups):
+        last = gi == 3
+        _conv_phase(prog, N=N, OH=OH, OW=OW, out=dx, taps=taps, a_maps=a_maps, b_maps=b_maps, bnhw=bnhw,
+                    block_n=bnk, b_mn=1, in_stride=1, out_s=2, out_ph=ph, out_pw=pw,
+                    sync=((1 if ksplit > 1 else sync) if last else 0), name="%s.p%d%d" % (name, ph, pw),
+                    bnred=bnred if ksplit == 1 else None, use_nvalid=use_nvalid, ksplit=ksplit, slices=slices)
+    if ksplit > 1 or splittable:
+        assert ksplit == 1 or splittable
+        conv_finalize(prog, slices, ksplit, dx, w.Cin, bnred=bnred, use_nvalid=use_nvalid, sync=sync, name=name + ".fin")
 
 
 def conv_wgrad(prog: Program, dy: torch.Tensor, x: torch.Tensor, dW_ptr: int, Kout: int, C: int, R: int, stride: int,
@@ -422,14 +492,14 @@ class MegaResNet:
             c1 = keep.setdefault(pre + ".c1", self._act(N, OH, OW, planes))
             conv_fprop(prog, z1, self._wdesc(wc, packbuf, pre + ".conv1.weight"), c1, 3, stride,
                        stats=stats_for(pre + ".n2", planes), group_n=group_n, use_nvalid=use_nvalid, name=pre + ".conv1",
-                       split_target=split)
+                       split_target=split, splittable=(mode == "train" and OH <= 16))
             z2 = keep.setdefault(pre + ".z2", self._act(N, OH, OW, planes))
             napply(pre + ".n2", c1, z2, planes)
             nxt = (self.blocks[bi + 1]["prefix"] + ".n1") if bi + 1 < len(self.blocks) else "n4"
             yo = keep.setdefault(pre + ".out", self._act(N, OH, OW, planes))
             conv_fprop(prog, z2, self._wdesc(wc, packbuf, pre + ".conv2.weight"), yo, 3, 1, res=res,
                        stats=stats_for(nxt, planes), group_n=group_n, use_nvalid=use_nvalid, name=pre + ".conv2",
-                       split_target=split)
+                       split_target=split, splittable=(mode == "train" and OH <= 16))
             st.setdefault("yin", {})[pre] = y
             y, cin, H, W = yo, planes, OH, OW
         z4 = keep.setdefault("z4", self._act(N, H, W, cin))
@@ -513,7 +583,7 @@ class MegaResNet:
                             beta=self._pptr(wc, site + ".bias"), T=st["T"][site], eps=self.eps) if fuse else None
 
             conv_dgrad(prog, ds, self._wdesc(wc, st["packbuf"], pre + ".conv2.weight"), dz2, 3, 1, name=pre + ".conv2.dgrad",
-                       split_target=split, bnred=red_of(pre + ".n2", c1))
+                       split_target=split, bnred=red_of(pre + ".n2", c1), splittable=(H <= 16))
             dc1 = bk.setdefault(pre + ".dc1", self._act(N, H, W, planes))
             norm_bwd(prog, c1, dz2, dc1, planes, stats=st["S"][pre + ".n2"], gamma=self._pptr(wc, pre + ".n2.weight"),
                      beta=self._pptr(wc, pre + ".n2.bias"), T=st["T"][pre + ".n2"],
@@ -528,7 +598,8 @@ class MegaResNet:
                 wsc = self._wdesc(wc, st["packbuf"], pre + ".shortcut.weight")
                 if stride == 2:
                     conv_dgrad(prog, dc1, self._wdesc(wc, st["packbuf"], pre + ".conv1.weight"), dz1, 3, 2, dy2=ds,
-                               w2=wsc, name=pre + ".conv1.dgrad", split_target=split, bnred=red_of(pre + ".n1", y_in))
+                               w2=wsc, name=pre + ".conv1.dgrad", split_target=split, bnred=red_of(pre + ".n1", y_in),
+                               splittable=(IH <= 16))
                     dz1b = None
                     fuse1 = fuse
                 else:        # widening block without down-sampling (not in resnet18/34, kept for completeness)
@@ -540,7 +611,8 @@ class MegaResNet:
                 dres = None
             else:
                 conv_dgrad(prog, dc1, self._wdesc(wc, st["packbuf"], pre + ".conv1.weight"), dz1, 3, stride,
-                           name=pre + ".conv1.dgrad", split_target=split, bnred=red_of(pre + ".n1", y_in))
+                           name=pre + ".conv1.dgrad", split_target=split, bnred=red_of(pre + ".n1", y_in),
+                           splittable=(IH <= 16))
                 dz1b, dres, fuse1 = None, ds, fuse
             ds_prev = bk.setdefault(pre + ".ds", self._act(N, IH, IW, cin))
             norm_bwd(prog, y_in, dz1, ds_prev, cin, stats=st["S"][pre + ".n1"], gamma=self._pptr(wc, pre + ".n1.weight"),
