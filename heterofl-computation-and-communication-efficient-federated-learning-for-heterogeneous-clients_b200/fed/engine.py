@@ -269,7 +269,7 @@ class Engine:
         """Resident-kernel training (fed/mega_trainer.py): BatchNorm Block-ResNets in bf16 on a GPU."""
         if not (self.is_cuda and cu.available() and self.dtype == torch.bfloat16 and not self.is_lm):
             return False
-        if os.environ.get("HFL_MEGA", "1") == "0" or not self.cfg.get("fused", True):
+        if os.environ.get("HFL_MEGA_TRAIN", os.environ.get("HFL_MEGA", "1")) == "0" or not self.cfg.get("fused", True):
             return False
         from .mega_trainer import MegaSlot
         return MegaSlot.eligible(model, self.cfg)
