@@ -44,7 +44,7 @@ class Evaluator:
         self.mega = None
         self._mega_sbn = None
         self._mega_test = None
-        if self.fused is not None and os.environ.get("HFL_MEGA_EVAL", os.environ.get("HFL_MEGA", "1")) != "0":
+        if self.fused is not None and os.environ.get("HFL_MEGA_EVAL", os.environ.get("HFL_MEGA", "0")) == "1":
             from .mega_trainer import MegaSlot
             if MegaSlot.eligible(model, cfg):
                 from ..models.mega_resnet import MegaResNet
