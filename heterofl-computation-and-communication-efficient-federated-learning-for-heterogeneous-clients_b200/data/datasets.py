@@ -153,8 +153,77 @@ def _read_cifar_batches(folder, names):
     return np.ascontiguousarray(img), np.asarray(labels, dtype=np.int64)
 
 
+# Where the reference downloads each corpus from (src/datasets/{mnist,cifar,lm}.py `file` lists): (url, md5).
+DOWNLOADS = {
+    "MNIST": [("http://yann.lecun.com/exdb/mnist/train-images-idx3-ubyte.gz", "f68b3c2dcbeaaa9fbdd348bbdeb94873"),
+              ("http://yann.lecun.com/exdb/mnist/train-labels-idx1-ubyte.gz", "d53e105ee54ea40749a09fcbcd1e9432"),
+              ("http://yann.lecun.com/exdb/mnist/t10k-images-idx3-ubyte.gz", "9fb629c4189551a2d022fa330f9573f3"),
+              ("http://yann.lecun.com/exdb/mnist/t10k-labels-idx1-ubyte.gz", "ec29112dd5afa0611ce80d1b7f02629c")],
+    "FashionMNIST": [
+        ("http://fashion-mnist.s3-website.eu-central-1.amazonaws.com/train-images-idx3-ubyte.gz",
+         "8d4fb7e6c68d591d4c3dfef9ec88bf0d"),
+        ("http://fashion-mnist.s3-website.eu-central-1.amazonaws.com/train-labels-idx1-ubyte.gz",
+         "25c81989df183df01b3e8a0aad5dffbe"),
+        ("http://fashion-mnist.s3-website.eu-central-1.amazonaws.com/t10k-images-idx3-ubyte.gz",
+         "bef4ecab320f06d8554ea6380940ec79"),
+        ("http://fashion-mnist.s3-website.eu-central-1.amazonaws.com/t10k-labels-idx1-ubyte.gz",
+         "bb300cfdad3c16e7a12a480ee83cd310")],
+    "EMNIST": [("http://www.itl.nist.gov/iaui/vip/cs_links/EMNIST/gzip.zip", "58c8d27c78d21e728a6bc7b3cc06412e")],
+    "CIFAR10": [("https://www.cs.toronto.edu/~kriz/cifar-10-python.tar.gz", "c58f30108f718f92721af3b95e74349a")],
+    "CIFAR100": [("https://www.cs.toronto.edu/~kriz/cifar-100-python.tar.gz", "eb9058c3a382ffc7106e4002c42a8d85")],
+    "PennTreebank": [("https://raw.githubusercontent.com/wojzaremba/lstm/master/data/ptb.train.txt", None),
+                     ("https://raw.githubusercontent.com/wojzaremba/lstm/master/data/ptb.valid.txt", None),
+                     ("https://raw.githubusercontent.com/wojzaremba/lstm/master/data/ptb.test.txt", None)],
+    "WikiText2": [("https://s3.amazonaws.com/research.metamind.io/wikitext/wikitext-2-v1.zip", None)],
+    "WikiText103": [("https://s3.amazonaws.com/research.metamind.io/wikitext/wikitext-103-v1.zip", None)],
+}
+# EMNIST subsets (reference src/datasets/mnist.py:86-130); `subset` selects which idx files are read
+EMNIST_SUBSETS = ("byclass", "bymerge", "balanced", "letters", "digits", "mnist")
+
+
+def download_dataset(data_name: str, root: str) -> bool:
+    """Fetch and unpack the raw files of ``data_name`` into ``root/raw`` (the reference's ``download()``:
+    ``src/datasets/mnist.py:59-66``, ``cifar.py``, ``lm.py``).  Returns False when the network is unreachable."""
+    import socket
+    from .extra import download_url, extract_file
+    raw = os.path.join(root, "raw")
+    old_to = socket.getdefaulttimeout()
+    socket.setdefaulttimeout(float(os.environ.get("HFL_DOWNLOAD_TIMEOUT", "15")))
+    try:
+        for url, md5 in DOWNLOADS.get(data_name, []):
+            fn = os.path.basename(url)
+            download_url(url, raw, fn, md5)
+            if fn.endswith((".gz", ".zip", ".tgz", ".tar")):
+                extract_file(os.path.join(raw, fn))
+        return True
+    except Exception as e:          # no egress (this sandbox), DNS failure, moved URL ...
+        import warnings
+        warnings.warn("could not download %s: %s" % (data_name, e))
+        return False
+    finally:
+        socket.setdefaulttimeout(old_to)
+
+
+def _load_emnist_raw(raw, split, subset):
+    """EMNIST idx files (``raw/gzip/emnist-<subset>-{train,test}-{images-idx3,labels-idx1}-ubyte[.gz]``); images are
+    stored transposed (reference ``src/datasets/mnist.py:113-118``)."""
+    sub = subset if subset in EMNIST_SUBSETS else "balanced"
+    folder = os.path.join(raw, "gzip")
+    pi = _find(folder, "emnist-%s-%s-images-idx3-ubyte" % (sub, split))
+    pl = _find(folder, "emnist-%s-%s-labels-idx1-ubyte" % (sub, split))
+    if not (pi and pl):
+        return None
+    img = np.ascontiguousarray(np.transpose(read_idx_images(pi), (0, 2, 1)))
+    lab = read_idx_labels(pl)
+    if sub == "letters":          # labels 1..26 in the files; class indices are 0-based
+        lab = lab - lab.min()
+    return img[..., None], lab
+
+
 def _load_vision_raw(data_name, root, split):
     raw = os.path.join(root, "raw")
+    if data_name == "EMNIST":
+        return None               # needs the subset name: handled by fetch_dataset through _load_emnist_raw
     if data_name in ("MNIST", "FashionMNIST"):
         pre = "train" if split == "train" else "t10k"
         pi, pl = _find(raw, pre + "-images-idx3-ubyte"), _find(raw, pre + "-labels-idx1-ubyte")
@@ -243,7 +312,13 @@ def fetch_dataset(cfg: Dict, root: str = "./data") -> Dict[str, object]:
         if name in DATA_SIZES:
             got = None
             if synth is not True:
-                got = _load_vision_processed(droot, split, subset) or _load_vision_raw(name, droot, split)
+                def _raw():
+                    if name == "EMNIST":
+                        return _load_emnist_raw(os.path.join(droot, "raw"), split, subset)
+                    return _load_vision_raw(name, droot, split)
+                got = _load_vision_processed(droot, split, subset) or _raw()
+                if got is None and cfg.get("download", True) and download_dataset(name, droot):
+                    got = _raw()
             if got is not None:
                 img, tgt = got
                 mean, std = DATA_STATS[name]
@@ -259,7 +334,8 @@ def fetch_dataset(cfg: Dict, root: str = "./data") -> Dict[str, object]:
             if synth is not True and os.path.exists(tokp):
                 from ..ckpt.compat import load as cload
                 out[split] = LMData(name, split, cload(tokp).long(), cload(os.path.join(droot, "processed", "meta.pt")))
-            elif synth is not True and _lm_raw(name, droot, split) is not None:
+            elif synth is not True and (_lm_raw(name, droot, split) is not None or (
+                    cfg.get("download", True) and download_dataset(name, droot) and _lm_raw(name, droot, split) is not None)):
                 out[split] = _lm_raw(name, droot, split)
             elif synth in (True, "auto"):
                 out[split] = synth_lm(name, split, sizes.get(split), cfg.get("synthetic_vocab"),

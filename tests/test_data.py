@@ -66,3 +66,25 @@ def test_lm_batchify_and_iid():
     assert sorted(sum(ds["train"].values(), [])) == list(range(100))
     for u in range(10):
         assert ls[u] == torch.unique(d["train"].token[ds["train"][u]]).tolist()
+
+
+def test_emnist_raw_reader(tmp_path):
+    """EMNIST idx files are read transposed, `letters` labels become 0-based (reference src/datasets/mnist.py:86-130)."""
+    import gzip
+    import struct
+
+    import numpy as np
+
+    from hfl_b200.data.datasets import _load_emnist_raw
+    g = tmp_path / "gzip"
+    g.mkdir()
+    img = np.random.randint(0, 255, (5, 28, 28), dtype=np.uint8)
+    lab = np.array([1, 2, 3, 26, 5], dtype=np.uint8)
+    with gzip.open(g / "emnist-letters-train-images-idx3-ubyte.gz", "wb") as f:
+        f.write(struct.pack(">IIII", 2051, 5, 28, 28) + img.tobytes())
+    with gzip.open(g / "emnist-letters-train-labels-idx1-ubyte.gz", "wb") as f:
+        f.write(struct.pack(">II", 2049, 5) + lab.tobytes())
+    x, y = _load_emnist_raw(str(tmp_path), "train", "letters")
+    assert x.shape == (5, 28, 28, 1) and (x[..., 0] == img.transpose(0, 2, 1)).all()
+    assert y.tolist() == [0, 1, 2, 25, 4]
+    assert _load_emnist_raw(str(tmp_path), "test", "letters") is None
