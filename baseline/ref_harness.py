@@ -126,7 +126,16 @@ def run(args, data_name: str, model_name: str, control: str, ClockSampler) -> No
     federation = T.Federation(model.state_dict(), cfg["model_rate"], label_split)
     samples_box = [0.0]
 
+    import contextlib
+    autocast = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if (getattr(args, "ref_autocast", False) and use_cuda) \
+        else contextlib.nullcontext
+    shard_eval = bool(getattr(args, "ref_shard_eval", False)) and world > 1 and not is_lm
+
     def one_round(epoch: int) -> None:
+        with autocast():
+            _one_round(epoch)
+
+    def _one_round(epoch: int) -> None:
         logger.safe(True)
         if world == 1:
             T.train(dataset["train"], data_split["train"], label_split, federation, model, optimizer, logger, epoch)
@@ -137,6 +146,8 @@ def run(args, data_name: str, model_name: str, control: str, ClockSampler) -> No
         if not args.no_eval:
             if is_lm:
                 T.test(dataset["test"], model, logger, epoch)
+            elif shard_eval:
+                _eval_sharded(T, dist, rank, world, dataset, data_split["test"], label_split, model, logger)
             else:
                 test_model = T.stats(dataset["train"], model)
                 T.test(dataset["test"], data_split["test"], label_split, test_model, logger, epoch)
@@ -186,7 +197,9 @@ def run(args, data_name: str, model_name: str, control: str, ClockSampler) -> No
         line = {"impl": "reference", "metric": "federated_train_samples_per_sec", "value": val, "unit": "samples/s",
                 "rounds_per_sec": args.steps / (ms / 1e3), "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                "scaling": "strong", "vs_baseline": None,
+                "dtype": "bf16-autocast" if getattr(args, "ref_autocast", False) else "fp32", "data": "synthetic",
+                "eval_sharded": shard_eval,
                 "config": {"model": "%s %s %s" % (data_name, model_name, control),
                            "global_batch": cfg["batch_size"]["train"], "seq_len": None,
                            "parallelism": "reference serial client loop" if world == 1 else
@@ -228,3 +241,48 @@ def _train_sharded(T, dist, rank, world, dataset, data_split, label_split, feder
             local_parameters[m][k] = t
     federation.combine(local_parameters, param_idx, user_idx)
     global_model.load_state_dict(federation.global_parameters)
+
+
+def _eval_sharded(T, dist, rank, world, dataset, test_split, label_split, model, logger) -> None:
+    """``--ref-shard-eval``: the reference's sBN pass and test loops with the data dealt to the ranks (the stock
+    reference runs both on every rank; this variant exists so that the multi-GPU ratio is not inflated by an
+    un-parallelised evaluation).  Uses the reference's own model classes, DataLoaders, collate and Metric."""
+    import torch
+    cfg = T.cfg
+    with torch.no_grad():
+        # ---- sBN: every rank accumulates BN running statistics over its 1/world of the train set, then the
+        # cumulative averages (momentum=None) are averaged over the ranks (equal shard sizes)
+        test_model = eval('T.models.{}(model_rate=cfg["global_model_rate"], track=True).to(cfg["device"])'
+                          .format(cfg["model_name"]))
+        test_model.load_state_dict(model.state_dict(), strict=False)
+        n = len(dataset["train"])
+        idx = list(range(rank, n, world))
+        loader = T.make_data_loader({"train": T.SplitDataset(dataset["train"], idx)})["train"]
+        test_model.train(True)
+        for inp in loader:
+            inp = T.to_device(T.collate(inp), cfg["device"])
+            test_model(inp)
+        for name, buf in test_model.named_buffers():
+            if buf.dtype.is_floating_point:
+                dist.all_reduce(buf)
+                buf.div_(world)
+        # ---- test: users dealt round-robin for the Local metrics, the global test set in strided slices
+        metric = T.Metric()
+        test_model.train(False)
+        for m in range(rank, cfg["num_users"], world):
+            loader = T.make_data_loader({"test": T.SplitDataset(dataset["test"], test_split[m])})["test"]
+            for inp in loader:
+                inp = T.collate(inp)
+                bs = inp["img"].size(0)
+                inp["label_split"] = torch.tensor(label_split[m])
+                inp = T.to_device(inp, cfg["device"])
+                out = test_model(inp)
+                logger.append(metric.evaluate(cfg["metric_name"]["test"]["Local"], inp, out), "test", bs)
+        gidx = list(range(rank, len(dataset["test"]), world))
+        loader = T.make_data_loader({"test": T.SplitDataset(dataset["test"], gidx)})["test"]
+        for inp in loader:
+            inp = T.collate(inp)
+            bs = inp["img"].size(0)
+            inp = T.to_device(inp, cfg["device"])
+            out = test_model(inp)
+            logger.append(metric.evaluate(cfg["metric_name"]["test"]["Global"], inp, out), "test", bs)

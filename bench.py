@@ -100,7 +100,7 @@ def run_ours(args):
     if args.no_fused:
         cfg["fused"] = False
     eng = Engine(cfg, info, options=EngineOptions(out_dir="/tmp/hfl_bench", quiet=True, save=False,
-                                                  max_concurrent=args.max_concurrent,
+                                                  compute_dtype=args.dtype, max_concurrent=args.max_concurrent,
                                                   agg_backend=args.agg_backend, async_eval=args.async_eval,
                                                   threaded_issue=not args.single_thread_issue))
     eng.setup()
@@ -134,6 +134,11 @@ def run_ours(args):
         eng.run_round(ep, evaluate=not args.no_eval)
         ep += 1
     eng.collect_eval()
+    # the end-to-end arm below re-runs EXACTLY these rounds (same sampled clients, same starting W_g): snapshot the
+    # sampling RNG, the global model and the LR schedule position here
+    snap = {"rng": torch.get_rng_state(), "arena": eng.global_arena.clone(), "running": dict(eng.running),
+            "sched": (eng.sched.optimizer.state_dict(), eng.sched.scheduler.state_dict())}
+    ep0 = ep
     with ClockSampler(info.local_rank) as cs:
         ms, samples, launches, last = timed(args.steps, ep)
     ep += args.steps
@@ -141,11 +146,13 @@ def run_ours(args):
     # end-to-end arm: dataset in pinned host memory, every round's inputs are copied H2D inside the timed region,
     # the round's metrics are read back D2H (run_round already does that)
     eng.set_data_residency(False)
-    eng.run_round(ep, evaluate=not args.no_eval)
+    eng.run_round(ep, evaluate=not args.no_eval)         # one untimed round on the pinned-host data path
     eng.collect_eval()
-    ep += 1
+    torch.set_rng_state(snap["rng"])
+    eng.global_arena.copy_(snap["arena"])
+    eng.running = dict(snap["running"])
     eng.h2d_bytes = eng.d2h_bytes = 0
-    ms_e, samples_e, _, _ = timed(args.steps, ep)
+    ms_e, samples_e, _, _ = timed(args.steps, ep0)
     h2d, d2h = eng.h2d_bytes / args.steps, eng.d2h_bytes / args.steps
     if info.is_main:
         peaks = {}
@@ -166,15 +173,21 @@ def run_ours(args):
             "metric": "federated_train_samples_per_sec", "value": samples / (ms / 1e3), "unit": "samples/s",
             "rounds_per_sec": args.steps / (ms / 1e3), "n_gpus": info.world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "hfl_b200",
+            "vs_baseline": None, "dtype": {"auto": "bf16"}.get(args.dtype, args.dtype), "data": "synthetic",
+            "impl": "hfl_b200", "engine": "resident-kernel (HFL_MEGA=1)" if os.environ.get("HFL_MEGA") == "1"
+            else "cuda-graph",
             "config": {"model": "%s %s %s" % (data, model, control), "global_batch": cfg["batch_size"]["train"],
                        "seq_len": None, "parallelism": "client-parallel x%d (P2P aggregate)" % info.world,
                        "round": "distribute+local-train+aggregate" + ("" if args.no_eval else "+sBN-stats+test"),
                        "eval_overlap": "sBN+test of round r overlap local training of round r+1 (side stream); the "
                                        "last round's evaluation completes inside the timed region"
                        if args.async_eval else "none",
-                       "train_samples_per_round": samples / args.steps, "l2": "inputs_exceed_L2 (150 MB train set "
-                       "+ per-client arenas streamed every round; no cross-round reuse fits the 126 MB L2)",
+                       "train_samples_per_round": samples / args.steps,
+                       "l2": ("inputs_exceed_L2 (every round streams the clients' arenas, optimiser state and the "
+                              "%s; nothing reusable across rounds fits the 126 MB L2)" %
+                              ("token stream + 77 MB vocabulary tables" if model == "transformer"
+                               else "150 MB train set (sBN pass)")),
+                       "e2e_rounds": "same rounds as `value` (sampling RNG + W_g restored)",
                        "local_epochs": cfg["num_epochs"]["local"], "prewarm_s": round(prewarm_s, 1)},
             "clocks": clocks,
             "e2e": {"value": samples_e / (ms_e / 1e3), "unit": "samples/s", "rounds_per_sec": args.steps / (ms_e / 1e3),
@@ -217,6 +230,15 @@ def main():
                     help="overlap sBN+test of round r with the training of round r+1 on a side stream (measured: no "
                          "gain on one GPU -- the big eval kernels delay the latency-bound training kernels)")
     ap.add_argument("--no-fused", action="store_true", help="A/B: autograd + library-BN path instead of the fused path")
+    ap.add_argument("--dtype", default="auto", choices=["auto", "bf16", "fp32"],
+                    help="compute dtype of this framework's arm (fp32 = precision-matched to the reference's fp32/TF32 arm: "
+                         "functional model + library kernels, no bf16 anywhere)")
+    ap.add_argument("--ref-autocast", action="store_true",
+                    help="reference arm only: run the reference under torch.autocast(bf16) (precision-matched the other "
+                         "way; NOT the stock code path, reported as dtype bf16-autocast)")
+    ap.add_argument("--ref-shard-eval", action="store_true",
+                    help="reference arm, N > 1 only: also shard the sBN pass and the test loops over the ranks (harness "
+                         "code around the reference's model; the stock reference evaluates everything on every rank)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus != world:
