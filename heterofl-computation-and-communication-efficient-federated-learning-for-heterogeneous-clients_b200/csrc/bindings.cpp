@@ -37,12 +37,6 @@ void hfl_multi_sgd_clip_step(const void*, const void*, int, float*, void*, float
 int hfl_gemm_bf16_tn(const void*, int, const void*, int, void*, int, int, const float*, const void*, float, int, int,
                      int, int, cudaStream_t);
 void hfl_gemm_timing(long long*);
-int hfl_conv_halo_supported(int, int, int, int, int, int, int, int);
-int hfl_conv_halo_fprop(const void*, const void*, void*, const void*, float*, int, int, int, int, int, cudaStream_t);
-int hfl_conv_direct_supported(int, int, int, int, int, int, int, int);
-int hfl_conv_direct_fprop(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t);
-int hfl_conv_direct_dgrad(const void*, const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t);
-int hfl_conv_direct_wgrad(const void*, const void*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
 int hfl_gemm_mc_wanted(int, int, int);
 int hfl_gemm_bf16_tn_mc(const void*, int, const void*, int, void*, int, const float*, const void*, float, int, int, int, int,
                         cudaStream_t);
@@ -674,97 +668,6 @@ torch::Tensor conv_wgrad_tc(torch::Tensor dy, torch::Tensor x, int64_t R, int64_
 }
 
 
-// ---- direct small-channel convolutions (csrc/conv_direct.cu; experimental, HFL_CONV_DIRECT=1) ---------------------
-bool conv_direct_supported(int64_t N, int64_t H, int64_t W, int64_t C, int64_t K, int64_t R, int64_t S, int64_t stride) {
-  return hfl_conv_direct_supported((int)N, (int)H, (int)W, (int)C, (int)K, (int)R, (int)S, (int)stride) == 0;
-}
-
-// x: [N, C, H, W] channels-last bf16; w: [K, C, R, S] stored K,R,S,C; residual like the output (optional)
-torch::Tensor conv_direct_fprop(torch::Tensor x, torch::Tensor w, c10::optional<torch::Tensor> residual, int64_t stride) {
-  CHECK_CUDA_T(x); CHECK_CUDA_T(w);
-  TORCH_CHECK(x.dim() == 4 && w.dim() == 4 && x.scalar_type() == torch::kBFloat16 && w.scalar_type() == torch::kBFloat16);
-  TORCH_CHECK(x.is_contiguous(torch::MemoryFormat::ChannelsLast) && w.permute({0, 2, 3, 1}).is_contiguous());
-  const int N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3), K = w.size(0), R = w.size(2), S = w.size(3);
-  TORCH_CHECK(w.size(1) == C);
-  TORCH_CHECK(hfl_conv_direct_supported(N, H, W, C, K, R, S, (int)stride) == 0, "conv_direct_fprop: unsupported problem");
-  TORCH_CHECK((reinterpret_cast<uintptr_t>(x.data_ptr()) & 15) == 0 && (reinterpret_cast<uintptr_t>(w.data_ptr()) & 1) == 0);
-  const int pad = R / 2, OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - S) / stride + 1;
-  c10::cuda::CUDAGuard guard(x.device());
-  auto y = torch::empty({N, K, OH, OW}, x.options().memory_format(torch::MemoryFormat::ChannelsLast));
-  const void* rp = nullptr;
-  if (residual.has_value()) {
-    TORCH_CHECK(residual->sizes() == y.sizes() && residual->is_contiguous(torch::MemoryFormat::ChannelsLast) &&
-                residual->scalar_type() == torch::kBFloat16);
-    rp = residual->data_ptr();
-  }
-  int e = hfl_conv_direct_fprop(x.data_ptr(), w.data_ptr(), rp, y.data_ptr(), N, H, W, C, K, R, S, (int)stride, cur_stream());
-  TORCH_CHECK(e == 0, "conv_direct_fprop failed with code ", e);
-  return y;
-}
-
-// dy: [N, K, OH, OW] channels-last bf16 -> dx [N, C, H, W]
-torch::Tensor conv_direct_dgrad(torch::Tensor dy, torch::Tensor w, int64_t H, int64_t W, int64_t stride) {
-  CHECK_CUDA_T(dy); CHECK_CUDA_T(w);
-  TORCH_CHECK(dy.dim() == 4 && w.dim() == 4 && dy.scalar_type() == torch::kBFloat16 && w.scalar_type() == torch::kBFloat16);
-  TORCH_CHECK(dy.is_contiguous(torch::MemoryFormat::ChannelsLast) && w.permute({0, 2, 3, 1}).is_contiguous());
-  const int N = dy.size(0), K = dy.size(1), C = w.size(1), R = w.size(2), S = w.size(3);
-  TORCH_CHECK(w.size(0) == K);
-  TORCH_CHECK(hfl_conv_direct_supported(N, (int)H, (int)W, C, K, R, S, (int)stride) == 0 && C % 4 == 0,
-              "conv_direct_dgrad: unsupported problem");
-  const int pad = R / 2;
-  TORCH_CHECK(dy.size(2) == (H + 2 * pad - R) / stride + 1 && dy.size(3) == (W + 2 * pad - S) / stride + 1);
-  c10::cuda::CUDAGuard guard(dy.device());
-  auto dx = torch::empty({N, C, H, W}, dy.options().memory_format(torch::MemoryFormat::ChannelsLast));
-  int e = hfl_conv_direct_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), N, (int)H, (int)W, C, K, R, S, (int)stride,
-                                cur_stream());
-  TORCH_CHECK(e == 0, "conv_direct_dgrad failed with code ", e);
-  return dx;
-}
-
-// -> dw fp32, logical [K, C, R, S] stored K,R,S,C
-torch::Tensor conv_direct_wgrad(torch::Tensor dy, torch::Tensor x, int64_t R, int64_t stride) {
-  CHECK_CUDA_T(dy); CHECK_CUDA_T(x);
-  TORCH_CHECK(dy.scalar_type() == torch::kBFloat16 && x.scalar_type() == torch::kBFloat16);
-  TORCH_CHECK(dy.is_contiguous(torch::MemoryFormat::ChannelsLast) && x.is_contiguous(torch::MemoryFormat::ChannelsLast));
-  const int N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3), K = dy.size(1);
-  TORCH_CHECK(hfl_conv_direct_supported(N, H, W, C, K, (int)R, (int)R, (int)stride) == 0, "conv_direct_wgrad: unsupported");
-  c10::cuda::CUDAGuard guard(x.device());
-  auto dw = torch::empty({K, R, R, C}, torch::TensorOptions().dtype(torch::kFloat32).device(x.device()));
-  int e = hfl_conv_direct_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr<float>(), N, H, W, C, K, (int)R, (int)R, (int)stride,
-                                cur_stream());
-  TORCH_CHECK(e >= 1, "conv_direct_wgrad failed with code ", e);
-  return dw.permute({0, 3, 1, 2});
-}
-
-
-// ---- halo-reusing 3x3 convolution (csrc/conv_halo_tcgen05.cu; experimental, HFL_CONV_HALO=1) -----------------------
-bool conv_halo_supported(int64_t N, int64_t H, int64_t W, int64_t C, int64_t K, int64_t R, int64_t S, int64_t stride) {
-  return hfl_conv_halo_supported((int)N, (int)H, (int)W, (int)C, (int)K, (int)R, (int)S, (int)stride) == 0;
-}
-
-torch::Tensor conv_halo_fprop(torch::Tensor x, torch::Tensor w, c10::optional<torch::Tensor> residual,
-                              c10::optional<torch::Tensor> stats) {
-  CHECK_CUDA_T(x); CHECK_CUDA_T(w);
-  TORCH_CHECK(x.dim() == 4 && w.dim() == 4 && x.scalar_type() == torch::kBFloat16 && w.scalar_type() == torch::kBFloat16);
-  TORCH_CHECK(x.is_contiguous(torch::MemoryFormat::ChannelsLast) && w.permute({0, 2, 3, 1}).is_contiguous());
-  const int N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3), K = w.size(0);
-  TORCH_CHECK(w.size(1) == C && w.size(2) == 3 && w.size(3) == 3);
-  TORCH_CHECK(hfl_conv_halo_supported(N, H, W, C, K, 3, 3, 1) == 0, "conv_halo_fprop: unsupported problem");
-  c10::cuda::CUDAGuard guard(x.device());
-  auto y = torch::empty({N, K, H, W}, x.options().memory_format(torch::MemoryFormat::ChannelsLast));
-  const void* rp = nullptr;
-  if (residual.has_value()) {
-    TORCH_CHECK(residual->sizes() == y.sizes() && residual->is_contiguous(torch::MemoryFormat::ChannelsLast) &&
-                residual->scalar_type() == torch::kBFloat16);
-    rp = residual->data_ptr();
-  }
-  float* sp = nullptr;
-  if (stats.has_value()) { TORCH_CHECK(stats->scalar_type() == torch::kFloat32 && stats->numel() == 2 * K && stats->is_contiguous()); sp = stats->data_ptr<float>(); }
-  int e = hfl_conv_halo_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), rp, sp, N, H, W, C, K, cur_stream());
-  TORCH_CHECK(e == 0, "conv_halo_fprop failed with code ", e);
-  return y;
-}
-
 // ---- peer memory runtime (cudaMalloc + CUDA IPC) ---------------------------------------------------------
 int64_t peer_alloc(int64_t bytes) {
   void* p = nullptr;
@@ -866,12 +769,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("out_fp32"), py::arg("bias_inside") = false, py::arg("out") = py::none());
   m.def("gemm_bf16_general", &gemm_bf16_general);
   m.def("gemm_timing", []() { std::vector<long long> v(16); hfl_gemm_timing(v.data()); return v; });
-  m.def("conv_halo_supported", &conv_halo_supported);
-  m.def("conv_halo_fprop", &conv_halo_fprop);
-  m.def("conv_direct_supported", &conv_direct_supported);
-  m.def("conv_direct_fprop", &conv_direct_fprop);
-  m.def("conv_direct_dgrad", &conv_direct_dgrad);
-  m.def("conv_direct_wgrad", &conv_direct_wgrad);
   m.def("lm_embed_fwd", &lm_embed_fwd);
   m.def("lm_embed_bwd", &lm_embed_bwd);
   m.def("lm_add_ln_fwd", &lm_add_ln_fwd);

@@ -128,44 +128,7 @@ def _tc_conv_ok(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> bool
     return True
 
 
-# EXPERIMENTAL direct CUDA-core convolutions for the narrow levels (csrc/conv_direct.cu): "0" (default) | "1".
-# Only small-batch problems whose channel counts are below one tensor-core tile qualify; not validated on hardware yet.
-CONV_DIRECT_MODE = os.environ.get("HFL_CONV_DIRECT", "0")
-CONV_DIRECT_MAX_PIXELS = int(os.environ.get("HFL_CONV_DIRECT_MAX_PIXELS", "20480"))
-
-
-def _direct_conv_ok(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> bool:
-    if CONV_DIRECT_MODE != "1" or not _use_kernels(x) or w.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
-        return False
-    N, C, H, W = x.shape
-    K, _, R, S = w.shape
-    if pad != R // 2 or min(C, K) > 32 or N * (H // stride) * (W // stride) > CONV_DIRECT_MAX_PIXELS:
-        return False
-    if not (x.is_contiguous(memory_format=torch.channels_last) and w.permute(0, 2, 3, 1).is_contiguous()):
-        return False
-    return bool(cu.C().conv_direct_supported(N, H, W, C, K, R, S, stride))
-
-
-# EXPERIMENTAL halo-reusing tcgen05 convolution (csrc/conv_halo_tcgen05.cu): "0" (default) | "1"
-CONV_HALO_MODE = os.environ.get("HFL_CONV_HALO", "0")
-
-
-def _halo_conv_ok(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> bool:
-    if CONV_HALO_MODE != "1" or not _use_kernels(x) or w.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
-        return False
-    if stride != 1 or pad != 1 or tuple(w.shape[2:]) != (3, 3):
-        return False
-    if not (x.is_contiguous(memory_format=torch.channels_last) and w.permute(0, 2, 3, 1).is_contiguous()):
-        return False
-    N, C, H, W = x.shape
-    return bool(cu.C().conv_halo_supported(N, H, W, C, w.shape[0], 3, 3, 1))
-
-
 def conv_fwd(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> torch.Tensor:
-    if _direct_conv_ok(x, w, stride, pad):
-        return cu.C().conv_direct_fprop(x, w, None, stride)
-    if _halo_conv_ok(x, w, stride, pad):
-        return cu.C().conv_halo_fprop(x, w, None, None)
     if _tc_conv_ok(x, w, stride, pad):
         return cu.C().conv_fprop_tc(x, w, None, None, stride)
     return F.conv2d(x, w, None, stride, pad)
@@ -197,17 +160,6 @@ def conv_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int, pa
     """``(dx | None, dw)``.  Library path: cuDNN dgrad + wgrad.  tcgen05 path (``HFL_CONV_BWD_TC``): stride-1 dgrad as
     an implicit GEMM with mirrored taps + MN-major filter operand, wgrad with both operands MN-major and split-K;
     ``dw`` then comes back as fp32 (the multi-tensor optimiser reads either precision)."""
-    if _direct_conv_ok(x, w, stride, pad) and dy.is_contiguous(memory_format=torch.channels_last):
-        C_ = cu.C()
-        dx = dw = None
-        if need_dx and x.shape[1] % 4 == 0:
-            dx = C_.conv_direct_dgrad(dy, w, x.shape[2], x.shape[3], stride)
-        if need_dw:
-            dw = C_.conv_direct_wgrad(dy, x, w.shape[2], stride)
-        if need_dx and dx is None:        # stem (3 input channels): the library computes dx when it is wanted at all
-            dx = torch.ops.aten.convolution_backward(dy, x, w, None, (stride, stride), (pad, pad), (1, 1), False, (0, 0), 1,
-                                                     (True, False, False))[0]
-        return dx, dw
     if not need_dw:
         if CONV_BWD_TC_MODE == "on" and _tc_bwd_ok(dy, x, w, stride, pad) and stride == 1 and cu.C().conv_tc_supported(
                 x.shape[0], x.shape[2], x.shape[3], w.shape[0], x.shape[1], w.shape[2], w.shape[3], 1):

@@ -436,54 +436,3 @@ def test_cluster_multicast_gemm(M, N, K):
     assert torch.allclose(y3.float(), 2.0 * ref + b.float(), atol=6e-2, rtol=3e-2)
 
 
-@pytest.mark.skipif(os.environ.get("HFL_EXPERIMENTAL", "0") != "1", reason="experimental kernels: set HFL_EXPERIMENTAL=1")
-@pytest.mark.parametrize("N,C,H,K,R,stride", [(10, 4, 32, 4, 3, 1), (10, 8, 32, 16, 3, 2), (10, 16, 16, 16, 3, 1),
-                                               (10, 32, 8, 64, 3, 2), (10, 8, 32, 16, 1, 2), (10, 3, 32, 8, 3, 1),
-                                               (7, 32, 4, 32, 3, 1), (10, 12, 16, 20, 3, 1)])
-def test_direct_conv_matches_torch(N, C, H, K, R, stride):
-    """csrc/conv_direct.cu (HFL_CONV_DIRECT=1 path): fprop (+residual), dgrad (stride 1/2, 1x1 shortcut), wgrad."""
-    cu = _cu()
-    C_ = cu.C()
-    dev = torch.device("cuda")
-    torch.manual_seed(N * C + K)
-    assert C_.conv_direct_supported(N, H, H, C, K, R, R, stride)
-    x = torch.randn(N, C, H, H, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
-    w = (torch.randn(K, C, R, R, device=dev) / (C * R * R) ** 0.5).bfloat16().contiguous(memory_format=torch.channels_last)
-    x32, w32 = x.float().requires_grad_(True), w.float().requires_grad_(True)
-    ref = torch.nn.functional.conv2d(x32, w32, None, stride, R // 2)
-    y = C_.conv_direct_fprop(x, w, None, stride)
-    assert y.shape == ref.shape and torch.allclose(y.float(), ref, atol=3e-2, rtol=3e-2), float((y.float() - ref).abs().max())
-    res = torch.randn_like(y)
-    y2 = C_.conv_direct_fprop(x, w, res, stride)
-    assert torch.allclose(y2.float(), ref + res.float(), atol=4e-2, rtol=3e-2)
-    dy = torch.randn_like(y)
-    ref.backward(dy.float())
-    dw = C_.conv_direct_wgrad(dy, x, R, stride)
-    assert dw.shape == w.shape
-    assert torch.allclose(dw, w32.grad, atol=5e-2, rtol=3e-2), float((dw - w32.grad).abs().max())
-    if C % 4 == 0:
-        dx = C_.conv_direct_dgrad(dy, w, H, H, stride)
-        assert torch.allclose(dx.float(), x32.grad, atol=4e-2, rtol=3e-2), float((dx.float() - x32.grad).abs().max())
-
-
-@pytest.mark.skipif(os.environ.get("HFL_EXPERIMENTAL", "0") != "1", reason="experimental kernels: set HFL_EXPERIMENTAL=1")
-@pytest.mark.parametrize("N,C,H,K", [(2, 64, 32, 64), (3, 64, 16, 128), (2, 128, 16, 128), (1, 128, 32, 64)])
-def test_halo_conv_matches_torch(N, C, H, K):
-    """csrc/conv_halo_tcgen05.cu: one haloed TMA brick per channel block, nine taps through shifted UMMA descriptors."""
-    cu = _cu()
-    C_ = cu.C()
-    dev = torch.device("cuda")
-    torch.manual_seed(N + C + K)
-    assert C_.conv_halo_supported(N, H, H, C, K, 3, 3, 1)
-    x = torch.randn(N, C, H, H, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
-    w = (torch.randn(K, C, 3, 3, device=dev) / (C * 9) ** 0.5).bfloat16().contiguous(memory_format=torch.channels_last)
-    ref = torch.nn.functional.conv2d(x.float(), w.float(), None, 1, 1)
-    y = C_.conv_halo_fprop(x, w, None, None)
-    assert torch.allclose(y.float(), ref, atol=3e-2, rtol=3e-2), float((y.float() - ref).abs().max())
-    res = torch.randn_like(y)
-    stats = torch.zeros(2 * K, device=dev)
-    y2 = C_.conv_halo_fprop(x, w, res, stats)
-    assert torch.allclose(y2.float(), ref + res.float(), atol=4e-2, rtol=3e-2)
-    yf = y2.float()
-    assert torch.allclose(stats[:K], yf.sum((0, 2, 3)), atol=0.5, rtol=2e-2)
-    assert torch.allclose(stats[K:], (yf * yf).sum((0, 2, 3)), atol=0.5, rtol=2e-2)
