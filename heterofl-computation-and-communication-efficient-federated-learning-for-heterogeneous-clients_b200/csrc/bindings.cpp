@@ -59,7 +59,7 @@ void hfl_lm_gelu_drop_bwd(const void*, const void*, const unsigned char*, float,
 void hfl_lm_colsum(const void*, int, int, int, float, float*, cudaStream_t);
 void hfl_lm_attn_fwd(const void*, const void*, const void*, int, int, int, int, float, void*, void*, cudaStream_t);
 int hfl_lm_attn_bwd(const void*, const void*, const void*, const void*, const void*, const void*, int, int, int, int,
-                    float, void*, void*, void*, float*, float*, float*, float, cudaStream_t);
+                    float, void*, void*, void*, float*, float*, float*, float, int, cudaStream_t);
 int hfl_head_smem_bytes(int, int, int);
 int hfl_head_fwd_bwd(const void*, int, int, int, const void*, const void*, int, int, const long long*,
                      const unsigned char*, float, float*, double*, void*, void*, void*, float*, cudaStream_t);
@@ -69,6 +69,8 @@ int hfl_conv_fprop_tc(const void*, const void*, void*, const void*, float*, int,
 int hfl_gemm_bf16_general(const void*, int, int, const void*, int, int, void*, int, int, float, int, int, int, int,
                           cudaStream_t);
 int hfl_gemm_general_splits(int, int, int);
+int hfl_gemm_grouped(int, const void* const*, int, int, const void* const*, int, int, void* const*, int, const void* const*,
+                     const float*, int, int, int, int, cudaStream_t);
 int hfl_conv_dgrad_tc(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, cudaStream_t);
 int hfl_conv_wgrad_tc_supported(int, int, int, int, int, int, int, int);
 int hfl_conv_wgrad_tc(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
@@ -577,7 +579,8 @@ std::vector<torch::Tensor> lm_attn_fwd(torch::Tensor q, torch::Tensor k, torch::
 
 std::vector<torch::Tensor> lm_attn_bwd(torch::Tensor dO, torch::Tensor q, torch::Tensor k, torch::Tensor v,
                                        torch::Tensor O, torch::Tensor P, int64_t N, int64_t S, int64_t H, double scale,
-                                       torch::Tensor dbq, torch::Tensor dbk, torch::Tensor dbv, double alpha_v) {
+                                       torch::Tensor dbq, torch::Tensor dbk, torch::Tensor dbv, double alpha_v,
+                                       bool scale_dv) {
   check_bf(dO, "dO"); check_bf(q, "q"); check_bf(k, "k"); check_bf(v, "v"); check_bf(O, "O"); check_bf(P, "P");
   TORCH_CHECK(O.sizes() == q.sizes());
   const int E = q.size(1), dh = E / H;
@@ -587,7 +590,7 @@ std::vector<torch::Tensor> lm_attn_bwd(torch::Tensor dO, torch::Tensor q, torch:
   auto dq = torch::empty_like(q), dk = torch::empty_like(q), dv = torch::empty_like(q);
   int e = hfl_lm_attn_bwd(dO.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), O.data_ptr(), P.data_ptr(), (int)N,
                           (int)S, (int)H, dh, (float)scale, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), f32p(dbq, E), f32p(dbk, E),
-                          f32p(dbv, E), (float)alpha_v, cur_stream());
+                          f32p(dbv, E), (float)alpha_v, scale_dv ? 1 : 0, cur_stream());
   TORCH_CHECK(e == 0, "lm_attn_bwd failed with code ", e);
   return {dq, dk, dv};
 }
@@ -711,6 +714,52 @@ void peer_barrier(torch::Tensor flag_ptrs, int64_t rank, int64_t world, int64_t 
 }
 
 
+
+// Grouped GEMMs sharing one launch (csrc/gemm_grouped_tcgen05.cu).  `a` / `b`: 1 or G tensors each (a single tensor is
+// shared by every group); layouts as in gemm_bf16_general.  accum = false: returns G outputs C_g = alpha_g (A_g B_g^T +
+// bias_g); accum = true: returns ONE output alpha_0 * sum_g A_g B_g^T.
+std::vector<torch::Tensor> gemm_grouped(std::vector<torch::Tensor> a, bool a_mn, std::vector<torch::Tensor> b, bool b_mn,
+                                        c10::optional<std::vector<torch::Tensor>> bias, std::vector<double> alpha,
+                                        bool accum) {
+  const int G = (int)std::max(a.size(), b.size());
+  TORCH_CHECK(G >= 1 && G <= 3 && (a.size() == 1 || (int)a.size() == G) && (b.size() == 1 || (int)b.size() == G));
+  TORCH_CHECK((int)alpha.size() == G || alpha.size() == 1);
+  auto A = [&](int g) -> torch::Tensor& { return a[a.size() == 1 ? 0 : g]; };
+  auto B = [&](int g) -> torch::Tensor& { return b[b.size() == 1 ? 0 : g]; };
+  const int64_t M = a_mn ? A(0).size(1) : A(0).size(0), K = a_mn ? A(0).size(0) : A(0).size(1);
+  const int64_t N = b_mn ? B(0).size(1) : B(0).size(0);
+  const void* ap[3]; const void* bp[3]; const void* biasp[3] = {nullptr, nullptr, nullptr}; void* cp[3]; float al[3];
+  for (int g = 0; g < G; ++g) {
+    auto& x = A(g); auto& w = B(g);
+    CHECK_CUDA_T(x); CHECK_CUDA_T(w);
+    TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.scalar_type() == torch::kBFloat16 && w.scalar_type() == torch::kBFloat16);
+    TORCH_CHECK(x.stride(1) == 1 && w.stride(1) == 1 && x.stride(0) % 8 == 0 && w.stride(0) % 8 == 0);
+    TORCH_CHECK(x.sizes() == A(0).sizes() && w.sizes() == B(0).sizes() && x.stride(0) == A(0).stride(0) &&
+                w.stride(0) == B(0).stride(0), "gemm_grouped: groups must share shapes and strides");
+    TORCH_CHECK((b_mn ? w.size(0) : w.size(1)) == K, "gemm_grouped: reduction dims differ");
+    TORCH_CHECK((reinterpret_cast<uintptr_t>(x.data_ptr()) & 15) == 0 && (reinterpret_cast<uintptr_t>(w.data_ptr()) & 15) == 0);
+    ap[g] = x.data_ptr(); bp[g] = w.data_ptr();
+    al[g] = (float)alpha[alpha.size() == 1 ? 0 : g];
+    if (bias.has_value()) {
+      auto& bt = (*bias)[g];
+      TORCH_CHECK(bt.scalar_type() == torch::kBFloat16 && bt.numel() == N && bt.is_contiguous());
+      biasp[g] = bt.data_ptr();
+    }
+  }
+  c10::cuda::CUDAGuard guard(A(0).device());
+  std::vector<torch::Tensor> out;
+  const int n_out = accum ? 1 : G;
+  for (int g = 0; g < n_out; ++g) {
+    out.push_back(torch::empty({M, N}, torch::TensorOptions().dtype(torch::kBFloat16).device(A(0).device())));
+    cp[g] = out.back().data_ptr();
+  }
+  for (int g = n_out; g < 3; ++g) cp[g] = cp[0];
+  int e = hfl_gemm_grouped(G, ap, (int)A(0).stride(0), a_mn ? 1 : 0, bp, (int)B(0).stride(0), b_mn ? 1 : 0, cp, (int)N,
+                           bias.has_value() ? biasp : nullptr, al, accum ? 1 : 0, (int)M, (int)N, (int)K, cur_stream());
+  TORCH_CHECK(e == 0, "gemm_grouped failed with code ", e);
+  return out;
+}
+
 // ---- resident client-training megakernel (csrc/mega_kernel.cu) ------------------------------------------
 // jobs: int64 [K, 4] device tensor of {program ptr, nvalid-table ptr (0: none), per-job ctl ptr, nsteps}
 void mega_launch(torch::Tensor jobs, int64_t nphase, int64_t nsteps, torch::Tensor ctl, int64_t grid,
@@ -768,6 +817,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_bf16_tn", &gemm_bf16_tn, py::arg("x"), py::arg("w"), py::arg("bias"), py::arg("alpha"), py::arg("gelu"),
         py::arg("out_fp32"), py::arg("bias_inside") = false, py::arg("out") = py::none());
   m.def("gemm_bf16_general", &gemm_bf16_general);
+  m.def("gemm_grouped", &gemm_grouped);
   m.def("gemm_timing", []() { std::vector<long long> v(16); hfl_gemm_timing(v.data()); return v; });
   m.def("lm_embed_fwd", &lm_embed_fwd);
   m.def("lm_embed_bwd", &lm_embed_bwd);
@@ -777,7 +827,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lm_gelu_drop_bwd", &lm_gelu_drop_bwd);
   m.def("lm_colsum", &lm_colsum);
   m.def("lm_attn_fwd", &lm_attn_fwd);
-  m.def("lm_attn_bwd", &lm_attn_bwd);
+  m.def("lm_attn_bwd", &lm_attn_bwd, py::arg("dO"), py::arg("q"), py::arg("k"), py::arg("v"), py::arg("O"), py::arg("P"),
+        py::arg("N"), py::arg("S"), py::arg("H"), py::arg("scale"), py::arg("dbq"), py::arg("dbk"), py::arg("dbv"),
+        py::arg("alpha_v"), py::arg("scale_dv") = false);
   m.def("lm_max_e", &hfl_lm_max_e);
   m.def("conv_tc_supported", &conv_tc_supported);
   m.def("conv_fprop_tc", &conv_fprop_tc);

@@ -405,7 +405,8 @@ __global__ void __launch_bounds__(256)
 lm_attn_bwd_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ q, const bf16* __restrict__ k,
                    const bf16* __restrict__ v, const bf16* __restrict__ O, const bf16* __restrict__ P, int S, int H,
                    int dh, float scale, bf16* __restrict__ dq, bf16* __restrict__ dk, bf16* __restrict__ dv,
-                   float* __restrict__ dbq, float* __restrict__ dbk, float* __restrict__ dbv, float alpha_v) {
+                   float* __restrict__ dbq, float* __restrict__ dbk, float* __restrict__ dbv, float alpha_v,
+                   int scale_dv /* 1: dv is written pre-multiplied by alpha_v (grouped q/k/v backward GEMMs) */) {
   __shared__ float sA[AT_S][AT_DH + 1];          // role Q: K      role K: Q
   __shared__ float sB[AT_S][AT_DH + 1];          // role Q: V      role K: dO
   __shared__ float sC[AT_BLK][AT_DH + 1];        // role Q: dO_i   role K: V_j
@@ -497,7 +498,7 @@ lm_attn_bwd_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ q, cons
         }
         const size_t g = base + (size_t)j * E + d;
         dk[g] = __float2bfloat16(ak);
-        dv[g] = __float2bfloat16(av);
+        dv[g] = __float2bfloat16(scale_dv ? av * alpha_v : av);
         atomicAdd(&sBias[0][d], ak);
         atomicAdd(&sBias[1][d], av);
       }
@@ -595,10 +596,10 @@ extern "C" void hfl_lm_attn_fwd(const void* q, const void* k, const void* v, int
 
 extern "C" int hfl_lm_attn_bwd(const void* dO, const void* q, const void* k, const void* v, const void* O, const void* P,
                                int N, int S, int H, int dh, float scale, void* dq, void* dk, void* dv, float* dbq,
-                               float* dbk, float* dbv, float alpha_v, cudaStream_t st) {
+                               float* dbk, float* dbv, float alpha_v, int scale_dv, cudaStream_t st) {
   lm_attn_bwd_kernel<<<dim3(N * H, 8), 256, 0, st>>>((const bf16*)dO, (const bf16*)q, (const bf16*)k, (const bf16*)v,
                                                      (const bf16*)O, (const bf16*)P, S, H, dh, scale, (bf16*)dq,
-                                                     (bf16*)dk, (bf16*)dv, dbq, dbk, dbv, alpha_v);
+                                                     (bf16*)dk, (bf16*)dv, dbq, dbk, dbv, alpha_v, scale_dv);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -65,6 +65,8 @@ class FusedTransformer:
         self._small_views: Dict[str, torch.Tensor] = {}
         self._big_views: Dict[str, torch.Tensor] = {}
         self._logits: Dict[int, torch.Tensor] = {}
+        import os
+        self.grouped = os.environ.get("HFL_LM_GROUPED", "1") != "0"     # grouped q/k/v GEMMs (forward, dW, dX)
         self.keep_last = False                     # numerics tests: keep the forward intermediates of the last step
         self.last: Dict = {}
 
@@ -145,9 +147,16 @@ class FusedTransformer:
         for l in range(L):
             pre = "transformer_encoder.layers.%d" % l
             site = 16 * (l + 1)
-            q = self._lin(x, P[pre + ".mha.linear_q.weight"], P[pre + ".mha.linear_q.bias"], 1.0)
-            k = self._lin(x, P[pre + ".mha.linear_k.weight"], P[pre + ".mha.linear_k.bias"], 1.0)
-            v = self._lin(x, P[pre + ".mha.linear_v.weight"], P[pre + ".mha.linear_v.bias"], inv)
+            Wq, Wk, Wv = (P[pre + ".mha.linear_%s.weight" % n] for n in "qkv")
+            grouped = self.grouped and _aligned(x) and all(_aligned(w) for w in (Wq, Wk, Wv)) and \
+                Wq.stride(0) == Wk.stride(0) == Wv.stride(0)
+            if grouped:     # q, k, v share the A operand: ONE launch (csrc/gemm_grouped_tcgen05.cu)
+                q, k, v = C.gemm_grouped([x], False, [Wq, Wk, Wv], False,
+                                         [P[pre + ".mha.linear_%s.bias" % n] for n in "qkv"], [1.0, 1.0, inv], False)
+            else:
+                q = self._lin(x, Wq, P[pre + ".mha.linear_q.bias"], 1.0)
+                k = self._lin(x, Wk, P[pre + ".mha.linear_k.bias"], 1.0)
+                v = self._lin(x, Wv, P[pre + ".mha.linear_v.bias"], inv)
             o, pr = C.lm_attn_fwd(q, k, v, N, S, H, att_scale)
             oo = self._lin(o, P[pre + ".mha.linear_o.weight"], P[pre + ".mha.linear_o.bias"], inv)
             x1, xh1, rstd1, dm1 = C.lm_add_ln_fwd(x, oo, P[pre + ".norm1.weight"], P[pre + ".norm1.bias"], LN_EPS, p,
@@ -158,7 +167,7 @@ class FusedTransformer:
             x2, xh2, rstd2, dm2 = C.lm_add_ln_fwd(x1, f, P[pre + ".norm2.weight"], P[pre + ".norm2.bias"], LN_EPS, p,
                                                   seed_t, step_t, site + 2)
             saved.append(dict(x=x, q=q, k=k, v=v, o=o, pr=pr, x1=x1, xh1=xh1, rstd1=rstd1, dm1=dm1, u=u, hh=hh,
-                              dmg=dmg, xh2=xh2, rstd2=rstd2, dm2=dm2))
+                              dmg=dmg, xh2=xh2, rstd2=rstd2, dm2=dm2, grouped=grouped))
             x = x2
         du = self._lin(x, P["decoder.linear1.weight"], P["decoder.linear1.bias"], inv)
         dg, _ = C.lm_gelu_drop_fwd(du, 0.0, seed_t, step_t, 0)
@@ -201,14 +210,23 @@ class FusedTransformer:
             do = self._dx(doo, P[pre + ".mha.linear_o.weight"], inv)
             dq, dk, dv = C.lm_attn_bwd(do, sv["q"], sv["k"], sv["v"], sv["o"], sv["pr"], N, S, H, att_scale,
                                        sg[pre + ".mha.linear_q.bias"], sg[pre + ".mha.linear_k.bias"],
-                                       sg[pre + ".mha.linear_v.bias"], inv)
+                                       sg[pre + ".mha.linear_v.bias"], inv, bool(sv["grouped"]))
             xin = sv["x"]
-            G[pre + ".mha.linear_q.weight"] = self._dw(dq, xin, 1.0)
-            G[pre + ".mha.linear_k.weight"] = self._dw(dk, xin, 1.0)
-            G[pre + ".mha.linear_v.weight"] = self._dw(dv, xin, inv)
-            parts = [dz1, self._dx(dq, P[pre + ".mha.linear_q.weight"], 1.0),
-                     self._dx(dk, P[pre + ".mha.linear_k.weight"], 1.0),
-                     self._dx(dv, P[pre + ".mha.linear_v.weight"], inv)]
+            if sv["grouped"]:
+                # dv arrives pre-multiplied by 1/s: the three weight gradients are one launch (shared B operand = x,
+                # both operands MN-major) and the three input gradients accumulate in ONE TMEM tile
+                Wq, Wk, Wv = (P[pre + ".mha.linear_%s.weight" % n] for n in "qkv")
+                gq, gk, gv = C.gemm_grouped([dq, dk, dv], True, [xin], True, None, [1.0], False)
+                G[pre + ".mha.linear_q.weight"], G[pre + ".mha.linear_k.weight"] = gq, gk
+                G[pre + ".mha.linear_v.weight"] = gv
+                parts = [dz1, C.gemm_grouped([dq, dk, dv], False, [Wq, Wk, Wv], True, None, [1.0], True)[0]]
+            else:
+                G[pre + ".mha.linear_q.weight"] = self._dw(dq, xin, 1.0)
+                G[pre + ".mha.linear_k.weight"] = self._dw(dk, xin, 1.0)
+                G[pre + ".mha.linear_v.weight"] = self._dw(dv, xin, inv)
+                parts = [dz1, self._dx(dq, P[pre + ".mha.linear_q.weight"], 1.0),
+                         self._dx(dk, P[pre + ".mha.linear_k.weight"], 1.0),
+                         self._dx(dv, P[pre + ".mha.linear_v.weight"], inv)]
         C.lm_embed_bwd(parts, dm0, p, xh0, rstd0, P["transformer_embedding.norm.weight"], src, S,
                        self._big_views[EMB], self._big_views[POS], sg["transformer_embedding.norm.weight"],
                        sg["transformer_embedding.norm.bias"])

@@ -285,3 +285,29 @@ def test_gemm_bias_inside_padded_out_and_ragged_extents():
     _close(dw, dlv.float().t() @ d.float(), 2e-2, "dW")
     dx = C.gemm_bf16_general(dlv, False, w, True, 1.0, False)   # [M, K] = dl w, ragged reduction (33 278)
     _close(dx, dlv.float() @ w.float(), 3e-2, "dX")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,E", [(64, 256), (64, 128), (128, 64), (6400, 256)])
+def test_grouped_qkv_gemms(M, E):
+    """csrc/gemm_grouped_tcgen05.cu: the three forms used for q/k/v (forward with bias, dW, accumulated dX) vs fp32."""
+    from hfl_b200.ops import cuda as cu
+    C = cu.C()
+    dev = "cuda"
+    torch.manual_seed(0)
+    x = torch.randn(M, E, device=dev).bfloat16()
+    W = [(torch.randn(E, E, device=dev) * 0.05).bfloat16() for _ in range(3)]
+    b = [(torch.randn(E, device=dev) * 0.1).bfloat16() for _ in range(3)]
+    al = [1.0, 1.0, 0.5]
+    q, k, v = C.gemm_grouped([x], False, W, False, b, al, False)
+    for y, w, bb, a in zip((q, k, v), W, b, al):
+        ref = a * (x.float() @ w.float().t() + bb.float())
+        assert torch.allclose(y.float(), ref, atol=3e-2, rtol=3e-2), float((y.float() - ref).abs().max())
+    dy = [(torch.randn(M, E, device=dev) * 0.1).bfloat16() for _ in range(3)]
+    gw = C.gemm_grouped(dy, True, [x], True, None, [1.0], False)
+    for g, d in zip(gw, dy):
+        ref = d.float().t() @ x.float()
+        assert torch.allclose(g.float(), ref, atol=0.05 * float(ref.abs().max()) + 1e-2, rtol=3e-2)
+    dx = C.gemm_grouped(dy, False, W, True, None, [1.0], True)[0]
+    ref = sum(d.float() @ w.float() for d, w in zip(dy, W))
+    assert torch.allclose(dx.float(), ref, atol=0.03 * float(ref.abs().max()) + 1e-2, rtol=3e-2)
