@@ -69,3 +69,26 @@ if which in ("all", "lm"):
         C.lm_add_ln_bwd([do, q], xh, rs, ga, dm, 0.2, dbs[0], dbs[1], dbs[2], 1.0)
 torch.cuda.synchronize()
 print("done", which)
+if which in ("all", "mega"):
+    # one launch of the resident-training megakernel: a level-a client, 3 steps of batch 10 (target for ncu -k mega_kernel)
+    from hfl_b200.data.datasets import fetch_dataset, process_dataset
+    from hfl_b200.data.pipeline import VisionAugment
+    from hfl_b200.fed.mega_trainer import MegaSlot
+    from hfl_b200.models import Model
+    cfg = make_cfg("CIFAR10", "resnet18", "1_100_0.1_non-iid-2_dynamic_a1-b1-c1-d1-e1_bn_1_1", synthetic=True,
+                   synthetic_size={"train": 200, "test": 50})
+    ds = fetch_dataset(cfg)
+    process_dataset(cfg, ds)
+    spec = build_spec(cfg)
+    model = Model(spec, cfg, 1.0, True)
+    slot = MegaSlot(model, cfg, dev, 10, grid=int(sys.argv[2]) if len(sys.argv) > 2 else 148)
+    slot.load_params(torch.randn(model.layout.size, device=dev) * 0.05)
+    slot.begin_client(0.05, torch.ones(10, dtype=torch.uint8))
+    aug = VisionAugment(ds["train"], True, dev, torch.bfloat16)
+    imgs, labs = ds["train"].img[:30].to(dev), ds["train"].target[:30].to(dev)
+    for _ in range(2):
+        for _ in slot.train_vision(imgs, labs, aug, 1, 10, torch.Generator().manual_seed(1)):
+            pass
+    torch.cuda.synchronize()
+    slot.check()
+torch.cuda.synchronize()
