@@ -26,11 +26,16 @@ void hfl_masked_ce(const void*, int, const long long*, const unsigned char*, int
                    float, float*, double*, cudaStream_t);
 void hfl_augment(const unsigned char*, const long long*, const int*, const float*, const float*, int, int, int, int,
                  int, void*, int, cudaStream_t);
+int hfl_gn_act_fwd(const void*, const void*, const void*, const void*, int, void*, void*, float*, float*, int, int, int,
+                   int, float, int, cudaStream_t);
+int hfl_gn_act_bwd(const void*, const void*, const void*, const void*, const float*, const float*, const void*,
+                   const void*, int, void*, float*, void*, void*, int, int, int, int, int, int, float, cudaStream_t);
 int hfl_bn_act_fwd(const void*, const void*, void*, void*, const void*, const void*, int, float, int, int, int, int,
-                   float*, float*, float*, float*, int, cudaStream_t);
+                   float*, float*, float*, float*, int, const int*, int, cudaStream_t);
 void hfl_affine_act(const void*, const void*, void*, void*, const float*, const float*, long, int, int, cudaStream_t);
 int hfl_bn_act_bwd(const void*, const void*, const void*, const void*, const float*, const float*, const void*,
-                   const void*, int, int, int, int, float, int, void*, void*, void*, float*, int, cudaStream_t);
+                   const void*, int, int, int, int, float, int, void*, void*, void*, float*, int, const int*, int,
+                   cudaStream_t);
 int hfl_ms_chunk();
 void hfl_multi_sgd_clip_step(const void*, const void*, int, float*, void*, float*, const float*, float, float, float,
                              float*, cudaStream_t);
@@ -62,7 +67,8 @@ int hfl_lm_attn_bwd(const void*, const void*, const void*, const void*, const vo
                     float, void*, void*, void*, float*, float*, float*, float, int, cudaStream_t);
 int hfl_head_smem_bytes(int, int, int);
 int hfl_head_fwd_bwd(const void*, int, int, int, const void*, const void*, int, int, const long long*,
-                     const unsigned char*, float, float*, double*, void*, void*, void*, float*, cudaStream_t);
+                     const unsigned char*, float, float*, double*, void*, void*, void*, float*, const int*,
+                     cudaStream_t);
 int hfl_conv_tc_supported(int, int, int, int, int, int, int, int);
 int hfl_conv_fprop_tc(const void*, const void*, void*, const void*, float*, int, int, int, int, int, int, int, int,
                       cudaStream_t);
@@ -238,7 +244,10 @@ static const void* optp(const c10::optional<torch::Tensor>& t) { return t.has_va
 // [s (or undefined), y, mean[G,C], invstd[G,C], var_unbiased[G,C]]
 std::vector<torch::Tensor> bn_act_fwd(torch::Tensor x, c10::optional<torch::Tensor> res, torch::Tensor gamma,
                                       torch::Tensor beta, double eps, int64_t groups, int64_t C, bool relu,
-                                      c10::optional<torch::Tensor> ws_persistent) {
+                                      c10::optional<torch::Tensor> ws_persistent,
+                                      c10::optional<torch::Tensor> nvalid, int64_t samples) {
+  // nvalid (int32 [1], device): only the first *nvalid of `samples` samples are real (partial last batch of an epoch
+  // inside a captured step); statistics skip the rest and s / y are zero there
   CHECK_CUDA_T(x);
   TORCH_CHECK(x.scalar_type() == torch::kBFloat16, "bn_act_fwd: bf16 activations only");
   TORCH_CHECK(is_pow2(C) && C >= 4 && C <= 2048, "bn_act_fwd: C must be a power of two in [4, 2048]");
@@ -259,10 +268,18 @@ std::vector<torch::Tensor> bn_act_fwd(torch::Tensor x, c10::optional<torch::Tens
   const bool wp = ws_persistent.has_value() && groups == 1;
   if (wp) TORCH_CHECK(ws_persistent->scalar_type() == torch::kFloat32 && ws_persistent->numel() >= 2 * C + 1);
   auto ws = wp ? *ws_persistent : torch::empty({groups, 2, C}, fopt);
+  const int* nvp = nullptr;
+  int rps = 0;
+  if (nvalid.has_value()) {
+    TORCH_CHECK(nvalid->scalar_type() == torch::kInt32 && nvalid->is_cuda() && groups == 1 && samples > 0 &&
+                M % samples == 0 && ((M / samples) * C) % 8 == 0, "bn_act_fwd: bad nvalid / samples");
+    nvp = nvalid->data_ptr<int>();
+    rps = (int)(M / samples);
+  }
   int e = hfl_bn_act_fwd(x.data_ptr(), optp(res), res.has_value() ? s.data_ptr() : nullptr, y.data_ptr(),
                          gamma.data_ptr(), beta.data_ptr(), pb ? 1 : 0, (float)eps, (int)groups, (int)(M / groups),
                          (int)C, relu ? 1 : 0, sp, sp + groups * C, sp + 2 * groups * C, ws.data_ptr<float>(), wp ? 1 : 0,
-                         cur_stream());
+                         nvp, rps, cur_stream());
   TORCH_CHECK(e == 0, "bn_act_fwd launch failed: ", cudaGetErrorString((cudaError_t)e));
   check_launch();
   return {s, y, stats[0], stats[1], stats[2]};
@@ -287,7 +304,8 @@ std::vector<torch::Tensor> affine_act(torch::Tensor x, c10::optional<torch::Tens
 torch::Tensor bn_act_bwd(torch::Tensor dy, c10::optional<torch::Tensor> dy2, c10::optional<torch::Tensor> dres,
                          torch::Tensor s, torch::Tensor mean, torch::Tensor invstd, torch::Tensor gamma,
                          torch::Tensor beta, torch::Tensor dgamma, torch::Tensor dbeta, int64_t C, int64_t hw,
-                         double dy_scale, bool relu, c10::optional<torch::Tensor> ws_persistent) {
+                         double dy_scale, bool relu, c10::optional<torch::Tensor> ws_persistent,
+                         c10::optional<torch::Tensor> nvalid, int64_t samples) {
   CHECK_CUDA_T(dy); CHECK_CUDA_T(s);
   TORCH_CHECK(s.scalar_type() == torch::kBFloat16 && dy.scalar_type() == torch::kBFloat16);
   TORCH_CHECK(is_pow2(C) && C >= 4 && C <= 2048);
@@ -306,11 +324,73 @@ torch::Tensor bn_act_bwd(torch::Tensor dy, c10::optional<torch::Tensor> dy2, c10
   const bool wp = ws_persistent.has_value();
   if (wp) TORCH_CHECK(ws_persistent->scalar_type() == torch::kFloat32 && ws_persistent->numel() >= 2 * C + 1);
   auto ws = wp ? *ws_persistent : torch::empty({2, C}, torch::TensorOptions().dtype(torch::kFloat32).device(s.device()));
+  const int* nvp = nullptr;
+  int rps = 0;
+  if (nvalid.has_value()) {
+    TORCH_CHECK(nvalid->scalar_type() == torch::kInt32 && nvalid->is_cuda() && samples > 0 && M % samples == 0 &&
+                ((M / samples) * C) % 8 == 0, "bn_act_bwd: bad nvalid / samples");
+    nvp = nvalid->data_ptr<int>();
+    rps = (int)(M / samples);
+  }
   int e = hfl_bn_act_bwd(dy.data_ptr(), optp(dy2), optp(dres), s.data_ptr(), mean.data_ptr<float>(),
                          invstd.data_ptr<float>(), gamma.data_ptr(), beta.data_ptr(), pb ? 1 : 0, (int)M, (int)C,
                          (int)hw, (float)dy_scale, relu ? 1 : 0, ds.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                         ws.data_ptr<float>(), wp ? 1 : 0, cur_stream());
+                         ws.data_ptr<float>(), wp ? 1 : 0, nvp, rps, cur_stream());
   TORCH_CHECK(e == 0, "bn_act_bwd launch failed: ", cudaGetErrorString((cudaError_t)e));
+  check_launch();
+  return ds;
+}
+
+// ---- fused GroupNorm / InstanceNorm / LayerNorm (csrc/gn_kernels.cu) ---------------------------------------
+// x, res: NHWC-dense bf16 [N, HW, C]; returns [s (or undefined), y, mean[N,G], rstd[N,G]]
+std::vector<torch::Tensor> gn_act_fwd(torch::Tensor x, c10::optional<torch::Tensor> res, torch::Tensor gamma,
+                                      torch::Tensor beta, double eps, int64_t N, int64_t C, int64_t G, bool relu) {
+  CHECK_CUDA_T(x);
+  TORCH_CHECK(x.scalar_type() == torch::kBFloat16, "gn_act_fwd: bf16 activations only");
+  TORCH_CHECK(G >= 1 && C % G == 0 && x.numel() % (N * C) == 0);
+  const bool pb = gamma.scalar_type() == torch::kBFloat16;
+  TORCH_CHECK(pb || gamma.scalar_type() == torch::kFloat32);
+  TORCH_CHECK(gamma.is_contiguous() && beta.is_contiguous() && beta.scalar_type() == gamma.scalar_type());
+  c10::cuda::CUDAGuard guard(x.device());
+  auto y = torch::empty_like(x);
+  torch::Tensor s;
+  if (res.has_value()) { TORCH_CHECK(res->numel() == x.numel() && res->scalar_type() == torch::kBFloat16); s = torch::empty_like(x); }
+  auto stats = torch::empty({2, N, G}, torch::TensorOptions().dtype(torch::kFloat32).device(x.device()));
+  float* sp = stats.data_ptr<float>();
+  int e = hfl_gn_act_fwd(x.data_ptr(), optp(res), gamma.data_ptr(), beta.data_ptr(), pb ? 1 : 0,
+                         res.has_value() ? s.data_ptr() : nullptr, y.data_ptr(), sp, sp + N * G, (int)N,
+                         (int)(x.numel() / (N * C)), (int)C, (int)G, (float)eps, relu ? 1 : 0, cur_stream());
+  TORCH_CHECK(e == 0, "gn_act_fwd launch failed: ", e);
+  check_launch();
+  return {s, y, stats[0], stats[1]};
+}
+
+// returns ds; writes dgamma / dbeta (dtype of gamma) in place
+torch::Tensor gn_act_bwd(torch::Tensor dy, c10::optional<torch::Tensor> dy2, c10::optional<torch::Tensor> dres,
+                         torch::Tensor s, torch::Tensor mean, torch::Tensor rstd, torch::Tensor gamma,
+                         torch::Tensor beta, torch::Tensor dgamma, torch::Tensor dbeta, int64_t N, int64_t C, int64_t G,
+                         int64_t hw, double dy_scale, bool relu) {
+  CHECK_CUDA_T(dy); CHECK_CUDA_T(s);
+  TORCH_CHECK(s.scalar_type() == torch::kBFloat16 && dy.scalar_type() == torch::kBFloat16);
+  TORCH_CHECK(G >= 1 && C % G == 0 && s.numel() % (N * C) == 0 && mean.numel() == N * G && rstd.numel() == N * G);
+  if (hw > 0) {
+    TORCH_CHECK(dy.numel() * hw == s.numel());
+  } else {
+    TORCH_CHECK(dy.numel() == s.numel());
+  }
+  const bool pb = gamma.scalar_type() == torch::kBFloat16;
+  TORCH_CHECK(dgamma.scalar_type() == gamma.scalar_type() && dbeta.scalar_type() == gamma.scalar_type());
+  TORCH_CHECK(dgamma.is_contiguous() && dbeta.is_contiguous() && mean.scalar_type() == torch::kFloat32 &&
+              mean.is_contiguous() && rstd.is_contiguous());
+  c10::cuda::CUDAGuard guard(s.device());
+  auto ds = torch::empty_like(s);
+  auto part = torch::empty({N, 2, C}, torch::TensorOptions().dtype(torch::kFloat32).device(s.device()));
+  int e = hfl_gn_act_bwd(dy.data_ptr(), optp(dy2), optp(dres), s.data_ptr(), mean.data_ptr<float>(),
+                         rstd.data_ptr<float>(), gamma.data_ptr(), beta.data_ptr(), pb ? 1 : 0, ds.data_ptr(),
+                         part.data_ptr<float>(), dgamma.data_ptr(), dbeta.data_ptr(), (int)N,
+                         (int)(s.numel() / (N * C)), (int)C, (int)G, relu ? 1 : 0, (int)hw, (float)dy_scale,
+                         cur_stream());
+  TORCH_CHECK(e == 0, "gn_act_bwd launch failed: ", e);
   check_launch();
   return ds;
 }
@@ -332,7 +412,7 @@ void multi_sgd_clip_step(torch::Tensor segs, torch::Tensor blocks, torch::Tensor
 // y4: [N, C, H, W] channels-last bf16.  Returns [loss, dW, db, dpooled[N, C] (bf16)]
 std::vector<torch::Tensor> head_fwd_bwd(torch::Tensor y4, torch::Tensor W, torch::Tensor bias, torch::Tensor target,
                                         c10::optional<torch::Tensor> mask, double n_weight,
-                                        c10::optional<torch::Tensor> meter) {
+                                        c10::optional<torch::Tensor> meter, c10::optional<torch::Tensor> nvalid) {
   CHECK_CUDA_T(y4);
   TORCH_CHECK(y4.dim() == 4 && y4.scalar_type() == torch::kBFloat16 && y4.is_contiguous(torch::MemoryFormat::ChannelsLast));
   const int N = y4.size(0), C = y4.size(1), HW = y4.size(2) * y4.size(3), Kc = W.size(0);
@@ -352,7 +432,8 @@ std::vector<torch::Tensor> head_fwd_bwd(torch::Tensor y4, torch::Tensor W, torch
   auto pooled = torch::empty({N, C}, torch::TensorOptions().dtype(torch::kFloat32).device(y4.device()));
   int e = hfl_head_fwd_bwd(y4.data_ptr(), N, HW, C, W.data_ptr(), bias.data_ptr(), pb ? 1 : 0, Kc,
                            (const long long*)target.data_ptr<int64_t>(), mp, (float)n_weight, loss.data_ptr<float>(), mt,
-                           dW.data_ptr(), db.data_ptr(), dp.data_ptr(), pooled.data_ptr<float>(), cur_stream());
+                           dW.data_ptr(), db.data_ptr(), dp.data_ptr(), pooled.data_ptr<float>(),
+                           nvalid.has_value() ? nvalid->data_ptr<int>() : nullptr, cur_stream());
   TORCH_CHECK(e == 0, "head_fwd_bwd failed: ", e);
   return {loss, dW, db, dp};
 }
@@ -810,6 +891,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_act_fwd", &bn_act_fwd);
   m.def("affine_act", &affine_act);
   m.def("bn_act_bwd", &bn_act_bwd);
+  m.def("gn_act_fwd", &gn_act_fwd);
+  m.def("gn_act_bwd", &gn_act_bwd);
   m.def("multi_sgd_clip_step", &multi_sgd_clip_step);
   m.def("ms_chunk", &hfl_ms_chunk);
   m.def("head_fwd_bwd", &head_fwd_bwd);

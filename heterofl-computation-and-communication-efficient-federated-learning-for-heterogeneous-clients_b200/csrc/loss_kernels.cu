@@ -126,8 +126,12 @@ head_fwd_bwd_kernel(const float* __restrict__ pooled_g, int N, int C, const PT* 
                     const PT* __restrict__ bias, int Kc, const long long* __restrict__ target,
                     const unsigned char* __restrict__ mask, float n_weight, float* __restrict__ loss_out,
                     double* __restrict__ meter, PT* __restrict__ dW, PT* __restrict__ db,
-                    __nv_bfloat16* __restrict__ dpooled) {
+                    __nv_bfloat16* __restrict__ dpooled, const int* __restrict__ nvalid) {
+  // nvalid != nullptr: only the first *nvalid rows are real samples (partial batch inside a captured step); the loss
+  // is their mean, the padding rows get zero gradient and the meter weighs the step by *nvalid.
   extern __shared__ float sm[];
+  const int Nv = nvalid ? max(min(*nvalid, N), 1) : N;
+  if (nvalid) n_weight = (float)Nv;
   float* pooled = sm;                 // [N, C]
   float* logit = pooled + N * C;      // [N, Kc]  (becomes dlogits)
   float* red = logit + N * Kc;        // [N] row losses, [N] correct
@@ -160,11 +164,12 @@ head_fwd_bwd_kernel(const float* __restrict__ pooled_g, int N, int C, const PT* 
     se = warp_sum(se);
     const float lse = __logf(se) + bmx;
     const int t = (int)target[n];
-    if (lane == 0) { red[n] = lse - logit[n * Kc + t]; red[N + n] = (cand == t) ? 1.f : 0.f; }
+    const bool real = n < Nv;
+    if (lane == 0) { red[n] = real ? lse - logit[n * Kc + t] : 0.f; red[N + n] = (real && cand == t) ? 1.f : 0.f; }
     __syncwarp();
     for (int k = lane; k < Kc; k += 32) {
-      const bool on = (mask == nullptr || mask[k]);
-      const float g = on ? (__expf(logit[n * Kc + k] - lse) - (k == t ? 1.f : 0.f)) / (float)N : 0.f;
+      const bool on = real && (mask == nullptr || mask[k]);
+      const float g = on ? (__expf(logit[n * Kc + k] - lse) - (k == t ? 1.f : 0.f)) / (float)Nv : 0.f;
       logit[n * Kc + k] = __bfloat162float(__float2bfloat16(g));
     }
   }
@@ -173,7 +178,7 @@ head_fwd_bwd_kernel(const float* __restrict__ pooled_g, int N, int C, const PT* 
     if (tid == 0) {
       float a = 0.f, c = 0.f;
       for (int n = 0; n < N; ++n) { a += red[n]; c += red[N + n]; }
-      const float loss = a / (float)N;
+      const float loss = a / (float)Nv;
       *loss_out = loss;
       if (meter != nullptr) {
         meter[0] += (double)loss * n_weight;
@@ -214,7 +219,7 @@ extern "C" int hfl_head_smem_bytes(int N, int C, int Kc) { return (N * C + N * K
 extern "C" int hfl_head_fwd_bwd(const void* y, int N, int HW, int C, const void* W, const void* bias, int param_bf16,
                                 int Kc, const long long* target, const unsigned char* mask, float n_weight,
                                 float* loss_out, double* meter, void* dW, void* db, void* dpooled, float* pooled_ws,
-                                cudaStream_t stream) {
+                                const int* nvalid, cudaStream_t stream) {
   const int smem = hfl_head_smem_bytes(N, C, Kc);
   if (smem > 200 * 1024) return -1;
   hfl::head_pool_kernel<<<(N * C + 255) / 256, 256, 0, stream>>>((const __nv_bfloat16*)y, N, HW, C, pooled_ws);
@@ -226,13 +231,13 @@ extern "C" int hfl_head_fwd_bwd(const void* y, int N, int HW, int C, const void*
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, 512, smem, stream>>>(pooled_ws, N, C, (const __nv_bfloat16*)W, (const __nv_bfloat16*)bias, Kc, target,
                                      mask, n_weight, loss_out, meter, (__nv_bfloat16*)dW, (__nv_bfloat16*)db,
-                                     (__nv_bfloat16*)dpooled);
+                                     (__nv_bfloat16*)dpooled, nvalid);
   } else {
     auto kern = hfl::head_fwd_bwd_kernel<float>;
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, 512, smem, stream>>>(pooled_ws, N, C, (const float*)W, (const float*)bias, Kc, target, mask, n_weight,
-                                     loss_out, meter, (float*)dW, (float*)db, (__nv_bfloat16*)dpooled);
+                                     loss_out, meter, (float*)dW, (float*)db, (__nv_bfloat16*)dpooled, nvalid);
   }
   hfl::count_launch(2);
   return (int)cudaGetLastError();

@@ -113,7 +113,11 @@ __global__ void __launch_bounds__(NT)
 bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                   __nv_bfloat16* __restrict__ s_out, __nv_bfloat16* __restrict__ y, const PT* __restrict__ gamma,
                   const PT* __restrict__ beta, float eps, int Mg, int C, int relu, float* __restrict__ mean_out,
-                  float* __restrict__ invstd_out, float* __restrict__ varu_out) {
+                  float* __restrict__ invstd_out, float* __restrict__ varu_out, const int* __restrict__ nvalid,
+                  int rps) {
+  // nvalid != nullptr (training step with a partial last batch inside a captured graph): only the first
+  // *nvalid samples (rps rows each) are real; the statistics ignore the padding rows and s / y are written as zeros
+  // there, so the padding never reaches a weight gradient.
   // NV > 0: the CTA's slice (NV vectors per thread) stays in registers between the statistics pass and the apply
   //         pass -- one global read, one write, all loads in flight at once.
   // NV == 0: looping fallback for tensors larger than 16 CTAs x 512 threads x 10 vectors (second pass re-reads L2).
@@ -127,6 +131,9 @@ bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
   const int nvec = Mg * C / 8;
   const int per = NV > 0 ? NV * NT : ((nvec + K - 1) / K + NT - 1) / NT * NT;   // multiple of NT
   const int v0 = min(k * per, nvec), v1 = min(v0 + per, nvec);
+  const int Mv = nvalid ? min(*nvalid * rps, Mg) : Mg;
+  const int vv = min(v1, Mv * C / 8);          // vectors below vv hold real rows
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
   const uint4* xv = reinterpret_cast<const uint4*>(x) + gvec0;
   const uint4* rv = res ? reinterpret_cast<const uint4*>(res) + gvec0 : nullptr;
   uint4* sv = s_out ? reinterpret_cast<uint4*>(s_out) + gvec0 : nullptr;
@@ -141,8 +148,8 @@ bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
       const int v = v0 + j * NT + threadIdx.x;
-      keep[j] = v < v1 ? xv[v] : make_uint4(0, 0, 0, 0);
-      if (rv) rr[j] = v < v1 ? rv[v] : make_uint4(0, 0, 0, 0);
+      keep[j] = v < vv ? xv[v] : zero4;
+      if (rv) rr[j] = v < vv ? rv[v] : zero4;
     }
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
@@ -164,6 +171,10 @@ bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
   } else {
     for (int v = v0 + threadIdx.x; v < v1; v += NT) {
       float f[8];
+      if (v >= vv) {
+        if (rv) sv[v] = zero4;
+        continue;
+      }
       unpack8(xv[v], f);
       if (rv) {
         float r[8];
@@ -183,7 +194,7 @@ bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
   cluster.sync();
   cluster_channel_reduce(cluster, C, sa, sb, ta, tb);
   __syncthreads();
-  const float inv_n = 1.f / (float)Mg;
+  const float inv_n = 1.f / (float)max(Mv, 1);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float mean = ta[c] * inv_n;
     const float var = fmaxf(tb[c] * inv_n - mean * mean, 0.f);
@@ -194,7 +205,7 @@ bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
     if (k == 0) {
       mean_out[(long)g * C + c] = mean;
       invstd_out[(long)g * C + c] = invstd;
-      if (varu_out) varu_out[(long)g * C + c] = var * ((float)Mg / fmaxf((float)Mg - 1.f, 1.f));
+      if (varu_out) varu_out[(long)g * C + c] = var * ((float)Mv / fmaxf((float)Mv - 1.f, 1.f));
     }
   }
   __syncthreads();
@@ -215,12 +226,13 @@ bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
         f[e] = f[e] * pa[e] + pb[e];
         if (relu) f[e] = fmaxf(f[e], 0.f);
       }
-      if (v < v1) yv[v] = pack8(f);
+      if (v < v1) yv[v] = v < vv ? pack8(f) : zero4;
     }
   } else {
     const uint4* in2 = rv ? reinterpret_cast<const uint4*>(sv) : xv;
     for (int v = v0 + threadIdx.x; v < v1; v += NT) {
       float f[8];
+      if (v >= vv) { yv[v] = zero4; continue; }
       unpack8(in2[v], f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -272,7 +284,8 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
                   const __nv_bfloat16* __restrict__ dres, const __nv_bfloat16* __restrict__ s,
                   const float* __restrict__ mean, const float* __restrict__ invstd, const PT* __restrict__ gamma,
                   const PT* __restrict__ beta, int M, int C, int hw, float dy_scale, int relu,
-                  __nv_bfloat16* __restrict__ ds, PT* __restrict__ dgamma, PT* __restrict__ dbeta) {
+                  __nv_bfloat16* __restrict__ ds, PT* __restrict__ dgamma, PT* __restrict__ dbeta,
+                  const int* __restrict__ nvalid, int rps) {
   extern __shared__ float smem[];
   float *sa = smem, *sb = smem + C, *ta = smem + 2 * C, *tb = smem + 3 * C, *c_m = smem + 4 * C, *c_i = smem + 5 * C;
   cg::cluster_group cluster = cg::this_cluster();
@@ -283,6 +296,9 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
   const int nvec = M * C / 8;
   const int per = NV > 0 ? NV * NT : ((nvec + K - 1) / K + NT - 1) / NT * NT;
   const int v0 = min(k * per, nvec), v1 = min(v0 + per, nvec);
+  const int Mv = nvalid ? min(*nvalid * rps, M) : M;
+  const int vv = min(v1, Mv * C / 8);          // padding rows: no contribution to the sums, ds = 0
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
   const uint4* sv = reinterpret_cast<const uint4*>(s);
   const uint4* gv = reinterpret_cast<const uint4*>(dy);
   const uint4* g2v = reinterpret_cast<const uint4*>(dy2);
@@ -349,13 +365,13 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
       const int v = v0 + j * NT + threadIdx.x;
-      ks[j] = v < v1 ? sv[v] : make_uint4(0, 0, 0, 0);
+      ks[j] = v < vv ? sv[v] : zero4;
     }
     if (KEEP_G) {
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const int v = v0 + j * NT + threadIdx.x;
-        kg[j % NG] = v < v1 ? load_g_raw(v) : make_uint4(0, 0, 0, 0);
+        kg[j % NG] = v < vv ? load_g_raw(v) : zero4;
       }
 #pragma unroll
       for (int j = 0; j < NR; ++j) accumulate(ks[j], kg[j % NG]);
@@ -363,12 +379,12 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const int v = v0 + j * NT + threadIdx.x;
-        uint4 gs = v < v1 ? load_g_raw(v) : make_uint4(0, 0, 0, 0);
+        uint4 gs = v < vv ? load_g_raw(v) : zero4;
         accumulate(ks[j], gs);
       }
     }
   } else {
-    for (int v = v0 + threadIdx.x; v < v1; v += NT) {
+    for (int v = v0 + threadIdx.x; v < vv; v += NT) {
       uint4 gs = load_g_raw(v);
       accumulate(sv[v], gs);
     }
@@ -381,7 +397,7 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
   if (k == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) { stp(dbeta, c, ta[c]); stp(dgamma, c, tb[c]); }
   }
-  const float inv_n = 1.f / (float)M;
+  const float inv_n = 1.f / (float)max(Mv, 1);
   float qa[8], qb[8];
   {
     const int base = (8 * threadIdx.x) % C;
@@ -416,13 +432,16 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
       const int v = v0 + j * NT + threadIdx.x;
-      if (v < v1) {
+      if (v < vv) {
         if (KEEP_G) apply(v, ks[j], kg[j % NG]);
         else apply(v, ks[j], masked_g(v, ks[j]));
+      } else if (v < v1) {
+        dv[v] = zero4;
       }
     }
   } else {
     for (int v = v0 + threadIdx.x; v < v1; v += NT) {
+      if (v >= vv) { dv[v] = zero4; continue; }
       const uint4 xs = sv[v];
       apply(v, xs, masked_g(v, xs));
     }
@@ -437,8 +456,10 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT)
 bn_stats_wide_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
-                     __nv_bfloat16* __restrict__ s_out, int nvec, int C, float* __restrict__ ws) {
+                     __nv_bfloat16* __restrict__ s_out, int nvec, int C, float* __restrict__ ws,
+                     const int* __restrict__ nvalid, int rps) {
   // blockIdx.y = statistics group (ghost batch); nvec = vectors per group; ws = [G][2][C]
+  const int vv = nvalid ? min(*nvalid * rps * C / 8, nvec) : nvec;
   extern __shared__ float smem[];
   float *sa = smem, *sb = smem + C;
   const long goff = (long)blockIdx.y * nvec;
@@ -451,6 +472,10 @@ bn_stats_wide_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
   for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
   for (int v = blockIdx.x * NT + threadIdx.x; v < nvec; v += gridDim.x * NT) {
     float f[8];
+    if (v >= vv) {
+      if (rv) sv[v] = make_uint4(0, 0, 0, 0);
+      continue;
+    }
     unpack8(xv[v], f);
     if (rv) {
       float r[8];
@@ -490,10 +515,11 @@ __global__ void __launch_bounds__(NT)
 bn_apply_wide_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restrict__ y, const PT* __restrict__ gamma,
                      const PT* __restrict__ beta, float eps, int M, int C, int relu, float* __restrict__ ws,
                      float* __restrict__ mean_out, float* __restrict__ invstd_out, float* __restrict__ varu_out,
-                     int self_clean) {
+                     int self_clean, const int* __restrict__ nvalid, int rps) {
   extern __shared__ float smem[];
   float *sc_a = smem, *sc_b = smem + C;
-  const float inv_n = 1.f / (float)M;
+  const int Mv = nvalid ? max(min(*nvalid * rps, M), 1) : M;
+  const float inv_n = 1.f / (float)Mv;
   {   // blockIdx.y = statistics group
     const long g = blockIdx.y;
     ws += g * 2 * C;
@@ -513,7 +539,7 @@ bn_apply_wide_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restr
     if (blockIdx.x == 0) {
       mean_out[c] = mean;
       invstd_out[c] = invstd;
-      if (varu_out) varu_out[c] = var * ((float)M / fmaxf((float)M - 1.f, 1.f));
+      if (varu_out) varu_out[c] = var * ((float)Mv / fmaxf((float)Mv - 1.f, 1.f));
     }
   }
   __syncthreads();
@@ -525,10 +551,12 @@ bn_apply_wide_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restr
     for (int e = 0; e < 8; ++e) { pa[e] = sc_a[(base + e) % C]; pb[e] = sc_b[(base + e) % C]; }
   }
   const int nvec = M * C / 8;
+  const int vv = nvalid ? min(*nvalid * rps * C / 8, nvec) : nvec;
   const uint4* sv = reinterpret_cast<const uint4*>(s);
   uint4* yv = reinterpret_cast<uint4*>(y);
   for (int v = blockIdx.x * NT + threadIdx.x; v < nvec; v += gridDim.x * NT) {
     float f[8];
+    if (v >= vv) { yv[v] = make_uint4(0, 0, 0, 0); continue; }
     unpack8(sv[v], f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -544,9 +572,11 @@ __global__ void __launch_bounds__(NT)
 bn_bwd_reduce_wide_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
                           const __nv_bfloat16* __restrict__ s, const float* __restrict__ mean,
                           const float* __restrict__ invstd, const PT* __restrict__ gamma, const PT* __restrict__ beta,
-                          int nvec, int C, int relu, float* __restrict__ ws) {
+                          int nvec_all, int C, int relu, float* __restrict__ ws, const int* __restrict__ nvalid,
+                          int rps) {
   extern __shared__ float smem[];
   float *sa = smem, *sb = smem + C;
+  const int nvec = nvalid ? min(*nvalid * rps * C / 8, nvec_all) : nvec_all;   // padding rows carry no gradient
   float pm[8], pi[8], pg[8], pb[8];
   {
     const int base = (8 * threadIdx.x) % C;
@@ -594,9 +624,10 @@ bn_bwd_apply_wide_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat
                          const float* __restrict__ mean, const float* __restrict__ invstd,
                          const PT* __restrict__ gamma, const PT* __restrict__ beta, int M, int C, int relu,
                          float* __restrict__ ws, __nv_bfloat16* __restrict__ ds, PT* __restrict__ dgamma,
-                         PT* __restrict__ dbeta, int self_clean) {
+                         PT* __restrict__ dbeta, int self_clean, const int* __restrict__ nvalid, int rps) {
   float pm[8], pi[8], pg[8], pb[8], qa[8], qb[8];
-  const float inv_n = 1.f / (float)M;
+  const int Mv = nvalid ? max(min(*nvalid * rps, M), 1) : M;
+  const float inv_n = 1.f / (float)Mv;
   {
     const int base = (8 * threadIdx.x) % C;
 #pragma unroll
@@ -616,8 +647,10 @@ bn_bwd_apply_wide_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat
   const uint4* g2v = reinterpret_cast<const uint4*>(dy2);
   const uint4* rv = reinterpret_cast<const uint4*>(dres);
   uint4* dv = reinterpret_cast<uint4*>(ds);
+  const int vv = nvalid ? min(*nvalid * rps * C / 8, nvec) : nvec;
   for (int v = blockIdx.x * NT + threadIdx.x; v < nvec; v += gridDim.x * NT) {
     float x[8], g[8], o[8], r[8];
+    if (v >= vv) { dv[v] = make_uint4(0, 0, 0, 0); continue; }
     unpack8(sv[v], x);
     unpack8(gv[v], g);
     if (dy2) {
@@ -719,7 +752,8 @@ static int wide_grid(long nvec) {
 extern "C" int hfl_bn_act_fwd(const void* x, const void* res, void* s_out, void* y, const void* gamma,
                               const void* beta, int param_bf16, float eps, int groups, int Mg, int C, int relu,
                               float* mean_out, float* invstd_out, float* varu_out, float* ws, int ws_persistent,
-                              cudaStream_t stream) {
+                              const int* nvalid, int rps, cudaStream_t stream) {
+  if (groups > 1) nvalid = nullptr;               // ghost batches are always full
   if (((long)Mg * C > WIDE_ELEMS || groups > 1) && ws != nullptr) {   // ghost batches: always the wide path
     const int nvec = Mg * C / 8;
     int gx = wide_grid(nvec);
@@ -728,16 +762,16 @@ extern "C" int hfl_bn_act_fwd(const void* x, const void* res, void* s_out, void*
     const int self_clean = (ws_persistent && groups == 1) ? 1 : 0;
     if (!self_clean) cudaMemsetAsync(ws, 0, 2 * (size_t)C * groups * sizeof(float), stream);
     bn_stats_wide_kernel<<<grid, NT, wide_smem(C), stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res,
-                                                             (__nv_bfloat16*)s_out, nvec, C, ws);
+                                                             (__nv_bfloat16*)s_out, nvec, C, ws, nvalid, rps);
     const void* sin = res ? s_out : x;
     if (param_bf16)
       bn_apply_wide_kernel<__nv_bfloat16><<<grid, NT, 2 * C * sizeof(float), stream>>>(
           (const __nv_bfloat16*)sin, (__nv_bfloat16*)y, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, eps, Mg, C,
-          relu, ws, mean_out, invstd_out, varu_out, self_clean);
+          relu, ws, mean_out, invstd_out, varu_out, self_clean, nvalid, rps);
     else
       bn_apply_wide_kernel<float><<<grid, NT, 2 * C * sizeof(float), stream>>>(
           (const __nv_bfloat16*)sin, (__nv_bfloat16*)y, (const float*)gamma, (const float*)beta, eps, Mg, C, relu, ws,
-          mean_out, invstd_out, varu_out, self_clean);
+          mean_out, invstd_out, varu_out, self_clean, nvalid, rps);
     count_launch(2);
     return (int)cudaGetLastError();
   }
@@ -750,12 +784,12 @@ extern "C" int hfl_bn_act_fwd(const void* x, const void* res, void* s_out, void*
     HFL_NV_DISPATCH(NV, (e = launch_cluster(bn_act_fwd_kernel<__nv_bfloat16, NVC>, grid, K, smem, stream,
                                             (const __nv_bfloat16*)x, (const __nv_bfloat16*)res, (__nv_bfloat16*)s_out,
                                             (__nv_bfloat16*)y, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
-                                            eps, Mg, C, relu, mean_out, invstd_out, varu_out)))
+                                            eps, Mg, C, relu, mean_out, invstd_out, varu_out, nvalid, rps)))
   } else {
     HFL_NV_DISPATCH(NV, (e = launch_cluster(bn_act_fwd_kernel<float, NVC>, grid, K, smem, stream,
                                             (const __nv_bfloat16*)x, (const __nv_bfloat16*)res, (__nv_bfloat16*)s_out,
                                             (__nv_bfloat16*)y, (const float*)gamma, (const float*)beta, eps, Mg, C, relu,
-                                            mean_out, invstd_out, varu_out)))
+                                            mean_out, invstd_out, varu_out, nvalid, rps)))
   }
   count_launch();
   return (int)e;
@@ -775,7 +809,7 @@ extern "C" void hfl_affine_act(const void* x, const void* res, void* s_out, void
 extern "C" int hfl_bn_act_bwd(const void* dy, const void* dy2, const void* dres, const void* s, const float* mean,
                               const float* invstd, const void* gamma, const void* beta, int param_bf16, int M, int C,
                               int hw, float dy_scale, int relu, void* ds, void* dgamma, void* dbeta, float* ws,
-                              int ws_persistent, cudaStream_t stream) {
+                              int ws_persistent, const int* nvalid, int rps, cudaStream_t stream) {
   if (hw == 0 && (long)M * C > WIDE_ELEMS && ws != nullptr) {
     const int nvec = M * C / 8;
     const int grid = wide_grid(nvec);
@@ -784,19 +818,19 @@ extern "C" int hfl_bn_act_bwd(const void* dy, const void* dy2, const void* dres,
     if (param_bf16) {
       bn_bwd_reduce_wide_kernel<__nv_bfloat16><<<grid, NT, wide_smem(C), stream>>>(
           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)s, mean, invstd,
-          (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, nvec, C, relu, ws);
+          (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, nvec, C, relu, ws, nvalid, rps);
       bn_bwd_apply_wide_kernel<__nv_bfloat16><<<grid, NT, 0, stream>>>(
           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean,
           invstd, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, M, C, relu, ws, (__nv_bfloat16*)ds,
-          (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, self_clean);
+          (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, self_clean, nvalid, rps);
     } else {
       bn_bwd_reduce_wide_kernel<float><<<grid, NT, wide_smem(C), stream>>>(
           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)s, mean, invstd, (const float*)gamma,
-          (const float*)beta, nvec, C, relu, ws);
+          (const float*)beta, nvec, C, relu, ws, nvalid, rps);
       bn_bwd_apply_wide_kernel<float><<<grid, NT, 0, stream>>>(
           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean,
           invstd, (const float*)gamma, (const float*)beta, M, C, relu, ws, (__nv_bfloat16*)ds, (float*)dgamma,
-          (float*)dbeta, self_clean);
+          (float*)dbeta, self_clean, nvalid, rps);
     }
     count_launch(2);
     return (int)cudaGetLastError();
@@ -811,13 +845,14 @@ extern "C" int hfl_bn_act_bwd(const void* dy, const void* dy2, const void* dres,
                                             (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2,
                                             (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean, invstd,
                                             (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, M, C, hw, dy_scale,
-                                            relu, (__nv_bfloat16*)ds, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta)))
+                                            relu, (__nv_bfloat16*)ds, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta,
+                                            nvalid, rps)))
   } else {
     HFL_NV_DISPATCH(NV, (e = launch_cluster(bn_act_bwd_kernel<float, NVC>, grid, K, smem, stream,
                                             (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2,
                                             (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean, invstd,
                                             (const float*)gamma, (const float*)beta, M, C, hw, dy_scale, relu,
-                                            (__nv_bfloat16*)ds, (float*)dgamma, (float*)dbeta)))
+                                            (__nv_bfloat16*)ds, (float*)dgamma, (float*)dbeta, nvalid, rps)))
   }
   count_launch();
   return (int)e;

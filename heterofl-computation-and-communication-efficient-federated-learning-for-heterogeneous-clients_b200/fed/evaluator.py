@@ -38,7 +38,7 @@ class Evaluator:
         self._test_g = None
         self.fused = None
         if self.device.type == "cuda" and compute_dtype == torch.bfloat16 and cu.available() \
-                and cfg.get("fused", True) and FusedResNet.eligible(model.spec):
+                and cfg.get("fused", True) and FusedResNet.eligible(model.spec, train_only=False):
             self.fused = FusedResNet(model.spec, model.scale_rate)
         # resident-kernel programs (models/mega_resnet.py): the whole sBN pass / test pass of this rank is ONE launch
         self.mega = None

@@ -166,14 +166,15 @@ class TrainSlot:
         else:
             sgd_clip_step_torch(self.w, self.wc, self.g, self.mom, self.lr, self.momentum, self.wd, self.max_norm)
 
-    def _fwd_bwd(self, inp: Dict, n_weight: float) -> None:
+    def _fwd_bwd(self, inp: Dict, n_weight: float, nvalid: Optional[torch.Tensor] = None) -> None:
         mask = self.mask_t if self.use_mask else None
         if self.fused is not None and self.model.is_lm:
             _, self._grads = self.fused.train_step(self.Pv, inp["label"], mask, (self.meter.buf, n_weight),
                                                    self.rng_seed, self.step_ctr)
             return
         if self.fused is not None:
-            _, self._grads = self.fused.train_step(self.Pv, inp["img"], inp["label"], mask, (self.meter.buf, n_weight))
+            _, self._grads = self.fused.train_step(self.Pv, inp["img"], inp["label"], mask, (self.meter.buf, n_weight),
+                                                   nvalid)
             return
         if self.use_kernels:
             inp = dict(inp)
@@ -194,13 +195,17 @@ class TrainSlot:
         perms = torch.stack([torch.randperm(n, generator=generator) for _ in range(epochs)])
         params = aug.draw(epochs * n, generator).view(epochs, n, 3)
         perms_d = perms.to(self.device, non_blocking=True)
-        if self.use_graph and full > 0:
-            self._vision_static(imgs_u8, labels, aug, batch, perms_d, params, epochs, full, max_n, max_epochs)
+        # the fused ResNet step takes the number of real samples from the device (``nvalid``), so the partial last
+        # batch of an epoch replays the SAME captured graph as the full ones; other models run it eagerly
+        masked = self.use_graph and rem > 0 and self.fused is not None and not self.model.is_lm
+        if self.use_graph and (full > 0 or masked):
+            self._vision_static(imgs_u8, labels, aug, batch, perms_d, params, epochs, full, max_n, max_epochs,
+                                rem if masked else 0)
         for ep in range(epochs):
             for s in range(steps_per_epoch):
                 lo = s * batch
                 bs = min(batch, n - lo)
-                if self.use_graph and bs == batch:
+                if self.use_graph and (bs == batch or masked):
                     self._replay(("v", batch, tuple(imgs_u8.shape[1:])))
                 else:
                     idx = perms_d[ep, lo:lo + bs]
@@ -210,37 +215,55 @@ class TrainSlot:
                     self._opt_step()
                 yield
 
-    def _vision_static(self, imgs_u8, labels, aug, batch, perms_d, params, epochs, full, max_n=0, max_epochs=0):
+    def _vision_static(self, imgs_u8, labels, aug, batch, perms_d, params, epochs, full, max_n=0, max_epochs=0,
+                       rem=0):
         """(Re)bind the static buffers the captured step reads from, capturing the graph on first use.  ``max_n`` /
-        ``max_epochs`` (largest shard / local epochs of the run) size the buffers so they never have to grow."""
+        ``max_epochs`` (largest shard / local epochs of the run) size the buffers so they never have to grow.
+        ``rem > 0``: every epoch ends with a padded step of ``rem`` real samples (fused ResNet path)."""
         key = ("v", batch, tuple(imgs_u8.shape[1:]))
         n = imgs_u8.shape[0]
         cap = self._static.get(key)
         max_n = max(n, max_n, cap["imgs"].shape[0] if cap else 0)
-        max_rows = max(epochs, max_epochs) * (max_n // batch)
+        max_rows = max(epochs, max_epochs) * ((max_n + batch - 1) // batch)
         if cap is None or cap["imgs"].shape[0] < n or cap["idx"].shape[0] < max_rows:
             cap = {"imgs": torch.zeros((max_n,) + tuple(imgs_u8.shape[1:]), dtype=torch.uint8, device=self.device),
                    "labels": torch.zeros(max_n, dtype=torch.int64, device=self.device),
                    "idx": torch.zeros(max_rows, batch, dtype=torch.int64, device=self.device),
                    "par": torch.zeros(max_rows, batch, 3, dtype=torch.int32, device=self.device),
+                   "nv": torch.full((max_rows,), batch, dtype=torch.int32, device=self.device),
                    "row": self.step_ctr}
             self._static[key] = cap
             self.graphs.pop(key, None)
         cap["imgs"][:n].copy_(imgs_u8, non_blocking=True)
         cap["labels"][:n].copy_(labels, non_blocking=True)
-        # only full batches go through the graph: rows = (epoch, step) pairs in execution order
-        for ep in range(epochs):
-            cap["idx"][ep * full:(ep + 1) * full].copy_(perms_d[ep, :full * batch].view(full, batch), non_blocking=True)
-            cap["par"][ep * full:(ep + 1) * full].copy_(params[ep, :full * batch].view(full, batch, 3),
-                                                        non_blocking=True)
+        # rows = (epoch, step) pairs in execution order; a padded last step repeats sample 0 of the permutation in
+        # its unused slots (real pixels: the padding rows stay finite until the first norm zeroes them)
+        spe = full + (1 if rem else 0)
+        if rem:
+            padn = spe * batch - n
+            idx_t = torch.cat([perms_d, perms_d[:, :1].expand(epochs, padn)], dim=1).view(epochs * spe, batch)
+            par_t = torch.cat([params, params[:, :1].expand(epochs, padn, 3)], dim=1).view(epochs * spe, batch, 3)
+            nv_t = torch.full((epochs, spe), batch, dtype=torch.int32)
+            nv_t[:, -1] = rem
+        else:
+            idx_t = perms_d[:, :full * batch].reshape(epochs * full, batch)
+            par_t = params[:, :full * batch].reshape(epochs * full, batch, 3)
+            nv_t = torch.full((epochs, spe), batch, dtype=torch.int32)
+        rows = epochs * spe
+        cap["idx"][:rows].copy_(idx_t, non_blocking=True)
+        cap["par"][:rows].copy_(par_t, non_blocking=True)
+        cap["nv"][:rows].copy_(nv_t.view(-1), non_blocking=True)
         if key not in self.graphs:
+            use_nv = self.fused is not None and not self.model.is_lm
+
             def step():
                 row = cap["row"]
                 idx = cap["idx"].index_select(0, row).view(-1)
                 par = cap["par"].index_select(0, row).view(-1, 3)
                 x = aug(cap["imgs"], idx, par)
                 y = cap["labels"].index_select(0, idx)
-                self._fwd_bwd({"img": x, "label": y}, float(batch))
+                nv = cap["nv"].index_select(0, row) if use_nv else None
+                self._fwd_bwd({"img": x, "label": y}, float(batch), nv)
                 self._opt_step()
                 row.add_(1)
             self._capture(key, step)

@@ -27,8 +27,9 @@ from ..plan.spec import ModelSpec
 
 class FusedResNet:
     def __init__(self, spec: ModelSpec, scale_rate: float, overlap_wgrad: bool = True):
-        assert spec.family == "resnet" and spec.meta["norm"] == "bn" and spec.meta["kind"] == "block"
+        assert FusedResNet.eligible(spec)
         self.spec, self.blocks = spec, spec.meta["blocks"]
+        self.norm = spec.meta["norm"]                       # "bn": batch statistics; "gn" / "in" / "ln": per sample
         self.scale_rate = float(scale_rate)
         self.overlap_wgrad = overlap_wgrad
         self._side = None
@@ -61,14 +62,45 @@ class FusedResNet:
         return dx, dw
 
     @staticmethod
-    def eligible(spec: ModelSpec) -> bool:
-        return spec.family == "resnet" and spec.meta.get("norm") == "bn" and spec.meta.get("kind") == "block"
+    def eligible(spec: ModelSpec, train_only: bool = True) -> bool:
+        """BatchNorm models use the fused path for training, the sBN pass and evaluation; GroupNorm / InstanceNorm /
+        LayerNorm models for the training step (their evaluation has no statistics pass and runs the functional
+        model)."""
+        norms = ("bn", "gn", "in", "ln") if train_only else ("bn",)
+        return spec.family == "resnet" and spec.meta.get("norm") in norms and spec.meta.get("kind") == "block"
+
+    def _nf(self, x, res, P, name, eps, ws_tag, nvalid=None):
+        """fused (residual add +) norm + ReLU forward -> (s, y, saved statistics)"""
+        if self.norm == "bn":
+            s, y, m, i, _ = fo.bn_act_fwd(x, res, P[name + ".weight"], P[name + ".bias"], eps,
+                                          ws=self._scratch(ws_tag, x), nvalid=nvalid)
+        else:
+            s, y, m, i = fo.gn_act_fwd(x, res, P[name + ".weight"], P[name + ".bias"], eps,
+                                       fo.NORM_GROUPS[self.norm](x.shape[1]))
+        return s, y, m, i
+
+    def _nb(self, dy, dy2, dres, s, m, i, P, G, name, ws_tag, nvalid=None, **kw):
+        G[name + ".weight"] = torch.empty_like(P[name + ".weight"])
+        G[name + ".bias"] = torch.empty_like(P[name + ".bias"])
+        if self.norm == "bn":
+            return fo.bn_act_bwd(dy, dy2, dres, s, m, i, P[name + ".weight"], P[name + ".bias"], G[name + ".weight"],
+                                 G[name + ".bias"], ws=self._scratch(ws_tag, s) if ws_tag else None, nvalid=nvalid, **kw)
+        return fo.gn_act_bwd(dy, dy2, dres, s, m, i, P[name + ".weight"], P[name + ".bias"], G[name + ".weight"],
+                             G[name + ".bias"], fo.NORM_GROUPS[self.norm](s.shape[1]), **kw)
 
     # ---------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def train_step(self, P: Dict[str, torch.Tensor], x: torch.Tensor, y: torch.Tensor,
-                   label_mask: Optional[torch.Tensor], meter=None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
-        """One forward+backward.  Returns ``(loss, grads)`` with a gradient tensor for every parameter."""
+                   label_mask: Optional[torch.Tensor], meter=None,
+                   nvalid: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+        """One forward+backward.  Returns ``(loss, grads)`` with a gradient tensor for every parameter.
+
+        ``nvalid`` (int32 ``[1]`` on the device): the batch is padded and only its first ``nvalid`` samples are real
+        (the partial last batch of an epoch running through the SAME captured graph as the full ones).  BatchNorm
+        statistics, the loss mean and the meter use ``nvalid``; the padding rows are zeroed after every norm in the
+        forward and the backward pass, so they contribute exactly nothing to any weight gradient.  Per-sample norms
+        (GroupNorm family) need no masking beyond the head: a zero output gradient stays zero."""
+        nv = nvalid
         s_rate = self.scale_rate
         eps = BN_EPS * s_rate * s_rate          # Scaler folded into epsilon
         G: Dict[str, torch.Tensor] = {}
@@ -78,16 +110,14 @@ class FusedResNet:
         cur, res = c0, None                     # block input is s = cur (+ res)
         for blk in self.blocks:
             pre, stride = blk["prefix"], blk["stride"]
-            s_in, o1, m1, i1, _ = fo.bn_act_fwd(cur, res, P[pre + ".n1.weight"], P[pre + ".n1.bias"], eps,
-                                                ws=self._scratch(pre + ".n1.f", cur))
+            s_in, o1, m1, i1 = self._nf(cur, res, P, pre + ".n1", eps, pre + ".n1.f", nv)
             sc = fo.conv_fwd(o1, P[pre + ".shortcut.weight"], stride, 0) if blk["shortcut"] else s_in
             c1 = fo.conv_fwd(o1, P[pre + ".conv1.weight"], stride, 1)
-            _, o2, m2, i2, _ = fo.bn_act_fwd(c1, None, P[pre + ".n2.weight"], P[pre + ".n2.bias"], eps,
-                                             ws=self._scratch(pre + ".n2.f", c1))
+            _, o2, m2, i2 = self._nf(c1, None, P, pre + ".n2", eps, pre + ".n2.f", nv)
             c2 = fo.conv_fwd(o2, P[pre + ".conv2.weight"], 1, 1)
             saved.append((blk, s_in, o1, m1, i1, c1, o2, m2, i2))
             cur, res = c2, sc
-        s4, y4, m4, i4, _ = fo.bn_act_fwd(cur, res, P["n4.weight"], P["n4.bias"], eps, ws=self._scratch("n4.f", cur))
+        s4, y4, m4, i4 = self._nf(cur, res, P, "n4", eps, "n4.f", nv)
         # ---- head: global average pool -> linear -> masked CE (forward + backward) ----
         N, C, H, W = y4.shape
         Wl, bl = P["linear.weight"], P["linear.bias"]
@@ -96,37 +126,31 @@ class FusedResNet:
             mt, nw = (meter if meter is not None else (None, float(N)))
             mask = label_mask if (label_mask is None or label_mask.dtype == torch.uint8) else label_mask.to(torch.uint8)
             loss, G["linear.weight"], G["linear.bias"], dpooled = cu.C().head_fwd_bwd(
-                y4, Wl, bl, y.contiguous(), mask, float(nw), mt)
+                y4, Wl, bl, y.contiguous(), mask, float(nw), mt, nv)
             loss = loss.view(())
         else:
             pooled = y4.mean(dim=(2, 3))
             logits = F.linear(pooled, Wl, bl)
-            loss, dlogits = self._ce(logits, y, label_mask, meter)
+            nvi = fo._nv(nv, N)
+            loss, dl = self._ce(logits[:nvi], y[:nvi], label_mask, meter)
+            dlogits = torch.zeros_like(logits)
+            dlogits[:nvi] = dl
             G["linear.weight"] = dlogits.t().mm(pooled)
             G["linear.bias"] = dlogits.sum(0)
             dpooled = dlogits.mm(Wl)                                  # [N, C]
         # ---- backward ----
-        G["n4.weight"], G["n4.bias"] = torch.empty_like(P["n4.weight"]), torch.empty_like(P["n4.bias"])
-        ds = fo.bn_act_bwd(dpooled, None, None, s4, m4, i4, P["n4.weight"], P["n4.bias"], G["n4.weight"], G["n4.bias"],
-                           hw=H * W, dy_scale=1.0 / (H * W))
+        ds = self._nb(dpooled, None, None, s4, m4, i4, P, G, "n4", None, nv, hw=H * W, dy_scale=1.0 / (H * W))
         for (blk, s_in, o1, m1, i1, c1, o2, m2, i2) in reversed(saved):
             pre, stride = blk["prefix"], blk["stride"]
             # ds = grad wrt block output (= c2 + sc)
             do2, G[pre + ".conv2.weight"] = self._conv_bwd(ds, o2, P[pre + ".conv2.weight"], 1, 1, keep)
-            G[pre + ".n2.weight"] = torch.empty_like(P[pre + ".n2.weight"])
-            G[pre + ".n2.bias"] = torch.empty_like(P[pre + ".n2.bias"])
-            dc1 = fo.bn_act_bwd(do2, None, None, c1, m2, i2, P[pre + ".n2.weight"], P[pre + ".n2.bias"],
-                                G[pre + ".n2.weight"], G[pre + ".n2.bias"], ws=self._scratch(pre + ".n2.b", c1))
+            dc1 = self._nb(do2, None, None, c1, m2, i2, P, G, pre + ".n2", pre + ".n2.b", nv)
             do1, G[pre + ".conv1.weight"] = self._conv_bwd(dc1, o1, P[pre + ".conv1.weight"], stride, 1, keep)
-            G[pre + ".n1.weight"] = torch.empty_like(P[pre + ".n1.weight"])
-            G[pre + ".n1.bias"] = torch.empty_like(P[pre + ".n1.bias"])
             if blk["shortcut"]:
                 do1b, G[pre + ".shortcut.weight"] = self._conv_bwd(ds, o1, P[pre + ".shortcut.weight"], stride, 0, keep)
-                ds = fo.bn_act_bwd(do1, do1b, None, s_in, m1, i1, P[pre + ".n1.weight"], P[pre + ".n1.bias"],
-                                   G[pre + ".n1.weight"], G[pre + ".n1.bias"], ws=self._scratch(pre + ".n1.b", s_in))
+                ds = self._nb(do1, do1b, None, s_in, m1, i1, P, G, pre + ".n1", pre + ".n1.b", nv)
             else:
-                ds = fo.bn_act_bwd(do1, None, ds, s_in, m1, i1, P[pre + ".n1.weight"], P[pre + ".n1.bias"],
-                                   G[pre + ".n1.weight"], G[pre + ".n1.bias"], ws=self._scratch(pre + ".n1.b", s_in))
+                ds = self._nb(do1, None, ds, s_in, m1, i1, P, G, pre + ".n1", pre + ".n1.b", nv)
         _, G["conv1.weight"] = self._conv_bwd(ds, x, P["conv1.weight"], 1, 1, keep, need_dx=False)
         if self._side is not None and x.is_cuda:
             torch.cuda.current_stream(x.device).wait_stream(self._side)    # join: all weight gradients are complete

@@ -29,18 +29,33 @@ def _rows(x: torch.Tensor) -> torch.Tensor:
     return x.reshape(-1, x.shape[-1])
 
 
+def _nv(nvalid, N: int) -> int:
+    return N if nvalid is None else max(min(int(nvalid), N), 1)
+
+
 def bn_act_fwd(x: torch.Tensor, res: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, eps: float,
-               groups: int = 1, relu: bool = True, ws: Optional[torch.Tensor] = None):
+               groups: int = 1, relu: bool = True, ws: Optional[torch.Tensor] = None, nvalid=None):
     """``s = x (+ res)``; per-group batch statistics; ``y = relu(bn(s))``.
+
+    ``nvalid`` (int32 ``[1]`` device tensor on the kernel path, int / tensor on the oracle path): only the first
+    ``nvalid`` samples of the batch are real -- the partial last batch of an epoch padded to the captured batch size.
+    Statistics ignore the padding samples and ``s`` / ``y`` are zero there.
 
     Returns ``(s, y, mean[G,C], invstd[G,C], var_unbiased[G,C])`` (``s is x`` when ``res`` is None).
     """
     C = x.shape[1]
     if _use_kernels(x):
-        s, y, mean, invstd, varu = cu.C().bn_act_fwd(x, res, gamma, beta, float(eps), int(groups), int(C), bool(relu), ws)
+        s, y, mean, invstd, varu = cu.C().bn_act_fwd(x, res, gamma, beta, float(eps), int(groups), int(C), bool(relu), ws,
+                                                     nvalid, int(x.shape[0]))
         return (s if res is not None else x), y, mean, invstd, varu
     s = x if res is None else (x + res)
     N = s.shape[0]
+    if nvalid is not None and _nv(nvalid, N) < N:
+        assert groups == 1
+        nv = _nv(nvalid, N)
+        sv, yv, mean, invstd, varu = bn_act_fwd(x[:nv], None if res is None else res[:nv], gamma, beta, eps, 1, relu)
+        pad = lambda t: torch.cat([t, torch.zeros((N - nv,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)])
+        return (pad(sv) if res is not None else x), pad(yv), mean, invstd, varu
     sf = _f(s).reshape(groups, N // groups, C, -1)
     var, mean = torch.var_mean(sf, dim=(1, 3), unbiased=False, keepdim=True)
     invstd = torch.rsqrt(var + eps)
@@ -71,7 +86,7 @@ def affine_act(x: torch.Tensor, res: Optional[torch.Tensor], a: torch.Tensor, b:
 def bn_act_bwd(dy: torch.Tensor, dy2: Optional[torch.Tensor], dres: Optional[torch.Tensor], s: torch.Tensor,
                mean: torch.Tensor, invstd: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
                dgamma: torch.Tensor, dbeta: torch.Tensor, hw: int = 0, dy_scale: float = 1.0,
-               relu: bool = True, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+               relu: bool = True, ws: Optional[torch.Tensor] = None, nvalid=None) -> torch.Tensor:
     """Backward of ``y = relu(bn(s))`` for one statistics group.  ``dy`` is the gradient w.r.t. ``y`` (``hw > 0``:
     ``dy`` is ``[N, C]`` and is broadcast over the ``hw`` positions of every sample, scaled by ``dy_scale``);
     ``dy2`` is an optional second gradient w.r.t. ``y``; ``dres`` an optional gradient w.r.t. ``s`` arriving through
@@ -79,7 +94,13 @@ def bn_act_bwd(dy: torch.Tensor, dy2: Optional[torch.Tensor], dres: Optional[tor
     C = s.shape[1]
     if _use_kernels(s):
         return cu.C().bn_act_bwd(dy, dy2, dres, s, mean.reshape(-1), invstd.reshape(-1), gamma, beta, dgamma, dbeta,
-                                 int(C), int(hw), float(dy_scale), bool(relu), ws)
+                                 int(C), int(hw), float(dy_scale), bool(relu), ws, nvalid, int(s.shape[0]))
+    if nvalid is not None and _nv(nvalid, s.shape[0]) < s.shape[0]:
+        nv, N = _nv(nvalid, s.shape[0]), s.shape[0]
+        cut = lambda t: None if t is None else t[:nv]
+        dsv = bn_act_bwd(dy[:nv], cut(dy2), cut(dres), s[:nv], mean, invstd, gamma, beta, dgamma, dbeta, hw, dy_scale,
+                         relu)
+        return torch.cat([dsv, torch.zeros((N - nv,) + tuple(dsv.shape[1:]), dtype=dsv.dtype, device=dsv.device)])
     shape = (1, C) + (1,) * (s.dim() - 2)
     sf = _f(s)
     m, iv = mean.reshape(shape).float(), invstd.reshape(shape).float()
@@ -99,6 +120,68 @@ def bn_act_bwd(dy: torch.Tensor, dy2: Optional[torch.Tensor], dres: Optional[tor
         ds = ds + _f(dres)
     dgamma.copy_(sg.to(dgamma.dtype))
     dbeta.copy_(sb.to(dbeta.dtype))
+    ds = ds.to(s.dtype)
+    if ds.dim() == 4 and ds.is_cuda:
+        ds = ds.contiguous(memory_format=torch.channels_last)
+    return ds
+
+
+NORM_GROUPS = {"gn": lambda C: 4, "in": lambda C: C, "ln": lambda C: 1}        # same table as ops.nn.norm_act
+
+
+def gn_act_fwd(x: torch.Tensor, res: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+               G: int, relu: bool = True):
+    """``s = x (+ res)``; per-(sample, channel-group) statistics; ``y = relu(group_norm(s))`` (``csrc/gn_kernels.cu``).
+
+    Reference: ``nn.GroupNorm`` behind the Scaler, followed by ReLU (``src/models/resnet.py:18-26``).
+    Returns ``(s, y, mean[N,G], rstd[N,G])`` (``s is x`` when ``res`` is None)."""
+    N, C = x.shape[0], x.shape[1]
+    if _use_kernels(x):
+        s, y, mean, rstd = cu.C().gn_act_fwd(x, res, gamma, beta, float(eps), int(N), int(C), int(G), bool(relu))
+        return (s if res is not None else x), y, mean, rstd
+    s = x if res is None else (x + res)
+    sf = _f(s).reshape(N, G, -1)
+    var, mean = torch.var_mean(sf, dim=2, unbiased=False, keepdim=True)
+    rstd = torch.rsqrt(var + eps)
+    shape = (1, C) + (1,) * (s.dim() - 2)
+    y = ((sf - mean) * rstd).reshape(s.shape) * _f(gamma).view(shape) + _f(beta).view(shape)
+    if relu:
+        y = F.relu(y)
+    y = y.to(s.dtype)
+    if s.dim() == 4 and s.is_cuda:
+        y = y.contiguous(memory_format=torch.channels_last)
+    return s, y, mean.reshape(N, G), rstd.reshape(N, G)
+
+
+def gn_act_bwd(dy: torch.Tensor, dy2: Optional[torch.Tensor], dres: Optional[torch.Tensor], s: torch.Tensor,
+               mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+               dgamma: torch.Tensor, dbeta: torch.Tensor, G: int, hw: int = 0, dy_scale: float = 1.0,
+               relu: bool = True) -> torch.Tensor:
+    """Backward of ``y = relu(group_norm(s))``; same gradient-join conventions as :func:`bn_act_bwd`."""
+    N, C = s.shape[0], s.shape[1]
+    if _use_kernels(s):
+        return cu.C().gn_act_bwd(dy, dy2, dres, s, mean.contiguous(), rstd.contiguous(), gamma, beta, dgamma, dbeta,
+                                 int(N), int(C), int(G), int(hw), float(dy_scale), bool(relu))
+    shape = (1, C) + (1,) * (s.dim() - 2)
+    sf = _f(s)
+    xh = ((sf.reshape(N, G, -1) - mean.reshape(N, G, 1).to(sf.dtype)) * rstd.reshape(N, G, 1).to(sf.dtype))
+    xh = xh.reshape(s.shape)
+    ga, be = _f(gamma).view(shape), _f(beta).view(shape)
+    if hw > 0:
+        g = (_f(dy) * dy_scale).view(dy.shape[0], C, *([1] * (s.dim() - 2))).expand_as(sf)
+    else:
+        g = _f(dy) if dy2 is None else _f(dy) + _f(dy2)
+    if relu:
+        g = g * ((xh * ga + be) > 0)
+    red = [d for d in range(s.dim()) if d != 1]
+    dgamma.copy_((g * xh).sum(red).to(dgamma.dtype))
+    dbeta.copy_(g.sum(red).to(dbeta.dtype))
+    dxh = (g * ga).reshape(N, G, -1)
+    xg = xh.reshape(N, G, -1)
+    ds = rstd.reshape(N, G, 1).to(sf.dtype) * (dxh - dxh.mean(2, keepdim=True) - xg * (dxh * xg).mean(2, keepdim=True))
+    ds = ds.reshape(s.shape)
+    if dres is not None:
+        ds = ds + _f(dres)
     ds = ds.to(s.dtype)
     if ds.dim() == 4 and ds.is_cuda:
         ds = ds.contiguous(memory_format=torch.channels_last)

@@ -8,8 +8,8 @@ from hfl_b200.models.fused_resnet import FusedResNet
 from hfl_b200.ops.nn import NormCtx
 
 
-def _setup(rate, scale, dev="cpu", dtype=torch.float32, cl=False, mask=1):
-    cfg = make_cfg("CIFAR10", "resnet18", "1_10_0.5_iid_fix_a1-c1_bn_%d_%d" % (scale, mask), classes_size=10)
+def _setup(rate, scale, dev="cpu", dtype=torch.float32, cl=False, mask=1, norm="bn"):
+    cfg = make_cfg("CIFAR10", "resnet18", "1_10_0.5_iid_fix_a1-c1_%s_%d_%d" % (norm, scale, mask), classes_size=10)
     model = make_model(cfg, rate, channels_last=cl)
     torch.manual_seed(0)
     arena = model.new_arena(dev, dtype)
@@ -39,6 +39,39 @@ def test_fused_train_step_matches_autograd_cpu(rate, scale):
     assert set(G) == set(P)
     for k in P:
         assert torch.allclose(G[k], P[k].grad, atol=1e-8, rtol=1e-6), k
+
+
+@pytest.mark.parametrize("norm,rate", [("gn", 0.25), ("in", 0.0625), ("ln", 0.125), ("gn", 0.0625)])
+def test_fused_groupnorm_family_matches_autograd_cpu(norm, rate):
+    """GroupNorm(4) / InstanceNorm / LayerNorm sub-networks through the same hand-written backward."""
+    cfg, model, arena = _setup(rate, 1, dtype=torch.float64, norm=norm)
+    assert FusedResNet.eligible(model.spec) and not FusedResNet.eligible(model.spec, train_only=False)
+    P = {k: v.detach().requires_grad_() for k, v in model.layout.views(arena).items()}
+    x = torch.randn(4, 3, 32, 32, dtype=torch.float64)
+    y = torch.randint(0, 10, (4,))
+    out = model.forward(P, {"img": x, "label": y}, NormCtx("train"), None)
+    out["loss"].backward()
+    loss, G = FusedResNet(model.spec, model.scale_rate).train_step({k: v.detach() for k, v in P.items()}, x, y, None)
+    assert torch.allclose(loss, out["loss"], atol=1e-9, rtol=1e-9)
+    for k in P:
+        assert torch.allclose(G[k], P[k].grad, atol=1e-8, rtol=1e-6), k
+
+
+@pytest.mark.parametrize("norm", ["bn", "gn"])
+def test_fused_padded_partial_batch_cpu(norm):
+    """A batch padded to the captured size with ``nvalid`` real samples == the step on the real samples alone."""
+    cfg, model, arena = _setup(0.25, 1, dtype=torch.float64, norm=norm)
+    P = dict(model.layout.views(arena))
+    x = torch.randn(6, 3, 32, 32, dtype=torch.float64)
+    y = torch.randint(0, 10, (6,))
+    fused = FusedResNet(model.spec, model.scale_rate)
+    loss_a, Ga = fused.train_step(P, x[:4], y[:4], None)
+    xp = x.clone()
+    xp[4:] = x[:1]                                   # padding slots repeat a real sample (trainer convention)
+    loss_b, Gb = fused.train_step(P, xp, y, None, nvalid=torch.tensor([4], dtype=torch.int32))
+    assert torch.allclose(loss_a, loss_b, atol=1e-10)
+    for k in Ga:
+        assert torch.allclose(Ga[k], Gb[k], atol=1e-9, rtol=1e-7), k
 
 
 def test_fused_stats_and_eval_match_functional_cpu():
@@ -146,3 +179,143 @@ def test_fused_norm_kernels_exact_shapes():
                     assert float((ds.float().cpu() - ds2).abs().max()) < 0.03 * scale + 2e-2, (C, H, hw)
                     assert torch.allclose(dg.float().cpu(), dg2, atol=0.05 * float(dg2.abs().max()) + 1e-2), (C, H, hw)
                     assert torch.allclose(db.float().cpu(), db2, atol=0.05 * float(db2.abs().max()) + 1e-2), (C, H, hw)
+
+
+def _cl(t):
+    return t.bfloat16().contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.gpu
+def test_bn_kernels_partial_batch_nvalid():
+    """Device-side ``nvalid``: kernels on a padded batch == kernels on the real samples alone; padding rows are zero.
+    Shapes cover the cluster path, the register-resident wide slices and the split (2-launch) path."""
+    from hfl_b200.ops import cuda as cu
+    from hfl_b200.ops import fused as fo
+    assert cu.available()
+    dev = torch.device("cuda")
+    torch.manual_seed(3)
+    N = 10
+    for C, H in [(4, 32), (32, 4), (64, 32), (128, 16), (512, 4), (16, 16)]:
+        for nv in (1, 3, 9, 10):
+            nvt = torch.tensor([nv], dtype=torch.int32, device=dev)
+            x = _cl(torch.randn(N, C, H, H, device=dev) * 1.5 + 0.3)
+            r = _cl(torch.randn(N, C, H, H, device=dev))
+            ga = (torch.rand(C, device=dev) + 0.5).bfloat16()
+            be = (torch.randn(C, device=dev) * 0.3).bfloat16()
+            ws = torch.zeros(2 * C + 1, dtype=torch.float32, device=dev)
+            for res in (None, r):
+                s, y, m, iv, _ = fo.bn_act_fwd(x, res, ga, be, 1e-5, 1, ws=ws, nvalid=nvt)
+                s1, y1, m1, iv1, _ = fo.bn_act_fwd(x[:nv].contiguous(memory_format=torch.channels_last),
+                                                   None if res is None else res[:nv].contiguous(
+                                                       memory_format=torch.channels_last), ga, be, 1e-5, 1)
+                assert torch.allclose(m, m1, atol=1e-4, rtol=1e-4), (C, H, nv)
+                assert torch.allclose(iv, iv1, atol=1e-3, rtol=1e-3), (C, H, nv)
+                assert torch.allclose(y[:nv].float(), y1.float(), atol=2e-2, rtol=2e-2), (C, H, nv)
+                assert float(y[nv:].float().abs().sum()) == 0.0
+                if res is not None:
+                    assert torch.equal(s[:nv], s1) and float(s[nv:].float().abs().sum()) == 0.0
+            assert float(ws.abs().sum()) == 0.0                         # self-cleaning scratch protocol intact
+            s, y, m, iv, _ = fo.bn_act_fwd(x, None, ga, be, 1e-5, 1, nvalid=nvt)
+            dy, dr = _cl(torch.randn(N, C, H, H, device=dev)), _cl(torch.randn(N, C, H, H, device=dev))
+            for (d2, dres, hw) in [(None, None, 0), (dr, None, 0), (None, dr, 0), (None, None, H * H)]:
+                dg, db = torch.empty_like(ga), torch.empty_like(be)
+                dg1, db1 = torch.empty_like(ga), torch.empty_like(be)
+                dyy = dy if hw == 0 else torch.randn(N, C, device=dev).bfloat16()
+                cut = lambda t: None if t is None else t[:nv].contiguous(
+                    memory_format=torch.channels_last if t.dim() == 4 else torch.contiguous_format)
+                ds = fo.bn_act_bwd(dyy, d2, dres, x, m, iv, ga, be, dg, db, hw=hw, dy_scale=0.5 if hw else 1.0,
+                                   nvalid=nvt)
+                ds1 = fo.bn_act_bwd(cut(dyy), cut(d2), cut(dres), cut(x), m, iv, ga, be, dg1, db1, hw=hw,
+                                    dy_scale=0.5 if hw else 1.0)
+                sc = float(ds1.float().abs().max()) + 1e-6
+                assert float((ds[:nv].float() - ds1.float()).abs().max()) < 0.02 * sc + 1e-2, (C, H, nv, hw)
+                assert float(ds[nv:].float().abs().sum()) == 0.0
+                assert torch.allclose(dg.float(), dg1.float(), atol=0.02 * float(dg1.float().abs().max()) + 1e-2)
+                assert torch.allclose(db.float(), db1.float(), atol=0.02 * float(db1.float().abs().max()) + 1e-2)
+
+
+@pytest.mark.gpu
+def test_gn_kernels_match_oracle():
+    """gn_act_fwd / gn_act_bwd (csrc/gn_kernels.cu) vs the torch fp32 oracle: GroupNorm(4), InstanceNorm, LayerNorm."""
+    from hfl_b200.ops import cuda as cu
+    from hfl_b200.ops import fused as fo
+    assert cu.available()
+    dev = torch.device("cuda")
+    torch.manual_seed(4)
+    N = 10
+    for C, H in [(4, 32), (8, 16), (32, 4), (64, 32), (128, 16), (512, 4)]:
+        for kind in ("gn", "in", "ln"):
+            G = fo.NORM_GROUPS[kind](C)
+            x, r = _cl(torch.randn(N, C, H, H, device=dev) * 1.5 + 0.3), _cl(torch.randn(N, C, H, H, device=dev))
+            for pdt in (torch.bfloat16, torch.float32):
+                ga = (torch.rand(C, device=dev) + 0.5).to(pdt)
+                be = (torch.randn(C, device=dev) * 0.3).to(pdt)
+                for res in (None, r):
+                    s, y, m, rs = fo.gn_act_fwd(x, res, ga, be, 1e-5, G)
+                    s2, y2, m2, rs2 = fo.gn_act_fwd(x.float().cpu(), None if res is None else res.float().cpu(),
+                                                    ga.float().cpu(), be.float().cpu(), 1e-5, G)
+                    assert torch.allclose(s.float().cpu(), s2.bfloat16().float(), atol=1e-2), (C, H, kind)
+                    assert torch.allclose(m.cpu(), m2, atol=2e-2, rtol=2e-2), (C, H, kind)
+                    assert torch.allclose(rs.cpu(), rs2, atol=2e-2, rtol=2e-2), (C, H, kind)
+                    assert torch.allclose(y.float().cpu(), y2, atol=6e-2, rtol=3e-2), (C, H, kind)
+                s, y, m, rs = fo.gn_act_fwd(x, None, ga, be, 1e-5, G)
+                dy, dr = _cl(torch.randn(N, C, H, H, device=dev)), _cl(torch.randn(N, C, H, H, device=dev))
+                for (d2, dres, hw) in [(None, None, 0), (dr, None, 0), (None, dr, 0), (None, None, H * H)]:
+                    dg, db = torch.empty_like(ga), torch.empty_like(be)
+                    dyy = dy if hw == 0 else torch.randn(N, C, device=dev).bfloat16()
+                    ds = fo.gn_act_bwd(dyy, d2, dres, x, m, rs, ga, be, dg, db, G, hw=hw, dy_scale=0.5 if hw else 1.0)
+                    dg2, db2 = torch.empty(C), torch.empty(C)
+                    c = lambda t: None if t is None else t.float().cpu()
+                    ds2 = fo.gn_act_bwd(c(dyy), c(d2), c(dres), c(x), m.cpu(), rs.cpu(), c(ga), c(be), dg2, db2, G,
+                                        hw=hw, dy_scale=0.5 if hw else 1.0)
+                    sc = float(ds2.abs().max()) + 1e-6
+                    assert float((ds.float().cpu() - ds2).abs().max()) < 0.03 * sc + 2e-2, (C, H, kind, hw)
+                    assert torch.allclose(dg.float().cpu(), dg2, atol=0.05 * float(dg2.abs().max()) + 1e-2), (C, H, kind)
+                    assert torch.allclose(db.float().cpu(), db2, atol=0.05 * float(db2.abs().max()) + 1e-2), (C, H, kind)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("norm,rate", [("gn", 1.0), ("gn", 0.0625), ("in", 0.25), ("ln", 0.5)])
+def test_fused_groupnorm_train_step_gpu_bf16(norm, rate):
+    dev = torch.device("cuda")
+    cfg, model, arena = _setup(rate, 1, dev, torch.float32, cl=True, norm=norm)
+    wc = arena.bfloat16()
+    P32 = {k: v.float().detach().requires_grad_() for k, v in model.layout.views(wc).items()}
+    P16 = dict(model.layout.views(wc))
+    x = _cl(torch.randn(10, 3, 32, 32, device=dev))
+    y = torch.randint(0, 10, (10,), device=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    out = model.forward(P32, {"img": x.float(), "label": y}, NormCtx("train"), None)
+    out["loss"].backward()
+    loss, G = FusedResNet(model.spec, model.scale_rate).train_step(P16, x, y, None)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(out["loss"])) < 0.05 * max(1.0, abs(float(out["loss"])))
+    cat = lambda d: torch.cat([d[k].float().flatten() for k in sorted(P32)])
+    g_fused, g_fp32 = cat(G), cat({k: P32[k].grad for k in P32})
+    c = float(torch.nn.functional.cosine_similarity(g_fused, g_fp32, dim=0))
+    print("%s rate %g: cos(fused, fp32) = %.4f" % (norm, rate, c))
+    assert c > 0.97
+    assert float((g_fused.norm() - g_fp32.norm()).abs()) < 0.2 * float(g_fp32.norm())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("norm", ["bn", "gn"])
+def test_fused_padded_partial_batch_gpu(norm):
+    """Whole fused step, padded batch of 10 with 3 real samples vs the 3-sample step (bf16 kernels both sides)."""
+    dev = torch.device("cuda")
+    cfg, model, arena = _setup(0.5, 1, dev, torch.float32, cl=True, norm=norm)
+    P16 = dict(model.layout.views(arena.bfloat16()))
+    x = _cl(torch.randn(10, 3, 32, 32, device=dev))
+    x[3:] = x[:1]
+    y = torch.randint(0, 10, (10,), device=dev)
+    fused = FusedResNet(model.spec, model.scale_rate, overlap_wgrad=False)
+    m1, m2 = (torch.zeros(4, dtype=torch.float64, device=dev) for _ in range(2))
+    la, Ga = fused.train_step(P16, x[:3].contiguous(memory_format=torch.channels_last), y[:3].contiguous(), None,
+                              (m1, 3.0))
+    lb, Gb = fused.train_step(P16, x, y, None, (m2, 10.0), nvalid=torch.tensor([3], dtype=torch.int32, device=dev))
+    torch.cuda.synchronize()
+    assert abs(float(la) - float(lb)) < 1e-3
+    assert torch.allclose(m1, m2, rtol=1e-4, atol=1e-4)           # meter weighs the padded step by nvalid
+    cat = lambda d: torch.cat([d[k].float().flatten() for k in sorted(d)])
+    c = float(torch.nn.functional.cosine_similarity(cat(Ga), cat(Gb), dim=0))
+    assert c > 0.995, c

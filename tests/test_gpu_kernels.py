@@ -244,6 +244,42 @@ def test_train_slot_graph_matches_eager():
     assert outs[0][1]["Local-Loss"] == pytest.approx(outs[1][1]["Local-Loss"], rel=1e-3)
 
 
+def test_train_slot_partial_batch_in_graph():
+    """bf16 fused path: a shard that is not a multiple of the batch size trains entirely inside the captured graph
+    (device-side ``nvalid``) and lands where the eager loop (real 3-sample last batch) lands."""
+    _cu()
+    from hfl_b200.data.datasets import synth_vision
+    from hfl_b200.data.pipeline import VisionAugment
+    from hfl_b200.fed.trainer import TrainSlot
+    from hfl_b200.models import Model
+    dev = torch.device("cuda")
+    cfg = make_cfg("CIFAR10", "resnet18", "1_10_0.5_iid_fix_a1-d1_bn_1_1", classes_size=10)
+    spec = build_spec(cfg)
+    ds = synth_vision("CIFAR10", "train", 23)
+    img, lab = ds.img.to(dev), ds.target.to(dev)
+    aug = VisionAugment(ds, True, dev, torch.bfloat16)
+    init, outs = None, []
+    for use_graph in (False, True):
+        model = Model(spec, cfg, 0.25, True)
+        slot = TrainSlot(model, cfg, dev, torch.bfloat16, use_graph)
+        assert slot.fused is not None
+        if init is None:
+            init = model.new_arena(dev)
+        slot.load_params(init)
+        slot.begin_client(0.05, torch.ones(10, dtype=torch.uint8))
+        g = torch.Generator().manual_seed(5)
+        with torch.cuda.stream(slot.stream):
+            steps = sum(1 for _ in slot.train_vision(img, lab, aug, 2, 10, g))
+        torch.cuda.synchronize()
+        assert steps == 6
+        outs.append((slot.w.clone(), slot.metrics()))
+    a, b = outs[0][0], outs[1][0]
+    d0 = (a - init).float()
+    assert float(torch.nn.functional.cosine_similarity(d0, (b - init).float(), dim=0)) > 0.98
+    assert outs[0][1]["Local-Loss"] == pytest.approx(outs[1][1]["Local-Loss"], rel=5e-2)
+    assert outs[0][1]["Local-Accuracy"] == pytest.approx(outs[1][1]["Local-Accuracy"], abs=10.0)
+
+
 @pytest.mark.parametrize("data,model,control,sizes", [
     ("CIFAR10", "resnet18", "1_10_0.5_non-iid-2_dynamic_a1-b1-c1-d1-e1_bn_1_1", {"train": 1000, "test": 200}),
     ("MNIST", "conv", "1_10_0.5_iid_fix_a1-e1_bn_1_1", {"train": 1000, "test": 200}),
