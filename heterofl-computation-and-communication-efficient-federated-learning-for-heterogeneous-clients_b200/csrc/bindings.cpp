@@ -26,6 +26,8 @@ void hfl_masked_ce(const void*, int, const long long*, const unsigned char*, int
                    float, float*, double*, cudaStream_t);
 void hfl_augment(const unsigned char*, const long long*, const int*, const float*, const float*, int, int, int, int,
                  int, void*, int, cudaStream_t);
+int hfl_maxpool2_fwd(const void*, void*, int, int, int, int, cudaStream_t);
+int hfl_maxpool2_bwd(const void*, const void*, void*, int, int, int, int, cudaStream_t);
 int hfl_gn_act_fwd(const void*, const void*, const void*, const void*, int, void*, void*, float*, float*, int, int, int,
                    int, float, int, cudaStream_t);
 int hfl_gn_act_bwd(const void*, const void*, const void*, const void*, const float*, const float*, const void*,
@@ -339,6 +341,34 @@ torch::Tensor bn_act_bwd(torch::Tensor dy, c10::optional<torch::Tensor> dy2, c10
   TORCH_CHECK(e == 0, "bn_act_bwd launch failed: ", cudaGetErrorString((cudaError_t)e));
   check_launch();
   return ds;
+}
+
+// ---- 2x2 max pooling (csrc/pool_kernels.cu) ---------------------------------------------------------------
+static void check_nhwc_bf16(const torch::Tensor& t, const char* what) {
+  CHECK_CUDA_T(t);
+  TORCH_CHECK(t.dim() == 4 && t.scalar_type() == torch::kBFloat16 && t.is_contiguous(torch::MemoryFormat::ChannelsLast),
+              what, ": channels-last bf16 [N, C, H, W] expected");
+}
+torch::Tensor maxpool2_fwd(torch::Tensor x) {
+  check_nhwc_bf16(x, "maxpool2_fwd");
+  const int N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3);
+  TORCH_CHECK(H >= 2 && W >= 2);
+  c10::cuda::CUDAGuard guard(x.device());
+  auto y = torch::empty({N, C, H / 2, W / 2}, x.options().memory_format(torch::MemoryFormat::ChannelsLast));
+  int e = hfl_maxpool2_fwd(x.data_ptr(), y.data_ptr(), N, H, W, C, cur_stream());
+  TORCH_CHECK(e == 0, "maxpool2_fwd launch failed: ", e);
+  return y;
+}
+torch::Tensor maxpool2_bwd(torch::Tensor dy, torch::Tensor x) {
+  check_nhwc_bf16(x, "maxpool2_bwd");
+  check_nhwc_bf16(dy, "maxpool2_bwd");
+  const int N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3);
+  TORCH_CHECK(dy.size(0) == N && dy.size(1) == C && dy.size(2) == H / 2 && dy.size(3) == W / 2);
+  c10::cuda::CUDAGuard guard(x.device());
+  auto dx = torch::empty_like(x);
+  int e = hfl_maxpool2_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), N, H, W, C, cur_stream());
+  TORCH_CHECK(e == 0, "maxpool2_bwd launch failed: ", e);
+  return dx;
 }
 
 // ---- fused GroupNorm / InstanceNorm / LayerNorm (csrc/gn_kernels.cu) ---------------------------------------
@@ -891,6 +921,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_act_fwd", &bn_act_fwd);
   m.def("affine_act", &affine_act);
   m.def("bn_act_bwd", &bn_act_bwd);
+  m.def("maxpool2_fwd", &maxpool2_fwd);
+  m.def("maxpool2_bwd", &maxpool2_bwd);
   m.def("gn_act_fwd", &gn_act_fwd);
   m.def("gn_act_bwd", &gn_act_bwd);
   m.def("multi_sgd_clip_step", &multi_sgd_clip_step);

@@ -25,6 +25,7 @@ import torch
 
 from ..data.pipeline import VisionAugment, lm_windows
 from ..models import Model
+from ..models.fused_conv import FusedConvNet
 from ..models.fused_resnet import FusedResNet
 from ..models.fused_transformer import EMB, FusedTransformer
 from ..ops import cuda as cu
@@ -84,6 +85,8 @@ class TrainSlot:
         if self.use_kernels and self.mixed and compute_dtype == torch.bfloat16 and cfg.get("fused", True):
             if FusedResNet.eligible(model.spec):
                 self.fused = FusedResNet(model.spec, model.scale_rate)
+            elif FusedConvNet.eligible(model.spec):
+                self.fused = FusedConvNet(model.spec, model.scale_rate)
             elif model.is_lm and FusedTransformer.eligible(model.spec, model.layout.entries[EMB].shape[1]):
                 self.fused = FusedTransformer(model.spec, model.scale_rate, cfg.get("mask_rate", 0.15),
                                               cfg["transformer"]["dropout"])

@@ -188,6 +188,25 @@ def gn_act_bwd(dy: torch.Tensor, dy2: Optional[torch.Tensor], dres: Optional[tor
     return ds
 
 
+def maxpool2_fwd(x: torch.Tensor) -> torch.Tensor:
+    """``F.max_pool2d(x, 2)`` on NHWC bf16 (``csrc/pool_kernels.cu``); reference ``src/models/conv.py:29-45``."""
+    if _use_kernels(x) and x.is_contiguous(memory_format=torch.channels_last):
+        return cu.C().maxpool2_fwd(x)
+    return F.max_pool2d(x, 2)
+
+
+def maxpool2_bwd(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """Gradient of :func:`maxpool2_fwd` w.r.t. its input; the arg-max is recomputed from ``x`` (first maximum wins)."""
+    if _use_kernels(x) and x.is_contiguous(memory_format=torch.channels_last) \
+            and dy.is_contiguous(memory_format=torch.channels_last):
+        return cu.C().maxpool2_bwd(dy, x)
+    N, C, H, W = x.shape
+    _, idx = F.max_pool2d(_f(x), 2, return_indices=True)
+    dx = torch.zeros(N, C, H * W, dtype=dy.dtype, device=dy.device)
+    dx.scatter_(2, idx.reshape(N, C, -1), dy.reshape(N, C, -1))
+    return dx.reshape(N, C, H, W)
+
+
 # tcgen05 implicit-GEMM forward convolution: "off" | "on" (whenever the shape qualifies) | "auto" = only where it
 # measurably beats the library (profiles/conv_bench.md): the latency-bound training shapes with <= 9 K-blocks
 # (C_in = 64, batch-10 tiles); large-batch and deep-K shapes stay on cuDNN until the kernel is persistent / 2-CTA.

@@ -319,3 +319,83 @@ def test_fused_padded_partial_batch_gpu(norm):
     cat = lambda d: torch.cat([d[k].float().flatten() for k in sorted(d)])
     c = float(torch.nn.functional.cosine_similarity(cat(Ga), cat(Gb), dim=0))
     assert c > 0.995, c
+
+
+def _setup_conv(rate, dev="cpu", dtype=torch.float32, cl=False):
+    cfg = make_cfg("MNIST", "conv", "1_10_0.5_iid_fix_a1-e1_bn_1_1", classes_size=10)
+    model = make_model(cfg, rate, channels_last=cl)
+    torch.manual_seed(0)
+    arena = model.new_arena(dev, dtype)
+    for k, v in model.layout.views(arena).items():
+        if v.dim() == 1:
+            v.add_(torch.randn_like(v) * 0.2)        # non-trivial conv biases and BN affine parameters
+    return cfg, model, arena
+
+
+@pytest.mark.parametrize("rate,nv", [(0.25, None), (0.0625, None), (0.125, 4)])
+def test_fused_convnet_matches_autograd_cpu(rate, nv):
+    """MNIST CNN: manual backward (bias-free conv + BN + ReLU + maxpool chain) == autograd in float64."""
+    from hfl_b200.models.fused_conv import FusedConvNet
+    cfg, model, arena = _setup_conv(rate, dtype=torch.float64)
+    P = {k: v.detach().requires_grad_() for k, v in model.layout.views(arena).items()}
+    x = torch.randn(6, 1, 28, 28, dtype=torch.float64)
+    y = torch.randint(0, 10, (6,))
+    lm = torch.zeros(10, dtype=torch.uint8)
+    lm[[0, 2, 5]] = 1
+    lm[y] = 1
+    n = 6 if nv is None else nv
+    out = model.forward(P, {"img": x[:n], "label": y[:n]}, NormCtx("train"), lm)
+    out["loss"].backward()
+    fused = FusedConvNet(model.spec, model.scale_rate)
+    nvt = None if nv is None else torch.tensor([nv], dtype=torch.int32)
+    loss, G = fused.train_step({k: v.detach() for k, v in P.items()}, x, y, lm, nvalid=nvt)
+    assert torch.allclose(loss, out["loss"], atol=1e-9, rtol=1e-9)
+    assert set(G) == set(P)
+    for k in P:
+        assert torch.allclose(G[k], P[k].grad, atol=1e-8, rtol=1e-6), k
+
+
+@pytest.mark.gpu
+def test_maxpool_kernels_match_torch():
+    from hfl_b200.ops import cuda as cu
+    from hfl_b200.ops import fused as fo
+    assert cu.available()
+    dev = torch.device("cuda")
+    torch.manual_seed(2)
+    for N, C, H, W in [(10, 64, 28, 28), (10, 128, 14, 14), (10, 256, 7, 7), (3, 4, 28, 28), (10, 16, 7, 7), (2, 8, 5, 6)]:
+        x = _cl(torch.randn(N, C, H, W, device=dev).relu())          # ReLU output: plenty of tied zeros
+        xr = x.float().requires_grad_()
+        yr = torch.nn.functional.max_pool2d(xr, 2)
+        y = fo.maxpool2_fwd(x)
+        assert torch.equal(y.float(), yr.detach())
+        dy = _cl(torch.randn_like(yr))
+        yr.backward(dy.float())
+        dx = fo.maxpool2_bwd(dy, x)
+        assert torch.equal(dx.float(), xr.grad), (N, C, H, W)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rate", [1.0, 0.0625])
+def test_fused_convnet_gpu_bf16(rate):
+    from hfl_b200.models.fused_conv import FusedConvNet
+    dev = torch.device("cuda")
+    cfg, model, arena = _setup_conv(rate, dev, torch.float32, cl=True)
+    wc = arena.bfloat16()
+    P32 = {k: v.float().detach().requires_grad_() for k, v in model.layout.views(wc).items()}
+    P16 = dict(model.layout.views(wc))
+    x = _cl(torch.randn(10, 1, 28, 28, device=dev))
+    y = torch.randint(0, 10, (10,), device=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    out = model.forward(P32, {"img": x.float(), "label": y}, NormCtx("train"), None)
+    out["loss"].backward()
+    meter = torch.zeros(4, dtype=torch.float64, device=dev)
+    loss, G = FusedConvNet(model.spec, model.scale_rate).train_step(P16, x, y, None, (meter, 10.0))
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(out["loss"])) < 0.05 * max(1.0, abs(float(out["loss"])))
+    names = [k for k in sorted(P32) if not (k.endswith(".bias") and P32[k].grad.abs().max() < 1e-4)]
+    cat = lambda d: torch.cat([d[k].float().flatten() for k in names])
+    g_fused, g_fp32 = cat(G), cat({k: P32[k].grad for k in P32})
+    c = float(torch.nn.functional.cosine_similarity(g_fused, g_fp32, dim=0))
+    print("conv rate %g: cos(fused, fp32) = %.4f" % (rate, c))
+    assert c > 0.97
+    assert float((g_fused.norm() - g_fp32.norm()).abs()) < 0.2 * float(g_fp32.norm())
