@@ -26,6 +26,10 @@ void hfl_masked_ce(const void*, int, const long long*, const unsigned char*, int
                    float, float*, double*, cudaStream_t);
 void hfl_augment(const unsigned char*, const long long*, const int*, const float*, const float*, int, int, int, int,
                  int, void*, int, cudaStream_t);
+int hfl_mx_sf_bytes(int, int);
+int hfl_mx_quantize(const void*, int, int, int, void*, int, void*, cudaStream_t);
+int hfl_gemm_mxfp8(const void*, int, const void*, const void*, int, const void*, void*, int, int, const float*, float, int,
+                   int, int, cudaStream_t);
 int hfl_maxpool2_fwd(const void*, void*, int, int, int, int, cudaStream_t);
 int hfl_maxpool2_bwd(const void*, const void*, void*, int, int, int, int, cudaStream_t);
 int hfl_gn_act_fwd(const void*, const void*, const void*, const void*, int, void*, void*, float*, float*, int, int, int,
@@ -341,6 +345,46 @@ torch::Tensor bn_act_bwd(torch::Tensor dy, c10::optional<torch::Tensor> dy2, c10
   TORCH_CHECK(e == 0, "bn_act_bwd launch failed: ", cudaGetErrorString((cudaError_t)e));
   check_launch();
   return ds;
+}
+
+// ---- MXFP8 block-scaled GEMM (csrc/gemm_mxfp8_tcgen05.cu) --------------------------------------------------
+// x: bf16 [R, K] (K % 128 == 0, K contiguous) -> [q uint8 [R, K] (e4m3 bit patterns), sf uint8 [tiles * 512] (ue8m0)]
+std::vector<torch::Tensor> mx_quantize(torch::Tensor x) {
+  CHECK_CUDA_T(x);
+  TORCH_CHECK(x.dim() == 2 && x.scalar_type() == torch::kBFloat16 && x.stride(1) == 1, "mx_quantize: bf16 [R, K]");
+  const int64_t R = x.size(0), K = x.size(1);
+  TORCH_CHECK(K % 128 == 0 && x.stride(0) % 8 == 0 && (reinterpret_cast<uintptr_t>(x.data_ptr()) & 15) == 0,
+              "mx_quantize: K % 128 == 0 and 16-byte aligned rows required");
+  c10::cuda::CUDAGuard guard(x.device());
+  auto bopt = torch::TensorOptions().dtype(torch::kUInt8).device(x.device());
+  auto q = torch::empty({R, K}, bopt);
+  auto sf = torch::zeros({(int64_t)hfl_mx_sf_bytes((int)R, (int)K)}, bopt);
+  int e = hfl_mx_quantize(x.data_ptr(), (int)R, (int)K, (int)x.stride(0), q.data_ptr(), (int)K, sf.data_ptr(),
+                          cur_stream());
+  TORCH_CHECK(e == 0, "mx_quantize failed: ", e);
+  return {q, sf};
+}
+
+// C[M, N] = alpha * dequant(aq, sfa) . dequant(bq, sfb)^T (+ bias fp32 [N]); bf16 or fp32 output
+torch::Tensor gemm_mxfp8(torch::Tensor aq, torch::Tensor sfa, torch::Tensor bq, torch::Tensor sfb,
+                         c10::optional<torch::Tensor> bias, double alpha, bool out_fp32) {
+  CHECK_CUDA_T(aq); CHECK_CUDA_T(bq); CHECK_CUDA_T(sfa); CHECK_CUDA_T(sfb);
+  TORCH_CHECK(aq.dim() == 2 && bq.dim() == 2 && aq.size(1) == bq.size(1) && aq.scalar_type() == torch::kUInt8 &&
+              bq.scalar_type() == torch::kUInt8 && aq.is_contiguous() && bq.is_contiguous(), "gemm_mxfp8: operands");
+  const int64_t M = aq.size(0), N = bq.size(0), K = aq.size(1);
+  TORCH_CHECK(K % 128 == 0 && sfa.numel() == hfl_mx_sf_bytes((int)M, (int)K) &&
+              sfb.numel() == hfl_mx_sf_bytes((int)N, (int)K), "gemm_mxfp8: scale-factor buffers do not match");
+  const float* bp = nullptr;
+  if (bias.has_value()) {
+    TORCH_CHECK(bias->scalar_type() == torch::kFloat32 && bias->numel() == N && bias->is_contiguous());
+    bp = bias->data_ptr<float>();
+  }
+  c10::cuda::CUDAGuard guard(aq.device());
+  auto C = torch::empty({M, N}, torch::TensorOptions().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16).device(aq.device()));
+  int e = hfl_gemm_mxfp8(aq.data_ptr(), (int)K, sfa.data_ptr(), bq.data_ptr(), (int)K, sfb.data_ptr(), C.data_ptr(),
+                         (int)N, out_fp32 ? 0 : 1, bp, (float)alpha, (int)M, (int)N, (int)K, cur_stream());
+  TORCH_CHECK(e == 0, "gemm_mxfp8 failed: ", e);
+  return C;
 }
 
 // ---- 2x2 max pooling (csrc/pool_kernels.cu) ---------------------------------------------------------------
@@ -921,6 +965,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_act_fwd", &bn_act_fwd);
   m.def("affine_act", &affine_act);
   m.def("bn_act_bwd", &bn_act_bwd);
+  m.def("mx_quantize", &mx_quantize);
+  m.def("gemm_mxfp8", &gemm_mxfp8);
   m.def("maxpool2_fwd", &maxpool2_fwd);
   m.def("maxpool2_bwd", &maxpool2_bwd);
   m.def("gn_act_fwd", &gn_act_fwd);
