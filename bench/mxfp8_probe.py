@@ -3,6 +3,7 @@ import sys
 
 import torch
 
+sys.path.insert(0, ".")
 from hfl_b200.ops import cuda as cu
 from hfl_b200.ops import mxfp8 as mx
 

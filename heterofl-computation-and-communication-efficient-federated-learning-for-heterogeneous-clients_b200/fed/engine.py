@@ -32,7 +32,7 @@ from ..data.pipeline import VisionAugment
 from ..data.split import split_dataset
 from ..models import Model
 from ..ops import cuda as cu
-from ..parallel.dist import DistInfo, all_reduce_sum, barrier
+from ..parallel.dist import DistInfo, all_reduce_sum, barrier, broadcast
 from ..parallel.schedule import assign_clients, client_cost
 from ..plan.spec import build_spec
 from ..utils.logger import Logger
@@ -341,6 +341,19 @@ class Engine:
     def current_lr(self) -> float:
         return float(self.sched.lr)
 
+    def _sync_sampling(self, user_idx: List[int]) -> List[int]:
+        """Every rank draws the round's clients and rates from its own default generator (reference RNG order); the
+        draws only agree while all ranks consume that generator identically.  Rank 0's draw is authoritative: one
+        small broadcast per round removes the dependence on lock-step RNG state (an eager dropout / [MASK] draw on one
+        rank would otherwise make ranks silently aggregate different client sets)."""
+        fed, info = self.federation, self.info
+        rates = np.asarray(fed.model_rate, dtype=np.float64)
+        buf = torch.cat([torch.tensor(user_idx, dtype=torch.float64), torch.from_numpy(rates)]).to(self.device)
+        buf = broadcast(info, buf, 0).cpu()
+        k = len(user_idx)
+        fed.model_rate = buf[k:].numpy().astype(np.asarray(fed.model_rate).dtype)
+        return [int(u) for u in buf[:k].tolist()]
+
     def run_round(self, epoch: Optional[int] = None, evaluate: Optional[bool] = None) -> Dict:
         """One communication round; returns metrics + phase timings (ms)."""
         if not self._setup_done:
@@ -355,6 +368,8 @@ class Engine:
         # 1. sampling (same RNG order as the reference: randperm, then multinomial inside distribute)
         user_idx = fed.sample_users()
         fed.make_model_rate()
+        if info.world > 1:
+            user_idx = self._sync_sampling(user_idx)
         rates = [float(fed.model_rate[u]) for u in user_idx]
         levels = [self.tables.level_id(r) for r in rates]
         M = len(user_idx)

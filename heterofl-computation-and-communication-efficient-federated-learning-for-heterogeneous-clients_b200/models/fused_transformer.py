@@ -67,6 +67,9 @@ class FusedTransformer:
         self._logits: Dict[int, torch.Tensor] = {}
         import os
         self.grouped = os.environ.get("HFL_LM_GROUPED", "1") != "0"     # grouped q/k/v GEMMs (forward, dW, dX)
+        # opt-in reduced precision: forward GEMMs of the feed-forward blocks in MXFP8 (e4m3 + ue8m0 block scales,
+        # csrc/gemm_mxfp8_tcgen05.cu); backward stays bf16.  Off by default: bench.py's dtype is bf16.
+        self.fp8 = os.environ.get("HFL_LM_FP8", "0") == "1"
         self.keep_last = False                     # numerics tests: keep the forward intermediates of the last step
         self.last: Dict = {}
 
@@ -101,6 +104,16 @@ class FusedTransformer:
             out.copy_(y)
             return out
         return y
+
+    def _lin_ffn(self, x, w, b, alpha):
+        """``_lin`` for the feed-forward GEMMs: MXFP8 operands when enabled and K is a multiple of the 128-element
+        scale-factor tile, bf16 otherwise."""
+        if self.fp8 and x.shape[1] % 128 == 0 and _aligned(x) and _aligned(w) and x.is_contiguous() and w.is_contiguous():
+            from ..ops import mxfp8 as mx
+            aq, sfa = mx.quantize(x)
+            bq, sfb = mx.quantize(w)
+            return mx.mx_gemm(aq, sfa, bq, sfb, b.float() * alpha, alpha, False)
+        return self._lin(x, w, b, alpha)
 
     @staticmethod
     def _dx(dy, w, alpha):
@@ -161,9 +174,9 @@ class FusedTransformer:
             oo = self._lin(o, P[pre + ".mha.linear_o.weight"], P[pre + ".mha.linear_o.bias"], inv)
             x1, xh1, rstd1, dm1 = C.lm_add_ln_fwd(x, oo, P[pre + ".norm1.weight"], P[pre + ".norm1.bias"], LN_EPS, p,
                                                   seed_t, step_t, site)
-            u = self._lin(x1, P[pre + ".linear1.weight"], P[pre + ".linear1.bias"], inv)
+            u = self._lin_ffn(x1, P[pre + ".linear1.weight"], P[pre + ".linear1.bias"], inv)
             hh, dmg = C.lm_gelu_drop_fwd(u, p, seed_t, step_t, site + 1)
-            f = self._lin(hh, P[pre + ".linear2.weight"], P[pre + ".linear2.bias"], inv)
+            f = self._lin_ffn(hh, P[pre + ".linear2.weight"], P[pre + ".linear2.bias"], inv)
             x2, xh2, rstd2, dm2 = C.lm_add_ln_fwd(x1, f, P[pre + ".norm2.weight"], P[pre + ".norm2.bias"], LN_EPS, p,
                                                   seed_t, step_t, site + 2)
             saved.append(dict(x=x, q=q, k=k, v=v, o=o, pr=pr, x1=x1, xh1=xh1, rstd1=rstd1, dm1=dm1, u=u, hh=hh,

@@ -227,6 +227,38 @@ def test_fused_transformer_step_matches_autograd(rate, N):
     assert worst > 0.97
 
 
+def test_fused_transformer_mxfp8_ffn():
+    """``HFL_LM_FP8=1``: the feed-forward GEMMs run on block-scaled e4m3 operands; loss and gradients stay within the
+    format's error budget of the bf16 step."""
+    cu = _cu()
+    from hfl_b200.models import Model
+    from hfl_b200.models.fused_transformer import FusedTransformer
+    from hfl_b200.plan.spec import build_spec
+    dev = torch.device("cuda")
+    V = 1000
+    cfg = make_cfg("WikiText2", "transformer", "1_100_0.1_iid_fix_a5-b5_none_1_1", num_tokens=V, classes_size=V)
+    spec = build_spec(cfg)
+    model = Model(spec, cfg, 1.0, True)
+    torch.manual_seed(3)
+    arena = model.new_arena(dev)
+    Pv = model.layout.views(arena.bfloat16())
+    tokens = torch.randint(0, V, (4, 64), device=dev)
+    outs = []
+    for fp8 in (False, True):
+        ft = FusedTransformer(spec, model.scale_rate, mask_rate=0.0, dropout=0.0)
+        ft.fp8 = fp8
+        seed, step = _rng(dev)
+        n0 = cu.launch_count()
+        loss, G = ft.train_step(Pv, tokens, None, None, seed, step)
+        torch.cuda.synchronize()
+        outs.append((float(loss), torch.cat([G[k].float().reshape(-1) for k in sorted(G)]), cu.launch_count() - n0))
+    assert outs[1][2] > outs[0][2]                                  # the quantise + block-scaled GEMM launches ran
+    assert outs[1][0] == pytest.approx(outs[0][0], rel=2e-2)
+    cos = float(F.cosine_similarity(outs[0][1], outs[1][1], dim=0))
+    print("loss bf16 %.4f fp8 %.4f, gradient cosine %.4f" % (outs[0][0], outs[1][0], cos))
+    assert cos > 0.97
+
+
 def test_fused_lm_slot_trains_in_graph():
     """TrainSlot picks the fused transformer, captures it in a CUDA graph and the loss falls over replays."""
     _cu()
