@@ -3,11 +3,45 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <utility>
 
 namespace hfl {
 
 // Host-side launch accounting (bench.py reports how many of OUR kernels ran inside the timed region).
 void count_launch(int n = 1);
+
+// ---------------------------------------------------------------------------------- programmatic dependent launch
+// A train step is a chain of ~100-200 small dependent kernels (3-10 us each); between two kernel nodes of a stream /
+// captured graph the GPU otherwise drains kernel N completely before it starts fetching, scheduling and running the
+// prologue of kernel N+1 (barrier init, TMEM allocation, tensor-map prefetch).  Every kernel of this library
+//   * is launched through launch_k(), which sets cudaLaunchAttributeProgrammaticStreamSerialization (captured into
+//     CUDA graphs as a programmatic edge), and
+//   * executes pdl_wait() (griddepcontrol.wait: returns once ALL prerequisite grids have completed and their memory is
+//     visible) before its first access to global data, followed by pdl_trigger() (griddepcontrol.launch_dependents) so
+//     the next kernel may become resident and run ITS prologue while this one computes.
+// Transitivity: a grid completes only after every one of its CTAs has exited, and every CTA that reaches its main body
+// has passed pdl_wait(); so when a dependent's wait returns, the whole chain before it has completed.  The instructions
+// are no-ops in a kernel that was launched without the attribute (HFL_PDL=0).
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -86,6 +86,7 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel
 
   if (warp == 0) {
     if (lane == 0) {
@@ -226,7 +227,7 @@ static int launch_conv_v(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, 
     configured = true;
   }
   dim3 grid(tiles_m, g.Kout / BLOCK_N);
-  kern<<<grid, CV_THREADS, smem, stream>>>(tx, tw, (__nv_bfloat16*)Y, (const __nv_bfloat16*)residual, stats, g);
+  launch_k(kern, dim3(grid), dim3(CV_THREADS), smem, stream, tx, tw, (__nv_bfloat16*)Y, (const __nv_bfloat16*)residual, stats, g);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -364,6 +365,7 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __g
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel
   if (num_k > 0) {
     if (warp == 0) {
       if (lane == 0) {
@@ -499,7 +501,7 @@ extern "C" int hfl_conv_wgrad_tc(const void* dY, const void* X, float* dW, int N
   }
   if (splits > 1 && zero_first) cudaMemsetAsync(dW, 0, (size_t)Kout * R * S * C * sizeof(float), stream);
   dim3 grid((Kout + 127) / 128, C / 64, R * S * splits);
-  hfl::conv_wgrad_tcgen05_kernel<<<grid, hfl::CV_THREADS, hfl::WG_SMEM, stream>>>(tdy, tx, dW, g);
+  hfl::launch_k(hfl::conv_wgrad_tcgen05_kernel, dim3(grid), dim3(hfl::CV_THREADS), hfl::WG_SMEM, stream, tdy, tx, dW, g);
   hfl::count_launch();
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? splits : -(int)e;

@@ -10,6 +10,7 @@ __global__ void augment_kernel(const unsigned char* __restrict__ src, const long
                                const int* __restrict__ params, const float* __restrict__ mean,
                                const float* __restrict__ inv_std, int B, int H, int W, int C, int pad,
                                T* __restrict__ out) {
+  pdl_sync();
   const int total = B * H * W * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i % C;
@@ -45,9 +46,9 @@ extern "C" void hfl_augment(const unsigned char* src, const long long* idx, cons
   int blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (out_bf16)
-    augment_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(src, idx, params, mean, inv_std, B, H, W, C, pad,
+    launch_k(augment_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, src, idx, params, mean, inv_std, B, H, W, C, pad,
                                                              (__nv_bfloat16*)out);
   else
-    augment_kernel<float><<<blocks, 256, 0, stream>>>(src, idx, params, mean, inv_std, B, H, W, C, pad, (float*)out);
+    launch_k(augment_kernel<float>, dim3(blocks), dim3(256), 0, stream, src, idx, params, mean, inv_std, B, H, W, C, pad, (float*)out);
   count_launch();
 }

@@ -53,6 +53,7 @@ aggregate_kernel(const TensorDesc* __restrict__ tensors, const LevelDesc* __rest
                  const unsigned long long* __restrict__ client_ptr, const int* __restrict__ client_level,
                  const unsigned char* __restrict__ client_mask, int mask_stride, int M,
                  const unsigned long long* __restrict__ out_ptr, int n_out) {
+  pdl_sync();
   __shared__ ClientSm cs[MAX_CLIENTS_SMEM];
   const int2 bt = block_tab[block_lo + blockIdx.x];
   const TensorDesc d = tensors[bt.x];
@@ -115,6 +116,7 @@ aggregate_v2_kernel(const TensorDesc* __restrict__ tensors, const LevelDesc* __r
                     const unsigned long long* __restrict__ out_ptr, int n_out,
                     const unsigned long long* __restrict__ red_src, int red_n_src, float* __restrict__ red_dst,
                     int red_n) {
+  pdl_sync();
   if (blockIdx.x == 0 && red_n > 0) {
     for (int i = threadIdx.x; i < red_n; i += FED_THREADS) {
       float acc = 0.f;
@@ -205,6 +207,7 @@ distribute_kernel(const TensorDesc* __restrict__ tensors, const LevelDesc* __res
                   const float* __restrict__ global_w,
                   const unsigned long long* __restrict__ w_ptr, const unsigned long long* __restrict__ wc_ptr,
                   const unsigned long long* __restrict__ mom_ptr, const int* __restrict__ client_level) {
+  pdl_sync();
   const int m = blockIdx.y;
   const int lv = client_level[m];
   const int nb = lvl_block_start[lv + 1] - lvl_block_start[lv];
@@ -236,6 +239,7 @@ distribute_kernel(const TensorDesc* __restrict__ tensors, const LevelDesc* __res
 // ---------------------------------------------------------------------------------------------------------
 __global__ void peer_sum_kernel(const unsigned long long* __restrict__ src_ptr, int n_src, float* __restrict__ dst,
                                 int n) {
+  pdl_sync();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float acc = 0.f;
     for (int s = 0; s < n_src; ++s) acc += reinterpret_cast<const float*>(src_ptr[s])[i];
@@ -252,7 +256,7 @@ extern "C" void hfl_aggregate(const void* tensors, const void* levels, int T, co
                               const void* client_mask, int mask_stride, int M, const void* out_ptr, int n_out,
                               cudaStream_t stream) {
   if (n_blocks <= 0 || M <= 0) return;
-  aggregate_kernel<<<n_blocks, FED_THREADS, 0, stream>>>(
+  launch_k(aggregate_kernel, dim3(n_blocks), dim3(FED_THREADS), 0, stream, 
       (const TensorDesc*)tensors, (const LevelDesc*)levels, T, (const int2*)block_tab, block_lo,
       (const unsigned long long*)client_ptr, (const int*)client_level, (const unsigned char*)client_mask,
       mask_stride, M, (const unsigned long long*)out_ptr, n_out);
@@ -265,7 +269,7 @@ extern "C" void hfl_distribute(const void* tensors, const void* levels, int T, c
                                const void* client_level, int M, cudaStream_t stream) {
   if (M <= 0 || max_blocks <= 0) return;
   dim3 grid(max_blocks, M);
-  distribute_kernel<<<grid, FED_THREADS, 0, stream>>>(
+  launch_k(distribute_kernel, dim3(grid), dim3(FED_THREADS), 0, stream, 
       (const TensorDesc*)tensors, (const LevelDesc*)levels, T, (const int2*)lvl_block_tab,
       (const int*)lvl_block_start, global_w, (const unsigned long long*)w_ptr,
       (const unsigned long long*)wc_ptr, (const unsigned long long*)mom_ptr, (const int*)client_level);
@@ -276,7 +280,7 @@ extern "C" void hfl_peer_sum(const void* src_ptr, int n_src, float* dst, int n, 
   if (n <= 0) return;
   int blocks = (n + 255) / 256;
   if (blocks > 1184) blocks = 1184;
-  peer_sum_kernel<<<blocks, 256, 0, stream>>>((const unsigned long long*)src_ptr, n_src, dst, n);
+  launch_k(peer_sum_kernel, dim3(blocks), dim3(256), 0, stream, (const unsigned long long*)src_ptr, n_src, dst, n);
   count_launch();
 }
 
@@ -285,7 +289,7 @@ extern "C" void hfl_aggregate_v2(const void* tensors, const void* levels, int T,
                                  const void* client_mask, int mask_stride, const void* out_ptr, int n_out,
                                  const void* red_src, int red_n_src, float* red_dst, int red_n, cudaStream_t stream) {
   if (n_blocks <= 0) return;
-  aggregate_v2_kernel<<<n_blocks, FED_THREADS, 0, stream>>>(
+  launch_k(aggregate_v2_kernel, dim3(n_blocks), dim3(FED_THREADS), 0, stream, 
       (const TensorDesc*)tensors, (const LevelDesc*)levels, T, vec4, (const int2*)block_tab, block_lo,
       (const unsigned long long*)client_ptr, lvl_start, L, (const unsigned char*)client_mask, mask_stride,
       (const unsigned long long*)out_ptr, n_out, (const unsigned long long*)red_src, red_n_src, red_dst, red_n);

@@ -62,6 +62,7 @@ gemm_grouped_tcgen05_kernel(const __grid_constant__ GroupArgs G, int M, int N, i
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
@@ -150,7 +151,7 @@ static int launch_grouped(const GroupArgs& G, int M, int N, int K, int ldc, cuda
     configured = true;
   }
   dim3 grid((M + GG_BLOCK_M - 1) / GG_BLOCK_M, (N + GG_BLOCK_N - 1) / GG_BLOCK_N, ACCUM ? 1 : G.ngroups);
-  kern<<<grid, GG_THREADS, GG_SMEM, stream>>>(G, M, N, K, ldc);
+  launch_k(kern, dim3(grid), dim3(GG_THREADS), GG_SMEM, stream, G, M, N, K, ldc);
   count_launch();
   return (int)cudaGetLastError();
 }

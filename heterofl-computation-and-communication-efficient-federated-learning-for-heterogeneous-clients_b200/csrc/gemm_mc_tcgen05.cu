@@ -93,6 +93,7 @@ gemm_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   cluster_sync_all();                                    // peer barriers are initialised before anything signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel
 
   if (warp == 0) {
     if (lane == 0) {
@@ -178,7 +179,7 @@ static int launch_mc(const CUtensorMap& ta, const CUtensorMap& tb, void* C, cons
   }
   const int tiles_m = (M + MC_BLOCK_M - 1) / MC_BLOCK_M;
   dim3 grid((tiles_m + 1) / 2 * 2, (N + MC_BLOCK_N - 1) / MC_BLOCK_N);     // x is a multiple of the cluster size
-  kern<<<grid, MC_THREADS, MC_SMEM, stream>>>(ta, tb, (__nv_bfloat16*)C, bias, bias_h, alpha, M, N, K, ldc);
+  launch_k(kern, dim3(grid), dim3(MC_THREADS), MC_SMEM, stream, ta, tb, (__nv_bfloat16*)C, bias, bias_h, alpha, M, N, K, ldc);
   count_launch();
   return (int)cudaGetLastError();
 }

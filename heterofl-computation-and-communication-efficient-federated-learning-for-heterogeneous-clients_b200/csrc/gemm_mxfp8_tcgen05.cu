@@ -40,6 +40,7 @@ constexpr uint32_t MX_TMEM_COLS = 256;                    // 128 accumulator + 4
 // ---------------------------------------------------------------------------------------------------------
 __global__ void mx_quantize_kernel(const __nv_bfloat16* __restrict__ x, int R, int K, int ldx, uint8_t* __restrict__ q,
                                    int ldq, uint8_t* __restrict__ sf, int num_kb) {
+  pdl_sync();
   const int kblocks = K / 32;
   const long total = (long)R * kblocks;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -150,6 +151,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel
 
   if (warp == 0) {
     if (lane == 0) {
@@ -243,7 +245,7 @@ extern "C" int hfl_mx_quantize(const void* x, int R, int K, int ldx, void* q, in
   const long total = (long)R * (K / 32);
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  mx_quantize_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, R, K, ldx, (uint8_t*)q, ldq, (uint8_t*)sf,
+  launch_k(mx_quantize_kernel, dim3((int)blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, R, K, ldx, (uint8_t*)q, ldq, (uint8_t*)sf,
                                                  K / 128);
   count_launch();
   return (int)cudaGetLastError();
@@ -266,7 +268,7 @@ extern "C" int hfl_gemm_mxfp8(const void* Aq, int lda, const void* sfa, const vo
     auto kern = gemm_mxfp8_kernel<OB, BI>;                                                                     \
     ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MX_SMEM);                     \
     if (ce != cudaSuccess) return (int)ce;                                                                     \
-    kern<<<grid, MX_THREADS, MX_SMEM, st>>>(ta, tb, (const uint8_t*)sfa, (const uint8_t*)sfb, C, bias, alpha, M, N, \
+    launch_k(kern, dim3(grid), dim3(MX_THREADS), MX_SMEM, st, ta, tb, (const uint8_t*)sfa, (const uint8_t*)sfb, C, bias, alpha, M, N, \
                                             K, ldc);                                                           \
   } while (0)
   if (out_bf16) { if (bias) MX_LAUNCH(true, true); else MX_LAUNCH(true, false); }

@@ -81,6 +81,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel
   if (threadIdx.x == 0) GEMM_T(1);
 
   if (warp == 0) {
@@ -201,6 +202,7 @@ gemm_tcgen05_general_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel
   if (warp == 0) {
     if (lane == 0) {
       for (int kb = 0; kb < num_k; ++kb) {
@@ -284,7 +286,7 @@ static int launch_gemm_general(const CUtensorMap& ta, const CUtensorMap& tb, voi
     configured = true;
   }
   dim3 grid((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M, (N + 127) / 128, splits);
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, C, alpha, M, N, K, ldc);
+  launch_k(kern, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, C, alpha, M, N, K, ldc);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -338,7 +340,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* C, co
     configured = true;
   }
   dim3 grid((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M, (N + BLOCK_N - 1) / BLOCK_N);
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, C, bias, bias_h, alpha, M, N, K, ldc);
+  launch_k(kern, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, C, bias, bias_h, alpha, M, N, K, ldc);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -27,6 +27,7 @@ gn_act_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
                   const void* __restrict__ gamma, const void* __restrict__ beta, int pb,
                   __nv_bfloat16* __restrict__ s_out, __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
                   float* __restrict__ rstd, int HW, int C, int G, float eps, int relu) {
+  pdl_sync();
   __shared__ float sm[33];
   const int n = blockIdx.x / G, g = blockIdx.x - n * G;
   const int Cg = C / G, cnt = HW * Cg;
@@ -69,6 +70,7 @@ gn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
                   const void* __restrict__ gamma, const void* __restrict__ beta, int pb,
                   __nv_bfloat16* __restrict__ ds, float* __restrict__ part, int HW, int C, int G, int relu, int hw_bcast,
                   float dy_scale) {
+  pdl_sync();
   // part: fp32 [N][2][C] per-sample shares of dgamma / dbeta (summed over samples by gn_param_grad_kernel)
   // hw_bcast > 0: dy is [N, C] and is broadcast over the hw_bcast positions of every sample (gradient of the global
   // average pool), scaled by dy_scale
@@ -136,6 +138,7 @@ gn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
 // dgamma[c] = sum_n part[n][0][c], dbeta[c] = sum_n part[n][1][c]; written in the parameter dtype
 __global__ void gn_param_grad_kernel(const float* __restrict__ part, void* __restrict__ dgamma, void* __restrict__ dbeta,
                                      int N, int C, int pb) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float a = 0.f, b = 0.f;
@@ -160,7 +163,7 @@ extern "C" int hfl_gn_act_fwd(const void* x, const void* res, const void* gamma,
                               void* y, float* mean, float* rstd, int N, int HW, int C, int G, float eps, int relu,
                               cudaStream_t st) {
   if (G < 1 || C % G != 0) return -1;
-  gn_act_fwd_kernel<<<N * G, GN_THREADS, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res, gamma, beta, pb,
+  launch_k(gn_act_fwd_kernel, dim3(N * G), dim3(GN_THREADS), 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)res, gamma, beta, pb,
                                                  (__nv_bfloat16*)s_out, (__nv_bfloat16*)y, mean, rstd, HW, C, G, eps,
                                                  relu);
   count_launch();
@@ -174,12 +177,12 @@ extern "C" int hfl_gn_act_bwd(const void* dy, const void* dy2, const void* dres,
                               float dy_scale, cudaStream_t st) {
   if (G < 1 || C % G != 0) return -1;
   const int smem = 2 * (C / G) * (int)sizeof(float);
-  gn_act_bwd_kernel<<<N * G, GN_THREADS, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2,
+  launch_k(gn_act_bwd_kernel, dim3(N * G), dim3(GN_THREADS), smem, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2,
                                                     (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean, rstd,
                                                     gamma, beta, pb, (__nv_bfloat16*)ds, part, HW, C, G, relu, hw_bcast,
                                                     dy_scale);
   count_launch();
-  gn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, dgamma, dbeta, N, C, pb);
+  launch_k(gn_param_grad_kernel, dim3((C + 127) / 128), dim3(128), 0, st, part, dgamma, dbeta, N, C, pb);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -56,6 +56,7 @@ lm_embed_fwd_kernel(const long long* __restrict__ tok, const bf16* __restrict__ 
                     float eps, float p_mask, float p_drop, const long long* seed_p, const long long* step_p, uint32_t site,
                     bf16* __restrict__ out, int* __restrict__ src, bf16* __restrict__ xhat, float* __restrict__ rstd,
                     uint8_t* __restrict__ dmask) {
+  pdl_sync();
   const int m = blockIdx.x * LN_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (m >= M) return;
   const uint32_t k_mask = rng_key(seed_p, step_p, site), k_drop = rng_key(seed_p, step_p, site + 1);
@@ -110,6 +111,7 @@ lm_embed_bwd_kernel(DyParts dy, const uint8_t* __restrict__ dmask, float p_drop,
                     const float* __restrict__ rstd, const bf16* __restrict__ gamma, const int* __restrict__ src, int M,
                     int S, int E, float* __restrict__ demb, float* __restrict__ dpos, float* __restrict__ dgamma,
                     float* __restrict__ dbeta) {
+  pdl_sync();
   __shared__ float sm_g[LN_WARPS][LN_MAX_PL * 32];
   __shared__ float sm_b[LN_WARPS][LN_MAX_PL * 32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -166,6 +168,7 @@ lm_add_ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ h, con
                      const bf16* __restrict__ beta, int M, int E, float eps, float p_drop, const long long* seed_p,
                      const long long* step_p, uint32_t site, bf16* __restrict__ y, bf16* __restrict__ xhat,
                      float* __restrict__ rstd, uint8_t* __restrict__ dmask) {
+  pdl_sync();
   const int m = blockIdx.x * LN_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (m >= M) return;
   const uint32_t k_drop = p_drop > 0.f ? rng_key(seed_p, step_p, site) : 0u;
@@ -216,6 +219,7 @@ lm_add_ln_bwd_kernel(DyParts dy, const bf16* __restrict__ xhat, const float* __r
                      const bf16* __restrict__ gamma, const uint8_t* __restrict__ dmask, float p_drop, int M, int E,
                      bf16* __restrict__ dz, bf16* __restrict__ dh, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ dbias, float bias_alpha) {
+  pdl_sync();
   __shared__ float sm_g[LN_WARPS][LN_MAX_PL * 32];
   __shared__ float sm_b[LN_WARPS][LN_MAX_PL * 32];
   __shared__ float sm_h[LN_WARPS][LN_MAX_PL * 32];
@@ -273,6 +277,7 @@ lm_add_ln_bwd_kernel(DyParts dy, const bf16* __restrict__ xhat, const float* __r
 __global__ void lm_gelu_drop_fwd_kernel(const bf16* __restrict__ u, long n, float p_drop, const long long* seed_p,
                                         const long long* step_p, uint32_t site, bf16* __restrict__ h,
                                         uint8_t* __restrict__ dmask) {
+  pdl_sync();
   const uint32_t k_drop = p_drop > 0.f ? rng_key(seed_p, step_p, site) : 0u;
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -291,6 +296,7 @@ constexpr int GB_ROWS = 32;   // rows per CTA in the column-reducing elementwise
 __global__ void __launch_bounds__(128)
 lm_gelu_drop_bwd_kernel(const bf16* __restrict__ dh, const bf16* __restrict__ u, const uint8_t* __restrict__ dmask,
                         float p_drop, int M, int F, bf16* __restrict__ du, float* __restrict__ dbias, float bias_alpha) {
+  pdl_sync();
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= F) return;
   const int r0 = blockIdx.y * GB_ROWS, r1 = min(M, r0 + GB_ROWS);
@@ -310,6 +316,7 @@ lm_gelu_drop_bwd_kernel(const bf16* __restrict__ dh, const bf16* __restrict__ u,
 // out[c] += alpha * sum_r x[r, c]
 __global__ void __launch_bounds__(128)
 lm_colsum_kernel(const bf16* __restrict__ x, int M, int N, int ld, float alpha, float* __restrict__ out) {
+  pdl_sync();
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= N) return;
   const int r0 = blockIdx.y * GB_ROWS, r1 = min(M, r0 + GB_ROWS);
@@ -342,6 +349,7 @@ __device__ __forceinline__ float half_warp_max(float v) {
 __global__ void __launch_bounds__(256)
 lm_attn_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, int S, int H,
                    int dh, float scale, bf16* __restrict__ o, bf16* __restrict__ P) {
+  pdl_sync();
   __shared__ float sK[AT_S][AT_DH + 1];
   __shared__ float sV[AT_S][AT_DH + 1];
   __shared__ float sQ[AT_BLK][AT_DH + 1];
@@ -407,6 +415,7 @@ lm_attn_bwd_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ q, cons
                    int dh, float scale, bf16* __restrict__ dq, bf16* __restrict__ dk, bf16* __restrict__ dv,
                    float* __restrict__ dbq, float* __restrict__ dbk, float* __restrict__ dbv, float alpha_v,
                    int scale_dv /* 1: dv is written pre-multiplied by alpha_v (grouped q/k/v backward GEMMs) */) {
+  pdl_sync();
   __shared__ float sA[AT_S][AT_DH + 1];          // role Q: K      role K: Q
   __shared__ float sB[AT_S][AT_DH + 1];          // role Q: V      role K: dO
   __shared__ float sC[AT_BLK][AT_DH + 1];        // role Q: dO_i   role K: V_j
@@ -523,7 +532,7 @@ extern "C" void hfl_lm_embed_fwd(const long long* tok, const void* emb, const vo
                                  const void* beta, int M, int S, int E, int mask_id, float eps, float p_mask,
                                  float p_drop, const long long* seed_p, const long long* step_p, unsigned site, void* out,
                                  int* src, void* xhat, float* rstd, unsigned char* dmask, cudaStream_t st) {
-  lm_embed_fwd_kernel<<<(M + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, st>>>(
+  launch_k(lm_embed_fwd_kernel, dim3((M + LN_WARPS - 1) / LN_WARPS), dim3(LN_WARPS * 32), 0, st, 
       tok, (const bf16*)emb, (const bf16*)pos, (const bf16*)gamma, (const bf16*)beta, M, S, E, mask_id, eps, p_mask,
       p_drop, seed_p, step_p, site, (bf16*)out, src, (bf16*)xhat, rstd, dmask);
   count_launch();
@@ -539,7 +548,7 @@ static DyParts make_parts(const void* const* dy, int n) {
 extern "C" void hfl_lm_embed_bwd(const void* const* dy, int n_dy, const unsigned char* dmask, float p_drop,
                                  const void* xhat, const float* rstd, const void* gamma, const int* src, int M, int S,
                                  int E, float* demb, float* dpos, float* dgamma, float* dbeta, cudaStream_t st) {
-  lm_embed_bwd_kernel<<<(M + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, st>>>(
+  launch_k(lm_embed_bwd_kernel, dim3((M + LN_WARPS - 1) / LN_WARPS), dim3(LN_WARPS * 32), 0, st, 
       make_parts(dy, n_dy), dmask, p_drop, (const bf16*)xhat, rstd, (const bf16*)gamma, src, M, S, E, demb, dpos, dgamma,
       dbeta);
   count_launch();
@@ -549,7 +558,7 @@ extern "C" void hfl_lm_add_ln_fwd(const void* x, const void* h, const void* gamm
                                   float eps, float p_drop, const long long* seed_p, const long long* step_p,
                                   unsigned site, void* y, void* xhat, float* rstd, unsigned char* dmask,
                                   cudaStream_t st) {
-  lm_add_ln_fwd_kernel<<<(M + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, st>>>(
+  launch_k(lm_add_ln_fwd_kernel, dim3((M + LN_WARPS - 1) / LN_WARPS), dim3(LN_WARPS * 32), 0, st, 
       (const bf16*)x, (const bf16*)h, (const bf16*)gamma, (const bf16*)beta, M, E, eps, p_drop, seed_p, step_p, site,
       (bf16*)y, (bf16*)xhat, rstd, dmask);
   count_launch();
@@ -559,7 +568,7 @@ extern "C" void hfl_lm_add_ln_bwd(const void* const* dy, int n_dy, const void* x
                                   const void* gamma, const unsigned char* dmask, float p_drop, int M, int E, void* dz,
                                   void* dh, float* dgamma, float* dbeta, float* dbias, float bias_alpha,
                                   cudaStream_t st) {
-  lm_add_ln_bwd_kernel<<<(M + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, st>>>(
+  launch_k(lm_add_ln_bwd_kernel, dim3((M + LN_WARPS - 1) / LN_WARPS), dim3(LN_WARPS * 32), 0, st, 
       make_parts(dy, n_dy), (const bf16*)xhat, rstd, (const bf16*)gamma, dmask, p_drop, M, E, (bf16*)dz, (bf16*)dh,
       dgamma, dbeta, dbias, bias_alpha);
   count_launch();
@@ -569,27 +578,27 @@ extern "C" void hfl_lm_gelu_drop_fwd(const void* u, long n, float p_drop, const 
                                      const long long* step_p, unsigned site, void* h, unsigned char* dmask,
                                      cudaStream_t st) {
   const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
-  lm_gelu_drop_fwd_kernel<<<blocks, 256, 0, st>>>((const bf16*)u, n, p_drop, seed_p, step_p, site, (bf16*)h, dmask);
+  launch_k(lm_gelu_drop_fwd_kernel, dim3(blocks), dim3(256), 0, st, (const bf16*)u, n, p_drop, seed_p, step_p, site, (bf16*)h, dmask);
   count_launch();
 }
 
 extern "C" void hfl_lm_gelu_drop_bwd(const void* dh, const void* u, const unsigned char* dmask, float p_drop, int M,
                                      int F, void* du, float* dbias, float bias_alpha, cudaStream_t st) {
   dim3 grid((F + 127) / 128, (M + GB_ROWS - 1) / GB_ROWS);
-  lm_gelu_drop_bwd_kernel<<<grid, 128, 0, st>>>((const bf16*)dh, (const bf16*)u, dmask, p_drop, M, F, (bf16*)du, dbias,
+  launch_k(lm_gelu_drop_bwd_kernel, dim3(grid), dim3(128), 0, st, (const bf16*)dh, (const bf16*)u, dmask, p_drop, M, F, (bf16*)du, dbias,
                                                 bias_alpha);
   count_launch();
 }
 
 extern "C" void hfl_lm_colsum(const void* x, int M, int N, int ld, float alpha, float* out, cudaStream_t st) {
   dim3 grid((N + 127) / 128, (M + GB_ROWS - 1) / GB_ROWS);
-  lm_colsum_kernel<<<grid, 128, 0, st>>>((const bf16*)x, M, N, ld, alpha, out);
+  launch_k(lm_colsum_kernel, dim3(grid), dim3(128), 0, st, (const bf16*)x, M, N, ld, alpha, out);
   count_launch();
 }
 
 extern "C" void hfl_lm_attn_fwd(const void* q, const void* k, const void* v, int N, int S, int H, int dh, float scale,
                                 void* o, void* P, cudaStream_t st) {
-  lm_attn_fwd_kernel<<<dim3(N * H, 4), 256, 0, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, S, H, dh, scale,
+  launch_k(lm_attn_fwd_kernel, dim3(dim3(N * H, 4)), dim3(256), 0, st, (const bf16*)q, (const bf16*)k, (const bf16*)v, S, H, dh, scale,
                                                      (bf16*)o, (bf16*)P);
   count_launch();
 }
@@ -597,7 +606,7 @@ extern "C" void hfl_lm_attn_fwd(const void* q, const void* k, const void* v, int
 extern "C" int hfl_lm_attn_bwd(const void* dO, const void* q, const void* k, const void* v, const void* O, const void* P,
                                int N, int S, int H, int dh, float scale, void* dq, void* dk, void* dv, float* dbq,
                                float* dbk, float* dbv, float alpha_v, int scale_dv, cudaStream_t st) {
-  lm_attn_bwd_kernel<<<dim3(N * H, 8), 256, 0, st>>>((const bf16*)dO, (const bf16*)q, (const bf16*)k, (const bf16*)v,
+  launch_k(lm_attn_bwd_kernel, dim3(dim3(N * H, 8)), dim3(256), 0, st, (const bf16*)dO, (const bf16*)q, (const bf16*)k, (const bf16*)v,
                                                      (const bf16*)O, (const bf16*)P, S, H, dh, scale, (bf16*)dq,
                                                      (bf16*)dk, (bf16*)dv, dbq, dbk, dbv, alpha_v, scale_dv);
   count_launch();

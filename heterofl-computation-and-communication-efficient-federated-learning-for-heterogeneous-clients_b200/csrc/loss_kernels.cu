@@ -21,6 +21,7 @@ __global__ void ce_rows_kernel(const T* __restrict__ logits, const long long* __
                                const unsigned char* __restrict__ mask, int rows, int V, int ld,
                                T* __restrict__ dlogits, float* __restrict__ row_loss,
                                float* __restrict__ row_correct) {
+  pdl_sync();
   __shared__ float sm[33];
   __shared__ int s_arg;
   const int r = blockIdx.x;
@@ -65,6 +66,7 @@ __global__ void ce_rows_kernel(const T* __restrict__ logits, const long long* __
 
 __global__ void ce_finalize_kernel(const float* __restrict__ row_loss, const float* __restrict__ row_correct, int rows,
                                    float n_weight, float* __restrict__ loss_out, double* __restrict__ meter) {
+  pdl_sync();
   __shared__ float sm[33];
   float a = 0.f, c = 0.f;
   for (int i = threadIdx.x; i < rows; i += blockDim.x) { a += row_loss[i]; c += row_correct[i]; }
@@ -91,12 +93,12 @@ extern "C" void hfl_masked_ce(const void* logits, int is_bf16, const long long* 
                               float* loss_out, double* meter, cudaStream_t stream) {
   const int threads = V <= 64 ? 32 : (V <= 1024 ? 128 : 512);
   if (is_bf16)
-    ce_rows_kernel<__nv_bfloat16><<<rows, threads, 0, stream>>>((const __nv_bfloat16*)logits, target, mask, rows, V, ld,
+    launch_k(ce_rows_kernel<__nv_bfloat16>, dim3(rows), dim3(threads), 0, stream, (const __nv_bfloat16*)logits, target, mask, rows, V, ld,
                                                                 (__nv_bfloat16*)dlogits, row_loss, row_correct);
   else
-    ce_rows_kernel<float><<<rows, threads, 0, stream>>>((const float*)logits, target, mask, rows, V, ld,
+    launch_k(ce_rows_kernel<float>, dim3(rows), dim3(threads), 0, stream, (const float*)logits, target, mask, rows, V, ld,
                                                         (float*)dlogits, row_loss, row_correct);
-  ce_finalize_kernel<<<1, 256, 0, stream>>>(row_loss, row_correct, rows, n_weight, loss_out, meter);
+  launch_k(ce_finalize_kernel, dim3(1), dim3(256), 0, stream, row_loss, row_correct, rows, n_weight, loss_out, meter);
   count_launch(2);
 }
 
@@ -110,6 +112,7 @@ namespace hfl {
 
 // pass 1: global average pool, one thread per (n, c); 20 small CTAs instead of one long loop
 __global__ void head_pool_kernel(const __nv_bfloat16* __restrict__ y, int N, int HW, int C, float* __restrict__ pooled) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   const int n = i / C, c = i - n * C;
@@ -127,6 +130,7 @@ head_fwd_bwd_kernel(const float* __restrict__ pooled_g, int N, int C, const PT* 
                     const unsigned char* __restrict__ mask, float n_weight, float* __restrict__ loss_out,
                     double* __restrict__ meter, PT* __restrict__ dW, PT* __restrict__ db,
                     __nv_bfloat16* __restrict__ dpooled, const int* __restrict__ nvalid) {
+  pdl_sync();
   // nvalid != nullptr: only the first *nvalid rows are real samples (partial batch inside a captured step); the loss
   // is their mean, the padding rows get zero gradient and the meter weighs the step by *nvalid.
   extern __shared__ float sm[];
@@ -222,21 +226,21 @@ extern "C" int hfl_head_fwd_bwd(const void* y, int N, int HW, int C, const void*
                                 const int* nvalid, cudaStream_t stream) {
   const int smem = hfl_head_smem_bytes(N, C, Kc);
   if (smem > 200 * 1024) return -1;
-  hfl::head_pool_kernel<<<(N * C + 255) / 256, 256, 0, stream>>>((const __nv_bfloat16*)y, N, HW, C, pooled_ws);
+  hfl::launch_k(hfl::head_pool_kernel, dim3((N * C + 255) / 256), dim3(256), 0, stream, (const __nv_bfloat16*)y, N, HW, C, pooled_ws);
   const int grid = C >= 128 ? C / 64 : 1;
   cudaError_t e = cudaSuccess;
   if (param_bf16) {
     auto kern = hfl::head_fwd_bwd_kernel<__nv_bfloat16>;
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<grid, 512, smem, stream>>>(pooled_ws, N, C, (const __nv_bfloat16*)W, (const __nv_bfloat16*)bias, Kc, target,
+    launch_k(kern, dim3(grid), dim3(512), smem, stream, pooled_ws, N, C, (const __nv_bfloat16*)W, (const __nv_bfloat16*)bias, Kc, target,
                                      mask, n_weight, loss_out, meter, (__nv_bfloat16*)dW, (__nv_bfloat16*)db,
                                      (__nv_bfloat16*)dpooled, nvalid);
   } else {
     auto kern = hfl::head_fwd_bwd_kernel<float>;
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<grid, 512, smem, stream>>>(pooled_ws, N, C, (const float*)W, (const float*)bias, Kc, target, mask, n_weight,
+    launch_k(kern, dim3(grid), dim3(512), smem, stream, pooled_ws, N, C, (const float*)W, (const float*)bias, Kc, target, mask, n_weight,
                                      loss_out, meter, (float*)dW, (float*)db, (__nv_bfloat16*)dpooled, nvalid);
   }
   hfl::count_launch(2);

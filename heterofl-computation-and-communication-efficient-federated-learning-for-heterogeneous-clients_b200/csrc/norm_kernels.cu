@@ -115,6 +115,7 @@ bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
                   const PT* __restrict__ beta, float eps, int Mg, int C, int relu, float* __restrict__ mean_out,
                   float* __restrict__ invstd_out, float* __restrict__ varu_out, const int* __restrict__ nvalid,
                   int rps) {
+  pdl_sync();
   // nvalid != nullptr (training step with a partial last batch inside a captured graph): only the first
   // *nvalid samples (rps rows each) are real; the statistics ignore the padding rows and s / y are written as zeros
   // there, so the padding never reaches a weight gradient.
@@ -249,6 +250,7 @@ bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
 __global__ void affine_act_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                                   __nv_bfloat16* __restrict__ s_out, __nv_bfloat16* __restrict__ y,
                                   const float* __restrict__ a, const float* __restrict__ b, long nvec, int C, int relu) {
+  pdl_sync();
   const uint4* xv = reinterpret_cast<const uint4*>(x);
   const uint4* rv = reinterpret_cast<const uint4*>(res);
   for (long v = blockIdx.x * (long)blockDim.x + threadIdx.x; v < nvec; v += (long)gridDim.x * blockDim.x) {
@@ -286,6 +288,7 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
                   const PT* __restrict__ beta, int M, int C, int hw, float dy_scale, int relu,
                   __nv_bfloat16* __restrict__ ds, PT* __restrict__ dgamma, PT* __restrict__ dbeta,
                   const int* __restrict__ nvalid, int rps) {
+  pdl_sync();
   extern __shared__ float smem[];
   float *sa = smem, *sb = smem + C, *ta = smem + 2 * C, *tb = smem + 3 * C, *c_m = smem + 4 * C, *c_i = smem + 5 * C;
   cg::cluster_group cluster = cg::this_cluster();
@@ -458,6 +461,7 @@ __global__ void __launch_bounds__(NT)
 bn_stats_wide_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                      __nv_bfloat16* __restrict__ s_out, int nvec, int C, float* __restrict__ ws,
                      const int* __restrict__ nvalid, int rps) {
+  pdl_sync();
   // blockIdx.y = statistics group (ghost batch); nvec = vectors per group; ws = [G][2][C]
   const int vv = nvalid ? min(*nvalid * rps * C / 8, nvec) : nvec;
   extern __shared__ float smem[];
@@ -516,6 +520,7 @@ bn_apply_wide_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restr
                      const PT* __restrict__ beta, float eps, int M, int C, int relu, float* __restrict__ ws,
                      float* __restrict__ mean_out, float* __restrict__ invstd_out, float* __restrict__ varu_out,
                      int self_clean, const int* __restrict__ nvalid, int rps) {
+  pdl_sync();
   extern __shared__ float smem[];
   float *sc_a = smem, *sc_b = smem + C;
   const int Mv = nvalid ? max(min(*nvalid * rps, M), 1) : M;
@@ -574,6 +579,7 @@ bn_bwd_reduce_wide_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
                           const float* __restrict__ invstd, const PT* __restrict__ gamma, const PT* __restrict__ beta,
                           int nvec_all, int C, int relu, float* __restrict__ ws, const int* __restrict__ nvalid,
                           int rps) {
+  pdl_sync();
   extern __shared__ float smem[];
   float *sa = smem, *sb = smem + C;
   const int nvec = nvalid ? min(*nvalid * rps * C / 8, nvec_all) : nvec_all;   // padding rows carry no gradient
@@ -625,6 +631,7 @@ bn_bwd_apply_wide_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat
                          const PT* __restrict__ gamma, const PT* __restrict__ beta, int M, int C, int relu,
                          float* __restrict__ ws, __nv_bfloat16* __restrict__ ds, PT* __restrict__ dgamma,
                          PT* __restrict__ dbeta, int self_clean, const int* __restrict__ nvalid, int rps) {
+  pdl_sync();
   float pm[8], pi[8], pg[8], pb[8], qa[8], qb[8];
   const int Mv = nvalid ? max(min(*nvalid * rps, M), 1) : M;
   const float inv_n = 1.f / (float)Mv;
@@ -721,13 +728,15 @@ static cudaError_t launch_cluster(Kern kern, dim3 grid, int cluster_x, size_t sm
   cfg.blockDim = dim3(NT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster_x;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
@@ -761,15 +770,15 @@ extern "C" int hfl_bn_act_fwd(const void* x, const void* res, void* s_out, void*
     dim3 grid(gx, groups);
     const int self_clean = (ws_persistent && groups == 1) ? 1 : 0;
     if (!self_clean) cudaMemsetAsync(ws, 0, 2 * (size_t)C * groups * sizeof(float), stream);
-    bn_stats_wide_kernel<<<grid, NT, wide_smem(C), stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res,
+    launch_k(bn_stats_wide_kernel, dim3(grid), dim3(NT), wide_smem(C), stream, (const __nv_bfloat16*)x, (const __nv_bfloat16*)res,
                                                              (__nv_bfloat16*)s_out, nvec, C, ws, nvalid, rps);
     const void* sin = res ? s_out : x;
     if (param_bf16)
-      bn_apply_wide_kernel<__nv_bfloat16><<<grid, NT, 2 * C * sizeof(float), stream>>>(
+      launch_k(bn_apply_wide_kernel<__nv_bfloat16>, dim3(grid), dim3(NT), 2 * C * sizeof(float), stream, 
           (const __nv_bfloat16*)sin, (__nv_bfloat16*)y, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, eps, Mg, C,
           relu, ws, mean_out, invstd_out, varu_out, self_clean, nvalid, rps);
     else
-      bn_apply_wide_kernel<float><<<grid, NT, 2 * C * sizeof(float), stream>>>(
+      launch_k(bn_apply_wide_kernel<float>, dim3(grid), dim3(NT), 2 * C * sizeof(float), stream, 
           (const __nv_bfloat16*)sin, (__nv_bfloat16*)y, (const float*)gamma, (const float*)beta, eps, Mg, C, relu, ws,
           mean_out, invstd_out, varu_out, self_clean, nvalid, rps);
     count_launch(2);
@@ -801,7 +810,7 @@ extern "C" void hfl_affine_act(const void* x, const void* res, void* s_out, void
   long blocks = (nvec + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  affine_act_kernel<<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res,
+  launch_k(affine_act_kernel, dim3((int)blocks), dim3(256), 0, stream, (const __nv_bfloat16*)x, (const __nv_bfloat16*)res,
                                                      (__nv_bfloat16*)s_out, (__nv_bfloat16*)y, a, b, nvec, C, relu);
   count_launch();
 }
@@ -816,18 +825,18 @@ extern "C" int hfl_bn_act_bwd(const void* dy, const void* dy2, const void* dres,
     const int self_clean = ws_persistent ? 1 : 0;
     if (!self_clean) cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(float), stream);
     if (param_bf16) {
-      bn_bwd_reduce_wide_kernel<__nv_bfloat16><<<grid, NT, wide_smem(C), stream>>>(
+      launch_k(bn_bwd_reduce_wide_kernel<__nv_bfloat16>, dim3(grid), dim3(NT), wide_smem(C), stream, 
           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)s, mean, invstd,
           (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, nvec, C, relu, ws, nvalid, rps);
-      bn_bwd_apply_wide_kernel<__nv_bfloat16><<<grid, NT, 0, stream>>>(
+      launch_k(bn_bwd_apply_wide_kernel<__nv_bfloat16>, dim3(grid), dim3(NT), 0, stream, 
           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean,
           invstd, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, M, C, relu, ws, (__nv_bfloat16*)ds,
           (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, self_clean, nvalid, rps);
     } else {
-      bn_bwd_reduce_wide_kernel<float><<<grid, NT, wide_smem(C), stream>>>(
+      launch_k(bn_bwd_reduce_wide_kernel<float>, dim3(grid), dim3(NT), wide_smem(C), stream, 
           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)s, mean, invstd, (const float*)gamma,
           (const float*)beta, nvec, C, relu, ws, nvalid, rps);
-      bn_bwd_apply_wide_kernel<float><<<grid, NT, 0, stream>>>(
+      launch_k(bn_bwd_apply_wide_kernel<float>, dim3(grid), dim3(NT), 0, stream, 
           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)dres, (const __nv_bfloat16*)s, mean,
           invstd, (const float*)gamma, (const float*)beta, M, C, relu, ws, (__nv_bfloat16*)ds, (float*)dgamma,
           (float*)dbeta, self_clean, nvalid, rps);

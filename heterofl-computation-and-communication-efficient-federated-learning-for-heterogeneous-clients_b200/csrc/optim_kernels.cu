@@ -28,6 +28,7 @@ template <> struct GradVec<__nv_bfloat16> {
 
 template <typename G>
 __global__ void __launch_bounds__(256) grad_norm_sq_kernel(const G* __restrict__ g, int n4, float* __restrict__ scratch) {
+  pdl_sync();
   __shared__ float sm[33];
   float acc = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(256)
 sgd_update_kernel(float* __restrict__ w, __nv_bfloat16* __restrict__ wc, G* __restrict__ g, float* __restrict__ mom,
                   int n4, const float* __restrict__ lr_p, float mu, float wd, float max_norm,
                   float* __restrict__ scratch /* [0]=norm^2, [1]=done-block counter (as uint) */) {
+  pdl_sync();
   const float total = sqrtf(*reinterpret_cast<volatile float*>(scratch));
   const float coef = fminf(1.f, max_norm / (total + 1e-6f));
   const float lr = *lr_p;
@@ -104,12 +106,12 @@ extern "C" void hfl_sgd_clip_step(float* w, void* wc, void* g, int g_is_bf16, fl
   const int n4 = (int)(n / 4);
   const int grid = grid_for(n4);
   if (g_is_bf16) {
-    grad_norm_sq_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)g, n4, scratch);
-    sgd_update_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w, (__nv_bfloat16*)wc, (__nv_bfloat16*)g, mom, n4, lr,
+    launch_k(grad_norm_sq_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)g, n4, scratch);
+    launch_k(sgd_update_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, w, (__nv_bfloat16*)wc, (__nv_bfloat16*)g, mom, n4, lr,
                                                               mu, wd, max_norm, scratch);
   } else {
-    grad_norm_sq_kernel<float><<<grid, 256, 0, stream>>>((const float*)g, n4, scratch);
-    sgd_update_kernel<float><<<grid, 256, 0, stream>>>(w, (__nv_bfloat16*)wc, (float*)g, mom, n4, lr, mu, wd,
+    launch_k(grad_norm_sq_kernel<float>, dim3(grid), dim3(256), 0, stream, (const float*)g, n4, scratch);
+    launch_k(sgd_update_kernel<float>, dim3(grid), dim3(256), 0, stream, w, (__nv_bfloat16*)wc, (float*)g, mom, n4, lr, mu, wd,
                                                       max_norm, scratch);
   }
   count_launch(2);
@@ -133,6 +135,7 @@ __device__ __forceinline__ float seg_grad(const Seg& s, long i) {
 
 __global__ void __launch_bounds__(256) multi_norm_sq_kernel(const Seg* __restrict__ segs, const int2* __restrict__ blocks,
                                                             float* __restrict__ scratch) {
+  pdl_sync();
   __shared__ float sm[33];
   const int2 b = blocks[blockIdx.x];
   const Seg s = segs[b.x];
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(256)
 multi_sgd_update_kernel(const Seg* __restrict__ segs, const int2* __restrict__ blocks, float* __restrict__ w,
                         __nv_bfloat16* __restrict__ wc, float* __restrict__ mom, const float* __restrict__ lr_p,
                         float mu, float wd, float max_norm, float* __restrict__ scratch) {
+  pdl_sync();
   const float total = sqrtf(*reinterpret_cast<volatile float*>(scratch));
   const float coef = fminf(1.f, max_norm / (total + 1e-6f));
   const float lr = *lr_p;
@@ -187,8 +191,8 @@ extern "C" void hfl_multi_sgd_clip_step(const void* segs, const void* blocks, in
                                         float* mom, const float* lr, float mu, float wd, float max_norm,
                                         float* scratch, cudaStream_t stream) {
   if (n_blocks <= 0) return;
-  hfl::multi_norm_sq_kernel<<<n_blocks, 256, 0, stream>>>((const hfl::Seg*)segs, (const int2*)blocks, scratch);
-  hfl::multi_sgd_update_kernel<<<n_blocks, 256, 0, stream>>>((const hfl::Seg*)segs, (const int2*)blocks, w,
+  hfl::launch_k(hfl::multi_norm_sq_kernel, dim3(n_blocks), dim3(256), 0, stream, (const hfl::Seg*)segs, (const int2*)blocks, scratch);
+  hfl::launch_k(hfl::multi_sgd_update_kernel, dim3(n_blocks), dim3(256), 0, stream, (const hfl::Seg*)segs, (const int2*)blocks, w,
                                                             (__nv_bfloat16*)wc, mom, lr, mu, wd, max_norm, scratch);
   hfl::count_launch(2);
 }

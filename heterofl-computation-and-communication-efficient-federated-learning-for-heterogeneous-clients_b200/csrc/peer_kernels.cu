@@ -8,6 +8,7 @@
 // A bounded spin (~60 s: a peer may legitimately be busy capturing CUDA graphs on a cold start) turns a lost peer into
 // an error flag (PeerPool.check) instead of a hung GPU.
 #include <atomic>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace hfl {
@@ -15,9 +16,19 @@ namespace hfl {
 static std::atomic<long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// HFL_PDL=0 launches every kernel with plain stream serialisation (A/B switch; read once)
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("HFL_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
 __global__ void peer_barrier_kernel(const unsigned long long* __restrict__ flag_ptrs, int rank, int world,
                                     unsigned epoch, int* __restrict__ err) {
   const int p = threadIdx.x;
+  pdl_sync();             // "this rank's earlier kernels have completed" is what the flag publishes
   if (p < world) {
     unsigned* remote = reinterpret_cast<unsigned*>(flag_ptrs[p]) + rank;
     __threadfence_system();
@@ -44,7 +55,7 @@ extern "C" void hfl_launch_count_add(long n) { g_launches.fetch_add(n, std::memo
 
 extern "C" void hfl_peer_barrier(const void* flag_ptrs, int rank, int world, unsigned epoch, int* err,
                                  cudaStream_t stream) {
-  peer_barrier_kernel<<<1, 32 * ((world + 31) / 32), 0, stream>>>((const unsigned long long*)flag_ptrs, rank, world,
+  launch_k(peer_barrier_kernel, dim3(1), dim3(32 * ((world + 31) / 32)), 0, stream, (const unsigned long long*)flag_ptrs, rank, world,
                                                                   epoch, err);
   count_launch();
 }

@@ -25,6 +25,7 @@ __device__ __forceinline__ uint4 pack8h(const float (&f)[8]) {
 template <int VEC>
 __global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
                                     int W, int C) {
+  pdl_sync();
   const int OH = H / 2, OW = W / 2, CV = C / VEC;
   const long total = (long)N * OH * OW * CV;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -61,6 +62,7 @@ __global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
 template <int VEC>
 __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                     __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C) {
+  pdl_sync();
   const int OH = H / 2, OW = W / 2, CV = C / VEC;
   const int WH = (H + 1) / 2, WW = (W + 1) / 2;      // windows incl. the partial ones
   const long total = (long)N * WH * WW * CV;
@@ -128,9 +130,9 @@ extern "C" int hfl_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int
   const bool v8 = (C % 8) == 0;
   const long total = (long)N * (H / 2) * (W / 2) * (v8 ? C / 8 : C);
   if (v8)
-    hfl::maxpool2_fwd_kernel<8><<<pool_grid(total), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C);
+    hfl::launch_k(hfl::maxpool2_fwd_kernel<8>, dim3(pool_grid(total)), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C);
   else
-    hfl::maxpool2_fwd_kernel<1><<<pool_grid(total), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C);
+    hfl::launch_k(hfl::maxpool2_fwd_kernel<1>, dim3(pool_grid(total)), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C);
   hfl::count_launch();
   return (int)cudaGetLastError();
 }
@@ -139,10 +141,10 @@ extern "C" int hfl_maxpool2_bwd(const void* dy, const void* x, void* dx, int N, 
   const bool v8 = (C % 8) == 0;
   const long total = (long)N * ((H + 1) / 2) * ((W + 1) / 2) * (v8 ? C / 8 : C);
   if (v8)
-    hfl::maxpool2_bwd_kernel<8><<<pool_grid(total), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+    hfl::launch_k(hfl::maxpool2_bwd_kernel<8>, dim3(pool_grid(total)), dim3(256), 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
                                                                  (__nv_bfloat16*)dx, N, H, W, C);
   else
-    hfl::maxpool2_bwd_kernel<1><<<pool_grid(total), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+    hfl::launch_k(hfl::maxpool2_bwd_kernel<1>, dim3(pool_grid(total)), dim3(256), 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
                                                                  (__nv_bfloat16*)dx, N, H, W, C);
   hfl::count_launch();
   return (int)cudaGetLastError();

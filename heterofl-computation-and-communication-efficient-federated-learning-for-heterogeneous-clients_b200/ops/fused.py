@@ -209,7 +209,9 @@ def maxpool2_bwd(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
 
 # tcgen05 implicit-GEMM forward convolution: "off" | "on" (whenever the shape qualifies) | "auto" = only where it
 # measurably beats the library (profiles/conv_bench.md): the latency-bound training shapes with <= 9 K-blocks
-# (C_in = 64, batch-10 tiles); large-batch and deep-K shapes stay on cuDNN until the kernel is persistent / 2-CTA.
+# (C_in = 64, batch-10 tiles) | "train" = every qualifying shape of a training-sized batch (<= CONV_TC_MAX_PIXELS
+# output pixels), any channel count: keeps the train step on our own kernels so that consecutive launches chain
+# through programmatic dependent launch; the large-batch sBN / test passes stay on the library.
 CONV_TC_MODE = os.environ.get("HFL_CONV_TC", "auto")
 CONV_TC_MAX_PIXELS = int(os.environ.get("HFL_CONV_TC_MAX_PIXELS", "20480"))
 
@@ -227,6 +229,8 @@ def _tc_conv_ok(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> bool
         return False
     if CONV_TC_MODE == "auto":
         return N * (H // stride) * (W // stride) <= CONV_TC_MAX_PIXELS and C <= 64
+    if CONV_TC_MODE == "train":
+        return N * (H // stride) * (W // stride) <= CONV_TC_MAX_PIXELS
     return True
 
 
