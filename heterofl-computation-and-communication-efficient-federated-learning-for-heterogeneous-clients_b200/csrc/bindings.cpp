@@ -75,6 +75,8 @@ int hfl_head_smem_bytes(int, int, int);
 int hfl_head_fwd_bwd(const void*, int, int, int, const void*, const void*, int, int, const long long*,
                      const unsigned char*, float, float*, double*, void*, void*, void*, float*, const int*,
                      cudaStream_t);
+int hfl_bn_apply_sums(const void*, void*, const void*, const void*, int, float, int, int, int, float*, float*, float*,
+                      float*, const int*, int, cudaStream_t);
 int hfl_conv_tc_supported(int, int, int, int, int, int, int, int);
 int hfl_conv_fprop_tc(const void*, const void*, void*, const void*, float*, int, int, int, int, int, int, int, int,
                       cudaStream_t);
@@ -289,6 +291,38 @@ std::vector<torch::Tensor> bn_act_fwd(torch::Tensor x, c10::optional<torch::Tens
   TORCH_CHECK(e == 0, "bn_act_fwd launch failed: ", cudaGetErrorString((cudaError_t)e));
   check_launch();
   return {s, y, stats[0], stats[1], stats[2]};
+}
+
+// y = relu(bn(s)) where the per-channel (sum, sum of squares) of s were accumulated into `ws` (fp32 [2C+1], self-cleaning)
+// by the producing convolution's epilogue.  Returns [y, mean[1,C], invstd[1,C], var_unbiased[1,C]].
+std::vector<torch::Tensor> bn_apply_sums(torch::Tensor s, torch::Tensor gamma, torch::Tensor beta, double eps, int64_t C,
+                                         bool relu, torch::Tensor ws, c10::optional<torch::Tensor> nvalid,
+                                         int64_t samples) {
+  CHECK_CUDA_T(s);
+  TORCH_CHECK(s.scalar_type() == torch::kBFloat16 && is_pow2(C) && C >= 8 && C <= 2048);
+  const int64_t M = s.numel() / C;
+  TORCH_CHECK((M * C) % 8 == 0);
+  const bool pb = gamma.scalar_type() == torch::kBFloat16;
+  TORCH_CHECK(pb || gamma.scalar_type() == torch::kFloat32);
+  TORCH_CHECK(gamma.is_contiguous() && beta.is_contiguous() && beta.scalar_type() == gamma.scalar_type());
+  TORCH_CHECK(ws.scalar_type() == torch::kFloat32 && ws.numel() >= 2 * C + 1 && ws.is_contiguous());
+  c10::cuda::CUDAGuard guard(s.device());
+  auto y = torch::empty_like(s);
+  auto stats = torch::empty({3, 1, C}, torch::TensorOptions().dtype(torch::kFloat32).device(s.device()));
+  float* sp = stats.data_ptr<float>();
+  const int* nvp = nullptr;
+  int rps = 0;
+  if (nvalid.has_value()) {
+    TORCH_CHECK(nvalid->scalar_type() == torch::kInt32 && nvalid->is_cuda() && samples > 0 && M % samples == 0 &&
+                ((M / samples) * C) % 8 == 0, "bn_apply_sums: bad nvalid / samples");
+    nvp = nvalid->data_ptr<int>();
+    rps = (int)(M / samples);
+  }
+  int e = hfl_bn_apply_sums(s.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), pb ? 1 : 0, (float)eps, (int)M,
+                            (int)C, relu ? 1 : 0, ws.data_ptr<float>(), sp, sp + C, sp + 2 * C, nvp, rps, cur_stream());
+  TORCH_CHECK(e == 0, "bn_apply_sums launch failed: ", cudaGetErrorString((cudaError_t)e));
+  check_launch();
+  return {y, stats[0], stats[1], stats[2]};
 }
 
 std::vector<torch::Tensor> affine_act(torch::Tensor x, c10::optional<torch::Tensor> res, torch::Tensor a,
@@ -778,7 +812,7 @@ torch::Tensor conv_fprop_tc(torch::Tensor x, torch::Tensor w, c10::optional<torc
     rp = residual->data_ptr();
   }
   float* sp = nullptr;
-  if (stats.has_value()) { TORCH_CHECK(stats->scalar_type() == torch::kFloat32 && stats->numel() == 2 * K && stats->is_contiguous()); sp = stats->data_ptr<float>(); }
+  if (stats.has_value()) { TORCH_CHECK(stats->scalar_type() == torch::kFloat32 && stats->numel() >= 2 * K && stats->is_contiguous()); sp = stats->data_ptr<float>(); }
   int e = hfl_conv_fprop_tc(x.data_ptr(), w.data_ptr(), y.data_ptr(), rp, sp, N, H, W, C, K, R, S, (int)stride, cur_stream());
   TORCH_CHECK(e == 0, "conv_fprop_tc failed with code ", e);
   return y;
@@ -963,6 +997,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("masked_ce", &masked_ce);
   m.def("augment", &augment);
   m.def("bn_act_fwd", &bn_act_fwd);
+  m.def("bn_apply_sums", &bn_apply_sums);
   m.def("affine_act", &affine_act);
   m.def("bn_act_bwd", &bn_act_bwd);
   m.def("mx_quantize", &mx_quantize);

@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -33,6 +34,37 @@ struct ConvGeom {
   int bn, bh, bw;          // pixel brick of one tile (bn*bh*bw == 128, bw == OW)
   int tiles_h;             // ceil(OH / bh)
 };
+
+// Column sums over the 32 lanes of a warp: on return lane j holds sum_over_lanes(v[j]) in v[0]  (31 shuffles).
+__device__ __forceinline__ void warp_col_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+}
+// thread-block-cluster helpers (split-K reduction through distributed shared memory)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 
 template <int BLOCK_N>
 struct ConvSmem {
@@ -68,8 +100,16 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
   const int tile_h = blockIdx.x - tile_n * g.tiles_h;  // row-group index
   const int n0 = tile_n * g.bn, oh0 = tile_h * g.bh;
   const int n_blk = blockIdx.y;
-  const int cblocks = g.C / CV_BLOCK_K;
-  const int num_k = g.R * g.S * cblocks;
+  const int cblocks = (g.C + CV_BLOCK_K - 1) / CV_BLOCK_K;   // a partial last block is zero-filled by the TMA unit
+  const int num_k_all = g.R * g.S * cblocks;
+  // split-K (gridDim.z > 1, launched as thread-block clusters {1, 1, ksplit}): the deep-K layers of a batch-10 step
+  // have 2-8 output tiles and 36-72 k-blocks each; the CTAs of a cluster reduce disjoint k-ranges of ONE tile into
+  // their own TMEM accumulators and combine them through distributed shared memory (no atomics, no zero-filled
+  // scratch, no second kernel).
+  const int ksplit = gridDim.z;
+  const int k_per = (num_k_all + ksplit - 1) / ksplit;
+  const int kb0 = blockIdx.z * k_per;
+  const int num_k = max(min(k_per, num_k_all - kb0), 0);
   constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 
   if (warp == 0 && lane == 0) {
@@ -93,7 +133,7 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
       for (int kb = 0; kb < num_k; ++kb) {
         const int st = kb % CV_STAGES;
         const uint32_t ph = (kb / CV_STAGES) & 1;
-        const int tap = kb / cblocks, cb = kb - tap * cblocks;
+        const int tap = (kb0 + kb) / cblocks, cb = (kb0 + kb) - tap * cblocks;
         const int r = tap / g.S, s = tap - r * g.S;
         mbar_wait(&empty_bar[st], ph ^ 1);
         uint8_t* sa = smem + st * S::STAGE_BYTES;
@@ -102,16 +142,17 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         if (!DGRAD) {
           // A: box {64ch, bw, bh, bn} at (c, w, h, n) = (cb*64, s - pad, oh0*stride + r - pad, n0); halo -> zero fill
           tma_load_4d(sa, &tmap_x, &full_bar[st], cb * CV_BLOCK_K, s - g.pad, oh0 * g.stride + r - g.pad, n0);
-          // B: rows = output channels, cols = (tap, c)
-          tma_load_2d(sb, &tmap_w, &full_bar[st], tap * g.C + cb * CV_BLOCK_K, n_blk * BLOCK_N);
+          // B: box {64 c, 1 tap, BLOCK_N k_out} of the filter seen as {C, R*S, K_out}; channels / rows beyond the
+          // tensor are zero-filled, so any C and K_out that are multiples of 8 ride the same 128-byte-swizzle path
+          tma_load_3d(sb, &tmap_w, &full_bar[st], cb * CV_BLOCK_K, tap, n_blk * BLOCK_N);
         } else {
           // A: dY box at the mirrored tap offset
           tma_load_4d(sa, &tmap_x, &full_bar[st], cb * CV_BLOCK_K, g.pad - s, oh0 + g.pad - r, n0);
-          // B (MN-major): 64(c) x 64(k_out) boxes of the [K_out_total, R*S*C_total] filter matrix; here g.Kout is the
-          // number of dX channels (= filter C) and g.C the reduction length (= filter K_out)
+          // B (MN-major): 64(c) x 64(k_out) boxes of the {C, R*S, K_out} filter; here g.Kout is the number of dX
+          // channels (= filter C) and g.C the reduction length (= filter K_out)
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
-            tma_load_2d(sb + j * 8192, &tmap_w, &full_bar[st], tap * g.Kout + n_blk * BLOCK_N + j * 64, cb * CV_BLOCK_K);
+            tma_load_3d(sb + j * 8192, &tmap_w, &full_bar[st], n_blk * BLOCK_N + j * 64, tap, cb * CV_BLOCK_K);
         }
       }
     }
@@ -135,6 +176,27 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
       }
       __syncwarp();
     }
+  } else if (warp >= 4 && ksplit > 1) {
+    // ---- split-K, step 1: this CTA's partial accumulator -> fp32 staging tile in its own shared memory (the stage
+    // ring is free: the accumulator barrier fires after the last MMA has read it)
+    const int q = warp - 4;
+    if (num_k > 0) mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    float* stg = reinterpret_cast<float*>(smem) + (size_t)(q * 32 + lane) * (BLOCK_N + 4);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      if (num_k > 0) {
+        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(stg + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    tcgen05_fence_before();
   } else if (warp >= 4) {
     const int q = warp - 4;
     mbar_wait(tmem_full_bar, 0);
@@ -151,60 +213,129 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     const size_t pix = ((size_t)n * g.OH + oh) * g.OW + w_l;
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      const int col0 = n_blk * BLOCK_N + c0;
+      const int ncol = min(32, g.Kout - col0);              // produced channels in this chunk (multiple of 8)
+      if (ncol <= 0) break;                                 // warp-uniform
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + c0, v);
       tmem_ld_wait();
-      const int col0 = n_blk * BLOCK_N + c0;
       float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = ok ? __uint_as_float(v[j]) : 0.f;
+      for (int j = 0; j < 32; ++j) f[j] = (ok && j < ncol) ? __uint_as_float(v[j]) : 0.f;
       if (ok) {
         __nv_bfloat16* dst = Y + pix * g.Kout + col0;
         if (HAS_RES) {
           const uint4* rp = reinterpret_cast<const uint4*>(residual + pix * g.Kout + col0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint4 u = rp[j];
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+            if (8 * j < ncol) {
+              const uint4 u = rp[j];
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { f[8 * j + 2 * e] += __low2float(h[e]); f[8 * j + 2 * e + 1] += __high2float(h[e]); }
+              for (int e = 0; e < 4; ++e) { f[8 * j + 2 * e] += __low2float(h[e]); f[8 * j + 2 * e + 1] += __high2float(h[e]); }
+            }
           }
         }
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-          uint4 u;
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-          h[0] = __floats2bfloat162_rn(f[j], f[j + 1]);
-          h[1] = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-          h[2] = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-          h[3] = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-          *reinterpret_cast<uint4*>(dst + j) = u;
-          if (HAS_STATS) {   // statistics of the bf16-rounded outputs (what a separate BN kernel would read)
-            f[j] = __low2float(h[0]); f[j + 1] = __high2float(h[0]); f[j + 2] = __low2float(h[1]); f[j + 3] = __high2float(h[1]);
-            f[j + 4] = __low2float(h[2]); f[j + 5] = __high2float(h[2]); f[j + 6] = __low2float(h[3]); f[j + 7] = __high2float(h[3]);
+          if (j < ncol) {
+            uint4 u;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+            h[0] = __floats2bfloat162_rn(f[j], f[j + 1]);
+            h[1] = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+            h[2] = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+            h[3] = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+            *reinterpret_cast<uint4*>(dst + j) = u;
+            if (HAS_STATS) {   // statistics of the bf16-rounded outputs (what a separate BN kernel would read)
+              f[j] = __low2float(h[0]); f[j + 1] = __high2float(h[0]); f[j + 2] = __low2float(h[1]); f[j + 3] = __high2float(h[1]);
+              f[j + 4] = __low2float(h[2]); f[j + 5] = __high2float(h[2]); f[j + 6] = __low2float(h[3]); f[j + 7] = __high2float(h[3]);
+            }
           }
         }
       }
       if (HAS_STATS) {
-        // column sums over the warp's 32 rows: butterfly where lane j ends up owning column j
+        // column sums over the warp's 32 rows (rows outside the image / batch hold zeros): 2 x 31 shuffles, lane j
+        // ends up owning column j
+        float sq[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float sx = f[j], sq = f[j] * f[j];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            sx += __shfl_xor_sync(0xffffffffu, sx, o);
-            sq += __shfl_xor_sync(0xffffffffu, sq, o);
-          }
-          if (lane == j) {
-            atomicAdd(&stats[col0 + j], sx);
-            atomicAdd(&stats[g.Kout + col0 + j], sq);
-          }
+        for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
+        warp_col_reduce32(f, lane);
+        warp_col_reduce32(sq, lane);
+        if (lane < ncol) {
+          red_add_f32(&stats[col0 + lane], f[0]);
+          red_add_f32(&stats[g.Kout + col0 + lane], sq[0]);
         }
       }
     }
     tcgen05_fence_before();
   }
   __syncthreads();
+  if (ksplit > 1) {
+    // ---- split-K, step 2: CTA z of the cluster sums rows [z*RPC, (z+1)*RPC) of all ksplit staging tiles through
+    // DSMEM and runs the normal epilogue (residual, bf16 store, BatchNorm statistics) on them
+    cluster_sync_all();
+    if (warp >= 4) {
+      constexpr int PITCH = BLOCK_N + 4;
+      constexpr int CG = BLOCK_N / 4;                        // float4 column groups per row
+      const int t = threadIdx.x - 128;
+      const int cg = t % CG;                                  // this thread's 4 columns (fixed), rows strided
+      const int rpc = CV_BLOCK_M / ksplit;
+      const int row0 = blockIdx.z * rpc;
+      const int col = n_blk * BLOCK_N + cg * 4;
+      const bool col_ok = col < g.Kout;                       // K_out is a multiple of 8: the 4 columns share the answer
+      const uint32_t stg0 = smem_u32(smem);
+      float sx[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int rr = t / CG; rr < rpc; rr += 128 / CG) {
+        const int m = row0 + rr;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t off = (uint32_t)(m * PITCH + cg * 4) * 4u;
+        for (int z = 0; z < ksplit; ++z) {
+          const float4 p = ld_dsmem_f4(mapa_u32(stg0 + off, (uint32_t)z));
+          acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+        }
+        const int w_l = m % g.bw;
+        const int tt = m / g.bw;
+        const int h_l = tt % g.bh, n_l = tt / g.bh;
+        const int n = n0 + n_l, oh = oh0 + h_l;
+        if (!((n < g.N) && (oh < g.OH) && col_ok)) continue;
+        const size_t pix = ((size_t)n * g.OH + oh) * g.OW + w_l;
+        if (HAS_RES) {
+          const uint2 u = *reinterpret_cast<const uint2*>(residual + pix * g.Kout + col);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+          acc.x += __low2float(h[0]); acc.y += __high2float(h[0]); acc.z += __low2float(h[1]); acc.w += __high2float(h[1]);
+        }
+        uint2 o;
+        __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+        ho[0] = __floats2bfloat162_rn(acc.x, acc.y);
+        ho[1] = __floats2bfloat162_rn(acc.z, acc.w);
+        *reinterpret_cast<uint2*>(Y + pix * g.Kout + col) = o;
+        if (HAS_STATS) {
+          const float a0 = __low2float(ho[0]), a1 = __high2float(ho[0]), a2 = __low2float(ho[1]), a3 = __high2float(ho[1]);
+          sx[0] += a0; sx[1] += a1; sx[2] += a2; sx[3] += a3;
+          sq[0] += a0 * a0; sq[1] += a1 * a1; sq[2] += a2 * a2; sq[3] += a3 * a3;
+        }
+      }
+      if (HAS_STATS) {
+        // lanes that share a column group (CG < 32) combine first
+#pragma unroll
+        for (int o = 16; o >= CG; o >>= 1) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            sx[e] += __shfl_xor_sync(0xffffffffu, sx[e], o);
+            sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], o);
+          }
+        }
+        if (lane < CG && col_ok) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            red_add_f32(&stats[col + e], sx[e]);
+            red_add_f32(&stats[g.Kout + col + e], sq[e]);
+          }
+        }
+      }
+    }
+    cluster_sync_all();     // peers may still be reading this CTA's staging tile
+  }
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -215,9 +346,18 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
 
 using namespace hfl;
 
+// K,R,S,C filter as a 3-D tensor {C, R*S, K_out} (innermost first); box {box_c, 1, box_k}
+static int make_tmap_filter_bf16(CUtensorMap* m, const void* Wt, int C, int taps, int Kout, int box_c, int box_k) {
+  const uint64_t dims[3] = {(uint64_t)C, (uint64_t)taps, (uint64_t)Kout};
+  const uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)taps * C * 2};
+  const uint32_t box[3] = {(uint32_t)box_c, 1u, (uint32_t)box_k};
+  const uint32_t estr[3] = {1u, 1u, 1u};
+  return make_tmap_bf16_generic(m, Wt, 3, dims, strides, box, estr);
+}
+
 template <int BLOCK_N, bool DGRAD, bool HAS_RES, bool HAS_STATS>
 static int launch_conv_v(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, const void* residual, float* stats,
-                         const ConvGeom& g, int tiles_m, cudaStream_t stream) {
+                         const ConvGeom& g, int tiles_m, int n_tiles, int ksplit, cudaStream_t stream) {
   auto kern = conv_fprop_tcgen05_kernel<BLOCK_N, DGRAD, HAS_RES, HAS_STATS>;
   constexpr int smem = ConvSmem<BLOCK_N>::TOTAL;
   static bool configured = false;
@@ -226,28 +366,59 @@ static int launch_conv_v(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, 
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  dim3 grid(tiles_m, g.Kout / BLOCK_N);
-  launch_k(kern, dim3(grid), dim3(CV_THREADS), smem, stream, tx, tw, (__nv_bfloat16*)Y, (const __nv_bfloat16*)residual, stats, g);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles_m, n_tiles, ksplit);
+  cfg.blockDim = dim3(CV_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (ksplit > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = ksplit;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tx, tw, (__nv_bfloat16*)Y, (const __nv_bfloat16*)residual, stats, g);
   count_launch();
-  return (int)cudaGetLastError();
+  return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
+}
+
+// split-K factor of a tile grid: only when the grid leaves most SMs idle and the reduction is long; powers of two
+// (the cluster splits the 128 tile rows evenly), every split keeps >= 4 k-blocks.  HFL_CONV_KSPLIT=1 disables.
+static int conv_ksplit(int tiles, int num_k) {
+  static const int cap = []() { const char* e = getenv("HFL_CONV_KSPLIT"); return e ? atoi(e) : 8; }();
+  int ks = 1;
+  while (ks * 2 <= cap && tiles * ks * 2 <= 148 && num_k / (ks * 2) >= 4) ks *= 2;
+  return ks;
 }
 
 template <int BLOCK_N, bool DGRAD = false>
 static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, const void* residual, float* stats,
-                       const ConvGeom& g, int tiles_m, cudaStream_t stream) {
+                       const ConvGeom& g, int tiles_m, int n_tiles, cudaStream_t stream) {
   if (residual != nullptr && (reinterpret_cast<uintptr_t>(residual) & 15) != 0) return -3;
   if ((reinterpret_cast<uintptr_t>(Y) & 15) != 0) return -3;
+  const int num_k = g.R * g.S * ((g.C + CV_BLOCK_K - 1) / CV_BLOCK_K);
+  const int ks = conv_ksplit(tiles_m * n_tiles, num_k);
   if (residual != nullptr) {
-    if (stats != nullptr) return launch_conv_v<BLOCK_N, DGRAD, true, true>(tx, tw, Y, residual, stats, g, tiles_m, stream);
-    return launch_conv_v<BLOCK_N, DGRAD, true, false>(tx, tw, Y, residual, stats, g, tiles_m, stream);
+    if (stats != nullptr) return launch_conv_v<BLOCK_N, DGRAD, true, true>(tx, tw, Y, residual, stats, g, tiles_m, n_tiles, ks, stream);
+    return launch_conv_v<BLOCK_N, DGRAD, true, false>(tx, tw, Y, residual, stats, g, tiles_m, n_tiles, ks, stream);
   }
-  if (stats != nullptr) return launch_conv_v<BLOCK_N, DGRAD, false, true>(tx, tw, Y, residual, stats, g, tiles_m, stream);
-  return launch_conv_v<BLOCK_N, DGRAD, false, false>(tx, tw, Y, residual, stats, g, tiles_m, stream);
+  if (stats != nullptr) return launch_conv_v<BLOCK_N, DGRAD, false, true>(tx, tw, Y, residual, stats, g, tiles_m, n_tiles, ks, stream);
+  return launch_conv_v<BLOCK_N, DGRAD, false, false>(tx, tw, Y, residual, stats, g, tiles_m, n_tiles, ks, stream);
 }
 
 // 0 if this problem can run on the tcgen05 path
 extern "C" int hfl_conv_tc_supported(int N, int H, int W, int C, int Kout, int R, int S, int stride) {
-  if (C % 64 != 0 || Kout % 64 != 0) return 1;
+  if (C % 8 != 0 || Kout % 8 != 0) return 1;     // 16-byte global strides for TMA; partial 64-blocks are zero-filled
   if (!((R == 3 && S == 3) || (R == 1 && S == 1))) return 2;
   if (stride != 1 && stride != 2) return 3;
   const int pad = R / 2;
@@ -273,17 +444,19 @@ extern "C" int hfl_conv_fprop_tc(const void* X, const void* Wt, void* Y, const v
   g.bn = rows / g.bh;
   g.tiles_h = (g.OH + g.bh - 1) / g.bh;
   const int tiles_m = ((N + g.bn - 1) / g.bn) * g.tiles_h;
-  const int block_n = (Kout % 128 == 0) ? 128 : 64;
+  const int block_n = (Kout % 128 == 0) ? 128 : (Kout > 32 ? 64 : 32);
   CUtensorMap tx, tw;
   // traversal strides: box extents are given in traversed elements (ceil(box/stride) elements are loaded)
   int r = make_tmap_nhwc_bf16(&tx, X, (uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N, CV_BLOCK_K,
                               (uint32_t)(g.bw * stride), (uint32_t)(g.bh * stride), (uint32_t)g.bn, (uint32_t)stride,
                               (uint32_t)stride, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r) return 1000 + r;
-  r = make_tmap_2d_bf16(&tw, Wt, (uint64_t)R * S * C, (uint64_t)Kout, (uint64_t)R * S * C * 2, CV_BLOCK_K, block_n);
+  r = make_tmap_filter_bf16(&tw, Wt, C, R * S, Kout, CV_BLOCK_K, block_n);
   if (r) return 2000 + r;
-  if (block_n == 128) return launch_conv<128>(tx, tw, Y, residual, stats, g, tiles_m, stream);
-  return launch_conv<64>(tx, tw, Y, residual, stats, g, tiles_m, stream);
+  const int n_tiles = (Kout + block_n - 1) / block_n;
+  if (block_n == 128) return launch_conv<128>(tx, tw, Y, residual, stats, g, tiles_m, n_tiles, stream);
+  if (block_n == 64) return launch_conv<64>(tx, tw, Y, residual, stats, g, tiles_m, n_tiles, stream);
+  return launch_conv<32>(tx, tw, Y, residual, stats, g, tiles_m, n_tiles, stream);
 }
 
 // Stride-1 data gradient: dX[N,H,W,C] from dY[N,H,W,Kout] and the K,R,S,C filter.  `residual` is an optional tensor
@@ -303,15 +476,16 @@ extern "C" int hfl_conv_dgrad_tc(const void* dY, const void* Wt, void* dX, const
   g.bn = rows / g.bh;
   g.tiles_h = (H + g.bh - 1) / g.bh;
   const int tiles_m = ((N + g.bn - 1) / g.bn) * g.tiles_h;
-  const int block_n = (C % 128 == 0) ? 128 : 64;
+  const int block_n = (C % 128 == 0) ? 128 : 64;      // MN-major B: whole 64-channel boxes (zero-filled past C)
   CUtensorMap tx, tw;
   int r = make_tmap_nhwc_bf16(&tx, dY, (uint64_t)Kout, (uint64_t)W, (uint64_t)H, (uint64_t)N, CV_BLOCK_K, (uint32_t)g.bw,
                               (uint32_t)g.bh, (uint32_t)g.bn, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r) return 1000 + r;
-  r = make_tmap_2d_bf16(&tw, Wt, (uint64_t)R * S * C, (uint64_t)Kout, (uint64_t)R * S * C * 2, 64, CV_BLOCK_K);
+  r = make_tmap_filter_bf16(&tw, Wt, C, R * S, Kout, 64, CV_BLOCK_K);
   if (r) return 2000 + r;
-  if (block_n == 128) return launch_conv<128, true>(tx, tw, dX, residual, nullptr, g, tiles_m, stream);
-  return launch_conv<64, true>(tx, tw, dX, residual, nullptr, g, tiles_m, stream);
+  const int n_tiles = (C + block_n - 1) / block_n;
+  if (block_n == 128) return launch_conv<128, true>(tx, tw, dX, residual, nullptr, g, tiles_m, n_tiles, stream);
+  return launch_conv<64, true>(tx, tw, dX, residual, nullptr, g, tiles_m, n_tiles, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -378,9 +552,12 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __g
           mbar_wait(&empty_bar[st], ph ^ 1);
           uint8_t* sa = smem + st * WG_STAGE_BYTES;
           uint8_t* sb = sa + WG_A_BYTES;
-          mbar_expect_tx(&full_bar[st], WG_STAGE_BYTES);
+          // a K_out tail of <= 64 channels loads one dY box only: accumulator rows 64..127 then hold whatever the
+          // stale half-stage multiplies to and are never stored (k < K_out mask in the epilogue)
+          const bool two = k_blk * 128 + 64 < g.Kout;
+          mbar_expect_tx(&full_bar[st], two ? WG_STAGE_BYTES : WG_STAGE_BYTES - 8192);
           tma_load_4d(sa, &tmap_dy, &full_bar[st], k_blk * 128, 0, oh0, n0);
-          tma_load_4d(sa + 8192, &tmap_dy, &full_bar[st], k_blk * 128 + 64, 0, oh0, n0);
+          if (two) tma_load_4d(sa + 8192, &tmap_dy, &full_bar[st], k_blk * 128 + 64, 0, oh0, n0);
           tma_load_4d(sb, &tmap_x, &full_bar[st], c_blk * 64, s - g.pad, oh0 * g.stride + r - g.pad, n0);
         }
       }
@@ -428,7 +605,7 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __g
 #pragma unroll 4
       for (int r0 = 0; r0 < 32; r0 += 2) {
         const int k = k_blk * 128 + q * 32 + r0 + rsub;
-        if (k < g.Kout) {
+        if (k < g.Kout && c_blk * 64 + cseg < g.C) {
           const float4 val = *reinterpret_cast<const float4*>(my + (r0 + rsub) * PITCH + cseg * 4);
           float* dst = dW + ((size_t)k * g.R * g.S + tap) * g.C + c_blk * 64 + cseg;
           if (g.splits == 1) {
@@ -451,7 +628,7 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __g
 }  // namespace hfl
 
 extern "C" int hfl_conv_wgrad_tc_supported(int N, int H, int W, int C, int Kout, int R, int S, int stride) {
-  if (C % 64 != 0 || Kout % 64 != 0) return 1;
+  if (C % 8 != 0 || Kout % 8 != 0) return 1;
   if (!((R == 3 && S == 3) || (R == 1 && S == 1))) return 2;
   if (stride != 1 && stride != 2) return 3;
   const int pad = R / 2;
@@ -480,7 +657,7 @@ extern "C" int hfl_conv_wgrad_tc(const void* dY, const void* X, float* dW, int N
   g.bn = rows / g.bh;
   g.bricks_h = g.OH / g.bh;
   g.bricks = (N / g.bn) * g.bricks_h;
-  const int base_ctas = ((Kout + 127) / 128) * (C / 64) * R * S;
+  const int base_ctas = ((Kout + 127) / 128) * ((C + 63) / 64) * R * S;
   int splits = 1;
   while (base_ctas * splits < 96 && splits * 8 <= g.bricks) splits *= 2;   // fill the machine, keep >= 8 bricks per CTA
   g.splits = splits;
@@ -500,7 +677,7 @@ extern "C" int hfl_conv_wgrad_tc(const void* dY, const void* X, float* dW, int N
     configured = true;
   }
   if (splits > 1 && zero_first) cudaMemsetAsync(dW, 0, (size_t)Kout * R * S * C * sizeof(float), stream);
-  dim3 grid((Kout + 127) / 128, C / 64, R * S * splits);
+  dim3 grid((Kout + 127) / 128, (C + 63) / 64, R * S * splits);
   hfl::launch_k(hfl::conv_wgrad_tcgen05_kernel, dim3(grid), dim3(hfl::CV_THREADS), hfl::WG_SMEM, stream, tdy, tx, dW, g);
   hfl::count_launch();
   cudaError_t e = cudaGetLastError();

@@ -804,6 +804,25 @@ extern "C" int hfl_bn_act_fwd(const void* x, const void* res, void* s_out, void*
   return (int)e;
 }
 
+// Apply-only half of the split path for producers that already left (sum, sum of squares) in `ws` = [2C sums][ticket]:
+// the tcgen05 convolution's statistics epilogue (conv_tcgen05.cu).  The kernel re-zeroes `ws` itself (ticket protocol).
+extern "C" int hfl_bn_apply_sums(const void* s, void* y, const void* gamma, const void* beta, int param_bf16, float eps,
+                                 int M, int C, int relu, float* ws, float* mean_out, float* invstd_out, float* varu_out,
+                                 const int* nvalid, int rps, cudaStream_t stream) {
+  const int nvec = M * C / 8;
+  dim3 grid(wide_grid(nvec), 1);
+  if (param_bf16)
+    launch_k(bn_apply_wide_kernel<__nv_bfloat16>, grid, dim3(NT), 2 * C * sizeof(float), stream,
+             (const __nv_bfloat16*)s, (__nv_bfloat16*)y, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, eps, M, C,
+             relu, ws, mean_out, invstd_out, varu_out, 1, nvalid, rps);
+  else
+    launch_k(bn_apply_wide_kernel<float>, grid, dim3(NT), 2 * C * sizeof(float), stream, (const __nv_bfloat16*)s,
+             (__nv_bfloat16*)y, (const float*)gamma, (const float*)beta, eps, M, C, relu, ws, mean_out, invstd_out,
+             varu_out, 1, nvalid, rps);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 extern "C" void hfl_affine_act(const void* x, const void* res, void* s_out, void* y, const float* a, const float* b,
                                long n, int C, int relu, cudaStream_t stream) {
   const long nvec = n / 8;

@@ -35,14 +35,15 @@ class FusedResNet:
         self._side = None
         self._ws: Dict[str, torch.Tensor] = {}
 
-    def _scratch(self, name: str, like: torch.Tensor) -> Optional[torch.Tensor]:
+    def _scratch(self, name: str, like: torch.Tensor, channels: Optional[int] = None) -> Optional[torch.Tensor]:
         """Persistent, self-cleaning fp32 [2C+1] scratch of one BN call site (forward and backward use separate
         slabs); lets the wide statistics kernels run without a memset node per launch."""
         if not like.is_cuda:
             return None
         t = self._ws.get(name)
         if t is None:
-            t = torch.zeros(2 * like.shape[1] + 1, dtype=torch.float32, device=like.device)
+            C = like.shape[1] if channels is None else int(channels)
+            t = torch.zeros(2 * C + 1, dtype=torch.float32, device=like.device)
             self._ws[name] = t
         return t
 
@@ -79,6 +80,15 @@ class FusedResNet:
                                        fo.NORM_GROUPS[self.norm](x.shape[1]))
         return s, y, m, i
 
+    def _cnf(self, pend, P, name, eps, ws_tag, nvalid=None):
+        """3x3 convolution ``pend = (input, weight, stride, residual)`` followed by ``_nf`` -> (s, y, saved stats);
+        BatchNorm models fuse the residual add and the batch statistics into the convolution's epilogue."""
+        xin, w, stride, res = pend
+        if self.norm == "bn":
+            return fo.conv_bn_act_fwd(xin, w, stride, 1, res, P[name + ".weight"], P[name + ".bias"], eps,
+                                      self._scratch(ws_tag, xin, w.shape[0]), nvalid)
+        return self._nf(fo.conv_fwd(xin, w, stride, 1), res, P, name, eps, ws_tag, nvalid)
+
     def _nb(self, dy, dy2, dres, s, m, i, P, G, name, ws_tag, nvalid=None, **kw):
         G[name + ".weight"] = torch.empty_like(P[name + ".weight"])
         G[name + ".bias"] = torch.empty_like(P[name + ".bias"])
@@ -106,18 +116,24 @@ class FusedResNet:
         G: Dict[str, torch.Tensor] = {}
         saved = []
         keep: List[torch.Tensor] = []
+        # Every norm consumes the convolution in front of it (+ the block's shortcut): conv -> (residual add + batch
+        # statistics in the tcgen05 epilogue) -> apply + ReLU.  `pend` = (input, weight, residual) of the convolution
+        # whose output the NEXT norm normalises.
         c0 = fo.conv_fwd(x, P["conv1.weight"], 1, 1)
-        cur, res = c0, None                     # block input is s = cur (+ res)
-        for blk in self.blocks:
+        s_in = o1 = m1 = i1 = None
+        pend = None
+        for bi, blk in enumerate(self.blocks):
             pre, stride = blk["prefix"], blk["stride"]
-            s_in, o1, m1, i1 = self._nf(cur, res, P, pre + ".n1", eps, pre + ".n1.f", nv)
+            if pend is None:                    # first block: normalises the stem convolution
+                s_in, o1, m1, i1 = self._nf(c0, None, P, pre + ".n1", eps, pre + ".n1.f", nv)
+            else:
+                s_in, o1, m1, i1 = self._cnf(pend, P, pre + ".n1", eps, pre + ".n1.f", nv)
             sc = fo.conv_fwd(o1, P[pre + ".shortcut.weight"], stride, 0) if blk["shortcut"] else s_in
-            c1 = fo.conv_fwd(o1, P[pre + ".conv1.weight"], stride, 1)
-            _, o2, m2, i2 = self._nf(c1, None, P, pre + ".n2", eps, pre + ".n2.f", nv)
-            c2 = fo.conv_fwd(o2, P[pre + ".conv2.weight"], 1, 1)
+            c1, o2, m2, i2 = self._cnf((o1, P[pre + ".conv1.weight"], stride, None), P, pre + ".n2", eps, pre + ".n2.f",
+                                       nv)
             saved.append((blk, s_in, o1, m1, i1, c1, o2, m2, i2))
-            cur, res = c2, sc
-        s4, y4, m4, i4 = self._nf(cur, res, P, "n4", eps, "n4.f", nv)
+            pend = (o2, P[pre + ".conv2.weight"], 1, sc)
+        s4, y4, m4, i4 = self._cnf(pend, P, "n4", eps, "n4.f", nv)
         # ---- head: global average pool -> linear -> masked CE (forward + backward) ----
         N, C, H, W = y4.shape
         Wl, bl = P["linear.weight"], P["linear.bias"]

@@ -240,6 +240,30 @@ def conv_fwd(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> torch.T
     return F.conv2d(x, w, None, stride, pad)
 
 
+CONV_STATS_FUSE = os.environ.get("HFL_CONV_STATS", "1") != "0"
+
+
+def conv_bn_act_fwd(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int, res: Optional[torch.Tensor],
+                    gamma: torch.Tensor, beta: torch.Tensor, eps: float, ws: Optional[torch.Tensor], nvalid=None,
+                    relu: bool = True):
+    """``s = conv(x, w) (+ res)``; ``y = relu(bn(s))`` with batch statistics.  Returns ``(s, y, mean, invstd)``.
+
+    When the convolution runs on the tcgen05 kernel, its epilogue adds the residual, writes ``s`` and accumulates the
+    per-channel (sum, sum of squares) of the bf16-rounded ``s`` into ``ws`` (the BN call site's persistent fp32
+    ``[2C+1]`` scratch); the norm is then a single apply pass (``bn_apply_sums``) -- no statistics kernel, no separate
+    residual add (reference block: ``src/models/resnet.py:44-50``).  Otherwise: library convolution + ``bn_act_fwd``.
+    Padding samples (``nvalid``) hold zeros in ``x`` and ``res``, so they add exactly nothing to the sums."""
+    if CONV_STATS_FUSE and ws is not None and _tc_conv_ok(x, w, stride, pad) and w.shape[0] >= 8:
+        C_ = cu.C()
+        K = w.shape[0]
+        s = C_.conv_fprop_tc(x, w, res, ws, stride)
+        y, mean, invstd, _ = C_.bn_apply_sums(s, gamma, beta, float(eps), int(K), bool(relu), ws, nvalid, int(x.shape[0]))
+        return s, y, mean, invstd
+    c = conv_fwd(x, w, stride, pad)
+    s, y, mean, invstd, _ = bn_act_fwd(c, res, gamma, beta, eps, ws=ws, nvalid=nvalid, relu=relu)
+    return s, y, mean, invstd
+
+
 # library convolutions: let cuDNN time its candidate kernels per shape (the reference does the same,
 # src/train_classifier_fed.py:19).  The heuristic picks are poor for the narrow levels (C = 4..32: e.g. a 41 us
 # wgrad2d_grouped_direct_kernel); the search runs in the warm-up steps that precede every graph capture.

@@ -346,7 +346,11 @@ def test_tcgen05_gemm_matches_torch(M, N, K):
 
 @pytest.mark.parametrize("N,C,H,K,R,stride", [(10, 64, 32, 64, 3, 1), (10, 64, 32, 128, 3, 2), (10, 128, 16, 128, 3, 1),
                                                (10, 64, 32, 128, 1, 2), (10, 256, 8, 256, 3, 1), (10, 256, 8, 512, 3, 2),
-                                               (10, 512, 4, 512, 3, 1), (3, 128, 16, 256, 1, 2), (64, 64, 32, 64, 3, 1)])
+                                               (10, 512, 4, 512, 3, 1), (3, 128, 16, 256, 1, 2), (64, 64, 32, 64, 3, 1),
+                                               # sub-64 channel counts (levels b..e): partial 64-blocks are TMA zero fill
+                                               (10, 32, 32, 32, 3, 1), (10, 16, 32, 16, 3, 1), (10, 8, 32, 8, 3, 1),
+                                               (10, 32, 32, 64, 3, 2), (10, 16, 16, 32, 1, 2), (10, 8, 32, 16, 3, 2),
+                                               (7, 128, 8, 64, 3, 1), (10, 96, 16, 160, 3, 1)])
 def test_tcgen05_conv_fprop_matches_torch(N, C, H, K, R, stride):
     cu = _cu()
     dev = torch.device("cuda")
@@ -371,6 +375,51 @@ def test_tcgen05_conv_fprop_matches_torch(N, C, H, K, R, stride):
     yf = y2.float()
     assert torch.allclose(stats[0], yf.sum(dim=(0, 2, 3)), rtol=2e-3, atol=0.5)
     assert torch.allclose(stats[1], (yf * yf).sum(dim=(0, 2, 3)), rtol=2e-3, atol=0.5)
+
+
+@pytest.mark.parametrize("N,C,H,K,stride,with_res,nvalid", [(10, 64, 32, 64, 1, True, None), (10, 64, 32, 128, 2, False, None),
+                                                            (10, 256, 8, 256, 1, True, None), (10, 512, 4, 512, 1, True, 3),
+                                                            (10, 16, 32, 16, 1, True, 7), (10, 8, 32, 16, 2, False, None),
+                                                            (10, 128, 16, 128, 1, True, 10)])
+def test_conv_bn_act_fused_matches_unfused(N, C, H, K, stride, with_res, nvalid, monkeypatch):
+    """conv -> (residual + batch statistics in the tcgen05 epilogue) -> bn_apply_sums  ==  conv -> bn_act_fwd, also
+    with a padded partial batch, over two consecutive calls (the scratch must come back zeroed)."""
+    cu = _cu()
+    from hfl_b200.ops import fused as fo
+    dev = torch.device("cuda")
+    torch.manual_seed(N + C + K)
+    monkeypatch.setattr(fo, "CONV_TC_MODE", "on")
+    x = torch.randn(N, C, H, H, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    OH = H // stride
+    res = torch.randn(N, K, OH, OH, device=dev).bfloat16().contiguous(memory_format=torch.channels_last) if with_res else None
+    nv = None
+    if nvalid is not None:
+        nv = torch.tensor([nvalid], dtype=torch.int32, device=dev)
+        x[nvalid:] = 0
+        if res is not None:
+            res[nvalid:] = 0
+    w = (torch.randn(K, C, 3, 3, device=dev) / (C * 9) ** 0.5).bfloat16().contiguous(memory_format=torch.channels_last)
+    gamma = (1 + 0.1 * torch.randn(K, device=dev)).bfloat16()
+    beta = (0.1 * torch.randn(K, device=dev)).bfloat16()
+    ws = torch.zeros(2 * K + 1, device=dev)
+    for _ in range(2):
+        s, y, m, i = fo.conv_bn_act_fwd(x, w, stride, 1, res, gamma, beta, 1e-5, ws, nv)
+        torch.cuda.synchronize()
+        assert float(ws.abs().max()) == 0.0                       # self-cleaned for the next step
+    # fp32 reference of the same op
+    nvi = N if nvalid is None else nvalid
+    c = torch.nn.functional.conv2d(x.float(), w.float(), None, stride, 1)
+    sr = c if res is None else c + res.float()
+    mean = sr[:nvi].mean(dim=(0, 2, 3))
+    var = sr[:nvi].var(dim=(0, 2, 3), unbiased=False)
+    yr = torch.relu((sr - mean.view(1, -1, 1, 1)) * torch.rsqrt(var + 1e-5).view(1, -1, 1, 1) * gamma.float().view(1, -1, 1, 1)
+                    + beta.float().view(1, -1, 1, 1))
+    yr[nvi:] = 0
+    assert float((s.float() - sr).abs().max()) < 4e-2 * max(1.0, float(sr.abs().max()))
+    assert torch.allclose(m.view(-1), mean, atol=2e-2, rtol=2e-2)
+    assert torch.allclose(i.view(-1), torch.rsqrt(var + 1e-5), atol=2e-2, rtol=2e-2)
+    assert float((y.float() - yr).abs().max()) < 6e-2 * max(1.0, float(yr.abs().max()))
+    assert float(y[nvi:].abs().max()) == 0.0 if nvi < N else True
 
 
 def test_tc_linear_forward_backward():
@@ -409,7 +458,8 @@ def test_tcgen05_gemm_general_layouts(a_mn, b_mn, M, N, K):
 
 
 @pytest.mark.parametrize("N,C,H,K,R", [(10, 64, 32, 64, 3), (10, 128, 16, 128, 3), (10, 64, 16, 128, 3), (10, 256, 8, 256, 3),
-                                        (10, 512, 4, 512, 3), (4, 128, 16, 64, 1)])
+                                        (10, 512, 4, 512, 3), (4, 128, 16, 64, 1), (10, 32, 32, 32, 3), (10, 16, 32, 16, 3),
+                                        (10, 8, 16, 8, 3), (10, 32, 16, 64, 3), (10, 64, 16, 32, 3), (6, 16, 8, 24, 1)])
 def test_tcgen05_conv_dgrad_matches_autograd(N, C, H, K, R):
     """Stride-1 data gradient on the implicit-GEMM kernel (mirrored taps, MN-major filter operand)."""
     cu = _cu()
@@ -432,7 +482,9 @@ def test_tcgen05_conv_dgrad_matches_autograd(N, C, H, K, R):
 
 @pytest.mark.parametrize("N,C,H,K,R,stride", [(10, 64, 32, 64, 3, 1), (10, 64, 32, 128, 3, 2), (10, 128, 16, 128, 3, 1),
                                                (10, 64, 32, 128, 1, 2), (10, 256, 8, 256, 3, 1), (12, 512, 4, 512, 3, 1),
-                                               (8, 256, 8, 512, 3, 2)])
+                                               (8, 256, 8, 512, 3, 2), (10, 32, 32, 32, 3, 1), (10, 16, 32, 16, 3, 1),
+                                               (10, 8, 32, 8, 3, 1), (10, 32, 32, 64, 3, 2), (10, 16, 16, 32, 1, 2),
+                                               (10, 64, 16, 32, 3, 1), (10, 8, 32, 16, 3, 2)])
 def test_tcgen05_conv_wgrad_matches_autograd(N, C, H, K, R, stride):
     """Weight gradient with both operands MN-major (pixels = reduction), split-K with fp32 atomics."""
     cu = _cu()
