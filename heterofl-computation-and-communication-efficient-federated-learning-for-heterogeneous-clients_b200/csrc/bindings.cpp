@@ -62,7 +62,13 @@ void hfl_lm_embed_bwd(const void* const*, int, const unsigned char*, float, cons
 void hfl_lm_add_ln_fwd(const void*, const void*, const void*, const void*, int, int, float, float, const long long*,
                        const long long*, unsigned, void*, void*, float*, unsigned char*, cudaStream_t);
 void hfl_lm_add_ln_bwd(const void* const*, int, const void*, const float*, const void*, const unsigned char*, float, int,
-                       int, void*, void*, float*, float*, float*, float, cudaStream_t);
+                       int, void*, void*, float*, float*, float*, float, const float*, cudaStream_t);
+int hfl_lm_vocab_supported(int, int, int);
+int hfl_lm_vocab_tiles(int);
+int hfl_lm_vocab_fwd(const void*, int, const void*, int, const void*, const unsigned char*, const long long*, int, int, int,
+                     float*, float*, int*, float*, float*, float, float*, double*, float*, int, cudaStream_t);
+int hfl_lm_vocab_bwd(const void*, int, const void*, int, const void*, const unsigned char*, const long long*, const float*,
+                     int, int, int, void*, int, float*, float*, cudaStream_t);
 void hfl_lm_gelu_drop_fwd(const void*, long, float, const long long*, const long long*, unsigned, void*, unsigned char*,
                           cudaStream_t);
 void hfl_lm_gelu_drop_bwd(const void*, const void*, const unsigned char*, float, int, int, void*, float*, float,
@@ -78,8 +84,8 @@ int hfl_head_fwd_bwd(const void*, int, int, int, const void*, const void*, int, 
 int hfl_bn_apply_sums(const void*, void*, const void*, const void*, int, float, int, int, int, float*, float*, float*,
                       float*, const int*, int, cudaStream_t);
 int hfl_conv_tc_supported(int, int, int, int, int, int, int, int);
-int hfl_conv_fprop_tc(const void*, const void*, void*, const void*, float*, int, int, int, int, int, int, int, int,
-                      cudaStream_t);
+int hfl_conv_fprop_tc(const void*, const void*, void*, const void*, float*, const int*, int, int, int, int, int, int, int,
+                      int, cudaStream_t);
 int hfl_gemm_bf16_general(const void*, int, int, const void*, int, int, void*, int, int, float, int, int, int, int,
                           cudaStream_t);
 int hfl_gemm_general_splits(int, int, int);
@@ -634,8 +640,8 @@ static float* f32p(const torch::Tensor& t, int64_t n) {
 struct DyList {
   const void* p[4];
   int n;
-  DyList(const std::vector<torch::Tensor>& dys, int64_t numel) {
-    TORCH_CHECK(!dys.empty() && dys.size() <= 4, "1..4 gradient branches");
+  DyList(const std::vector<torch::Tensor>& dys, int64_t numel, bool allow_empty = false) {
+    TORCH_CHECK((allow_empty || !dys.empty()) && dys.size() <= 4, "1..4 gradient branches");
     n = (int)dys.size();
     for (int i = 0; i < 4; ++i) p[i] = nullptr;
     for (int i = 0; i < n; ++i) { check_bf(dys[i], "dy"); TORCH_CHECK(dys[i].numel() == numel); p[i] = dys[i].data_ptr(); }
@@ -700,10 +706,17 @@ std::vector<torch::Tensor> lm_add_ln_fwd(c10::optional<torch::Tensor> x, torch::
 // returns (dz, dh); dh aliases dz when there is no dropout
 std::vector<torch::Tensor> lm_add_ln_bwd(std::vector<torch::Tensor> dys, torch::Tensor xhat, torch::Tensor rstd,
                                          torch::Tensor gamma, torch::Tensor dmask, double p_drop, torch::Tensor dgamma,
-                                         torch::Tensor dbeta, c10::optional<torch::Tensor> dbias, double bias_alpha) {
+                                         torch::Tensor dbeta, c10::optional<torch::Tensor> dbias, double bias_alpha,
+                                         c10::optional<torch::Tensor> dy_f32) {
   check_bf(xhat, "xhat"); check_bf(gamma, "gamma");
   const int M = xhat.size(0), E = xhat.size(1);
-  DyList dl(dys, (int64_t)M * E);
+  DyList dl(dys, (int64_t)M * E, dy_f32.has_value());
+  const float* dyf = nullptr;
+  if (dy_f32.has_value()) {   // one more gradient branch, fp32 (the fused vocabulary head's dX accumulator)
+    TORCH_CHECK(dy_f32->is_cuda() && dy_f32->scalar_type() == torch::kFloat32 && dy_f32->is_contiguous() &&
+                dy_f32->numel() == (int64_t)M * E);
+    dyf = dy_f32->data_ptr<float>();
+  }
   TORCH_CHECK(E <= hfl_lm_max_e());
   TORCH_CHECK(p_drop <= 0 || dmask.numel() == (int64_t)M * E);
   c10::cuda::CUDAGuard guard(xhat.device());
@@ -712,9 +725,61 @@ std::vector<torch::Tensor> lm_add_ln_bwd(std::vector<torch::Tensor> dys, torch::
   hfl_lm_add_ln_bwd(dl.p, dl.n, xhat.data_ptr(), rstd.data_ptr<float>(), gamma.data_ptr(),
                     p_drop > 0 ? dmask.data_ptr<uint8_t>() : nullptr, (float)p_drop, M, E, dz.data_ptr(),
                     p_drop > 0 ? dh.data_ptr() : nullptr, f32p(dgamma, E), f32p(dbeta, E),
-                    dbias.has_value() ? f32p(*dbias, E) : nullptr, (float)bias_alpha, cur_stream());
+                    dbias.has_value() ? f32p(*dbias, E) : nullptr, (float)bias_alpha, dyf, cur_stream());
   check_launch();
   return {dz, dh};
+}
+
+// ---- fused vocabulary head (csrc/lm_vocab_tcgen05.cu) ----------------------------------------------------------
+bool lm_vocab_supported(int64_t M, int64_t V, int64_t E) { return hfl_lm_vocab_supported((int)M, (int)V, (int)E) == 0; }
+
+// d: [M, E] bf16 (decoder LayerNorm output), W: [V, E] bf16, b: [V] bf16, target: [M] int64, mask: uint8 [V] (optional).
+// Returns [loss (fp32 [1]), dW (bf16 [V, E]), dX (fp32 [M, E])]; dbias (fp32 [V]) is accumulated in place.  train = false:
+// loss / meter only.
+std::vector<torch::Tensor> lm_vocab_head(torch::Tensor d, torch::Tensor W, torch::Tensor b, torch::Tensor target,
+                                         c10::optional<torch::Tensor> mask, double n_weight,
+                                         c10::optional<torch::Tensor> meter, c10::optional<torch::Tensor> dbias, bool train) {
+  check_bf(d, "d"); check_bf(W, "W"); check_bf(b, "b");
+  TORCH_CHECK(d.dim() == 2 && W.dim() == 2 && d.size(1) == W.size(1) && b.numel() == W.size(0) && b.is_contiguous());
+  TORCH_CHECK(d.stride(1) == 1 && W.stride(1) == 1 && d.stride(0) % 8 == 0 && W.stride(0) % 8 == 0);
+  TORCH_CHECK(((uintptr_t)d.data_ptr() & 15) == 0 && ((uintptr_t)W.data_ptr() & 15) == 0);
+  const int M = d.size(0), E = d.size(1), V = W.size(0);
+  TORCH_CHECK(hfl_lm_vocab_supported(M, V, E) == 0, "lm_vocab_head: unsupported shape");
+  TORCH_CHECK(target.is_cuda() && target.scalar_type() == torch::kInt64 && target.is_contiguous() && target.numel() == M);
+  const unsigned char* mp = nullptr;
+  if (mask.has_value()) {
+    TORCH_CHECK(mask->is_cuda() && mask->scalar_type() == torch::kUInt8 && mask->numel() >= V);
+    mp = mask->data_ptr<unsigned char>();
+  }
+  double* mt = nullptr;
+  if (meter.has_value()) { TORCH_CHECK(meter->scalar_type() == torch::kFloat64 && meter->numel() >= 4); mt = meter->data_ptr<double>(); }
+  c10::cuda::CUDAGuard guard(d.device());
+  const int T = hfl_lm_vocab_tiles(V);
+  auto fopt = torch::TensorOptions().dtype(torch::kFloat32).device(d.device());
+  auto part = torch::empty({2, M, T}, fopt);
+  auto parg = torch::empty({M, T}, fopt.dtype(torch::kInt32));
+  auto rowbuf = torch::empty({2, M}, fopt);          // target logit, log-sum-exp
+  auto loss = torch::empty({1}, fopt);
+  torch::Tensor dW, dX;
+  if (train) {
+    dW = torch::empty({V, E}, d.options());
+    dX = torch::empty({M, E}, fopt);
+  }
+  const long long* tp = (const long long*)target.data_ptr<int64_t>();
+  int e = hfl_lm_vocab_fwd(d.data_ptr(), (int)d.stride(0), W.data_ptr(), (int)W.stride(0), b.data_ptr(), mp, tp, M, V, E,
+                           part.data_ptr<float>(), part.data_ptr<float>() + (int64_t)M * T, parg.data_ptr<int>(),
+                           rowbuf.data_ptr<float>(), rowbuf.data_ptr<float>() + M, (float)n_weight, loss.data_ptr<float>(),
+                           mt, train ? dX.data_ptr<float>() : nullptr, train ? M * E : 0, cur_stream());
+  TORCH_CHECK(e == 0, "lm_vocab_fwd failed with code ", e);
+  if (train) {
+    TORCH_CHECK(dbias.has_value() && dbias->scalar_type() == torch::kFloat32 && dbias->numel() >= V && dbias->is_contiguous());
+    e = hfl_lm_vocab_bwd(d.data_ptr(), (int)d.stride(0), W.data_ptr(), (int)W.stride(0), b.data_ptr(), mp, tp,
+                         rowbuf.data_ptr<float>() + M, M, V, E, dW.data_ptr(), E, dbias->data_ptr<float>(),
+                         dX.data_ptr<float>(), cur_stream());
+    TORCH_CHECK(e == 0, "lm_vocab_bwd failed with code ", e);
+  }
+  check_launch();
+  return {loss, dW, dX};
 }
 
 std::vector<torch::Tensor> lm_gelu_drop_fwd(torch::Tensor u, double p_drop, torch::Tensor seed, torch::Tensor step,
@@ -792,7 +857,7 @@ bool conv_tc_supported(int64_t N, int64_t H, int64_t W, int64_t C, int64_t Kout,
 // x: [N, C, H, W] channels-last bf16; w: [K, C, R, S] with channels-last strides (physically K,R,S,C);
 // residual: like the output (optional); stats: fp32 [2, K] accumulated in place (optional).  padding = R/2.
 torch::Tensor conv_fprop_tc(torch::Tensor x, torch::Tensor w, c10::optional<torch::Tensor> residual,
-                            c10::optional<torch::Tensor> stats, int64_t stride) {
+                            c10::optional<torch::Tensor> stats, int64_t stride, c10::optional<torch::Tensor> nvalid) {
   CHECK_CUDA_T(x); CHECK_CUDA_T(w);
   TORCH_CHECK(x.dim() == 4 && w.dim() == 4 && x.scalar_type() == torch::kBFloat16 && w.scalar_type() == torch::kBFloat16);
   TORCH_CHECK(x.is_contiguous(torch::MemoryFormat::ChannelsLast), "conv_fprop_tc: x must be channels-last");
@@ -813,7 +878,9 @@ torch::Tensor conv_fprop_tc(torch::Tensor x, torch::Tensor w, c10::optional<torc
   }
   float* sp = nullptr;
   if (stats.has_value()) { TORCH_CHECK(stats->scalar_type() == torch::kFloat32 && stats->numel() >= 2 * K && stats->is_contiguous()); sp = stats->data_ptr<float>(); }
-  int e = hfl_conv_fprop_tc(x.data_ptr(), w.data_ptr(), y.data_ptr(), rp, sp, N, H, W, C, K, R, S, (int)stride, cur_stream());
+  const int* nvp = nullptr;   // int32 [1] on the device: samples >= *nvalid are padding (zero outputs, no statistics)
+  if (nvalid.has_value()) { TORCH_CHECK(nvalid->is_cuda() && nvalid->scalar_type() == torch::kInt32); nvp = nvalid->data_ptr<int>(); }
+  int e = hfl_conv_fprop_tc(x.data_ptr(), w.data_ptr(), y.data_ptr(), rp, sp, nvp, N, H, W, C, K, R, S, (int)stride, cur_stream());
   TORCH_CHECK(e == 0, "conv_fprop_tc failed with code ", e);
   return y;
 }
@@ -1018,7 +1085,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lm_embed_fwd", &lm_embed_fwd);
   m.def("lm_embed_bwd", &lm_embed_bwd);
   m.def("lm_add_ln_fwd", &lm_add_ln_fwd);
-  m.def("lm_add_ln_bwd", &lm_add_ln_bwd);
+  m.def("lm_add_ln_bwd", &lm_add_ln_bwd, py::arg("dys"), py::arg("xhat"), py::arg("rstd"), py::arg("gamma"), py::arg("dmask"),
+        py::arg("p_drop"), py::arg("dgamma"), py::arg("dbeta"), py::arg("dbias"), py::arg("bias_alpha"),
+        py::arg("dy_f32") = py::none());
+  m.def("lm_vocab_supported", &lm_vocab_supported);
+  m.def("lm_vocab_head", &lm_vocab_head);
   m.def("lm_gelu_drop_fwd", &lm_gelu_drop_fwd);
   m.def("lm_gelu_drop_bwd", &lm_gelu_drop_bwd);
   m.def("lm_colsum", &lm_colsum);
@@ -1028,7 +1099,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("alpha_v"), py::arg("scale_dv") = false);
   m.def("lm_max_e", &hfl_lm_max_e);
   m.def("conv_tc_supported", &conv_tc_supported);
-  m.def("conv_fprop_tc", &conv_fprop_tc);
+  m.def("conv_fprop_tc", &conv_fprop_tc, py::arg("x"), py::arg("w"), py::arg("residual"), py::arg("stats"), py::arg("stride"),
+        py::arg("nvalid") = py::none());
   m.def("conv_dgrad_tc", &conv_dgrad_tc);
   m.def("conv_wgrad_tc", &conv_wgrad_tc);
   m.def("conv_wgrad_tc_supported", &conv_wgrad_tc_supported);

@@ -86,7 +86,7 @@ template <int BLOCK_N, bool DGRAD, bool HAS_RES, bool HAS_STATS>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                           __nv_bfloat16* __restrict__ Y, const __nv_bfloat16* __restrict__ residual,
-                          float* __restrict__ stats /* [2, Kout] or null */, const ConvGeom g) {
+                          float* __restrict__ stats /* [2, Kout] or null */, const int* __restrict__ nvalid, const ConvGeom g) {
   extern __shared__ uint8_t smem_raw[];
   using S = ConvSmem<BLOCK_N>;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -209,7 +209,11 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     const int t = m / g.bw;
     const int h_l = t % g.bh, n_l = t / g.bh;
     const int n = n0 + n_l, oh = oh0 + h_l;
-    const bool ok = (n < g.N) && (oh < g.OH);
+    // nvalid (training step with a padded partial batch): samples >= *nvalid are padding -- their outputs are written
+    // as zeros (whatever the inputs / residual hold there) and stay out of the statistics
+    const int nlim = nvalid ? min(g.N, __ldg(nvalid)) : g.N;
+    const bool inr = (n < g.N) && (oh < g.OH);
+    const bool ok = inr && (n < nlim);
     const size_t pix = ((size_t)n * g.OH + oh) * g.OW + w_l;
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -222,9 +226,9 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
       float f[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = (ok && j < ncol) ? __uint_as_float(v[j]) : 0.f;
-      if (ok) {
+      if (inr) {
         __nv_bfloat16* dst = Y + pix * g.Kout + col0;
-        if (HAS_RES) {
+        if (HAS_RES && ok) {
           const uint4* rp = reinterpret_cast<const uint4*>(residual + pix * g.Kout + col0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -284,6 +288,7 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
       const int col = n_blk * BLOCK_N + cg * 4;
       const bool col_ok = col < g.Kout;                       // K_out is a multiple of 8: the 4 columns share the answer
       const uint32_t stg0 = smem_u32(smem);
+      const int nlim2 = nvalid ? min(g.N, __ldg(nvalid)) : g.N;
       float sx[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
       for (int rr = t / CG; rr < rpc; rr += 128 / CG) {
         const int m = row0 + rr;
@@ -299,6 +304,10 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         const int n = n0 + n_l, oh = oh0 + h_l;
         if (!((n < g.N) && (oh < g.OH) && col_ok)) continue;
         const size_t pix = ((size_t)n * g.OH + oh) * g.OW + w_l;
+        if (n >= nlim2) {                                     // padding sample: zeros, no statistics
+          *reinterpret_cast<uint2*>(Y + pix * g.Kout + col) = make_uint2(0u, 0u);
+          continue;
+        }
         if (HAS_RES) {
           const uint2 u = *reinterpret_cast<const uint2*>(residual + pix * g.Kout + col);
           const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -357,7 +366,7 @@ static int make_tmap_filter_bf16(CUtensorMap* m, const void* Wt, int C, int taps
 
 template <int BLOCK_N, bool DGRAD, bool HAS_RES, bool HAS_STATS>
 static int launch_conv_v(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, const void* residual, float* stats,
-                         const ConvGeom& g, int tiles_m, int n_tiles, int ksplit, cudaStream_t stream) {
+                         const int* nvalid, const ConvGeom& g, int tiles_m, int n_tiles, int ksplit, cudaStream_t stream) {
   auto kern = conv_fprop_tcgen05_kernel<BLOCK_N, DGRAD, HAS_RES, HAS_STATS>;
   constexpr int smem = ConvSmem<BLOCK_N>::TOTAL;
   static bool configured = false;
@@ -387,15 +396,24 @@ static int launch_conv_v(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, 
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tx, tw, (__nv_bfloat16*)Y, (const __nv_bfloat16*)residual, stats, g);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tx, tw, (__nv_bfloat16*)Y, (const __nv_bfloat16*)residual, stats, nvalid, g);
   count_launch();
   return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }
 
 // split-K factor of a tile grid: only when the grid leaves most SMs idle and the reduction is long; powers of two
-// (the cluster splits the 128 tile rows evenly), every split keeps >= 4 k-blocks.  HFL_CONV_KSPLIT=1 disables.
+// (the cluster splits the 128 tile rows evenly), every split keeps >= 4 k-blocks.
+// Policy (measured, profiles/pdl_conv_ab.md): splitting shortens the isolated step (the 8-GPU regime, one or two clients
+// per GPU, chain-bound) but on one GPU, where 10-16 clients already fill the SMs, the 8x larger grids of 200 KB CTAs
+// cost more than they save (round 516 vs 480 ms).  Default: on from 4 ranks up, off below; HFL_CONV_KSPLIT=<cap>
+// overrides (1 = off).
 static int conv_ksplit(int tiles, int num_k) {
-  static const int cap = []() { const char* e = getenv("HFL_CONV_KSPLIT"); return e ? atoi(e) : 8; }();
+  static const int cap = []() {
+    const char* e = getenv("HFL_CONV_KSPLIT");
+    if (e) return atoi(e);
+    const char* w = getenv("WORLD_SIZE");
+    return (w && atoi(w) >= 4) ? 8 : 1;
+  }();
   int ks = 1;
   while (ks * 2 <= cap && tiles * ks * 2 <= 148 && num_k / (ks * 2) >= 4) ks *= 2;
   return ks;
@@ -403,17 +421,17 @@ static int conv_ksplit(int tiles, int num_k) {
 
 template <int BLOCK_N, bool DGRAD = false>
 static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, const void* residual, float* stats,
-                       const ConvGeom& g, int tiles_m, int n_tiles, cudaStream_t stream) {
+                       const int* nvalid, const ConvGeom& g, int tiles_m, int n_tiles, cudaStream_t stream) {
   if (residual != nullptr && (reinterpret_cast<uintptr_t>(residual) & 15) != 0) return -3;
   if ((reinterpret_cast<uintptr_t>(Y) & 15) != 0) return -3;
   const int num_k = g.R * g.S * ((g.C + CV_BLOCK_K - 1) / CV_BLOCK_K);
   const int ks = conv_ksplit(tiles_m * n_tiles, num_k);
   if (residual != nullptr) {
-    if (stats != nullptr) return launch_conv_v<BLOCK_N, DGRAD, true, true>(tx, tw, Y, residual, stats, g, tiles_m, n_tiles, ks, stream);
-    return launch_conv_v<BLOCK_N, DGRAD, true, false>(tx, tw, Y, residual, stats, g, tiles_m, n_tiles, ks, stream);
+    if (stats != nullptr) return launch_conv_v<BLOCK_N, DGRAD, true, true>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, ks, stream);
+    return launch_conv_v<BLOCK_N, DGRAD, true, false>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, ks, stream);
   }
-  if (stats != nullptr) return launch_conv_v<BLOCK_N, DGRAD, false, true>(tx, tw, Y, residual, stats, g, tiles_m, n_tiles, ks, stream);
-  return launch_conv_v<BLOCK_N, DGRAD, false, false>(tx, tw, Y, residual, stats, g, tiles_m, n_tiles, ks, stream);
+  if (stats != nullptr) return launch_conv_v<BLOCK_N, DGRAD, false, true>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, ks, stream);
+  return launch_conv_v<BLOCK_N, DGRAD, false, false>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, ks, stream);
 }
 
 // 0 if this problem can run on the tcgen05 path
@@ -431,8 +449,9 @@ extern "C" int hfl_conv_tc_supported(int N, int H, int W, int C, int Kout, int R
   return 0;
 }
 
-extern "C" int hfl_conv_fprop_tc(const void* X, const void* Wt, void* Y, const void* residual, float* stats, int N,
-                                 int H, int W, int C, int Kout, int R, int S, int stride, cudaStream_t stream) {
+extern "C" int hfl_conv_fprop_tc(const void* X, const void* Wt, void* Y, const void* residual, float* stats,
+                                 const int* nvalid, int N, int H, int W, int C, int Kout, int R, int S, int stride,
+                                 cudaStream_t stream) {
   if (hfl_conv_tc_supported(N, H, W, C, Kout, R, S, stride) != 0) return -2;
   ConvGeom g;
   g.N = N; g.H = H; g.W = W; g.C = C; g.Kout = Kout; g.R = R; g.S = S; g.stride = stride; g.pad = R / 2;
@@ -454,9 +473,9 @@ extern "C" int hfl_conv_fprop_tc(const void* X, const void* Wt, void* Y, const v
   r = make_tmap_filter_bf16(&tw, Wt, C, R * S, Kout, CV_BLOCK_K, block_n);
   if (r) return 2000 + r;
   const int n_tiles = (Kout + block_n - 1) / block_n;
-  if (block_n == 128) return launch_conv<128>(tx, tw, Y, residual, stats, g, tiles_m, n_tiles, stream);
-  if (block_n == 64) return launch_conv<64>(tx, tw, Y, residual, stats, g, tiles_m, n_tiles, stream);
-  return launch_conv<32>(tx, tw, Y, residual, stats, g, tiles_m, n_tiles, stream);
+  if (block_n == 128) return launch_conv<128>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, stream);
+  if (block_n == 64) return launch_conv<64>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, stream);
+  return launch_conv<32>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, stream);
 }
 
 // Stride-1 data gradient: dX[N,H,W,C] from dY[N,H,W,Kout] and the K,R,S,C filter.  `residual` is an optional tensor
@@ -484,8 +503,8 @@ extern "C" int hfl_conv_dgrad_tc(const void* dY, const void* Wt, void* dX, const
   r = make_tmap_filter_bf16(&tw, Wt, C, R * S, Kout, 64, CV_BLOCK_K);
   if (r) return 2000 + r;
   const int n_tiles = (C + block_n - 1) / block_n;
-  if (block_n == 128) return launch_conv<128, true>(tx, tw, dX, residual, nullptr, g, tiles_m, n_tiles, stream);
-  return launch_conv<64, true>(tx, tw, dX, residual, nullptr, g, tiles_m, n_tiles, stream);
+  if (block_n == 128) return launch_conv<128, true>(tx, tw, dX, residual, nullptr, nullptr, g, tiles_m, n_tiles, stream);
+  return launch_conv<64, true>(tx, tw, dX, residual, nullptr, nullptr, g, tiles_m, n_tiles, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------

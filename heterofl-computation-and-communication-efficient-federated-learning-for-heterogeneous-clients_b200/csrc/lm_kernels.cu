@@ -104,7 +104,7 @@ lm_embed_fwd_kernel(const long long* __restrict__ tok, const bf16* __restrict__ 
 // Shared LayerNorm-backward core: g = dy * gamma; dz = rstd * (g - mean(g) - xhat * mean(g * xhat)).
 // Column partials (dgamma, dbeta [, dbias]) are reduced across the CTA's warps in shared memory, then one atomicAdd
 // per column per CTA.
-struct DyParts { const bf16* p[4]; int n; };
+struct DyParts { const bf16* p[4]; int n; const float* f; };   // up to 4 bf16 branches + one optional fp32 branch
 
 __global__ void __launch_bounds__(LN_WARPS * 32)
 lm_embed_bwd_kernel(DyParts dy, const uint8_t* __restrict__ dmask, float p_drop, const bf16* __restrict__ xhat,
@@ -127,6 +127,7 @@ lm_embed_bwd_kernel(DyParts dy, const uint8_t* __restrict__ dmask, float p_drop,
       const size_t o = (size_t)m * E + c;
       float d = 0.f;
       for (int k = 0; k < dy.n; ++k) d += __bfloat162float(dy.p[k][o]);
+      if (dy.f != nullptr) d += dy.f[o];
       if (p_drop > 0.f) d = dmask[o] ? d * keep_scale : 0.f;
       dyv[i] = d;
       xh[i] = __bfloat162float(xhat[o]);
@@ -236,6 +237,7 @@ lm_add_ln_bwd_kernel(DyParts dy, const bf16* __restrict__ xhat, const float* __r
       const size_t o = (size_t)m * E + c;
       float d = 0.f;
       for (int k = 0; k < dy.n; ++k) d += __bfloat162float(dy.p[k][o]);
+      if (dy.f != nullptr) d += dy.f[o];
       dyv[i] = d;
       xh[i] = __bfloat162float(xhat[o]);
       const float g = d * __bfloat162float(gamma[c]);
@@ -538,9 +540,10 @@ extern "C" void hfl_lm_embed_fwd(const long long* tok, const void* emb, const vo
   count_launch();
 }
 
-static DyParts make_parts(const void* const* dy, int n) {
+static DyParts make_parts(const void* const* dy, int n, const float* f = nullptr) {
   DyParts d;
   d.n = n;
+  d.f = f;
   for (int i = 0; i < 4; ++i) d.p[i] = (const bf16*)(i < n ? dy[i] : nullptr);
   return d;
 }
@@ -567,9 +570,9 @@ extern "C" void hfl_lm_add_ln_fwd(const void* x, const void* h, const void* gamm
 extern "C" void hfl_lm_add_ln_bwd(const void* const* dy, int n_dy, const void* xhat, const float* rstd,
                                   const void* gamma, const unsigned char* dmask, float p_drop, int M, int E, void* dz,
                                   void* dh, float* dgamma, float* dbeta, float* dbias, float bias_alpha,
-                                  cudaStream_t st) {
+                                  const float* dy_f32, cudaStream_t st) {
   launch_k(lm_add_ln_bwd_kernel, dim3((M + LN_WARPS - 1) / LN_WARPS), dim3(LN_WARPS * 32), 0, st, 
-      make_parts(dy, n_dy), (const bf16*)xhat, rstd, (const bf16*)gamma, dmask, p_drop, M, E, (bf16*)dz, (bf16*)dh,
+      make_parts(dy, n_dy, dy_f32), (const bf16*)xhat, rstd, (const bf16*)gamma, dmask, p_drop, M, E, (bf16*)dz, (bf16*)dh,
       dgamma, dbeta, dbias, bias_alpha);
   count_launch();
 }

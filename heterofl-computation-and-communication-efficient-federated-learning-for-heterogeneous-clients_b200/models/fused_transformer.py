@@ -70,6 +70,9 @@ class FusedTransformer:
         # opt-in reduced precision: forward GEMMs of the feed-forward blocks in MXFP8 (e4m3 + ue8m0 block scales,
         # csrc/gemm_mxfp8_tcgen05.cu); backward stays bf16.  Off by default: bench.py's dtype is bf16.
         self.fp8 = os.environ.get("HFL_LM_FP8", "0") == "1"
+        # fused vocabulary head (csrc/lm_vocab_tcgen05.cu): decoder.linear2 + label mask + cross-entropy forward and
+        # backward in three launches, no [tokens, vocabulary] tensor in memory
+        self.vocab_fused = os.environ.get("HFL_LM_VOCAB_FUSED", "1") != "0"
         self.keep_last = False                     # numerics tests: keep the forward intermediates of the last step
         self.last: Dict = {}
 
@@ -186,23 +189,33 @@ class FusedTransformer:
         dg, _ = C.lm_gelu_drop_fwd(du, 0.0, seed_t, step_t, 0)
         d, xhd, rstdd, _ = C.lm_add_ln_fwd(None, dg, P["decoder.norm1.weight"], P["decoder.norm1.bias"], LN_EPS, 0.0,
                                            seed_t, step_t, 0)
-        Vp = (V + 7) // 8 * 8                       # row-padded logits: 16-byte row strides for the TMA maps
-        buf = self._logits.get(M)
-        if buf is None:
-            buf = torch.zeros(M, Vp, dtype=torch.bfloat16, device=tok.device)
-            self._logits[M] = buf
-        logits = self._lin(d, P["decoder.linear2.weight"], P["decoder.linear2.bias"], 1.0, out=buf[:, :V])
         n_weight = float(N) if meter is None else float(meter[1])
-        loss, dlogits = C.masked_ce(logits, tok, label_mask, n_weight, None if meter is None else meter[0], True)
-        if self.keep_last:
-            self.last = dict(src=src, dm0=dm0, saved=saved, logits=logits, x_final=x)
+        W2, b2 = P["decoder.linear2.weight"], P["decoder.linear2.bias"]
+        if self.vocab_fused and C.lm_vocab_supported(M, V, E) and _aligned(d) and _aligned(W2) and b2.is_contiguous():
+            # ---- fused head: logits live only in TMEM; loss, dW2, db2 and dX come out of three launches ----------
+            loss, G["decoder.linear2.weight"], dd32 = C.lm_vocab_head(
+                d, W2, b2, tok, label_mask, n_weight, None if meter is None else meter[0], sg["decoder.linear2.bias"], True)
+            if self.keep_last:
+                self.last = dict(src=src, dm0=dm0, saved=saved, logits=None, x_final=x)
+            dzd, _ = C.lm_add_ln_bwd([], xhd, rstdd, P["decoder.norm1.weight"], dm0, 0.0, sg["decoder.norm1.weight"],
+                                     sg["decoder.norm1.bias"], None, 0.0, dd32)
+        else:
+            Vp = (V + 7) // 8 * 8                       # row-padded logits: 16-byte row strides for the TMA maps
+            buf = self._logits.get(M)
+            if buf is None:
+                buf = torch.zeros(M, Vp, dtype=torch.bfloat16, device=tok.device)
+                self._logits[M] = buf
+            logits = self._lin(d, W2, b2, 1.0, out=buf[:, :V])
+            loss, dlogits = C.masked_ce(logits, tok, label_mask, n_weight, None if meter is None else meter[0], True)
+            if self.keep_last:
+                self.last = dict(src=src, dm0=dm0, saved=saved, logits=logits, x_final=x)
 
-        # ---- backward --------------------------------------------------------------------------------------
-        G["decoder.linear2.weight"] = self._dw(dlogits, d, 1.0)
-        C.lm_colsum(dlogits, 1.0, sg["decoder.linear2.bias"])
-        dd = self._dx(dlogits, P["decoder.linear2.weight"], 1.0)
-        dzd, _ = C.lm_add_ln_bwd([dd], xhd, rstdd, P["decoder.norm1.weight"], dm0, 0.0, sg["decoder.norm1.weight"],
-                                 sg["decoder.norm1.bias"], None, 0.0)
+            # ---- backward --------------------------------------------------------------------------------------
+            G["decoder.linear2.weight"] = self._dw(dlogits, d, 1.0)
+            C.lm_colsum(dlogits, 1.0, sg["decoder.linear2.bias"])
+            dd = self._dx(dlogits, W2, 1.0)
+            dzd, _ = C.lm_add_ln_bwd([dd], xhd, rstdd, P["decoder.norm1.weight"], dm0, 0.0, sg["decoder.norm1.weight"],
+                                     sg["decoder.norm1.bias"], None, 0.0)
         ddu = C.lm_gelu_drop_bwd(dzd, du, dm0, 0.0, sg["decoder.linear1.bias"], inv)
         G["decoder.linear1.weight"] = self._dw(ddu, x, inv)
         parts = [self._dx(ddu, P["decoder.linear1.weight"], inv)]

@@ -212,7 +212,7 @@ def maxpool2_bwd(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
 # (C_in = 64, batch-10 tiles) | "train" = every qualifying shape of a training-sized batch (<= CONV_TC_MAX_PIXELS
 # output pixels), any channel count: keeps the train step on our own kernels so that consecutive launches chain
 # through programmatic dependent launch; the large-batch sBN / test passes stay on the library.
-CONV_TC_MODE = os.environ.get("HFL_CONV_TC", "auto")
+CONV_TC_MODE = os.environ.get("HFL_CONV_TC", "train")
 CONV_TC_MAX_PIXELS = int(os.environ.get("HFL_CONV_TC_MAX_PIXELS", "20480"))
 
 
@@ -252,11 +252,12 @@ def conv_bn_act_fwd(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int, res
     per-channel (sum, sum of squares) of the bf16-rounded ``s`` into ``ws`` (the BN call site's persistent fp32
     ``[2C+1]`` scratch); the norm is then a single apply pass (``bn_apply_sums``) -- no statistics kernel, no separate
     residual add (reference block: ``src/models/resnet.py:44-50``).  Otherwise: library convolution + ``bn_act_fwd``.
-    Padding samples (``nvalid``) hold zeros in ``x`` and ``res``, so they add exactly nothing to the sums."""
+    Padding samples (``nvalid``): the epilogue writes zeros there and keeps them out of the sums, whatever ``x`` and
+    ``res`` hold in those rows."""
     if CONV_STATS_FUSE and ws is not None and _tc_conv_ok(x, w, stride, pad) and w.shape[0] >= 8:
         C_ = cu.C()
         K = w.shape[0]
-        s = C_.conv_fprop_tc(x, w, res, ws, stride)
+        s = C_.conv_fprop_tc(x, w, res, ws, stride, nvalid)
         y, mean, invstd, _ = C_.bn_apply_sums(s, gamma, beta, float(eps), int(K), bool(relu), ws, nvalid, int(x.shape[0]))
         return s, y, mean, invstd
     c = conv_fwd(x, w, stride, pad)
@@ -275,7 +276,7 @@ if os.environ.get("HFL_CUDNN_BENCHMARK", _default_bench) != "0":
     torch.backends.cudnn.benchmark = True
 
 # backward convolutions on the tcgen05 kernels: "off" | "on" (dgrad + wgrad) | "wgrad" (weight gradient only)
-CONV_BWD_TC_MODE = os.environ.get("HFL_CONV_BWD_TC", "wgrad")
+CONV_BWD_TC_MODE = os.environ.get("HFL_CONV_BWD_TC", "on")
 
 
 def _tc_bwd_ok(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> bool:

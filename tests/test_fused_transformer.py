@@ -343,3 +343,51 @@ def test_grouped_qkv_gemms(M, E):
     dx = C.gemm_grouped(dy, False, W, True, None, [1.0], True)[0]
     ref = sum(d.float() @ w.float() for d, w in zip(dy, W))
     assert torch.allclose(dx.float(), ref, atol=0.03 * float(ref.abs().max()) + 1e-2, rtol=3e-2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,E,V,masked", [(64, 256, 33278, True), (128, 128, 1000, True), (40, 64, 515, False),
+                                           (64, 256, 4096, False)])
+def test_fused_vocab_head_matches_torch(M, E, V, masked):
+    """decoder.linear2 + zero-fill label mask + cross-entropy, forward and backward, without materialised logits
+    (csrc/lm_vocab_tcgen05.cu) against the fp32 PyTorch composition of the same ops (reference
+    src/models/transformer.py:125-129,154-161)."""
+    cu = _cu()
+    C = cu.C()
+    dev = torch.device("cuda")
+    torch.manual_seed(M + E + V)
+    assert C.lm_vocab_supported(M, V, E)
+    d = torch.randn(M, E, device=dev).bfloat16()
+    W = (torch.randn(V, E, device=dev) / E ** 0.5).bfloat16()
+    b = (0.1 * torch.randn(V, device=dev)).bfloat16()
+    tgt = torch.randint(0, V, (M,), device=dev)
+    mask = None
+    if masked:
+        mask = (torch.rand(V, device=dev) < 0.6).to(torch.uint8)
+        mask[tgt[: M // 2]] = 1                         # half of the targets are certainly unmasked
+    meter = torch.zeros(4, dtype=torch.float64, device=dev)
+    dbias = torch.zeros(V, device=dev)
+    loss, dW, dX = C.lm_vocab_head(d, W, b, tgt, mask, float(M), meter, dbias, True)
+    torch.cuda.synchronize()
+    # fp32 reference
+    d32, W32, b32 = (t.float().requires_grad_(True) for t in (d, W, b))
+    z = d32 @ W32.t() + b32
+    if mask is not None:
+        z = z.masked_fill(mask.bool().view(1, -1) == 0, 0.0)
+    ref = F.cross_entropy(z, tgt)
+    ref.backward()
+    assert float(loss) == pytest.approx(float(ref), rel=2e-3, abs=2e-3)
+    assert float(meter[0]) == pytest.approx(float(ref) * M, rel=2e-3, abs=2e-3)
+    assert float(meter[1]) == float((z.argmax(1) == tgt).sum())
+    assert float(meter[2]) == float(M)
+
+    def close(a, r, what):
+        err = float((a.float() - r).abs().max())
+        assert err < 2e-2 * max(float(r.abs().max()), 1e-6) + 1e-6, (what, err, float(r.abs().max()))
+    close(dW, W32.grad, "dW")
+    close(dX, d32.grad, "dX")
+    close(dbias, b32.grad, "dbias")
+    # evaluation mode: loss / meter only
+    meter2 = torch.zeros(4, dtype=torch.float64, device=dev)
+    loss2, _, _ = C.lm_vocab_head(d, W, b, tgt, mask, float(M), meter2, None, False)
+    assert float(loss2) == pytest.approx(float(loss), rel=1e-5)
