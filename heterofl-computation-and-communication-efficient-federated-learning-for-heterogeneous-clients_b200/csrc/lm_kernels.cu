@@ -20,6 +20,7 @@
 // Random bits: every draw is hash(seed, step, site, element) -- `seed`/`step` are device scalars (the step counter is
 // bumped inside the captured CUDA graph), so a replayed graph draws fresh masks every step.  Masks are written out
 // (uint8) for the backward pass and for the numerics tests.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace hfl {
@@ -599,8 +600,19 @@ extern "C" void hfl_lm_colsum(const void* x, int M, int N, int ld, float alpha, 
   count_launch();
 }
 
+// tensor-core (mma.sync) attention kernels, csrc/lm_attn_mma.cu; HFL_LM_ATTN_MMA=0 selects the CUDA-core kernels above
+extern "C" void hfl_lm_attn_fwd_mma(const void*, const void*, const void*, int, int, int, int, float, void*, void*,
+                                    cudaStream_t);
+extern "C" int hfl_lm_attn_bwd_mma(const void*, const void*, const void*, const void*, const void*, const void*, int, int,
+                                   int, int, float, void*, void*, void*, float*, float*, float*, float, int, cudaStream_t);
+static bool attn_mma_enabled() {
+  static const bool on = []() { const char* e = getenv("HFL_LM_ATTN_MMA"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
+
 extern "C" void hfl_lm_attn_fwd(const void* q, const void* k, const void* v, int N, int S, int H, int dh, float scale,
                                 void* o, void* P, cudaStream_t st) {
+  if (attn_mma_enabled()) { hfl_lm_attn_fwd_mma(q, k, v, N, S, H, dh, scale, o, P, st); return; }
   launch_k(lm_attn_fwd_kernel, dim3(dim3(N * H, 4)), dim3(256), 0, st, (const bf16*)q, (const bf16*)k, (const bf16*)v, S, H, dh, scale,
                                                      (bf16*)o, (bf16*)P);
   count_launch();
@@ -609,6 +621,8 @@ extern "C" void hfl_lm_attn_fwd(const void* q, const void* k, const void* v, int
 extern "C" int hfl_lm_attn_bwd(const void* dO, const void* q, const void* k, const void* v, const void* O, const void* P,
                                int N, int S, int H, int dh, float scale, void* dq, void* dk, void* dv, float* dbq,
                                float* dbk, float* dbv, float alpha_v, int scale_dv, cudaStream_t st) {
+  if (attn_mma_enabled())
+    return hfl_lm_attn_bwd_mma(dO, q, k, v, O, P, N, S, H, dh, scale, dq, dk, dv, dbq, dbk, dbv, alpha_v, scale_dv, st);
   launch_k(lm_attn_bwd_kernel, dim3(dim3(N * H, 8)), dim3(256), 0, st, (const bf16*)dO, (const bf16*)q, (const bf16*)k, (const bf16*)v,
                                                      (const bf16*)O, (const bf16*)P, S, H, dh, scale, (bf16*)dq,
                                                      (bf16*)dk, (bf16*)dv, dbq, dbk, dbv, alpha_v, scale_dv);
