@@ -67,6 +67,31 @@ if which in ("all", "lm"):
         C.lm_attn_bwd(do, q, k, v, o, P, N_, S_, H_, 1.0 / math.sqrt(32), dbs[0], dbs[1], dbs[2], 1.0)
         y, xh, rs, dm = C.lm_add_ln_fwd(q, k, ga, ga, 1e-5, 0.2, seed, seed, 3)
         C.lm_add_ln_bwd([do, q], xh, rs, ga, dm, 0.2, dbs[0], dbs[1], dbs[2], 1.0)
+if which in ("all", "convtrain"):
+    # batch-10 training shapes: residual + BatchNorm statistics in the epilogue; the deep-K layer runs as 8-CTA split-K
+    # clusters with the DSMEM reduction when HFL_CONV_KSPLIT=8
+    for (Cc, H) in ((64, 32), (512, 4)):
+        x = torch.randn(10, Cc, H, H, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+        w = (torch.randn(Cc, Cc, 3, 3, device=dev) * 0.02).bfloat16().contiguous(memory_format=torch.channels_last)
+        res = torch.randn_like(x)
+        ws = torch.zeros(2 * Cc + 1, device=dev)
+        for _ in range(reps):
+            ws.zero_()
+            C.conv_fprop_tc(x, w, res, ws, 1)
+            C.conv_dgrad_tc(x, w, None, 1)
+        dy2 = torch.randn(10, 2 * Cc, H // 2, H // 2, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+        w2 = (torch.randn(2 * Cc, Cc, 3, 3, device=dev) * 0.02).bfloat16().contiguous(memory_format=torch.channels_last)
+        for _ in range(reps):
+            C.conv_dgrad_tc(dy2, w2, None, 2)
+if which in ("all", "vocab"):
+    M_, E_, V_ = 64, 256, 33278
+    d = torch.randn(M_, E_, device=dev).bfloat16()
+    W = (torch.randn(V_, E_, device=dev) / 16).bfloat16()
+    b = torch.zeros(V_, device=dev).bfloat16()
+    tgt = torch.randint(0, V_, (M_,), device=dev)
+    db = torch.zeros(V_, device=dev)
+    for _ in range(reps):
+        C.lm_vocab_head(d, W, b, tgt, None, float(M_), None, db, True)
 torch.cuda.synchronize()
 print("done", which)
 if which in ("all", "mega"):

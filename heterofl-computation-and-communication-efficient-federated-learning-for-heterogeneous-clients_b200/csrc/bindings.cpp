@@ -91,7 +91,8 @@ int hfl_gemm_bf16_general(const void*, int, int, const void*, int, int, void*, i
 int hfl_gemm_general_splits(int, int, int);
 int hfl_gemm_grouped(int, const void* const*, int, int, const void* const*, int, int, void* const*, int, const void* const*,
                      const float*, int, int, int, int, cudaStream_t);
-int hfl_conv_dgrad_tc(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, cudaStream_t);
+int hfl_conv_dgrad_tc(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, int, cudaStream_t);
+int hfl_conv_dgrad_tc_supported(int, int, int, int, int, int, int, int);
 int hfl_conv_wgrad_tc_supported(int, int, int, int, int, int, int, int);
 int hfl_conv_wgrad_tc(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int hfl_mega_phase_bytes();
@@ -885,15 +886,20 @@ torch::Tensor conv_fprop_tc(torch::Tensor x, torch::Tensor w, c10::optional<torc
   return y;
 }
 
-// dy: [N, K, H, W] channels-last bf16 (stride-1 conv output grad); w: [K, C, R, S] stored K,R,S,C; returns dx [N, C, H, W]
-torch::Tensor conv_dgrad_tc(torch::Tensor dy, torch::Tensor w, c10::optional<torch::Tensor> residual) {
+// dy: [N, K, OH, OW] channels-last bf16 (gradient of a stride-1 or stride-2 convolution's output, padding R/2, even input
+// extent); w: [K, C, R, S] stored K,R,S,C; returns dx [N, C, stride*OH, stride*OW]
+bool conv_dgrad_tc_supported(int64_t N, int64_t H, int64_t W, int64_t C, int64_t Kout, int64_t R, int64_t S, int64_t stride) {
+  return hfl_conv_dgrad_tc_supported((int)N, (int)H, (int)W, (int)C, (int)Kout, (int)R, (int)S, (int)stride) == 0;
+}
+
+torch::Tensor conv_dgrad_tc(torch::Tensor dy, torch::Tensor w, c10::optional<torch::Tensor> residual, int64_t stride) {
   CHECK_CUDA_T(dy); CHECK_CUDA_T(w);
   TORCH_CHECK(dy.dim() == 4 && w.dim() == 4 && dy.scalar_type() == torch::kBFloat16 && w.scalar_type() == torch::kBFloat16);
   TORCH_CHECK(dy.is_contiguous(torch::MemoryFormat::ChannelsLast) && w.permute({0, 2, 3, 1}).is_contiguous());
-  const int N = dy.size(0), K = dy.size(1), H = dy.size(2), W = dy.size(3);
+  const int N = dy.size(0), K = dy.size(1), H = dy.size(2) * stride, W = dy.size(3) * stride;
   const int C = w.size(1), R = w.size(2), S = w.size(3);
   TORCH_CHECK(w.size(0) == K);
-  TORCH_CHECK(hfl_conv_tc_supported(N, H, W, K, C, R, S, 1) == 0, "conv_dgrad_tc: unsupported problem");
+  TORCH_CHECK(hfl_conv_dgrad_tc_supported(N, H, W, C, K, R, S, (int)stride) == 0, "conv_dgrad_tc: unsupported problem");
   c10::cuda::CUDAGuard guard(dy.device());
   auto dx = torch::empty({N, C, H, W}, dy.options().memory_format(torch::MemoryFormat::ChannelsLast));
   const void* rp = nullptr;
@@ -901,7 +907,7 @@ torch::Tensor conv_dgrad_tc(torch::Tensor dy, torch::Tensor w, c10::optional<tor
     TORCH_CHECK(residual->sizes() == dx.sizes() && residual->is_contiguous(torch::MemoryFormat::ChannelsLast));
     rp = residual->data_ptr();
   }
-  int e = hfl_conv_dgrad_tc(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), rp, N, H, W, C, K, R, S, cur_stream());
+  int e = hfl_conv_dgrad_tc(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), rp, N, H, W, C, K, R, S, (int)stride, cur_stream());
   TORCH_CHECK(e == 0, "conv_dgrad_tc failed with code ", e);
   return dx;
 }
@@ -1101,7 +1107,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv_tc_supported", &conv_tc_supported);
   m.def("conv_fprop_tc", &conv_fprop_tc, py::arg("x"), py::arg("w"), py::arg("residual"), py::arg("stats"), py::arg("stride"),
         py::arg("nvalid") = py::none());
-  m.def("conv_dgrad_tc", &conv_dgrad_tc);
+  m.def("conv_dgrad_tc", &conv_dgrad_tc, py::arg("dy"), py::arg("w"), py::arg("residual"), py::arg("stride") = 1);
+  m.def("conv_dgrad_tc_supported", &conv_dgrad_tc_supported);
   m.def("conv_wgrad_tc", &conv_wgrad_tc);
   m.def("conv_wgrad_tc_supported", &conv_wgrad_tc_supported);
   m.def("mega_launch", &mega_launch, py::arg("jobs"), py::arg("nphase"), py::arg("nsteps"), py::arg("ctl"), py::arg("grid"),

@@ -33,6 +33,14 @@ struct ConvGeom {
   int N, H, W, C, Kout, OH, OW, R, S, stride, pad;
   int bn, bh, bw;          // pixel brick of one tile (bn*bh*bw == 128, bw == OW)
   int tiles_h;             // ceil(OH / bh)
+  // data gradient only: parity classes of a strided convolution.  The dX pixels (out_s*a + ph, out_s*b + pw) of class
+  // cls = ph*2 + pw receive contributions from the filter taps r = (ph + pad) mod out_s (+ out_s ...) only, each a plain
+  // shifted read of dY -- so every class is a small stride-1 problem over the dY grid with its own tap list, written
+  // with stride out_s.  Stride 1: one class, all taps.  taps[cls][t] = filter tap | (dh + 8) << 8 | (dw + 8) << 16.
+  int tiles_m_cls;         // M tiles per class (blockIdx.x = cls * tiles_m_cls + tile)
+  int out_s, out_H, out_W; // output pixel stride / extent (dgrad: dX; fprop: out_s = 1, OH, OW)
+  int ntaps[4];
+  int taps[4][9];
 };
 
 // Column sums over the 32 lanes of a warp: on return lane j holds sum_over_lanes(v[j]) in v[0]  (31 shuffles).
@@ -96,12 +104,14 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_n = blockIdx.x / g.tiles_h;           // image-group index
-  const int tile_h = blockIdx.x - tile_n * g.tiles_h;  // row-group index
+  const int cls = DGRAD ? blockIdx.x / g.tiles_m_cls : 0;      // parity class of a strided data gradient
+  const int bx = DGRAD ? blockIdx.x - cls * g.tiles_m_cls : blockIdx.x;
+  const int tile_n = bx / g.tiles_h;                   // image-group index
+  const int tile_h = bx - tile_n * g.tiles_h;          // row-group index
   const int n0 = tile_n * g.bn, oh0 = tile_h * g.bh;
   const int n_blk = blockIdx.y;
   const int cblocks = (g.C + CV_BLOCK_K - 1) / CV_BLOCK_K;   // a partial last block is zero-filled by the TMA unit
-  const int num_k_all = g.R * g.S * cblocks;
+  const int num_k_all = (DGRAD ? g.ntaps[cls] : g.R * g.S) * cblocks;   // 0: a class no filter tap reaches (zeros)
   // split-K (gridDim.z > 1, launched as thread-block clusters {1, 1, ksplit}): the deep-K layers of a batch-10 step
   // have 2-8 output tiles and 36-72 k-blocks each; the CTAs of a cluster reduce disjoint k-ranges of ONE tile into
   // their own TMEM accumulators and combine them through distributed shared memory (no atomics, no zero-filled
@@ -146,13 +156,15 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
           // tensor are zero-filled, so any C and K_out that are multiples of 8 ride the same 128-byte-swizzle path
           tma_load_3d(sb, &tmap_w, &full_bar[st], cb * CV_BLOCK_K, tap, n_blk * BLOCK_N);
         } else {
-          // A: dY box at the mirrored tap offset
-          tma_load_4d(sa, &tmap_x, &full_bar[st], cb * CV_BLOCK_K, g.pad - s, oh0 + g.pad - r, n0);
+          // A: dY box at the tap's (mirrored) offset; `tap` indexes this class's tap list
+          const int tw = g.taps[cls][tap];
+          const int ftap = tw & 0xff, dh = ((tw >> 8) & 0xff) - 8, dw = ((tw >> 16) & 0xff) - 8;
+          tma_load_4d(sa, &tmap_x, &full_bar[st], cb * CV_BLOCK_K, dw, oh0 + dh, n0);
           // B (MN-major): 64(c) x 64(k_out) boxes of the {C, R*S, K_out} filter; here g.Kout is the number of dX
           // channels (= filter C) and g.C the reduction length (= filter K_out)
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
-            tma_load_3d(sb + j * 8192, &tmap_w, &full_bar[st], n_blk * BLOCK_N + j * 64, tap, cb * CV_BLOCK_K);
+            tma_load_3d(sb + j * 8192, &tmap_w, &full_bar[st], n_blk * BLOCK_N + j * 64, ftap, cb * CV_BLOCK_K);
         }
       }
     }
@@ -199,7 +211,7 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     tcgen05_fence_before();
   } else if (warp >= 4) {
     const int q = warp - 4;
-    mbar_wait(tmem_full_bar, 0);
+    if (num_k > 0) mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
     // One accumulator row (= one output pixel, K_out contiguous bf16) per thread: 64-byte runs per thread and chunk.
     // (A shared-memory transposed write-out like the GEMM's was measured 5-10 % SLOWER here -- the fp32 staging traffic
@@ -214,15 +226,20 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     const int nlim = nvalid ? min(g.N, __ldg(nvalid)) : g.N;
     const bool inr = (n < g.N) && (oh < g.OH);
     const bool ok = inr && (n < nlim);
-    const size_t pix = ((size_t)n * g.OH + oh) * g.OW + w_l;
+    const size_t pix = ((size_t)n * g.out_H + (size_t)(oh * g.out_s + (cls >> 1))) * g.out_W + (size_t)(w_l * g.out_s + (cls & 1));
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       const int col0 = n_blk * BLOCK_N + c0;
       const int ncol = min(32, g.Kout - col0);              // produced channels in this chunk (multiple of 8)
       if (ncol <= 0) break;                                 // warp-uniform
       uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + c0, v);
-      tmem_ld_wait();
+      if (num_k > 0) {
+        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
       float f[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = (ok && j < ncol) ? __uint_as_float(v[j]) : 0.f;
@@ -303,7 +320,7 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         const int h_l = tt % g.bh, n_l = tt / g.bh;
         const int n = n0 + n_l, oh = oh0 + h_l;
         if (!((n < g.N) && (oh < g.OH) && col_ok)) continue;
-        const size_t pix = ((size_t)n * g.OH + oh) * g.OW + w_l;
+        const size_t pix = ((size_t)n * g.out_H + (size_t)(oh * g.out_s + (cls >> 1))) * g.out_W + (size_t)(w_l * g.out_s + (cls & 1));
         if (n >= nlim2) {                                     // padding sample: zeros, no statistics
           *reinterpret_cast<uint2*>(Y + pix * g.Kout + col) = make_uint2(0u, 0u);
           continue;
@@ -421,10 +438,11 @@ static int conv_ksplit(int tiles, int num_k) {
 
 template <int BLOCK_N, bool DGRAD = false>
 static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, const void* residual, float* stats,
-                       const int* nvalid, const ConvGeom& g, int tiles_m, int n_tiles, cudaStream_t stream) {
+                       const int* nvalid, const ConvGeom& g, int tiles_m, int n_tiles, cudaStream_t stream,
+                       int num_k_hint = -1) {
   if (residual != nullptr && (reinterpret_cast<uintptr_t>(residual) & 15) != 0) return -3;
   if ((reinterpret_cast<uintptr_t>(Y) & 15) != 0) return -3;
-  const int num_k = g.R * g.S * ((g.C + CV_BLOCK_K - 1) / CV_BLOCK_K);
+  const int num_k = num_k_hint >= 0 ? num_k_hint : g.R * g.S * ((g.C + CV_BLOCK_K - 1) / CV_BLOCK_K);
   const int ks = conv_ksplit(tiles_m * n_tiles, num_k);
   if (residual != nullptr) {
     if (stats != nullptr) return launch_conv_v<BLOCK_N, DGRAD, true, true>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, ks, stream);
@@ -463,6 +481,8 @@ extern "C" int hfl_conv_fprop_tc(const void* X, const void* Wt, void* Y, const v
   g.bn = rows / g.bh;
   g.tiles_h = (g.OH + g.bh - 1) / g.bh;
   const int tiles_m = ((N + g.bn - 1) / g.bn) * g.tiles_h;
+  g.tiles_m_cls = tiles_m; g.out_s = 1; g.out_H = g.OH; g.out_W = g.OW;
+  for (int c = 0; c < 4; ++c) g.ntaps[c] = 0;
   const int block_n = (Kout % 128 == 0) ? 128 : (Kout > 32 ? 64 : 32);
   CUtensorMap tx, tw;
   // traversal strides: box extents are given in traversed elements (ceil(box/stride) elements are loaded)
@@ -478,33 +498,59 @@ extern "C" int hfl_conv_fprop_tc(const void* X, const void* Wt, void* Y, const v
   return launch_conv<32>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, stream);
 }
 
-// Stride-1 data gradient: dX[N,H,W,C] from dY[N,H,W,Kout] and the K,R,S,C filter.  `residual` is an optional tensor
-// added to dX (gradient arriving through a skip connection).
+// Data gradient: dX[N,H,W,C] from dY[N,OH,OW,Kout] and the K,R,S,C filter, stride 1 or 2 (H = stride * OH).  `residual` is
+// an optional tensor added to dX (gradient arriving through a skip connection).  A strided gradient runs as `stride^2`
+// parity classes inside ONE launch (see ConvGeom); classes no tap reaches (1x1 filters) are written as zeros.
+extern "C" int hfl_conv_dgrad_tc_supported(int N, int H, int W, int C, int Kout, int R, int S, int stride) {
+  if (stride != 1 && stride != 2) return 3;
+  if (H % stride != 0 || W % stride != 0) return 8;
+  return hfl_conv_tc_supported(N, H / stride, W / stride, Kout, C, R, S, 1);   // tiling over the dY grid, roles swapped
+}
+
 extern "C" int hfl_conv_dgrad_tc(const void* dY, const void* Wt, void* dX, const void* residual, int N, int H, int W,
-                                 int C, int Kout, int R, int S, cudaStream_t stream) {
-  // the forward-shape predicate with the channel roles swapped
-  if (hfl_conv_tc_supported(N, H, W, Kout, C, R, S, 1) != 0) return -2;
+                                 int C, int Kout, int R, int S, int stride, cudaStream_t stream) {
+  if (hfl_conv_dgrad_tc_supported(N, H, W, C, Kout, R, S, stride) != 0) return -2;
+  const int OH = H / stride, OW = W / stride;
   ConvGeom g;
-  g.N = N; g.H = H; g.W = W; g.R = R; g.S = S; g.stride = 1; g.pad = R / 2;
+  g.N = N; g.H = OH; g.W = OW; g.R = R; g.S = S; g.stride = 1; g.pad = R / 2;
   g.C = Kout;            // reduction channels (dY)
   g.Kout = C;            // produced channels (dX)
-  g.OH = H; g.OW = W;
-  g.bw = W;
-  const int rows = 128 / W;
-  g.bh = rows < H ? rows : H;
+  g.OH = OH; g.OW = OW;
+  g.bw = OW;
+  const int rows = 128 / OW;
+  g.bh = rows < OH ? rows : OH;
   g.bn = rows / g.bh;
-  g.tiles_h = (H + g.bh - 1) / g.bh;
+  g.tiles_h = (OH + g.bh - 1) / g.bh;
   const int tiles_m = ((N + g.bn - 1) / g.bn) * g.tiles_h;
+  g.tiles_m_cls = tiles_m; g.out_s = stride; g.out_H = H; g.out_W = W;
+  const int ncls = stride * stride;
+  int max_taps = 0;
+  for (int cls = 0; cls < 4; ++cls) {
+    g.ntaps[cls] = 0;
+    if (cls >= ncls) continue;
+    const int ph = stride == 1 ? 0 : (cls >> 1), pw = stride == 1 ? 0 : (cls & 1);
+    for (int r = 0; r < R; ++r) {
+      if ((ph + g.pad - r) % stride != 0) continue;          // (ph + pad - r) may be negative: C % keeps the sign, 0 stays 0
+      for (int s2 = 0; s2 < S; ++s2) {
+        if ((pw + g.pad - s2) % stride != 0) continue;
+        const int dh = (ph + g.pad - r) / stride, dw = (pw + g.pad - s2) / stride;     // exact divisions
+        g.taps[cls][g.ntaps[cls]++] = (r * S + s2) | ((dh + 8) << 8) | ((dw + 8) << 16);
+      }
+    }
+    if (g.ntaps[cls] > max_taps) max_taps = g.ntaps[cls];
+  }
   const int block_n = (C % 128 == 0) ? 128 : 64;      // MN-major B: whole 64-channel boxes (zero-filled past C)
   CUtensorMap tx, tw;
-  int r = make_tmap_nhwc_bf16(&tx, dY, (uint64_t)Kout, (uint64_t)W, (uint64_t)H, (uint64_t)N, CV_BLOCK_K, (uint32_t)g.bw,
+  int r = make_tmap_nhwc_bf16(&tx, dY, (uint64_t)Kout, (uint64_t)OW, (uint64_t)OH, (uint64_t)N, CV_BLOCK_K, (uint32_t)g.bw,
                               (uint32_t)g.bh, (uint32_t)g.bn, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r) return 1000 + r;
   r = make_tmap_filter_bf16(&tw, Wt, C, R * S, Kout, 64, CV_BLOCK_K);
   if (r) return 2000 + r;
   const int n_tiles = (C + block_n - 1) / block_n;
-  if (block_n == 128) return launch_conv<128, true>(tx, tw, dX, residual, nullptr, nullptr, g, tiles_m, n_tiles, stream);
-  return launch_conv<64, true>(tx, tw, dX, residual, nullptr, nullptr, g, tiles_m, n_tiles, stream);
+  const int grid_m = tiles_m * ncls;
+  const int num_k = max_taps * ((Kout + CV_BLOCK_K - 1) / CV_BLOCK_K);
+  if (block_n == 128) return launch_conv<128, true>(tx, tw, dX, residual, nullptr, nullptr, g, grid_m, n_tiles, stream, num_k);
+  return launch_conv<64, true>(tx, tw, dX, residual, nullptr, nullptr, g, grid_m, n_tiles, stream, num_k);
 }
 
 // ---------------------------------------------------------------------------------------------------------

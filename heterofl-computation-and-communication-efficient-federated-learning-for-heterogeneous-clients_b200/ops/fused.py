@@ -286,15 +286,21 @@ def _tc_bwd_ok(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int, 
             and w.permute(0, 2, 3, 1).is_contiguous())
 
 
+def _tc_dgrad_ok(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int) -> bool:
+    N, C, H, W = x.shape
+    K, _, R, S = w.shape
+    return CONV_BWD_TC_MODE == "on" and stride in (1, 2) and cu.C().conv_dgrad_tc_supported(N, H, W, C, K, R, S, stride)
+
+
 def conv_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int, pad: int, need_dx: bool = True,
              need_dw: bool = True):
-    """``(dx | None, dw)``.  Library path: cuDNN dgrad + wgrad.  tcgen05 path (``HFL_CONV_BWD_TC``): stride-1 dgrad as
-    an implicit GEMM with mirrored taps + MN-major filter operand, wgrad with both operands MN-major and split-K;
-    ``dw`` then comes back as fp32 (the multi-tensor optimiser reads either precision)."""
+    """``(dx | None, dw)``.  tcgen05 path (``HFL_CONV_BWD_TC``): dgrad as an implicit GEMM with mirrored taps + MN-major
+    filter operand (stride 2: the four output-parity classes of the strided gradient inside one launch), wgrad with
+    both operands MN-major and split-K; ``dw`` then comes back as fp32 (the multi-tensor optimiser reads either
+    precision).  Library path (cuDNN) for whatever the kernels do not cover."""
     if not need_dw:
-        if CONV_BWD_TC_MODE == "on" and _tc_bwd_ok(dy, x, w, stride, pad) and stride == 1 and cu.C().conv_tc_supported(
-                x.shape[0], x.shape[2], x.shape[3], w.shape[0], x.shape[1], w.shape[2], w.shape[3], 1):
-            return cu.C().conv_dgrad_tc(dy, w, None), None
+        if _tc_bwd_ok(dy, x, w, stride, pad) and _tc_dgrad_ok(dy, x, w, stride):
+            return cu.C().conv_dgrad_tc(dy, w, None, stride), None
         dx, _, _ = torch.ops.aten.convolution_backward(dy, x, w, None, (stride, stride), (pad, pad), (1, 1), False,
                                                        (0, 0), 1, (True, False, False))
         return dx, None
@@ -303,8 +309,8 @@ def conv_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int, pa
         K, _, R, S = w.shape
         C_ = cu.C()
         dx = dw = None
-        if CONV_BWD_TC_MODE == "on" and need_dx and stride == 1 and C_.conv_tc_supported(N, H, W, K, C, R, S, 1):
-            dx = C_.conv_dgrad_tc(dy, w, None)
+        if need_dx and _tc_dgrad_ok(dy, x, w, stride):
+            dx = C_.conv_dgrad_tc(dy, w, None, stride)
         if C_.conv_wgrad_tc_supported(N, H, W, C, K, R, S, stride):
             dw = C_.conv_wgrad_tc(dy, x, R, stride)
         if (dx is not None or not need_dx) and dw is not None:

@@ -478,6 +478,31 @@ def test_tcgen05_conv_dgrad_matches_autograd(N, C, H, K, R):
     assert float((dx2.float() - ref - res.float()).abs().max()) < 4e-2 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("N,C,H,K,R", [(10, 64, 32, 128, 3), (10, 128, 16, 256, 3), (10, 256, 8, 512, 3), (10, 64, 32, 128, 1),
+                                        (10, 16, 32, 32, 3), (10, 8, 16, 16, 1), (3, 32, 16, 64, 3)])
+def test_tcgen05_conv_dgrad_stride2_matches_autograd(N, C, H, K, R):
+    """Data gradient of a stride-2 convolution: the four output-parity classes (1 / 2 / 2 / 4 taps for a 3x3 filter, a
+    single class for 1x1 with the other three written as zeros) run inside one launch of the implicit-GEMM kernel."""
+    cu = _cu()
+    dev = torch.device("cuda")
+    torch.manual_seed(N + C + K + R)
+    x = torch.randn(N, C, H, H, device=dev, requires_grad=True)
+    w = (torch.randn(K, C, R, R, device=dev) / (C * R * R) ** 0.5).bfloat16()
+    y = torch.nn.functional.conv2d(x, w.float(), None, 2, R // 2)
+    dy = torch.randn_like(y).bfloat16().contiguous(memory_format=torch.channels_last)
+    y.backward(dy.float())
+    wk = w.contiguous(memory_format=torch.channels_last) if R > 1 else w.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    assert cu.C().conv_dgrad_tc_supported(N, H, H, C, K, R, R, 2)
+    dx = cu.C().conv_dgrad_tc(dy, wk, None, 2)
+    torch.cuda.synchronize()
+    ref = x.grad
+    assert dx.shape == ref.shape
+    assert float((dx.float() - ref).abs().max()) < 3e-2 * max(1.0, float(ref.abs().max()))
+    res = torch.randn_like(ref).bfloat16().contiguous(memory_format=torch.channels_last)
+    dx2 = cu.C().conv_dgrad_tc(dy, wk, res, 2)
+    assert float((dx2.float() - ref - res.float()).abs().max()) < 4e-2 * max(1.0, float(ref.abs().max()))
+
+
 @pytest.mark.parametrize("N,C,H,K,R,stride", [(10, 64, 32, 64, 3, 1), (10, 64, 32, 128, 3, 2), (10, 128, 16, 128, 3, 1),
                                                (10, 64, 32, 128, 1, 2), (10, 256, 8, 256, 3, 1), (12, 512, 4, 512, 3, 1),
                                                (8, 256, 8, 512, 3, 2), (10, 32, 32, 32, 3, 1), (10, 16, 32, 16, 3, 1),
