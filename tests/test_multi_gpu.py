@@ -138,3 +138,46 @@ def test_two_gpu_engine_runs(tmp_path, backend):
     h = torch.load(ret, weights_only=False)["hist"]
     assert all(np.isfinite(v) for v in h["train/Local-Loss"] + h["test/Global-Loss"])
     assert h["train/Local-Loss"][-1] < h["train/Local-Loss"][0]
+
+
+def _round_worker(rank, world, port, ret, out_dir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from hfl_b200.fed.engine import Engine, EngineOptions
+    from hfl_b200.parallel.dist import init_distributed, shutdown
+    info = init_distributed()
+    torch.manual_seed(0)
+    eng = Engine(_cfg(), info, options=EngineOptions(out_dir=out_dir, quiet=True, save=False))
+    eng.setup()
+    w0 = eng.global_arena.float().cpu().clone()
+    res = eng.run_round(1)
+    torch.cuda.synchronize()
+    if eng._peer is not None:
+        eng._peer.check()
+    if rank == 0:
+        torch.save({"w0": w0, "w1": eng.global_arena.float().cpu().clone(), "train": res["train"], "test": res["test"],
+                    "train_n": res["train_n"]}, ret)
+    shutdown()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_rank_count_invariance(tmp_path):
+    """The same communication round on 1 rank and on 2 ranks (clients sharded, P2P aggregation): same client sample, same
+    number of training samples, and the global update W_g(1) - W_g(0) agrees in direction and size -- the clients' bf16
+    trajectories differ only by kernel scheduling (atomics order, library algorithm choices), not by the rank count."""
+    outs = []
+    for world in (1, 2):
+        ret = str(tmp_path / ("w%d.pt" % world))
+        mp.spawn(_round_worker, args=(world, 29500 + world * 7 + (os.getpid() % 100), ret, str(tmp_path / ("d%d" % world))),
+                 nprocs=world, join=True)
+        outs.append(torch.load(ret, weights_only=False))
+    a, b = outs
+    assert torch.equal(a["w0"], b["w0"])
+    assert a["train_n"] == b["train_n"]
+    da, db = a["w1"] - a["w0"], b["w1"] - b["w0"]
+    cos = float(torch.nn.functional.cosine_similarity(da, db, dim=0))
+    ratio = float(db.norm() / da.norm())
+    print("rank-count invariance: cos %.4f  norm ratio %.4f  loss %.4f / %.4f" % (
+        cos, ratio, a["train"]["Local-Loss"], b["train"]["Local-Loss"]))
+    assert cos > 0.9 and 0.9 < ratio < 1.1, (cos, ratio)
+    assert abs(a["train"]["Local-Loss"] - b["train"]["Local-Loss"]) < 0.1 * max(1.0, abs(a["train"]["Local-Loss"]))
