@@ -749,7 +749,9 @@ static cudaError_t launch_cluster(Kern kern, dim3 grid, int cluster_x, size_t sm
     default: { constexpr int NVC = 0; CALL; break; }  \
   }
 
-static const long WIDE_ELEMS = 48L * 1024;          // per-group elements above which the split (2-launch) path wins
+// per-group elements above which the split (2-launch) path wins over the single cluster kernel (measured on one GPU with
+// 10-16 concurrent clients); HFL_BN_WIDE_ELEMS overrides for A/B (the cluster kernel holds at most 16 x 512 x 10 vectors)
+static const long WIDE_ELEMS = []() { const char* e = getenv("HFL_BN_WIDE_ELEMS"); return e ? atol(e) : 48L * 1024; }();
 static size_t wide_smem(int C) { return (2 * (size_t)C + 2 * 16 * (size_t)(C < 256 ? C : 256)) * sizeof(float); }
 static int wide_grid(long nvec) {
   long b = (nvec + NT * 2 - 1) / (NT * 2);
