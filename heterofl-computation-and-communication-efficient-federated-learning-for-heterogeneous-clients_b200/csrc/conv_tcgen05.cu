@@ -431,8 +431,12 @@ static int conv_ksplit(int tiles, int num_k) {
     const char* w = getenv("WORLD_SIZE");
     return (w && atoi(w) >= 4) ? 8 : 1;
   }();
+  // only the deep reductions (C >= 256: 36 / 72 k-blocks) split, and every split keeps >= 8 k-blocks: with 9-18 k-blocks the
+  // cluster launch + DSMEM reduction cost more than the shorter mainloop saves (isolated narrow-level steps were 40-50 us
+  // SLOWER when their 9-k-block convolutions were split in two, gpurun_out/r2i)
+  if (num_k < 32) return 1;
   int ks = 1;
-  while (ks * 2 <= cap && tiles * ks * 2 <= 148 && num_k / (ks * 2) >= 4) ks *= 2;
+  while (ks * 2 <= cap && tiles * ks * 2 <= 148 && num_k / (ks * 2) >= 8) ks *= 2;
   return ks;
 }
 
