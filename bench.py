@@ -101,7 +101,8 @@ def run_ours(args):
         cfg["fused"] = False
     eng = Engine(cfg, info, options=EngineOptions(out_dir="/tmp/hfl_bench", quiet=True, save=False,
                                                   compute_dtype=args.dtype, max_concurrent=args.max_concurrent,
-                                                  agg_backend=args.agg_backend, async_eval=args.async_eval,
+                                                  agg_backend=args.agg_backend,
+                                                  async_eval=(True if args.async_eval else (False if args.sync_eval else None)),
                                                   threaded_issue=not args.single_thread_issue))
     eng.setup()
     t0 = time.time()
@@ -181,7 +182,7 @@ def run_ours(args):
                        "round": "distribute+local-train+aggregate" + ("" if args.no_eval else "+sBN-stats+test"),
                        "eval_overlap": "sBN+test of round r overlap local training of round r+1 (side stream); the "
                                        "last round's evaluation completes inside the timed region"
-                       if args.async_eval else "none",
+                       if eng._async_eval_ok() else "none",
                        "train_samples_per_round": samples / args.steps,
                        "l2": ("inputs_exceed_L2 (every round streams the clients' arenas, optimiser state and the "
                               "%s; nothing reusable across rounds fits the 126 MB L2)" %
@@ -227,8 +228,9 @@ def main():
     ap.add_argument("--agg-backend", default="auto")
     ap.add_argument("--single-thread-issue", action="store_true", help="A/B: issue all graph replays from one host thread")
     ap.add_argument("--async-eval", action="store_true",
-                    help="overlap sBN+test of round r with the training of round r+1 on a side stream (measured: no "
-                         "gain on one GPU -- the big eval kernels delay the latency-bound training kernels)")
+                    help="force: overlap sBN+test of round r with the training of round r+1 on a side stream (default: "
+                         "automatic, on from 4 ranks up; measured: no gain on one GPU, 231 -> 213 ms/round on 8)")
+    ap.add_argument("--sync-eval", action="store_true", help="force the evaluation inside its own round (A/B)")
     ap.add_argument("--no-fused", action="store_true", help="A/B: autograd + library-BN path instead of the fused path")
     ap.add_argument("--dtype", default="auto", choices=["auto", "bf16", "fp32"],
                     help="compute dtype of this framework's arm (fp32 = precision-matched to the reference's fp32/TF32 arm: "

@@ -43,6 +43,9 @@ int hfl_bn_act_bwd(const void*, const void*, const void*, const void*, const flo
                    const void*, int, int, int, int, float, int, void*, void*, void*, float*, int, const int*, int,
                    cudaStream_t);
 int hfl_ms_chunk();
+void hfl_emb_sparse_norm(const int*, int, const float*, int, float*, cudaStream_t);
+void hfl_emb_sparse_apply(const int*, int, float*, int, long, float*, void*, float*, const float*, float, const float*,
+                          cudaStream_t);
 void hfl_multi_sgd_clip_step(const void*, const void*, int, float*, void*, float*, const float*, float, float, float,
                              float*, cudaStream_t);
 int hfl_gemm_bf16_tn(const void*, int, const void*, int, void*, int, int, const float*, const void*, float, int, int,
@@ -84,6 +87,7 @@ int hfl_head_fwd_bwd(const void*, int, int, int, const void*, const void*, int, 
 int hfl_bn_apply_sums(const void*, void*, const void*, const void*, int, float, int, int, int, float*, float*, float*,
                       float*, const int*, int, cudaStream_t);
 int hfl_conv_tc_supported(int, int, int, int, int, int, int, int);
+void hfl_conv_set_ksplit(int);
 int hfl_conv_fprop_tc(const void*, const void*, void*, const void*, float*, const int*, int, int, int, int, int, int, int,
                       int, cudaStream_t);
 int hfl_gemm_bf16_general(const void*, int, int, const void*, int, int, void*, int, int, float, int, int, int, int,
@@ -520,6 +524,29 @@ void multi_sgd_clip_step(torch::Tensor segs, torch::Tensor blocks, torch::Tensor
   hfl_multi_sgd_clip_step(segs.data_ptr(), blocks.data_ptr(), (int)blocks.size(0), w.data_ptr<float>(),
                           wc.has_value() ? wc->data_ptr() : nullptr, mom.data_ptr<float>(), lr.data_ptr<float>(),
                           (float)mu, (float)wd, (float)max_norm, scratch.data_ptr<float>(), cur_stream());
+  check_launch();
+}
+
+// row-sparse embedding gradient (csrc/optim_kernels.cu): src int32 [M] (table row per token), g fp32 [rows, E]
+void emb_sparse_norm(torch::Tensor src, torch::Tensor g, torch::Tensor scratch) {
+  CHECK_CUDA_T(src); CHECK_CUDA_T(g);
+  TORCH_CHECK(src.scalar_type() == torch::kInt32 && src.is_contiguous() && g.scalar_type() == torch::kFloat32 &&
+              g.dim() == 2 && g.is_contiguous() && scratch.scalar_type() == torch::kFloat32);
+  c10::cuda::CUDAGuard guard(g.device());
+  hfl_emb_sparse_norm(src.data_ptr<int>(), (int)src.numel(), g.data_ptr<float>(), (int)g.size(1), scratch.data_ptr<float>(),
+                      cur_stream());
+  check_launch();
+}
+void emb_sparse_apply(torch::Tensor src, torch::Tensor g, int64_t off, torch::Tensor w, c10::optional<torch::Tensor> wc,
+                      torch::Tensor mom, torch::Tensor lr, double max_norm, torch::Tensor scratch) {
+  CHECK_CUDA_T(src); CHECK_CUDA_T(g); CHECK_CUDA_T(w);
+  TORCH_CHECK(src.scalar_type() == torch::kInt32 && src.is_contiguous() && g.scalar_type() == torch::kFloat32 &&
+              g.dim() == 2 && g.is_contiguous() && w.scalar_type() == torch::kFloat32 && mom.scalar_type() == torch::kFloat32);
+  TORCH_CHECK(off >= 0 && off + g.numel() <= w.numel());
+  c10::cuda::CUDAGuard guard(g.device());
+  hfl_emb_sparse_apply(src.data_ptr<int>(), (int)src.numel(), g.data_ptr<float>(), (int)g.size(1), (long)off,
+                       w.data_ptr<float>(), wc.has_value() ? wc->data_ptr() : nullptr, mom.data_ptr<float>(),
+                       lr.data_ptr<float>(), (float)max_norm, scratch.data_ptr<float>(), cur_stream());
   check_launch();
 }
 
@@ -1081,6 +1108,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gn_act_bwd", &gn_act_bwd);
   m.def("multi_sgd_clip_step", &multi_sgd_clip_step);
   m.def("ms_chunk", &hfl_ms_chunk);
+  m.def("emb_sparse_norm", &emb_sparse_norm);
+  m.def("emb_sparse_apply", &emb_sparse_apply);
   m.def("head_fwd_bwd", &head_fwd_bwd);
   m.def("head_smem_bytes", &hfl_head_smem_bytes);
   m.def("gemm_bf16_tn", &gemm_bf16_tn, py::arg("x"), py::arg("w"), py::arg("bias"), py::arg("alpha"), py::arg("gelu"),
@@ -1109,6 +1138,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("nvalid") = py::none());
   m.def("conv_dgrad_tc", &conv_dgrad_tc, py::arg("dy"), py::arg("w"), py::arg("residual"), py::arg("stride") = 1);
   m.def("conv_dgrad_tc_supported", &conv_dgrad_tc_supported);
+  m.def("conv_set_ksplit", [](int64_t cap) { hfl_conv_set_ksplit((int)cap); });
   m.def("conv_wgrad_tc", &conv_wgrad_tc);
   m.def("conv_wgrad_tc_supported", &conv_wgrad_tc_supported);
   m.def("mega_launch", &mega_launch, py::arg("jobs"), py::arg("nphase"), py::arg("nsteps"), py::arg("ctl"), py::arg("grid"),

@@ -424,13 +424,17 @@ static int launch_conv_v(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, 
 // per GPU, chain-bound) but on one GPU, where 10-16 clients already fill the SMs, the 8x larger grids of 200 KB CTAs
 // cost more than they save (round 516 vs 480 ms).  Default: on from 4 ranks up, off below; HFL_CONV_KSPLIT=<cap>
 // overrides (1 = off).
+static int g_ksplit_override = -1;          // tests / probes: hfl_conv_set_ksplit(cap); -1 = policy below
+extern "C" void hfl_conv_set_ksplit(int cap) { g_ksplit_override = cap; }
+
 static int conv_ksplit(int tiles, int num_k) {
-  static const int cap = []() {
+  static const int policy_cap = []() {
     const char* e = getenv("HFL_CONV_KSPLIT");
     if (e) return atoi(e);
     const char* w = getenv("WORLD_SIZE");
     return (w && atoi(w) >= 4) ? 8 : 1;
   }();
+  const int cap = g_ksplit_override >= 1 ? g_ksplit_override : policy_cap;
   // only the deep reductions (C >= 256: 36 / 72 k-blocks) split, and every split keeps >= 8 k-blocks: with 9-18 k-blocks the
   // cluster launch + DSMEM reduction cost more than the shorter mainloop saves (isolated narrow-level steps were 40-50 us
   // SLOWER when their 9-k-block convolutions were split in two, gpurun_out/r2i)

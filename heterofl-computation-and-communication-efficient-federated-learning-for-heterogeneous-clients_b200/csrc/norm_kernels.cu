@@ -765,7 +765,11 @@ extern "C" int hfl_bn_act_fwd(const void* x, const void* res, void* s_out, void*
                               float* mean_out, float* invstd_out, float* varu_out, float* ws, int ws_persistent,
                               const int* nvalid, int rps, cudaStream_t stream) {
   if (groups > 1) nvalid = nullptr;               // ghost batches are always full
-  if (((long)Mg * C > WIDE_ELEMS || groups > 1) && ws != nullptr) {   // ghost batches: always the wide path
+  // ghost batches (sBN pass): the wide path by default; HFL_BN_GHOST_CLUSTER=1 keeps every ghost batch in the registers of
+  // one cluster instead (one read of x instead of two) when it fits 16 CTAs x 512 threads x 10 vectors
+  static const bool ghost_cluster = []() { const char* e = getenv("HFL_BN_GHOST_CLUSTER"); return e && e[0] == '1'; }();
+  const bool ghost_wide = groups > 1 && !(ghost_cluster && (long)Mg * C <= 16L * NT * 10 * 8);
+  if (((long)Mg * C > WIDE_ELEMS || ghost_wide) && ws != nullptr && !(groups > 1 && !ghost_wide)) {
     const int nvec = Mg * C / 8;
     int gx = wide_grid(nvec);
     if (groups > 1 && gx > 16) gx = 16;           // many groups already fill the machine

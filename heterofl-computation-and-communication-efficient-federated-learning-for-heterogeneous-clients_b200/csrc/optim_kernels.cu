@@ -128,7 +128,10 @@ namespace hfl {
 struct Seg { const void* g; long off; long n; long bf16; };
 constexpr int MS_CHUNK = 4096;
 
+// s.g == nullptr: a segment whose gradient is applied separately (row-sparse embedding table, below); the dense pass
+// runs its weight-decay / momentum part with a zero gradient and the norm pass skips it
 __device__ __forceinline__ float seg_grad(const Seg& s, long i) {
+  if (s.g == nullptr) return 0.f;
   return s.bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(s.g)[i])
                 : reinterpret_cast<const float*>(s.g)[i];
 }
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(256) multi_norm_sq_kernel(const Seg* __restric
   __shared__ float sm[33];
   const int2 b = blocks[blockIdx.x];
   const Seg s = segs[b.x];
+  if (s.g == nullptr) return;                       // whole CTA: no gradient array to read
   const long end = min((long)b.y + MS_CHUNK, s.n);
   float acc = 0.f;
   for (long i = b.y + threadIdx.x; i < end; i += 256) {
@@ -183,9 +187,74 @@ multi_sgd_update_kernel(const Seg* __restrict__ segs, const int2* __restrict__ b
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Row-sparse gradient of an embedding table (masked-LM step: <= tokens-per-step rows of the 33 279 x E table are touched).
+// SGD with momentum and weight decay is affine in the gradient:
+//     mom' = mu*mom + wd*w + c*g,   w' = w - lr*mom'      (c = clip coefficient)
+// so the dense pass above runs with g = 0 for this segment (it never reads, and nobody has to zero, the 34 MB gradient
+// array) and the touched rows receive the missing  mom += c*g,  w -= lr*c*g  afterwards -- the same update up to fp32
+// rounding order.  `src[m]` = table row read by token m (duplicates allowed: the first occurrence owns the row).
+//   sparse_norm : adds sum g^2 of the unique touched rows to scratch[0]      (BEFORE the dense norm / update)
+//   sparse_apply: applies the correction, refreshes the bf16 copy, zeroes the rows of g   (AFTER the dense update, which
+//                 leaves the total gradient norm in scratch[2])
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool first_occurrence(const int* __restrict__ src, int m) {
+  const int r = src[m];
+  int dup = 0;
+  for (int t = threadIdx.x; t < m; t += blockDim.x) dup |= (src[t] == r);
+  return __syncthreads_or(dup) == 0;
+}
+
+__global__ void __launch_bounds__(128)
+emb_sparse_norm_kernel(const int* __restrict__ src, const float* __restrict__ g, int E, float* __restrict__ scratch) {
+  pdl_sync();
+  __shared__ float sm[33];
+  const int m = blockIdx.x;
+  if (!first_occurrence(src, m)) return;
+  const float* row = g + (size_t)src[m] * E;
+  float acc = 0.f;
+  for (int c = threadIdx.x; c < E; c += blockDim.x) acc += row[c] * row[c];
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) atomicAdd(scratch, acc);
+}
+
+__global__ void __launch_bounds__(128)
+emb_sparse_apply_kernel(const int* __restrict__ src, float* __restrict__ g, int E, long off, float* __restrict__ w,
+                        __nv_bfloat16* __restrict__ wc, float* __restrict__ mom, const float* __restrict__ lr_p,
+                        float max_norm, const float* __restrict__ scratch) {
+  pdl_sync();
+  const int m = blockIdx.x;
+  if (!first_occurrence(src, m)) return;
+  const float coef = fminf(1.f, max_norm / (scratch[2] + 1e-6f));
+  const float lr = *lr_p;
+  const size_t r = (size_t)src[m] * E;
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    const float gv = g[r + c] * coef;
+    const size_t o = (size_t)off + r + c;
+    mom[o] += gv;
+    const float nw = w[o] - lr * gv;
+    w[o] = nw;
+    if (wc) wc[o] = __float2bfloat16(nw);
+    g[r + c] = 0.f;
+  }
+}
+
 }  // namespace hfl
 
 extern "C" int hfl_ms_chunk() { return hfl::MS_CHUNK; }
+
+extern "C" void hfl_emb_sparse_norm(const int* src, int M, const float* g, int E, float* scratch, cudaStream_t stream) {
+  if (M <= 0) return;
+  hfl::launch_k(hfl::emb_sparse_norm_kernel, dim3(M), dim3(128), 0, stream, src, g, E, scratch);
+  hfl::count_launch();
+}
+extern "C" void hfl_emb_sparse_apply(const int* src, int M, float* g, int E, long off, float* w, void* wc, float* mom,
+                                     const float* lr, float max_norm, const float* scratch, cudaStream_t stream) {
+  if (M <= 0) return;
+  hfl::launch_k(hfl::emb_sparse_apply_kernel, dim3(M), dim3(128), 0, stream, src, g, E, off, w, (__nv_bfloat16*)wc, mom, lr,
+                max_norm, scratch);
+  hfl::count_launch();
+}
 
 extern "C" void hfl_multi_sgd_clip_step(const void* segs, const void* blocks, int n_blocks, float* w, void* wc,
                                         float* mom, const float* lr, float mu, float wd, float max_norm,

@@ -40,6 +40,16 @@ class Evaluator:
         if self.device.type == "cuda" and compute_dtype == torch.bfloat16 and cu.available() \
                 and cfg.get("fused", True) and FusedResNet.eligible(model.spec, train_only=False):
             self.fused = FusedResNet(model.spec, model.scale_rate)
+        # masked-LM evaluation: the encoder forward on the fused LM kernels (models/fused_transformer.py)
+        self.fused_lm = None
+        if self.device.type == "cuda" and compute_dtype == torch.bfloat16 and cu.available() and cfg.get("fused", True) \
+                and model.is_lm and os.environ.get("HFL_LM_EVAL_FUSED", "1") != "0":
+            from ..models.fused_transformer import FusedTransformer
+            if FusedTransformer.eligible(model.spec, int(model.layout.entries[
+                    "transformer_embedding.embedding.weight"].shape[1])):
+                self.fused_lm = FusedTransformer(model.spec, model.scale_rate, mask_rate=float(cfg.get("mask_rate", 0.15)))
+                self._lm_seed = torch.tensor([int(cfg.get("seed", 0)) * 7919 + 17], dtype=torch.int64, device=self.device)
+                self._lm_step = torch.zeros(1, dtype=torch.int64, device=self.device)
         # resident-kernel programs (models/mega_resnet.py): the whole sBN pass / test pass of this rank is ONE launch
         self.mega = None
         self._mega_sbn = None
@@ -457,7 +467,14 @@ class Evaluator:
         for b0 in range(0, len(full), WB):
             grp = full[b0:b0 + WB]
             tok = torch.cat([rows_dev[:, s0:s0 + bptt] for s0, _ in grp], dim=0).contiguous()      # [len*r, bptt]
-            z = self.model.forward(P, {"label": tok}, ctx, None, want_score="raw")["logits"]        # [len*r*bptt, V]
+            if self.fused_lm is not None:
+                # encoder on the fused kernels (fresh [MASK] draw per forward: device-side counter), then ONE vocabulary GEMM
+                self._lm_step.add_(1)
+                d = self.fused_lm.forward_hidden_eval(P, tok, self._lm_seed, self._lm_step)
+                from ..ops.linear import tc_linear
+                z = tc_linear(d, P["decoder.linear2.weight"], P["decoder.linear2.bias"], 1.0)
+            else:
+                z = self.model.forward(P, {"label": tok}, ctx, None, want_score="raw")["logits"]    # [len*r*bptt, V]
             z = z.view(len(grp), r * bptt, -1)
             tgt = tok.view(len(grp), r * bptt)
             for wi in range(len(grp)):           # per-window mean CE (every window weighs r, reference semantics)

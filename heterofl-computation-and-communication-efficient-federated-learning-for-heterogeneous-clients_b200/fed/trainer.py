@@ -143,8 +143,13 @@ class TrainSlot:
                                  else torch.contiguous_format)
                 self._grads[name] = g
             assert g.numel() == e.numel, name
-            rows.append((g.data_ptr(), e.offset, e.numel, 1 if g.dtype == torch.bfloat16 else 0))
+            ptr = 0 if (name == EMB and self._emb_sparse()) else g.data_ptr()     # 0: applied row-sparsely afterwards
+            rows.append((ptr, e.offset, e.numel, 1 if g.dtype == torch.bfloat16 else 0))
         return rows
+
+    def _emb_sparse(self) -> bool:
+        f = self.fused
+        return bool(getattr(f, "emb_sparse", False) and getattr(f, "emb_src", None) is not None and self.grad_sync is None)
 
     grad_sync = None   # optional callable run between backward and the optimiser (data-parallel all-reduce)
 
@@ -158,8 +163,15 @@ class TrainSlot:
             else:
                 self.seg_tab.copy_(torch.tensor(rows, dtype=torch.int64), non_blocking=False)
                 self._seg_active = None
+            sparse = self._emb_sparse()
+            if sparse:      # row-sparse token-table gradient: its norm first, its update after the dense pass
+                ge = self._grads[EMB]
+                cu.C().emb_sparse_norm(self.fused.emb_src, ge, self.scratch)
             cu.C().multi_sgd_clip_step(self.seg_tab, self.blk_tab, self.w, self.wc, self.mom, self.lr_t,
                                        self.momentum, self.wd, self.max_norm, self.scratch)
+            if sparse:
+                cu.C().emb_sparse_apply(self.fused.emb_src, ge, int(self.model.layout.entries[EMB].offset), self.w, self.wc,
+                                        self.mom, self.lr_t, self.max_norm, self.scratch)
             if not self._capturing:
                 self._grads = None
             return
@@ -172,6 +184,8 @@ class TrainSlot:
     def _fwd_bwd(self, inp: Dict, n_weight: float, nvalid: Optional[torch.Tensor] = None) -> None:
         mask = self.mask_t if self.use_mask else None
         if self.fused is not None and self.model.is_lm:
+            if self.grad_sync is not None:
+                self.fused.emb_sparse = False     # dense all-reduce of every gradient: the token table stays dense
             _, self._grads = self.fused.train_step(self.Pv, inp["label"], mask, (self.meter.buf, n_weight),
                                                    self.rng_seed, self.step_ctr)
             return

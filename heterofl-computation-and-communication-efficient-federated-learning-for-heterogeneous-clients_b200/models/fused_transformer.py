@@ -73,6 +73,10 @@ class FusedTransformer:
         # fused vocabulary head (csrc/lm_vocab_tcgen05.cu): decoder.linear2 + label mask + cross-entropy forward and
         # backward in three launches, no [tokens, vocabulary] tensor in memory
         self.vocab_fused = os.environ.get("HFL_LM_VOCAB_FUSED", "1") != "0"
+        # row-sparse token-table gradient: the optimiser applies it to the <= N*S touched rows only (csrc/optim_kernels.cu);
+        # the trainer switches it off when gradients are all-reduced densely (data-parallel centralised training)
+        self.emb_sparse = os.environ.get("HFL_LM_EMB_SPARSE", "1") != "0"
+        self.emb_src: Optional[torch.Tensor] = None      # int32 [N*S]: table row read by every token of the last step
         self.keep_last = False                     # numerics tests: keep the forward intermediates of the last step
         self.last: Dict = {}
 
@@ -134,6 +138,38 @@ class FusedTransformer:
         y = dy.t() @ x
         return y if alpha == 1.0 else y * alpha
 
+    # -- evaluation: forward only ------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_hidden_eval(self, P: Dict[str, torch.Tensor], tokens: torch.Tensor, seed_t: torch.Tensor,
+                            step_t: torch.Tensor) -> torch.Tensor:
+        """Eval-mode forward (Scaler = identity, no dropout, 15 % [MASK] replacement as in every forward of the
+        reference, ``src/models/transformer.py:149-152``) up to the decoder LayerNorm on the fused kernels: returns
+        ``d`` ``[N*S, E]``; the caller applies the vocabulary projection / loss.  ~30 launches for any batch size instead
+        of the ~120 eager ops of the functional model."""
+        C = cu.C()
+        N, S = tokens.shape
+        H, V, L = self.H, self.V, self.L
+        E = P[EMB].shape[1]
+        att_scale = 1.0 / math.sqrt(E // H)
+        tok = tokens.reshape(-1).contiguous()
+        x = C.lm_embed_fwd(tok, P[EMB], P[POS], P["transformer_embedding.norm.weight"],
+                           P["transformer_embedding.norm.bias"], S, V, LN_EPS, self.mask_rate, 0.0, seed_t, step_t, 1)[0]
+        for l in range(L):
+            pre = "transformer_encoder.layers.%d" % l
+            q = self._lin(x, P[pre + ".mha.linear_q.weight"], P[pre + ".mha.linear_q.bias"], 1.0)
+            k = self._lin(x, P[pre + ".mha.linear_k.weight"], P[pre + ".mha.linear_k.bias"], 1.0)
+            v = self._lin(x, P[pre + ".mha.linear_v.weight"], P[pre + ".mha.linear_v.bias"], 1.0)
+            o = C.lm_attn_fwd(q, k, v, N, S, H, att_scale)[0]
+            oo = self._lin(o, P[pre + ".mha.linear_o.weight"], P[pre + ".mha.linear_o.bias"], 1.0)
+            x1 = C.lm_add_ln_fwd(x, oo, P[pre + ".norm1.weight"], P[pre + ".norm1.bias"], LN_EPS, 0.0, seed_t, step_t, 0)[0]
+            u = self._lin(x1, P[pre + ".linear1.weight"], P[pre + ".linear1.bias"], 1.0)
+            hh = C.lm_gelu_drop_fwd(u, 0.0, seed_t, step_t, 0)[0]
+            f = self._lin(hh, P[pre + ".linear2.weight"], P[pre + ".linear2.bias"], 1.0)
+            x = C.lm_add_ln_fwd(x1, f, P[pre + ".norm2.weight"], P[pre + ".norm2.bias"], LN_EPS, 0.0, seed_t, step_t, 0)[0]
+        du = self._lin(x, P["decoder.linear1.weight"], P["decoder.linear1.bias"], 1.0)
+        dg = C.lm_gelu_drop_fwd(du, 0.0, seed_t, step_t, 0)[0]
+        return C.lm_add_ln_fwd(None, dg, P["decoder.norm1.weight"], P["decoder.norm1.bias"], LN_EPS, 0.0, seed_t, step_t, 0)[0]
+
     # -- one step --------------------------------------------------------------------------------------------
     def train_step(self, P: Dict[str, torch.Tensor], tokens: torch.Tensor, label_mask: Optional[torch.Tensor],
                    meter: Optional[Tuple[torch.Tensor, float]], seed_t: torch.Tensor, step_t: torch.Tensor,
@@ -152,7 +188,10 @@ class FusedTransformer:
         tok = tokens.reshape(-1).contiguous()
         G: Dict[str, torch.Tensor] = {}
         self._small.zero_()
-        self._big.zero_()
+        if self.emb_sparse:
+            self._big_views[POS].zero_()      # the token-table rows are re-zeroed by the sparse optimiser pass
+        else:
+            self._big.zero_()
         sg = self._small_views
 
         # ---- forward ---------------------------------------------------------------------------------------
@@ -259,4 +298,5 @@ class FusedTransformer:
         for k_, v_ in sg.items():
             G[k_] = v_
         G[EMB], G[POS] = self._big_views[EMB], self._big_views[POS]
+        self.emb_src = src
         return loss.view(()), G

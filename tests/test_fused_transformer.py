@@ -391,3 +391,82 @@ def test_fused_vocab_head_matches_torch(M, E, V, masked):
     meter2 = torch.zeros(4, dtype=torch.float64, device=dev)
     loss2, _, _ = C.lm_vocab_head(d, W, b, tgt, mask, float(M), meter2, None, False)
     assert float(loss2) == pytest.approx(float(loss), rel=1e-5)
+
+
+@pytest.mark.gpu
+def test_fused_eval_forward_matches_functional_model():
+    """Evaluation forward on the fused LM kernels (encoder up to the decoder LayerNorm) == the functional eval-mode model
+    with the [MASK] replacement switched off on both sides."""
+    cu = _cu()
+    from hfl_b200.models import Model
+    from hfl_b200.models.fused_transformer import FusedTransformer
+    from hfl_b200.models.transformer import transformer_forward
+    from hfl_b200.ops.nn import NormCtx
+    from hfl_b200.plan.spec import build_spec
+    dev = torch.device("cuda")
+    V = 1000
+    cfg = make_cfg("WikiText2", "transformer", "1_100_0.1_iid_fix_a5-b5_none_1_1", num_tokens=V, classes_size=V)
+    spec = build_spec(cfg)
+    model = Model(spec, cfg, 1.0, True)
+    torch.manual_seed(5)
+    arena = model.new_arena(dev)
+    for k, v in model.layout.views(arena).items():
+        if v.dim() == 1:
+            v.add_(0.1 * torch.randn_like(v))
+    Pv = model.layout.views(arena.bfloat16())
+    N = 24
+    tokens = torch.randint(0, V, (N, 64), device=dev)
+    ft = FusedTransformer(spec, model.scale_rate, mask_rate=0.0, dropout=0.0)
+    seed, step = _rng(dev)
+    d = ft.forward_hidden_eval(Pv, tokens, seed, step)
+    z = torch.nn.functional.linear(d.float(), Pv["decoder.linear2.weight"].float(), Pv["decoder.linear2.bias"].float())
+    P32 = {k: v.float() for k, v in Pv.items()}
+    ref = transformer_forward(spec, P32, {"label": tokens, "mlm_mask": torch.zeros(N, 64, dtype=torch.bool, device=dev)},
+                              NormCtx("eval"), model.scale_rate, None, "raw", 0.0, 0.0)["logits"]
+    torch.cuda.synchronize()
+    lf = torch.nn.functional.cross_entropy(z, tokens.reshape(-1))
+    lr = torch.nn.functional.cross_entropy(ref.float(), tokens.reshape(-1))
+    assert float(lf) == pytest.approx(float(lr), rel=2e-2)
+    cos = float(torch.nn.functional.cosine_similarity(z.reshape(-1), ref.float().reshape(-1), dim=0))
+    assert cos > 0.995, cos
+
+
+@pytest.mark.gpu
+def test_sparse_embedding_optimizer_matches_dense(monkeypatch):
+    """Row-sparse token-table update (dense zero-gradient pass + correction of the touched rows) == the dense update:
+    two TrainSlots with the same seed, one per mode, agree after graph-replayed steps (same kernels, same RNG; only the
+    fp32 rounding order of the token-table update differs)."""
+    _cu()
+    from hfl_b200.fed.trainer import TrainSlot
+    from hfl_b200.models import Model
+    from hfl_b200.plan.spec import build_spec
+    dev = torch.device("cuda")
+    V = 600
+    cfg = make_cfg("WikiText2", "transformer", "1_100_0.1_iid_fix_a5-b5_none_1_1", num_tokens=V, classes_size=V)
+    spec = build_spec(cfg)
+    model = Model(spec, cfg, 1.0, True)
+    torch.manual_seed(0)
+    arena = model.new_arena(dev)
+    mask = torch.ones(V + 1, dtype=torch.uint8)
+    mask[V] = 0
+    base = torch.randint(0, 40, (1, 64), device=dev)
+    rows = base.repeat(1, 6)
+    outs = []
+    for sparse in ("1", "0"):
+        monkeypatch.setenv("HFL_LM_EMB_SPARSE", sparse)
+        slot = TrainSlot(model, cfg, dev, torch.bfloat16, True)
+        assert slot.fused.emb_sparse == (sparse == "1")
+        slot.load_params(arena.clone())
+        slot.begin_client(0.1, mask, rng_seed=11)
+        for _ in slot.train_lm(rows, 1, 64):
+            pass
+        torch.cuda.synchronize()
+        outs.append((slot.w.clone(), slot.mom.clone(), slot.wc.float().clone(), slot.meter.buf.clone()))
+        if sparse == "1":
+            assert float(slot.fused._big_views["transformer_embedding.embedding.weight"].abs().max()) == 0.0
+    (wa, ma, ca, ta), (wb, mb, cb, tb) = outs
+    assert torch.allclose(ta, tb, rtol=2e-3, atol=1e-6)                 # same losses along the way
+    dw = (wa - arena).float()
+    assert float((wa - wb).abs().max()) <= 1e-5 * max(1.0, float(wa.abs().max())) + 2e-2 * float(dw.abs().max())
+    assert float((ma - mb).abs().max()) <= 2e-2 * max(1e-3, float(mb.abs().max()))
+    assert float((ca - cb).abs().max()) <= 2e-2 * max(1.0, float(cb.abs().max()))

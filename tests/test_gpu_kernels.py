@@ -19,6 +19,18 @@ def _cu():
     return cu
 
 
+@pytest.fixture(params=[1, 8], ids=["nosplit", "ksplit8"])
+def ksplit_cap(request):
+    """Run a convolution test without and with the cluster split-K path (8 CTAs per output tile, DSMEM reduction); the
+    production policy (csrc/conv_tcgen05.cu:conv_ksplit) only enables it from 4 ranks up."""
+    from hfl_b200.ops import cuda as cu
+    if not (torch.cuda.is_available() and cu.available()):
+        pytest.skip("needs the CUDA extension")
+    cu.C().conv_set_ksplit(request.param)
+    yield request.param
+    cu.C().conv_set_ksplit(-1)
+
+
 def test_extension_loaded():
     cu = _cu()
     assert cu.launch_count() >= 0
@@ -351,7 +363,7 @@ def test_tcgen05_gemm_matches_torch(M, N, K):
                                                (10, 32, 32, 32, 3, 1), (10, 16, 32, 16, 3, 1), (10, 8, 32, 8, 3, 1),
                                                (10, 32, 32, 64, 3, 2), (10, 16, 16, 32, 1, 2), (10, 8, 32, 16, 3, 2),
                                                (7, 128, 8, 64, 3, 1), (10, 96, 16, 160, 3, 1)])
-def test_tcgen05_conv_fprop_matches_torch(N, C, H, K, R, stride):
+def test_tcgen05_conv_fprop_matches_torch(N, C, H, K, R, stride, ksplit_cap):
     cu = _cu()
     dev = torch.device("cuda")
     torch.manual_seed(N + C + K + R)
@@ -381,7 +393,7 @@ def test_tcgen05_conv_fprop_matches_torch(N, C, H, K, R, stride):
                                                             (10, 256, 8, 256, 1, True, None), (10, 512, 4, 512, 1, True, 3),
                                                             (10, 16, 32, 16, 1, True, 7), (10, 8, 32, 16, 2, False, None),
                                                             (10, 128, 16, 128, 1, True, 10)])
-def test_conv_bn_act_fused_matches_unfused(N, C, H, K, stride, with_res, nvalid, monkeypatch):
+def test_conv_bn_act_fused_matches_unfused(N, C, H, K, stride, with_res, nvalid, monkeypatch, ksplit_cap):
     """conv -> (residual + batch statistics in the tcgen05 epilogue) -> bn_apply_sums  ==  conv -> bn_act_fwd, also
     with a padded partial batch, over two consecutive calls (the scratch must come back zeroed)."""
     cu = _cu()
@@ -458,7 +470,7 @@ def test_tcgen05_gemm_general_layouts(a_mn, b_mn, M, N, K):
 @pytest.mark.parametrize("N,C,H,K,R", [(10, 64, 32, 64, 3), (10, 128, 16, 128, 3), (10, 64, 16, 128, 3), (10, 256, 8, 256, 3),
                                         (10, 512, 4, 512, 3), (4, 128, 16, 64, 1), (10, 32, 32, 32, 3), (10, 16, 32, 16, 3),
                                         (10, 8, 16, 8, 3), (10, 32, 16, 64, 3), (10, 64, 16, 32, 3), (6, 16, 8, 24, 1)])
-def test_tcgen05_conv_dgrad_matches_autograd(N, C, H, K, R):
+def test_tcgen05_conv_dgrad_matches_autograd(N, C, H, K, R, ksplit_cap):
     """Stride-1 data gradient on the implicit-GEMM kernel (mirrored taps, MN-major filter operand)."""
     cu = _cu()
     dev = torch.device("cuda")
@@ -480,7 +492,7 @@ def test_tcgen05_conv_dgrad_matches_autograd(N, C, H, K, R):
 
 @pytest.mark.parametrize("N,C,H,K,R", [(10, 64, 32, 128, 3), (10, 128, 16, 256, 3), (10, 256, 8, 512, 3), (10, 64, 32, 128, 1),
                                         (10, 16, 32, 32, 3), (10, 8, 16, 16, 1), (3, 32, 16, 64, 3)])
-def test_tcgen05_conv_dgrad_stride2_matches_autograd(N, C, H, K, R):
+def test_tcgen05_conv_dgrad_stride2_matches_autograd(N, C, H, K, R, ksplit_cap):
     """Data gradient of a stride-2 convolution: the four output-parity classes (1 / 2 / 2 / 4 taps for a 3x3 filter, a
     single class for 1x1 with the other three written as zeros) run inside one launch of the implicit-GEMM kernel."""
     cu = _cu()
