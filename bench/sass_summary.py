@@ -10,8 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = glob.glob(os.path.join(ROOT, "heterofl*_b200"))[0]
 OBJ = os.path.join(PKG, "ops", "_build")
 OUT = os.path.join(ROOT, "profiles", "sass")
-KEYS = ["UTCHMMA", "UTMALDG", "UTMALDG.2D.MULTICAST", "LDTM", "UTCBAR", "UTCBAR.MULTICAST", "UTCATOMSWS", "UCGABAR_ARV",
-        "SYNCS", "ATOMS", "ATOMG", "RED", "BAR", "LDG", "STG", "LDS", "STS", "SHFL", "MUFU", "HFMA2"]
+KEYS = ["UTCHMMA", "UTCQMMA", "UTCCP", "HMMA", "UTMALDG", "UTMALDG.2D.MULTICAST", "UBLKCP", "LDTM", "UTCBAR", "UTCBAR.MULTICAST",
+        "UTCATOMSWS", "UCGABAR_ARV", "UCGABAR_WAIT", "MAPA", "ACQBULK", "PREEXIT", "SYNCS", "ATOMS", "ATOMG", "RED", "BAR", "LDG", "STG",
+        "LDS", "STS", "SHFL", "MUFU", "HFMA2"]
 
 
 def sass(obj, fun=None):
@@ -26,8 +27,14 @@ def main():
              "(kind::f16), `UTMALDG` = TMA cp.async.bulk.tensor (`.MULTICAST` = cluster multicast), `LDTM` = tcgen05.ld,",
              "`UTCBAR` = tcgen05.commit -> mbarrier (`.MULTICAST` = arrive on the same barrier in every CTA of the mask),",
              "`SYNCS` = mbarrier ops, `UCGABAR_ARV` = cluster barrier, `ATOMS`/`RED`/`ATOMG` = shared/global atomics; `LDG.E...` on",
-             "peer-mapped pointers are the P2P loads of `aggregate_kernel`.  Full listings: `gemm_mc_tcgen05.sass` (cluster +",
-             "multicast GEMM, all variants), `gemm_tcgen05.sass` (one TN and one general instantiation), `conv_tcgen05.sass`", "(fprop<128> without residual/statistics + wgrad).", ""]
+             "peer-mapped pointers are the P2P loads of `aggregate_kernel`.  `UTCQMMA` / `UTCCP` / `UBLKCP` = block-scaled",
+             "tcgen05.mma (MXFP8), tcgen05.cp of the scale factors, cp.async.bulk; `HMMA` = mma.sync (attention kernels);",
+             "`ACQBULK` / `PREEXIT` = griddepcontrol.wait / launch_dependents (programmatic dependent launch, every kernel);",
+             "`UCGABAR_ARV` / `UCGABAR_WAIT` + `MAPA` + `LD...` on `shared::cluster` = the cluster split-K reduction of the",
+             "convolution and the cluster BatchNorm kernels.  Full listings: `gemm_mc_tcgen05.sass` (cluster + multicast GEMM,",
+             "all variants), `gemm_tcgen05.sass` (one TN and one general instantiation), `conv_tcgen05.sass` (fprop<128> with",
+             "residual + statistics, incl. the split-K path; dgrad<128>; wgrad), `lm_vocab_tcgen05.sass` (fused vocabulary",
+             "head, backward kernel), `lm_attn_mma.sass` (tensor-core attention).", ""]
     for obj in sorted(glob.glob(os.path.join(OBJ, "*.cu.o"))):
         txt = sass(obj)
         kernels = re.findall(r"Function : (\S+)", txt)
@@ -65,7 +72,10 @@ def main():
     open(os.path.join(OUT, "gemm_tcgen05.sass"), "w").write(
         pick("gemm_tcgen05.cu.o", [r"gemm_tcgen05_kernelILi128ELb1ELi2ELb0", r"gemm_tcgen05_general_kernelILi128ELb1ELb1ELb1"]))
     open(os.path.join(OUT, "conv_tcgen05.sass"), "w").write(
-        pick("conv_tcgen05.cu.o", [r"conv_fprop_tcgen05_kernelILi128ELb0ELb0ELb0", r"conv_wgrad_tcgen05_kernel"]))
+        pick("conv_tcgen05.cu.o", [r"conv_fprop_tcgen05_kernelILi128ELb0ELb1ELb1", r"conv_fprop_tcgen05_kernelILi128ELb1ELb0ELb0",
+                                   r"conv_wgrad_tcgen05_kernel"]))
+    open(os.path.join(OUT, "lm_vocab_tcgen05.sass"), "w").write(pick("lm_vocab_tcgen05.cu.o", [r"lm_vocab_bwd_kernel"]))
+    open(os.path.join(OUT, "lm_attn_mma.sass"), "w").write(sass(os.path.join(OBJ, "lm_attn_mma.cu.o")))
 
 
 if __name__ == "__main__":
