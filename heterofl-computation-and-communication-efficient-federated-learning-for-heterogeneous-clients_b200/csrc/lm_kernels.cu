@@ -605,14 +605,18 @@ extern "C" void hfl_lm_attn_fwd_mma(const void*, const void*, const void*, int, 
                                     cudaStream_t);
 extern "C" int hfl_lm_attn_bwd_mma(const void*, const void*, const void*, const void*, const void*, const void*, int, int,
                                    int, int, float, void*, void*, void*, float*, float*, float*, float, int, cudaStream_t);
-static bool attn_mma_enabled() {
-  static const bool on = []() { const char* e = getenv("HFL_LM_ATTN_MMA"); return e == nullptr || e[0] != '0'; }();
-  return on;
+// Dispatch (measured, profiles/pdl_conv_ab.md + profiles/prof_attn_mma.md): the federated step has N*H = 8 (row, head) pairs --
+// there the CUDA-core kernels, which split a pair over 4-8 CTAs, finish in 7.3 / 9.3 us against 10.3 / 17.5 us for the
+// one-CTA-per-pair mma kernels; from a few dozen pairs up (evaluation: 6 400, centralised training) the machine is full
+// either way and the contraction belongs on the tensor cores.  HFL_LM_ATTN_MMA=1 / 0 forces one path.
+static bool attn_mma_enabled(int pairs) {
+  static const int mode = []() { const char* e = getenv("HFL_LM_ATTN_MMA"); return e == nullptr ? -1 : (e[0] != '0' ? 1 : 0); }();
+  return mode < 0 ? pairs >= 32 : mode == 1;
 }
 
 extern "C" void hfl_lm_attn_fwd(const void* q, const void* k, const void* v, int N, int S, int H, int dh, float scale,
                                 void* o, void* P, cudaStream_t st) {
-  if (attn_mma_enabled()) { hfl_lm_attn_fwd_mma(q, k, v, N, S, H, dh, scale, o, P, st); return; }
+  if (attn_mma_enabled(N * H)) { hfl_lm_attn_fwd_mma(q, k, v, N, S, H, dh, scale, o, P, st); return; }
   launch_k(lm_attn_fwd_kernel, dim3(dim3(N * H, 4)), dim3(256), 0, st, (const bf16*)q, (const bf16*)k, (const bf16*)v, S, H, dh, scale,
                                                      (bf16*)o, (bf16*)P);
   count_launch();
@@ -621,7 +625,7 @@ extern "C" void hfl_lm_attn_fwd(const void* q, const void* k, const void* v, int
 extern "C" int hfl_lm_attn_bwd(const void* dO, const void* q, const void* k, const void* v, const void* O, const void* P,
                                int N, int S, int H, int dh, float scale, void* dq, void* dk, void* dv, float* dbq,
                                float* dbk, float* dbv, float alpha_v, int scale_dv, cudaStream_t st) {
-  if (attn_mma_enabled())
+  if (attn_mma_enabled(N * H))
     return hfl_lm_attn_bwd_mma(dO, q, k, v, O, P, N, S, H, dh, scale, dq, dk, dv, dbq, dbk, dbv, alpha_v, scale_dv, st);
   launch_k(lm_attn_bwd_kernel, dim3(dim3(N * H, 8)), dim3(256), 0, st, (const bf16*)dO, (const bf16*)q, (const bf16*)k, (const bf16*)v,
                                                      (const bf16*)O, (const bf16*)P, S, H, dh, scale, (bf16*)dq,

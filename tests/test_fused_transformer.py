@@ -128,7 +128,9 @@ def test_gelu_dropout_fwd_bwd(M, Fd, p):
     _close(out, 0.5 * dh.float().sum(0), 1e-2, "colsum")
 
 
-@pytest.mark.parametrize("N,S,H,dh", [(1, 64, 8, 32), (3, 64, 8, 16), (2, 36, 8, 2), (2, 64, 4, 8)])
+@pytest.mark.parametrize("N,S,H,dh", [(1, 64, 8, 32), (3, 64, 8, 16), (2, 36, 8, 2), (2, 64, 4, 8),
+                                      # >= 32 (row, head) pairs: the tensor-core (mma.sync) kernels are dispatched
+                                      (6, 64, 8, 32), (5, 64, 8, 16), (16, 36, 8, 2), (9, 64, 4, 8), (40, 50, 8, 32)])
 def test_attention_fwd_bwd(N, S, H, dh):
     C = _cu().C()
     dev = torch.device("cuda")
