@@ -776,6 +776,7 @@ class Engine:
             self.logger.safe(False)
             if self.opt.save and self.info.is_main:
                 self.save_checkpoint(self.epoch, None)
+            self.logger.reset()
         self.logger.safe(False)
 
     def _log_round(self, res: Dict, dt: float) -> None:
