@@ -1,19 +1,33 @@
-// Implicit-GEMM convolution forward on tcgen05 / TMEM, operands fed by TMA (sm_100a).
+// Implicit-GEMM convolution forward / data gradient / weight gradient on tcgen05 / TMEM, operands fed by TMA (sm_100a).
 //
 //   Y[n, oh, ow, k] = sum_{r,s,c} X[n, oh*stride + r - pad, ow*stride + s - pad, c] * Wt[k, r, s, c]   (+ residual)
 //
 // X, Y are NHWC bf16, Wt is K,R,S,C bf16 (the layout the parameter arenas store, plan/layout.py), fp32 accumulation.
+// Reference ops: every nn.Conv2d of src/models/resnet.py:44-50,140-158 (and their autograd backward).
 // GEMM view: M = N*OH*OW output pixels, N = K_out, K = R*S*C.  One CTA computes a 128-pixel x BLOCK_N tile:
 //
 //   * the 128 pixels are a (bn images) x (bh rows) x (OW columns) brick, so the A-operand slice for filter tap (r,s)
 //     and channel block cb is ONE 4-D TMA box {64 ch, OW, bh, bn} of X starting at the tap's halo offset -- padding is
 //     the TMA unit's out-of-bounds zero fill, stride-2 is the tensor map's traversal stride.  No im2col buffer, no
 //     index arithmetic in the kernel: the producer warp only changes box coordinates.
-//   * B-operand slices are 2-D boxes of the [K_out, R*S*C] filter matrix; both land in 128B-swizzled smem and are
-//     consumed by tcgen05.mma (M128 x BLOCK_N x K16, cta_group::1) issued by one elected thread; a 4-stage mbarrier
-//     ring overlaps TMA with MMA; the accumulator lives in TMEM and is drained by 4 epilogue warps with tcgen05.ld.
-//   * epilogue: optional residual add, bf16 store, and (optional) per-channel sum / sum-of-squares of the tile
-//     (BatchNorm batch statistics of the conv output) reduced in-warp and atomically added to a [2, K_out] buffer.
+//   * B-operand slices are 3-D boxes {64 c, 1 tap, BLOCK_N k} of the filter seen as {C, R*S, K_out}; both land in
+//     128B-swizzled smem and are consumed by tcgen05.mma (M128 x BLOCK_N x K16, cta_group::1) issued by one elected
+//     thread; a 4-stage mbarrier ring overlaps TMA with MMA; the accumulator lives in TMEM and is drained by 4 epilogue
+//     warps with tcgen05.ld.
+//   * channel counts: any multiple of 8 (16-byte global strides).  A partial 64-channel block -- the narrow HeteroFL
+//     levels have 8..32 channels -- is TMA zero fill on both operands; BLOCK_N is 32 / 64 / 128 and the epilogue masks
+//     the columns beyond K_out.
+//   * epilogue (fprop): optional residual add, bf16 store, optional per-channel sum / sum-of-squares of the rounded
+//     outputs (BatchNorm batch statistics of the NEXT norm: it becomes an apply-only pass, norm_kernels.cu
+//     hfl_bn_apply_sums), optional device-side `nvalid` (padding samples of a partial batch: zeros, out of the sums).
+//   * data gradient: the same kernel with mirrored taps and the filter read MN-major in place (no transposed / flipped
+//     weight copy); a stride-2 gradient runs as four output-parity classes inside one launch (ConvGeom::taps).
+//   * split-K (deep reductions, few tiles: the 256- / 512-channel layers of a batch-10 step): thread-block clusters
+//     {1,1,ksplit}; every CTA reduces a k-range of the SAME tile into its own TMEM accumulator, stages it as fp32 in its
+//     shared memory, and after a cluster barrier CTA z sums rows [z*128/ksplit, ...) of all peers through DSMEM and runs
+//     the normal epilogue on them.  No atomics, no zero-filled scratch, no second kernel.
+//   * every launch carries the programmatic-dependent-launch attribute; griddepcontrol.wait sits after the barrier /
+//     TMEM / descriptor set-up (common.cuh).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
