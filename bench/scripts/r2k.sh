@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out/r2k
 O=gpurun_out/r2k
-python -m pytest tests/test_fused_transformer.py -m gpu -q -k "eval_forward or sparse_embedding or vocab_head" 2>&1 | tail -12 | tee $O/t_new.log
+python -m pytest tests/test_fused_transformer.py tests/test_gpu_kernels.py -m gpu -q -k "eval_forward or sparse_embedding or vocab_head or attention or shortcut_fold" 2>&1 | tail -12 | tee $O/t_new.log
 python -m pytest tests -m gpu -q 2>&1 | tail -8 | tee $O/t_all.log
 run() {
   name=$1; shift
@@ -24,6 +24,7 @@ run lm_d_default -- --config wikitext --steps 3 --warmup 3
 run c2_a_default -- --steps 5 --warmup 3
 run c2_b_ghostcluster HFL_BN_GHOST_CLUSTER=1 -- --steps 5 --warmup 3
 run c2_c_default -- --steps 5 --warmup 3
+run c2_d_nofold HFL_CONV_SC_FOLD=0 -- --steps 5 --warmup 3
 probe() {
   name=$1; cfg=$2; shift; shift
   env "$@" timeout 400 python bench/step_probe2.py --config $cfg > $O/probe_$name.json 2> $O/probe_$name.err

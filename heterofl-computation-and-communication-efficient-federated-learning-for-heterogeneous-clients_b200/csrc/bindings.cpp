@@ -90,6 +90,8 @@ int hfl_conv_tc_supported(int, int, int, int, int, int, int, int);
 void hfl_conv_set_ksplit(int);
 int hfl_conv_fprop_tc(const void*, const void*, void*, const void*, float*, const int*, int, int, int, int, int, int, int,
                       int, cudaStream_t);
+int hfl_conv_fprop_tc2(const void*, const void*, void*, const void*, float*, const int*, int, int, int, int, int, int, int,
+                       int, const void*, const void*, int, int, cudaStream_t);
 int hfl_gemm_bf16_general(const void*, int, int, const void*, int, int, void*, int, int, float, int, int, int, int,
                           cudaStream_t);
 int hfl_gemm_general_splits(int, int, int);
@@ -884,8 +886,11 @@ bool conv_tc_supported(int64_t N, int64_t H, int64_t W, int64_t C, int64_t Kout,
 
 // x: [N, C, H, W] channels-last bf16; w: [K, C, R, S] with channels-last strides (physically K,R,S,C);
 // residual: like the output (optional); stats: fp32 [2, K] accumulated in place (optional).  padding = R/2.
+// x2 / w2 (optional): block input [N, C2, s2*OH, s2*OW] and 1x1 shortcut filter [K, C2, 1, 1]; their stride-s2 convolution is
+// accumulated into the same output tile (one launch for  conv2(o2) + shortcut(o1)  of a ResNet transition block)
 torch::Tensor conv_fprop_tc(torch::Tensor x, torch::Tensor w, c10::optional<torch::Tensor> residual,
-                            c10::optional<torch::Tensor> stats, int64_t stride, c10::optional<torch::Tensor> nvalid) {
+                            c10::optional<torch::Tensor> stats, int64_t stride, c10::optional<torch::Tensor> nvalid,
+                            c10::optional<torch::Tensor> x2, c10::optional<torch::Tensor> w2, int64_t stride2) {
   CHECK_CUDA_T(x); CHECK_CUDA_T(w);
   TORCH_CHECK(x.dim() == 4 && w.dim() == 4 && x.scalar_type() == torch::kBFloat16 && w.scalar_type() == torch::kBFloat16);
   TORCH_CHECK(x.is_contiguous(torch::MemoryFormat::ChannelsLast), "conv_fprop_tc: x must be channels-last");
@@ -908,7 +913,21 @@ torch::Tensor conv_fprop_tc(torch::Tensor x, torch::Tensor w, c10::optional<torc
   if (stats.has_value()) { TORCH_CHECK(stats->scalar_type() == torch::kFloat32 && stats->numel() >= 2 * K && stats->is_contiguous()); sp = stats->data_ptr<float>(); }
   const int* nvp = nullptr;   // int32 [1] on the device: samples >= *nvalid are padding (zero outputs, no statistics)
   if (nvalid.has_value()) { TORCH_CHECK(nvalid->is_cuda() && nvalid->scalar_type() == torch::kInt32); nvp = nvalid->data_ptr<int>(); }
-  int e = hfl_conv_fprop_tc(x.data_ptr(), w.data_ptr(), y.data_ptr(), rp, sp, nvp, N, H, W, C, K, R, S, (int)stride, cur_stream());
+  const void* x2p = nullptr;
+  const void* w2p = nullptr;
+  int C2 = 0;
+  if (x2.has_value()) {
+    TORCH_CHECK(w2.has_value() && x2->dim() == 4 && x2->scalar_type() == torch::kBFloat16 && w2->scalar_type() == torch::kBFloat16);
+    TORCH_CHECK(x2->is_contiguous(torch::MemoryFormat::ChannelsLast), "conv_fprop_tc: x2 must be channels-last");
+    C2 = x2->size(1);
+    TORCH_CHECK(x2->size(0) == N && x2->size(2) == OH * stride2 && x2->size(3) == OW * stride2, "conv_fprop_tc: x2 extent");
+    TORCH_CHECK(w2->dim() == 4 && w2->size(0) == K && w2->size(1) == C2 && w2->size(2) == 1 && w2->size(3) == 1 &&
+                w2->permute({0, 2, 3, 1}).is_contiguous(), "conv_fprop_tc: w2 must be a [K, C2, 1, 1] filter");
+    x2p = x2->data_ptr();
+    w2p = w2->data_ptr();
+  }
+  int e = hfl_conv_fprop_tc2(x.data_ptr(), w.data_ptr(), y.data_ptr(), rp, sp, nvp, N, H, W, C, K, R, S, (int)stride, x2p, w2p, C2,
+                             (int)stride2, cur_stream());
   TORCH_CHECK(e == 0, "conv_fprop_tc failed with code ", e);
   return y;
 }
@@ -1135,7 +1154,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lm_max_e", &hfl_lm_max_e);
   m.def("conv_tc_supported", &conv_tc_supported);
   m.def("conv_fprop_tc", &conv_fprop_tc, py::arg("x"), py::arg("w"), py::arg("residual"), py::arg("stats"), py::arg("stride"),
-        py::arg("nvalid") = py::none());
+        py::arg("nvalid") = py::none(), py::arg("x2") = py::none(), py::arg("w2") = py::none(), py::arg("stride2") = 1);
   m.def("conv_dgrad_tc", &conv_dgrad_tc, py::arg("dy"), py::arg("w"), py::arg("residual"), py::arg("stride") = 1);
   m.def("conv_dgrad_tc_supported", &conv_dgrad_tc_supported);
   m.def("conv_set_ksplit", [](int64_t cap) { hfl_conv_set_ksplit((int)cap); });

@@ -55,6 +55,10 @@ struct ConvGeom {
   int out_s, out_H, out_W; // output pixel stride / extent (dgrad: dX; fprop: out_s = 1, OH, OW)
   int ntaps[4];
   int taps[4][9];
+  // forward only: a second operand pair accumulated into the same tile -- the 1x1 stride-`stride2` shortcut convolution
+  // of a ResNet transition block (src/models/resnet.py:44-50: out = conv2(..) + shortcut(x)): kb2 extra k-blocks whose
+  // A boxes come from tmap_x2 (the block input) and whose B boxes come from tmap_w2 (the shortcut filter)
+  int kb2, stride2;
 };
 
 // Column sums over the 32 lanes of a warp: on return lane j holds sum_over_lanes(v[j]) in v[0]  (31 shuffles).
@@ -107,6 +111,7 @@ struct ConvSmem {
 template <int BLOCK_N, bool DGRAD, bool HAS_RES, bool HAS_STATS>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                          const __grid_constant__ CUtensorMap tmap_x2, const __grid_constant__ CUtensorMap tmap_w2,
                           __nv_bfloat16* __restrict__ Y, const __nv_bfloat16* __restrict__ residual,
                           float* __restrict__ stats /* [2, Kout] or null */, const int* __restrict__ nvalid, const ConvGeom g) {
   extern __shared__ uint8_t smem_raw[];
@@ -125,7 +130,8 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
   const int n0 = tile_n * g.bn, oh0 = tile_h * g.bh;
   const int n_blk = blockIdx.y;
   const int cblocks = (g.C + CV_BLOCK_K - 1) / CV_BLOCK_K;   // a partial last block is zero-filled by the TMA unit
-  const int num_k_all = (DGRAD ? g.ntaps[cls] : g.R * g.S) * cblocks;   // 0: a class no filter tap reaches (zeros)
+  const int num_k_main = (DGRAD ? g.ntaps[cls] : g.R * g.S) * cblocks;  // 0: a class no filter tap reaches (zeros)
+  const int num_k_all = num_k_main + (DGRAD ? 0 : g.kb2);               // + k-blocks of the folded shortcut convolution
   // split-K (gridDim.z > 1, launched as thread-block clusters {1, 1, ksplit}): the deep-K layers of a batch-10 step
   // have 2-8 output tiles and 36-72 k-blocks each; the CTAs of a cluster reduce disjoint k-ranges of ONE tile into
   // their own TMEM accumulators and combine them through distributed shared memory (no atomics, no zero-filled
@@ -157,12 +163,20 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
       for (int kb = 0; kb < num_k; ++kb) {
         const int st = kb % CV_STAGES;
         const uint32_t ph = (kb / CV_STAGES) & 1;
-        const int tap = (kb0 + kb) / cblocks, cb = (kb0 + kb) - tap * cblocks;
+        const int kg = kb0 + kb;
+        const int tap = kg / cblocks, cb = kg - tap * cblocks;
         const int r = tap / g.S, s = tap - r * g.S;
         mbar_wait(&empty_bar[st], ph ^ 1);
         uint8_t* sa = smem + st * S::STAGE_BYTES;
         uint8_t* sb = sa + S::A_BYTES;
         mbar_expect_tx(&full_bar[st], S::STAGE_BYTES);
+        if (!DGRAD && kg >= num_k_main) {
+          // folded 1x1 shortcut: A = the block input at the strided output positions, B = the shortcut filter
+          const int cb2 = kg - num_k_main;
+          tma_load_4d(sa, &tmap_x2, &full_bar[st], cb2 * CV_BLOCK_K, 0, oh0 * g.stride2, n0);
+          tma_load_3d(sb, &tmap_w2, &full_bar[st], cb2 * CV_BLOCK_K, 0, n_blk * BLOCK_N);
+          continue;
+        }
         if (!DGRAD) {
           // A: box {64ch, bw, bh, bn} at (c, w, h, n) = (cb*64, s - pad, oh0*stride + r - pad, n0); halo -> zero fill
           tma_load_4d(sa, &tmap_x, &full_bar[st], cb * CV_BLOCK_K, s - g.pad, oh0 * g.stride + r - g.pad, n0);
@@ -396,8 +410,9 @@ static int make_tmap_filter_bf16(CUtensorMap* m, const void* Wt, int C, int taps
 }
 
 template <int BLOCK_N, bool DGRAD, bool HAS_RES, bool HAS_STATS>
-static int launch_conv_v(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, const void* residual, float* stats,
-                         const int* nvalid, const ConvGeom& g, int tiles_m, int n_tiles, int ksplit, cudaStream_t stream) {
+static int launch_conv_v(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tx2, const CUtensorMap& tw2, void* Y,
+                         const void* residual, float* stats, const int* nvalid, const ConvGeom& g, int tiles_m, int n_tiles,
+                         int ksplit, cudaStream_t stream) {
   auto kern = conv_fprop_tcgen05_kernel<BLOCK_N, DGRAD, HAS_RES, HAS_STATS>;
   constexpr int smem = ConvSmem<BLOCK_N>::TOTAL;
   static bool configured = false;
@@ -427,7 +442,8 @@ static int launch_conv_v(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, 
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tx, tw, (__nv_bfloat16*)Y, (const __nv_bfloat16*)residual, stats, nvalid, g);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tx, tw, tx2, tw2, (__nv_bfloat16*)Y, (const __nv_bfloat16*)residual, stats,
+                                     nvalid, g);
   count_launch();
   return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }
@@ -461,17 +477,19 @@ static int conv_ksplit(int tiles, int num_k) {
 template <int BLOCK_N, bool DGRAD = false>
 static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, void* Y, const void* residual, float* stats,
                        const int* nvalid, const ConvGeom& g, int tiles_m, int n_tiles, cudaStream_t stream,
-                       int num_k_hint = -1) {
+                       int num_k_hint = -1, const CUtensorMap* tx2p = nullptr, const CUtensorMap* tw2p = nullptr) {
+  const CUtensorMap& tx2 = tx2p ? *tx2p : tx;      // unused copies when no second operand pair is folded in
+  const CUtensorMap& tw2 = tw2p ? *tw2p : tw;
   if (residual != nullptr && (reinterpret_cast<uintptr_t>(residual) & 15) != 0) return -3;
   if ((reinterpret_cast<uintptr_t>(Y) & 15) != 0) return -3;
   const int num_k = num_k_hint >= 0 ? num_k_hint : g.R * g.S * ((g.C + CV_BLOCK_K - 1) / CV_BLOCK_K);
   const int ks = conv_ksplit(tiles_m * n_tiles, num_k);
   if (residual != nullptr) {
-    if (stats != nullptr) return launch_conv_v<BLOCK_N, DGRAD, true, true>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, ks, stream);
-    return launch_conv_v<BLOCK_N, DGRAD, true, false>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, ks, stream);
+    if (stats != nullptr) return launch_conv_v<BLOCK_N, DGRAD, true, true>(tx, tw, tx2, tw2, Y, residual, stats, nvalid, g, tiles_m, n_tiles, ks, stream);
+    return launch_conv_v<BLOCK_N, DGRAD, true, false>(tx, tw, tx2, tw2, Y, residual, stats, nvalid, g, tiles_m, n_tiles, ks, stream);
   }
-  if (stats != nullptr) return launch_conv_v<BLOCK_N, DGRAD, false, true>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, ks, stream);
-  return launch_conv_v<BLOCK_N, DGRAD, false, false>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, ks, stream);
+  if (stats != nullptr) return launch_conv_v<BLOCK_N, DGRAD, false, true>(tx, tw, tx2, tw2, Y, residual, stats, nvalid, g, tiles_m, n_tiles, ks, stream);
+  return launch_conv_v<BLOCK_N, DGRAD, false, false>(tx, tw, tx2, tw2, Y, residual, stats, nvalid, g, tiles_m, n_tiles, ks, stream);
 }
 
 // 0 if this problem can run on the tcgen05 path
@@ -489,9 +507,11 @@ extern "C" int hfl_conv_tc_supported(int N, int H, int W, int C, int Kout, int R
   return 0;
 }
 
-extern "C" int hfl_conv_fprop_tc(const void* X, const void* Wt, void* Y, const void* residual, float* stats,
-                                 const int* nvalid, int N, int H, int W, int C, int Kout, int R, int S, int stride,
-                                 cudaStream_t stream) {
+// X2 / Wt2 (optional): the block input [N, stride2*OH, stride2*OW, C2] and the 1x1 shortcut filter [Kout, C2] whose
+// stride-`stride2` convolution is accumulated into the same output tile (ResNet transition blocks).
+extern "C" int hfl_conv_fprop_tc2(const void* X, const void* Wt, void* Y, const void* residual, float* stats,
+                                  const int* nvalid, int N, int H, int W, int C, int Kout, int R, int S, int stride,
+                                  const void* X2, const void* Wt2, int C2, int stride2, cudaStream_t stream) {
   if (hfl_conv_tc_supported(N, H, W, C, Kout, R, S, stride) != 0) return -2;
   ConvGeom g;
   g.N = N; g.H = H; g.W = W; g.C = C; g.Kout = Kout; g.R = R; g.S = S; g.stride = stride; g.pad = R / 2;
@@ -505,8 +525,9 @@ extern "C" int hfl_conv_fprop_tc(const void* X, const void* Wt, void* Y, const v
   const int tiles_m = ((N + g.bn - 1) / g.bn) * g.tiles_h;
   g.tiles_m_cls = tiles_m; g.out_s = 1; g.out_H = g.OH; g.out_W = g.OW;
   for (int c = 0; c < 4; ++c) g.ntaps[c] = 0;
+  g.kb2 = 0; g.stride2 = 1;
   const int block_n = (Kout % 128 == 0) ? 128 : (Kout > 32 ? 64 : 32);
-  CUtensorMap tx, tw;
+  CUtensorMap tx, tw, tx2, tw2;
   // traversal strides: box extents are given in traversed elements (ceil(box/stride) elements are loaded)
   int r = make_tmap_nhwc_bf16(&tx, X, (uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N, CV_BLOCK_K,
                               (uint32_t)(g.bw * stride), (uint32_t)(g.bh * stride), (uint32_t)g.bn, (uint32_t)stride,
@@ -514,10 +535,30 @@ extern "C" int hfl_conv_fprop_tc(const void* X, const void* Wt, void* Y, const v
   if (r) return 1000 + r;
   r = make_tmap_filter_bf16(&tw, Wt, C, R * S, Kout, CV_BLOCK_K, block_n);
   if (r) return 2000 + r;
+  if (X2 != nullptr) {
+    if (C2 % 8 != 0 || (stride2 != 1 && stride2 != 2) || g.bw * stride2 > 256 || g.bh * stride2 > 256) return -4;
+    g.kb2 = (C2 + CV_BLOCK_K - 1) / CV_BLOCK_K;
+    g.stride2 = stride2;
+    r = make_tmap_nhwc_bf16(&tx2, X2, (uint64_t)C2, (uint64_t)g.OW * stride2, (uint64_t)g.OH * stride2, (uint64_t)N, CV_BLOCK_K,
+                            (uint32_t)(g.bw * stride2), (uint32_t)(g.bh * stride2), (uint32_t)g.bn, (uint32_t)stride2,
+                            (uint32_t)stride2, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r) return 3000 + r;
+    r = make_tmap_filter_bf16(&tw2, Wt2, C2, 1, Kout, CV_BLOCK_K, block_n);
+    if (r) return 4000 + r;
+  }
   const int n_tiles = (Kout + block_n - 1) / block_n;
-  if (block_n == 128) return launch_conv<128>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, stream);
-  if (block_n == 64) return launch_conv<64>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, stream);
-  return launch_conv<32>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, stream);
+  const int num_k = R * S * ((C + CV_BLOCK_K - 1) / CV_BLOCK_K) + g.kb2;
+  const CUtensorMap* p2 = X2 != nullptr ? &tx2 : nullptr;
+  const CUtensorMap* q2 = X2 != nullptr ? &tw2 : nullptr;
+  if (block_n == 128) return launch_conv<128>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, stream, num_k, p2, q2);
+  if (block_n == 64) return launch_conv<64>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, stream, num_k, p2, q2);
+  return launch_conv<32>(tx, tw, Y, residual, stats, nvalid, g, tiles_m, n_tiles, stream, num_k, p2, q2);
+}
+
+extern "C" int hfl_conv_fprop_tc(const void* X, const void* Wt, void* Y, const void* residual, float* stats,
+                                 const int* nvalid, int N, int H, int W, int C, int Kout, int R, int S, int stride,
+                                 cudaStream_t stream) {
+  return hfl_conv_fprop_tc2(X, Wt, Y, residual, stats, nvalid, N, H, W, C, Kout, R, S, stride, nullptr, nullptr, 0, 1, stream);
 }
 
 // Data gradient: dX[N,H,W,C] from dY[N,OH,OW,Kout] and the K,R,S,C filter, stride 1 or 2 (H = stride * OH).  `residual` is
@@ -545,6 +586,7 @@ extern "C" int hfl_conv_dgrad_tc(const void* dY, const void* Wt, void* dX, const
   g.tiles_h = (OH + g.bh - 1) / g.bh;
   const int tiles_m = ((N + g.bn - 1) / g.bn) * g.tiles_h;
   g.tiles_m_cls = tiles_m; g.out_s = stride; g.out_H = H; g.out_W = W;
+  g.kb2 = 0; g.stride2 = 1;
   const int ncls = stride * stride;
   int max_taps = 0;
   for (int cls = 0; cls < 4; ++cls) {

@@ -84,9 +84,14 @@ class FusedResNet:
         """3x3 convolution ``pend = (input, weight, stride, residual)`` followed by ``_nf`` -> (s, y, saved stats);
         BatchNorm models fuse the residual add and the batch statistics into the convolution's epilogue."""
         xin, w, stride, res = pend
+        shortcut = None
+        if isinstance(res, tuple):                        # ("conv", block input, shortcut filter, stride)
+            shortcut, res = res[1:], None
         if self.norm == "bn":
             return fo.conv_bn_act_fwd(xin, w, stride, 1, res, P[name + ".weight"], P[name + ".bias"], eps,
-                                      self._scratch(ws_tag, xin, w.shape[0]), nvalid)
+                                      self._scratch(ws_tag, xin, w.shape[0]), nvalid, shortcut=shortcut)
+        if shortcut is not None:
+            res = fo.conv_fwd(shortcut[0], shortcut[1], shortcut[2], 0)
         return self._nf(fo.conv_fwd(xin, w, stride, 1), res, P, name, eps, ws_tag, nvalid)
 
     def _nb(self, dy, dy2, dres, s, m, i, P, G, name, ws_tag, nvalid=None, **kw):
@@ -128,7 +133,9 @@ class FusedResNet:
                 s_in, o1, m1, i1 = self._nf(c0, None, P, pre + ".n1", eps, pre + ".n1.f", nv)
             else:
                 s_in, o1, m1, i1 = self._cnf(pend, P, pre + ".n1", eps, pre + ".n1.f", nv)
-            sc = fo.conv_fwd(o1, P[pre + ".shortcut.weight"], stride, 0) if blk["shortcut"] else s_in
+            # residual of this block's output: the block input, or (transition blocks) its 1x1 shortcut convolution --
+            # handed to the NEXT norm's convolution as an operand pair so that it is folded into the same launch
+            sc = ("conv", o1, P[pre + ".shortcut.weight"], stride) if blk["shortcut"] else s_in
             c1, o2, m2, i2 = self._cnf((o1, P[pre + ".conv1.weight"], stride, None), P, pre + ".n2", eps, pre + ".n2.f",
                                        nv)
             saved.append((blk, s_in, o1, m1, i1, c1, o2, m2, i2))

@@ -241,11 +241,12 @@ def conv_fwd(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> torch.T
 
 
 CONV_STATS_FUSE = os.environ.get("HFL_CONV_STATS", "1") != "0"
+CONV_SC_FOLD = os.environ.get("HFL_CONV_SC_FOLD", "1") != "0"
 
 
 def conv_bn_act_fwd(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int, res: Optional[torch.Tensor],
                     gamma: torch.Tensor, beta: torch.Tensor, eps: float, ws: Optional[torch.Tensor], nvalid=None,
-                    relu: bool = True):
+                    relu: bool = True, shortcut=None):
     """``s = conv(x, w) (+ res)``; ``y = relu(bn(s))`` with batch statistics.  Returns ``(s, y, mean, invstd)``.
 
     When the convolution runs on the tcgen05 kernel, its epilogue adds the residual, writes ``s`` and accumulates the
@@ -253,8 +254,26 @@ def conv_bn_act_fwd(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int, res
     ``[2C+1]`` scratch); the norm is then a single apply pass (``bn_apply_sums``) -- no statistics kernel, no separate
     residual add (reference block: ``src/models/resnet.py:44-50``).  Otherwise: library convolution + ``bn_act_fwd``.
     Padding samples (``nvalid``): the epilogue writes zeros there and keeps them out of the sums, whatever ``x`` and
-    ``res`` hold in those rows."""
-    if CONV_STATS_FUSE and ws is not None and _tc_conv_ok(x, w, stride, pad) and w.shape[0] >= 8:
+    ``res`` hold in those rows.
+
+    ``shortcut = (x_in, w_sc, stride_sc)`` instead of ``res``: the residual is the 1x1 shortcut convolution of the block
+    input; on the tcgen05 path it is FOLDED into the same launch (extra k-blocks of the same accumulator tile), so a
+    transition block's ``conv2(..) + shortcut(x)`` is one kernel and the shortcut output never exists in memory."""
+    fused = CONV_STATS_FUSE and ws is not None and _tc_conv_ok(x, w, stride, pad) and w.shape[0] >= 8
+    if shortcut is not None:
+        xs, wsc, ssc = shortcut
+        fold = (fused and CONV_SC_FOLD and xs.shape[1] % 8 == 0 and ssc in (1, 2)
+                and xs.is_contiguous(memory_format=torch.channels_last) and wsc.permute(0, 2, 3, 1).is_contiguous()
+                and xs.shape[2] == ssc * ((x.shape[2] + 2 * pad - w.shape[2]) // stride + 1))
+        if fold:
+            C_ = cu.C()
+            K = w.shape[0]
+            s = C_.conv_fprop_tc(x, w, None, ws, stride, nvalid, xs, wsc, int(ssc))
+            y, mean, invstd, _ = C_.bn_apply_sums(s, gamma, beta, float(eps), int(K), bool(relu), ws, nvalid,
+                                                  int(x.shape[0]))
+            return s, y, mean, invstd
+        res = conv_fwd(xs, wsc, ssc, 0)
+    if fused:
         C_ = cu.C()
         K = w.shape[0]
         s = C_.conv_fprop_tc(x, w, res, ws, stride, nvalid)

@@ -432,6 +432,46 @@ def test_conv_bn_act_fused_matches_unfused(N, C, H, K, stride, with_res, nvalid,
     assert float(y[nvi:].abs().max()) == 0.0 if nvi < N else True
 
 
+@pytest.mark.parametrize("N,C2,H2,K,s2,nvalid", [(10, 64, 32, 128, 2, None), (10, 128, 16, 256, 2, 6), (10, 16, 32, 32, 2, None),
+                                                (10, 256, 8, 512, 2, None), (10, 32, 16, 64, 1, None)])
+def test_conv_shortcut_fold_matches_unfused(N, C2, H2, K, s2, nvalid, monkeypatch, ksplit_cap):
+    """Transition block: conv2(o2) + shortcut_1x1(o1) + BatchNorm statistics in ONE tcgen05 launch (the shortcut's k-blocks
+    are accumulated into the same TMEM tile) == the two convolutions computed separately in fp32."""
+    cu = _cu()
+    from hfl_b200.ops import fused as fo
+    dev = torch.device("cuda")
+    torch.manual_seed(N + C2 + K)
+    monkeypatch.setattr(fo, "CONV_TC_MODE", "on")
+    OH = H2 // s2
+    o2 = torch.randn(N, K, OH, OH, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    o1 = torch.randn(N, C2, H2, H2, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(K, K, 3, 3, device=dev) / (K * 9) ** 0.5).bfloat16().contiguous(memory_format=torch.channels_last)
+    wsc = (torch.randn(K, C2, 1, 1, device=dev) / C2 ** 0.5).bfloat16()
+    wsc = wsc.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    gamma = (1 + 0.1 * torch.randn(K, device=dev)).bfloat16()
+    beta = (0.1 * torch.randn(K, device=dev)).bfloat16()
+    ws = torch.zeros(2 * K + 1, device=dev)
+    nv = None if nvalid is None else torch.tensor([nvalid], dtype=torch.int32, device=dev)
+    s, y, m, i = fo.conv_bn_act_fwd(o2, w, 1, 1, None, gamma, beta, 1e-5, ws, nv, shortcut=(o1, wsc, s2))
+    torch.cuda.synchronize()
+    assert float(ws.abs().max()) == 0.0
+    nvi = N if nvalid is None else nvalid
+    sr = torch.nn.functional.conv2d(o2.float(), w.float(), None, 1, 1) + torch.nn.functional.conv2d(o1.float(), wsc.float(), None, s2, 0)
+    sr[nvi:] = 0
+    mean = sr[:nvi].mean(dim=(0, 2, 3))
+    var = sr[:nvi].var(dim=(0, 2, 3), unbiased=False)
+    yr = torch.relu((sr - mean.view(1, -1, 1, 1)) * torch.rsqrt(var + 1e-5).view(1, -1, 1, 1) * gamma.float().view(1, -1, 1, 1)
+                    + beta.float().view(1, -1, 1, 1))
+    yr[nvi:] = 0
+    assert float((s.float() - sr).abs().max()) < 4e-2 * max(1.0, float(sr.abs().max()))
+    assert torch.allclose(m.view(-1), mean, atol=2e-2, rtol=2e-2)
+    assert float((y.float() - yr).abs().max()) < 6e-2 * max(1.0, float(yr.abs().max()))
+    # and the unfolded path (HFL_CONV_SC_FOLD=0) gives the same block output
+    monkeypatch.setattr(fo, "CONV_SC_FOLD", False)
+    s2_, y2, _, _ = fo.conv_bn_act_fwd(o2, w, 1, 1, None, gamma, beta, 1e-5, ws, nv, shortcut=(o1, wsc, s2))
+    assert float((s2_.float() - s.float()).abs().max()) < 4e-2 * max(1.0, float(sr.abs().max()))
+
+
 def test_tc_linear_forward_backward():
     _cu()
     from hfl_b200.ops.linear import tc_linear
