@@ -3,6 +3,8 @@
 set -u
 mkdir -p gpurun_out/r2l
 O=gpurun_out/r2l
+python -m pytest tests/test_fused_transformer.py -m gpu -q -k "attention" 2>&1 | tail -4 | tee $O/t_attn.log
+python -m pytest tests -m gpu -q -x 2>&1 | tail -6 | tee $O/t_all.log
 python __graft_entry__.py --smoke 2>&1 | tail -4 | tee $O/smoke.log
 run() {
   name=$1; shift

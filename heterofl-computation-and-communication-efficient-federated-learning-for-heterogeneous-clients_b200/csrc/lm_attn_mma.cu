@@ -233,6 +233,7 @@ lm_attn_bwd_mma_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ q, 
   __shared__ __align__(16) bf16 sP[AM_S][AM_PS];          // P  [query][key]
   __shared__ __align__(16) bf16 sS[AM_S][AM_PS];          // dS [query][key]
   __shared__ float sDelta[AM_S];
+  __shared__ float sRS[AM_S];                             // fp32 row sums of dS (phase A) -> k-bias gradient
   __shared__ float sBias[3][AM_DH];
   const int n = blockIdx.x / H, h = blockIdx.x % H, E = H * dh;
   const size_t base = (size_t)n * S * E + (size_t)h * dh;
@@ -281,16 +282,30 @@ lm_attn_bwd_mma_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ q, 
     for (int hf = 0; hf < 2; ++hf) {
       const int i = r0 + g + 8 * hf;
       const float dl = sDelta[i];
+      float rsum = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const int j = 8 * nt + 2 * tq;
         const uint32_t pu = am_ld32(&sP[i][j]);
         const float s0 = am_lo(pu) * (dp[nt][2 * hf] - dl) * scale;
         const float s1 = am_hi(pu) * (dp[nt][2 * hf + 1] - dl) * scale;
+        rsum += s0 + s1;
         const uint32_t u = am_pack2(s0, s1);
         ds[nt][hf] = u;
         *reinterpret_cast<uint32_t*>(&sS[i][j]) = u;
       }
+      rsum += __shfl_xor_sync(0xffffffffu, rsum, 1);
+      rsum += __shfl_xor_sync(0xffffffffu, rsum, 2);
+      if (tq == 0) sRS[i] = rsum;
+    }
+    __syncwarp();
+    {
+      // k-bias gradient = sum_j dK[j][d] = sum_i Q[i][d] * (sum_j dS[i][j]).  A softmax gradient row sums to zero, which
+      // the fp32 row sums keep to round-off; summing the dK tile (built from bf16-rounded dS) would not.
+      float acc = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) acc += sRS[r0 + rr] * __bfloat162float(sQ[r0 + rr][lane]);
+      atomicAdd(&sBias[1][lane], acc);
     }
     float dqc[4][4];
 #pragma unroll
@@ -341,8 +356,7 @@ lm_attn_bwd_mma_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ q, 
     }
     am_store_rows(dk, base, E, dh, S, j0, g, tq, dkc, 1.f);
     am_store_rows(dv, base, E, dh, S, j0, g, tq, dvc, scale_dv ? alpha_v : 1.f);
-    am_bias_accum(sBias[1], dkc, g, tq);
-    am_bias_accum(sBias[2], dvc, g, tq);
+    am_bias_accum(sBias[2], dvc, g, tq);            // (the k-bias gradient comes from phase A's fp32 row sums)
   }
   __syncthreads();
   if (tid < dh) {
