@@ -447,7 +447,9 @@ class Engine:
     def _async_eval_ok(self) -> bool:
         want = self.opt.async_eval
         if want is None:
-            want = self.info.world >= 4
+            # vision models only: the masked-LM evaluation on a helper thread next to the following round's training timed
+            # out in the peer barrier at 4 ranks (gpurun_out/r2m) and gains little there (its test pass is sharded)
+            want = self.info.world >= 4 and not self.is_lm
         return bool(want and self.is_cuda and self._agg_backend in ("local", "p2p"))
 
     def _launch_eval(self, epoch: int) -> None:
