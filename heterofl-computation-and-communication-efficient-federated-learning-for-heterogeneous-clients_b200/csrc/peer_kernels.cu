@@ -28,7 +28,10 @@ bool pdl_enabled() {
 __global__ void peer_barrier_kernel(const unsigned long long* __restrict__ flag_ptrs, int rank, int world,
                                     unsigned epoch, int* __restrict__ err) {
   const int p = threadIdx.x;
-  pdl_sync();             // "this rank's earlier kernels have completed" is what the flag publishes
+  // "this rank's earlier kernels have completed" is what the flag publishes.  No early launch_dependents here: the kernel may
+  // spin for as long as the slowest peer trains, and a dependent launched early (the aggregation grid: ~2 800 CTAs parked in
+  // griddepcontrol.wait) would occupy every SM slot meanwhile -- starving the evaluation stream of the asynchronous mode.
+  pdl_wait();
   if (p < world) {
     unsigned* remote = reinterpret_cast<unsigned*>(flag_ptrs[p]) + rank;
     __threadfence_system();

@@ -467,7 +467,9 @@ class Evaluator:
         for b0 in range(0, len(full), WB):
             grp = full[b0:b0 + WB]
             tok = torch.cat([rows_dev[:, s0:s0 + bptt] for s0, _ in grp], dim=0).contiguous()      # [len*r, bptt]
-            if self.fused_lm is not None and sync:     # (asynchronous evaluation on the helper thread: functional model)
+            # (asynchronous evaluation on the helper thread: functional model, see fed/engine.py:_async_eval_ok;
+            # HFL_LM_EVAL_FUSED_ASYNC=1 is the diagnosis switch)
+            if self.fused_lm is not None and (sync or os.environ.get("HFL_LM_EVAL_FUSED_ASYNC") == "1"):
                 # encoder on the fused kernels (fresh [MASK] draw per forward: device-side counter), then ONE vocabulary GEMM
                 self._lm_step.add_(1)
                 d = self.fused_lm.forward_hidden_eval(P, tok, self._lm_seed, self._lm_step)
