@@ -767,7 +767,7 @@ extern "C" int hfl_conv_wgrad_tc_supported(int N, int H, int W, int C, int Kout,
   if (rows > OH && (rows % OH) != 0) return 5;
   if (rows < OH && (OH % rows) != 0) return 6;
   const int bh = rows < OH ? rows : OH, bn = rows / bh;
-  if (N % bn != 0) return 7;        // partial image groups would need masking of dY rows (TMA OOB handles X only)
+  (void)bn;                         // a partial last image group is fine: both TMA boxes zero-fill the images beyond N
   return 0;
 }
 
@@ -785,7 +785,7 @@ extern "C" int hfl_conv_wgrad_tc(const void* dY, const void* X, float* dW, int N
   g.bh = rows < g.OH ? rows : g.OH;
   g.bn = rows / g.bh;
   g.bricks_h = g.OH / g.bh;
-  g.bricks = (N / g.bn) * g.bricks_h;
+  g.bricks = ((N + g.bn - 1) / g.bn) * g.bricks_h;
   const int base_ctas = ((Kout + 127) / 128) * ((C + 63) / 64) * R * S;
   int splits = 1;
   while (base_ctas * splits < 96 && splits * 8 <= g.bricks) splits *= 2;   // fill the machine, keep >= 8 bricks per CTA

@@ -559,7 +559,9 @@ def test_tcgen05_conv_dgrad_stride2_matches_autograd(N, C, H, K, R, ksplit_cap):
                                                (10, 64, 32, 128, 1, 2), (10, 256, 8, 256, 3, 1), (12, 512, 4, 512, 3, 1),
                                                (8, 256, 8, 512, 3, 2), (10, 32, 32, 32, 3, 1), (10, 16, 32, 16, 3, 1),
                                                (10, 8, 32, 8, 3, 1), (10, 32, 32, 64, 3, 2), (10, 16, 16, 32, 1, 2),
-                                               (10, 64, 16, 32, 3, 1), (10, 8, 32, 16, 3, 2)])
+                                               (10, 64, 16, 32, 3, 1), (10, 8, 32, 16, 3, 2),
+                                               # partial last image group (4x4 / 2x2 maps at batch 10: 4 / 16 images per brick)
+                                               (10, 512, 4, 512, 3, 1), (10, 256, 8, 512, 3, 2), (10, 128, 4, 128, 1, 2), (7, 64, 4, 64, 3, 1)])
 def test_tcgen05_conv_wgrad_matches_autograd(N, C, H, K, R, stride):
     """Weight gradient with both operands MN-major (pixels = reduction), split-K with fp32 atomics."""
     cu = _cu()
