@@ -135,3 +135,21 @@ def test_checkpoint_is_reference_compatible(ref, tmp_path):
     e2 = Engine(_cfg(rounds=6, resume_mode=1), options=EngineOptions(out_dir=out, quiet=True))
     e2.setup()
     assert e2.epoch == 5 and e2.logger.history["train/Local-Loss"] == [1.5]
+
+
+def test_async_eval_policy_and_late_test_logging(tmp_path):
+    """Asynchronous evaluation is a CUDA-only mode (automatic from 4 ranks up, vision models): on CPU the engine never
+    selects it, and `_log_test` -- the path fit() uses for the one-round-late metrics of that mode -- feeds the logger
+    exactly like the in-round evaluation."""
+    assert EngineOptions().async_eval is None
+    eng = Engine(_cfg(rounds=1), options=EngineOptions(out_dir=str(tmp_path / "a"), quiet=True, save=False,
+                                                      async_eval=True))
+    eng.setup()
+    assert not eng._async_eval_ok()                       # no CUDA device: forced on or not, the mode stays off
+    res = eng.run_round(1)
+    assert "test" in res and "prev_eval" not in res and "eval_pending" not in res
+    eng.logger.safe(True)
+    eng._log_test({"epoch": 1, "test": res["test"], "_test_n": res.get("_test_n", {})})
+    eng.logger.safe(False)
+    key = "test/Global-Accuracy"
+    assert key in eng.logger.history and eng.logger.history[key][-1] == pytest.approx(res["test"]["Global-Accuracy"])
