@@ -40,7 +40,6 @@ namespace hfl {
 
 constexpr int CV_BLOCK_M = 128;
 constexpr int CV_BLOCK_K = 64;
-constexpr int CV_STAGES = 4;
 constexpr int CV_THREADS = 256;
 
 struct ConvGeom {
@@ -97,7 +96,14 @@ struct ConvSmem {
   static constexpr int A_BYTES = CV_BLOCK_M * CV_BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * CV_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = CV_STAGES * STAGE_BYTES + 1024 + 256;
+  // ring depth: the batch-10 training tiles have 9-18 k-blocks, so a 4-stage ring paid 2-3 serial TMA round trips (~1 us
+  // each) per tile; 6-9 stages (~190 KB) put (almost) the whole reduction in flight at once.  HFL_CONV_STAGES4 restores 4.
+#ifdef HFL_CONV_STAGES4
+  static constexpr int STAGES = 4;
+#else
+  static constexpr int STAGES = BLOCK_N >= 128 ? 6 : (BLOCK_N >= 64 ? 8 : 9);
+#endif
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
 // DGRAD = true turns the same kernel into the stride-1 data-gradient:
@@ -117,6 +123,7 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
   extern __shared__ uint8_t smem_raw[];
   using S = ConvSmem<BLOCK_N>;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int CV_STAGES = S::STAGES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + CV_STAGES * S::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + CV_STAGES;
   uint64_t* tmem_full_bar = empty_bar + CV_STAGES;
