@@ -96,12 +96,14 @@ struct ConvSmem {
   static constexpr int A_BYTES = CV_BLOCK_M * CV_BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * CV_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // ring depth: the batch-10 training tiles have 9-18 k-blocks, so a 4-stage ring paid 2-3 serial TMA round trips (~1 us
-  // each) per tile; 6-9 stages (~190 KB) put (almost) the whole reduction in flight at once.  HFL_CONV_STAGES4 restores 4.
-#ifdef HFL_CONV_STAGES4
-  static constexpr int STAGES = 4;
-#else
+  // ring depth: 4 stages.  A 6-9 stage ring (-DHFL_CONV_DEEP_RING: the whole 9-18 k-block reduction of a batch-10 tile in
+  // flight at once, ~190 KB) was measured on the same box (gpurun_out/r2s): isolated steps unchanged (921 vs 924 us level a,
+  // 495 vs 498 us level c -- the TMA round trips are not what bounds these tiles), 4 concurrent slots 7 % slower (one
+  // CTA per SM instead of two), round 476 vs 457 ms.
+#ifdef HFL_CONV_DEEP_RING
   static constexpr int STAGES = BLOCK_N >= 128 ? 6 : (BLOCK_N >= 64 ? 8 : 9);
+#else
+  static constexpr int STAGES = 4;
 #endif
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
 };
