@@ -55,6 +55,9 @@ def build_parser(script: str) -> argparse.ArgumentParser:
     ap.add_argument("--nvtx", default=0, type=int, help="emit an NVTX range per round phase")
     ap.add_argument("--fault_drop", default=0.0, type=float,
                     help="fault injection: probability that an active client's update is lost each round")
+    ap.add_argument("--async_eval", default="auto", type=str,
+                    help="overlap a round's sBN + test passes with the next round's training: auto (vision models from 4 "
+                         "ranks up) | 1 | 0; test metrics are then logged one round late")
     return ap
 
 
@@ -82,7 +85,9 @@ def _options(args: Dict):
     return EngineOptions(compute_dtype=args["compute_dtype"], max_concurrent=args["max_concurrent"],
                          agg_backend=args["agg_backend"], out_dir=args["out_dir"], tensorboard=True,
                          quiet=bool(args["quiet"]), nvtx=bool(args.get("nvtx", 0)),
-                         fault_drop=float(args.get("fault_drop", 0.0)))
+                         fault_drop=float(args.get("fault_drop", 0.0)),
+                         async_eval={"1": True, "true": True, "0": False, "false": False}.get(
+                             str(args.get("async_eval", "auto")).lower(), None))
 
 
 def run(script: str, argv: Optional[List[str]] = None) -> None:
